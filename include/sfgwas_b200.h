@@ -1,0 +1,129 @@
+/*
+ * sfgwas_b200.h -- C ABI of libsfgwas_b200.so: the B200 (sm_100a) implementation of the genotype x CKKS-ciphertext
+ * MatMult hot path of hhcho/sfgwas.  Plain pointers and sizes only; no Go, torch or C++ types cross this boundary.
+ *
+ * The reference has no FFI for this path: the boundary is the set of exported Go functions of package `gwas`
+ * (SURVEY.md 8b).  Each entry point below names the reference function whose body it replaces; the cgo shim that
+ * binds them (go/gwas/matmult_b200.go) keeps the Go signatures verbatim.  See INTEGRATION.md.
+ *
+ * Conventions
+ *  - Every function returns 0 on success, non-zero on failure; sfg_last_error(ctx) gives the message.  The Go shim
+ *    panics on non-zero, matching the reference's panic/log.Fatal behaviour (gwas/matmult.go:360-362).
+ *  - Polynomials are uint64 residues, limb-major: a ciphertext of L limbs is [2][L][N], a plaintext [L][N], exactly the
+ *    order of Lattigo's Poly.Coeffs[l][j] (gwas/matmult.go:372-375,394-395).  "flat" entry points take one contiguous
+ *    buffer; the "_ptrs" variants take one pointer per limb (cgo: one Go slice per limb).
+ *  - Host buffers are never retained after a call returns.  Handles are owned by the library and must be destroyed.
+ *  - The library is re-entrant across contexts; calls on ONE context are serialised by the caller or by distinct
+ *    sfg_ctx handles (one per goroutine, like the reference's per-goroutine ckks.Evaluator, gwas/matmult.go:1110).
+ *  - There is no CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef SFGWAS_B200_H
+#define SFGWAS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sfg_ctx sfg_ctx;       /* ckks.Parameters + ring tables + Galois keys on one GPU (crypto.CryptoParams subset) */
+typedef struct sfg_geno sfg_geno;     /* device-resident int8 genotype matrix (what a GenoFileStream yields, App. D.1) */
+typedef struct sfg_cache sfg_cache;   /* device-resident diagonal cache (replaces the DiagCacheStream files, App. D.2) */
+
+/* ---- context: replaces ring.NewRing / ckks.NewEvaluator setup done inside the path (gwas/matmult.go:328,345,403,1110) ---- */
+/* qi/pi: params.Qi()/Pi(); scale: params.Scale(); psi: optional nQ+nP primitive 2N-th roots (NULL = Lattigo's rule). */
+int sfg_ctx_create(int device, int logN, const uint64_t *qi, int nQ, const uint64_t *pi, int nP, double scale,
+                   const uint64_t *psi, sfg_ctx **out);
+void sfg_ctx_destroy(sfg_ctx *ctx);
+const char *sfg_last_error(const sfg_ctx *ctx);
+int sfg_version(void);
+/* HBM budget for cached diagonals in bytes (0 = 70% of free memory at preprocess time). */
+int sfg_ctx_set_cache_budget(sfg_ctx *ctx, size_t bytes);
+/* counters: kernels launched so far by this context; encoder statistics {rechecked coefficients, unresolved ties}. */
+unsigned long long sfg_ctx_launch_count(const sfg_ctx *ctx);
+int sfg_ctx_encoder_stats(sfg_ctx *ctx, unsigned long long out[2]);
+int sfg_ctx_psi(const sfg_ctx *ctx, uint64_t *psi_out /* nQ+nP */);
+
+/* Galois (rotation) keys: cryptoParams.RotKs.Keys[galEl].Value[i][0|1].Coeffs[*] (crypto/crypto.go:232-275, gwas/matmult.go:1110).
+ * key: [beta][2][nQ+nP][N] contiguous, NTT + Montgomery form as Lattigo stores it.  rot_left: the left-rotation amount k
+ * with galEl = 5^k mod 2N. */
+int sfg_ctx_set_rotation_key(sfg_ctx *ctx, int rot_left, const uint64_t *key);
+int sfg_ctx_set_rotation_key_ptrs(sfg_ctx *ctx, int rot_left, const uint64_t *const *limbs /* beta*2*(nQ+nP) pointers */);
+int sfg_ctx_has_rotation_key(const sfg_ctx *ctx, int rot_left);
+
+/* ---- lattice primitives (each mirrors one reference / Lattigo function; used by the parity tests and the NTT sweep) ---- */
+/* ring.NTT / ring.InvNTT on npoly polynomials, polynomial p uses modulus index limb_idx[p % nsel] (Q then P). In place. */
+int sfg_ntt(sfg_ctx *ctx, uint64_t *polys, int npoly, const int *limb_idx, int nsel, int inverse);
+/* MulCoeffsAndAdd128 (gwas/matmult.go:247-289): acc is n x {hi, lo} like the reference's uint128 struct */
+int sfg_mul_coeffs_and_add128(sfg_ctx *ctx, const uint64_t *a, const uint64_t *b, uint64_t *acc_hi_lo, size_t n);
+/* ReduceAndAddUint128 (gwas/matmult.go:291-324) for modulus index `limb` */
+int sfg_reduce_and_add_uint128(sfg_ctx *ctx, const uint64_t *acc_hi_lo, uint64_t *out, int limb, size_t n);
+/* MFormLvl (gwas/matmult.go:411-431): p is [level+1][N], in place */
+int sfg_mform_lvl(sfg_ctx *ctx, int level, uint64_t *p);
+/* crypto.RotateRightWithEvaluator (crypto/basics.go:201-210) on nct ciphertexts [nct][2][level+1][N] */
+int sfg_rotate_right(sfg_ctx *ctx, int level, const uint64_t *cts, int nct, int nrot, uint64_t *out);
+
+/* ---- genotype matrix: what GenoFileStream.NextRow (gwas/filestream.go:414-426) delivers, kept in HBM ---- */
+int sfg_geno_create(sfg_ctx *ctx, size_t nrows, size_t ncols, sfg_geno **out);
+/* append `nrows_chunk` consecutive rows (row-major int8, ncols each; filtered rows/cols already removed by the Go stream) */
+int sfg_geno_push_rows(sfg_geno *g, const int8_t *rows, size_t nrows_chunk);
+void sfg_geno_destroy(sfg_geno *g);
+/* EncodeDiagWithEncoder + ToMontgomeryForm for one (block row, shift) (gwas/matmult.go:711-731,401-409):
+ * out [m_ct][level+1][N] (Montgomery form iff mont != 0), present[m_ct] = 0 for nil plaintexts. nrot = right rotation. */
+int sfg_encode_diag(sfg_ctx *ctx, const sfg_geno *g, int block_row, int shift, int nrot, int level, int mont, uint64_t *out,
+                    uint8_t *present, int64_t *coeffs_out /* optional [m_ct][N], NULL to skip */);
+
+/* ---- the three stream entry points (gwas/matmult.go:914, 1043, 1238) ---- */
+/* MatMult4StreamPreprocess(cryptoParams, gfs, maxLevel, cacheFilePrefix): builds the diagonal cache in HBM (or, when it
+ * exceeds the budget, a handle that regenerates diagonals on the fly; results are identical). */
+int sfg_matmult4_stream_preprocess(sfg_ctx *ctx, const sfg_geno *g, int max_level, sfg_cache **out);
+void sfg_cache_destroy(sfg_cache *cache);
+/* number of non-nil diagonal polynomials, bytes resident, and whether they are materialised */
+int sfg_cache_info(const sfg_cache *cache, size_t *num_polys, size_t *bytes, int *materialised, int *m_ct, int *num_block_rows);
+/* copy one cached plaintext to the host: out [max_level][N] (the used limbs, NTT + Montgomery form); *present = 0 if nil */
+int sfg_cache_get_diag(sfg_ctx *ctx, const sfg_cache *cache, int block_row, int shift, int block_col, uint64_t *out, int *present);
+
+/* MatMult4StreamCompute(cryptoParams, A, maxLevel, cacheFilePrefix) (gwas/matmult.go:1043-1236).
+ * A: [s][num_block_rows][2][level_a+1][N]; out: [s][m_ct][2][max_level][N] = the deterministic sum
+ * S[i][bj] = sum_g RotL_{g d}(reduce(acc[i][g])[bj]) at level max_level-1; the Go shim adds it into
+ * crypto.CZeroMat with eva.Add to keep the reference's randomised-zero semantics. */
+int sfg_matmult4_stream_compute(sfg_ctx *ctx, const uint64_t *A, int s, int num_block_rows, int level_a, int max_level,
+                                const sfg_cache *cache, uint64_t *out);
+/* same, A and out given as one pointer per limb: A_limbs[((i*nbr+bi)*2+c)*(level_a+1)+l], out_limbs[((i*m_ct+bj)*2+c)*max_level+l] */
+int sfg_matmult4_stream_compute_ptrs(sfg_ctx *ctx, const uint64_t *const *A_limbs, int s, int num_block_rows, int level_a,
+                                     int max_level, const sfg_cache *cache, uint64_t *const *out_limbs);
+
+/* MatMult4Stream(cryptoParams, A, gfs, maxLevel, computeSquaredSum, square, nproc) (gwas/matmult.go:1238-1505).
+ * sum / sq_sum: ncols float64 each (may be NULL when compute_squared_sum == 0). The genotype handle is not modified. */
+int sfg_matmult4_stream(sfg_ctx *ctx, const uint64_t *A, int s, int level_a, const sfg_geno *g, int max_level,
+                        int compute_squared_sum, int square, uint64_t *out, double *sum, double *sq_sum);
+
+/* ---- multi-GPU building blocks: block-row sharding with a modular-add reduce between K2 and K6 ---- */
+/* size in uint64 of the per-call accumulator image cv[d][m_ct][s][2][max_level][N] */
+size_t sfg_cv_elems(const sfg_ctx *ctx, const sfg_cache *cache, int s, int max_level);
+/* partial products over block rows [bi_lo, bi_hi): canonical residues written to the DEVICE buffer d_cv */
+int sfg_matmult4_partial(sfg_ctx *ctx, const uint64_t *A, int s, int num_block_rows, int level_a, int max_level,
+                         const sfg_cache *cache, int bi_lo, int bi_hi, uint64_t *d_cv);
+/* after an integer SUM all-reduce / reduce-scatter of up to 2^8 partial images: x mod q per limb, on device */
+int sfg_cv_mod_reduce(sfg_ctx *ctx, const sfg_cache *cache, int s, int max_level, uint64_t *d_cv, size_t first_elem, size_t num_elems);
+/* giant-step rotations and sum for giant indices [g_lo, g_hi): out [s][m_ct][2][max_level][N] on the HOST (partial over g) */
+int sfg_matmult4_finish(sfg_ctx *ctx, const sfg_cache *cache, int s, int max_level, const uint64_t *d_cv, int g_lo, int g_hi,
+                        uint64_t *out);
+/* out = (a + b) mod q limb-wise on host buffers of ncts ciphertexts [2][nl][N] (combining per-rank partial sums) */
+int sfg_ct_add(sfg_ctx *ctx, const uint64_t *a, const uint64_t *b, int ncts, int nl, uint64_t *out);
+
+/* synchronise the context's stream (timing helper) */
+int sfg_ctx_sync(sfg_ctx *ctx);
+/* device-resident variant used by bench.py to time the kernels with inputs already in HBM:
+ * d_A [s][nbr][2][level_a+1][N] and d_out [s][m_ct][2][max_level][N] are DEVICE pointers. */
+int sfg_matmult4_stream_compute_dev(sfg_ctx *ctx, const uint64_t *d_A, int s, int num_block_rows, int level_a, int max_level,
+                                    const sfg_cache *cache, uint64_t *d_out);
+/* last call's phase timings in milliseconds (CUDA events on the context stream): {baby rotations, MAC, giant rotations, total} */
+int sfg_ctx_last_timings(const sfg_ctx *ctx, float out_ms[4]);
+void *sfg_ctx_stream(const sfg_ctx *ctx); /* cudaStream_t of the context */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

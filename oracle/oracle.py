@@ -160,7 +160,7 @@ def gen_primes(logN: int, bits: int, count: int, avoid=()) -> list[int]:
     return out
 
 
-def test_params(logN: int, shape: str = "pn13") -> dict:
+def small_params(logN: int, shape: str = "pn13") -> dict:
     """Small rings mirroring the limb-width structure of PN13QP218 (33+5x30 | 36) or PN14QP438 (46+9x34 | 43,43)."""
     if shape == "pn13":
         q0 = gen_primes(logN, 33, 1)

@@ -1,0 +1,430 @@
+// capi.cu -- extern "C" boundary of libsfgwas_b200.so (include/sfgwas_b200.h).
+#include <cmath>
+#include <cstring>
+
+#include "../../include/sfgwas_b200.h"
+#include "matmult.h"
+
+using namespace sfg;
+
+struct sfg_ctx {
+    Ctx c;
+};
+struct sfg_geno {
+    Geno *g;
+};
+struct sfg_cache {
+    Cache *ca;
+};
+
+static std::string g_create_err;
+
+extern "C" {
+
+int sfg_version(void) { return 1; }
+
+int sfg_ctx_create(int device, int logN, const uint64_t *qi, int nQ, const uint64_t *pi, int nP, double scale, const uint64_t *psi,
+                   sfg_ctx **out) {
+    *out = nullptr;
+    sfg_ctx *h = new sfg_ctx();
+    Ctx *c = &h->c;
+    auto fail = [&](const std::string &m) {
+        g_create_err = m;
+        delete h;
+        return -1;
+    };
+    if (logN < 6 || logN > 17) return fail("logN out of range [6, 17]");
+    if (nQ < 1 || nP < 1 || nQ + nP > kMaxLimbs) return fail("unsupported number of moduli");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) return fail(std::string("no CUDA device: ") + cudaGetErrorString(e) + " (libsfgwas_b200 has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail("device index out of range");
+    c->device = device;
+    c->logN = logN;
+    c->N = 1 << logN;
+    c->slots = c->N >> 1;
+    c->d = (int)std::ceil(std::sqrt((double)c->slots));  // gwas/matmult.go:918,1047
+    c->nQ = nQ;
+    c->nP = nP;
+    c->nQP = nQ + nP;
+    c->beta = (nQ + nP - 1) / nP;
+    c->scale = scale;
+    c->mod.assign(qi, qi + nQ);
+    c->mod.insert(c->mod.end(), pi, pi + nP);
+    if (cudaSetDevice(device) != cudaSuccess) return fail("cudaSetDevice failed");
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return fail("cudaStreamCreate failed");
+    if (ctx_build_tables(c, psi)) {
+        std::string m = c->err;
+        cudaStreamDestroy(c->stream);
+        c->stream = nullptr;
+        return fail(m);
+    }
+    *out = h;
+    return 0;
+}
+
+void sfg_ctx_destroy(sfg_ctx *h) {
+    if (!h) return;
+    Ctx *c = &h->c;
+    cudaSetDevice(c->device);
+    cudaFree(c->lc);
+    cudaFree(c->tw);
+    cudaFree(c->roots);
+    cudaFree(c->ddcos);
+    cudaFree(c->rot5);
+    cudaFree(c->enc_stats);
+    for (auto &kv : c->bc_ks) cudaFree(kv.second);
+    for (auto &kv : c->bc_md) cudaFree(kv.second);
+    for (auto &kv : c->pinv) cudaFree(kv.second);
+    for (auto &kv : c->keys) {
+        cudaFree(kv.second.key);
+        cudaFree(kv.second.perm);
+    }
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete h;
+}
+
+const char *sfg_last_error(const sfg_ctx *h) { return h ? h->c.err.c_str() : g_create_err.c_str(); }
+
+int sfg_ctx_set_cache_budget(sfg_ctx *h, size_t bytes) {
+    h->c.cache_budget = bytes;
+    return 0;
+}
+unsigned long long sfg_ctx_launch_count(const sfg_ctx *h) { return h->c.launches; }
+int sfg_ctx_encoder_stats(sfg_ctx *h, unsigned long long out[2]) {
+    Ctx *c = &h->c;
+    SFG_CUDA(c, cudaSetDevice(c->device));
+    SFG_CUDA(c, cudaMemcpy(out, c->enc_stats, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    return 0;
+}
+int sfg_ctx_psi(const sfg_ctx *h, uint64_t *psi_out) {
+    for (int i = 0; i < h->c.nQP; i++) psi_out[i] = h->c.psi[i];
+    return 0;
+}
+int sfg_ctx_sync(sfg_ctx *h) {
+    Ctx *c = &h->c;
+    SFG_CUDA(c, cudaSetDevice(c->device));
+    SFG_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+void *sfg_ctx_stream(const sfg_ctx *h) { return (void *)h->c.stream; }
+int sfg_ctx_last_timings(const sfg_ctx *, float out_ms[4]) {
+    for (int i = 0; i < 4; i++) out_ms[i] = g_last_ms[i];
+    return 0;
+}
+
+static int set_key_dev(Ctx *c, int rot_left, uint64_t *dkey) {
+    const uint64_t galEl = h_galois_element(c->logN, rot_left);
+    std::vector<uint32_t> idx(c->N);
+    h_permute_ntt_index(c->logN, galEl, idx.data());
+    uint32_t *dperm = nullptr;
+    SFG_CUDA(c, cudaMalloc(&dperm, sizeof(uint32_t) * c->N));
+    SFG_CUDA(c, cudaMemcpy(dperm, idx.data(), sizeof(uint32_t) * c->N, cudaMemcpyHostToDevice));
+    std::lock_guard<std::mutex> g(c->mu);
+    auto it = c->keys.find(galEl);
+    if (it != c->keys.end()) {
+        cudaFree(it->second.key);
+        cudaFree(it->second.perm);
+    }
+    c->keys[galEl] = GaloisKey{galEl, dkey, dperm};
+    return 0;
+}
+
+int sfg_ctx_set_rotation_key(sfg_ctx *h, int rot_left, const uint64_t *key) {
+    Ctx *c = &h->c;
+    SFG_CUDA(c, cudaSetDevice(c->device));
+    const size_t n = (size_t)c->beta * 2 * c->nQP * c->N;
+    uint64_t *d = nullptr;
+    SFG_CUDA(c, cudaMalloc(&d, n * 8));
+    SFG_CUDA(c, cudaMemcpy(d, key, n * 8, cudaMemcpyHostToDevice));
+    return set_key_dev(c, rot_left, d);
+}
+int sfg_ctx_set_rotation_key_ptrs(sfg_ctx *h, int rot_left, const uint64_t *const *limbs) {
+    Ctx *c = &h->c;
+    SFG_CUDA(c, cudaSetDevice(c->device));
+    const size_t np = (size_t)c->beta * 2 * c->nQP;
+    uint64_t *d = nullptr;
+    SFG_CUDA(c, cudaMalloc(&d, np * c->N * 8));
+    for (size_t p = 0; p < np; p++) SFG_CUDA(c, cudaMemcpy(d + p * c->N, limbs[p], (size_t)c->N * 8, cudaMemcpyHostToDevice));
+    return set_key_dev(c, rot_left, d);
+}
+int sfg_ctx_has_rotation_key(const sfg_ctx *h, int rot_left) {
+    return h->c.keys.count(h_galois_element(h->c.logN, rot_left)) ? 1 : 0;
+}
+
+// ---- primitives ----
+int sfg_ntt(sfg_ctx *h, uint64_t *polys, int npoly, const int *limb_idx, int nsel, int inverse) {
+    Ctx *c = &h->c;
+    if (nsel < 1 || nsel > kMaxLimbs || npoly % nsel) SFG_FAIL(c, "sfg_ntt: npoly must be a multiple of nsel (<= %d)", kMaxLimbs);
+    SFG_CUDA(c, cudaSetDevice(c->device));
+    LimbSel sel;
+    sel.n = nsel;
+    for (int i = 0; i < nsel; i++) {
+        if (limb_idx[i] < 0 || limb_idx[i] >= c->nQP) SFG_FAIL(c, "sfg_ntt: modulus index %d out of range", limb_idx[i]);
+        sel.idx[i] = limb_idx[i];
+    }
+    Buf d;
+    const size_t bytes = (size_t)npoly * c->N * 8;
+    if (d.alloc(c, bytes)) return -1;
+    SFG_CUDA(c, cudaMemcpyAsync(d.p, polys, bytes, cudaMemcpyHostToDevice, c->stream));
+    if (launch_ntt(c, d.as<uint64_t>(), (size_t)nsel * c->N, d.as<uint64_t>(), (size_t)nsel * c->N, npoly, sel, inverse != 0, c->stream)) return -1;
+    SFG_CUDA(c, cudaMemcpyAsync(polys, d.p, bytes, cudaMemcpyDeviceToHost, c->stream));
+    SFG_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int sfg_mul_coeffs_and_add128(sfg_ctx *h, const uint64_t *a, const uint64_t *b, uint64_t *acc, size_t n) {
+    Ctx *c = &h->c;
+    SFG_CUDA(c, cudaSetDevice(c->device));
+    Buf da, db, dacc;
+    if (da.alloc(c, n * 8) || db.alloc(c, n * 8) || dacc.alloc(c, n * 16)) return -1;
+    SFG_CUDA(c, cudaMemcpyAsync(da.p, a, n * 8, cudaMemcpyHostToDevice, c->stream));
+    SFG_CUDA(c, cudaMemcpyAsync(db.p, b, n * 8, cudaMemcpyHostToDevice, c->stream));
+    SFG_CUDA(c, cudaMemcpyAsync(dacc.p, acc, n * 16, cudaMemcpyHostToDevice, c->stream));
+    if (launch_mul_coeffs_and_add128(c, da.as<uint64_t>(), db.as<uint64_t>(), dacc.as<uint64_t>(), n, c->stream)) return -1;
+    SFG_CUDA(c, cudaMemcpyAsync(acc, dacc.p, n * 16, cudaMemcpyDeviceToHost, c->stream));
+    SFG_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+int sfg_reduce_and_add_uint128(sfg_ctx *h, const uint64_t *acc, uint64_t *out, int limb, size_t n) {
+    Ctx *c = &h->c;
+    if (limb < 0 || limb >= c->nQP) SFG_FAIL(c, "modulus index out of range");
+    SFG_CUDA(c, cudaSetDevice(c->device));
+    Buf dacc, dout;
+    if (dacc.alloc(c, n * 16) || dout.alloc(c, n * 8)) return -1;
+    SFG_CUDA(c, cudaMemcpyAsync(dacc.p, acc, n * 16, cudaMemcpyHostToDevice, c->stream));
+    SFG_CUDA(c, cudaMemcpyAsync(dout.p, out, n * 8, cudaMemcpyHostToDevice, c->stream));
+    if (launch_reduce_and_add128(c, dacc.as<uint64_t>(), dout.as<uint64_t>(), limb, n, c->stream)) return -1;
+    SFG_CUDA(c, cudaMemcpyAsync(out, dout.p, n * 8, cudaMemcpyDeviceToHost, c->stream));
+    SFG_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+int sfg_mform_lvl(sfg_ctx *h, int level, uint64_t *p) {
+    Ctx *c = &h->c;
+    if (level < 0 || level >= c->nQ) SFG_FAIL(c, "level out of range");
+    SFG_CUDA(c, cudaSetDevice(c->device));
+    Buf d;
+    const size_t bytes = (size_t)(level + 1) * c->N * 8;
+    if (d.alloc(c, bytes)) return -1;
+    SFG_CUDA(c, cudaMemcpyAsync(d.p, p, bytes, cudaMemcpyHostToDevice, c->stream));
+    if (launch_mform(c, d.as<uint64_t>(), level + 1, c->stream)) return -1;
+    SFG_CUDA(c, cudaMemcpyAsync(p, d.p, bytes, cudaMemcpyDeviceToHost, c->stream));
+    SFG_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+int sfg_rotate_right(sfg_ctx *h, int level, const uint64_t *cts, int nct, int nrot, uint64_t *out) {
+    Ctx *c = &h->c;
+    if (level < 0 || level >= c->nQ || nct < 1) SFG_FAIL(c, "sfg_rotate_right: bad level / count");
+    SFG_CUDA(c, cudaSetDevice(c->device));
+    const size_t bytes = (size_t)nct * 2 * (level + 1) * c->N * 8;
+    Buf din, dout;
+    if (din.alloc(c, bytes) || dout.alloc(c, bytes)) return -1;
+    SFG_CUDA(c, cudaMemcpyAsync(din.p, cts, bytes, cudaMemcpyHostToDevice, c->stream));
+    if (rotate_right_dev(c, level, din.as<uint64_t>(), nct, nrot, dout.as<uint64_t>())) return -1;
+    SFG_CUDA(c, cudaMemcpy(out, dout.p, bytes, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+// ---- genotype ----
+int sfg_geno_create(sfg_ctx *h, size_t nrows, size_t ncols, sfg_geno **out) {
+    *out = nullptr;
+    Geno *g = nullptr;
+    if (geno_create(&h->c, nrows, ncols, &g)) return -1;
+    *out = new sfg_geno{g};
+    return 0;
+}
+int sfg_geno_push_rows(sfg_geno *g, const int8_t *rows, size_t n) { return geno_push(g->g, rows, n); }
+void sfg_geno_destroy(sfg_geno *g) {
+    if (!g) return;
+    geno_release(g->g);
+    delete g;
+}
+int sfg_encode_diag(sfg_ctx *h, const sfg_geno *g, int block_row, int shift, int nrot, int level, int mont, uint64_t *out,
+                    uint8_t *present, int64_t *coeffs_out) {
+    return encode_diag_host(&h->c, g->g, block_row, shift, nrot, level, mont != 0, out, present, coeffs_out);
+}
+
+// ---- stream entry points ----
+int sfg_matmult4_stream_preprocess(sfg_ctx *h, const sfg_geno *g, int max_level, sfg_cache **out) {
+    *out = nullptr;
+    Cache *ca = nullptr;
+    if (cache_build(&h->c, g->g, max_level, &ca)) return -1;
+    *out = new sfg_cache{ca};
+    return 0;
+}
+void sfg_cache_destroy(sfg_cache *cache) {
+    if (!cache) return;
+    cache_destroy(cache->ca);
+    delete cache;
+}
+int sfg_cache_info(const sfg_cache *cache, size_t *num_polys, size_t *bytes, int *materialised, int *m_ct, int *nbr) {
+    const Cache *ca = cache->ca;
+    if (num_polys) *num_polys = ca->npoly;
+    if (bytes) *bytes = ca->materialised ? ca->npoly * (size_t)ca->L * ca->c->N * 8 : 0;
+    if (materialised) *materialised = ca->materialised ? 1 : 0;
+    if (m_ct) *m_ct = ca->m_ct;
+    if (nbr) *nbr = ca->nbr;
+    return 0;
+}
+int sfg_cache_get_diag(sfg_ctx *h, const sfg_cache *cache, int bi, int shift, int bj, uint64_t *out, int *present) {
+    Ctx *c = &h->c;
+    const Cache *ca = cache->ca;
+    if (bi < 0 || bi >= ca->nbr || shift < 0 || shift >= ca->slots || bj < 0 || bj >= ca->m_ct) SFG_FAIL(c, "cache_get_diag: index out of range");
+    const long long po = ca->pidx[((size_t)bi * ca->slots + shift) * ca->m_ct + bj];
+    *present = po >= 0;
+    if (po < 0) return 0;
+    if (!ca->materialised) SFG_FAIL(c, "cache is not materialised (diagonals are regenerated on the fly)");
+    SFG_CUDA(c, cudaSetDevice(c->device));
+    SFG_CUDA(c, cudaMemcpy(out, ca->P + po, (size_t)ca->L * c->N * 8, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int sfg_matmult4_stream_compute_dev(sfg_ctx *h, const uint64_t *d_A, int s, int nbr, int level_a, int max_level,
+                                    const sfg_cache *cache, uint64_t *d_out) {
+    return mm_compute_dev(&h->c, d_A, s, nbr, level_a, max_level, cache->ca, d_out);
+}
+
+int sfg_matmult4_stream_compute(sfg_ctx *h, const uint64_t *A, int s, int nbr, int level_a, int max_level, const sfg_cache *cache,
+                                uint64_t *out) {
+    Ctx *c = &h->c;
+    if (s < 1 || nbr < 1 || level_a < 0) SFG_FAIL(c, "bad A dimensions");
+    SFG_CUDA(c, cudaSetDevice(c->device));
+    const size_t abytes = (size_t)s * nbr * 2 * (level_a + 1) * c->N * 8;
+    const size_t obytes = (size_t)s * cache->ca->m_ct * 2 * max_level * c->N * 8;
+    Buf dA, dO;
+    if (dA.alloc(c, abytes) || dO.alloc(c, obytes)) return -1;
+    SFG_CUDA(c, cudaMemcpyAsync(dA.p, A, abytes, cudaMemcpyHostToDevice, c->stream));
+    if (mm_compute_dev(c, dA.as<uint64_t>(), s, nbr, level_a, max_level, cache->ca, dO.as<uint64_t>())) return -1;
+    SFG_CUDA(c, cudaMemcpyAsync(out, dO.p, obytes, cudaMemcpyDeviceToHost, c->stream));
+    SFG_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int sfg_matmult4_stream_compute_ptrs(sfg_ctx *h, const uint64_t *const *A_limbs, int s, int nbr, int level_a, int max_level,
+                                     const sfg_cache *cache, uint64_t *const *out_limbs) {
+    Ctx *c = &h->c;
+    if (s < 1 || nbr < 1 || level_a < 0) SFG_FAIL(c, "bad A dimensions");
+    SFG_CUDA(c, cudaSetDevice(c->device));
+    const size_t N = c->N;
+    const size_t na = (size_t)s * nbr * 2 * (level_a + 1), no = (size_t)s * cache->ca->m_ct * 2 * max_level;
+    Buf dA, dO;
+    if (dA.alloc(c, na * N * 8) || dO.alloc(c, no * N * 8)) return -1;
+    for (size_t p = 0; p < na; p++) SFG_CUDA(c, cudaMemcpyAsync(dA.as<uint64_t>() + p * N, A_limbs[p], N * 8, cudaMemcpyHostToDevice, c->stream));
+    if (mm_compute_dev(c, dA.as<uint64_t>(), s, nbr, level_a, max_level, cache->ca, dO.as<uint64_t>())) return -1;
+    for (size_t p = 0; p < no; p++) SFG_CUDA(c, cudaMemcpyAsync(out_limbs[p], dO.as<uint64_t>() + p * N, N * 8, cudaMemcpyDeviceToHost, c->stream));
+    SFG_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int sfg_matmult4_stream(sfg_ctx *h, const uint64_t *A, int s, int level_a, const sfg_geno *g, int max_level, int compute_squared_sum,
+                        int square, uint64_t *out, double *sum, double *sq_sum) {
+    Ctx *c = &h->c;
+    const Geno *src = g->g;
+    if (src->filled != src->nrows) SFG_FAIL(c, "genotype matrix incomplete");
+    if (compute_squared_sum && (!sum || !sq_sum)) SFG_FAIL(c, "sum / sq_sum buffers required when compute_squared_sum is set");
+    SFG_CUDA(c, cudaSetDevice(c->device));
+    // working copy: missing -> 0, (sum, sqSum), optional squaring  (gwas/matmult.go:1289-1304)
+    Geno *w = nullptr;
+    if (geno_create(c, src->nrows, src->ncols, &w)) return -1;
+    w->filled = src->nrows;
+    int rc = -1;
+    Cache *ca = nullptr;
+    Buf dsum, dsq;
+    do {
+        if (cudaMemcpyAsync(w->d, src->d, src->nrows * src->ncols, cudaMemcpyDeviceToDevice, c->stream) != cudaSuccess) { c->err = "D2D copy failed"; break; }
+        if (compute_squared_sum) {
+            if (dsum.alloc(c, src->ncols * 8) || dsq.alloc(c, src->ncols * 8)) break;
+            cudaMemsetAsync(dsum.p, 0, src->ncols * 8, c->stream);
+            cudaMemsetAsync(dsq.p, 0, src->ncols * 8, c->stream);
+        }
+        if (launch_geno_prep(c, w->d, src->nrows, src->ncols, compute_squared_sum ? dsum.as<double>() : nullptr,
+                             compute_squared_sum ? dsq.as<double>() : nullptr, square != 0, c->stream)) break;
+        if (cache_build(c, w, max_level, &ca)) break;
+        const int nbr = ca->nbr;
+        const size_t abytes = (size_t)s * nbr * 2 * (level_a + 1) * c->N * 8;
+        const size_t obytes = (size_t)s * ca->m_ct * 2 * max_level * c->N * 8;
+        Buf dA, dO;
+        if (dA.alloc(c, abytes) || dO.alloc(c, obytes)) break;
+        if (cudaMemcpyAsync(dA.p, A, abytes, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) { c->err = "H2D copy of A failed"; break; }
+        if (mm_compute_dev(c, dA.as<uint64_t>(), s, nbr, level_a, max_level, ca, dO.as<uint64_t>())) break;
+        if (cudaMemcpyAsync(out, dO.p, obytes, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) { c->err = "D2H copy failed"; break; }
+        if (compute_squared_sum) {
+            cudaMemcpyAsync(sum, dsum.p, src->ncols * 8, cudaMemcpyDeviceToHost, c->stream);
+            cudaMemcpyAsync(sq_sum, dsq.p, src->ncols * 8, cudaMemcpyDeviceToHost, c->stream);
+        }
+        if (cudaStreamSynchronize(c->stream) != cudaSuccess) { c->err = "stream sync failed"; break; }
+        rc = 0;
+    } while (0);
+    if (ca) cache_destroy(ca);
+    geno_release(w);
+    return rc;
+}
+
+// ---- multi-GPU pieces ----
+size_t sfg_cv_elems(const sfg_ctx *h, const sfg_cache *cache, int s, int max_level) {
+    const Cache *ca = cache->ca;
+    (void)max_level;
+    return ca->gact.size() * (size_t)ca->m_ct * 2 * s * ca->L * h->c.N;
+}
+int sfg_matmult4_partial(sfg_ctx *h, const uint64_t *A, int s, int nbr, int level_a, int max_level, const sfg_cache *cache, int bi_lo,
+                         int bi_hi, uint64_t *d_cv) {
+    Ctx *c = &h->c;
+    SFG_CUDA(c, cudaSetDevice(c->device));
+    const size_t abytes = (size_t)s * nbr * 2 * (level_a + 1) * c->N * 8;
+    Buf dA;
+    if (dA.alloc(c, abytes)) return -1;
+    SFG_CUDA(c, cudaMemcpyAsync(dA.p, A, abytes, cudaMemcpyHostToDevice, c->stream));
+    return mm_partial_dev(c, dA.as<uint64_t>(), s, nbr, level_a, max_level, cache->ca, bi_lo, bi_hi, d_cv);
+}
+int sfg_cv_mod_reduce(sfg_ctx *h, const sfg_cache *cache, int s, int max_level, uint64_t *d_cv, size_t first_elem, size_t num_elems) {
+    Ctx *c = &h->c;
+    (void)s;
+    (void)max_level;
+    const size_t N = c->N, L = cache->ca->L;
+    if (first_elem % (L * N) || num_elems % (L * N)) SFG_FAIL(c, "cv_mod_reduce: range must cover whole [L][N] polynomials");
+    SFG_CUDA(c, cudaSetDevice(c->device));
+    if (launch_mod_reduce(c, d_cv + first_elem, num_elems / N, (int)L, c->stream)) return -1;
+    SFG_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+int sfg_matmult4_finish(sfg_ctx *h, const sfg_cache *cache, int s, int max_level, const uint64_t *d_cv, int g_lo, int g_hi, uint64_t *out) {
+    Ctx *c = &h->c;
+    SFG_CUDA(c, cudaSetDevice(c->device));
+    const size_t obytes = (size_t)s * cache->ca->m_ct * 2 * max_level * c->N * 8;
+    Buf dO;
+    if (dO.alloc(c, obytes)) return -1;
+    if (mm_finish_dev(c, cache->ca, s, max_level, d_cv, g_lo, g_hi, dO.as<uint64_t>())) return -1;
+    SFG_CUDA(c, cudaMemcpy(out, dO.p, obytes, cudaMemcpyDeviceToHost));
+    return 0;
+}
+int sfg_ct_add(sfg_ctx *h, const uint64_t *a, const uint64_t *b, int ncts, int nl, uint64_t *out) {
+    Ctx *c = &h->c;
+    if (nl < 1 || nl > c->nQ) SFG_FAIL(c, "ct_add: bad limb count");
+    SFG_CUDA(c, cudaSetDevice(c->device));
+    const size_t n = (size_t)ncts * 2 * nl * c->N;
+    Buf da, db;
+    if (da.alloc(c, n * 8) || db.alloc(c, n * 8)) return -1;
+    SFG_CUDA(c, cudaMemcpyAsync(da.p, a, n * 8, cudaMemcpyHostToDevice, c->stream));
+    SFG_CUDA(c, cudaMemcpyAsync(db.p, b, n * 8, cudaMemcpyHostToDevice, c->stream));
+    std::vector<long long> offs(ncts);
+    for (int t = 0; t < ncts; t++) offs[t] = (long long)t * 2 * nl * c->N;
+    Buf doffs;
+    if (doffs.alloc(c, std::max(1, ncts) * sizeof(long long))) return -1;
+    SFG_CUDA(c, cudaMemcpyAsync(doffs.p, offs.data(), ncts * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
+    KsBatch kb{};
+    kb.nct = ncts;
+    kb.in = da.as<uint64_t>();
+    kb.in_off = doffs.as<long long>();
+    kb.in_nl = nl;
+    kb.out = db.as<uint64_t>();
+    kb.out_off = doffs.as<long long>();
+    kb.out_nl = nl;
+    kb.out_limbs = nl;
+    kb.accumulate = true;
+    if (launch_copy_add(c, kb, c->stream)) return -1;
+    SFG_CUDA(c, cudaMemcpyAsync(out, db.p, n * 8, cudaMemcpyDeviceToHost, c->stream));
+    SFG_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+}  // extern "C"

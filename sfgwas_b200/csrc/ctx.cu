@@ -1,0 +1,146 @@
+// ctx.cu -- context construction: RNS constants, NTT twiddles, encoder tables, key-switch base-conversion tables.
+#include <cmath>
+#include <cstring>
+
+#include "ctx.h"
+
+namespace sfg {
+
+int ctx_build_tables(Ctx *c, const uint64_t *psi_opt) {
+    const int N = c->N, logN = c->logN, nQP = c->nQP;
+    SFG_CUDA(c, cudaSetDevice(c->device));
+    c->lc_h.resize(nQP);
+    c->psi.resize(nQP);
+    std::vector<uint64_t> tw((size_t)nQP * 4 * N);
+    for (int i = 0; i < nQP; i++) {
+        const uint64_t q = c->mod[i];
+        if ((q & 1) == 0 || q >= (1ULL << 62) || (q - 1) % (2ULL * N) != 0) SFG_FAIL(c, "modulus %d (%llu) is not an NTT-friendly prime < 2^62", i, (unsigned long long)q);
+        c->lc_h[i] = h_limb_const(q, N);
+        // Lattigo ring.genNTTParams: psi = g^((q-1)/2N), psiInv = g^(q-1-(q-1)/2N)   
+        uint64_t psi = psi_opt ? psi_opt[i] : h_powmod(h_primitive_root(q), (q - 1) / (2ULL * N), q);
+        if (h_powmod(psi, N, q) != q - 1) SFG_FAIL(c, "psi for modulus %d is not a primitive 2N-th root of unity", i);
+        c->psi[i] = psi;
+        const uint64_t psiInv = h_invmod(psi, q);
+        uint64_t *w = &tw[(size_t)i * 4 * N], *wsh = w + N, *wi = w + 2 * N, *wish = w + 3 * N;
+        uint64_t p = 1, pi = 1;
+        for (int j = 0; j < N; j++) {  // NttPsi[brv(j)] = psi^j, NttPsiInv[brv(j)] = psi^-j
+            const uint64_t r = h_bitrev((uint64_t)j, logN);
+            w[r] = p;
+            wsh[r] = h_shoup(p, q);
+            wi[r] = pi;
+            wish[r] = h_shoup(pi, q);
+            p = h_mulmod(p, psi, q);
+            pi = h_mulmod(pi, psiInv, q);
+        }
+    }
+    SFG_CUDA(c, cudaMalloc(&c->lc, sizeof(LimbConst) * nQP));
+    SFG_CUDA(c, cudaMemcpy(c->lc, c->lc_h.data(), sizeof(LimbConst) * nQP, cudaMemcpyHostToDevice));
+    SFG_CUDA(c, cudaMalloc(&c->tw, sizeof(uint64_t) * tw.size()));
+    SFG_CUDA(c, cudaMemcpy(c->tw, tw.data(), sizeof(uint64_t) * tw.size(), cudaMemcpyHostToDevice));
+
+    // encoder tables (Lattigo ckks encoder: m = 2N, rotGroup[j] = 5^j mod m, roots[k] = exp(2 pi i k / m); App. B.6)
+    const int M = 2 * N;
+    std::vector<double> roots(2 * (size_t)(M + 1)), dd(2 * (size_t)M);
+    h_trig_tables(M, roots.data(), dd.data());
+    std::vector<int> rot5(c->slots);
+    uint64_t five = 1;
+    for (int j = 0; j < c->slots; j++) {
+        rot5[j] = (int)five;
+        five = five * 5 % (uint64_t)M;
+    }
+    SFG_CUDA(c, cudaMalloc(&c->roots, sizeof(double) * roots.size()));
+    SFG_CUDA(c, cudaMemcpy(c->roots, roots.data(), sizeof(double) * roots.size(), cudaMemcpyHostToDevice));
+    SFG_CUDA(c, cudaMalloc(&c->ddcos, sizeof(double) * dd.size()));
+    SFG_CUDA(c, cudaMemcpy(c->ddcos, dd.data(), sizeof(double) * dd.size(), cudaMemcpyHostToDevice));
+    SFG_CUDA(c, cudaMalloc(&c->rot5, sizeof(int) * rot5.size()));
+    SFG_CUDA(c, cudaMemcpy(c->rot5, rot5.data(), sizeof(int) * rot5.size(), cudaMemcpyHostToDevice));
+    SFG_CUDA(c, cudaMalloc(&c->enc_stats, sizeof(unsigned long long) * 2));
+    SFG_CUDA(c, cudaMemset(c->enc_stats, 0, sizeof(unsigned long long) * 2));
+    // FP64 special-FFT error model for slot values |v| <= 4: scale * eps * log2(n) * 4 / sqrt(n); the window is 64x that
+    // (DESIGN.md "encoder exactness"; validated against the quad-precision oracle in tests/test_encode.py).
+    const double n = (double)c->slots;
+    const double err = c->scale * 1.1102230246251565e-16 * std::log2(n) * 4.0 / std::sqrt(n);
+    c->enc_delta = std::min(0.2, std::max(1e-9, 64.0 * err));
+    return 0;
+}
+
+static void fill_bc(const Ctx *c, const int *src, int ns, int tgt, BaseConv &b) {
+    memset(&b, 0, sizeof b);
+    b.ns = ns;
+    const uint64_t t = c->mod[tgt];
+    uint64_t smod = 1;
+    for (int k = 0; k < ns; k++) {
+        const uint64_t sk = c->mod[src[k]];
+        uint64_t prod = 1, prodT = 1;
+        for (int j = 0; j < ns; j++)
+            if (j != k) {
+                prod = h_mulmod(prod, c->mod[src[j]] % sk, sk);
+                prodT = h_mulmod(prodT, c->mod[src[j]] % t, t);
+            }
+        b.src_limb[k] = src[k];
+        b.sinv[k] = h_invmod(prod, sk);
+        b.sinv_sh[k] = h_shoup(b.sinv[k], sk);
+        b.fac[k] = prodT;
+        b.fac_sh[k] = h_shoup(prodT, t);
+        b.sf[k] = (double)sk;
+        smod = h_mulmod(smod, sk % t, t);
+    }
+    b.smod = smod;
+    b.smod_sh = h_shoup(smod, t);
+}
+
+// Tables for a key-switch at `level`: digit i covers Q limbs [i*alpha, min((i+1)*alpha, level+1)).
+//   ks: [beta_l][level+1+nP]  (target tt < level+1 -> Q limb tt ; else P limb tt-(level+1)); ns = 0 when the target
+//       lies inside the digit (the NTT-domain input limb is reused, Lattigo decomposeAndSplitNTT).
+//   md: [level+1]  P -> q_l ;  pinv: [level+1][2]  P^-1 mod q_l with Shoup companion.
+int ctx_get_ks_tables(Ctx *c, int level, BaseConv **ks, BaseConv **md, uint64_t **pinv) {
+    std::lock_guard<std::mutex> g(c->mu);
+    if (level < 0 || level >= c->nQ) SFG_FAIL(c, "key-switch level %d out of range", level);
+    if (!c->bc_ks.count(level)) {
+        const int nl = level + 1, alpha = c->nP, beta = (nl + alpha - 1) / alpha, nt = nl + c->nP;
+        if (alpha > kMaxAlpha) SFG_FAIL(c, "more than %d special primes are not supported", kMaxAlpha);
+        std::vector<BaseConv> h((size_t)beta * nt);
+        for (int i = 0; i < beta; i++) {
+            int src[kMaxAlpha], ns = 0;
+            for (int k = i * alpha; k < std::min((i + 1) * alpha, nl); k++) src[ns++] = k;
+            for (int tt = 0; tt < nt; tt++) {
+                const int tgt = tt < nl ? tt : c->nQ + (tt - nl);
+                BaseConv &b = h[(size_t)i * nt + tt];
+                if (tt >= i * alpha && tt < i * alpha + ns) {
+                    memset(&b, 0, sizeof b);
+                } else {
+                    fill_bc(c, src, ns, tgt, b);
+                }
+            }
+        }
+        std::vector<BaseConv> hm(nl);
+        std::vector<uint64_t> hp((size_t)nl * 2);
+        int psrc[kMaxAlpha];
+        for (int p = 0; p < c->nP; p++) psrc[p] = c->nQ + p;
+        for (int l = 0; l < nl; l++) {
+            fill_bc(c, psrc, c->nP, l, hm[l]);
+            const uint64_t q = c->mod[l];
+            uint64_t Pm = 1;
+            for (int p = 0; p < c->nP; p++) Pm = h_mulmod(Pm, c->mod[c->nQ + p] % q, q);
+            hp[2 * l] = h_invmod(Pm, q);
+            hp[2 * l + 1] = h_shoup(hp[2 * l], q);
+        }
+        BaseConv *dks = nullptr, *dmd = nullptr;
+        uint64_t *dp = nullptr;
+        SFG_CUDA(c, cudaMalloc(&dks, sizeof(BaseConv) * h.size()));
+        SFG_CUDA(c, cudaMemcpy(dks, h.data(), sizeof(BaseConv) * h.size(), cudaMemcpyHostToDevice));
+        SFG_CUDA(c, cudaMalloc(&dmd, sizeof(BaseConv) * hm.size()));
+        SFG_CUDA(c, cudaMemcpy(dmd, hm.data(), sizeof(BaseConv) * hm.size(), cudaMemcpyHostToDevice));
+        SFG_CUDA(c, cudaMalloc(&dp, sizeof(uint64_t) * hp.size()));
+        SFG_CUDA(c, cudaMemcpy(dp, hp.data(), sizeof(uint64_t) * hp.size(), cudaMemcpyHostToDevice));
+        c->bc_ks[level] = dks;
+        c->bc_md[level] = dmd;
+        c->pinv[level] = dp;
+    }
+    *ks = c->bc_ks[level];
+    *md = c->bc_md[level];
+    *pinv = c->pinv[level];
+    return 0;
+}
+
+}  // namespace sfg

@@ -1,0 +1,88 @@
+// ctx.h -- host-side context of libsfgwas_b200 (C++17, CUDA runtime only; no torch types).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "modarith.cuh"
+
+namespace sfg {
+
+constexpr int kMaxAlpha = 8;   // max #moduli per key-switch digit / #P moduli (Lattigo arrays are size 8 too)
+constexpr int kMaxLimbs = 48;
+
+// Fast exact base conversion {s_k} -> t of Lattigo (ring.modUpExact / Decomposer), SURVEY App. B.5.
+struct BaseConv {
+    int ns;                       // number of source moduli (1 => plain BRedAdd of the representative)
+    int src_limb[kMaxAlpha];      // QP index of each source modulus
+    uint64_t sinv[kMaxAlpha];     // (S/s_k)^-1 mod s_k
+    uint64_t sinv_sh[kMaxAlpha];
+    uint64_t fac[kMaxAlpha];      // S/s_k mod t
+    uint64_t fac_sh[kMaxAlpha];
+    uint64_t smod;                // S mod t
+    uint64_t smod_sh;
+    double sf[kMaxAlpha];         // float64(s_k)
+};
+
+struct GaloisKey {
+    uint64_t galEl = 0;
+    uint64_t *key = nullptr;      // device [beta][2][nQP][N], NTT + Montgomery form (Lattigo SwitchingKey)
+    uint32_t *perm = nullptr;     // device [N] PermuteNTTIndex(galEl)
+};
+
+struct Ctx {
+    int device = 0;
+    int logN = 0, N = 0, slots = 0, d = 0;
+    int nQ = 0, nP = 0, nQP = 0, beta = 0;
+    double scale = 0;
+    std::vector<uint64_t> mod, psi;        // host copies
+    std::vector<LimbConst> lc_h;
+    LimbConst *lc = nullptr;               // device [nQP]
+    uint64_t *tw = nullptr;                // device [nQP][4][N]
+    // encoder (special inverse FFT)
+    double2 *roots = nullptr;              // device [2N+1] exp(2 pi i k / 2N)
+    int *rot5 = nullptr;                   // device [slots] 5^j mod 2N
+    double2 *ddcos = nullptr;              // device [2N] cos(2 pi t / 2N) as double-double (hi, lo)
+    double enc_delta = 0;                  // half-integer ambiguity window for the FP64 path
+    unsigned long long *enc_stats = nullptr;  // device [2]: {rechecked coefficients, unresolved ties}
+    // key-switch tables per level: bc_ks[level] -> device array [beta_l][level+1+nP]; bc_md -> [level+1]
+    std::map<int, BaseConv *> bc_ks, bc_md;
+    std::map<int, uint64_t *> pinv;        // device [level+1][2]: P^-1 mod q_l and Shoup companion
+    std::map<uint64_t, GaloisKey> keys;    // galEl -> key
+    cudaStream_t stream = nullptr;
+    size_t cache_budget = 0;               // bytes of HBM the diagonal cache may take (0 = auto)
+    std::mutex mu;
+    std::string err;
+    // counters
+    unsigned long long launches = 0;
+};
+
+#define SFG_CUDA(ctx, expr)                                                                             \
+    do {                                                                                                \
+        cudaError_t e__ = (expr);                                                                       \
+        if (e__ != cudaSuccess) {                                                                       \
+            char buf__[512];                                                                            \
+            snprintf(buf__, sizeof buf__, "%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e__)); \
+            (ctx)->err = buf__;                                                                         \
+            return -1;                                                                                  \
+        }                                                                                               \
+    } while (0)
+
+#define SFG_FAIL(ctx, ...)                              \
+    do {                                                \
+        char buf__[512];                                \
+        snprintf(buf__, sizeof buf__, __VA_ARGS__);     \
+        (ctx)->err = buf__;                             \
+        return -1;                                      \
+    } while (0)
+
+// ---- table builders (ctx.cu) ----
+int ctx_build_tables(Ctx *c, const uint64_t *psi_opt);
+int ctx_get_ks_tables(Ctx *c, int level, BaseConv **ks, BaseConv **md, uint64_t **pinv);
+
+}  // namespace sfg

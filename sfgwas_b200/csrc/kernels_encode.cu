@@ -1,0 +1,216 @@
+// kernels_encode.cu -- on-device generation of the NTT-domain plaintext diagonals (K5 + K4 + K3 of SURVEY 2.2):
+//   GetDiag (gwas/matmult.go:636-664)  ->  convertToComplex128WithRot (:666-672)  ->  EncoderBig.EncodeNTT (:711-731,
+//   Lattigo App. B.6)  ->  ToMontgomeryForm (:401-440).
+//
+// One CTA per diagonal polynomial.  The CKKS canonical-embedding inverse ("special" inverse FFT over the rotation
+// group 5^j) runs in FP64 in shared memory.  The reference rounds scale*w_k computed with 256-bit floats, i.e. the
+// correctly rounded value.  FP64 alone is not bit-exact, so every coefficient whose scaled value lies within
+// `delta` of a half-integer is recomputed exactly-enough by a direct double-double sum of the n terms
+// v_j * cos/sin(2 pi 5^j k / 2N) (error ~1e-25), which resolves the rounding.  Coefficients that are still within
+// 1e-13 of a tie after that are counted in stats[1] (never observed; a genuine tie needs an exact half-integer).
+#include "kernels.h"
+#include "ntt.cuh"
+
+namespace sfg {
+
+// ---- double-double helpers ----
+struct dd {
+    double hi, lo;
+};
+__device__ __forceinline__ dd two_sum(double a, double b) {
+    double s = a + b, bb = s - a;
+    return dd{s, (a - (s - bb)) + (b - bb)};
+}
+__device__ __forceinline__ dd dd_add(dd a, dd b) {
+    dd s = two_sum(a.hi, b.hi);
+    dd t = two_sum(a.lo, b.lo);
+    s.lo += t.hi;
+    s = two_sum(s.hi, s.lo);
+    s.lo += t.lo;
+    return two_sum(s.hi, s.lo);
+}
+__device__ __forceinline__ dd dd_mul_d(dd a, double b) {
+    double p = a.hi * b;
+    double e = __fma_rn(a.hi, b, -p);
+    e = __fma_rn(a.lo, b, e);
+    return two_sum(p, e);
+}
+
+constexpr int kMaxFlag = 2048;
+
+template <int NPER>
+__global__ void __launch_bounds__(1024, 1)
+k_encode(const int8_t *__restrict__ X, size_t ld, const EncJob *__restrict__ jobs, int logN, int nl, int mont, double sc,
+         double delta, const double2 *__restrict__ roots, const int *__restrict__ rot5, const double2 *__restrict__ ddcos,
+         const uint64_t *__restrict__ tw, const LimbConst *__restrict__ lcs, uint64_t *__restrict__ out,
+         long long *__restrict__ coeff_out, unsigned long long *__restrict__ stats) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int N = 1 << logN, n = N >> 1, M = N << 1, logn = logN - 1;
+    double *re = reinterpret_cast<double *>(smem_raw);
+    double *im = re + n;
+    uint64_t *s = reinterpret_cast<uint64_t *>(smem_raw);  // aliases re/im after the FFT
+    int8_t *vals = reinterpret_cast<int8_t *>(smem_raw + (size_t)N * 8);
+    int *flag_idx = reinterpret_cast<int *>(vals + n);
+    long long *flag_val = reinterpret_cast<long long *>(flag_idx + kMaxFlag);
+    dd *red = reinterpret_cast<dd *>(flag_val + kMaxFlag);  // [32] warp partials
+    __shared__ int nflag;
+
+    const EncJob job = jobs[blockIdx.x];
+    const int T = blockDim.x, tid = threadIdx.x;
+    if (tid == 0) nflag = 0;
+
+    // 1. gather the generalized diagonal, right-rotated by nrot:  v[(j+nrot) mod n] = X[(shift+j) mod n][j]
+    for (int j = tid; j < n; j += T) {
+        int row = job.shift + j;
+        if (row >= n) row -= n;
+        int8_t v = 0;
+        if (row < job.r && j < job.cdim) v = X[(size_t)(job.row0 + row) * ld + job.col0 + j];
+        int dst = j + job.nrot;
+        if (dst >= n) dst -= n;
+        vals[dst] = v;
+        re[dst] = (double)v;
+        im[dst] = 0.0;
+    }
+    __syncthreads();
+
+    // 2. special inverse FFT (Lattigo invfft, App. B.6), decimation in frequency, result in bit-reversed order
+    for (int len = n, loglen = logn; len >= 2; len >>= 1, loglen--) {
+        const int lenh = len >> 1, lenq = len << 2, gap = M / lenq;
+        for (int b = tid; b < (n >> 1); b += T) {
+            const int grp = b >> (loglen - 1), j = b & (lenh - 1);
+            const int i0 = (grp << loglen) + j, i1 = i0 + lenh;
+            const int idx = (lenq - (rot5[j] & (lenq - 1))) * gap;
+            const double2 w = roots[idx];
+            const double ur = re[i0] + re[i1], ui = im[i0] + im[i1];
+            const double vr = re[i0] - re[i1], vi = im[i0] - im[i1];
+            re[i0] = ur;
+            im[i0] = ui;
+            re[i1] = vr * w.x - vi * w.y;
+            im[i1] = vr * w.y + vi * w.x;
+        }
+        __syncthreads();
+    }
+
+    // 3. scale, round half away from zero, flag near-ties
+    long long m[NPER];
+#pragma unroll
+    for (int r = 0; r < NPER; r++) {
+        const int k = tid + r * T;
+        const int kk = k < n ? k : k - n;
+        const int pos = __brev((unsigned)kk) >> (32 - logn);
+        const double x = (k < n ? re[pos] : im[pos]) * sc;
+        const double ax = fabs(x);
+        const double fl = floor(ax);
+        const double fr = ax - fl;
+        long long v = (long long)fl + (fr >= 0.5 ? 1 : 0);
+        m[r] = x < 0 ? -v : v;
+        if (fabs(fr - 0.5) < delta) {
+            const int f = atomicAdd(&nflag, 1);
+            if (f < kMaxFlag) flag_idx[f] = k;
+        }
+    }
+    __syncthreads();
+
+    // 4. exact re-evaluation of the flagged coefficients in double-double
+    const int nf = nflag < kMaxFlag ? nflag : kMaxFlag;
+    if (nflag > 0) {
+        for (int f = 0; f < nf; f++) {
+            const int k = flag_idx[f];
+            const int kk = k < n ? k : k - n;
+            const int shiftq = k < n ? 0 : (M >> 2);  // imaginary part: -sin(t) = -cos(t - pi/2)
+            dd acc{0.0, 0.0};
+            for (int j = tid; j < n; j += T) {
+                const int v = vals[j];
+                if (v != 0) {
+                    const int t = (int)(((long long)rot5[j] * kk - shiftq) & (M - 1));
+                    const double2 cs = ddcos[t];
+                    acc = dd_add(acc, dd_mul_d(dd{cs.x, cs.y}, (double)v));
+                }
+            }
+            // block reduction
+            for (int o = 16; o > 0; o >>= 1) {
+                dd other{__shfl_down_sync(0xffffffffu, acc.hi, o), __shfl_down_sync(0xffffffffu, acc.lo, o)};
+                acc = dd_add(acc, other);
+            }
+            if ((tid & 31) == 0) red[tid >> 5] = acc;
+            __syncthreads();
+            if (tid == 0) {
+                dd tot{0.0, 0.0};
+                for (int w = 0; w < (T + 31) / 32; w++) tot = dd_add(tot, red[w]);
+                if (k >= n) { tot.hi = -tot.hi; tot.lo = -tot.lo; }
+                dd x = dd_mul_d(tot, sc);
+                const bool neg = x.hi < 0;
+                if (neg) { x.hi = -x.hi; x.lo = -x.lo; }
+                double ip = floor(x.hi);
+                double fr = (x.hi - ip) + x.lo;
+                if (fr < 0) { ip -= 1.0; fr += 1.0; }
+                if (fr >= 1.0) { ip += 1.0; fr -= 1.0; }
+                long long v = (long long)ip + (fr >= 0.5 ? 1 : 0);
+                flag_val[f] = neg ? -v : v;
+                atomicAdd(&stats[0], 1ULL);
+                if (fabs(fr - 0.5) < 1e-13) atomicAdd(&stats[1], 1ULL);
+            }
+            __syncthreads();
+        }
+        if (nflag > kMaxFlag && tid == 0) atomicAdd(&stats[1], (unsigned long long)(nflag - kMaxFlag));
+#pragma unroll
+        for (int r = 0; r < NPER; r++) {
+            const int k = tid + r * T;
+            for (int f = 0; f < nf; f++)
+                if (flag_idx[f] == k) m[r] = flag_val[f];
+        }
+        __syncthreads();
+    }
+
+    if (coeff_out) {
+#pragma unroll
+        for (int r = 0; r < NPER; r++) coeff_out[(size_t)blockIdx.x * N + tid + r * T] = m[r];
+    }
+
+    // 5. RNS reduce, NTT per limb, Montgomery form, store
+    for (int l = 0; l < nl; l++) {
+        const LimbConst lc = lcs[l];
+        const NttTab tab = ntt_tab(tw, l, N);
+#pragma unroll
+        for (int r = 0; r < NPER; r++) {
+            const long long v = m[r];
+            uint64_t x = bred_add((uint64_t)(v < 0 ? -v : v), lc);
+            if (v < 0 && x != 0) x = lc.q - x;
+            s[tid + r * T] = x;
+        }
+        __syncthreads();
+        ntt_fwd_smem(s, logN, 1, 0, tab, lc.q);
+        uint64_t *o = out + job.out_off + (size_t)l * N;
+#pragma unroll
+        for (int r = 0; r < NPER; r++) {
+            const uint64_t x = s[tid + r * T];
+            o[tid + r * T] = mont ? mform(x, lc) : x;
+        }
+        __syncthreads();
+    }
+}
+
+int launch_encode(Ctx *c, const int8_t *X, size_t ld, const EncJob *jobs_dev, int njobs, int nl, bool mont, uint64_t *out,
+                  long long *coeff_out, cudaStream_t st) {
+    if (njobs <= 0) return 0;
+    const int logN = c->logN, N = c->N, n = c->slots;
+    if (logN < 8 || logN > 14) SFG_FAIL(c, "on-device diagonal encoder supports 8 <= logN <= 14 (got %d)", logN);
+    const int NPER = logN == 14 ? 16 : 8;
+    const int T = N / NPER;
+    const size_t smem = (size_t)N * 8 + n + kMaxFlag * (sizeof(int) + sizeof(long long)) + 32 * sizeof(dd) + 64;
+    const double sc = c->scale / (double)n;
+    if (NPER == 16) {
+        SFG_CUDA(c, cudaFuncSetAttribute(k_encode<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_encode<16><<<njobs, T, smem, st>>>(X, ld, jobs_dev, logN, nl, mont ? 1 : 0, sc, c->enc_delta, c->roots, c->rot5, c->ddcos,
+                                            c->tw, c->lc, out, coeff_out, c->enc_stats);
+    } else {
+        SFG_CUDA(c, cudaFuncSetAttribute(k_encode<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_encode<8><<<njobs, T, smem, st>>>(X, ld, jobs_dev, logN, nl, mont ? 1 : 0, sc, c->enc_delta, c->roots, c->rot5, c->ddcos,
+                                           c->tw, c->lc, out, coeff_out, c->enc_stats);
+    }
+    c->launches++;
+    SFG_CUDA(c, cudaGetLastError());
+    return 0;
+}
+
+}  // namespace sfg

@@ -1,0 +1,218 @@
+// kernels_ntt.cu -- batched negacyclic NTT/INTT over RNS limbs, plus the stand-alone K1/K2/K3 kernels and the
+// genotype preparation scan.  sm_100a only.
+//
+// NTT layout: one CTA owns one polynomial-limb (or a 2^14-coefficient sub-block of it for logN > 14) in shared memory;
+// stages run over smem; the first (forward) / last (inverse) log2(N/S) stages of logN > 14 run over global memory.
+#include "kernels.h"
+#include "ntt.cuh"
+
+namespace sfg {
+
+constexpr int kMaxLogS = 14;  // 2^14 * 8 B = 128 KB of shared memory per CTA
+
+template <bool INV>
+__global__ void __launch_bounds__(1024, 1)
+k_ntt_smem(const uint64_t *__restrict__ src, size_t src_gstride, uint64_t *__restrict__ dst, size_t dst_gstride, LimbSel sel,
+           int logN, int logS, const uint64_t *__restrict__ tw, const LimbConst *__restrict__ lcs) {
+    extern __shared__ __align__(16) uint64_t s[];
+    const int N = 1 << logN, S = 1 << logS, nblk = N >> logS;
+    const int p = blockIdx.x / nblk, blk = blockIdx.x % nblk;
+    const int g = p / sel.n, k = p % sel.n, limb = sel.idx[k];
+    const uint64_t *in = src + (size_t)g * src_gstride + (size_t)k * N + (size_t)blk * S;
+    uint64_t *out = dst + (size_t)g * dst_gstride + (size_t)k * N + (size_t)blk * S;
+    const LimbConst lc = lcs[limb];
+    const NttTab tab = ntt_tab(tw, limb, N);
+    for (int i = threadIdx.x; i < S; i += blockDim.x) s[i] = in[i];
+    __syncthreads();
+    if (!INV)
+        ntt_fwd_smem(s, logS, nblk, blk, tab, lc.q);
+    else
+        ntt_inv_smem(s, logS, N, blk, tab, lc, nblk == 1);
+    for (int i = threadIdx.x; i < S; i += blockDim.x) out[i] = s[i];
+}
+
+// One global-memory radix-2 stage (only used for logN > 14).  Forward: stage with m groups (m < N/S).
+// Inverse: stage with h groups (h < N/S ... 1); `last` multiplies by N^-1.
+template <bool INV>
+__global__ void k_ntt_gstage(uint64_t *__restrict__ data, size_t gstride, LimbSel sel, int logN, int m, int last,
+                             const uint64_t *__restrict__ tw, const LimbConst *__restrict__ lcs) {
+    const int N = 1 << logN;
+    const int p = blockIdx.y;
+    const int g = p / sel.n, k = p % sel.n, limb = sel.idx[k];
+    uint64_t *a = data + (size_t)g * gstride + (size_t)k * N;
+    const LimbConst lc = lcs[limb];
+    const NttTab tab = ntt_tab(tw, limb, N);
+    const int t = N / (2 * m);
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < N / 2; b += gridDim.x * blockDim.x) {
+        const int i = b / t, j = b % t, idx = 2 * i * t + j;
+        if (!INV) {
+            const uint64_t U = a[idx], V = mul_shoup(a[idx + t], tab.w[m + i], tab.wsh[m + i], lc.q);
+            a[idx] = add_mod(U, V, lc.q);
+            a[idx + t] = sub_mod(U, V, lc.q);
+        } else {
+            const uint64_t U = a[idx], V = a[idx + t];
+            uint64_t x = add_mod(U, V, lc.q), y = mul_shoup(sub_mod(U, V, lc.q), tab.wi[m + i], tab.wish[m + i], lc.q);
+            if (last) {
+                x = mul_shoup(x, lc.ninv, lc.ninv_sh, lc.q);
+                y = mul_shoup(y, lc.ninv, lc.ninv_sh, lc.q);
+            }
+            a[idx] = x;
+            a[idx + t] = y;
+        }
+    }
+}
+
+__global__ void k_copy_polys(const uint64_t *__restrict__ src, size_t src_gstride, uint64_t *__restrict__ dst, size_t dst_gstride,
+                             int n_per_group, int N) {
+    const int p = blockIdx.y, g = p / n_per_group, k = p % n_per_group;
+    const uint64_t *in = src + (size_t)g * src_gstride + (size_t)k * N;
+    uint64_t *out = dst + (size_t)g * dst_gstride + (size_t)k * N;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) out[i] = in[i];
+}
+
+int launch_ntt(Ctx *c, const uint64_t *src, size_t src_gstride, uint64_t *dst, size_t dst_gstride, int npoly, const LimbSel &sel,
+               bool inverse, cudaStream_t st) {
+    if (npoly <= 0) return 0;
+    const int logN = c->logN, N = c->N;
+    const int logS = logN < kMaxLogS ? logN : kMaxLogS, S = 1 << logS, nblk = N >> logS;
+    const int threads = S / 2 < 1024 ? S / 2 : 1024;
+    const size_t smem = (size_t)S * sizeof(uint64_t);
+    static bool attr_set = false;
+    if (!attr_set) {
+        SFG_CUDA(c, cudaFuncSetAttribute(k_ntt_smem<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << kMaxLogS) * 8));
+        SFG_CUDA(c, cudaFuncSetAttribute(k_ntt_smem<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << kMaxLogS) * 8));
+        attr_set = true;
+    }
+    if (nblk == 1) {
+        if (!inverse)
+            k_ntt_smem<false><<<npoly, threads, smem, st>>>(src, src_gstride, dst, dst_gstride, sel, logN, logS, c->tw, c->lc);
+        else
+            k_ntt_smem<true><<<npoly, threads, smem, st>>>(src, src_gstride, dst, dst_gstride, sel, logN, logS, c->tw, c->lc);
+        c->launches++;
+    } else {
+        // large rings: global stages work in place on dst
+        dim3 gg(64, npoly);
+        if (!inverse) {
+            if (src != dst) {
+                k_copy_polys<<<gg, 256, 0, st>>>(src, src_gstride, dst, dst_gstride, sel.n, N);
+                c->launches++;
+            }
+            for (int m = 1; m < nblk; m <<= 1) {
+                k_ntt_gstage<false><<<gg, 256, 0, st>>>(dst, dst_gstride, sel, logN, m, 0, c->tw, c->lc);
+                c->launches++;
+            }
+            k_ntt_smem<false><<<npoly * nblk, threads, smem, st>>>(dst, dst_gstride, dst, dst_gstride, sel, logN, logS, c->tw, c->lc);
+            c->launches++;
+        } else {
+            k_ntt_smem<true><<<npoly * nblk, threads, smem, st>>>(src, src_gstride, dst, dst_gstride, sel, logN, logS, c->tw, c->lc);
+            c->launches++;
+            for (int h = nblk >> 1; h >= 1; h >>= 1) {
+                k_ntt_gstage<true><<<gg, 256, 0, st>>>(dst, dst_gstride, sel, logN, h, h == 1, c->tw, c->lc);
+                c->launches++;
+            }
+        }
+    }
+    SFG_CUDA(c, cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K1 / K2 / K3 as stand-alone kernels: the exact restatement of gwas/matmult.go:247-324,411-440, used by the parity
+// tests; the production MAC fuses K1+K2 (kernels_mac.cu).  Accumulators are (hi, lo) pairs like the reference's uint128.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void k_mul_coeffs_and_add128(const uint64_t *__restrict__ a, const uint64_t *__restrict__ b, ulonglong2 *__restrict__ acc,
+                                        size_t n) {
+    for (size_t j = blockIdx.x * (size_t)blockDim.x + threadIdx.x; j < n; j += (size_t)gridDim.x * blockDim.x) {
+        ulonglong2 z = acc[j];  // x = hi, y = lo (gwas/matmult.go:196-199)
+        u128 t{z.y, z.x};
+        mac128(t, a[j], b[j]);
+        acc[j] = make_ulonglong2(t.hi, t.lo);
+    }
+}
+__global__ void k_reduce_and_add128(const ulonglong2 *__restrict__ acc, uint64_t *__restrict__ out, LimbConst lc, size_t n) {
+    for (size_t j = blockIdx.x * (size_t)blockDim.x + threadIdx.x; j < n; j += (size_t)gridDim.x * blockDim.x) {
+        const ulonglong2 z = acc[j];
+        const uint64_t hhi = __umul64hi(z.y * lc.qinv, lc.q);
+        out[j] += z.x - hhi + lc.q;  // gwas/matmult.go:300-301 (not range-reduced)
+    }
+}
+__global__ void k_mform(uint64_t *__restrict__ p, int N, const LimbConst *__restrict__ lcs) {
+    const LimbConst lc = lcs[blockIdx.y];
+    uint64_t *a = p + (size_t)blockIdx.y * N;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < N; j += gridDim.x * blockDim.x) a[j] = mform(a[j], lc);
+}
+__global__ void k_mod_reduce(uint64_t *__restrict__ x, int L, int N, const LimbConst *__restrict__ lcs) {
+    const size_t poly = blockIdx.y;
+    const LimbConst lc = lcs[poly % L];
+    uint64_t *a = x + poly * (size_t)N;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < N; j += gridDim.x * blockDim.x) a[j] = bred_add(a[j], lc);
+}
+
+int launch_mul_coeffs_and_add128(Ctx *c, const uint64_t *a, const uint64_t *b, uint64_t *acc, size_t n, cudaStream_t st) {
+    const int blocks = (int)std::min<size_t>((n + 255) / 256, 148 * 8);
+    k_mul_coeffs_and_add128<<<blocks, 256, 0, st>>>(a, b, (ulonglong2 *)acc, n);
+    c->launches++;
+    SFG_CUDA(c, cudaGetLastError());
+    return 0;
+}
+int launch_reduce_and_add128(Ctx *c, const uint64_t *acc, uint64_t *out, int limb, size_t n, cudaStream_t st) {
+    const int blocks = (int)std::min<size_t>((n + 255) / 256, 148 * 8);
+    k_reduce_and_add128<<<blocks, 256, 0, st>>>((const ulonglong2 *)acc, out, c->lc_h[limb], n);
+    c->launches++;
+    SFG_CUDA(c, cudaGetLastError());
+    return 0;
+}
+int launch_mform(Ctx *c, uint64_t *p, int nlimbs, cudaStream_t st) {
+    dim3 g((c->N + 255) / 256, nlimbs);
+    k_mform<<<g, 256, 0, st>>>(p, c->N, c->lc);
+    c->launches++;
+    SFG_CUDA(c, cudaGetLastError());
+    return 0;
+}
+int launch_mod_reduce(Ctx *c, uint64_t *x, size_t npoly, int L, cudaStream_t st) {
+    const size_t maxy = 65535;
+    for (size_t off = 0; off < npoly; off += maxy - (maxy % L)) {
+        const size_t cnt = std::min(npoly - off, maxy - (maxy % L));
+        dim3 g((c->N + 255) / 256, (unsigned)cnt);
+        k_mod_reduce<<<g, 256, 0, st>>>(x + off * c->N, L, c->N, c->lc);
+        c->launches++;
+    }
+    SFG_CUDA(c, cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Genotype preparation: gwas/matmult.go:1289-1304 (missing -> 0, sum / sqSum before squaring, optional square).
+// One thread per 16 consecutive columns of a row slab; per-column partial sums are reduced over a slab of rows in
+// registers and flushed with one atomicAdd per (slab, column).  The sums are exact: every partial is a small integer.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void k_geno_prep(int8_t *__restrict__ X, size_t rows, size_t ncols, double *__restrict__ sum, double *__restrict__ sqsum,
+                            int square, int rows_per_slab) {
+    const size_t col = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= ncols) return;
+    const size_t r0 = (size_t)blockIdx.y * rows_per_slab;
+    const size_t r1 = r0 + rows_per_slab < rows ? r0 + rows_per_slab : rows;
+    long long s1 = 0, s2 = 0;
+    for (size_t r = r0; r < r1; r++) {
+        int8_t v = X[r * ncols + col];
+        if (v < 0) v = 0;
+        const int8_t v2 = (int8_t)(v * v);  // int8 arithmetic like the reference (row[rj]*row[rj])
+        s1 += v;
+        s2 += v2;
+        X[r * ncols + col] = square ? v2 : v;
+    }
+    if (sum) atomicAdd(&sum[col], (double)s1);
+    if (sqsum) atomicAdd(&sqsum[col], (double)s2);
+}
+
+int launch_geno_prep(Ctx *c, int8_t *X, size_t rows, size_t ncols, double *sum, double *sqsum, bool square, cudaStream_t st) {
+    if (rows == 0 || ncols == 0) return 0;
+    const int rows_per_slab = 256;
+    dim3 g((unsigned)((ncols + 255) / 256), (unsigned)((rows + rows_per_slab - 1) / rows_per_slab));
+    k_geno_prep<<<g, 256, 0, st>>>(X, rows, ncols, sum, sqsum, square ? 1 : 0, rows_per_slab);
+    c->launches++;
+    SFG_CUDA(c, cudaGetLastError());
+    return 0;
+}
+
+}  // namespace sfg

@@ -1,0 +1,571 @@
+// matmult.cu -- host orchestration of MatMult4StreamPreprocess / MatMult4StreamCompute / MatMult4Stream
+// (gwas/matmult.go:914-1505) on one GPU, and the block-row-sharded pieces used for multi-GPU runs.
+//
+// Reference control flow -> device schedule
+//   Preprocess : per block row, per active shift, per block column: GetDiag + EncodeNTT + MForm, written to disk.
+//                Here: one encode CTA per diagonal polynomial, written into a compact HBM cache (or regenerated per
+//                giant-step chunk when the cache would not fit the budget).
+//   Compute    : per block row: baby rotations of A (key-switch), then for every cached diagonal a 128-bit lazy MAC into
+//                acc[i][giant] under a mutex; afterwards per (i, giant): Montgomery reduce, giant rotation, Add into out.
+//                Here: (1) all baby rotations, batched per baby step over every (i, bi) that shares the Galois key;
+//                (2) ONE output-stationary MAC launch per giant chunk that streams the diagonals exactly once and
+//                emits canonical residues (K1+K2 fused); (3) giant rotations batched per giant step over every (i, bj),
+//                accumulated into out in place (K6+K7 fused).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "matmult.h"
+
+namespace sfg {
+
+thread_local float g_last_ms[4] = {0, 0, 0, 0};
+
+// ---------------------------------------------------------------------------------------------------------------
+// genotype matrix
+// ---------------------------------------------------------------------------------------------------------------
+int geno_create(Ctx *c, size_t nrows, size_t ncols, Geno **out) {
+    if (nrows == 0 || ncols == 0) SFG_FAIL(c, "empty genotype matrix (%zu x %zu)", nrows, ncols);
+    SFG_CUDA(c, cudaSetDevice(c->device));
+    Geno *g = new Geno();
+    g->c = c;
+    g->nrows = nrows;
+    g->ncols = ncols;
+    cudaError_t e = cudaMalloc(&g->d, nrows * ncols);
+    if (e != cudaSuccess) {
+        delete g;
+        SFG_FAIL(c, "cudaMalloc of %zu x %zu genotype matrix failed: %s", nrows, ncols, cudaGetErrorString(e));
+    }
+    *out = g;
+    return 0;
+}
+int geno_push(Geno *g, const int8_t *rows, size_t n) {
+    Ctx *c = g->c;
+    if (g->filled + n > g->nrows) SFG_FAIL(c, "geno_push: %zu rows pushed into a %zu-row matrix (already %zu)", n, g->nrows, g->filled);
+    SFG_CUDA(c, cudaSetDevice(c->device));
+    SFG_CUDA(c, cudaMemcpyAsync(g->d + g->filled * g->ncols, rows, n * g->ncols, cudaMemcpyHostToDevice, c->stream));
+    SFG_CUDA(c, cudaStreamSynchronize(c->stream));
+    g->filled += n;
+    return 0;
+}
+void geno_release(Geno *g) {
+    if (!g) return;
+    if (--g->refs == 0) {
+        cudaSetDevice(g->c->device);
+        cudaFree(g->d);
+        delete g;
+    }
+}
+
+// gwas/matmult.go:627-631 GetDiagBool for index = -shift
+static inline bool diag_exists(int r, int cdim, int slots, int shift) {
+    const int index = (slots - shift) % slots;
+    return (slots + 1 - r) <= index || index <= cdim - 1;
+}
+
+static int block_rows(const Cache *ca, int bi) {
+    return (int)std::min<size_t>((size_t)(bi + 1) * ca->slots, ca->nrows) - bi * ca->slots;
+}
+static int block_cols(const Cache *ca, int bj) {
+    return (int)std::min<size_t>((size_t)(bj + 1) * ca->slots, ca->ncols) - bj * ca->slots;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Preprocess (gwas/matmult.go:914-1041)
+// ---------------------------------------------------------------------------------------------------------------
+static int encode_jobs(Ctx *c, const Cache *ca, const std::vector<EncJob> &jobs, uint64_t *P) {
+    if (jobs.empty()) return 0;
+    Buf dj;
+    if (dj.alloc(c, jobs.size() * sizeof(EncJob))) return -1;
+    SFG_CUDA(c, cudaMemcpyAsync(dj.p, jobs.data(), jobs.size() * sizeof(EncJob), cudaMemcpyHostToDevice, c->stream));
+    const size_t chunk = 1 << 20;
+    for (size_t o = 0; o < jobs.size(); o += chunk) {
+        const int n = (int)std::min(chunk, jobs.size() - o);
+        if (launch_encode(c, ca->g->d, ca->ncols, dj.as<EncJob>() + o, n, ca->L, true, P, nullptr, c->stream)) return -1;
+    }
+    SFG_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int cache_build(Ctx *c, Geno *g, int maxLevel, Cache **out) {
+    if (g->filled != g->nrows) SFG_FAIL(c, "genotype matrix incomplete: %zu of %zu rows pushed", g->filled, g->nrows);
+    if (maxLevel < 1 || maxLevel > c->nQ - 1) SFG_FAIL(c, "maxLevel %d needs %d Q limbs, parameters have %d", maxLevel, maxLevel + 1, c->nQ);
+    SFG_CUDA(c, cudaSetDevice(c->device));
+    Cache *ca = new Cache();
+    ca->c = c;
+    ca->g = g;
+    g->refs++;
+    ca->maxLevel = maxLevel;
+    ca->L = maxLevel;  // limb-COUNT quirk: accumulators cover limbs 0..maxLevel-1 (gwas/matmult.go:1125 -> :231, App. A.4)
+    ca->slots = c->slots;
+    ca->d = c->d;
+    ca->nrows = g->nrows;
+    ca->ncols = g->ncols;
+    ca->m_ct = (int)((g->ncols - 1) / c->slots) + 1;   // matmult.go:920
+    ca->nbr = (int)((g->nrows - 1) / c->slots) + 1;    // matmult.go:921
+    const int slots = ca->slots, d = ca->d, m_ct = ca->m_ct, nbr = ca->nbr;
+    ca->baby.assign((size_t)nbr * d, 0);
+    ca->giant.assign((size_t)nbr * d, 0);
+    ca->shiftT.assign((size_t)nbr * slots, 0);
+    ca->pidx.assign((size_t)nbr * slots * m_ct, -1);
+    const size_t LN = (size_t)ca->L * c->N;
+    size_t npoly = 0;
+    for (int bi = 0; bi < nbr; bi++) {
+        const int nr = block_rows(ca, bi);
+        for (int shift = 0; shift < slots; shift++) {
+            bool any = false;
+            for (int bj = 0; bj < m_ct; bj++) {
+                if (diag_exists(nr, block_cols(ca, bj), slots, shift)) {
+                    any = true;
+                    ca->pidx[((size_t)bi * slots + shift) * m_ct + bj] = (long long)(npoly++ * LN);
+                }
+            }
+            if (any) {  // matmult.go:962-974
+                ca->baby[(size_t)bi * d + shift % d] = 1;
+                ca->giant[(size_t)bi * d + shift / d] = 1;
+                ca->shiftT[(size_t)bi * slots + shift] = 1;
+            }
+        }
+    }
+    ca->npoly = npoly;
+    ca->kidx.assign((size_t)nbr * d, -1);
+    for (int bi = 0; bi < nbr; bi++)
+        for (int b = 0; b < d; b++)
+            if (ca->baby[(size_t)bi * d + b]) {
+                ca->kidx[(size_t)bi * d + b] = (int)ca->kbi.size();
+                ca->kbi.push_back(bi);
+                ca->kb.push_back(b);
+            }
+    for (int gi = 0; gi < d; gi++) {
+        bool any = false;
+        for (int bi = 0; bi < nbr; bi++) any |= ca->giant[(size_t)bi * d + gi] != 0;
+        if (any) ca->gact.push_back(gi);
+    }
+    // materialise if it fits the budget
+    size_t budget = c->cache_budget;
+    if (budget == 0) {
+        size_t fr = 0, tot = 0;
+        SFG_CUDA(c, cudaMemGetInfo(&fr, &tot));
+        budget = (size_t)(0.70 * (double)fr);
+    }
+    const size_t bytes = npoly * LN * sizeof(uint64_t);
+    if (bytes <= budget) {
+        cudaError_t e = cudaMalloc(&ca->P, bytes);
+        if (e == cudaSuccess) {
+            std::vector<EncJob> jobs;
+            jobs.reserve(npoly);
+            for (int bi = 0; bi < nbr; bi++)
+                for (int shift = 0; shift < slots; shift++)
+                    for (int bj = 0; bj < m_ct; bj++) {
+                        const long long po = ca->pidx[((size_t)bi * slots + shift) * m_ct + bj];
+                        if (po < 0) continue;
+                        // EncodeDiagWithEncoder(blockVec, -shift, d*giant, maxLevel, enc)  matmult.go:1024
+                        jobs.push_back(EncJob{bi * slots, bj * slots, block_rows(ca, bi), block_cols(ca, bj), shift, d * (shift / d), po});
+                    }
+            if (encode_jobs(c, ca, jobs, ca->P)) {
+                cache_destroy(ca);
+                return -1;
+            }
+            ca->materialised = true;
+        } else {
+            cudaGetLastError();
+        }
+    }
+    *out = ca;
+    return 0;
+}
+
+void cache_destroy(Cache *ca) {
+    if (!ca) return;
+    cudaSetDevice(ca->c->device);
+    cudaFree(ca->P);
+    geno_release(ca->g);
+    delete ca;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// helpers
+// ---------------------------------------------------------------------------------------------------------------
+static int find_key(Ctx *c, int rot_left, const GaloisKey **out) {
+    const uint64_t galEl = h_galois_element(c->logN, rot_left);
+    std::lock_guard<std::mutex> g(c->mu);
+    auto it = c->keys.find(galEl);
+    if (it == c->keys.end()) SFG_FAIL(c, "rotation key for left rotation by %d (galEl %llu) not loaded", rot_left, (unsigned long long)galEl);
+    *out = &it->second;
+    return 0;
+}
+
+struct Scratch {
+    Buf c2, acc, offs;
+    int cap = 0;
+    int ensure(Ctx *c, int nct, int nl) {
+        if (nct <= cap) return 0;
+        const size_t N = c->N;
+        if (c2.alloc(c, (size_t)nct * nl * N * 8)) return -1;
+        if (acc.alloc(c, (size_t)nct * 2 * (nl + c->nP) * N * 8)) return -1;
+        cap = nct;
+        return 0;
+    }
+};
+
+struct PhaseTimer {
+    std::vector<cudaEvent_t> ev;
+    std::vector<int> phase;
+    cudaStream_t st;
+    explicit PhaseTimer(cudaStream_t s) : st(s) {}
+    void mark(int ph) {  // ph = phase that STARTS here (-1 = end)
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, st);
+        ev.push_back(e);
+        phase.push_back(ph);
+    }
+    void finish(float out[4]) {
+        out[0] = out[1] = out[2] = out[3] = 0;
+        if (ev.empty()) return;
+        cudaEventSynchronize(ev.back());
+        for (size_t i = 0; i + 1 < ev.size(); i++) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+            if (phase[i] >= 0 && phase[i] < 3) out[phase[i]] += ms;
+        }
+        cudaEventElapsedTime(&out[3], ev.front(), ev.back());
+        for (auto e : ev) cudaEventDestroy(e);
+        ev.clear();
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// (1) baby-step rotation cache  R[k][row = 2i+c][l < L][N]  for the K entries whose block row is in [bi_lo, bi_hi)
+//     gwas/matmult.go:1083-1119 : rotCache[i][baby] = RotateRightWithEvaluator(A[i][bi], -baby)
+// ---------------------------------------------------------------------------------------------------------------
+static int build_rot_cache(Ctx *c, const Cache *ca, const uint64_t *d_A, int s, int levelA, int bi_lo, int bi_hi,
+                           std::vector<int> &klist, Buf &R, Scratch &scr) {
+    const int d = ca->d, nbr = ca->nbr, L = ca->L, N = c->N, nlA = levelA + 1, nrows = 2 * s;
+    klist.clear();
+    std::vector<int> klocal((size_t)nbr * d, -1);
+    for (size_t k = 0; k < ca->kbi.size(); k++)
+        if (ca->kbi[k] >= bi_lo && ca->kbi[k] < bi_hi) {
+            klocal[(size_t)ca->kbi[k] * d + ca->kb[k]] = (int)klist.size();
+            klist.push_back((int)k);
+        }
+    const size_t LN = (size_t)L * N;
+    if (R.alloc(c, klist.size() * nrows * LN * 8)) return -1;
+    const size_t ctA = (size_t)2 * nlA * N;
+    // offsets for every batch, uploaded once
+    struct Batch { int b, nct; long long first, stride; size_t off_pos; };
+    std::vector<Batch> batches;
+    std::vector<long long> offs;
+    for (int b = 0; b < d; b++) {
+        std::vector<int> bis;
+        for (int bi = bi_lo; bi < bi_hi; bi++)
+            if (ca->baby[(size_t)bi * d + b]) bis.push_back(bi);
+        if (bis.empty()) continue;
+        if ((int)bis.size() == nbr) {  // every block row: one batch over all (i, bi), cts are contiguous in A
+            Batch bt{b, s * nbr, 0, (long long)ctA, offs.size()};
+            for (int t = 0; t < s * nbr; t++) offs.push_back((long long)t * ctA);
+            for (int t = 0; t < s * nbr; t++) {
+                const int i = t / nbr, bi = t % nbr;
+                offs.push_back((long long)(((size_t)klocal[(size_t)bi * d + b] * nrows + 2 * i) * LN));
+            }
+            batches.push_back(bt);
+        } else {
+            for (int bi : bis) {
+                Batch bt{b, s, (long long)(bi * ctA), (long long)(nbr * ctA), offs.size()};
+                for (int i = 0; i < s; i++) offs.push_back((long long)(((size_t)i * nbr + bi) * ctA));
+                for (int i = 0; i < s; i++) offs.push_back((long long)(((size_t)klocal[(size_t)bi * d + b] * nrows + 2 * i) * LN));
+                batches.push_back(bt);
+            }
+        }
+    }
+    if (scr.offs.alloc(c, std::max<size_t>(offs.size(), 1) * sizeof(long long))) return -1;
+    SFG_CUDA(c, cudaMemcpyAsync(scr.offs.p, offs.data(), offs.size() * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
+    if (scr.ensure(c, s * nbr, ca->maxLevel + 1)) return -1;
+    for (const Batch &bt : batches) {
+        KsBatch kb;
+        kb.level = ca->maxLevel;  // A is dropped to maxLevel: only limbs 0..maxLevel are read (crypto/basics.go:806-824)
+        kb.nct = bt.nct;
+        kb.in = d_A;
+        kb.in_off = scr.offs.as<long long>() + bt.off_pos;
+        kb.in_first = bt.first;
+        kb.in_stride = bt.stride;
+        kb.in_nl = nlA;
+        kb.out = R.as<uint64_t>();
+        kb.out_off = scr.offs.as<long long>() + bt.off_pos + bt.nct;
+        kb.out_nl = L;
+        kb.out_limbs = L;  // limb index maxLevel of the rotated ct is never read by the MAC (App. A.4)
+        kb.accumulate = false;
+        kb.c2 = scr.c2.as<uint64_t>();
+        kb.acc = scr.acc.as<uint64_t>();
+        if (bt.b == 0) {
+            if (launch_copy_add(c, kb, c->stream)) return -1;
+        } else {
+            const GaloisKey *key;
+            if (find_key(c, bt.b, &key)) return -1;
+            if (launch_rotate(c, kb, *key, c->stream)) return -1;
+        }
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// (2) MAC for the giant steps gact[gi_lo .. gi_hi) -> d_cv [(gi-gi_lo)*m_ct + bj][row][l][N]
+//     gwas/matmult.go:1154-1168 (CPMultAccWithoutMRedV2) + :1203 (ModularReduceV2)
+// ---------------------------------------------------------------------------------------------------------------
+static int run_mac(Ctx *c, const Cache *ca, const uint64_t *R, const std::vector<int> &klist, int s, int gi_lo, int gi_hi,
+                   uint64_t *d_cv) {
+    const int d = ca->d, m_ct = ca->m_ct, slots = ca->slots, L = ca->L, N = c->N;
+    const int K = (int)klist.size(), ncols = (gi_hi - gi_lo) * m_ct;
+    if (K == 0 || ncols == 0) return 0;
+    const size_t LN = (size_t)L * N;
+    std::vector<long long> poff((size_t)ncols * K, -1);
+    std::vector<EncJob> jobs;  // only when the cache is not materialised
+    size_t ntmp = 0;
+    for (int gi = gi_lo; gi < gi_hi; gi++) {
+        const int g = ca->gact[gi];
+        for (int bj = 0; bj < m_ct; bj++) {
+            const size_t col = (size_t)(gi - gi_lo) * m_ct + bj;
+            for (int kk = 0; kk < K; kk++) {
+                const int bi = ca->kbi[klist[kk]], b = ca->kb[klist[kk]];
+                const int shift = g * d + b;
+                if (shift >= slots) continue;
+                const long long po = ca->pidx[((size_t)bi * slots + shift) * m_ct + bj];
+                if (po < 0) continue;
+                if (ca->materialised) {
+                    poff[col * K + kk] = po;
+                } else {
+                    poff[col * K + kk] = (long long)(ntmp * LN);
+                    jobs.push_back(EncJob{bi * slots, bj * slots, block_rows(ca, bi), block_cols(ca, bj), shift, d * g, (long long)(ntmp * LN)});
+                    ntmp++;
+                }
+            }
+        }
+    }
+    Buf dpoff, tmpP;
+    if (dpoff.alloc(c, poff.size() * sizeof(long long))) return -1;
+    SFG_CUDA(c, cudaMemcpyAsync(dpoff.p, poff.data(), poff.size() * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
+    const uint64_t *P = ca->P;
+    if (!ca->materialised) {
+        if (tmpP.alloc(c, std::max<size_t>(ntmp, 1) * LN * 8)) return -1;
+        if (encode_jobs(c, ca, jobs, tmpP.as<uint64_t>())) return -1;
+        P = tmpP.as<uint64_t>();
+    }
+    if (launch_mac(c, R, P, dpoff.as<long long>(), K, 2 * s, ncols, L, d_cv, c->stream)) return -1;
+    SFG_CUDA(c, cudaStreamSynchronize(c->stream));  // poff / tmpP are freed on return
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// (3) giant-step alignment + accumulation (gwas/matmult.go:1203-1227):
+//     out[i][bj] += RotateRightWithEvaluator(cv[i][g][bj], -g*d)   for g in gact[gi_lo .. gi_hi)
+// ---------------------------------------------------------------------------------------------------------------
+static int run_giant(Ctx *c, const Cache *ca, int s, const uint64_t *d_cv, int gi_lo, int gi_hi, uint64_t *d_out, Scratch &scr) {
+    const int d = ca->d, m_ct = ca->m_ct, L = ca->L, N = c->N, nrows = 2 * s;
+    const size_t LN = (size_t)L * N;
+    const int nct = m_ct * s;
+    if (gi_hi <= gi_lo) return 0;
+    std::vector<long long> offs;
+    for (int gi = gi_lo; gi < gi_hi; gi++) {
+        for (int t = 0; t < nct; t++) {  // t = bj*s + i : consecutive ciphertexts of the cv image
+            const int bj = t / s, i = t % s;
+            offs.push_back((long long)((((size_t)(gi - gi_lo) * m_ct + bj) * nrows + 2 * i) * LN));
+        }
+    }
+    const size_t out_pos = offs.size();
+    for (int t = 0; t < nct; t++) {
+        const int bj = t / s, i = t % s;
+        offs.push_back((long long)(((size_t)i * m_ct + bj) * 2 * LN));
+    }
+    Buf doffs;
+    if (doffs.alloc(c, offs.size() * sizeof(long long))) return -1;
+    SFG_CUDA(c, cudaMemcpyAsync(doffs.p, offs.data(), offs.size() * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
+    if (scr.ensure(c, nct, L)) return -1;
+    for (int gi = gi_lo; gi < gi_hi; gi++) {
+        const int g = ca->gact[gi];
+        KsBatch kb;
+        kb.level = L - 1;  // ModularReduceV2 creates the ct at level len(acc0)-1 (gwas/matmult.go:350)
+        kb.nct = nct;
+        kb.in = d_cv;
+        kb.in_off = doffs.as<long long>() + (size_t)(gi - gi_lo) * nct;
+        kb.in_first = offs[(size_t)(gi - gi_lo) * nct];
+        kb.in_stride = (long long)(2 * LN);
+        kb.in_nl = L;
+        kb.out = d_out;
+        kb.out_off = doffs.as<long long>() + out_pos;
+        kb.out_nl = L;
+        kb.out_limbs = L;
+        kb.accumulate = true;
+        kb.c2 = scr.c2.as<uint64_t>();
+        kb.acc = scr.acc.as<uint64_t>();
+        if (g == 0) {
+            if (launch_copy_add(c, kb, c->stream)) return -1;
+        } else {
+            const GaloisKey *key;
+            if (find_key(c, (g * d) % ca->slots, &key)) return -1;
+            if (launch_rotate(c, kb, *key, c->stream)) return -1;
+        }
+    }
+    SFG_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+static int check_args(Ctx *c, const Cache *ca, int s, int nbr, int levelA, int maxLevel) {
+    if (s < 1) SFG_FAIL(c, "A has no rows");
+    if (s > 16) SFG_FAIL(c, "s = %d ciphertext rows: at most 16 per call (split A)", s);
+    if (nbr != ca->nbr) SFG_FAIL(c, "A has %d block rows but the genotype matrix has %d", nbr, ca->nbr);
+    if (maxLevel != ca->maxLevel) SFG_FAIL(c, "maxLevel %d differs from the cache's %d", maxLevel, ca->maxLevel);
+    if (levelA < maxLevel) SFG_FAIL(c, "DropLevel: requested level %d when input is %d", maxLevel, levelA);  // crypto/basics.go:817
+    if (levelA > c->nQ - 1) SFG_FAIL(c, "input level %d exceeds the parameter chain", levelA);
+    return 0;
+}
+
+int mm_compute_dev(Ctx *c, const uint64_t *d_A, int s, int nbr, int levelA, int maxLevel, Cache *ca, uint64_t *d_out) {
+    if (check_args(c, ca, s, nbr, levelA, maxLevel)) return -1;
+    SFG_CUDA(c, cudaSetDevice(c->device));
+    const int L = ca->L, N = c->N, m_ct = ca->m_ct;
+    const size_t LN = (size_t)L * N;
+    PhaseTimer tm(c->stream);
+    Scratch scr;
+    Buf R;
+    std::vector<int> klist;
+    tm.mark(0);
+    if (build_rot_cache(c, ca, d_A, s, levelA, 0, nbr, klist, R, scr)) return -1;
+    SFG_CUDA(c, cudaMemsetAsync(d_out, 0, (size_t)s * m_ct * 2 * LN * 8, c->stream));
+    // giant chunks bounded by the cv image size (default 24 GiB)
+    const size_t per_g = (size_t)m_ct * 2 * s * LN * 8;
+    size_t fr = 0, tot = 0;
+    SFG_CUDA(c, cudaMemGetInfo(&fr, &tot));
+    size_t cv_budget = std::min<size_t>((size_t)24 << 30, fr / 3);
+    int gchunk = (int)std::max<size_t>(1, cv_budget / per_g);
+    const int ng = (int)ca->gact.size();
+    gchunk = std::min(gchunk, ng);
+    Buf cv;
+    if (cv.alloc(c, (size_t)gchunk * per_g)) return -1;
+    for (int g0 = 0; g0 < ng; g0 += gchunk) {
+        const int g1 = std::min(ng, g0 + gchunk);
+        tm.mark(1);
+        if (run_mac(c, ca, R.as<uint64_t>(), klist, s, g0, g1, cv.as<uint64_t>())) return -1;
+        tm.mark(2);
+        if (run_giant(c, ca, s, cv.as<uint64_t>(), g0, g1, d_out, scr)) return -1;
+    }
+    tm.mark(-1);
+    tm.finish(g_last_ms);
+    SFG_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int mm_partial_dev(Ctx *c, const uint64_t *d_A, int s, int nbr, int levelA, int maxLevel, Cache *ca, int bi_lo, int bi_hi,
+                   uint64_t *d_cv) {
+    if (check_args(c, ca, s, nbr, levelA, maxLevel)) return -1;
+    if (bi_lo < 0 || bi_hi > nbr || bi_lo > bi_hi) SFG_FAIL(c, "block-row range [%d, %d) out of [0, %d)", bi_lo, bi_hi, nbr);
+    SFG_CUDA(c, cudaSetDevice(c->device));
+    const size_t LN = (size_t)ca->L * c->N;
+    const size_t total = ca->gact.size() * (size_t)ca->m_ct * 2 * s * LN;
+    PhaseTimer tm(c->stream);
+    Scratch scr;
+    Buf R;
+    std::vector<int> klist;
+    tm.mark(0);
+    if (build_rot_cache(c, ca, d_A, s, levelA, bi_lo, bi_hi, klist, R, scr)) return -1;
+    tm.mark(1);
+    if (klist.empty()) {
+        SFG_CUDA(c, cudaMemsetAsync(d_cv, 0, total * 8, c->stream));
+    } else if (run_mac(c, ca, R.as<uint64_t>(), klist, s, 0, (int)ca->gact.size(), d_cv)) {
+        return -1;
+    }
+    tm.mark(-1);
+    tm.finish(g_last_ms);
+    SFG_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int mm_finish_dev(Ctx *c, Cache *ca, int s, int maxLevel, const uint64_t *d_cv, int g_lo, int g_hi, uint64_t *d_out) {
+    if (maxLevel != ca->maxLevel) SFG_FAIL(c, "maxLevel mismatch");
+    const int ng = (int)ca->gact.size();
+    if (g_lo < 0 || g_hi > ng || g_lo > g_hi) SFG_FAIL(c, "giant range [%d, %d) out of [0, %d)", g_lo, g_hi, ng);
+    SFG_CUDA(c, cudaSetDevice(c->device));
+    const size_t LN = (size_t)ca->L * c->N;
+    PhaseTimer tm(c->stream);
+    Scratch scr;
+    SFG_CUDA(c, cudaMemsetAsync(d_out, 0, (size_t)s * ca->m_ct * 2 * LN * 8, c->stream));
+    tm.mark(2);
+    const size_t per_g = (size_t)ca->m_ct * 2 * s * LN;
+    if (run_giant(c, ca, s, d_cv + (size_t)g_lo * per_g, g_lo, g_hi, d_out, scr)) return -1;
+    tm.mark(-1);
+    tm.finish(g_last_ms);
+    return 0;
+}
+
+// crypto/basics.go:201-210
+int rotate_right_dev(Ctx *c, int level, const uint64_t *d_in, int nct, int nrot, uint64_t *d_out) {
+    SFG_CUDA(c, cudaSetDevice(c->device));
+    const int slots = c->slots, N = c->N, nl = level + 1;
+    nrot %= slots;
+    if (nrot < 0) nrot += slots;
+    const size_t ct = (size_t)2 * nl * N;
+    std::vector<long long> offs(nct);
+    for (int t = 0; t < nct; t++) offs[t] = (long long)(t * ct);
+    Buf doffs;
+    if (doffs.alloc(c, std::max(1, nct) * sizeof(long long))) return -1;
+    SFG_CUDA(c, cudaMemcpyAsync(doffs.p, offs.data(), nct * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
+    Scratch scr;
+    if (scr.ensure(c, nct, nl)) return -1;
+    KsBatch kb;
+    kb.level = level;
+    kb.nct = nct;
+    kb.in = d_in;
+    kb.in_off = doffs.as<long long>();
+    kb.in_first = 0;
+    kb.in_stride = (long long)ct;
+    kb.in_nl = nl;
+    kb.out = d_out;
+    kb.out_off = doffs.as<long long>();
+    kb.out_nl = nl;
+    kb.out_limbs = nl;
+    kb.accumulate = false;
+    kb.c2 = scr.c2.as<uint64_t>();
+    kb.acc = scr.acc.as<uint64_t>();
+    if (nrot == 0) {
+        if (launch_copy_add(c, kb, c->stream)) return -1;
+    } else {
+        const GaloisKey *key;
+        if (find_key(c, slots - nrot, &key)) return -1;  // RotateNew(ct, slots - nrot): left rotation
+        if (launch_rotate(c, kb, *key, c->stream)) return -1;
+    }
+    SFG_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int encode_diag_host(Ctx *c, const Geno *g, int bi, int shift, int nrot, int level, bool mont, uint64_t *out, uint8_t *present,
+                     int64_t *coeffs) {
+    SFG_CUDA(c, cudaSetDevice(c->device));
+    const int slots = c->slots, N = c->N, nl = level + 1;
+    const int m_ct = (int)((g->ncols - 1) / slots) + 1, nbr = (int)((g->nrows - 1) / slots) + 1;
+    if (bi < 0 || bi >= nbr || shift < 0 || shift >= slots) SFG_FAIL(c, "encode_diag: block row %d / shift %d out of range", bi, shift);
+    if (level < 0 || level >= c->nQ) SFG_FAIL(c, "encode_diag: level %d out of range", level);
+    const int nr = (int)std::min<size_t>((size_t)(bi + 1) * slots, g->nrows) - bi * slots;
+    std::vector<EncJob> jobs;
+    std::vector<int> which;
+    for (int bj = 0; bj < m_ct; bj++) {
+        const int nc = (int)std::min<size_t>((size_t)(bj + 1) * slots, g->ncols) - bj * slots;
+        present[bj] = diag_exists(nr, nc, slots, shift) ? 1 : 0;
+        if (present[bj]) {
+            jobs.push_back(EncJob{bi * slots, bj * slots, nr, nc, shift, ((nrot % slots) + slots) % slots, (long long)(jobs.size() * (size_t)nl * N)});
+            which.push_back(bj);
+        }
+    }
+    if (jobs.empty()) return 0;
+    Buf dj, dout, dco;
+    if (dj.alloc(c, jobs.size() * sizeof(EncJob)) || dout.alloc(c, jobs.size() * (size_t)nl * N * 8)) return -1;
+    if (coeffs && dco.alloc(c, jobs.size() * (size_t)N * 8)) return -1;
+    SFG_CUDA(c, cudaMemcpyAsync(dj.p, jobs.data(), jobs.size() * sizeof(EncJob), cudaMemcpyHostToDevice, c->stream));
+    if (launch_encode(c, g->d, g->ncols, dj.as<EncJob>(), (int)jobs.size(), nl, mont, dout.as<uint64_t>(), coeffs ? dco.as<long long>() : nullptr, c->stream)) return -1;
+    SFG_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (size_t k = 0; k < jobs.size(); k++) {
+        SFG_CUDA(c, cudaMemcpy(out + (size_t)which[k] * nl * N, dout.as<uint64_t>() + k * (size_t)nl * N, (size_t)nl * N * 8, cudaMemcpyDeviceToHost));
+        if (coeffs) SFG_CUDA(c, cudaMemcpy(coeffs + (size_t)which[k] * N, dco.as<long long>() + k * (size_t)N, (size_t)N * 8, cudaMemcpyDeviceToHost));
+    }
+    return 0;
+}
+
+}  // namespace sfg

@@ -1,0 +1,73 @@
+// matmult.h -- host-side orchestration of the stream MatMult entry points (gwas/matmult.go:914-1505).
+#pragma once
+#include <atomic>
+#include <vector>
+
+#include "kernels.h"
+
+namespace sfg {
+
+struct Geno {
+    Ctx *c = nullptr;
+    size_t nrows = 0, ncols = 0, filled = 0;
+    int8_t *d = nullptr;  // device, row-major nrows x ncols
+    std::atomic<int> refs{1};
+};
+
+struct Cache {
+    Ctx *c = nullptr;
+    Geno *g = nullptr;            // retained (needed when diagonals are regenerated on the fly)
+    bool own_geno_copy = false;
+    int maxLevel = 0, L = 0;      // L = maxLevel limbs are used by the MAC
+    int slots = 0, d = 0, m_ct = 0, nbr = 0;
+    size_t nrows = 0, ncols = 0;
+    std::vector<uint8_t> baby, giant, shiftT;  // [nbr][d], [nbr][d], [nbr][slots]   (matmult.go:962-974)
+    bool materialised = false;
+    uint64_t *P = nullptr;        // device compact [npoly][L][N], NTT + Montgomery form
+    size_t npoly = 0;
+    std::vector<long long> pidx;  // host [(bi*slots+shift)*m_ct+bj] -> element offset into P or -1 (nil, matmult.go:703-705)
+    // K list: (bi, b) pairs with an active baby step, in (bi, b) order; kidx[bi*d+b] -> k or -1
+    std::vector<int> kbi, kb, kidx;
+    std::vector<int> gact;        // active giant indices (any block row)
+};
+
+struct Buf {  // RAII device buffer
+    void *p = nullptr;
+    size_t bytes = 0;
+    ~Buf() { release(); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+    }
+    int alloc(Ctx *c, size_t n) {
+        release();
+        if (n == 0) n = 16;
+        SFG_CUDA(c, cudaMalloc(&p, n));
+        bytes = n;
+        return 0;
+    }
+    template <typename T>
+    T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+int geno_create(Ctx *c, size_t nrows, size_t ncols, Geno **out);
+int geno_push(Geno *g, const int8_t *rows, size_t n);
+void geno_release(Geno *g);
+
+int cache_build(Ctx *c, Geno *g, int maxLevel, Cache **out);
+void cache_destroy(Cache *cache);
+
+// full single-GPU compute: d_A device [s][nbr][2][nlA][N] -> d_out device [s][m_ct][2][L][N]
+int mm_compute_dev(Ctx *c, const uint64_t *d_A, int s, int nbr, int levelA, int maxLevel, Cache *cache, uint64_t *d_out);
+// multi-GPU pieces
+int mm_partial_dev(Ctx *c, const uint64_t *d_A, int s, int nbr, int levelA, int maxLevel, Cache *cache, int bi_lo, int bi_hi,
+                   uint64_t *d_cv);
+int mm_finish_dev(Ctx *c, Cache *cache, int s, int maxLevel, const uint64_t *d_cv, int g_lo, int g_hi, uint64_t *d_out);
+int rotate_right_dev(Ctx *c, int level, const uint64_t *d_in, int nct, int nrot, uint64_t *d_out);
+int encode_diag_host(Ctx *c, const Geno *g, int bi, int shift, int nrot, int level, bool mont, uint64_t *out, uint8_t *present,
+                     int64_t *coeffs);
+
+extern thread_local float g_last_ms[4];
+
+}  // namespace sfg

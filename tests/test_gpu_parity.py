@@ -1,0 +1,434 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (sfgwas_b200.gwas mirrors the Go entry points), against the
+CPU oracle on the same seeded inputs, and against the committed golden vectors.  Integer work must be BIT-EXACT."""
+import hashlib
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def load(name):
+    with open(os.path.join(G, name + ".json")) as f:
+        return json.load(f)
+
+
+def sha(xs):
+    h = hashlib.sha256()
+    for x in xs:
+        h.update(int(x).to_bytes(8, "little"))
+    return h.hexdigest()
+
+
+def u64(xs):
+    return np.array(xs, dtype=np.uint64)
+
+
+def make(params):
+    from oracle.oracle import Oracle
+    from sfgwas_b200 import CryptoParams
+
+    o = Oracle.from_params(params)
+    cps = CryptoParams(params["logN"], params["Q"], params["P"], params["scale"])
+    return o, cps
+
+
+@pytest.fixture(scope="module")
+def small13():
+    from oracle.oracle import small_params
+
+    o, cps = make(small_params(8, "pn13"))
+    sk = o.keygen_secret(1)
+    keys = o.gen_bsgs_keys(sk)
+    cps.SetRotKeys(keys)
+    return o, cps, sk, keys
+
+
+@pytest.fixture(scope="module")
+def small14():
+    from oracle.oracle import small_params
+
+    o, cps = make(small_params(9, "pn14"))
+    sk = o.keygen_secret(1)
+    keys = o.gen_bsgs_keys(sk)
+    cps.SetRotKeys(keys)
+    return o, cps, sk, keys
+
+
+# ---- K1 / K2 / K3 ----------------------------------------------------------------------------------------------------
+def test_k1_k2_k3_golden():
+    from sfgwas_b200 import CryptoParams
+
+    cases = load("primitives")["cases"]
+    for case in cases:
+        q = case["q"]
+        # a context whose modulus 0 is q (any NTT-friendly logN that divides q-1)
+        logN = 8
+        cps = CryptoParams(logN, [q], [0x800004001 if q != 0x800004001 else 0x1FFFEC001], 2.0 ** 30)
+        a, b = u64(case["a"]), u64(case["b"])
+        acc = u64(case["acc_in"])
+        cps.MulCoeffsAndAdd128(a, b, acc)
+        assert acc.tolist() == case["acc_out"]
+        out = u64(case["red_in"])
+        cps.ReduceAndAddUint128(acc, out, 0)
+        assert out.tolist() == case["red_out"]
+        p = np.zeros((1, cps.N), dtype=np.uint64)
+        p[0, : len(case["a"])] = a
+        assert cps.MFormLvl(0, p)[0, : len(case["a"])].tolist() == case["mform"]
+        cps.close()
+
+
+def test_k1_k2_vs_oracle_random(small13):
+    o, cps, _, _ = small13
+    rng = np.random.default_rng(0)
+    n = 4096
+    for limb in (0, 1, o.nQ):
+        q = o.moduli[limb]
+        a = rng.integers(0, q, n, dtype=np.uint64)
+        b = rng.integers(0, q, n, dtype=np.uint64)
+        acc_g = rng.integers(0, 1 << 63, (n, 2), dtype=np.uint64) * np.uint64(2) + np.uint64(1)
+        acc_o = acc_g.copy()
+        for _ in range(3):
+            cps.MulCoeffsAndAdd128(a, b, acc_g)
+            o.mul_coeffs_and_add128(a, b, acc_o)
+        assert (acc_g == acc_o).all()
+        out_g = rng.integers(0, q, n, dtype=np.uint64)
+        out_o = out_g.copy()
+        cps.ReduceAndAddUint128(acc_g, out_g, limb)
+        o.reduce_and_add_uint128(acc_o, out_o, limb)
+        assert (out_g == out_o).all()
+
+
+# ---- NTT -------------------------------------------------------------------------------------------------------------
+def test_ntt_golden():
+    from sfgwas_b200 import CryptoParams
+
+    by_logn = {}
+    for case in load("ntt")["cases"]:
+        by_logn.setdefault(case["logN"], []).append(case)
+    for logN, cases in by_logn.items():
+        qs = [c["q"] for c in cases]
+        cps = CryptoParams(logN, qs[:-1] if len(qs) > 1 else qs, qs[-1:], 2.0 ** 30)
+        assert cps.psi() == [c["psi"] for c in cases]
+        for idx, c in enumerate(cases):
+            q = c["q"]
+            if "input" in c:
+                a = u64(c["input"])
+            else:
+                r2 = random.Random(c["seed"])
+                a = u64([r2.randrange(q) for _ in range(1 << logN)])
+            A = cps.NTT(a[None], [idx])[0]
+            assert A[:8].tolist() == c["first"]
+            assert sha(A.tolist()) == c["sha256"]
+            assert (cps.NTT(A[None], [idx], inverse=True)[0] == a).all()
+        cps.close()
+
+
+@pytest.mark.parametrize("logN", [6, 10, 12, 13, 14, 15, 16])
+def test_ntt_vs_oracle_all_sizes(logN):
+    from oracle.oracle import gen_primes
+
+    qs = gen_primes(logN, 45, 2) + gen_primes(logN, 30, 1)
+    ps = gen_primes(logN, 55, 1)
+    o, cps = make(dict(logN=logN, Q=qs, P=ps, scale=2.0 ** 30))
+    rng = np.random.default_rng(logN)
+    polys = np.stack([rng.integers(0, m, o.N, dtype=np.uint64) for m in o.moduli] * 2)  # 2 groups of nQP limbs
+    got = cps.NTT(polys, list(range(o.nQP)))
+    want = np.stack([o.ntt(i % o.nQP, polys[i]) for i in range(polys.shape[0])])
+    assert (got == want).all()
+    back = cps.NTT(got, list(range(o.nQP)), inverse=True)
+    assert (back == polys).all()
+    cps.close()
+
+
+# ---- encoder ---------------------------------------------------------------------------------------------------------
+def test_encode_golden_small():
+    from oracle.oracle import small_params
+    from sfgwas_b200 import CryptoParams, GenoFileStream
+
+    for case in load("encode")["cases"]:
+        if "values" not in case or case["logN"] < 8:
+            continue
+        logN = case["logN"]
+        p = small_params(logN, "pn13")
+        cps = CryptoParams(logN, p["Q"], p["P"], case["scale"])
+        n = cps.slots
+        v = np.array(case["values"], dtype=np.int8)
+        # a slots x slots block whose main diagonal (shift 0) is v
+        X = np.zeros((n, n), dtype=np.int8)
+        X[np.arange(n), np.arange(n)] = v
+        g = GenoFileStream.from_matrix(cps, X)
+        _, present, co = g.EncodeDiag(0, 0, case["nrot"], 5, mont=False, want_coeffs=True)
+        assert present.all()
+        assert co[0].tolist() == case["coeffs"]
+        cps.close()
+
+
+@pytest.mark.parametrize("name,nshift", [("PN13QP218", 6), ("PN14QP438", 3)])
+def test_encode_vs_oracle_real_params(name, nshift):
+    """Plaintext diagonals at the real parameter sets: bit-exact against the quad-precision oracle (and, on a few
+    coefficients, against the 200-bit mpmath golden values)."""
+    from oracle.oracle import PARAMS
+    from sfgwas_b200 import GenoFileStream
+
+    o, cps = make(PARAMS[name])
+    rng = np.random.default_rng(13)
+    n = o.slots
+    nr, nc = n + 37, n + 11  # ragged second block row / column
+    X = rng.integers(0, 3, (nr, nc)).astype(np.int8)
+    g = GenoFileStream.from_matrix(cps, X)
+    d = o.d
+    shifts = [0, 1, d, n - 1] + [int(x) for x in rng.integers(0, n, nshift)]
+    for bi in (0, 1):
+        for shift in shifts[: (len(shifts) if bi == 0 else 3)]:
+            nrot = d * (shift // d)
+            pv, present = g.EncodeDiag(bi, shift, nrot, 5, mont=True)
+            for bj in range(2):
+                blk = X[bi * n : (bi + 1) * n, bj * n : (bj + 1) * n]
+                ok, diag = o.get_diag(blk, -shift)
+                assert ok == bool(present[bj])
+                if ok:
+                    want = o.mform_lvl(5, o.encode_ntt(diag, nrot, 5))
+                    assert (pv[bj] == want).all(), (bi, shift, bj)
+    # golden picks (mpmath, 200 bit)
+    for case in load("encode")["cases"]:
+        if case["logN"] == o.logN and "picks" in case:
+            r2 = random.Random(case["seed"])
+            v = np.array([r2.choice([0, 1, 2]) for _ in range(n)], dtype=np.int8)
+            Xd = np.zeros((n, n), dtype=np.int8)
+            Xd[np.arange(n), np.arange(n)] = v
+            g2 = GenoFileStream.from_matrix(cps, Xd)
+            _, _, co = g2.EncodeDiag(0, 0, 0, 0, mont=False, want_coeffs=True)
+            assert [int(co[0][k]) for k in case["picks"]] == case["pick_coeffs"]
+    rechecked, unresolved = cps.encoder_stats()
+    assert unresolved == 0
+    cps.close()
+
+
+# ---- rotation / key-switch ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", ["pn13", "pn14", "pn15"])
+def test_rotate_vs_python_bignum_tiny(shape):
+    import pyref
+    from oracle.oracle import small_params
+
+    logN = 6
+    o, cps = make(small_params(logN, shape))
+    sk = o.keygen_secret(9)
+    k = 5
+    swk = o.gen_rotation_key(sk, k, seed=21)
+    cps.SetRotKey(k, swk)
+    rng = np.random.default_rng(4)
+    for level in (5, 4):
+        ct = np.stack([np.stack([rng.integers(0, o.Q[l], o.N, dtype=np.uint64) for l in range(level + 1)]) for _ in range(2)])
+        got = cps.RotateRightWithEvaluator(ct, -k)
+        want = pyref.rotate_right_ref(o.Q, o.P, logN, level, ct.tolist(), -k, swk.tolist())
+        assert got.tolist() == want
+        assert (got == o.rotate_right(ct, -k, swk)).all()
+    cps.close()
+
+
+@pytest.mark.parametrize("fix", ["small13", "small14"])
+def test_rotate_vs_oracle(fix, request):
+    o, cps, sk, keys = request.getfixturevalue(fix)
+    rng = np.random.default_rng(2)
+    for level in (5, 4):
+        cts = np.stack([np.stack([np.stack([rng.integers(0, o.Q[l], o.N, dtype=np.uint64) for l in range(level + 1)])
+                                  for _ in range(2)]) for _ in range(3)])
+        for k in (1, o.d - 1, o.d, 2 * o.d):
+            got = cps.RotateRightWithEvaluator(cts, -k)
+            for t in range(3):
+                assert (got[t] == o.rotate_right(cts[t], -k, keys[k])).all(), (level, k, t)
+        assert (cps.RotateRightWithEvaluator(cts, 0) == cts).all()
+        assert (cps.RotateRightWithEvaluator(cts, o.slots) == cts).all()
+
+
+def test_rotate_real_params_pn13():
+    from oracle.oracle import PARAMS
+
+    o, cps = make(PARAMS["PN13QP218"])
+    sk = o.keygen_secret(3)
+    rng = np.random.default_rng(8)
+    for k in (1, 64):
+        swk = o.gen_rotation_key(sk, k)
+        cps.SetRotKey(k, swk)
+        for level in (5, 4):
+            ct = np.stack([np.stack([rng.integers(0, o.Q[l], o.N, dtype=np.uint64) for l in range(level + 1)]) for _ in range(2)])
+            assert (cps.RotateRightWithEvaluator(ct, -k) == o.rotate_right(ct, -k, swk)).all()
+    cps.close()
+
+
+def test_missing_key_fails_loudly(small13):
+    from sfgwas_b200 import SfgError
+
+    o, cps, _, _ = small13
+    ct = np.zeros((2, 6, o.N), dtype=np.uint64)
+    with pytest.raises(SfgError):
+        cps.RotateRightWithEvaluator(ct, -(o.d + 1))  # no key for this rotation
+
+
+# ---- the stream entry points ---------------------------------------------------------------------------------------------
+def enc_matrix(o, sk, Ap, level=5):
+    s, nr = Ap.shape
+    nbr = (nr - 1) // o.slots + 1
+    A = np.zeros((s, nbr, 2, level + 1, o.N), dtype=np.uint64)
+    for i in range(s):
+        for b in range(nbr):
+            A[i, b] = o.encrypt_vector(sk, Ap[i, b * o.slots : (b + 1) * o.slots], level, seed=100 + 17 * i + b)
+    return A
+
+
+SHAPES = [(200, 300, 2), (128, 128, 1), (77, 50, 3), (1, 5, 1), (129, 1, 2), (300, 129, 5), (260, 520, 10)]
+
+
+@pytest.mark.parametrize("nr,nc,s", SHAPES)
+def test_preprocess_compute_bit_exact(small13, nr, nc, s):
+    from sfgwas_b200 import GenoFileStream, MatMult4StreamCompute, MatMult4StreamPreprocess
+
+    o, cps, sk, keys = small13
+    rng = np.random.default_rng(nr * 7 + nc)
+    X = rng.integers(0, 3, (nr, nc)).astype(np.int8)
+    Ap = rng.normal(size=(s, nr))
+    A = enc_matrix(o, sk, Ap)
+    gfs = GenoFileStream.from_matrix(cps, X)
+    cache = MatMult4StreamPreprocess(cps, gfs, 5, "unused_prefix")
+    assert cache.materialised
+    dc = o.preprocess(X, 5, nproc=8)
+    assert cache.num_polys == o.L.orc_diag_cache_num_polys(dc)
+    # cached plaintexts: bit-exact (limbs 0..4 are what the MAC reads)
+    for bi in range(cache.num_block_rows):
+        for shift in (0, 1, o.d, o.slots - 1):
+            for bj in range(cache.m_ct):
+                want = o.cache_get(dc, bi, shift, bj)
+                got = cache.get_diag(bi, shift, bj)
+                assert (want is None) == (got is None)
+                if want is not None:
+                    assert (got == want[:5]).all()
+    out = MatMult4StreamCompute(cps, A, 5, cache)
+    want = o.compute(A, dc, keys, 5, nproc=8)
+    o.cache_free(dc)
+    assert out.shape == want.shape
+    assert (out == want).all()
+    # numerical meaning (the reference's CPMatMult0 notion): decrypt(out) ~= A_plain . X ; tolerance 1e-4 relative
+    ref = Ap @ X.astype(float)
+    tol = 1e-4 * max(1.0, np.abs(ref).max())
+    got = o.decrypt_vector(sk, out[0, 0], o.scale * o.scale).real
+    w = ref[0, : o.slots]
+    assert np.abs(got[: len(w)] - w).max() < tol
+
+
+def test_compute_on_the_fly_cache_identical(small13):
+    """A cache that does not fit the HBM budget regenerates diagonals per giant chunk: same bits."""
+    from sfgwas_b200 import GenoFileStream, MatMult4StreamCompute, MatMult4StreamPreprocess
+
+    o, cps, sk, keys = small13
+    rng = np.random.default_rng(5)
+    X = rng.integers(0, 3, (200, 300)).astype(np.int8)
+    A = enc_matrix(o, sk, rng.normal(size=(2, 200)))
+    gfs = GenoFileStream.from_matrix(cps, X)
+    c1 = MatMult4StreamPreprocess(cps, gfs, 5)
+    cps.set_cache_budget(1)
+    c2 = MatMult4StreamPreprocess(cps, gfs, 5)
+    cps.set_cache_budget(0)
+    assert c1.materialised and not c2.materialised
+    assert (MatMult4StreamCompute(cps, A, 5, c1) == MatMult4StreamCompute(cps, A, 5, c2)).all()
+
+
+def test_pn14_shape_bit_exact(small14):
+    from sfgwas_b200 import GenoFileStream, MatMult4StreamCompute, MatMult4StreamPreprocess
+
+    o, cps, sk, keys = small14
+    rng = np.random.default_rng(14)
+    X = rng.integers(0, 3, (300, 520)).astype(np.int8)
+    A = enc_matrix(o, sk, rng.normal(size=(3, 300)), level=7)  # level 7 input is dropped to 5
+    gfs = GenoFileStream.from_matrix(cps, X)
+    cache = MatMult4StreamPreprocess(cps, gfs, 5)
+    out = MatMult4StreamCompute(cps, A, 5, cache)
+    dc = o.preprocess(X, 5, nproc=8)
+    want = o.compute(A, dc, keys, 5, nproc=8)
+    o.cache_free(dc)
+    assert (out == want).all()
+
+
+def test_matmult4_stream_fused(small13):
+    from sfgwas_b200 import GenoFileStream, MatMult4Stream
+
+    o, cps, sk, keys = small13
+    rng = np.random.default_rng(21)
+    X = rng.integers(-1, 3, (150, 140)).astype(np.int8)  # -1 = missing
+    A = enc_matrix(o, sk, rng.normal(size=(2, 150)))
+    gfs = GenoFileStream.from_matrix(cps, X)
+    for sq_sum, square in ((True, True), (True, False), (False, False)):
+        out, sm, sq = MatMult4Stream(cps, A, gfs, 5, sq_sum, square, 0)
+        want, wsm, wsq = o.matmult4_stream(A, X, keys, 5, sq_sum, square, nproc=8)
+        assert (out == want).all()
+        if sq_sum:
+            assert (sm == wsm).all() and (sq == wsq).all()
+        else:
+            assert sm is None and sq is None
+
+
+def test_error_behaviour(small13):
+    from sfgwas_b200 import GenoFileStream, MatMult4StreamCompute, MatMult4StreamPreprocess, SfgError
+
+    o, cps, sk, keys = small13
+    X = np.ones((10, 10), dtype=np.int8)
+    gfs = GenoFileStream.from_matrix(cps, X)
+    cache = MatMult4StreamPreprocess(cps, gfs, 5)
+    with pytest.raises(SfgError):  # input level below maxLevel: DropLevel is fatal in the reference (crypto/basics.go:817)
+        MatMult4StreamCompute(cps, np.zeros((1, 1, 2, 5, o.N), dtype=np.uint64), 5, cache)
+    with pytest.raises(SfgError):  # wrong number of block rows
+        MatMult4StreamCompute(cps, np.zeros((1, 2, 2, 6, o.N), dtype=np.uint64), 5, cache)
+    g2 = GenoFileStream(cps, 4, 4)
+    g2.push_rows(np.zeros((2, 4), dtype=np.int8))
+    with pytest.raises(SfgError):  # incomplete stream
+        MatMult4StreamPreprocess(cps, g2, 5)
+
+
+def test_linearity_property_full_size_pn13():
+    """Size-independent property at the real logN=13 ring: MatMult(A1 + A2) == MatMult(A1) + MatMult(A2) is NOT bitwise
+    (key-switch rounding), but the MAC stage is: cv is linear mod q. Checked through one block with s=2 rows where row 1 =
+    2*row 0 (mod q): out row 1 decrypts to twice row 0; and idempotence: the same call twice gives identical bits."""
+    from oracle.oracle import PARAMS
+    from sfgwas_b200 import GenoFileStream, MatMult4StreamCompute, MatMult4StreamPreprocess
+
+    o, cps = make(PARAMS["PN13QP218"])
+    sk = o.keygen_secret(5)
+    d = o.d
+    # a narrow matrix keeps the number of needed keys small: nr = 40 rows -> shifts 0..39 and 4096-c+1.. ; use c = 1 column block
+    nr, nc = 40, 30
+    rng = np.random.default_rng(99)
+    X = rng.integers(0, 3, (nr, nc)).astype(np.int8)
+    need = set()
+    for shift in range(o.slots):
+        if shift <= nr - 1 or shift >= o.slots - nc + 1:
+            need.add(shift % d)
+            need.add((shift // d) * d)
+    need.discard(0)
+    keys = {k: o.gen_rotation_key(sk, k) for k in sorted(need)}
+    cps.SetRotKeys(keys)
+    Ap = rng.normal(size=(1, nr))
+    A1 = enc_matrix(o, sk, Ap)
+    A = np.concatenate([A1, A1], axis=0)
+    for l in range(6):
+        q = np.uint64(o.Q[l])
+        A[1, :, :, l] = (A[1, :, :, l] * np.uint64(2)) % q
+    gfs = GenoFileStream.from_matrix(cps, X)
+    cache = MatMult4StreamPreprocess(cps, gfs, 5)
+    out = MatMult4StreamCompute(cps, A, 5, cache)
+    out2 = MatMult4StreamCompute(cps, A, 5, cache)
+    assert (out == out2).all()
+    ref = (Ap @ X.astype(float))[0]
+    g0 = o.decrypt_vector(sk, out[0, 0], o.scale * o.scale).real[:nc]
+    g1 = o.decrypt_vector(sk, out[1, 0], o.scale * o.scale).real[:nc]
+    assert np.abs(g0 - ref).max() < 1e-3 and np.abs(g1 - 2 * ref).max() < 2e-3
+    # and bit-exact against the oracle at the real parameter set
+    dc = o.preprocess(X, 5, nproc=8)
+    want = o.compute(A, dc, keys, 5, nproc=8)
+    o.cache_free(dc)
+    assert (out == want).all()
+    cps.close()
