@@ -12,6 +12,7 @@
  *  - Polynomials are uint64 residues, limb-major: a ciphertext of L limbs is [2][L][N], a plaintext [L][N], exactly the
  *    order of Lattigo's Poly.Coeffs[l][j] (gwas/matmult.go:372-375,394-395).  "flat" entry points take one contiguous
  *    buffer; the "_ptrs" variants take one pointer per limb (cgo: one Go slice per limb).
+ *  - Data pointers may be host (pageable or pinned) or device pointers (unified addressing, cudaMemcpyDefault).
  *  - Host buffers are never retained after a call returns.  Handles are owned by the library and must be destroyed.
  *  - The library is re-entrant across contexts; calls on ONE context are serialised by the caller or by distinct
  *    sfg_ctx handles (one per goroutine, like the reference's per-goroutine ckks.Evaluator, gwas/matmult.go:1110).
@@ -119,8 +120,9 @@ int sfg_ctx_sync(sfg_ctx *ctx);
  * d_A [s][nbr][2][level_a+1][N] and d_out [s][m_ct][2][max_level][N] are DEVICE pointers. */
 int sfg_matmult4_stream_compute_dev(sfg_ctx *ctx, const uint64_t *d_A, int s, int num_block_rows, int level_a, int max_level,
                                     const sfg_cache *cache, uint64_t *d_out);
-/* last call's phase timings in milliseconds (CUDA events on the context stream): {baby rotations, MAC, giant rotations, total} */
-int sfg_ctx_last_timings(const sfg_ctx *ctx, float out_ms[4]);
+/* last call's phase timings in milliseconds (CUDA events on the context stream):
+ * {baby rotations, MAC phase, giant rotations, total, MAC kernel alone} */
+int sfg_ctx_last_timings(const sfg_ctx *ctx, float out_ms[5]);
 void *sfg_ctx_stream(const sfg_ctx *ctx); /* cudaStream_t of the context */
 
 #ifdef __cplusplus

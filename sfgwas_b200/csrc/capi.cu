@@ -94,7 +94,7 @@ unsigned long long sfg_ctx_launch_count(const sfg_ctx *h) { return h->c.launches
 int sfg_ctx_encoder_stats(sfg_ctx *h, unsigned long long out[2]) {
     Ctx *c = &h->c;
     SFG_CUDA(c, cudaSetDevice(c->device));
-    SFG_CUDA(c, cudaMemcpy(out, c->enc_stats, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    SFG_CUDA(c, cudaMemcpy(out, c->enc_stats, 2 * sizeof(unsigned long long), cudaMemcpyDefault));
     return 0;
 }
 int sfg_ctx_psi(const sfg_ctx *h, uint64_t *psi_out) {
@@ -108,8 +108,8 @@ int sfg_ctx_sync(sfg_ctx *h) {
     return 0;
 }
 void *sfg_ctx_stream(const sfg_ctx *h) { return (void *)h->c.stream; }
-int sfg_ctx_last_timings(const sfg_ctx *, float out_ms[4]) {
-    for (int i = 0; i < 4; i++) out_ms[i] = g_last_ms[i];
+int sfg_ctx_last_timings(const sfg_ctx *, float out_ms[5]) {
+    for (int i = 0; i < 5; i++) out_ms[i] = g_last_ms[i];
     return 0;
 }
 
@@ -119,7 +119,7 @@ static int set_key_dev(Ctx *c, int rot_left, uint64_t *dkey) {
     h_permute_ntt_index(c->logN, galEl, idx.data());
     uint32_t *dperm = nullptr;
     SFG_CUDA(c, cudaMalloc(&dperm, sizeof(uint32_t) * c->N));
-    SFG_CUDA(c, cudaMemcpy(dperm, idx.data(), sizeof(uint32_t) * c->N, cudaMemcpyHostToDevice));
+    SFG_CUDA(c, cudaMemcpy(dperm, idx.data(), sizeof(uint32_t) * c->N, cudaMemcpyDefault));
     std::lock_guard<std::mutex> g(c->mu);
     auto it = c->keys.find(galEl);
     if (it != c->keys.end()) {
@@ -136,7 +136,7 @@ int sfg_ctx_set_rotation_key(sfg_ctx *h, int rot_left, const uint64_t *key) {
     const size_t n = (size_t)c->beta * 2 * c->nQP * c->N;
     uint64_t *d = nullptr;
     SFG_CUDA(c, cudaMalloc(&d, n * 8));
-    SFG_CUDA(c, cudaMemcpy(d, key, n * 8, cudaMemcpyHostToDevice));
+    SFG_CUDA(c, cudaMemcpy(d, key, n * 8, cudaMemcpyDefault));
     return set_key_dev(c, rot_left, d);
 }
 int sfg_ctx_set_rotation_key_ptrs(sfg_ctx *h, int rot_left, const uint64_t *const *limbs) {
@@ -145,7 +145,7 @@ int sfg_ctx_set_rotation_key_ptrs(sfg_ctx *h, int rot_left, const uint64_t *cons
     const size_t np = (size_t)c->beta * 2 * c->nQP;
     uint64_t *d = nullptr;
     SFG_CUDA(c, cudaMalloc(&d, np * c->N * 8));
-    for (size_t p = 0; p < np; p++) SFG_CUDA(c, cudaMemcpy(d + p * c->N, limbs[p], (size_t)c->N * 8, cudaMemcpyHostToDevice));
+    for (size_t p = 0; p < np; p++) SFG_CUDA(c, cudaMemcpy(d + p * c->N, limbs[p], (size_t)c->N * 8, cudaMemcpyDefault));
     return set_key_dev(c, rot_left, d);
 }
 int sfg_ctx_has_rotation_key(const sfg_ctx *h, int rot_left) {
@@ -166,9 +166,9 @@ int sfg_ntt(sfg_ctx *h, uint64_t *polys, int npoly, const int *limb_idx, int nse
     Buf d;
     const size_t bytes = (size_t)npoly * c->N * 8;
     if (d.alloc(c, bytes)) return -1;
-    SFG_CUDA(c, cudaMemcpyAsync(d.p, polys, bytes, cudaMemcpyHostToDevice, c->stream));
+    SFG_CUDA(c, cudaMemcpyAsync(d.p, polys, bytes, cudaMemcpyDefault, c->stream));
     if (launch_ntt(c, d.as<uint64_t>(), (size_t)nsel * c->N, d.as<uint64_t>(), (size_t)nsel * c->N, npoly, sel, inverse != 0, c->stream)) return -1;
-    SFG_CUDA(c, cudaMemcpyAsync(polys, d.p, bytes, cudaMemcpyDeviceToHost, c->stream));
+    SFG_CUDA(c, cudaMemcpyAsync(polys, d.p, bytes, cudaMemcpyDefault, c->stream));
     SFG_CUDA(c, cudaStreamSynchronize(c->stream));
     return 0;
 }
@@ -178,11 +178,11 @@ int sfg_mul_coeffs_and_add128(sfg_ctx *h, const uint64_t *a, const uint64_t *b, 
     SFG_CUDA(c, cudaSetDevice(c->device));
     Buf da, db, dacc;
     if (da.alloc(c, n * 8) || db.alloc(c, n * 8) || dacc.alloc(c, n * 16)) return -1;
-    SFG_CUDA(c, cudaMemcpyAsync(da.p, a, n * 8, cudaMemcpyHostToDevice, c->stream));
-    SFG_CUDA(c, cudaMemcpyAsync(db.p, b, n * 8, cudaMemcpyHostToDevice, c->stream));
-    SFG_CUDA(c, cudaMemcpyAsync(dacc.p, acc, n * 16, cudaMemcpyHostToDevice, c->stream));
+    SFG_CUDA(c, cudaMemcpyAsync(da.p, a, n * 8, cudaMemcpyDefault, c->stream));
+    SFG_CUDA(c, cudaMemcpyAsync(db.p, b, n * 8, cudaMemcpyDefault, c->stream));
+    SFG_CUDA(c, cudaMemcpyAsync(dacc.p, acc, n * 16, cudaMemcpyDefault, c->stream));
     if (launch_mul_coeffs_and_add128(c, da.as<uint64_t>(), db.as<uint64_t>(), dacc.as<uint64_t>(), n, c->stream)) return -1;
-    SFG_CUDA(c, cudaMemcpyAsync(acc, dacc.p, n * 16, cudaMemcpyDeviceToHost, c->stream));
+    SFG_CUDA(c, cudaMemcpyAsync(acc, dacc.p, n * 16, cudaMemcpyDefault, c->stream));
     SFG_CUDA(c, cudaStreamSynchronize(c->stream));
     return 0;
 }
@@ -192,10 +192,10 @@ int sfg_reduce_and_add_uint128(sfg_ctx *h, const uint64_t *acc, uint64_t *out, i
     SFG_CUDA(c, cudaSetDevice(c->device));
     Buf dacc, dout;
     if (dacc.alloc(c, n * 16) || dout.alloc(c, n * 8)) return -1;
-    SFG_CUDA(c, cudaMemcpyAsync(dacc.p, acc, n * 16, cudaMemcpyHostToDevice, c->stream));
-    SFG_CUDA(c, cudaMemcpyAsync(dout.p, out, n * 8, cudaMemcpyHostToDevice, c->stream));
+    SFG_CUDA(c, cudaMemcpyAsync(dacc.p, acc, n * 16, cudaMemcpyDefault, c->stream));
+    SFG_CUDA(c, cudaMemcpyAsync(dout.p, out, n * 8, cudaMemcpyDefault, c->stream));
     if (launch_reduce_and_add128(c, dacc.as<uint64_t>(), dout.as<uint64_t>(), limb, n, c->stream)) return -1;
-    SFG_CUDA(c, cudaMemcpyAsync(out, dout.p, n * 8, cudaMemcpyDeviceToHost, c->stream));
+    SFG_CUDA(c, cudaMemcpyAsync(out, dout.p, n * 8, cudaMemcpyDefault, c->stream));
     SFG_CUDA(c, cudaStreamSynchronize(c->stream));
     return 0;
 }
@@ -206,9 +206,9 @@ int sfg_mform_lvl(sfg_ctx *h, int level, uint64_t *p) {
     Buf d;
     const size_t bytes = (size_t)(level + 1) * c->N * 8;
     if (d.alloc(c, bytes)) return -1;
-    SFG_CUDA(c, cudaMemcpyAsync(d.p, p, bytes, cudaMemcpyHostToDevice, c->stream));
+    SFG_CUDA(c, cudaMemcpyAsync(d.p, p, bytes, cudaMemcpyDefault, c->stream));
     if (launch_mform(c, d.as<uint64_t>(), level + 1, c->stream)) return -1;
-    SFG_CUDA(c, cudaMemcpyAsync(p, d.p, bytes, cudaMemcpyDeviceToHost, c->stream));
+    SFG_CUDA(c, cudaMemcpyAsync(p, d.p, bytes, cudaMemcpyDefault, c->stream));
     SFG_CUDA(c, cudaStreamSynchronize(c->stream));
     return 0;
 }
@@ -219,9 +219,9 @@ int sfg_rotate_right(sfg_ctx *h, int level, const uint64_t *cts, int nct, int nr
     const size_t bytes = (size_t)nct * 2 * (level + 1) * c->N * 8;
     Buf din, dout;
     if (din.alloc(c, bytes) || dout.alloc(c, bytes)) return -1;
-    SFG_CUDA(c, cudaMemcpyAsync(din.p, cts, bytes, cudaMemcpyHostToDevice, c->stream));
+    SFG_CUDA(c, cudaMemcpyAsync(din.p, cts, bytes, cudaMemcpyDefault, c->stream));
     if (rotate_right_dev(c, level, din.as<uint64_t>(), nct, nrot, dout.as<uint64_t>())) return -1;
-    SFG_CUDA(c, cudaMemcpy(out, dout.p, bytes, cudaMemcpyDeviceToHost));
+    SFG_CUDA(c, cudaMemcpy(out, dout.p, bytes, cudaMemcpyDefault));
     return 0;
 }
 
@@ -275,7 +275,7 @@ int sfg_cache_get_diag(sfg_ctx *h, const sfg_cache *cache, int bi, int shift, in
     if (po < 0) return 0;
     if (!ca->materialised) SFG_FAIL(c, "cache is not materialised (diagonals are regenerated on the fly)");
     SFG_CUDA(c, cudaSetDevice(c->device));
-    SFG_CUDA(c, cudaMemcpy(out, ca->P + po, (size_t)ca->L * c->N * 8, cudaMemcpyDeviceToHost));
+    SFG_CUDA(c, cudaMemcpy(out, ca->P + po, (size_t)ca->L * c->N * 8, cudaMemcpyDefault));
     return 0;
 }
 
@@ -293,9 +293,9 @@ int sfg_matmult4_stream_compute(sfg_ctx *h, const uint64_t *A, int s, int nbr, i
     const size_t obytes = (size_t)s * cache->ca->m_ct * 2 * max_level * c->N * 8;
     Buf dA, dO;
     if (dA.alloc(c, abytes) || dO.alloc(c, obytes)) return -1;
-    SFG_CUDA(c, cudaMemcpyAsync(dA.p, A, abytes, cudaMemcpyHostToDevice, c->stream));
+    SFG_CUDA(c, cudaMemcpyAsync(dA.p, A, abytes, cudaMemcpyDefault, c->stream));
     if (mm_compute_dev(c, dA.as<uint64_t>(), s, nbr, level_a, max_level, cache->ca, dO.as<uint64_t>())) return -1;
-    SFG_CUDA(c, cudaMemcpyAsync(out, dO.p, obytes, cudaMemcpyDeviceToHost, c->stream));
+    SFG_CUDA(c, cudaMemcpyAsync(out, dO.p, obytes, cudaMemcpyDefault, c->stream));
     SFG_CUDA(c, cudaStreamSynchronize(c->stream));
     return 0;
 }
@@ -309,9 +309,9 @@ int sfg_matmult4_stream_compute_ptrs(sfg_ctx *h, const uint64_t *const *A_limbs,
     const size_t na = (size_t)s * nbr * 2 * (level_a + 1), no = (size_t)s * cache->ca->m_ct * 2 * max_level;
     Buf dA, dO;
     if (dA.alloc(c, na * N * 8) || dO.alloc(c, no * N * 8)) return -1;
-    for (size_t p = 0; p < na; p++) SFG_CUDA(c, cudaMemcpyAsync(dA.as<uint64_t>() + p * N, A_limbs[p], N * 8, cudaMemcpyHostToDevice, c->stream));
+    for (size_t p = 0; p < na; p++) SFG_CUDA(c, cudaMemcpyAsync(dA.as<uint64_t>() + p * N, A_limbs[p], N * 8, cudaMemcpyDefault, c->stream));
     if (mm_compute_dev(c, dA.as<uint64_t>(), s, nbr, level_a, max_level, cache->ca, dO.as<uint64_t>())) return -1;
-    for (size_t p = 0; p < no; p++) SFG_CUDA(c, cudaMemcpyAsync(out_limbs[p], dO.as<uint64_t>() + p * N, N * 8, cudaMemcpyDeviceToHost, c->stream));
+    for (size_t p = 0; p < no; p++) SFG_CUDA(c, cudaMemcpyAsync(out_limbs[p], dO.as<uint64_t>() + p * N, N * 8, cudaMemcpyDefault, c->stream));
     SFG_CUDA(c, cudaStreamSynchronize(c->stream));
     return 0;
 }
@@ -345,12 +345,12 @@ int sfg_matmult4_stream(sfg_ctx *h, const uint64_t *A, int s, int level_a, const
         const size_t obytes = (size_t)s * ca->m_ct * 2 * max_level * c->N * 8;
         Buf dA, dO;
         if (dA.alloc(c, abytes) || dO.alloc(c, obytes)) break;
-        if (cudaMemcpyAsync(dA.p, A, abytes, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) { c->err = "H2D copy of A failed"; break; }
+        if (cudaMemcpyAsync(dA.p, A, abytes, cudaMemcpyDefault, c->stream) != cudaSuccess) { c->err = "H2D copy of A failed"; break; }
         if (mm_compute_dev(c, dA.as<uint64_t>(), s, nbr, level_a, max_level, ca, dO.as<uint64_t>())) break;
-        if (cudaMemcpyAsync(out, dO.p, obytes, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) { c->err = "D2H copy failed"; break; }
+        if (cudaMemcpyAsync(out, dO.p, obytes, cudaMemcpyDefault, c->stream) != cudaSuccess) { c->err = "D2H copy failed"; break; }
         if (compute_squared_sum) {
-            cudaMemcpyAsync(sum, dsum.p, src->ncols * 8, cudaMemcpyDeviceToHost, c->stream);
-            cudaMemcpyAsync(sq_sum, dsq.p, src->ncols * 8, cudaMemcpyDeviceToHost, c->stream);
+            cudaMemcpyAsync(sum, dsum.p, src->ncols * 8, cudaMemcpyDefault, c->stream);
+            cudaMemcpyAsync(sq_sum, dsq.p, src->ncols * 8, cudaMemcpyDefault, c->stream);
         }
         if (cudaStreamSynchronize(c->stream) != cudaSuccess) { c->err = "stream sync failed"; break; }
         rc = 0;
@@ -373,7 +373,7 @@ int sfg_matmult4_partial(sfg_ctx *h, const uint64_t *A, int s, int nbr, int leve
     const size_t abytes = (size_t)s * nbr * 2 * (level_a + 1) * c->N * 8;
     Buf dA;
     if (dA.alloc(c, abytes)) return -1;
-    SFG_CUDA(c, cudaMemcpyAsync(dA.p, A, abytes, cudaMemcpyHostToDevice, c->stream));
+    SFG_CUDA(c, cudaMemcpyAsync(dA.p, A, abytes, cudaMemcpyDefault, c->stream));
     return mm_partial_dev(c, dA.as<uint64_t>(), s, nbr, level_a, max_level, cache->ca, bi_lo, bi_hi, d_cv);
 }
 int sfg_cv_mod_reduce(sfg_ctx *h, const sfg_cache *cache, int s, int max_level, uint64_t *d_cv, size_t first_elem, size_t num_elems) {
@@ -394,7 +394,7 @@ int sfg_matmult4_finish(sfg_ctx *h, const sfg_cache *cache, int s, int max_level
     Buf dO;
     if (dO.alloc(c, obytes)) return -1;
     if (mm_finish_dev(c, cache->ca, s, max_level, d_cv, g_lo, g_hi, dO.as<uint64_t>())) return -1;
-    SFG_CUDA(c, cudaMemcpy(out, dO.p, obytes, cudaMemcpyDeviceToHost));
+    SFG_CUDA(c, cudaMemcpy(out, dO.p, obytes, cudaMemcpyDefault));
     return 0;
 }
 int sfg_ct_add(sfg_ctx *h, const uint64_t *a, const uint64_t *b, int ncts, int nl, uint64_t *out) {
@@ -404,13 +404,13 @@ int sfg_ct_add(sfg_ctx *h, const uint64_t *a, const uint64_t *b, int ncts, int n
     const size_t n = (size_t)ncts * 2 * nl * c->N;
     Buf da, db;
     if (da.alloc(c, n * 8) || db.alloc(c, n * 8)) return -1;
-    SFG_CUDA(c, cudaMemcpyAsync(da.p, a, n * 8, cudaMemcpyHostToDevice, c->stream));
-    SFG_CUDA(c, cudaMemcpyAsync(db.p, b, n * 8, cudaMemcpyHostToDevice, c->stream));
+    SFG_CUDA(c, cudaMemcpyAsync(da.p, a, n * 8, cudaMemcpyDefault, c->stream));
+    SFG_CUDA(c, cudaMemcpyAsync(db.p, b, n * 8, cudaMemcpyDefault, c->stream));
     std::vector<long long> offs(ncts);
     for (int t = 0; t < ncts; t++) offs[t] = (long long)t * 2 * nl * c->N;
     Buf doffs;
     if (doffs.alloc(c, std::max(1, ncts) * sizeof(long long))) return -1;
-    SFG_CUDA(c, cudaMemcpyAsync(doffs.p, offs.data(), ncts * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
+    SFG_CUDA(c, cudaMemcpyAsync(doffs.p, offs.data(), ncts * sizeof(long long), cudaMemcpyDefault, c->stream));
     KsBatch kb{};
     kb.nct = ncts;
     kb.in = da.as<uint64_t>();
@@ -422,7 +422,7 @@ int sfg_ct_add(sfg_ctx *h, const uint64_t *a, const uint64_t *b, int ncts, int n
     kb.out_limbs = nl;
     kb.accumulate = true;
     if (launch_copy_add(c, kb, c->stream)) return -1;
-    SFG_CUDA(c, cudaMemcpyAsync(out, db.p, n * 8, cudaMemcpyDeviceToHost, c->stream));
+    SFG_CUDA(c, cudaMemcpyAsync(out, db.p, n * 8, cudaMemcpyDefault, c->stream));
     SFG_CUDA(c, cudaStreamSynchronize(c->stream));
     return 0;
 }

@@ -1,10 +1,24 @@
 // ctx.cu -- context construction: RNS constants, NTT twiddles, encoder tables, key-switch base-conversion tables.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "ctx.h"
 
 namespace sfg {
+
+int launch_check(Ctx *c, const char *what, cudaStream_t st) {
+    static const bool debug = getenv("SFG_DEBUG") != nullptr;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && debug) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) {
+        char buf[512];
+        snprintf(buf, sizeof buf, "kernel %s: %s", what, cudaGetErrorString(e));
+        c->err = buf;
+        return -1;
+    }
+    return 0;
+}
 
 int ctx_build_tables(Ctx *c, const uint64_t *psi_opt) {
     const int N = c->N, logN = c->logN, nQP = c->nQP;

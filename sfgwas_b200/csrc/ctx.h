@@ -81,6 +81,14 @@ struct Ctx {
         return -1;                                      \
     } while (0)
 
+// after every kernel launch: catch launch errors; with SFG_DEBUG=1 also synchronise and report the failing kernel
+int launch_check(Ctx *c, const char *what, cudaStream_t st);
+#define SFG_LAUNCHED(ctx, what, st)                  \
+    do {                                             \
+        (ctx)->launches++;                           \
+        if (launch_check((ctx), (what), (st))) return -1; \
+    } while (0)
+
 // ---- table builders (ctx.cu) ----
 int ctx_build_tables(Ctx *c, const uint64_t *psi_opt);
 int ctx_get_ks_tables(Ctx *c, int level, BaseConv **ks, BaseConv **md, uint64_t **pinv);

@@ -208,8 +208,7 @@ int launch_encode(Ctx *c, const int8_t *X, size_t ld, const EncJob *jobs_dev, in
         k_encode<8><<<njobs, T, smem, st>>>(X, ld, jobs_dev, logN, nl, mont ? 1 : 0, sc, c->enc_delta, c->roots, c->rot5, c->ddcos,
                                            c->tw, c->lc, out, coeff_out, c->enc_stats);
     }
-    c->launches++;
-    SFG_CUDA(c, cudaGetLastError());
+    SFG_LAUNCHED(c, "k_encode", st);
     return 0;
 }
 

@@ -166,8 +166,7 @@ int launch_copy_add(Ctx *c, const KsBatch &b, cudaStream_t st) {
     if (b.nct <= 0) return 0;
     dim3 g(2 * b.out_limbs, b.nct);
     k_copy_add<<<g, 256, 0, st>>>(b.in, b.in_off, b.in_nl, b.out, b.out_off, b.out_nl, b.out_limbs, c->N, c->lc, b.accumulate ? 1 : 0);
-    c->launches++;
-    SFG_CUDA(c, cudaGetLastError());
+    SFG_LAUNCHED(c, "k_copy_add", st);
     return 0;
 }
 
@@ -191,7 +190,7 @@ static int rotate_impl(Ctx *c, const KsBatch &b, const GaloisKey &key, cudaStrea
     {
         dim3 g(nt, b.nct);
         k_ks_inner<NPER><<<g, T, smem, st>>>(b.in, b.in_off, b.in_nl, b.c2, key.key, ks, b.level, c->nQ, c->nP, c->logN, c->tw, c->lc, b.acc);
-        c->launches++;
+        SFG_LAUNCHED(c, "k_ks_inner", st);
     }
     // 3. INTT of the P limbs of acc: groups = (ct, comp), per-group limbs nQ..nQ+nP-1 located after the nl Q limbs
     LimbSel selp;
@@ -203,9 +202,8 @@ static int rotate_impl(Ctx *c, const KsBatch &b, const GaloisKey &key, cudaStrea
         dim3 g(b.out_limbs, 2, b.nct);
         k_ks_moddown<NPER><<<g, T, smem, st>>>(b.in, b.in_off, b.in_nl, b.acc, md, pinv, key.perm, b.level, c->nQ, c->nP, c->logN, c->tw,
                                               c->lc, b.out, b.out_off, b.out_nl, b.accumulate ? 1 : 0);
-        c->launches++;
+        SFG_LAUNCHED(c, "k_ks_moddown", st);
     }
-    SFG_CUDA(c, cudaGetLastError());
     return 0;
 }
 

@@ -125,8 +125,7 @@ static int launch_mac_cfg(Ctx *c, const uint64_t *R, const uint64_t *P, const lo
     SFG_CUDA(c, cudaFuncSetAttribute(k_mac<TR, TC, CG, RG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((ncols + CB - 1) / CB, c->N / kNB, L);
     k_mac<TR, TC, CG, RG><<<grid, THREADS, smem, st>>>(R, P, poff, K, nrows, ncols, L, c->N, c->lc, cv);
-    c->launches++;
-    SFG_CUDA(c, cudaGetLastError());
+    SFG_LAUNCHED(c, "k_mac", st);
     return 0;
 }
 

@@ -88,31 +88,30 @@ int launch_ntt(Ctx *c, const uint64_t *src, size_t src_gstride, uint64_t *dst, s
             k_ntt_smem<false><<<npoly, threads, smem, st>>>(src, src_gstride, dst, dst_gstride, sel, logN, logS, c->tw, c->lc);
         else
             k_ntt_smem<true><<<npoly, threads, smem, st>>>(src, src_gstride, dst, dst_gstride, sel, logN, logS, c->tw, c->lc);
-        c->launches++;
+        SFG_LAUNCHED(c, "k_ntt_smem", st);
     } else {
         // large rings: global stages work in place on dst
         dim3 gg(64, npoly);
         if (!inverse) {
             if (src != dst) {
                 k_copy_polys<<<gg, 256, 0, st>>>(src, src_gstride, dst, dst_gstride, sel.n, N);
-                c->launches++;
+                SFG_LAUNCHED(c, "k_copy_polys", st);
             }
             for (int m = 1; m < nblk; m <<= 1) {
                 k_ntt_gstage<false><<<gg, 256, 0, st>>>(dst, dst_gstride, sel, logN, m, 0, c->tw, c->lc);
-                c->launches++;
+                SFG_LAUNCHED(c, "k_ntt_gstage", st);
             }
             k_ntt_smem<false><<<npoly * nblk, threads, smem, st>>>(dst, dst_gstride, dst, dst_gstride, sel, logN, logS, c->tw, c->lc);
-            c->launches++;
+            SFG_LAUNCHED(c, "k_ntt_smem", st);
         } else {
             k_ntt_smem<true><<<npoly * nblk, threads, smem, st>>>(src, src_gstride, dst, dst_gstride, sel, logN, logS, c->tw, c->lc);
-            c->launches++;
+            SFG_LAUNCHED(c, "k_ntt_smem", st);
             for (int h = nblk >> 1; h >= 1; h >>= 1) {
                 k_ntt_gstage<true><<<gg, 256, 0, st>>>(dst, dst_gstride, sel, logN, h, h == 1, c->tw, c->lc);
-                c->launches++;
+                SFG_LAUNCHED(c, "k_ntt_gstage", st);
             }
         }
     }
-    SFG_CUDA(c, cudaGetLastError());
     return 0;
 }
 
@@ -151,22 +150,19 @@ __global__ void k_mod_reduce(uint64_t *__restrict__ x, int L, int N, const LimbC
 int launch_mul_coeffs_and_add128(Ctx *c, const uint64_t *a, const uint64_t *b, uint64_t *acc, size_t n, cudaStream_t st) {
     const int blocks = (int)std::min<size_t>((n + 255) / 256, 148 * 8);
     k_mul_coeffs_and_add128<<<blocks, 256, 0, st>>>(a, b, (ulonglong2 *)acc, n);
-    c->launches++;
-    SFG_CUDA(c, cudaGetLastError());
+    SFG_LAUNCHED(c, "k_mul_coeffs_and_add128", st);
     return 0;
 }
 int launch_reduce_and_add128(Ctx *c, const uint64_t *acc, uint64_t *out, int limb, size_t n, cudaStream_t st) {
     const int blocks = (int)std::min<size_t>((n + 255) / 256, 148 * 8);
     k_reduce_and_add128<<<blocks, 256, 0, st>>>((const ulonglong2 *)acc, out, c->lc_h[limb], n);
-    c->launches++;
-    SFG_CUDA(c, cudaGetLastError());
+    SFG_LAUNCHED(c, "k_reduce_and_add128", st);
     return 0;
 }
 int launch_mform(Ctx *c, uint64_t *p, int nlimbs, cudaStream_t st) {
     dim3 g((c->N + 255) / 256, nlimbs);
     k_mform<<<g, 256, 0, st>>>(p, c->N, c->lc);
-    c->launches++;
-    SFG_CUDA(c, cudaGetLastError());
+    SFG_LAUNCHED(c, "k_mform", st);
     return 0;
 }
 int launch_mod_reduce(Ctx *c, uint64_t *x, size_t npoly, int L, cudaStream_t st) {
@@ -175,9 +171,8 @@ int launch_mod_reduce(Ctx *c, uint64_t *x, size_t npoly, int L, cudaStream_t st)
         const size_t cnt = std::min(npoly - off, maxy - (maxy % L));
         dim3 g((c->N + 255) / 256, (unsigned)cnt);
         k_mod_reduce<<<g, 256, 0, st>>>(x + off * c->N, L, c->N, c->lc);
-        c->launches++;
+        SFG_LAUNCHED(c, "k_mod_reduce", st);
     }
-    SFG_CUDA(c, cudaGetLastError());
     return 0;
 }
 
@@ -210,8 +205,7 @@ int launch_geno_prep(Ctx *c, int8_t *X, size_t rows, size_t ncols, double *sum, 
     const int rows_per_slab = 256;
     dim3 g((unsigned)((ncols + 255) / 256), (unsigned)((rows + rows_per_slab - 1) / rows_per_slab));
     k_geno_prep<<<g, 256, 0, st>>>(X, rows, ncols, sum, sqsum, square ? 1 : 0, rows_per_slab);
-    c->launches++;
-    SFG_CUDA(c, cudaGetLastError());
+    SFG_LAUNCHED(c, "k_geno_prep", st);
     return 0;
 }
 

@@ -19,7 +19,8 @@
 
 namespace sfg {
 
-thread_local float g_last_ms[4] = {0, 0, 0, 0};
+thread_local float g_last_ms[5] = {0, 0, 0, 0, 0};
+thread_local float g_mac_kernel_ms = 0;
 
 // ---------------------------------------------------------------------------------------------------------------
 // genotype matrix
@@ -29,6 +30,7 @@ int geno_create(Ctx *c, size_t nrows, size_t ncols, Geno **out) {
     SFG_CUDA(c, cudaSetDevice(c->device));
     Geno *g = new Geno();
     g->c = c;
+    g->device = c->device;
     g->nrows = nrows;
     g->ncols = ncols;
     cudaError_t e = cudaMalloc(&g->d, nrows * ncols);
@@ -43,7 +45,7 @@ int geno_push(Geno *g, const int8_t *rows, size_t n) {
     Ctx *c = g->c;
     if (g->filled + n > g->nrows) SFG_FAIL(c, "geno_push: %zu rows pushed into a %zu-row matrix (already %zu)", n, g->nrows, g->filled);
     SFG_CUDA(c, cudaSetDevice(c->device));
-    SFG_CUDA(c, cudaMemcpyAsync(g->d + g->filled * g->ncols, rows, n * g->ncols, cudaMemcpyHostToDevice, c->stream));
+    SFG_CUDA(c, cudaMemcpyAsync(g->d + g->filled * g->ncols, rows, n * g->ncols, cudaMemcpyDefault, c->stream));
     SFG_CUDA(c, cudaStreamSynchronize(c->stream));
     g->filled += n;
     return 0;
@@ -51,7 +53,7 @@ int geno_push(Geno *g, const int8_t *rows, size_t n) {
 void geno_release(Geno *g) {
     if (!g) return;
     if (--g->refs == 0) {
-        cudaSetDevice(g->c->device);
+        cudaSetDevice(g->device);
         cudaFree(g->d);
         delete g;
     }
@@ -77,7 +79,7 @@ static int encode_jobs(Ctx *c, const Cache *ca, const std::vector<EncJob> &jobs,
     if (jobs.empty()) return 0;
     Buf dj;
     if (dj.alloc(c, jobs.size() * sizeof(EncJob))) return -1;
-    SFG_CUDA(c, cudaMemcpyAsync(dj.p, jobs.data(), jobs.size() * sizeof(EncJob), cudaMemcpyHostToDevice, c->stream));
+    SFG_CUDA(c, cudaMemcpyAsync(dj.p, jobs.data(), jobs.size() * sizeof(EncJob), cudaMemcpyDefault, c->stream));
     const size_t chunk = 1 << 20;
     for (size_t o = 0; o < jobs.size(); o += chunk) {
         const int n = (int)std::min(chunk, jobs.size() - o);
@@ -93,6 +95,7 @@ int cache_build(Ctx *c, Geno *g, int maxLevel, Cache **out) {
     SFG_CUDA(c, cudaSetDevice(c->device));
     Cache *ca = new Cache();
     ca->c = c;
+    ca->device = c->device;
     ca->g = g;
     g->refs++;
     ca->maxLevel = maxLevel;
@@ -177,7 +180,7 @@ int cache_build(Ctx *c, Geno *g, int maxLevel, Cache **out) {
 
 void cache_destroy(Cache *ca) {
     if (!ca) return;
-    cudaSetDevice(ca->c->device);
+    cudaSetDevice(ca->device);
     cudaFree(ca->P);
     geno_release(ca->g);
     delete ca;
@@ -279,7 +282,7 @@ static int build_rot_cache(Ctx *c, const Cache *ca, const uint64_t *d_A, int s, 
         }
     }
     if (scr.offs.alloc(c, std::max<size_t>(offs.size(), 1) * sizeof(long long))) return -1;
-    SFG_CUDA(c, cudaMemcpyAsync(scr.offs.p, offs.data(), offs.size() * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
+    SFG_CUDA(c, cudaMemcpyAsync(scr.offs.p, offs.data(), offs.size() * sizeof(long long), cudaMemcpyDefault, c->stream));
     if (scr.ensure(c, s * nbr, ca->maxLevel + 1)) return -1;
     for (const Batch &bt : batches) {
         KsBatch kb;
@@ -343,15 +346,25 @@ static int run_mac(Ctx *c, const Cache *ca, const uint64_t *R, const std::vector
     }
     Buf dpoff, tmpP;
     if (dpoff.alloc(c, poff.size() * sizeof(long long))) return -1;
-    SFG_CUDA(c, cudaMemcpyAsync(dpoff.p, poff.data(), poff.size() * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
+    SFG_CUDA(c, cudaMemcpyAsync(dpoff.p, poff.data(), poff.size() * sizeof(long long), cudaMemcpyDefault, c->stream));
     const uint64_t *P = ca->P;
     if (!ca->materialised) {
         if (tmpP.alloc(c, std::max<size_t>(ntmp, 1) * LN * 8)) return -1;
         if (encode_jobs(c, ca, jobs, tmpP.as<uint64_t>())) return -1;
         P = tmpP.as<uint64_t>();
     }
+    cudaEvent_t e0, e1;  // the MAC kernel alone, on the stream it is launched on (bench.py roofline)
+    SFG_CUDA(c, cudaEventCreate(&e0));
+    SFG_CUDA(c, cudaEventCreate(&e1));
+    SFG_CUDA(c, cudaEventRecord(e0, c->stream));
     if (launch_mac(c, R, P, dpoff.as<long long>(), K, 2 * s, ncols, L, d_cv, c->stream)) return -1;
+    SFG_CUDA(c, cudaEventRecord(e1, c->stream));
     SFG_CUDA(c, cudaStreamSynchronize(c->stream));  // poff / tmpP are freed on return
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    g_mac_kernel_ms += ms;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
     return 0;
 }
 
@@ -378,7 +391,7 @@ static int run_giant(Ctx *c, const Cache *ca, int s, const uint64_t *d_cv, int g
     }
     Buf doffs;
     if (doffs.alloc(c, offs.size() * sizeof(long long))) return -1;
-    SFG_CUDA(c, cudaMemcpyAsync(doffs.p, offs.data(), offs.size() * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
+    SFG_CUDA(c, cudaMemcpyAsync(doffs.p, offs.data(), offs.size() * sizeof(long long), cudaMemcpyDefault, c->stream));
     if (scr.ensure(c, nct, L)) return -1;
     for (int gi = gi_lo; gi < gi_hi; gi++) {
         const int g = ca->gact[gi];
@@ -425,6 +438,7 @@ int mm_compute_dev(Ctx *c, const uint64_t *d_A, int s, int nbr, int levelA, int 
     const int L = ca->L, N = c->N, m_ct = ca->m_ct;
     const size_t LN = (size_t)L * N;
     PhaseTimer tm(c->stream);
+    g_mac_kernel_ms = 0;
     Scratch scr;
     Buf R;
     std::vector<int> klist;
@@ -450,6 +464,7 @@ int mm_compute_dev(Ctx *c, const uint64_t *d_A, int s, int nbr, int levelA, int 
     }
     tm.mark(-1);
     tm.finish(g_last_ms);
+    g_last_ms[4] = g_mac_kernel_ms;
     SFG_CUDA(c, cudaStreamSynchronize(c->stream));
     return 0;
 }
@@ -462,6 +477,7 @@ int mm_partial_dev(Ctx *c, const uint64_t *d_A, int s, int nbr, int levelA, int 
     const size_t LN = (size_t)ca->L * c->N;
     const size_t total = ca->gact.size() * (size_t)ca->m_ct * 2 * s * LN;
     PhaseTimer tm(c->stream);
+    g_mac_kernel_ms = 0;
     Scratch scr;
     Buf R;
     std::vector<int> klist;
@@ -475,6 +491,7 @@ int mm_partial_dev(Ctx *c, const uint64_t *d_A, int s, int nbr, int levelA, int 
     }
     tm.mark(-1);
     tm.finish(g_last_ms);
+    g_last_ms[4] = g_mac_kernel_ms;
     SFG_CUDA(c, cudaStreamSynchronize(c->stream));
     return 0;
 }
@@ -493,6 +510,7 @@ int mm_finish_dev(Ctx *c, Cache *ca, int s, int maxLevel, const uint64_t *d_cv, 
     if (run_giant(c, ca, s, d_cv + (size_t)g_lo * per_g, g_lo, g_hi, d_out, scr)) return -1;
     tm.mark(-1);
     tm.finish(g_last_ms);
+    g_last_ms[4] = g_mac_kernel_ms;
     return 0;
 }
 
@@ -507,7 +525,7 @@ int rotate_right_dev(Ctx *c, int level, const uint64_t *d_in, int nct, int nrot,
     for (int t = 0; t < nct; t++) offs[t] = (long long)(t * ct);
     Buf doffs;
     if (doffs.alloc(c, std::max(1, nct) * sizeof(long long))) return -1;
-    SFG_CUDA(c, cudaMemcpyAsync(doffs.p, offs.data(), nct * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
+    SFG_CUDA(c, cudaMemcpyAsync(doffs.p, offs.data(), nct * sizeof(long long), cudaMemcpyDefault, c->stream));
     Scratch scr;
     if (scr.ensure(c, nct, nl)) return -1;
     KsBatch kb;
@@ -558,12 +576,12 @@ int encode_diag_host(Ctx *c, const Geno *g, int bi, int shift, int nrot, int lev
     Buf dj, dout, dco;
     if (dj.alloc(c, jobs.size() * sizeof(EncJob)) || dout.alloc(c, jobs.size() * (size_t)nl * N * 8)) return -1;
     if (coeffs && dco.alloc(c, jobs.size() * (size_t)N * 8)) return -1;
-    SFG_CUDA(c, cudaMemcpyAsync(dj.p, jobs.data(), jobs.size() * sizeof(EncJob), cudaMemcpyHostToDevice, c->stream));
+    SFG_CUDA(c, cudaMemcpyAsync(dj.p, jobs.data(), jobs.size() * sizeof(EncJob), cudaMemcpyDefault, c->stream));
     if (launch_encode(c, g->d, g->ncols, dj.as<EncJob>(), (int)jobs.size(), nl, mont, dout.as<uint64_t>(), coeffs ? dco.as<long long>() : nullptr, c->stream)) return -1;
     SFG_CUDA(c, cudaStreamSynchronize(c->stream));
     for (size_t k = 0; k < jobs.size(); k++) {
-        SFG_CUDA(c, cudaMemcpy(out + (size_t)which[k] * nl * N, dout.as<uint64_t>() + k * (size_t)nl * N, (size_t)nl * N * 8, cudaMemcpyDeviceToHost));
-        if (coeffs) SFG_CUDA(c, cudaMemcpy(coeffs + (size_t)which[k] * N, dco.as<long long>() + k * (size_t)N, (size_t)N * 8, cudaMemcpyDeviceToHost));
+        SFG_CUDA(c, cudaMemcpy(out + (size_t)which[k] * nl * N, dout.as<uint64_t>() + k * (size_t)nl * N, (size_t)nl * N * 8, cudaMemcpyDefault));
+        if (coeffs) SFG_CUDA(c, cudaMemcpy(coeffs + (size_t)which[k] * N, dco.as<long long>() + k * (size_t)N, (size_t)N * 8, cudaMemcpyDefault));
     }
     return 0;
 }

@@ -8,7 +8,8 @@
 namespace sfg {
 
 struct Geno {
-    Ctx *c = nullptr;
+    Ctx *c = nullptr;             // may dangle after sfg_ctx_destroy: only `device` is used on release
+    int device = 0;
     size_t nrows = 0, ncols = 0, filled = 0;
     int8_t *d = nullptr;  // device, row-major nrows x ncols
     std::atomic<int> refs{1};
@@ -16,6 +17,7 @@ struct Geno {
 
 struct Cache {
     Ctx *c = nullptr;
+    int device = 0;
     Geno *g = nullptr;            // retained (needed when diagonals are regenerated on the fly)
     bool own_geno_copy = false;
     int maxLevel = 0, L = 0;      // L = maxLevel limbs are used by the MAC
@@ -68,6 +70,7 @@ int rotate_right_dev(Ctx *c, int level, const uint64_t *d_in, int nct, int nrot,
 int encode_diag_host(Ctx *c, const Geno *g, int bi, int shift, int nrot, int level, bool mont, uint64_t *out, uint8_t *present,
                      int64_t *coeffs);
 
-extern thread_local float g_last_ms[4];
+extern thread_local float g_last_ms[5];  // baby, mac phase, giant, total, mac kernel only
+extern thread_local float g_mac_kernel_ms;
 
 }  // namespace sfg

@@ -14,6 +14,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import weakref
 
 import numpy as np
 
@@ -52,9 +53,12 @@ class CryptoParams:
         if rc != 0:
             raise SfgError("sfg_ctx_create: " + self.L.sfg_last_error(None).decode())
         self.h = h
+        self._children = weakref.WeakSet()
 
     def close(self):
         if getattr(self, "h", None):
+            for ch in list(self._children):  # handles that live on this context go first
+                ch.close()
             self.L.sfg_ctx_destroy(self.h)
             self.h = None
 
@@ -100,9 +104,9 @@ class CryptoParams:
         return int(out[0]), int(out[1])
 
     def last_timings(self):
-        out = (C.c_float * 4)()
+        out = (C.c_float * 5)()
         self.L.sfg_ctx_last_timings(self.h, out)
-        return dict(baby_ms=out[0], mac_ms=out[1], giant_ms=out[2], total_ms=out[3])
+        return dict(baby_ms=out[0], mac_ms=out[1], giant_ms=out[2], total_ms=out[3], mac_kernel_ms=out[4])
 
     # -- lattice primitives (parity-test surface) ----------------------------------------------------
     def NTT(self, polys: np.ndarray, limb_idx, inverse=False) -> np.ndarray:
@@ -147,6 +151,7 @@ class GenoFileStream:
         h = C.c_void_p()
         cps._check(cps.L.sfg_geno_create(cps.h, self.nrows, self.ncols, C.byref(h)), "sfg_geno_create")
         self.h = h
+        cps._children.add(self)
 
     @classmethod
     def from_matrix(cls, cps: CryptoParams, X: np.ndarray, chunk_rows: int = 1 << 14) -> "GenoFileStream":
@@ -198,6 +203,7 @@ class DiagCache:
 
     def __init__(self, cps: CryptoParams, h):
         self.cps, self.h = cps, h
+        cps._children.add(self)
         n, b, m, mc, nb = C.c_size_t(), C.c_size_t(), C.c_int(), C.c_int(), C.c_int()
         cps.L.sfg_cache_info(h, C.byref(n), C.byref(b), C.byref(m), C.byref(mc), C.byref(nb))
         self.num_polys, self.bytes, self.materialised, self.m_ct, self.num_block_rows = n.value, b.value, bool(m.value), mc.value, nb.value
