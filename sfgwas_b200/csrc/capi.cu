@@ -260,7 +260,7 @@ void sfg_cache_destroy(sfg_cache *cache) {
 int sfg_cache_info(const sfg_cache *cache, size_t *num_polys, size_t *bytes, int *materialised, int *m_ct, int *nbr) {
     const Cache *ca = cache->ca;
     if (num_polys) *num_polys = ca->npoly;
-    if (bytes) *bytes = ca->materialised ? ca->npoly * (size_t)ca->L * ca->c->N * 8 : 0;
+    if (bytes) *bytes = ca->materialised ? ca->npoly * (size_t)ca->lay.bytes : 0;
     if (materialised) *materialised = ca->materialised ? 1 : 0;
     if (m_ct) *m_ct = ca->m_ct;
     if (nbr) *nbr = ca->nbr;
@@ -270,12 +270,23 @@ int sfg_cache_get_diag(sfg_ctx *h, const sfg_cache *cache, int bi, int shift, in
     Ctx *c = &h->c;
     const Cache *ca = cache->ca;
     if (bi < 0 || bi >= ca->nbr || shift < 0 || shift >= ca->slots || bj < 0 || bj >= ca->m_ct) SFG_FAIL(c, "cache_get_diag: index out of range");
-    const long long po = ca->pidx[((size_t)bi * ca->slots + shift) * ca->m_ct + bj];
-    *present = po >= 0;
-    if (po < 0) return 0;
+    const int pi = ca->pidx[((size_t)bi * ca->slots + shift) * ca->m_ct + bj];
+    *present = pi >= 0;
+    if (pi < 0) return 0;
     if (!ca->materialised) SFG_FAIL(c, "cache is not materialised (diagonals are regenerated on the fly)");
     SFG_CUDA(c, cudaSetDevice(c->device));
-    SFG_CUDA(c, cudaMemcpy(out, ca->P + po, (size_t)ca->L * c->N * 8, cudaMemcpyDefault));
+    const size_t N = c->N;
+    for (int l = 0; l < ca->L; l++) {
+        const unsigned char *src = ca->P + (size_t)pi * ca->lay.bytes + ca->lay.off[l];
+        if (ca->lay.es[l] == 8) {
+            SFG_CUDA(c, cudaMemcpy(out + l * N, src, N * 8, cudaMemcpyDefault));
+        } else {  // packed narrow limb (plain u32): present it in the reference's cache form b*2^64 mod q
+            std::vector<uint32_t> tmp(N);
+            SFG_CUDA(c, cudaMemcpy(tmp.data(), src, N * 4, cudaMemcpyDefault));
+            const uint64_t q = c->mod[l], r64 = c->lc_h[l].r64;
+            for (size_t k = 0; k < N; k++) out[l * N + k] = h_mulmod(tmp[k], r64, q);
+        }
+    }
     return 0;
 }
 
@@ -406,20 +417,20 @@ int sfg_ct_add(sfg_ctx *h, const uint64_t *a, const uint64_t *b, int ncts, int n
     if (da.alloc(c, n * 8) || db.alloc(c, n * 8)) return -1;
     SFG_CUDA(c, cudaMemcpyAsync(da.p, a, n * 8, cudaMemcpyDefault, c->stream));
     SFG_CUDA(c, cudaMemcpyAsync(db.p, b, n * 8, cudaMemcpyDefault, c->stream));
-    std::vector<long long> offs(ncts);
-    for (int t = 0; t < ncts; t++) offs[t] = (long long)t * 2 * nl * c->N;
-    Buf doffs;
-    if (doffs.alloc(c, std::max(1, ncts) * sizeof(long long))) return -1;
+    std::vector<long long> offs(ncts), offs_b(ncts);
+    for (int t = 0; t < ncts; t++) { offs[t] = (long long)t * 2 * nl * c->N; offs_b[t] = offs[t] * 8; }
+    Buf doffs, doffs_b;
+    if (doffs.alloc(c, std::max(1, ncts) * sizeof(long long)) || doffs_b.alloc(c, std::max(1, ncts) * sizeof(long long))) return -1;
     SFG_CUDA(c, cudaMemcpyAsync(doffs.p, offs.data(), ncts * sizeof(long long), cudaMemcpyDefault, c->stream));
+    SFG_CUDA(c, cudaMemcpyAsync(doffs_b.p, offs_b.data(), ncts * sizeof(long long), cudaMemcpyDefault, c->stream));
     KsBatch kb{};
     kb.nct = ncts;
     kb.in = da.as<uint64_t>();
     kb.in_off = doffs.as<long long>();
     kb.in_nl = nl;
-    kb.out = db.as<uint64_t>();
-    kb.out_off = doffs.as<long long>();
-    kb.out_nl = nl;
-    kb.out_limbs = nl;
+    kb.out = db.p;
+    kb.out_off = doffs_b.as<long long>();
+    kb.out_layout = make_layout(c, nl, false);
     kb.accumulate = true;
     if (launch_copy_add(c, kb, c->stream)) return -1;
     SFG_CUDA(c, cudaMemcpyAsync(out, db.p, n * 8, cudaMemcpyDefault, c->stream));

@@ -3,7 +3,7 @@
 #include <cstdlib>
 #include <cstring>
 
-#include "ctx.h"
+#include "kernels.h"
 
 namespace sfg {
 
@@ -76,6 +76,20 @@ int ctx_build_tables(Ctx *c, const uint64_t *psi_opt) {
     const double err = c->scale * 1.1102230246251565e-16 * std::log2(n) * 4.0 / std::sqrt(n);
     c->enc_delta = std::min(0.2, std::max(1e-9, 64.0 * err));
     return 0;
+}
+
+PolyLayout make_layout(const Ctx *c, int nl, bool packed) {
+    PolyLayout lay{};
+    lay.nl = nl;
+    long long off = 0;
+    // wide limbs first keeps every limb 16-byte aligned regardless of N
+    for (int l = 0; l < nl; l++) {
+        lay.es[l] = (packed && c->mod[l] < (1ULL << 32)) ? 4 : 8;
+        lay.off[l] = off;
+        off += (long long)c->N * lay.es[l];
+    }
+    lay.bytes = off;
+    return lay;
 }
 
 static void fill_bc(const Ctx *c, const int *src, int ns, int tgt, BaseConv &b) {

@@ -9,6 +9,17 @@ struct LimbSel {
     int idx[kMaxLimbs];
 };
 
+// Byte layout of one [nl][N] polynomial record with a per-limb element size: 8 = uint64 residues (the reference's
+// layout; plaintext diagonals in Montgomery form), 4 = PACKED uint32 residues for moduli < 2^32 (plain, not Montgomery).
+constexpr int kMaxLayoutLimbs = 16;
+struct PolyLayout {
+    int nl;
+    int es[kMaxLayoutLimbs];
+    long long off[kMaxLayoutLimbs];
+    long long bytes;
+};
+PolyLayout make_layout(const Ctx *c, int nl, bool packed);
+
 // ---- NTT (kernels_ntt.cu) ----
 // Transforms npoly polynomials. poly p: group g = p / sel.n, k = p % sel.n; src = src_base + g*src_gstride + k*N,
 // dst likewise; modulus index = sel.idx[k].  In-place allowed (src == dst with equal strides).
@@ -32,15 +43,16 @@ struct EncJob {
     int r, cdim;     // block dimensions (<= slots)
     int shift;       // diagonal index in [0, slots)
     int nrot;        // right rotation applied before encoding (d*giant)
-    long long out_off;  // element offset of the [nl][N] output polynomial
+    long long out_off;  // BYTE offset of the output polynomial record
 };
-int launch_encode(Ctx *c, const int8_t *X, size_t ld, const EncJob *jobs_dev, int njobs, int nl, bool mont, uint64_t *out,
+// lay: output record layout (limbs 0..lay.nl-1). 8-byte limbs are stored in Montgomery form iff mont; 4-byte limbs plain.
+int launch_encode(Ctx *c, const int8_t *X, size_t ld, const EncJob *jobs_dev, int njobs, const PolyLayout &lay, bool mont, void *out,
                   long long *coeff_out /* optional [njobs][N] int64 coefficient-domain message, may be null */, cudaStream_t st);
 
 // ---- output-stationary MAC + Montgomery reduce (kernels_mac.cu) ----
-// R: rotation cache [K][nrows][L][N]; P: plaintext diagonals, element offsets poff[col*K + k] (-1 = nil);
-// cv: [ncols][nrows][L][N] canonical residues.
-int launch_mac(Ctx *c, const uint64_t *R, const uint64_t *P, const long long *poff, int K, int nrows, int ncols, int L,
+// R: rotation cache, record (k*nrows + row) of layout `lay`; P: plaintext diagonal records of the same layout, record index
+// pidx[col*K + k] (-1 = nil);  cv: [ncols][nrows][lay.nl][N] canonical uint64 residues.
+int launch_mac(Ctx *c, const void *R, const void *P, const int *pidx, int K, int nrows, int ncols, const PolyLayout &lay,
                uint64_t *cv, cudaStream_t st);
 
 // ---- key-switch + automorphism (kernels_ks.cu) ----
@@ -51,10 +63,9 @@ struct KsBatch {
     const long long *in_off;   // device [nct]; must be the arithmetic progression in_first + k*in_stride
     long long in_first, in_stride;
     int in_nl;              // limb count of the stored input cts (>= level+1)
-    uint64_t *out;          // ct k at out + out_off[k], layout [2][out_nl][N]; only limbs < out_limbs are produced
-    const long long *out_off;  // device [nct]
-    int out_nl;
-    int out_limbs;
+    void *out;              // ct k at (char*)out + out_off[k] BYTES: two consecutive records of out_layout (c0 then c1);
+    const long long *out_off;  // device [nct]                          only limbs < out_layout.nl are produced
+    PolyLayout out_layout;
     bool accumulate;        // out += result (mod q) instead of out = result
     // scratch (device): c2 [nct][nl][N], acc [nct][2][nl+nP][N]
     uint64_t *c2, *acc;

@@ -40,9 +40,9 @@ constexpr int kMaxFlag = 2048;
 
 template <int NPER>
 __global__ void __launch_bounds__(1024, 1)
-k_encode(const int8_t *__restrict__ X, size_t ld, const EncJob *__restrict__ jobs, int logN, int nl, int mont, double sc,
+k_encode(const int8_t *__restrict__ X, size_t ld, const EncJob *__restrict__ jobs, int logN, PolyLayout lay, int mont, double sc,
          double delta, const double2 *__restrict__ roots, const int *__restrict__ rot5, const double2 *__restrict__ ddcos,
-         const uint64_t *__restrict__ tw, const LimbConst *__restrict__ lcs, uint64_t *__restrict__ out,
+         const uint64_t *__restrict__ tw, const LimbConst *__restrict__ lcs, unsigned char *__restrict__ out,
          long long *__restrict__ coeff_out, unsigned long long *__restrict__ stats) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int N = 1 << logN, n = N >> 1, M = N << 1, logn = logN - 1;
@@ -168,7 +168,7 @@ k_encode(const int8_t *__restrict__ X, size_t ld, const EncJob *__restrict__ job
     }
 
     // 5. RNS reduce, NTT per limb, Montgomery form, store
-    for (int l = 0; l < nl; l++) {
+    for (int l = 0; l < lay.nl; l++) {
         const LimbConst lc = lcs[l];
         const NttTab tab = ntt_tab(tw, l, N);
 #pragma unroll
@@ -180,17 +180,22 @@ k_encode(const int8_t *__restrict__ X, size_t ld, const EncJob *__restrict__ job
         }
         __syncthreads();
         ntt_fwd_smem(s, logN, 1, 0, tab, lc.q);
-        uint64_t *o = out + job.out_off + (size_t)l * N;
+        unsigned char *o = out + job.out_off + lay.off[l];
+        if (lay.es[l] == 4) {  // packed narrow limb: plain residue
 #pragma unroll
-        for (int r = 0; r < NPER; r++) {
-            const uint64_t x = s[tid + r * T];
-            o[tid + r * T] = mont ? mform(x, lc) : x;
+            for (int r = 0; r < NPER; r++) reinterpret_cast<uint32_t *>(o)[tid + r * T] = (uint32_t)s[tid + r * T];
+        } else {
+#pragma unroll
+            for (int r = 0; r < NPER; r++) {
+                const uint64_t x = s[tid + r * T];
+                reinterpret_cast<uint64_t *>(o)[tid + r * T] = mont ? mform(x, lc) : x;
+            }
         }
         __syncthreads();
     }
 }
 
-int launch_encode(Ctx *c, const int8_t *X, size_t ld, const EncJob *jobs_dev, int njobs, int nl, bool mont, uint64_t *out,
+int launch_encode(Ctx *c, const int8_t *X, size_t ld, const EncJob *jobs_dev, int njobs, const PolyLayout &lay, bool mont, void *out,
                   long long *coeff_out, cudaStream_t st) {
     if (njobs <= 0) return 0;
     const int logN = c->logN, N = c->N, n = c->slots;
@@ -201,12 +206,12 @@ int launch_encode(Ctx *c, const int8_t *X, size_t ld, const EncJob *jobs_dev, in
     const double sc = c->scale / (double)n;
     if (NPER == 16) {
         SFG_CUDA(c, cudaFuncSetAttribute(k_encode<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_encode<16><<<njobs, T, smem, st>>>(X, ld, jobs_dev, logN, nl, mont ? 1 : 0, sc, c->enc_delta, c->roots, c->rot5, c->ddcos,
-                                            c->tw, c->lc, out, coeff_out, c->enc_stats);
+        k_encode<16><<<njobs, T, smem, st>>>(X, ld, jobs_dev, logN, lay, mont ? 1 : 0, sc, c->enc_delta, c->roots, c->rot5, c->ddcos,
+                                            c->tw, c->lc, (unsigned char *)out, coeff_out, c->enc_stats);
     } else {
         SFG_CUDA(c, cudaFuncSetAttribute(k_encode<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_encode<8><<<njobs, T, smem, st>>>(X, ld, jobs_dev, logN, nl, mont ? 1 : 0, sc, c->enc_delta, c->roots, c->rot5, c->ddcos,
-                                           c->tw, c->lc, out, coeff_out, c->enc_stats);
+        k_encode<8><<<njobs, T, smem, st>>>(X, ld, jobs_dev, logN, lay, mont ? 1 : 0, sc, c->enc_delta, c->roots, c->rot5, c->ddcos,
+                                           c->tw, c->lc, (unsigned char *)out, coeff_out, c->enc_stats);
     }
     SFG_LAUNCHED(c, "k_encode", st);
     return 0;

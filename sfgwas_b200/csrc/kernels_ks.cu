@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(1024, 1)
 k_ks_moddown(const uint64_t *__restrict__ in, const long long *__restrict__ in_off, int in_nl, const uint64_t *__restrict__ acc,
              const BaseConv *__restrict__ md, const uint64_t *__restrict__ pinv, const uint32_t *__restrict__ perm, int level,
              int nQ, int nP, int logN, const uint64_t *__restrict__ tw, const LimbConst *__restrict__ lcs,
-             uint64_t *__restrict__ out, const long long *__restrict__ out_off, int out_nl, int accumulate) {
+             unsigned char *__restrict__ out, const long long *__restrict__ out_off, PolyLayout olay, int accumulate) {
     extern __shared__ __align__(16) uint64_t s[];
     const int N = 1 << logN, nl = level + 1, nt = nl + nP;
     const int l = blockIdx.x, comp = blockIdx.y, ct = blockIdx.z;
@@ -142,30 +142,48 @@ k_ks_moddown(const uint64_t *__restrict__ in, const long long *__restrict__ in_o
         s[k] = v;
     }
     __syncthreads();
-    uint64_t *o = out + out_off[ct] + ((size_t)comp * out_nl + l) * N;
+    unsigned char *ob = out + out_off[ct] + (size_t)comp * olay.bytes + olay.off[l];
+    if (olay.es[l] == 4) {
+        uint32_t *o = reinterpret_cast<uint32_t *>(ob);
 #pragma unroll
-    for (int r = 0; r < NPER; r++) {
-        const int k = tid + r * T;
-        uint64_t v = s[perm[k]];  // PermuteNTTWithIndexLvl: out[k] = in[index[k]]
-        if (accumulate) v = add_mod(v, o[k], lc.q);
-        o[k] = v;
+        for (int r = 0; r < NPER; r++) {
+            const int k = tid + r * T;
+            uint64_t v = s[perm[k]];
+            if (accumulate) v = add_mod(v, (uint64_t)o[k], lc.q);
+            o[k] = (uint32_t)v;
+        }
+    } else {
+        uint64_t *o = reinterpret_cast<uint64_t *>(ob);
+#pragma unroll
+        for (int r = 0; r < NPER; r++) {
+            const int k = tid + r * T;
+            uint64_t v = s[perm[k]];  // PermuteNTTWithIndexLvl: out[k] = in[index[k]]
+            if (accumulate) v = add_mod(v, o[k], lc.q);
+            o[k] = v;
+        }
     }
 }
 
 __global__ void k_copy_add(const uint64_t *__restrict__ in, const long long *__restrict__ in_off, int in_nl,
-                           uint64_t *__restrict__ out, const long long *__restrict__ out_off, int out_nl, int out_limbs, int N,
+                           unsigned char *__restrict__ out, const long long *__restrict__ out_off, PolyLayout olay, int N,
                            const LimbConst *__restrict__ lcs, int accumulate) {
-    const int l = blockIdx.x % out_limbs, comp = blockIdx.x / out_limbs, ct = blockIdx.y;
+    const int l = blockIdx.x % olay.nl, comp = blockIdx.x / olay.nl, ct = blockIdx.y;
     const uint64_t q = lcs[l].q;
     const uint64_t *src = in + in_off[ct] + ((size_t)comp * in_nl + l) * N;
-    uint64_t *dst = out + out_off[ct] + ((size_t)comp * out_nl + l) * N;
-    for (int k = threadIdx.x; k < N; k += blockDim.x) dst[k] = accumulate ? add_mod(dst[k], src[k], q) : src[k];
+    unsigned char *db = out + out_off[ct] + (size_t)comp * olay.bytes + olay.off[l];
+    if (olay.es[l] == 4) {
+        uint32_t *dst = reinterpret_cast<uint32_t *>(db);
+        for (int k = threadIdx.x; k < N; k += blockDim.x) dst[k] = (uint32_t)(accumulate ? add_mod((uint64_t)dst[k], src[k], q) : src[k]);
+    } else {
+        uint64_t *dst = reinterpret_cast<uint64_t *>(db);
+        for (int k = threadIdx.x; k < N; k += blockDim.x) dst[k] = accumulate ? add_mod(dst[k], src[k], q) : src[k];
+    }
 }
 
 int launch_copy_add(Ctx *c, const KsBatch &b, cudaStream_t st) {
     if (b.nct <= 0) return 0;
-    dim3 g(2 * b.out_limbs, b.nct);
-    k_copy_add<<<g, 256, 0, st>>>(b.in, b.in_off, b.in_nl, b.out, b.out_off, b.out_nl, b.out_limbs, c->N, c->lc, b.accumulate ? 1 : 0);
+    dim3 g(2 * b.out_layout.nl, b.nct);
+    k_copy_add<<<g, 256, 0, st>>>(b.in, b.in_off, b.in_nl, (unsigned char *)b.out, b.out_off, b.out_layout, c->N, c->lc, b.accumulate ? 1 : 0);
     SFG_LAUNCHED(c, "k_copy_add", st);
     return 0;
 }
@@ -199,9 +217,9 @@ static int rotate_impl(Ctx *c, const KsBatch &b, const GaloisKey &key, cudaStrea
     if (launch_ntt(c, b.acc + (size_t)nl * N, (size_t)nt * N, b.acc + (size_t)nl * N, (size_t)nt * N, b.nct * 2 * c->nP, selp, true, st)) return -1;
     // 4. mod-down, + c0, automorphism, store / accumulate
     {
-        dim3 g(b.out_limbs, 2, b.nct);
+        dim3 g(b.out_layout.nl, 2, b.nct);
         k_ks_moddown<NPER><<<g, T, smem, st>>>(b.in, b.in_off, b.in_nl, b.acc, md, pinv, key.perm, b.level, c->nQ, c->nP, c->logN, c->tw,
-                                              c->lc, b.out, b.out_off, b.out_nl, b.accumulate ? 1 : 0);
+                                              c->lc, (unsigned char *)b.out, b.out_off, b.out_layout, b.accumulate ? 1 : 0);
         SFG_LAUNCHED(c, "k_ks_moddown", st);
     }
     return 0;

@@ -75,7 +75,7 @@ static int block_cols(const Cache *ca, int bj) {
 // ---------------------------------------------------------------------------------------------------------------
 // Preprocess (gwas/matmult.go:914-1041)
 // ---------------------------------------------------------------------------------------------------------------
-static int encode_jobs(Ctx *c, const Cache *ca, const std::vector<EncJob> &jobs, uint64_t *P) {
+static int encode_jobs(Ctx *c, const Cache *ca, const std::vector<EncJob> &jobs, void *P) {
     if (jobs.empty()) return 0;
     Buf dj;
     if (dj.alloc(c, jobs.size() * sizeof(EncJob))) return -1;
@@ -83,7 +83,7 @@ static int encode_jobs(Ctx *c, const Cache *ca, const std::vector<EncJob> &jobs,
     const size_t chunk = 1 << 20;
     for (size_t o = 0; o < jobs.size(); o += chunk) {
         const int n = (int)std::min(chunk, jobs.size() - o);
-        if (launch_encode(c, ca->g->d, ca->ncols, dj.as<EncJob>() + o, n, ca->L, true, P, nullptr, c->stream)) return -1;
+        if (launch_encode(c, ca->g->d, ca->ncols, dj.as<EncJob>() + o, n, ca->lay, true, P, nullptr, c->stream)) return -1;
     }
     SFG_CUDA(c, cudaStreamSynchronize(c->stream));
     return 0;
@@ -100,6 +100,8 @@ int cache_build(Ctx *c, Geno *g, int maxLevel, Cache **out) {
     g->refs++;
     ca->maxLevel = maxLevel;
     ca->L = maxLevel;  // limb-COUNT quirk: accumulators cover limbs 0..maxLevel-1 (gwas/matmult.go:1125 -> :231, App. A.4)
+    if (maxLevel > kMaxLayoutLimbs) SFG_FAIL(c, "maxLevel %d > %d not supported", maxLevel, kMaxLayoutLimbs);
+    ca->lay = make_layout(c, ca->L, true);
     ca->slots = c->slots;
     ca->d = c->d;
     ca->nrows = g->nrows;
@@ -111,7 +113,6 @@ int cache_build(Ctx *c, Geno *g, int maxLevel, Cache **out) {
     ca->giant.assign((size_t)nbr * d, 0);
     ca->shiftT.assign((size_t)nbr * slots, 0);
     ca->pidx.assign((size_t)nbr * slots * m_ct, -1);
-    const size_t LN = (size_t)ca->L * c->N;
     size_t npoly = 0;
     for (int bi = 0; bi < nbr; bi++) {
         const int nr = block_rows(ca, bi);
@@ -120,7 +121,7 @@ int cache_build(Ctx *c, Geno *g, int maxLevel, Cache **out) {
             for (int bj = 0; bj < m_ct; bj++) {
                 if (diag_exists(nr, block_cols(ca, bj), slots, shift)) {
                     any = true;
-                    ca->pidx[((size_t)bi * slots + shift) * m_ct + bj] = (long long)(npoly++ * LN);
+                    ca->pidx[((size_t)bi * slots + shift) * m_ct + bj] = (int)(npoly++);
                 }
             }
             if (any) {  // matmult.go:962-974
@@ -151,7 +152,8 @@ int cache_build(Ctx *c, Geno *g, int maxLevel, Cache **out) {
         SFG_CUDA(c, cudaMemGetInfo(&fr, &tot));
         budget = (size_t)(0.70 * (double)fr);
     }
-    const size_t bytes = npoly * LN * sizeof(uint64_t);
+    if (npoly > 0x7fffffffULL) SFG_FAIL(c, "too many diagonal polynomials");
+    const size_t bytes = npoly * (size_t)ca->lay.bytes;
     if (bytes <= budget) {
         cudaError_t e = cudaMalloc(&ca->P, bytes);
         if (e == cudaSuccess) {
@@ -160,10 +162,11 @@ int cache_build(Ctx *c, Geno *g, int maxLevel, Cache **out) {
             for (int bi = 0; bi < nbr; bi++)
                 for (int shift = 0; shift < slots; shift++)
                     for (int bj = 0; bj < m_ct; bj++) {
-                        const long long po = ca->pidx[((size_t)bi * slots + shift) * m_ct + bj];
-                        if (po < 0) continue;
+                        const int pi = ca->pidx[((size_t)bi * slots + shift) * m_ct + bj];
+                        if (pi < 0) continue;
                         // EncodeDiagWithEncoder(blockVec, -shift, d*giant, maxLevel, enc)  matmult.go:1024
-                        jobs.push_back(EncJob{bi * slots, bj * slots, block_rows(ca, bi), block_cols(ca, bj), shift, d * (shift / d), po});
+                        jobs.push_back(EncJob{bi * slots, bj * slots, block_rows(ca, bi), block_cols(ca, bj), shift, d * (shift / d),
+                                              (long long)pi * ca->lay.bytes});
                     }
             if (encode_jobs(c, ca, jobs, ca->P)) {
                 cache_destroy(ca);
@@ -252,8 +255,9 @@ static int build_rot_cache(Ctx *c, const Cache *ca, const uint64_t *d_A, int s, 
             klocal[(size_t)ca->kbi[k] * d + ca->kb[k]] = (int)klist.size();
             klist.push_back((int)k);
         }
-    const size_t LN = (size_t)L * N;
-    if (R.alloc(c, klist.size() * nrows * LN * 8)) return -1;
+    const size_t RB = (size_t)ca->lay.bytes;  // bytes of one (k, row) record
+    (void)L;
+    if (R.alloc(c, klist.size() * nrows * RB)) return -1;
     const size_t ctA = (size_t)2 * nlA * N;
     // offsets for every batch, uploaded once
     struct Batch { int b, nct; long long first, stride; size_t off_pos; };
@@ -269,14 +273,14 @@ static int build_rot_cache(Ctx *c, const Cache *ca, const uint64_t *d_A, int s, 
             for (int t = 0; t < s * nbr; t++) offs.push_back((long long)t * ctA);
             for (int t = 0; t < s * nbr; t++) {
                 const int i = t / nbr, bi = t % nbr;
-                offs.push_back((long long)(((size_t)klocal[(size_t)bi * d + b] * nrows + 2 * i) * LN));
+                offs.push_back((long long)(((size_t)klocal[(size_t)bi * d + b] * nrows + 2 * i) * RB));
             }
             batches.push_back(bt);
         } else {
             for (int bi : bis) {
                 Batch bt{b, s, (long long)(bi * ctA), (long long)(nbr * ctA), offs.size()};
                 for (int i = 0; i < s; i++) offs.push_back((long long)(((size_t)i * nbr + bi) * ctA));
-                for (int i = 0; i < s; i++) offs.push_back((long long)(((size_t)klocal[(size_t)bi * d + b] * nrows + 2 * i) * LN));
+                for (int i = 0; i < s; i++) offs.push_back((long long)(((size_t)klocal[(size_t)bi * d + b] * nrows + 2 * i) * RB));
                 batches.push_back(bt);
             }
         }
@@ -293,10 +297,9 @@ static int build_rot_cache(Ctx *c, const Cache *ca, const uint64_t *d_A, int s, 
         kb.in_first = bt.first;
         kb.in_stride = bt.stride;
         kb.in_nl = nlA;
-        kb.out = R.as<uint64_t>();
+        kb.out = R.p;
         kb.out_off = scr.offs.as<long long>() + bt.off_pos + bt.nct;
-        kb.out_nl = L;
-        kb.out_limbs = L;  // limb index maxLevel of the rotated ct is never read by the MAC (App. A.4)
+        kb.out_layout = ca->lay;  // limb index maxLevel of the rotated ct is never read by the MAC (App. A.4)
         kb.accumulate = false;
         kb.c2 = scr.c2.as<uint64_t>();
         kb.acc = scr.acc.as<uint64_t>();
@@ -315,13 +318,14 @@ static int build_rot_cache(Ctx *c, const Cache *ca, const uint64_t *d_A, int s, 
 // (2) MAC for the giant steps gact[gi_lo .. gi_hi) -> d_cv [(gi-gi_lo)*m_ct + bj][row][l][N]
 //     gwas/matmult.go:1154-1168 (CPMultAccWithoutMRedV2) + :1203 (ModularReduceV2)
 // ---------------------------------------------------------------------------------------------------------------
-static int run_mac(Ctx *c, const Cache *ca, const uint64_t *R, const std::vector<int> &klist, int s, int gi_lo, int gi_hi,
+static int run_mac(Ctx *c, const Cache *ca, const void *R, const std::vector<int> &klist, int s, int gi_lo, int gi_hi,
                    uint64_t *d_cv) {
     const int d = ca->d, m_ct = ca->m_ct, slots = ca->slots, L = ca->L, N = c->N;
     const int K = (int)klist.size(), ncols = (gi_hi - gi_lo) * m_ct;
     if (K == 0 || ncols == 0) return 0;
-    const size_t LN = (size_t)L * N;
-    std::vector<long long> poff((size_t)ncols * K, -1);
+    (void)L;
+    (void)N;
+    std::vector<int> poff((size_t)ncols * K, -1);
     std::vector<EncJob> jobs;  // only when the cache is not materialised
     size_t ntmp = 0;
     for (int gi = gi_lo; gi < gi_hi; gi++) {
@@ -332,32 +336,33 @@ static int run_mac(Ctx *c, const Cache *ca, const uint64_t *R, const std::vector
                 const int bi = ca->kbi[klist[kk]], b = ca->kb[klist[kk]];
                 const int shift = g * d + b;
                 if (shift >= slots) continue;
-                const long long po = ca->pidx[((size_t)bi * slots + shift) * m_ct + bj];
-                if (po < 0) continue;
+                const int pi = ca->pidx[((size_t)bi * slots + shift) * m_ct + bj];
+                if (pi < 0) continue;
                 if (ca->materialised) {
-                    poff[col * K + kk] = po;
+                    poff[col * K + kk] = pi;
                 } else {
-                    poff[col * K + kk] = (long long)(ntmp * LN);
-                    jobs.push_back(EncJob{bi * slots, bj * slots, block_rows(ca, bi), block_cols(ca, bj), shift, d * g, (long long)(ntmp * LN)});
+                    poff[col * K + kk] = (int)ntmp;
+                    jobs.push_back(EncJob{bi * slots, bj * slots, block_rows(ca, bi), block_cols(ca, bj), shift, d * g,
+                                          (long long)ntmp * ca->lay.bytes});
                     ntmp++;
                 }
             }
         }
     }
     Buf dpoff, tmpP;
-    if (dpoff.alloc(c, poff.size() * sizeof(long long))) return -1;
-    SFG_CUDA(c, cudaMemcpyAsync(dpoff.p, poff.data(), poff.size() * sizeof(long long), cudaMemcpyDefault, c->stream));
-    const uint64_t *P = ca->P;
+    if (dpoff.alloc(c, poff.size() * sizeof(int))) return -1;
+    SFG_CUDA(c, cudaMemcpyAsync(dpoff.p, poff.data(), poff.size() * sizeof(int), cudaMemcpyDefault, c->stream));
+    const void *P = ca->P;
     if (!ca->materialised) {
-        if (tmpP.alloc(c, std::max<size_t>(ntmp, 1) * LN * 8)) return -1;
-        if (encode_jobs(c, ca, jobs, tmpP.as<uint64_t>())) return -1;
-        P = tmpP.as<uint64_t>();
+        if (tmpP.alloc(c, std::max<size_t>(ntmp, 1) * (size_t)ca->lay.bytes)) return -1;
+        if (encode_jobs(c, ca, jobs, tmpP.p)) return -1;
+        P = tmpP.p;
     }
     cudaEvent_t e0, e1;  // the MAC kernel alone, on the stream it is launched on (bench.py roofline)
     SFG_CUDA(c, cudaEventCreate(&e0));
     SFG_CUDA(c, cudaEventCreate(&e1));
     SFG_CUDA(c, cudaEventRecord(e0, c->stream));
-    if (launch_mac(c, R, P, dpoff.as<long long>(), K, 2 * s, ncols, L, d_cv, c->stream)) return -1;
+    if (launch_mac(c, R, P, dpoff.as<int>(), K, 2 * s, ncols, ca->lay, d_cv, c->stream)) return -1;
     SFG_CUDA(c, cudaEventRecord(e1, c->stream));
     SFG_CUDA(c, cudaStreamSynchronize(c->stream));  // poff / tmpP are freed on return
     float ms = 0;
@@ -387,7 +392,7 @@ static int run_giant(Ctx *c, const Cache *ca, int s, const uint64_t *d_cv, int g
     const size_t out_pos = offs.size();
     for (int t = 0; t < nct; t++) {
         const int bj = t / s, i = t % s;
-        offs.push_back((long long)(((size_t)i * m_ct + bj) * 2 * LN));
+        offs.push_back((long long)(((size_t)i * m_ct + bj) * 2 * LN * 8));  // bytes
     }
     Buf doffs;
     if (doffs.alloc(c, offs.size() * sizeof(long long))) return -1;
@@ -405,8 +410,7 @@ static int run_giant(Ctx *c, const Cache *ca, int s, const uint64_t *d_cv, int g
         kb.in_nl = L;
         kb.out = d_out;
         kb.out_off = doffs.as<long long>() + out_pos;
-        kb.out_nl = L;
-        kb.out_limbs = L;
+        kb.out_layout = make_layout(c, L, false);
         kb.accumulate = true;
         kb.c2 = scr.c2.as<uint64_t>();
         kb.acc = scr.acc.as<uint64_t>();
@@ -458,7 +462,7 @@ int mm_compute_dev(Ctx *c, const uint64_t *d_A, int s, int nbr, int levelA, int 
     for (int g0 = 0; g0 < ng; g0 += gchunk) {
         const int g1 = std::min(ng, g0 + gchunk);
         tm.mark(1);
-        if (run_mac(c, ca, R.as<uint64_t>(), klist, s, g0, g1, cv.as<uint64_t>())) return -1;
+        if (run_mac(c, ca, R.p, klist, s, g0, g1, cv.as<uint64_t>())) return -1;
         tm.mark(2);
         if (run_giant(c, ca, s, cv.as<uint64_t>(), g0, g1, d_out, scr)) return -1;
     }
@@ -486,7 +490,7 @@ int mm_partial_dev(Ctx *c, const uint64_t *d_A, int s, int nbr, int levelA, int 
     tm.mark(1);
     if (klist.empty()) {
         SFG_CUDA(c, cudaMemsetAsync(d_cv, 0, total * 8, c->stream));
-    } else if (run_mac(c, ca, R.as<uint64_t>(), klist, s, 0, (int)ca->gact.size(), d_cv)) {
+    } else if (run_mac(c, ca, R.p, klist, s, 0, (int)ca->gact.size(), d_cv)) {
         return -1;
     }
     tm.mark(-1);
@@ -522,10 +526,12 @@ int rotate_right_dev(Ctx *c, int level, const uint64_t *d_in, int nct, int nrot,
     if (nrot < 0) nrot += slots;
     const size_t ct = (size_t)2 * nl * N;
     std::vector<long long> offs(nct);
-    for (int t = 0; t < nct; t++) offs[t] = (long long)(t * ct);
-    Buf doffs;
-    if (doffs.alloc(c, std::max(1, nct) * sizeof(long long))) return -1;
+    std::vector<long long> offs_b(nct);
+    for (int t = 0; t < nct; t++) { offs[t] = (long long)(t * ct); offs_b[t] = offs[t] * 8; }
+    Buf doffs, doffs_b;
+    if (doffs.alloc(c, std::max(1, nct) * sizeof(long long)) || doffs_b.alloc(c, std::max(1, nct) * sizeof(long long))) return -1;
     SFG_CUDA(c, cudaMemcpyAsync(doffs.p, offs.data(), nct * sizeof(long long), cudaMemcpyDefault, c->stream));
+    SFG_CUDA(c, cudaMemcpyAsync(doffs_b.p, offs_b.data(), nct * sizeof(long long), cudaMemcpyDefault, c->stream));
     Scratch scr;
     if (scr.ensure(c, nct, nl)) return -1;
     KsBatch kb;
@@ -537,9 +543,8 @@ int rotate_right_dev(Ctx *c, int level, const uint64_t *d_in, int nct, int nrot,
     kb.in_stride = (long long)ct;
     kb.in_nl = nl;
     kb.out = d_out;
-    kb.out_off = doffs.as<long long>();
-    kb.out_nl = nl;
-    kb.out_limbs = nl;
+    kb.out_off = doffs_b.as<long long>();
+    kb.out_layout = make_layout(c, nl, false);
     kb.accumulate = false;
     kb.c2 = scr.c2.as<uint64_t>();
     kb.acc = scr.acc.as<uint64_t>();
@@ -568,7 +573,7 @@ int encode_diag_host(Ctx *c, const Geno *g, int bi, int shift, int nrot, int lev
         const int nc = (int)std::min<size_t>((size_t)(bj + 1) * slots, g->ncols) - bj * slots;
         present[bj] = diag_exists(nr, nc, slots, shift) ? 1 : 0;
         if (present[bj]) {
-            jobs.push_back(EncJob{bi * slots, bj * slots, nr, nc, shift, ((nrot % slots) + slots) % slots, (long long)(jobs.size() * (size_t)nl * N)});
+            jobs.push_back(EncJob{bi * slots, bj * slots, nr, nc, shift, ((nrot % slots) + slots) % slots, (long long)(jobs.size() * (size_t)nl * N * 8)});
             which.push_back(bj);
         }
     }
@@ -577,7 +582,7 @@ int encode_diag_host(Ctx *c, const Geno *g, int bi, int shift, int nrot, int lev
     if (dj.alloc(c, jobs.size() * sizeof(EncJob)) || dout.alloc(c, jobs.size() * (size_t)nl * N * 8)) return -1;
     if (coeffs && dco.alloc(c, jobs.size() * (size_t)N * 8)) return -1;
     SFG_CUDA(c, cudaMemcpyAsync(dj.p, jobs.data(), jobs.size() * sizeof(EncJob), cudaMemcpyDefault, c->stream));
-    if (launch_encode(c, g->d, g->ncols, dj.as<EncJob>(), (int)jobs.size(), nl, mont, dout.as<uint64_t>(), coeffs ? dco.as<long long>() : nullptr, c->stream)) return -1;
+    if (launch_encode(c, g->d, g->ncols, dj.as<EncJob>(), (int)jobs.size(), make_layout(c, nl, false), mont, dout.p, coeffs ? dco.as<long long>() : nullptr, c->stream)) return -1;
     SFG_CUDA(c, cudaStreamSynchronize(c->stream));
     for (size_t k = 0; k < jobs.size(); k++) {
         SFG_CUDA(c, cudaMemcpy(out + (size_t)which[k] * nl * N, dout.as<uint64_t>() + k * (size_t)nl * N, (size_t)nl * N * 8, cudaMemcpyDefault));

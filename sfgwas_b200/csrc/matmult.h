@@ -25,9 +25,10 @@ struct Cache {
     size_t nrows = 0, ncols = 0;
     std::vector<uint8_t> baby, giant, shiftT;  // [nbr][d], [nbr][d], [nbr][slots]   (matmult.go:962-974)
     bool materialised = false;
-    uint64_t *P = nullptr;        // device compact [npoly][L][N], NTT + Montgomery form
+    PolyLayout lay{};             // record layout of cached diagonals and of the rotation cache (packed narrow limbs)
+    unsigned char *P = nullptr;   // device compact [npoly] records of `lay` (wide limbs: NTT + Montgomery form; narrow: plain u32)
     size_t npoly = 0;
-    std::vector<long long> pidx;  // host [(bi*slots+shift)*m_ct+bj] -> element offset into P or -1 (nil, matmult.go:703-705)
+    std::vector<int> pidx;        // host [(bi*slots+shift)*m_ct+bj] -> record index into P or -1 (nil, matmult.go:703-705)
     // K list: (bi, b) pairs with an active baby step, in (bi, b) order; kidx[bi*d+b] -> k or -1
     std::vector<int> kbi, kb, kidx;
     std::vector<int> gact;        // active giant indices (any block row)
