@@ -7,7 +7,8 @@
 // with row = (i, c) over the 2s ciphertext polynomials, k = (block row bi, baby step b), col = (giant g, block column bj).
 // The reference keeps u128 accumulators in memory under a mutex and streams the diagonals once.  Here the accumulators
 // live in registers (TR x TC per thread), the K loop is innermost, P is streamed from HBM exactly once, and the R / P
-// tiles of KB consecutive K steps are staged in shared memory by cp.async (LDGSTS, zero-fill for nil diagonals).
+// tiles of KB consecutive K steps are staged in shared memory by producer warps (cp.async / LDGSTS completing on
+// mbarriers); the consumer warps execute only LDS + MAC (no address math, no CTA-wide barrier).
 //
 // Only the canonical residue sum_k a_k*b_k mod q_l is observable, so the arithmetic is specialised by
 // limb width -- measured on B200 (profiles/microbench/mac_rate.cu): IMAD.WIDE.U32 issues at 32 lanes/clk/SM, so
@@ -22,14 +23,35 @@
 
 namespace sfg {
 
-__device__ __forceinline__ void cp_async16(void *smem, const void *gmem, int src_bytes) {
-    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(gmem), "r"(src_bytes));
+// ---- mbarrier / bulk-copy (TMA) primitives ----
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-template <int NWAIT>
-__device__ __forceinline__ void cp_async_wait() {
-    asm volatile("cp.async.wait_group %0;\n" ::"n"(NWAIT));
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// 16-byte global -> shared async copy (LDGSTS) with zero-fill when src_bytes == 0
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(smem_u32(smem)), "l"(gmem), "r"(src_bytes) : "memory");
+}
+// the executing thread arrives on `bar` once all its prior cp.async operations have completed (no pending-count increment)
+__device__ __forceinline__ void cp_async_mbar_arrive(uint64_t *bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
 }
 
 // ---- accumulators ----
@@ -79,88 +101,111 @@ __device__ __forceinline__ uint64_t finish_narrow(const AccN &A, const LimbConst
 }
 
 constexpr int kNB = 32;     // coefficients per CTA
-constexpr int kStages = 3;  // cp.async ring depth (each stage holds KB K-steps)
+constexpr int kStages = 4;  // pipeline depth (each stage holds KB K-steps)
 
 struct LimbList {
     int n;
     int idx[kMaxLayoutLimbs];
 };
 
-template <int TR, int TC, int CG, int RG, int KB, bool NARROW>
-__global__ void __launch_bounds__(kNB *CG *RG, 1)
+// Warp-specialised: warps 0 .. CG*RG-1 are consumers (LDS + MAC only); the last NPW warps are producers that fill the
+// stage ring with 16-byte cp.async (LDGSTS, zero-fill for nil diagonals / padding) and signal full[s] through
+// cp.async.mbarrier.arrive; consumers release a stage through empty[s].  No CTA-wide barrier inside the K loop.
+// (A first version issued one cp.async.bulk (TMA) per 128-256 B row: 3.4x slower -- per-copy overhead dominates.)
+template <int TR, int TC, int CG, int RG, int KB, int NPW, bool NARROW>
+__global__ void __launch_bounds__(kNB *(CG *RG + NPW), 1)
 k_mac(const char *__restrict__ R, const char *__restrict__ P, const int *__restrict__ pidx, int K, int nrows, int ncols, PolyLayout lay,
       LimbList limbs, int N, const LimbConst *__restrict__ lcs, uint64_t *__restrict__ cv, int Lcv) {
     using T = typename std::conditional<NARROW, uint32_t, uint64_t>::type;
-    constexpr int CB = CG * TC, RB = RG * TR, THREADS = kNB * CG * RG;
-    constexpr int ROWS = RB + CB;                       // smem rows per K-step: R rows then P rows
-    constexpr int PARTS = kNB * (int)sizeof(T) / 16;    // 16-byte chunks per row
-    constexpr int CHUNKS = KB * ROWS * PARTS;
-    constexpr int EPC = 16 / (int)sizeof(T);            // elements per chunk
-    extern __shared__ __align__(16) unsigned char sm_raw[];
-    T *sm = reinterpret_cast<T *>(sm_raw);              // [kStages][KB][ROWS][kNB]
+    constexpr int CB = CG * TC, RB = RG * TR, NCW = CG * RG, NPT = 32 * NPW;
+    constexpr int ROWS = RB + CB;                      // smem rows per K-step: R rows then P rows
+    constexpr int ROWBYTES = kNB * (int)sizeof(T);
+    constexpr int PARTS = ROWBYTES / 16;               // 16-byte chunks per row (8 or 16)
+    constexpr int SROWS = KB * ROWS;                   // rows per stage
+    constexpr int CHUNKS = SROWS * PARTS;
+    extern __shared__ __align__(128) unsigned char sm_raw[];
+    T *sm = reinterpret_cast<T *>(sm_raw);             // [kStages][KB][ROWS][kNB]
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(sm_raw + (size_t)kStages * SROWS * ROWBYTES);
+    uint64_t *empty_bar = full_bar + kStages;
+    uint64_t *rtab = empty_bar + kStages;              // [SROWS] stage-invariant row descriptors
+    //   R row : (kk*nrows + row)*rec  (byte offset, < 2^62)           ; 0xFFFF... = padding row
+    //   P row : (1<<63) | address of pidx[col*K + kk]                  ; 0xFFFF... = column outside the problem
 
-    const int tid = threadIdx.x;
-    const int lane = tid % kNB, cg = (tid / kNB) % CG, rg = tid / (kNB * CG);
+    const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
     const int col0 = blockIdx.x * CB;
     const int n0 = blockIdx.y * kNB;
     const int l = limbs.idx[blockIdx.z];
-    const LimbConst lc = lcs[l];
     const size_t rec = (size_t)lay.bytes;
-    const char *Rl = R + lay.off[l] + (size_t)n0 * sizeof(T);
-    const char *Pl = P + lay.off[l] + (size_t)n0 * sizeof(T);
     const int nstage = (K + KB - 1) / KB;
 
-    // Per-thread cp.async descriptors, fixed across pipeline stages: chunk j of this thread copies 16 bytes of one row of
-    // one K-step of the stage.  R rows advance by a constant stride per stage; P rows look up the record index.
-    constexpr int NCH = (CHUNKS + THREADS - 1) / THREADS;
-    const char *csrc[NCH];   // R chunks: source pointer for stage 0 ; P chunks: Pl + part*16
-    const int *cpi[NCH];     // P chunks: &pidx[col*K + kk] for stage 0 (nullptr for R chunks)
-    int cdst[NCH];           // element offset inside a stage buffer, -1 = no chunk
-    int ckk[NCH];
-    bool cok[NCH];           // row / column inside the problem
-#pragma unroll
-    for (int j = 0; j < NCH; j++) {
-        const int ch = tid + j * THREADS;
-        const int part = ch % PARTS, row = (ch / PARTS) % ROWS, kk = ch / (PARTS * ROWS);
-        cdst[j] = ch < CHUNKS ? (kk * ROWS + row) * kNB + part * EPC : -1;
-        ckk[j] = kk;
-        cpi[j] = nullptr;
+    if (tid == 0) {
+        for (int s = 0; s < kStages; s++) {
+            mbar_init(&full_bar[s], NPT);
+            mbar_init(&empty_bar[s], NCW);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    for (int rr = tid; rr < SROWS; rr += blockDim.x) {
+        const int kk = rr / ROWS, row = rr % ROWS;
+        uint64_t e = ~0ULL;
         if (row < RB) {
-            cok[j] = row < nrows;
-            csrc[j] = Rl + ((size_t)kk * nrows + (cok[j] ? row : 0)) * rec + part * 16;
+            if (row < nrows) e = ((uint64_t)kk * nrows + row) * rec;
         } else {
             const int col = col0 + (row - RB);
-            cok[j] = col < ncols;
-            csrc[j] = Pl + part * 16;
-            cpi[j] = pidx + (size_t)(cok[j] ? col : 0) * K + kk;
+            if (col < ncols) e = (1ULL << 63) | (uint64_t)(uintptr_t)(pidx + (size_t)col * K + kk);
         }
+        rtab[rr] = e;
     }
-    const size_t rstride = (size_t)KB * nrows * rec;
+    __syncthreads();
 
-    auto issue = [&](int sidx) {
-        T *dst = sm + (size_t)(sidx % kStages) * KB * ROWS * kNB;
-        const int k0 = sidx * KB;
+    if (wid >= NCW) {
+        // ===================== producer warps =====================
+        const int ptid = tid - NCW * 32;
+        const int part = ptid % PARTS, rsub = ptid / PARTS;
+        constexpr int RSTEP = NPT / PARTS;             // rows covered per pass of the producer threads
+        const char *Rl = R + lay.off[l] + (size_t)n0 * sizeof(T) + part * 16;
+        const char *Pl = P + lay.off[l] + (size_t)n0 * sizeof(T) + part * 16;
+        const size_t rstride = (size_t)KB * nrows * rec;
+        for (int sidx = 0; sidx < nstage; sidx++) {
+            const int s = sidx % kStages;
+            mbar_wait(&empty_bar[s], ((uint32_t)(sidx / kStages) & 1u) ^ 1u);  // slot free (immediate in the first round)
+            unsigned char *stage = sm_raw + (size_t)s * SROWS * ROWBYTES + part * 16;
+            const int k0 = sidx * KB;
+            const char *Rs = Rl + (size_t)sidx * rstride;
+            // phase 1: resolve every source address of this thread's rows (independent pidx loads overlap) ...
+            constexpr int NIT = (SROWS + RSTEP - 1) / RSTEP;
+            const char *src[NIT];
 #pragma unroll
-        for (int j = 0; j < NCH; j++) {
-            if (cdst[j] < 0) continue;
-            const char *src = R;
-            int bytes = 0;
-            if (cok[j] && k0 + ckk[j] < K) {
-                if (cpi[j] == nullptr) {
-                    src = csrc[j] + (size_t)sidx * rstride;
-                    bytes = 16;
-                } else {
-                    const int pi = __ldg(cpi[j] + k0);
-                    if (pi >= 0) {
-                        src = csrc[j] + (size_t)pi * rec;
-                        bytes = 16;
+            for (int j = 0; j < NIT; j++) {
+                const int rr = rsub + j * RSTEP;
+                src[j] = nullptr;
+                if (rr < SROWS) {
+                    const uint64_t e = rtab[rr];
+                    const int kk = rr / ROWS;
+                    if (e != ~0ULL && k0 + kk < K) {
+                        if (e >> 63) {
+                            const int pi = __ldg(reinterpret_cast<const int *>(e & ~(1ULL << 63)) + k0);
+                            if (pi >= 0) src[j] = Pl + (size_t)pi * rec;
+                        } else {
+                            src[j] = Rs + e;
+                        }
                     }
                 }
             }
-            cp_async16(dst + cdst[j], src, bytes);
+            // ... phase 2: issue the copies (zero-fill when there is no source)
+#pragma unroll
+            for (int j = 0; j < NIT; j++) {
+                const int rr = rsub + j * RSTEP;
+                if (rr < SROWS) cp_async16(stage + (size_t)rr * ROWBYTES, src[j] ? src[j] : R, src[j] ? 16 : 0);
+            }
+            cp_async_mbar_arrive(&full_bar[s]);
         }
-    };
+        return;
+    }
 
+    // ===================== consumer warps =====================
+    const int cg = wid % CG, rg = wid / CG;
+    const LimbConst lc = lcs[l];
     typename std::conditional<NARROW, AccN, AccW>::type acc[TR][TC];
 #pragma unroll
     for (int r = 0; r < TR; r++)
@@ -170,20 +215,10 @@ k_mac(const char *__restrict__ R, const char *__restrict__ P, const int *__restr
             else acc[r][c] = AccW{0, 0, 0, 0};
         }
 
-#pragma unroll
-    for (int st = 0; st < kStages - 1; st++) {
-        if (st < nstage) issue(st);
-        cp_async_commit();
-    }
     for (int sidx = 0; sidx < nstage; sidx++) {
-        cp_async_wait<kStages - 2>();
-        __syncthreads();
-        {   // prefetch stage sidx + kStages - 1 into the slot freed by stage sidx - 1
-            const int sn = sidx + kStages - 1;
-            if (sn < nstage) issue(sn);
-            cp_async_commit();
-        }
-        const T *st = sm + (size_t)(sidx % kStages) * KB * ROWS * kNB;
+        const int s = sidx % kStages;
+        mbar_wait(&full_bar[s], (uint32_t)(sidx / kStages) & 1u);
+        const T *st = sm + (size_t)s * SROWS * kNB;
 #pragma unroll
         for (int kk = 0; kk < KB; kk++) {
             const T *sk = st + (size_t)kk * ROWS * kNB;
@@ -200,8 +235,9 @@ k_mac(const char *__restrict__ R, const char *__restrict__ P, const int *__restr
                     else mac_wide(acc[r][c], (uint32_t)a[r], (uint32_t)(a[r] >> 32), (uint32_t)b[c], (uint32_t)(b[c] >> 32));
                 }
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[s]);
     }
-    cp_async_wait<0>();
 
     // epilogue: reduce and store canonical residues, cv[col][row][l][n] (u64)
     uint64_t r32 = 0;
@@ -223,14 +259,14 @@ k_mac(const char *__restrict__ R, const char *__restrict__ P, const int *__restr
     }
 }
 
-template <int TR, int TC, int CG, int RG, int KB, bool NARROW>
+template <int TR, int TC, int CG, int RG, int KB, int NPW, bool NARROW>
 static int launch_cfg(Ctx *c, const char *R, const char *P, const int *pidx, int K, int nrows, int ncols, const PolyLayout &lay,
                       const LimbList &limbs, uint64_t *cv, int Lcv, cudaStream_t st) {
-    constexpr int CB = CG * TC, RB = RG * TR, THREADS = kNB * CG * RG;
-    const size_t smem = (size_t)kStages * KB * (RB + CB) * kNB * (NARROW ? 4 : 8);
-    SFG_CUDA(c, cudaFuncSetAttribute(k_mac<TR, TC, CG, RG, KB, NARROW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    constexpr int CB = CG * TC, RB = RG * TR, THREADS = kNB * (CG * RG + NPW);
+    const size_t smem = (size_t)kStages * KB * (RB + CB) * kNB * (NARROW ? 4 : 8) + (2 * kStages + KB * (RB + CB)) * sizeof(uint64_t);
+    SFG_CUDA(c, cudaFuncSetAttribute(k_mac<TR, TC, CG, RG, KB, NPW, NARROW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((ncols + CB - 1) / CB, c->N / kNB, limbs.n);
-    k_mac<TR, TC, CG, RG, KB, NARROW><<<grid, THREADS, smem, st>>>(R, P, pidx, K, nrows, ncols, lay, limbs, c->N, c->lc, cv, Lcv);
+    k_mac<TR, TC, CG, RG, KB, NPW, NARROW><<<grid, THREADS, smem, st>>>(R, P, pidx, K, nrows, ncols, lay, limbs, c->N, c->lc, cv, Lcv);
     SFG_LAUNCHED(c, "k_mac", st);
     return 0;
 }
@@ -247,7 +283,7 @@ int launch_mac(Ctx *c, const void *R, const void *P, const int *pidx, int K, int
     }
     const char *Rc = (const char *)R, *Pc = (const char *)P;
     const int Lcv = lay.nl;
-#define SFG_MAC(TR, TC, CG, RG, KB, NARROW, LIMBS) launch_cfg<TR, TC, CG, RG, KB, NARROW>(c, Rc, Pc, pidx, K, nrows, ncols, lay, LIMBS, cv, Lcv, st)
+#define SFG_MAC(TR, TC, CG, RG, KB, NARROW, LIMBS) launch_cfg<TR, TC, CG, RG, KB, 4, NARROW>(c, Rc, Pc, pidx, K, nrows, ncols, lay, LIMBS, cv, Lcv, st)
     if (nar.n) {
         int rc;
         if (nrows <= 8) rc = SFG_MAC(8, 2, 16, 1, 4, true, nar);
@@ -261,14 +297,14 @@ int launch_mac(Ctx *c, const void *R, const void *P, const int *pidx, int K, int
     }
     if (wid.n) {
         int rc;
-        if (nrows <= 4) rc = SFG_MAC(4, 2, 16, 1, 2, false, wid);
-        else if (nrows <= 8) rc = SFG_MAC(4, 2, 8, 2, 2, false, wid);
-        else if (nrows <= 12) rc = SFG_MAC(4, 2, 5, 3, 2, false, wid);
-        else if (nrows <= 16) rc = SFG_MAC(4, 2, 4, 4, 2, false, wid);
-        else if (nrows <= 20) rc = SFG_MAC(4, 2, 3, 5, 2, false, wid);
-        else if (nrows <= 24) rc = SFG_MAC(4, 2, 2, 6, 2, false, wid);
-        else if (nrows <= 28) rc = SFG_MAC(4, 2, 2, 7, 2, false, wid);
-        else rc = SFG_MAC(4, 2, 2, 8, 2, false, wid);
+        if (nrows <= 4) rc = SFG_MAC(4, 2, 16, 1, 4, false, wid);
+        else if (nrows <= 8) rc = SFG_MAC(4, 2, 8, 2, 4, false, wid);
+        else if (nrows <= 12) rc = SFG_MAC(4, 2, 5, 3, 4, false, wid);
+        else if (nrows <= 16) rc = SFG_MAC(4, 2, 4, 4, 4, false, wid);
+        else if (nrows <= 20) rc = SFG_MAC(4, 2, 3, 5, 4, false, wid);
+        else if (nrows <= 24) rc = SFG_MAC(4, 2, 2, 6, 4, false, wid);
+        else if (nrows <= 28) rc = SFG_MAC(4, 2, 2, 7, 4, false, wid);
+        else rc = SFG_MAC(4, 2, 2, 8, 4, false, wid);
         if (rc) return rc;
     }
 #undef SFG_MAC
