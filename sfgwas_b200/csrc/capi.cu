@@ -69,6 +69,9 @@ void sfg_ctx_destroy(sfg_ctx *h) {
     cudaSetDevice(c->device);
     cudaFree(c->lc);
     cudaFree(c->tw);
+    cudaFree(c->tw2);
+    ws_release(c);
+    for (void *p : c->tw2_bufs) cudaFree(p);
     cudaFree(c->roots);
     cudaFree(c->ddcos);
     cudaFree(c->rot5);
@@ -113,7 +116,17 @@ int sfg_ctx_last_timings(const sfg_ctx *, float out_ms[5]) {
     return 0;
 }
 
-static int set_key_dev(Ctx *c, int rot_left, uint64_t *dkey) {
+static int set_key_dev(Ctx *c, int rot_left, uint64_t *draw) {
+    // convert to the device format of the key-switch kernels (TT order, Shoup pairs for narrow moduli)
+    const size_t n = (size_t)c->beta * 2 * c->nQP * c->N;
+    uint64_t *dkey = nullptr;
+    if (cudaMalloc(&dkey, n * 8) != cudaSuccess) {
+        cudaFree(draw);
+        SFG_FAIL(c, "cudaMalloc of a Galois key failed");
+    }
+    if (launch_key_convert(c, draw, dkey, c->stream)) return -1;
+    SFG_CUDA(c, cudaStreamSynchronize(c->stream));
+    cudaFree(draw);
     const uint64_t galEl = h_galois_element(c->logN, rot_left);
     std::vector<uint32_t> idx(c->N);
     h_permute_ntt_index(c->logN, galEl, idx.data());

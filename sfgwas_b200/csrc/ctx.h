@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "modarith.cuh"
+#include "ntt2.cuh"
 
 namespace sfg {
 
@@ -43,7 +44,9 @@ struct Ctx {
     std::vector<uint64_t> mod, psi;        // host copies
     std::vector<LimbConst> lc_h;
     LimbConst *lc = nullptr;               // device [nQP]
-    uint64_t *tw = nullptr;                // device [nQP][4][N]
+    uint64_t *tw = nullptr;                // device [nQP][4][N]  (radix-2 tables: encoder, logN > 14)
+    TwTab *tw2 = nullptr;                  // device [nQP]: per-class twiddle tables of the register-tiled transforms (ntt2.cuh)
+    std::vector<void *> tw2_bufs;          // device allocations behind tw2
     // encoder (special inverse FFT)
     double2 *roots = nullptr;              // device [2N+1] exp(2 pi i k / 2N)
     int *rot5 = nullptr;                   // device [slots] 5^j mod 2N
@@ -56,6 +59,12 @@ struct Ctx {
     std::map<uint64_t, GaloisKey> keys;    // galEl -> key
     cudaStream_t stream = nullptr;
     size_t cache_budget = 0;               // bytes of HBM the diagonal cache may take (0 = auto)
+    // grow-only device workspace, reused across calls (no cudaMalloc / cudaFree in the steady state)
+    struct WsBuf {
+        void *p = nullptr;
+        size_t bytes = 0;
+    };
+    WsBuf ws[16];
     std::mutex mu;
     std::string err;
     // counters
@@ -88,6 +97,11 @@ int launch_check(Ctx *c, const char *what, cudaStream_t st);
         (ctx)->launches++;                           \
         if (launch_check((ctx), (what), (st))) return -1; \
     } while (0)
+
+// workspace slots
+enum WsSlot { WS_C2 = 0, WS_ACC, WS_META, WS_R, WS_CV, WS_POFF, WS_TMPP, WS_A, WS_OUT, WS_META2, WS_COUNT };
+int ws_get(Ctx *c, int slot, size_t bytes, void **out);  // returns a buffer of at least `bytes` (contents undefined)
+void ws_release(Ctx *c);
 
 // ---- table builders (ctx.cu) ----
 int ctx_build_tables(Ctx *c, const uint64_t *psi_opt);

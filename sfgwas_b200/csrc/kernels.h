@@ -25,6 +25,10 @@ PolyLayout make_layout(const Ctx *c, int nl, bool packed);
 // dst likewise; modulus index = sel.idx[k].  In-place allowed (src == dst with equal strides).
 int launch_ntt(Ctx *c, const uint64_t *src, size_t src_gstride, uint64_t *dst, size_t dst_gstride, int npoly,
                const LimbSel &sel, bool inverse, cudaStream_t st);
+// same with per-group source offsets (device array of element offsets, overrides g*src_gstride; may be null) and, for inverse
+// transforms, inputs stored in TT order (ntt2.cuh)
+int launch_ntt_gather(Ctx *c, const uint64_t *src, const long long *src_off, size_t src_gstride, uint64_t *dst, size_t dst_gstride,
+                      int npoly, const LimbSel &sel, bool inverse, bool in_tt, cudaStream_t st);
 
 // ---- lazy MAC primitives as stand-alone kernels (parity tests of K1/K2/K3) ----
 int launch_mul_coeffs_and_add128(Ctx *c, const uint64_t *a, const uint64_t *b, uint64_t *acc_hi_lo, size_t n, cudaStream_t st);
@@ -56,23 +60,33 @@ int launch_mac(Ctx *c, const void *R, const void *P, const int *pidx, int K, int
                uint64_t *cv, cudaStream_t st);
 
 // ---- key-switch + automorphism (kernels_ks.cu) ----
+// A batch is a list of ciphertexts, each rotated with its own Galois key.  All arrays are DEVICE arrays of nct entries.
 struct KsBatch {
     int level;              // input level (nl = level+1 limbs)
-    int nct;                // ciphertexts in the batch (all use the same Galois key)
+    int nct;                // ciphertexts in the batch
     const uint64_t *in;     // ct k at in + in_off[k], layout [2][in_nl][N]
-    const long long *in_off;   // device [nct]; must be the arithmetic progression in_first + k*in_stride
-    long long in_first, in_stride;
+    const long long *in_off;
     int in_nl;              // limb count of the stored input cts (>= level+1)
+    // INTT(c1) is computed once per DISTINCT input: slot j of c2 holds the transform of the ct at in + c2_src_off[j];
+    // batch entry k reads slot c2_slot[k]
+    int n_c2;
+    const long long *c2_src_off;  // device [n_c2]
+    const int *c2_slot;           // device [nct]
+    const uint64_t *const *keys;  // device [nct]: converted Galois key (launch_key_convert) of entry k
+    const uint32_t *const *perms; // device [nct]: PermuteNTTIndex table of entry k
     void *out;              // ct k at (char*)out + out_off[k] BYTES: two consecutive records of out_layout (c0 then c1);
-    const long long *out_off;  // device [nct]                          only limbs < out_layout.nl are produced
+    const long long *out_off;  //                                       only limbs < out_layout.nl are produced
     PolyLayout out_layout;
-    bool accumulate;        // out += result (mod q) instead of out = result
-    // scratch (device): c2 [nct][nl][N], acc [nct][2][nl+nP][N]
+    bool accumulate;        // out += result (mod q) instead of out = result; entries of one batch must target distinct outputs
+    // scratch (device): c2 [n_c2][nl][N], acc [nct][2][nl+nP][N]
     uint64_t *c2, *acc;
+    int acc_cap;            // ciphertexts the acc scratch holds; larger batches are processed in chunks
 };
-int launch_rotate(Ctx *c, const KsBatch &b, const GaloisKey &key, cudaStream_t st);
+int launch_rotate(Ctx *c, const KsBatch &b, cudaStream_t st);
 // out (+)= in, limb-wise mod q, same offset conventions (used for rotation by 0)
 int launch_copy_add(Ctx *c, const KsBatch &b, cudaStream_t st);
+// Lattigo SwitchingKey [beta][2][nQP][N] (NTT + Montgomery) -> device format of k_ks_inner2 (TT order; narrow moduli as Shoup pairs)
+int launch_key_convert(Ctx *c, const uint64_t *in, uint64_t *out, cudaStream_t st);
 
 // modular canonicalisation of sums of residues: x[l][n] = x[l][n] mod q_l over npoly*[L][N] (multi-GPU reduce epilogue)
 int launch_mod_reduce(Ctx *c, uint64_t *x, size_t npoly, int L, cudaStream_t st);

@@ -6,20 +6,22 @@
 // only on the mathematical value of each step -- including the float64 quotient estimate `v` of Lattigo's fast exact
 // base conversion, which is reproduced operation by operation (IEEE division and addition in index order).
 //
-// Batched over ciphertexts that share one Galois key (all rows / block columns of one baby or giant step):
-//   1. INTT of c1                                                   (launch_ntt)
-//   2. k_ks_inner : per (ct, target modulus t in Q_level U P): for every digit, base-convert the digit to t, NTT in
-//                   shared memory (or reuse the NTT-domain input limb inside the digit), 128-bit lazy MAC with both
-//                   key polynomials held in registers, Montgomery reduce -> acc[ct][2][t]
-//   3. INTT of the P limbs of acc                                   (launch_ntt)
-//   4. k_ks_moddown : per (ct, component, Q limb): base-convert P -> q_l, NTT, (acc - ext) * P^-1, + c0, automorphism
-//                   gather from shared memory, store or accumulate (the giant-step sum of gwas/matmult.go:1223-1227).
+// A batch is any list of ciphertexts, each with its own Galois key (so all baby steps -- or many giant steps -- of a MatMult
+// call go through ONE sequence of launches and fill the 148 SMs):
+//   1. k_ntt2_inv    : c2 = INTT(c1)                                                         (kernels_ntt.cu)
+//   2. k_ks_inner2   : per (ct, target modulus t in Q_level U P [, slice]): for every digit, reduce / base-convert the digit
+//                      to t, forward NTT (register-tiled passes, ntt2.cuh), multiply with both key polynomials, accumulate in
+//                      shared memory -> acc[ct][2][t] in TT order (the order the next kernels read with unit stride)
+//   3. k_ntt2_inv    : INTT of the P limbs of acc (TT in, natural out)
+//   4. k_ks_moddown2 : per (ct, component, Q limb): base-convert P -> q_l, NTT, (acc - ext) * P^-1, + c0, automorphism
+//                      gather from shared memory, store or accumulate (the giant-step sum of gwas/matmult.go:1223-1227).
+// Kernels are instantiated per arithmetic class of the target modulus (ntt2.cuh) and launched once per class present.
 #include "kernels.h"
-#include "ntt.cuh"
+#include "ntt2.cuh"
 
 namespace sfg {
 
-// Lattigo fast exact base conversion for one coefficient: residues xs[k] (k < ns) -> target modulus t.
+// Lattigo fast exact base conversion for one coefficient: residues xs[k] (k < ns) -> target modulus t (canonical).
 __device__ __forceinline__ uint64_t base_conv_coeff(const BaseConv &bc, const uint64_t *xs, const LimbConst *lcs, uint64_t t) {
     double vi = 0.0;
     uint64_t acc = 0;
@@ -34,130 +36,181 @@ __device__ __forceinline__ uint64_t base_conv_coeff(const BaseConv &bc, const ui
     return sub_mod(acc, mul_shoup(v, bc.smod, bc.smod_sh, t), t);
 }
 
-template <int NPER>
-__global__ void __launch_bounds__(1024, 1)
-k_ks_inner(const uint64_t *__restrict__ in, const long long *__restrict__ in_off, int in_nl, const uint64_t *__restrict__ c2,
-           const uint64_t *__restrict__ key, const BaseConv *__restrict__ ks, int level, int nQ, int nP, int logN,
-           const uint64_t *__restrict__ tw, const LimbConst *__restrict__ lcs, uint64_t *__restrict__ accout) {
-    extern __shared__ __align__(16) uint64_t s[];
-    const int N = 1 << logN, nl = level + 1, nt = nl + nP, nQP = nQ + nP;
-    const int alpha = nP, beta = (nl + alpha - 1) / alpha;
-    const int tt = blockIdx.x, ct = blockIdx.y;
-    const int tgt = tt < nl ? tt : nQ + (tt - nl);
-    const int T = blockDim.x, tid = threadIdx.x;
-    const LimbConst lc = lcs[tgt];
-    const NttTab tab = ntt_tab(tw, tgt, N);
-    const uint64_t *c1 = in + in_off[ct] + (size_t)in_nl * N;  // second polynomial of the input ct
-    const uint64_t *c2ct = c2 + (size_t)ct * nl * N;
+struct TgtSel {  // targets (or limbs) of one arithmetic class
+    int n;
+    int tt[kMaxLimbs];
+};
 
-    // canonical accumulators (2 registers each): one Montgomery reduction per product keeps the kernel at 1024 threads
-    uint64_t a0[NPER], a1[NPER];
-#pragma unroll
-    for (int r = 0; r < NPER; r++) a0[r] = a1[r] = 0;
+// ---- Galois key conversion (once per key upload) ----------------------------------------------------------------------
+// in : Lattigo SwitchingKey [beta][2][nQP][N] u64, NTT + Montgomery form.
+// out: same shape, every polynomial in TT order; wide moduli keep the Montgomery u64, narrow moduli (q < 2^31) become
+//      (k, floor(k 2^32 / q)) pairs with k the plain residue, for the 32-bit Shoup multiplication.
+__global__ void k_key_convert(const uint64_t *__restrict__ in, uint64_t *__restrict__ out, int N, int nQP, const LimbConst *__restrict__ lcs) {
+    const int poly = blockIdx.y, limb = poly % nQP;
+    const LimbConst lc = lcs[limb];
+    const int kind = arith_kind(lc.q);
+    const uint64_t *src = in + (size_t)poly * N;
+    uint64_t *dst = out + (size_t)poly * N;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < N; j += gridDim.x * blockDim.x) {
+        const uint64_t km = src[j];
+        uint64_t o = km;
+        if (kind != kArW) {
+            const uint64_t k = mred(km, 1, lc);  // InvMForm
+            o = k | (((k << 32) / lc.q) << 32);
+        }
+        dst[tt_index(j, N)] = o;
+    }
+}
+int launch_key_convert(Ctx *c, const uint64_t *in, uint64_t *out, cudaStream_t st) {
+    dim3 g(std::max(1, c->N / 256), c->beta * 2 * c->nQP);
+    k_key_convert<<<g, 256, 0, st>>>(in, out, c->N, c->nQP, c->lc);
+    SFG_LAUNCHED(c, "k_key_convert", st);
+    return 0;
+}
+
+// ---- 2. inner products with the switching key ---------------------------------------------------------------------------
+template <class A, int CS>
+__global__ void __launch_bounds__(256, A::kKind == kArW ? 1 : 2)
+k_ks_inner2(const uint64_t *__restrict__ in, const long long *__restrict__ in_off, int in_nl, const uint64_t *__restrict__ c2,
+            const int *__restrict__ c2_slot,
+            const uint64_t *const *__restrict__ keys, const BaseConv *__restrict__ ks, int level, int nQ, int nP, int logN, PassPlan plan,
+            const TwTab *__restrict__ tabs, const LimbConst *__restrict__ lcs, uint64_t *__restrict__ accout, TgtSel sel) {
+    using T = typename A::T;
+    extern __shared__ __align__(16) unsigned char smraw[];
+    const int N = 1 << logN, logS = logN - CS, S = 1 << logS, nl = level + 1, nt = nl + nP, nQP = nQ + nP;
+    const int alpha = nP, beta = (nl + alpha - 1) / alpha;
+    const int sl = blockIdx.x & ((1 << CS) - 1), tt = sel.tt[blockIdx.x >> CS], ct = blockIdx.y;
+    const int tgt = tt < nl ? tt : nQ + (tt - nl);
+    const size_t SE = ntt_smem_elems(S);
+    T *s = reinterpret_cast<T *>(smraw), *a0 = s + SE, *a1 = a0 + SE;
+    const LimbConst lc = lcs[tgt];
+    const typename A::C c = A::make(lc);
+    const TwTab tab = tabs[tgt];
+    const uint64_t *c1 = in + in_off[ct] + (size_t)in_nl * N;  // second polynomial of the input ct (NTT domain)
+    const uint64_t *c2ct = c2 + (size_t)c2_slot[ct] * nl * N;  // its INTT, coefficient domain
+    const uint64_t *key = keys[ct];
+    const int gbase = sl << logS;                               // global index of local coefficient 0
 
     for (int i = 0; i < beta; i++) {
         const BaseConv &bc = ks[(size_t)i * nt + tt];
         const uint64_t *k0 = key + ((size_t)(i * 2 + 0) * nQP + tgt) * N;
         const uint64_t *k1 = key + ((size_t)(i * 2 + 1) * nQP + tgt) * N;
+        const bool first = i == 0;
+        // multiply coefficient j (local) with the two key polynomials and accumulate (thread-private shared-memory slots)
+        auto mac = [&](int j, T v) {
+            const int kpos = tt_index(gbase + j, N), sj = sidx(j);
+            if constexpr (A::kKind == kArW) {
+                const uint64_t p0 = mred(v, __ldg(k0 + kpos), lc), p1 = mred(v, __ldg(k1 + kpos), lc);
+                a0[sj] = first ? p0 : add_mod(a0[sj], p0, lc.q);
+                a1[sj] = first ? p1 : add_mod(a1[sj], p1, lc.q);
+            } else {
+                const uint2 w0 = __ldg(reinterpret_cast<const uint2 *>(k0) + kpos), w1 = __ldg(reinterpret_cast<const uint2 *>(k1) + kpos);
+                uint32_t p0 = A::mul_lazy(v, w0, c), p1 = A::mul_lazy(v, w1, c);
+                p0 = min(p0, p0 - c.q);
+                p1 = min(p1, p1 - c.q);
+                if (!first) {
+                    p0 += a0[sj];
+                    p1 += a1[sj];
+                    p0 = min(p0, p0 - c.q);
+                    p1 = min(p1, p1 - c.q);
+                }
+                a0[sj] = p0;
+                a1[sj] = p1;
+            }
+        };
         const int ns = bc.ns;
         if (ns == 0) {  // target lies inside the digit: reuse the NTT-domain input limb (decomposeAndSplitNTT)
-#pragma unroll
-            for (int r = 0; r < NPER; r++) {
-                const int k = tid + r * T;
-                const uint64_t v = c1[(size_t)tt * N + k];
-                a0[r] = add_mod(a0[r], mred(v, k0[k], lc), lc.q);
-                a1[r] = add_mod(a1[r], mred(v, k1[k], lc), lc.q);
-            }
-            continue;
-        }
-        if (ns == 1) {  // single-modulus digit: BRedAdd of the integer representative (DecomposeAndSplit)
-            const uint64_t *x = c2ct + (size_t)bc.src_limb[0] * N;
-#pragma unroll
-            for (int r = 0; r < NPER; r++) {
-                const int k = tid + r * T;
-                s[k] = bred_add(x[k], lc);
+            const uint64_t *x = c1 + (size_t)tt * N + gbase;
+            for (int j = threadIdx.x; j < S; j += blockDim.x) s[sidx(j)] = A::from_canon(x[j], c);
+            __syncthreads();
+            for (int p = threadIdx.x; p < (S >> 5); p += blockDim.x) {
+#pragma unroll 8
+                for (int k = 0; k < 32; k++) mac(32 * p + k, s[sidx(32 * p + k)]);
             }
         } else {
-#pragma unroll 1
-            for (int r = 0; r < NPER; r++) {
-                const int k = tid + r * T;
+            // coefficient-domain value of global coefficient g of this digit, reduced / base-converted to the target modulus
+            auto digit = [&](int g) -> T {
+                if (ns == 1) return A::load_u64(c2ct[(size_t)bc.src_limb[0] * N + g], c);  // DecomposeAndSplit, single modulus
                 uint64_t xs[kMaxAlpha];
-                for (int j = 0; j < ns; j++) xs[j] = c2ct[(size_t)bc.src_limb[j] * N + k];
-                s[k] = base_conv_coeff(bc, xs, lcs, lc.q);
-            }
-        }
-        __syncthreads();
-        ntt_fwd_smem(s, logN, 1, 0, tab, lc.q);
-#pragma unroll
-        for (int r = 0; r < NPER; r++) {
-            const int k = tid + r * T;
-            const uint64_t v = s[k];
-            a0[r] = add_mod(a0[r], mred(v, k0[k], lc), lc.q);
-            a1[r] = add_mod(a1[r], mred(v, k1[k], lc), lc.q);
+                for (int j = 0; j < ns; j++) xs[j] = c2ct[(size_t)bc.src_limb[j] * N + g];
+                return A::load_u64(base_conv_coeff(bc, xs, lcs, lc.q), c);
+            };
+            auto ld0 = [&](int j) -> T {
+                if constexpr (CS == 0) {
+                    return digit(j);
+                } else {  // the ring is cut into 2 slices: stage 0 is evaluated by both CTAs, each keeps its half
+                    T x = digit(j), y = digit(j + S);
+                    A::fwd(x, y, __ldg(reinterpret_cast<const typename A::TW *>(tab.fwd) + 1), c);
+                    return sl ? y : x;
+                }
+            };
+            ntt_forward<A>(s, logN, logS, sl, plan, tab, c, ld0, mac);
         }
         __syncthreads();
     }
     uint64_t *o0 = accout + ((size_t)(ct * 2 + 0) * nt + tt) * N;
     uint64_t *o1 = accout + ((size_t)(ct * 2 + 1) * nt + tt) * N;
-#pragma unroll
-    for (int r = 0; r < NPER; r++) {
-        const int k = tid + r * T;
-        o0[k] = a0[r];
-        o1[k] = a1[r];
+    for (int p = threadIdx.x; p < (S >> 5); p += blockDim.x) {
+#pragma unroll 8
+        for (int k = 0; k < 32; k++) {
+            const int j = 32 * p + k, kpos = tt_index(gbase + j, N);
+            o0[kpos] = a0[sidx(j)];
+            o1[kpos] = a1[sidx(j)];
+        }
     }
 }
 
-template <int NPER>
-__global__ void __launch_bounds__(1024, 1)
-k_ks_moddown(const uint64_t *__restrict__ in, const long long *__restrict__ in_off, int in_nl, const uint64_t *__restrict__ acc,
-             const BaseConv *__restrict__ md, const uint64_t *__restrict__ pinv, const uint32_t *__restrict__ perm, int level,
-             int nQ, int nP, int logN, const uint64_t *__restrict__ tw, const LimbConst *__restrict__ lcs,
-             unsigned char *__restrict__ out, const long long *__restrict__ out_off, PolyLayout olay, int accumulate) {
-    extern __shared__ __align__(16) uint64_t s[];
+// ---- 4. mod-down, + c0, automorphism, store / accumulate ---------------------------------------------------------------------
+template <class A>
+__global__ void __launch_bounds__(512, 1)
+k_ks_moddown2(const uint64_t *__restrict__ in, const long long *__restrict__ in_off, int in_nl, const uint64_t *__restrict__ acc,
+              const BaseConv *__restrict__ md, const uint64_t *__restrict__ pinv, const uint32_t *const *__restrict__ perms, int level,
+              int nQ, int nP, int logN, PassPlan plan, const TwTab *__restrict__ tabs, const LimbConst *__restrict__ lcs,
+              unsigned char *__restrict__ out, const long long *__restrict__ out_off, PolyLayout olay, int accumulate, TgtSel sel) {
+    using T = typename A::T;
+    extern __shared__ __align__(16) unsigned char smraw[];
+    T *s = reinterpret_cast<T *>(smraw);
     const int N = 1 << logN, nl = level + 1, nt = nl + nP;
-    const int l = blockIdx.x, comp = blockIdx.y, ct = blockIdx.z;
-    const int T = blockDim.x, tid = threadIdx.x;
+    const int l = sel.tt[blockIdx.x], comp = blockIdx.y, ct = blockIdx.z;
     const LimbConst lc = lcs[l];
-    const NttTab tab = ntt_tab(tw, l, N);
+    const typename A::C c = A::make(lc);
+    const TwTab tab = tabs[l];
     const BaseConv &bc = md[l];
-    const uint64_t *accP = acc + ((size_t)(ct * 2 + comp) * nt + nl) * N;  // P limbs, coefficient domain
-    const uint64_t *accQ = acc + ((size_t)(ct * 2 + comp) * nt + l) * N;
+    const uint64_t *accP = acc + ((size_t)(ct * 2 + comp) * nt + nl) * N;  // P limbs, coefficient domain, natural order
+    const uint64_t *accQ = acc + ((size_t)(ct * 2 + comp) * nt + l) * N;   // Q limb, NTT domain, TT order
     const uint64_t pi = pinv[2 * l], pish = pinv[2 * l + 1];
+    const uint32_t *perm = perms[ct];
 
-#pragma unroll 1
-    for (int r = 0; r < NPER; r++) {
-        const int k = tid + r * T;
+    auto ld0 = [&](int j) -> T {
+        if (nP == 1) return A::load_u64(accP[j], c);
         uint64_t xs[kMaxAlpha];
-        for (int j = 0; j < nP; j++) xs[j] = accP[(size_t)j * N + k];
-        s[k] = base_conv_coeff(bc, xs, lcs, lc.q);
-    }
+        for (int k = 0; k < nP; k++) xs[k] = accP[(size_t)k * N + j];
+        return A::load_u64(base_conv_coeff(bc, xs, lcs, lc.q), c);
+    };
+    auto fin = [&](int j, T v) {
+        const uint64_t e = A::canon(v, c);
+        const uint64_t r = mul_shoup(sub_mod(accQ[tt_index(j, N)], e, lc.q), pi, pish, lc.q);
+        s[sidx(j)] = (T)r;
+    };
+    ntt_forward<A>(s, logN, logN, 0, plan, tab, c, ld0, fin);
     __syncthreads();
-    ntt_fwd_smem(s, logN, 1, 0, tab, lc.q);
-    const uint64_t *c0 = in + in_off[ct] + (size_t)l * N;
-#pragma unroll
-    for (int r = 0; r < NPER; r++) {
-        const int k = tid + r * T;
-        uint64_t v = mul_shoup(sub_mod(accQ[k], s[k], lc.q), pi, pish, lc.q);
-        if (comp == 0) v = add_mod(v, c0[k], lc.q);
-        s[k] = v;
+    if (comp == 0) {
+        const uint64_t *c0 = in + in_off[ct] + (size_t)l * N;
+        for (int j = threadIdx.x; j < N; j += blockDim.x) s[sidx(j)] = (T)add_mod((uint64_t)s[sidx(j)], c0[j], lc.q);
+        __syncthreads();
     }
-    __syncthreads();
     unsigned char *ob = out + out_off[ct] + (size_t)comp * olay.bytes + olay.off[l];
     if (olay.es[l] == 4) {
         uint32_t *o = reinterpret_cast<uint32_t *>(ob);
-#pragma unroll
-        for (int r = 0; r < NPER; r++) {
-            const int k = tid + r * T;
-            uint64_t v = s[perm[k]];
+        for (int k = threadIdx.x; k < N; k += blockDim.x) {
+            uint64_t v = s[sidx(perm[k])];  // PermuteNTTWithIndexLvl: out[k] = in[index[k]]
             if (accumulate) v = add_mod(v, (uint64_t)o[k], lc.q);
             o[k] = (uint32_t)v;
         }
     } else {
         uint64_t *o = reinterpret_cast<uint64_t *>(ob);
-#pragma unroll
-        for (int r = 0; r < NPER; r++) {
-            const int k = tid + r * T;
-            uint64_t v = s[perm[k]];  // PermuteNTTWithIndexLvl: out[k] = in[index[k]]
+        for (int k = threadIdx.x; k < N; k += blockDim.x) {
+            uint64_t v = s[sidx(perm[k])];
             if (accumulate) v = add_mod(v, o[k], lc.q);
             o[k] = v;
         }
@@ -188,50 +241,98 @@ int launch_copy_add(Ctx *c, const KsBatch &b, cudaStream_t st) {
     return 0;
 }
 
-template <int NPER>
-static int rotate_impl(Ctx *c, const KsBatch &b, const GaloisKey &key, cudaStream_t st) {
-    const long long in_first = b.in_first, in_stride = b.in_stride;
-    const int N = c->N, nl = b.level + 1, nt = nl + c->nP;
-    const int T = N / NPER;
-    BaseConv *ks, *md;
-    uint64_t *pinv;
-    if (ctx_get_ks_tables(c, b.level, &ks, &md, &pinv)) return -1;
-    // 1. c2 = INTT(c1)
-    LimbSel sel;
-    sel.n = nl;
-    for (int i = 0; i < nl; i++) sel.idx[i] = i;
-    if (launch_ntt(c, b.in + in_first + (size_t)b.in_nl * N, (size_t)in_stride, b.c2, (size_t)nl * N, b.nct * nl, sel, true, st)) return -1;
-    // 2. inner products with the switching key
-    const size_t smem = (size_t)N * sizeof(uint64_t);
-    SFG_CUDA(c, cudaFuncSetAttribute(k_ks_inner<NPER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    SFG_CUDA(c, cudaFuncSetAttribute(k_ks_moddown<NPER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    {
-        dim3 g(nt, b.nct);
-        k_ks_inner<NPER><<<g, T, smem, st>>>(b.in, b.in_off, b.in_nl, b.c2, key.key, ks, b.level, c->nQ, c->nP, c->logN, c->tw, c->lc, b.acc);
-        SFG_LAUNCHED(c, "k_ks_inner", st);
+static int ntt_threads(int S) { return std::min(256, std::max(32, S >> 5)); }
+
+template <class A>
+static int inner_launch(Ctx *c, const KsBatch &b, BaseConv *ks, const TgtSel &sel, cudaStream_t st) {
+    if (sel.n == 0) return 0;
+    const int logN = c->logN, cs = logN > 13 ? 1 : 0, logS = logN - cs, S = 1 << logS;
+    const PassPlan plan = make_pass_plan(logS - 5);
+    const size_t smem = 3 * ntt_smem_elems(S) * sizeof(typename A::T);
+    dim3 g(sel.n << cs, b.nct);
+    if (cs == 0) {
+        SFG_CUDA(c, cudaFuncSetAttribute(k_ks_inner2<A, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_ks_inner2<A, 0><<<g, ntt_threads(S), smem, st>>>(b.in, b.in_off, b.in_nl, b.c2, b.c2_slot, b.keys, ks, b.level, c->nQ, c->nP, logN, plan, c->tw2, c->lc,
+                                                          b.acc, sel);
+    } else {
+        SFG_CUDA(c, cudaFuncSetAttribute(k_ks_inner2<A, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_ks_inner2<A, 1><<<g, ntt_threads(S), smem, st>>>(b.in, b.in_off, b.in_nl, b.c2, b.c2_slot, b.keys, ks, b.level, c->nQ, c->nP, logN, plan, c->tw2, c->lc,
+                                                          b.acc, sel);
     }
-    // 3. INTT of the P limbs of acc: groups = (ct, comp), per-group limbs nQ..nQ+nP-1 located after the nl Q limbs
-    LimbSel selp;
-    selp.n = c->nP;
-    for (int i = 0; i < c->nP; i++) selp.idx[i] = c->nQ + i;
-    if (launch_ntt(c, b.acc + (size_t)nl * N, (size_t)nt * N, b.acc + (size_t)nl * N, (size_t)nt * N, b.nct * 2 * c->nP, selp, true, st)) return -1;
-    // 4. mod-down, + c0, automorphism, store / accumulate
-    {
-        dim3 g(b.out_layout.nl, 2, b.nct);
-        k_ks_moddown<NPER><<<g, T, smem, st>>>(b.in, b.in_off, b.in_nl, b.acc, md, pinv, key.perm, b.level, c->nQ, c->nP, c->logN, c->tw,
-                                              c->lc, (unsigned char *)b.out, b.out_off, b.out_layout, b.accumulate ? 1 : 0);
-        SFG_LAUNCHED(c, "k_ks_moddown", st);
-    }
+    SFG_LAUNCHED(c, "k_ks_inner2", st);
     return 0;
 }
 
-int launch_rotate(Ctx *c, const KsBatch &b, const GaloisKey &key, cudaStream_t st) {
+template <class A>
+static int moddown_launch(Ctx *c, const KsBatch &b, BaseConv *md, uint64_t *pinv, const TgtSel &sel, cudaStream_t st) {
+    if (sel.n == 0) return 0;
+    const int logN = c->logN, N = c->N;
+    const PassPlan plan = make_pass_plan(logN - 5);
+    const size_t smem = ntt_smem_elems(N) * sizeof(typename A::T);
+    SFG_CUDA(c, cudaFuncSetAttribute(k_ks_moddown2<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 g(sel.n, 2, b.nct);
+    k_ks_moddown2<A><<<g, std::min(512, std::max(32, N >> 5)), smem, st>>>(b.in, b.in_off, b.in_nl, b.acc, md, pinv, b.perms, b.level, c->nQ, c->nP, logN,
+                                                                           plan, c->tw2, c->lc, (unsigned char *)b.out, b.out_off, b.out_layout,
+                                                                           b.accumulate ? 1 : 0, sel);
+    SFG_LAUNCHED(c, "k_ks_moddown2", st);
+    return 0;
+}
+
+static int rotate_chunk(Ctx *c, const KsBatch &b, BaseConv *ks, BaseConv *md, uint64_t *pinv, cudaStream_t st) {
+    const int N = c->N, nl = b.level + 1, nt = nl + c->nP;
+    // 2. inner products with the switching keys, one launch per arithmetic class of the target modulus
+    TgtSel ts[3] = {{0, {}}, {0, {}}, {0, {}}};
+    for (int tt = 0; tt < nt; tt++) {
+        const int tgt = tt < nl ? tt : c->nQ + (tt - nl);
+        TgtSel &t = ts[arith_kind(c->mod[tgt])];
+        t.tt[t.n++] = tt;
+    }
+    if (inner_launch<ArW>(c, b, ks, ts[kArW], st) || inner_launch<ArN30>(c, b, ks, ts[kArN30], st) || inner_launch<ArN31>(c, b, ks, ts[kArN31], st))
+        return -1;
+    // 3. INTT of the P limbs of acc (TT order in, natural order out, in place): groups = (ct, comp)
+    LimbSel selp;
+    selp.n = c->nP;
+    for (int i = 0; i < c->nP; i++) selp.idx[i] = c->nQ + i;
+    if (launch_ntt_gather(c, b.acc + (size_t)nl * N, nullptr, (size_t)nt * N, b.acc + (size_t)nl * N, (size_t)nt * N, b.nct * 2 * c->nP, selp, true,
+                          true, st))
+        return -1;
+    // 4. mod-down, + c0, automorphism, store / accumulate
+    TgtSel ls[3] = {{0, {}}, {0, {}}, {0, {}}};
+    for (int l = 0; l < b.out_layout.nl; l++) {
+        TgtSel &t = ls[arith_kind(c->mod[l])];
+        t.tt[t.n++] = l;
+    }
+    if (moddown_launch<ArW>(c, b, md, pinv, ls[kArW], st) || moddown_launch<ArN30>(c, b, md, pinv, ls[kArN30], st) ||
+        moddown_launch<ArN31>(c, b, md, pinv, ls[kArN31], st))
+        return -1;
+    return 0;
+}
+
+int launch_rotate(Ctx *c, const KsBatch &b, cudaStream_t st) {
     if (b.nct <= 0) return 0;
     if (c->logN > 14) SFG_FAIL(c, "fused key-switch kernels support logN <= 14 (got %d)", c->logN);
     if (c->logN < 6) SFG_FAIL(c, "logN >= 6 required");
-    if (c->logN == 14) return rotate_impl<16>(c, b, key, st);
-    if (c->logN >= 9) return rotate_impl<8>(c, b, key, st);
-    return rotate_impl<2>(c, b, key, st);
+    if (b.acc_cap < 1) SFG_FAIL(c, "key-switch scratch is empty");
+    const int N = c->N, nl = b.level + 1;
+    BaseConv *ks, *md;
+    uint64_t *pinv;
+    if (ctx_get_ks_tables(c, b.level, &ks, &md, &pinv)) return -1;
+    // 1. c2 = INTT(c1), once per distinct input ciphertext
+    LimbSel sel;
+    sel.n = nl;
+    for (int i = 0; i < nl; i++) sel.idx[i] = i;
+    if (launch_ntt_gather(c, b.in + (size_t)b.in_nl * N, b.c2_src_off, 0, b.c2, (size_t)nl * N, b.n_c2 * nl, sel, true, false, st)) return -1;
+    for (int k0 = 0; k0 < b.nct; k0 += b.acc_cap) {
+        KsBatch ch = b;
+        ch.nct = std::min(b.acc_cap, b.nct - k0);
+        ch.in_off += k0;
+        ch.c2_slot += k0;
+        ch.keys += k0;
+        ch.perms += k0;
+        ch.out_off += k0;
+        if (rotate_chunk(c, ch, ks, md, pinv, st)) return -1;
+    }
+    return 0;
 }
 
 }  // namespace sfg

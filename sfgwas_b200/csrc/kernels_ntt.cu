@@ -5,6 +5,7 @@
 // stages run over smem; the first (forward) / last (inverse) log2(N/S) stages of logN > 14 run over global memory.
 #include "kernels.h"
 #include "ntt.cuh"
+#include "ntt2.cuh"
 
 namespace sfg {
 
@@ -70,7 +71,103 @@ __global__ void k_copy_polys(const uint64_t *__restrict__ src, size_t src_gstrid
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) out[i] = in[i];
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// register-tiled transforms (ntt2.cuh) for rings that fit one CTA's shared memory (logN <= 14), one launch per arithmetic class
+// ---------------------------------------------------------------------------------------------------------------
+struct SubSel {  // the polynomials of a group that belong to one arithmetic class
+    int n;
+    int pos[kMaxLimbs];   // position k inside the group (polynomial at group base + k*N)
+    int limb[kMaxLimbs];  // modulus index
+};
+
+template <class A>
+__global__ void __launch_bounds__(512, 1)
+k_ntt2_fwd(const uint64_t *__restrict__ src, const long long *__restrict__ src_off, size_t src_gstride, uint64_t *__restrict__ dst,
+           size_t dst_gstride, SubSel sub, int logN, PassPlan plan, const TwTab *__restrict__ tabs, const LimbConst *__restrict__ lcs) {
+    using T = typename A::T;
+    extern __shared__ __align__(16) unsigned char smraw[];
+    T *s = reinterpret_cast<T *>(smraw);
+    const int N = 1 << logN, g = blockIdx.x / sub.n, kk = blockIdx.x % sub.n, k = sub.pos[kk], limb = sub.limb[kk];
+    const uint64_t *in = src + (src_off ? (size_t)src_off[g] : (size_t)g * src_gstride) + (size_t)k * N;
+    uint64_t *out = dst + (size_t)g * dst_gstride + (size_t)k * N;
+    const typename A::C c = A::make(lcs[limb]);
+    ntt_forward<A>(s, logN, logN, 0, plan, tabs[limb], c, [&](int j) { return A::from_canon(in[j], c); },
+                   [&](int j, T v) { s[sidx(j)] = A::canon(v, c); });
+    __syncthreads();
+    for (int j = threadIdx.x; j < N; j += blockDim.x) out[j] = s[sidx(j)];
+}
+
+template <class A>
+__global__ void __launch_bounds__(512, 1)
+k_ntt2_inv(const uint64_t *__restrict__ src, const long long *__restrict__ src_off, size_t src_gstride, uint64_t *__restrict__ dst,
+           size_t dst_gstride, SubSel sub, int logN, PassPlan plan, const TwTab *__restrict__ tabs, const LimbConst *__restrict__ lcs, int in_tt) {
+    using T = typename A::T;
+    extern __shared__ __align__(16) unsigned char smraw[];
+    T *s = reinterpret_cast<T *>(smraw);
+    const int N = 1 << logN, g = blockIdx.x / sub.n, kk = blockIdx.x % sub.n, k = sub.pos[kk], limb = sub.limb[kk];
+    const uint64_t *in = src + (src_off ? (size_t)src_off[g] : (size_t)g * src_gstride) + (size_t)k * N;
+    uint64_t *out = dst + (size_t)g * dst_gstride + (size_t)k * N;
+    const typename A::C c = A::make(lcs[limb]);
+    auto fin = [&](int j, T v) { out[j] = v; };
+    if (in_tt) {
+        ntt_inverse<A>(s, logN, plan, tabs[limb], c, [&](int j) { return A::from_canon(in[tt_index(j, N)], c); }, fin);
+    } else {
+        for (int j = threadIdx.x; j < N; j += blockDim.x) s[sidx(j)] = A::from_canon(in[j], c);
+        __syncthreads();
+        ntt_inverse<A>(s, logN, plan, tabs[limb], c, [&](int j) { return s[sidx(j)]; }, fin);
+    }
+}
+
+template <class A>
+static int ntt2_launch(Ctx *c, const uint64_t *src, const long long *src_off, size_t sgs, uint64_t *dst, size_t dgs, int ngroups,
+                       const SubSel &sub, bool inverse, bool in_tt, cudaStream_t st) {
+    if (sub.n == 0 || ngroups == 0) return 0;
+    const int logN = c->logN, N = c->N;
+    const PassPlan plan = make_pass_plan(logN - 5);
+    const size_t smem = ntt_smem_elems(N) * sizeof(typename A::T);
+    const int threads = std::min(512, std::max(32, N >> 5));
+    if (inverse) {
+        SFG_CUDA(c, cudaFuncSetAttribute(k_ntt2_inv<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_ntt2_inv<A><<<ngroups * sub.n, threads, smem, st>>>(src, src_off, sgs, dst, dgs, sub, logN, plan, c->tw2, c->lc, in_tt ? 1 : 0);
+        SFG_LAUNCHED(c, "k_ntt2_inv", st);
+    } else {
+        SFG_CUDA(c, cudaFuncSetAttribute(k_ntt2_fwd<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_ntt2_fwd<A><<<ngroups * sub.n, threads, smem, st>>>(src, src_off, sgs, dst, dgs, sub, logN, plan, c->tw2, c->lc);
+        SFG_LAUNCHED(c, "k_ntt2_fwd", st);
+    }
+    return 0;
+}
+
+static int launch_ntt_old(Ctx *c, const uint64_t *src, size_t src_gstride, uint64_t *dst, size_t dst_gstride, int npoly, const LimbSel &sel,
+                          bool inverse, cudaStream_t st);
+
+// src_off (device, optional): element offset of every group's first polynomial (overrides g*src_gstride).
+// in_tt: the inputs are in TT order (inverse transforms only).
+int launch_ntt_gather(Ctx *c, const uint64_t *src, const long long *src_off, size_t src_gstride, uint64_t *dst, size_t dst_gstride, int npoly,
+                      const LimbSel &sel, bool inverse, bool in_tt, cudaStream_t st) {
+    if (npoly <= 0) return 0;
+    if (c->logN > 14) {
+        if (src_off || in_tt) SFG_FAIL(c, "gathered / TT transforms support logN <= 14 (got %d)", c->logN);
+        return launch_ntt_old(c, src, src_gstride, dst, dst_gstride, npoly, sel, inverse, st);
+    }
+    SubSel sub[3] = {{0, {}, {}}, {0, {}, {}}, {0, {}, {}}};
+    for (int k = 0; k < sel.n; k++) {
+        SubSel &s = sub[arith_kind(c->mod[sel.idx[k]])];
+        s.pos[s.n] = k;
+        s.limb[s.n++] = sel.idx[k];
+    }
+    const int ngroups = npoly / sel.n;
+    if (ntt2_launch<ArW>(c, src, src_off, src_gstride, dst, dst_gstride, ngroups, sub[kArW], inverse, in_tt, st)) return -1;
+    if (ntt2_launch<ArN30>(c, src, src_off, src_gstride, dst, dst_gstride, ngroups, sub[kArN30], inverse, in_tt, st)) return -1;
+    if (ntt2_launch<ArN31>(c, src, src_off, src_gstride, dst, dst_gstride, ngroups, sub[kArN31], inverse, in_tt, st)) return -1;
+    return 0;
+}
 int launch_ntt(Ctx *c, const uint64_t *src, size_t src_gstride, uint64_t *dst, size_t dst_gstride, int npoly, const LimbSel &sel,
+               bool inverse, cudaStream_t st) {
+    return launch_ntt_gather(c, src, nullptr, src_gstride, dst, dst_gstride, npoly, sel, inverse, false, st);
+}
+
+static int launch_ntt_old(Ctx *c, const uint64_t *src, size_t src_gstride, uint64_t *dst, size_t dst_gstride, int npoly, const LimbSel &sel,
                bool inverse, cudaStream_t st) {
     if (npoly <= 0) return 0;
     const int logN = c->logN, N = c->N;

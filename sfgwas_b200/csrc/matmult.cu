@@ -20,7 +20,6 @@
 namespace sfg {
 
 thread_local float g_last_ms[5] = {0, 0, 0, 0, 0};
-thread_local float g_mac_kernel_ms = 0;
 
 // ---------------------------------------------------------------------------------------------------------------
 // genotype matrix
@@ -201,53 +200,115 @@ static int find_key(Ctx *c, int rot_left, const GaloisKey **out) {
     return 0;
 }
 
-struct Scratch {
-    Buf c2, acc, offs;
-    int cap = 0;
-    int ensure(Ctx *c, int nct, int nl) {
-        if (nct <= cap) return 0;
-        const size_t N = c->N;
-        if (c2.alloc(c, (size_t)nct * nl * N * 8)) return -1;
-        if (acc.alloc(c, (size_t)nct * 2 * (nl + c->nP) * N * 8)) return -1;
-        cap = nct;
-        return 0;
-    }
-};
-
 struct PhaseTimer {
     std::vector<cudaEvent_t> ev;
     std::vector<int> phase;
     cudaStream_t st;
     explicit PhaseTimer(cudaStream_t s) : st(s) {}
-    void mark(int ph) {  // ph = phase that STARTS here (-1 = end)
+    void mark(int ph) {  // ph = phase that STARTS here (-1 = end, 3 = MAC kernel proper)
         cudaEvent_t e;
         cudaEventCreate(&e);
         cudaEventRecord(e, st);
         ev.push_back(e);
         phase.push_back(ph);
     }
-    void finish(float out[4]) {
-        out[0] = out[1] = out[2] = out[3] = 0;
+    void finish(float out[5]) {
+        for (int i = 0; i < 5; i++) out[i] = 0;
         if (ev.empty()) return;
         cudaEventSynchronize(ev.back());
         for (size_t i = 0; i + 1 < ev.size(); i++) {
             float ms = 0;
             cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
-            if (phase[i] >= 0 && phase[i] < 3) out[phase[i]] += ms;
+            if (phase[i] == 3) {  // the MAC kernel alone: also part of the MAC phase
+                out[4] += ms;
+                out[1] += ms;
+            } else if (phase[i] >= 0 && phase[i] < 3) {
+                out[phase[i]] += ms;
+            }
         }
         cudaEventElapsedTime(&out[3], ev.front(), ev.back());
         for (auto e : ev) cudaEventDestroy(e);
         ev.clear();
     }
 };
+static thread_local PhaseTimer *g_tm = nullptr;
+
+// ---------------------------------------------------------------------------------------------------------------
+// rotation batches: every entry = one ciphertext rotated with its own Galois key (kernels_ks.cu)
+// ---------------------------------------------------------------------------------------------------------------
+struct RotEntry {
+    long long in_off;   // element offset of the input ct
+    long long out_off;  // BYTE offset of the output ct
+    int c2_slot;        // which INTT(c1) slot it reads
+    const GaloisKey *key;
+};
+
+// device image of the per-entry arrays of a list of batches, uploaded once
+struct RotMeta {
+    std::vector<long long> in_off, out_off, c2_src;
+    std::vector<const uint64_t *> keys;
+    std::vector<const uint32_t *> perms;
+    std::vector<int> c2_slot;
+    // device pointers after upload
+    const long long *d_in_off = nullptr, *d_out_off = nullptr, *d_c2_src = nullptr;
+    const uint64_t *const *d_keys = nullptr;
+    const uint32_t *const *d_perms = nullptr;
+    const int *d_c2_slot = nullptr;
+    void add(const RotEntry &e) {
+        in_off.push_back(e.in_off);
+        out_off.push_back(e.out_off);
+        c2_slot.push_back(e.c2_slot);
+        keys.push_back(e.key ? e.key->key : nullptr);
+        perms.push_back(e.key ? e.key->perm : nullptr);
+    }
+    int upload(Ctx *c, int slot) {
+        const size_t n = in_off.size(), m = c2_src.size();
+        const size_t bytes = (2 * n + m) * 8 + 2 * n * 8 + n * 4 + 64;
+        std::vector<unsigned char> h(bytes);
+        unsigned char *p = h.data();
+        size_t o_in = 0, o_out = n * 8, o_src = 2 * n * 8, o_keys = (2 * n + m) * 8, o_perms = o_keys + n * 8, o_slot = o_perms + n * 8;
+        memcpy(p + o_in, in_off.data(), n * 8);
+        memcpy(p + o_out, out_off.data(), n * 8);
+        memcpy(p + o_src, c2_src.data(), m * 8);
+        memcpy(p + o_keys, keys.data(), n * 8);
+        memcpy(p + o_perms, perms.data(), n * 8);
+        memcpy(p + o_slot, c2_slot.data(), n * 4);
+        void *d;
+        if (ws_get(c, slot, bytes, &d)) return -1;
+        SFG_CUDA(c, cudaMemcpyAsync(d, p, bytes, cudaMemcpyDefault, c->stream));
+        unsigned char *db = (unsigned char *)d;
+        d_in_off = (const long long *)(db + o_in);
+        d_out_off = (const long long *)(db + o_out);
+        d_c2_src = (const long long *)(db + o_src);
+        d_keys = (const uint64_t *const *)(db + o_keys);
+        d_perms = (const uint32_t *const *)(db + o_perms);
+        d_c2_slot = (const int *)(db + o_slot);
+        return 0;
+    }
+};
+
+// scratch for a batch: c2 [n_c2][nl][N], acc [cap][2][nl+nP][N] with cap bounded by a 2 GiB budget
+static int fill_scratch(Ctx *c, KsBatch &kb, int max_nct, int max_c2) {
+    const size_t N = c->N;
+    const int nl = kb.level + 1, nt = nl + c->nP;
+    const size_t per_ct = (size_t)2 * nt * N * 8;
+    const int cap = (int)std::max<size_t>(1, std::min<size_t>((size_t)max_nct, ((size_t)2 << 30) / per_ct));
+    void *pc2, *pacc;
+    if (ws_get(c, WS_C2, (size_t)max_c2 * nl * N * 8, &pc2) || ws_get(c, WS_ACC, (size_t)cap * per_ct, &pacc)) return -1;
+    kb.c2 = (uint64_t *)pc2;
+    kb.acc = (uint64_t *)pacc;
+    kb.acc_cap = cap;
+    return 0;
+}
 
 // ---------------------------------------------------------------------------------------------------------------
 // (1) baby-step rotation cache  R[k][row = 2i+c][l < L][N]  for the K entries whose block row is in [bi_lo, bi_hi)
 //     gwas/matmult.go:1083-1119 : rotCache[i][baby] = RotateRightWithEvaluator(A[i][bi], -baby)
+//     ONE batch over every (baby step, i, bi): each entry carries its own Galois key; INTT(c1) is shared by all baby steps.
 // ---------------------------------------------------------------------------------------------------------------
 static int build_rot_cache(Ctx *c, const Cache *ca, const uint64_t *d_A, int s, int levelA, int bi_lo, int bi_hi,
-                           std::vector<int> &klist, Buf &R, Scratch &scr) {
-    const int d = ca->d, nbr = ca->nbr, L = ca->L, N = c->N, nlA = levelA + 1, nrows = 2 * s;
+                           std::vector<int> &klist, void **R_out) {
+    const int d = ca->d, nbr = ca->nbr, N = c->N, nlA = levelA + 1, nrows = 2 * s;
     klist.clear();
     std::vector<int> klocal((size_t)nbr * d, -1);
     for (size_t k = 0; k < ca->kbi.size(); k++)
@@ -256,60 +317,64 @@ static int build_rot_cache(Ctx *c, const Cache *ca, const uint64_t *d_A, int s, 
             klist.push_back((int)k);
         }
     const size_t RB = (size_t)ca->lay.bytes;  // bytes of one (k, row) record
-    (void)L;
-    if (R.alloc(c, klist.size() * nrows * RB)) return -1;
+    void *R;
+    if (ws_get(c, WS_R, std::max<size_t>(klist.size(), 1) * nrows * RB, &R)) return -1;
+    *R_out = R;
     const size_t ctA = (size_t)2 * nlA * N;
-    // offsets for every batch, uploaded once
-    struct Batch { int b, nct; long long first, stride; size_t off_pos; };
-    std::vector<Batch> batches;
-    std::vector<long long> offs;
+    RotMeta rot, cpy;
+    std::vector<int> slot_of((size_t)s * nbr, -1);
     for (int b = 0; b < d; b++) {
-        std::vector<int> bis;
-        for (int bi = bi_lo; bi < bi_hi; bi++)
-            if (ca->baby[(size_t)bi * d + b]) bis.push_back(bi);
-        if (bis.empty()) continue;
-        if ((int)bis.size() == nbr) {  // every block row: one batch over all (i, bi), cts are contiguous in A
-            Batch bt{b, s * nbr, 0, (long long)ctA, offs.size()};
-            for (int t = 0; t < s * nbr; t++) offs.push_back((long long)t * ctA);
-            for (int t = 0; t < s * nbr; t++) {
-                const int i = t / nbr, bi = t % nbr;
-                offs.push_back((long long)(((size_t)klocal[(size_t)bi * d + b] * nrows + 2 * i) * RB));
-            }
-            batches.push_back(bt);
-        } else {
-            for (int bi : bis) {
-                Batch bt{b, s, (long long)(bi * ctA), (long long)(nbr * ctA), offs.size()};
-                for (int i = 0; i < s; i++) offs.push_back((long long)(((size_t)i * nbr + bi) * ctA));
-                for (int i = 0; i < s; i++) offs.push_back((long long)(((size_t)klocal[(size_t)bi * d + b] * nrows + 2 * i) * RB));
-                batches.push_back(bt);
+        const GaloisKey *key = nullptr;
+        if (b > 0) {
+            bool any = false;
+            for (int bi = bi_lo; bi < bi_hi; bi++) any |= ca->baby[(size_t)bi * d + b] != 0;
+            if (!any) continue;
+            if (find_key(c, b, &key)) return -1;
+        }
+        for (int bi = bi_lo; bi < bi_hi; bi++) {
+            if (!ca->baby[(size_t)bi * d + b]) continue;
+            for (int i = 0; i < s; i++) {
+                const long long in_off = (long long)(((size_t)i * nbr + bi) * ctA);
+                const long long out_off = (long long)(((size_t)klocal[(size_t)bi * d + b] * nrows + 2 * i) * RB);
+                if (b == 0) {
+                    cpy.add(RotEntry{in_off, out_off, 0, nullptr});
+                } else {
+                    int &sl = slot_of[(size_t)i * nbr + bi];
+                    if (sl < 0) {
+                        sl = (int)rot.c2_src.size();
+                        rot.c2_src.push_back(in_off);
+                    }
+                    rot.add(RotEntry{in_off, out_off, sl, key});
+                }
             }
         }
     }
-    if (scr.offs.alloc(c, std::max<size_t>(offs.size(), 1) * sizeof(long long))) return -1;
-    SFG_CUDA(c, cudaMemcpyAsync(scr.offs.p, offs.data(), offs.size() * sizeof(long long), cudaMemcpyDefault, c->stream));
-    if (scr.ensure(c, s * nbr, ca->maxLevel + 1)) return -1;
-    for (const Batch &bt : batches) {
-        KsBatch kb;
-        kb.level = ca->maxLevel;  // A is dropped to maxLevel: only limbs 0..maxLevel are read (crypto/basics.go:806-824)
-        kb.nct = bt.nct;
-        kb.in = d_A;
-        kb.in_off = scr.offs.as<long long>() + bt.off_pos;
-        kb.in_first = bt.first;
-        kb.in_stride = bt.stride;
-        kb.in_nl = nlA;
-        kb.out = R.p;
-        kb.out_off = scr.offs.as<long long>() + bt.off_pos + bt.nct;
-        kb.out_layout = ca->lay;  // limb index maxLevel of the rotated ct is never read by the MAC (App. A.4)
-        kb.accumulate = false;
-        kb.c2 = scr.c2.as<uint64_t>();
-        kb.acc = scr.acc.as<uint64_t>();
-        if (bt.b == 0) {
-            if (launch_copy_add(c, kb, c->stream)) return -1;
-        } else {
-            const GaloisKey *key;
-            if (find_key(c, bt.b, &key)) return -1;
-            if (launch_rotate(c, kb, *key, c->stream)) return -1;
-        }
+    KsBatch kb{};
+    kb.level = ca->maxLevel;  // A is dropped to maxLevel: only limbs 0..maxLevel are read (crypto/basics.go:806-824)
+    kb.in = d_A;
+    kb.in_nl = nlA;
+    kb.out = R;
+    kb.out_layout = ca->lay;  // limb index maxLevel of the rotated ct is never read by the MAC (App. A.4)
+    kb.accumulate = false;
+    if (!cpy.in_off.empty()) {
+        if (cpy.upload(c, WS_META2)) return -1;
+        kb.nct = (int)cpy.in_off.size();
+        kb.in_off = cpy.d_in_off;
+        kb.out_off = cpy.d_out_off;
+        if (launch_copy_add(c, kb, c->stream)) return -1;
+    }
+    if (!rot.in_off.empty()) {
+        if (rot.upload(c, WS_META)) return -1;
+        kb.nct = (int)rot.in_off.size();
+        kb.in_off = rot.d_in_off;
+        kb.out_off = rot.d_out_off;
+        kb.n_c2 = (int)rot.c2_src.size();
+        kb.c2_src_off = rot.d_c2_src;
+        kb.c2_slot = rot.d_c2_slot;
+        kb.keys = rot.d_keys;
+        kb.perms = rot.d_perms;
+        if (fill_scratch(c, kb, kb.nct, kb.n_c2)) return -1;
+        if (launch_rotate(c, kb, c->stream)) return -1;
     }
     return 0;
 }
@@ -320,11 +385,9 @@ static int build_rot_cache(Ctx *c, const Cache *ca, const uint64_t *d_A, int s, 
 // ---------------------------------------------------------------------------------------------------------------
 static int run_mac(Ctx *c, const Cache *ca, const void *R, const std::vector<int> &klist, int s, int gi_lo, int gi_hi,
                    uint64_t *d_cv) {
-    const int d = ca->d, m_ct = ca->m_ct, slots = ca->slots, L = ca->L, N = c->N;
+    const int d = ca->d, m_ct = ca->m_ct, slots = ca->slots;
     const int K = (int)klist.size(), ncols = (gi_hi - gi_lo) * m_ct;
     if (K == 0 || ncols == 0) return 0;
-    (void)L;
-    (void)N;
     std::vector<int> poff((size_t)ncols * K, -1);
     std::vector<EncJob> jobs;  // only when the cache is not materialised
     size_t ntmp = 0;
@@ -349,80 +412,68 @@ static int run_mac(Ctx *c, const Cache *ca, const void *R, const std::vector<int
             }
         }
     }
-    Buf dpoff, tmpP;
-    if (dpoff.alloc(c, poff.size() * sizeof(int))) return -1;
-    SFG_CUDA(c, cudaMemcpyAsync(dpoff.p, poff.data(), poff.size() * sizeof(int), cudaMemcpyDefault, c->stream));
+    void *dpoff, *tmpP = nullptr;
+    if (ws_get(c, WS_POFF, poff.size() * sizeof(int), &dpoff)) return -1;
+    SFG_CUDA(c, cudaMemcpyAsync(dpoff, poff.data(), poff.size() * sizeof(int), cudaMemcpyDefault, c->stream));
     const void *P = ca->P;
     if (!ca->materialised) {
-        if (tmpP.alloc(c, std::max<size_t>(ntmp, 1) * (size_t)ca->lay.bytes)) return -1;
-        if (encode_jobs(c, ca, jobs, tmpP.p)) return -1;
-        P = tmpP.p;
+        if (ws_get(c, WS_TMPP, std::max<size_t>(ntmp, 1) * (size_t)ca->lay.bytes, &tmpP)) return -1;
+        if (encode_jobs(c, ca, jobs, tmpP)) return -1;
+        P = tmpP;
     }
-    cudaEvent_t e0, e1;  // the MAC kernel alone, on the stream it is launched on (bench.py roofline)
-    SFG_CUDA(c, cudaEventCreate(&e0));
-    SFG_CUDA(c, cudaEventCreate(&e1));
-    SFG_CUDA(c, cudaEventRecord(e0, c->stream));
-    if (launch_mac(c, R, P, dpoff.as<int>(), K, 2 * s, ncols, ca->lay, d_cv, c->stream)) return -1;
-    SFG_CUDA(c, cudaEventRecord(e1, c->stream));
-    SFG_CUDA(c, cudaStreamSynchronize(c->stream));  // poff / tmpP are freed on return
-    float ms = 0;
-    cudaEventElapsedTime(&ms, e0, e1);
-    g_mac_kernel_ms += ms;
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
+    if (g_tm) g_tm->mark(3);  // the MAC kernel alone, on the stream it is launched on (bench.py roofline)
+    if (launch_mac(c, R, P, (const int *)dpoff, K, 2 * s, ncols, ca->lay, d_cv, c->stream)) return -1;
+    if (g_tm) g_tm->mark(1);
     return 0;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // (3) giant-step alignment + accumulation (gwas/matmult.go:1203-1227):
 //     out[i][bj] += RotateRightWithEvaluator(cv[i][g][bj], -g*d)   for g in gact[gi_lo .. gi_hi)
+//     one batch per giant step (entries of a batch must target distinct outputs), metadata uploaded once for all of them
 // ---------------------------------------------------------------------------------------------------------------
-static int run_giant(Ctx *c, const Cache *ca, int s, const uint64_t *d_cv, int gi_lo, int gi_hi, uint64_t *d_out, Scratch &scr) {
+static int run_giant(Ctx *c, const Cache *ca, int s, const uint64_t *d_cv, int gi_lo, int gi_hi, uint64_t *d_out) {
     const int d = ca->d, m_ct = ca->m_ct, L = ca->L, N = c->N, nrows = 2 * s;
     const size_t LN = (size_t)L * N;
     const int nct = m_ct * s;
     if (gi_hi <= gi_lo) return 0;
-    std::vector<long long> offs;
-    for (int gi = gi_lo; gi < gi_hi; gi++) {
-        for (int t = 0; t < nct; t++) {  // t = bj*s + i : consecutive ciphertexts of the cv image
-            const int bj = t / s, i = t % s;
-            offs.push_back((long long)((((size_t)(gi - gi_lo) * m_ct + bj) * nrows + 2 * i) * LN));
-        }
-    }
-    const size_t out_pos = offs.size();
-    for (int t = 0; t < nct; t++) {
-        const int bj = t / s, i = t % s;
-        offs.push_back((long long)(((size_t)i * m_ct + bj) * 2 * LN * 8));  // bytes
-    }
-    Buf doffs;
-    if (doffs.alloc(c, offs.size() * sizeof(long long))) return -1;
-    SFG_CUDA(c, cudaMemcpyAsync(doffs.p, offs.data(), offs.size() * sizeof(long long), cudaMemcpyDefault, c->stream));
-    if (scr.ensure(c, nct, L)) return -1;
+    RotMeta rot;
     for (int gi = gi_lo; gi < gi_hi; gi++) {
         const int g = ca->gact[gi];
-        KsBatch kb;
-        kb.level = L - 1;  // ModularReduceV2 creates the ct at level len(acc0)-1 (gwas/matmult.go:350)
-        kb.nct = nct;
-        kb.in = d_cv;
-        kb.in_off = doffs.as<long long>() + (size_t)(gi - gi_lo) * nct;
-        kb.in_first = offs[(size_t)(gi - gi_lo) * nct];
-        kb.in_stride = (long long)(2 * LN);
-        kb.in_nl = L;
-        kb.out = d_out;
-        kb.out_off = doffs.as<long long>() + out_pos;
-        kb.out_layout = make_layout(c, L, false);
-        kb.accumulate = true;
-        kb.c2 = scr.c2.as<uint64_t>();
-        kb.acc = scr.acc.as<uint64_t>();
-        if (g == 0) {
-            if (launch_copy_add(c, kb, c->stream)) return -1;
-        } else {
-            const GaloisKey *key;
-            if (find_key(c, (g * d) % ca->slots, &key)) return -1;
-            if (launch_rotate(c, kb, *key, c->stream)) return -1;
+        const GaloisKey *key = nullptr;
+        if (g > 0 && find_key(c, (g * d) % ca->slots, &key)) return -1;
+        for (int t = 0; t < nct; t++) {  // t = bj*s + i : consecutive ciphertexts of the cv image
+            const int bj = t / s, i = t % s;
+            const long long in_off = (long long)((((size_t)(gi - gi_lo) * m_ct + bj) * nrows + 2 * i) * LN);
+            rot.add(RotEntry{in_off, (long long)(((size_t)i * m_ct + bj) * 2 * LN * 8), t, key});
         }
     }
-    SFG_CUDA(c, cudaStreamSynchronize(c->stream));
+    rot.c2_src = rot.in_off;  // every entry is its own INTT slot (slot index restarts at 0 for every giant step)
+    if (rot.upload(c, WS_META)) return -1;
+    KsBatch kb{};
+    kb.level = L - 1;  // ModularReduceV2 creates the ct at level len(acc0)-1 (gwas/matmult.go:350)
+    kb.in = d_cv;
+    kb.in_nl = L;
+    kb.out = d_out;
+    kb.out_layout = make_layout(c, L, false);
+    kb.accumulate = true;
+    kb.nct = nct;
+    kb.n_c2 = nct;
+    if (fill_scratch(c, kb, nct, nct)) return -1;
+    for (int gi = gi_lo; gi < gi_hi; gi++) {
+        const size_t o = (size_t)(gi - gi_lo) * nct;
+        kb.in_off = rot.d_in_off + o;
+        kb.out_off = rot.d_out_off + o;
+        kb.c2_src_off = rot.d_c2_src + o;
+        kb.c2_slot = rot.d_c2_slot + o;
+        kb.keys = rot.d_keys + o;
+        kb.perms = rot.d_perms + o;
+        if (ca->gact[gi] == 0) {
+            if (launch_copy_add(c, kb, c->stream)) return -1;
+        } else if (launch_rotate(c, kb, c->stream)) {
+            return -1;
+        }
+    }
     return 0;
 }
 
@@ -442,33 +493,34 @@ int mm_compute_dev(Ctx *c, const uint64_t *d_A, int s, int nbr, int levelA, int 
     const int L = ca->L, N = c->N, m_ct = ca->m_ct;
     const size_t LN = (size_t)L * N;
     PhaseTimer tm(c->stream);
-    g_mac_kernel_ms = 0;
-    Scratch scr;
-    Buf R;
+    g_tm = &tm;
+    struct Reset { ~Reset() { g_tm = nullptr; } } reset;
+    void *R;
     std::vector<int> klist;
     tm.mark(0);
-    if (build_rot_cache(c, ca, d_A, s, levelA, 0, nbr, klist, R, scr)) return -1;
+    if (build_rot_cache(c, ca, d_A, s, levelA, 0, nbr, klist, &R)) return -1;
     SFG_CUDA(c, cudaMemsetAsync(d_out, 0, (size_t)s * m_ct * 2 * LN * 8, c->stream));
     // giant chunks bounded by the cv image size (default 24 GiB)
     const size_t per_g = (size_t)m_ct * 2 * s * LN * 8;
-    size_t fr = 0, tot = 0;
-    SFG_CUDA(c, cudaMemGetInfo(&fr, &tot));
-    size_t cv_budget = std::min<size_t>((size_t)24 << 30, fr / 3);
-    int gchunk = (int)std::max<size_t>(1, cv_budget / per_g);
     const int ng = (int)ca->gact.size();
-    gchunk = std::min(gchunk, ng);
-    Buf cv;
-    if (cv.alloc(c, (size_t)gchunk * per_g)) return -1;
+    int gchunk = ng;
+    if ((size_t)ng * per_g > c->ws[WS_CV].bytes) {
+        size_t fr = 0, tot = 0;
+        SFG_CUDA(c, cudaMemGetInfo(&fr, &tot));
+        const size_t cv_budget = std::min<size_t>((size_t)24 << 30, (fr + c->ws[WS_CV].bytes) / 3);
+        gchunk = std::min(ng, (int)std::max<size_t>(1, cv_budget / per_g));
+    }
+    void *cv;
+    if (ws_get(c, WS_CV, (size_t)gchunk * per_g, &cv)) return -1;
     for (int g0 = 0; g0 < ng; g0 += gchunk) {
         const int g1 = std::min(ng, g0 + gchunk);
         tm.mark(1);
-        if (run_mac(c, ca, R.p, klist, s, g0, g1, cv.as<uint64_t>())) return -1;
+        if (run_mac(c, ca, R, klist, s, g0, g1, (uint64_t *)cv)) return -1;
         tm.mark(2);
-        if (run_giant(c, ca, s, cv.as<uint64_t>(), g0, g1, d_out, scr)) return -1;
+        if (run_giant(c, ca, s, (const uint64_t *)cv, g0, g1, d_out)) return -1;
     }
     tm.mark(-1);
     tm.finish(g_last_ms);
-    g_last_ms[4] = g_mac_kernel_ms;
     SFG_CUDA(c, cudaStreamSynchronize(c->stream));
     return 0;
 }
@@ -481,21 +533,20 @@ int mm_partial_dev(Ctx *c, const uint64_t *d_A, int s, int nbr, int levelA, int 
     const size_t LN = (size_t)ca->L * c->N;
     const size_t total = ca->gact.size() * (size_t)ca->m_ct * 2 * s * LN;
     PhaseTimer tm(c->stream);
-    g_mac_kernel_ms = 0;
-    Scratch scr;
-    Buf R;
+    g_tm = &tm;
+    struct Reset { ~Reset() { g_tm = nullptr; } } reset;
+    void *R;
     std::vector<int> klist;
     tm.mark(0);
-    if (build_rot_cache(c, ca, d_A, s, levelA, bi_lo, bi_hi, klist, R, scr)) return -1;
+    if (build_rot_cache(c, ca, d_A, s, levelA, bi_lo, bi_hi, klist, &R)) return -1;
     tm.mark(1);
     if (klist.empty()) {
         SFG_CUDA(c, cudaMemsetAsync(d_cv, 0, total * 8, c->stream));
-    } else if (run_mac(c, ca, R.p, klist, s, 0, (int)ca->gact.size(), d_cv)) {
+    } else if (run_mac(c, ca, R, klist, s, 0, (int)ca->gact.size(), d_cv)) {
         return -1;
     }
     tm.mark(-1);
     tm.finish(g_last_ms);
-    g_last_ms[4] = g_mac_kernel_ms;
     SFG_CUDA(c, cudaStreamSynchronize(c->stream));
     return 0;
 }
@@ -507,14 +558,13 @@ int mm_finish_dev(Ctx *c, Cache *ca, int s, int maxLevel, const uint64_t *d_cv, 
     SFG_CUDA(c, cudaSetDevice(c->device));
     const size_t LN = (size_t)ca->L * c->N;
     PhaseTimer tm(c->stream);
-    Scratch scr;
     SFG_CUDA(c, cudaMemsetAsync(d_out, 0, (size_t)s * ca->m_ct * 2 * LN * 8, c->stream));
     tm.mark(2);
     const size_t per_g = (size_t)ca->m_ct * 2 * s * LN;
-    if (run_giant(c, ca, s, d_cv + (size_t)g_lo * per_g, g_lo, g_hi, d_out, scr)) return -1;
+    if (run_giant(c, ca, s, d_cv + (size_t)g_lo * per_g, g_lo, g_hi, d_out)) return -1;
     tm.mark(-1);
     tm.finish(g_last_ms);
-    g_last_ms[4] = g_mac_kernel_ms;
+    SFG_CUDA(c, cudaStreamSynchronize(c->stream));
     return 0;
 }
 
@@ -525,35 +575,32 @@ int rotate_right_dev(Ctx *c, int level, const uint64_t *d_in, int nct, int nrot,
     nrot %= slots;
     if (nrot < 0) nrot += slots;
     const size_t ct = (size_t)2 * nl * N;
-    std::vector<long long> offs(nct);
-    std::vector<long long> offs_b(nct);
-    for (int t = 0; t < nct; t++) { offs[t] = (long long)(t * ct); offs_b[t] = offs[t] * 8; }
-    Buf doffs, doffs_b;
-    if (doffs.alloc(c, std::max(1, nct) * sizeof(long long)) || doffs_b.alloc(c, std::max(1, nct) * sizeof(long long))) return -1;
-    SFG_CUDA(c, cudaMemcpyAsync(doffs.p, offs.data(), nct * sizeof(long long), cudaMemcpyDefault, c->stream));
-    SFG_CUDA(c, cudaMemcpyAsync(doffs_b.p, offs_b.data(), nct * sizeof(long long), cudaMemcpyDefault, c->stream));
-    Scratch scr;
-    if (scr.ensure(c, nct, nl)) return -1;
-    KsBatch kb;
+    const GaloisKey *key = nullptr;
+    if (nrot != 0 && find_key(c, slots - nrot, &key)) return -1;  // RotateNew(ct, slots - nrot): left rotation
+    RotMeta rot;
+    for (int t = 0; t < nct; t++) rot.add(RotEntry{(long long)(t * ct), (long long)(t * ct * 8), t, key});
+    rot.c2_src = rot.in_off;
+    if (rot.upload(c, WS_META)) return -1;
+    KsBatch kb{};
     kb.level = level;
     kb.nct = nct;
     kb.in = d_in;
-    kb.in_off = doffs.as<long long>();
-    kb.in_first = 0;
-    kb.in_stride = (long long)ct;
+    kb.in_off = rot.d_in_off;
     kb.in_nl = nl;
+    kb.n_c2 = nct;
+    kb.c2_src_off = rot.d_c2_src;
+    kb.c2_slot = rot.d_c2_slot;
+    kb.keys = rot.d_keys;
+    kb.perms = rot.d_perms;
     kb.out = d_out;
-    kb.out_off = doffs_b.as<long long>();
+    kb.out_off = rot.d_out_off;
     kb.out_layout = make_layout(c, nl, false);
     kb.accumulate = false;
-    kb.c2 = scr.c2.as<uint64_t>();
-    kb.acc = scr.acc.as<uint64_t>();
     if (nrot == 0) {
         if (launch_copy_add(c, kb, c->stream)) return -1;
     } else {
-        const GaloisKey *key;
-        if (find_key(c, slots - nrot, &key)) return -1;  // RotateNew(ct, slots - nrot): left rotation
-        if (launch_rotate(c, kb, *key, c->stream)) return -1;
+        if (fill_scratch(c, kb, nct, nct)) return -1;
+        if (launch_rotate(c, kb, c->stream)) return -1;
     }
     SFG_CUDA(c, cudaStreamSynchronize(c->stream));
     return 0;

@@ -72,6 +72,5 @@ int encode_diag_host(Ctx *c, const Geno *g, int bi, int shift, int nrot, int lev
                      int64_t *coeffs);
 
 extern thread_local float g_last_ms[5];  // baby, mac phase, giant, total, mac kernel only
-extern thread_local float g_mac_kernel_ms;
 
 }  // namespace sfg

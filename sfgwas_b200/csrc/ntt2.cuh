@@ -1,0 +1,304 @@
+// ntt2.cuh -- register-tiled negacyclic NTT / INTT over one CTA (sm_100a), specialised by limb width.
+//
+// Semantics are Lattigo's ring.NTT / ring.InvNTT: forward Cooley-Tukey from natural order to the
+// bit-reversed evaluation order a(psi^(2 brv(i)+1)), inverse Gentleman-Sande times N^-1; stage `s` has m = 2^s groups and uses
+// twiddle NttPsi[m + i] (NttPsiInv[m + i]).  Outputs are canonical, so any exact evaluation order is bit-identical.
+//
+// Organisation: a transform of 2^logS coefficients held in (padded) shared memory is a sequence of PASSES; a pass performs R <= 5
+// consecutive stages on 2^R coefficients held in registers (radix-2^R), so a 2^13-point transform is 3 passes (4 + 4 + 5 stages)
+// with 2 CTA barriers instead of 13.  The last forward pass (first inverse pass) works on 32 CONSECUTIVE coefficients per thread
+// and takes its 31 twiddles from a table transposed for coalesced access; polynomials that only feed such a pass can be kept in
+// global memory in the matching "TT" order (coefficient 32 P + k stored at k * N/32 + P).
+//
+// Arithmetic policies (the integer pipe is the bound, B200: IMAD 64 lanes/clk/SM, IMAD.WIDE 32):
+//   ArW   q < 2^62 : u64, Shoup multiplication with 64-bit companions, lazy forward butterflies (no conditional subtraction:
+//                    values grow by 2q per stage and fit 64 bits for q < 2^57; larger q fall back to Harvey's [0, 4q) form),
+//                    Harvey [0, 2q) inverse butterflies.                                  ~16 FMA-pipe slots per butterfly
+//   ArN30 q < 2^30 : u32, 32-bit Shoup, Harvey lazy butterflies in [0, 4q) / [0, 2q).      3 IMAD + 4 ALU per butterfly
+//   ArN31 q < 2^31 : u32, canonical butterflies (4q does not fit 32 bits).                 3 IMAD + 8 ALU per butterfly
+#pragma once
+#include "modarith.cuh"
+
+namespace sfg {
+
+enum ArithKind : int { kArW = 0, kArN30 = 1, kArN31 = 2 };
+__host__ __device__ inline int arith_kind(uint64_t q) { return q < (1ULL << 30) ? kArN30 : (q < (1ULL << 31) ? kArN31 : kArW); }
+
+// shared-memory index with one pad element per 32: conflict-free for unit-stride AND for the stride-32 last pass
+__device__ __forceinline__ int sidx(int i) { return i + (i >> 5); }
+__host__ __device__ inline size_t ntt_smem_elems(int S) { return (size_t)S + (S >> 5) + 1; }
+// "TT" global order of a polynomial of N coefficients
+__device__ __forceinline__ int tt_index(int idx, int N) { return (idx & 31) * (N >> 5) + (idx >> 5); }
+
+struct PassPlan {  // stage counts of the passes before the 5-stage last pass (forward order); sum + 5 == logS
+    int n;
+    int R[4];
+};
+inline PassPlan make_pass_plan(int nstages /* = logS - 5 >= 0 */) {
+    PassPlan p{0, {0, 0, 0, 0}};
+    const int np = (nstages + 4) / 5;
+    for (int i = 0; i < np; i++) p.R[i] = nstages / np + (i < nstages % np ? 1 : 0);
+    p.n = np;
+    return p;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// arithmetic policies
+// ---------------------------------------------------------------------------------------------------------------
+struct ArW {
+    using T = uint64_t;
+    using TW = ulonglong2;  // (w, floor(w 2^64 / q))
+    static constexpr int kKind = kArW;
+    struct C {
+        uint64_t q, q2, bred_hi, ninv, ninv_sh;
+        int big;  // q >= 2^57: keep forward values in [0, 4q)
+    };
+    __device__ static __forceinline__ C make(const LimbConst &lc) { return C{lc.q, 2 * lc.q, lc.bred_hi, lc.ninv, lc.ninv_sh, lc.q >= (1ULL << 57)}; }
+    __device__ static __forceinline__ T mul_lazy(T y, TW w, const C &c) { return y * w.x - __umul64hi(y, w.y) * c.q; }  // [0, 2q), any y
+    // any 64-bit value -> something the forward butterflies accept
+    __device__ static __forceinline__ T load_u64(uint64_t x, const C &c) { return c.big ? (x - __umul64hi(x, c.bred_hi) * c.q) : x; }
+    __device__ static __forceinline__ void fwd(T &x, T &y, TW w, const C &c) {
+        T x0 = x;
+        if (c.big) x0 = x0 >= c.q2 ? x0 - c.q2 : x0;
+        const T v = mul_lazy(y, w, c);
+        x = x0 + v;
+        y = x0 - v + c.q2;
+    }
+    __device__ static __forceinline__ void inv(T &x, T &y, TW w, const C &c) {  // in / out [0, 2q)
+        T u = x + y;
+        u = u >= c.q2 ? u - c.q2 : u;
+        const T d = x - y + c.q2;
+        y = mul_lazy(d, w, c);
+        x = u;
+    }
+    __device__ static __forceinline__ T canon(T x, const C &c) {  // any value -> [0, q)
+        const T r = x - __umul64hi(x, c.bred_hi) * c.q;
+        return r >= c.q ? r - c.q : r;
+    }
+    __device__ static __forceinline__ T inv_final(T x, const C &c) {  // x * N^-1 mod q, canonical
+        const T r = x * c.ninv - __umul64hi(x, c.ninv_sh) * c.q;
+        return r >= c.q ? r - c.q : r;
+    }
+    __device__ static __forceinline__ T from_canon(uint64_t x, const C &) { return x; }  // residue of THIS modulus
+    __host__ static TW make_tw(uint64_t w, uint64_t q) { return make_ulonglong2(w, h_shoup(w, q)); }
+};
+
+struct ArN30 {
+    using T = uint32_t;
+    using TW = uint2;  // (w, floor(w 2^32 / q))
+    static constexpr int kKind = kArN30;
+    struct C {
+        uint32_t q, q2, ninv, ninv_sh;
+        uint64_t q64, bred_hi;
+    };
+    __device__ static __forceinline__ C make(const LimbConst &lc) {
+        return C{(uint32_t)lc.q, (uint32_t)(2 * lc.q), (uint32_t)lc.ninv, (uint32_t)(lc.ninv_sh >> 32), lc.q, lc.bred_hi};
+    }
+    __device__ static __forceinline__ T mul_lazy(T y, TW w, const C &c) { return y * w.x - __umulhi(y, w.y) * c.q; }  // [0, 2q), any y
+    __device__ static __forceinline__ T load_u64(uint64_t x, const C &c) {  // any 64-bit value -> [0, 4q)
+        return x < 4 * c.q64 ? (uint32_t)x : (uint32_t)(x - __umul64hi(x, c.bred_hi) * c.q64);  // BRedAdd without the final subtraction
+    }
+    __device__ static __forceinline__ void fwd(T &x, T &y, TW w, const C &c) {  // in / out [0, 4q)
+        const T x0 = min(x, x - c.q2);
+        const T v = mul_lazy(y, w, c);
+        x = x0 + v;
+        y = x0 - v + c.q2;
+    }
+    __device__ static __forceinline__ void inv(T &x, T &y, TW w, const C &c) {  // in / out [0, 2q)
+        T u = x + y;
+        u = min(u, u - c.q2);
+        const T d = x - y + c.q2;
+        y = mul_lazy(d, w, c);
+        x = u;
+    }
+    __device__ static __forceinline__ T canon(T x, const C &c) {  // [0, 4q) -> [0, q)
+        x = min(x, x - c.q2);
+        return min(x, x - c.q);
+    }
+    __device__ static __forceinline__ T inv_final(T x, const C &c) {
+        const T r = x * c.ninv - __umulhi(x, c.ninv_sh) * c.q;
+        return min(r, r - c.q);
+    }
+    __device__ static __forceinline__ T from_canon(uint64_t x, const C &) { return (uint32_t)x; }
+    __host__ static TW make_tw(uint64_t w, uint64_t q) { return make_uint2((uint32_t)w, (uint32_t)((w << 32) / q)); }
+};
+
+struct ArN31 {
+    using T = uint32_t;
+    using TW = uint2;
+    static constexpr int kKind = kArN31;
+    using C = ArN30::C;
+    __device__ static __forceinline__ C make(const LimbConst &lc) { return ArN30::make(lc); }
+    __device__ static __forceinline__ T mul_lazy(T y, TW w, const C &c) { return y * w.x - __umulhi(y, w.y) * c.q; }
+    __device__ static __forceinline__ T mul_canon(T y, TW w, const C &c) {
+        const T r = mul_lazy(y, w, c);
+        return min(r, r - c.q);
+    }
+    __device__ static __forceinline__ T load_u64(uint64_t x, const C &c) {  // -> [0, q)
+        const uint32_t r = (uint32_t)(x - __umul64hi(x, c.bred_hi) * c.q64);  // [0, 2q)
+        return min(r, r - c.q);
+    }
+    __device__ static __forceinline__ void fwd(T &x, T &y, TW w, const C &c) {  // canonical in / out
+        const T v = mul_canon(y, w, c);
+        const T s = x + v, d = x - v;
+        x = min(s, s - c.q);
+        y = min(d, d + c.q);
+    }
+    __device__ static __forceinline__ void inv(T &x, T &y, TW w, const C &c) {
+        const T s = x + y;
+        T d = x - y;
+        d = min(d, d + c.q);
+        x = min(s, s - c.q);
+        y = mul_canon(d, w, c);
+    }
+    __device__ static __forceinline__ T canon(T x, const C &) { return x; }
+    __device__ static __forceinline__ T inv_final(T x, const C &c) {
+        const T r = x * c.ninv - __umulhi(x, c.ninv_sh) * c.q;
+        return min(r, r - c.q);
+    }
+    __device__ static __forceinline__ T from_canon(uint64_t x, const C &) { return (uint32_t)x; }
+    __host__ static TW make_tw(uint64_t w, uint64_t q) { return ArN30::make_tw(w, q); }
+};
+
+// Twiddle tables of one modulus (device pointers, element type A::TW):
+//   fwd[m + i]  = NttPsi[m + i]           fwd_last[(2^r - 1 + g) * N/32 + P] = NttPsi[2^(logN-5+r) + (P << r) + g]
+//   inv / inv_last: the same for NttPsiInv
+struct TwTab {
+    const void *fwd, *fwd_last, *inv, *inv_last;
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// passes.  A transform works on the slice `sl` (2^logS consecutive coefficients) of a 2^logN ring; local index j is global
+// index (sl << logS) + j.  ld(j) / st(j, v) move one coefficient (registers <-> wherever the caller keeps it).
+// ---------------------------------------------------------------------------------------------------------------
+template <class A, int R, bool LAST, class LD, class ST>
+__device__ __forceinline__ void fwd_pass(int s0, int logN, int logS, int sl, const typename A::TW *__restrict__ tw,
+                                         const typename A::C &c, LD ld, ST st) {
+    using T = typename A::T;
+    using TW = typename A::TW;
+    constexpr int E = 1 << R;
+    const int lobits = LAST ? 0 : logN - s0 - R;
+    const int nsub = 1 << (logS - R);
+    for (int p = threadIdx.x; p < nsub; p += blockDim.x) {
+        const int hl = p >> lobits, lo = p & ((1 << lobits) - 1);
+        const int base = (hl << (lobits + R)) | lo;
+        const int hi = ((sl << logS) | base) >> (lobits + R);  // global group index at stage s0
+        T v[E];
+#pragma unroll
+        for (int k = 0; k < E; k++) v[k] = ld(base + (k << lobits));
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const int half = E >> (r + 1);
+#pragma unroll
+            for (int g = 0; g < (1 << r); g++) {
+                TW w;
+                if (LAST) w = __ldg(tw + (size_t)((1 << r) - 1 + g) * (size_t)(1 << (logN - 5)) + hi);
+                else w = __ldg(tw + (1 << (s0 + r)) + (hi << r) + g);
+#pragma unroll
+                for (int j = 0; j < half; j++) A::fwd(v[g * 2 * half + j], v[g * 2 * half + j + half], w, c);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < E; k++) st(base + (k << lobits), v[k]);
+    }
+}
+
+template <class A, int R, bool LAST, class LD, class ST>
+__device__ __forceinline__ void inv_pass(int s0, int logN, int logS, int sl, const typename A::TW *__restrict__ tw,
+                                         const typename A::C &c, LD ld, ST st) {
+    using T = typename A::T;
+    using TW = typename A::TW;
+    constexpr int E = 1 << R;
+    const int lobits = LAST ? 0 : logN - s0 - R;
+    const int nsub = 1 << (logS - R);
+    for (int p = threadIdx.x; p < nsub; p += blockDim.x) {
+        const int hl = p >> lobits, lo = p & ((1 << lobits) - 1);
+        const int base = (hl << (lobits + R)) | lo;
+        const int hi = ((sl << logS) | base) >> (lobits + R);
+        T v[E];
+#pragma unroll
+        for (int k = 0; k < E; k++) v[k] = ld(base + (k << lobits));
+#pragma unroll
+        for (int r = R - 1; r >= 0; r--) {
+            const int half = E >> (r + 1);
+#pragma unroll
+            for (int g = 0; g < (1 << r); g++) {
+                TW w;
+                if (LAST) w = __ldg(tw + (size_t)((1 << r) - 1 + g) * (size_t)(1 << (logN - 5)) + hi);
+                else w = __ldg(tw + (1 << (s0 + r)) + (hi << r) + g);
+#pragma unroll
+                for (int j = 0; j < half; j++) A::inv(v[g * 2 * half + j], v[g * 2 * half + j + half], w, c);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < E; k++) st(base + (k << lobits), v[k]);
+    }
+}
+
+// run-time stage count -> compile-time radix
+template <class A, bool INV, class LD, class ST>
+__device__ __forceinline__ void mid_pass(int R, int s0, int logN, int logS, int sl, const typename A::TW *tw, const typename A::C &c, LD ld,
+                                         ST st) {
+    switch (R) {
+        case 1: INV ? inv_pass<A, 1, false>(s0, logN, logS, sl, tw, c, ld, st) : fwd_pass<A, 1, false>(s0, logN, logS, sl, tw, c, ld, st); break;
+        case 2: INV ? inv_pass<A, 2, false>(s0, logN, logS, sl, tw, c, ld, st) : fwd_pass<A, 2, false>(s0, logN, logS, sl, tw, c, ld, st); break;
+        case 3: INV ? inv_pass<A, 3, false>(s0, logN, logS, sl, tw, c, ld, st) : fwd_pass<A, 3, false>(s0, logN, logS, sl, tw, c, ld, st); break;
+        case 4: INV ? inv_pass<A, 4, false>(s0, logN, logS, sl, tw, c, ld, st) : fwd_pass<A, 4, false>(s0, logN, logS, sl, tw, c, ld, st); break;
+        default: INV ? inv_pass<A, 5, false>(s0, logN, logS, sl, tw, c, ld, st) : fwd_pass<A, 5, false>(s0, logN, logS, sl, tw, c, ld, st); break;
+    }
+}
+
+// Forward transform of slice `sl`.  ld0(j) supplies the input of local coefficient j in the policy's input range, AFTER the
+// first (logN - logS) stages when the ring is sliced (see slice_input()).  The passes before the last one go through the padded
+// shared-memory array `s`; the results of the last pass are handed to fin(j, value) -- 32 consecutive j per thread, lazy range.
+template <class A, class LD, class FIN>
+__device__ __forceinline__ void ntt_forward(typename A::T *s, int logN, int logS, int sl, const PassPlan &plan, const TwTab &tab,
+                                            const typename A::C &c, LD ld0, FIN fin) {
+    using T = typename A::T;
+    using TW = typename A::TW;
+    const TW *tw = reinterpret_cast<const TW *>(tab.fwd);
+    auto lds = [&](int j) { return s[sidx(j)]; };
+    auto sts = [&](int j, T v) { s[sidx(j)] = v; };
+    int s0 = logN - logS;
+    if (plan.n == 0) {
+        for (int j = threadIdx.x; j < (1 << logS); j += blockDim.x) sts(j, ld0(j));
+    }
+    for (int i = 0; i < plan.n; i++) {
+        if (i == 0) mid_pass<A, false>(plan.R[i], s0, logN, logS, sl, tw, c, ld0, sts);
+        else mid_pass<A, false>(plan.R[i], s0, logN, logS, sl, tw, c, lds, sts);
+        s0 += plan.R[i];
+        __syncthreads();
+    }
+    if (plan.n == 0) __syncthreads();
+    fwd_pass<A, 5, true>(s0, logN, logS, sl, reinterpret_cast<const TW *>(tab.fwd_last), c, lds, fin);
+}
+
+// Inverse transform of a whole ring (logS == logN).  ld_last(j) supplies the canonical input of coefficient j for the first
+// (stride-32) pass; fin(j, v) receives v = canonical coefficient j of the result (times N^-1), unit-stride across lanes.
+template <class A, class LD, class FIN>
+__device__ __forceinline__ void ntt_inverse(typename A::T *s, int logN, const PassPlan &plan, const TwTab &tab, const typename A::C &c,
+                                            LD ld_last, FIN fin) {
+    using T = typename A::T;
+    using TW = typename A::TW;
+    const TW *tw = reinterpret_cast<const TW *>(tab.inv);
+    auto lds = [&](int j) { return s[sidx(j)]; };
+    auto sts = [&](int j, T v) { s[sidx(j)] = v; };
+    int s0 = logN - 5;
+    inv_pass<A, 5, true>(s0, logN, logN, 0, reinterpret_cast<const TW *>(tab.inv_last), c, ld_last, sts);
+    __syncthreads();
+    for (int i = plan.n - 1; i >= 0; i--) {
+        s0 -= plan.R[i];
+        if (i == 0) {
+            auto fin2 = [&](int j, T v) { fin(j, A::inv_final(v, c)); };
+            mid_pass<A, true>(plan.R[i], s0, logN, logN, 0, tw, c, lds, fin2);
+        } else {
+            mid_pass<A, true>(plan.R[i], s0, logN, logN, 0, tw, c, lds, sts);
+            __syncthreads();
+        }
+    }
+    if (plan.n == 0) {
+        for (int j = threadIdx.x; j < (1 << logN); j += blockDim.x) fin(j, A::inv_final(lds(j), c));
+    }
+}
+
+}  // namespace sfg
