@@ -83,33 +83,33 @@ int ctx_build_tables(Ctx *c, const uint64_t *psi_opt) {
     // per-class tables of the register-tiled transforms (ntt2.cuh): [N] in Lattigo's order + the last-pass table in TT order
     if (logN <= 14) {
         std::vector<TwTab> tabs(nQP);
-        const int P = N >> 5, s0 = logN - 5;
+        const int P = N >> kLastR, s0 = logN - kLastR, NL = kLastE - 1;  // last-pass table: NL twiddles per group of 16
         for (int i = 0; i < nQP; i++) {
             const uint64_t q = c->mod[i];
             const uint64_t *w = &tw[(size_t)i * 4 * N], *wi = w + 2 * N;
             const bool wide = arith_kind(q) == kArW;
             const size_t es = wide ? sizeof(ulonglong2) : sizeof(uint2);
-            std::vector<unsigned char> h((size_t)(2 * N + 2 * 31 * P) * es);
+            std::vector<unsigned char> h((size_t)(2 * N + 2 * NL * P) * es);
             auto put = [&](size_t pos, uint64_t x) {
                 if (wide) reinterpret_cast<ulonglong2 *>(h.data())[pos] = ArW::make_tw(x, q);
                 else reinterpret_cast<uint2 *>(h.data())[pos] = ArN30::make_tw(x, q);
             };
             for (int j = 0; j < N; j++) {
                 put(j, w[j]);
-                put((size_t)N + 31 * P + j, wi[j]);
+                put((size_t)N + NL * P + j, wi[j]);
             }
-            for (int r = 0; r < 5; r++)
+            for (int r = 0; r < kLastR; r++)
                 for (int g = 0; g < (1 << r); g++)
                     for (int p = 0; p < P; p++) {
                         const size_t idx = ((size_t)1 << (s0 + r)) + ((size_t)p << r) + g;
                         put((size_t)N + (size_t)((1 << r) - 1 + g) * P + p, w[idx]);
-                        put((size_t)2 * N + 31 * P + (size_t)((1 << r) - 1 + g) * P + p, wi[idx]);
+                        put((size_t)2 * N + NL * P + (size_t)((1 << r) - 1 + g) * P + p, wi[idx]);
                     }
             unsigned char *d = nullptr;
             SFG_CUDA(c, cudaMalloc(&d, h.size()));
             SFG_CUDA(c, cudaMemcpy(d, h.data(), h.size(), cudaMemcpyHostToDevice));
             c->tw2_bufs.push_back(d);
-            tabs[i] = TwTab{d, d + (size_t)N * es, d + (size_t)(N + 31 * P) * es, d + (size_t)(2 * N + 31 * P) * es};
+            tabs[i] = TwTab{d, d + (size_t)N * es, d + (size_t)(N + NL * P) * es, d + (size_t)(2 * N + NL * P) * es};
         }
         SFG_CUDA(c, cudaMalloc(&c->tw2, sizeof(TwTab) * nQP));
         SFG_CUDA(c, cudaMemcpy(c->tw2, tabs.data(), sizeof(TwTab) * nQP, cudaMemcpyHostToDevice));

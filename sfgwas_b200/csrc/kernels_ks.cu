@@ -69,20 +69,22 @@ int launch_key_convert(Ctx *c, const uint64_t *in, uint64_t *out, cudaStream_t s
 }
 
 // ---- 2. inner products with the switching key ---------------------------------------------------------------------------
-template <class A, int CS>
-__global__ void __launch_bounds__(256, A::kKind == kArW ? 1 : 2)
+// One CTA per (ciphertext, target modulus [, slice]); thread p owns the 16 consecutive NTT-domain coefficients 16p .. 16p+15 of
+// both accumulators in REGISTERS for the whole digit loop (the last forward pass delivers exactly those).  A1: nP == 1 (every
+// digit is a single modulus: plain reduction of the representative, Lattigo DecomposeAndSplit).
+template <class A, int CS, bool A1>
+__global__ void __launch_bounds__(512, 1)
 k_ks_inner2(const uint64_t *__restrict__ in, const long long *__restrict__ in_off, int in_nl, const uint64_t *__restrict__ c2,
-            const int *__restrict__ c2_slot,
-            const uint64_t *const *__restrict__ keys, const BaseConv *__restrict__ ks, int level, int nQ, int nP, int logN, PassPlan plan,
-            const TwTab *__restrict__ tabs, const LimbConst *__restrict__ lcs, uint64_t *__restrict__ accout, TgtSel sel) {
+            const int *__restrict__ c2_slot, const uint64_t *const *__restrict__ keys, const BaseConv *__restrict__ ks, int level, int nQ,
+            int nP, int logN, PassPlan plan, const TwTab *__restrict__ tabs, const LimbConst *__restrict__ lcs, uint64_t *__restrict__ accout,
+            TgtSel sel) {
     using T = typename A::T;
     extern __shared__ __align__(16) unsigned char smraw[];
     const int N = 1 << logN, logS = logN - CS, S = 1 << logS, nl = level + 1, nt = nl + nP, nQP = nQ + nP;
     const int alpha = nP, beta = (nl + alpha - 1) / alpha;
     const int sl = blockIdx.x & ((1 << CS) - 1), tt = sel.tt[blockIdx.x >> CS], ct = blockIdx.y;
     const int tgt = tt < nl ? tt : nQ + (tt - nl);
-    const size_t SE = ntt_smem_elems(S);
-    T *s = reinterpret_cast<T *>(smraw), *a0 = s + SE, *a1 = a0 + SE;
+    T *s = reinterpret_cast<T *>(smraw);
     const LimbConst lc = lcs[tgt];
     const typename A::C c = A::make(lc);
     const TwTab tab = tabs[tgt];
@@ -90,52 +92,66 @@ k_ks_inner2(const uint64_t *__restrict__ in, const long long *__restrict__ in_of
     const uint64_t *c2ct = c2 + (size_t)c2_slot[ct] * nl * N;  // its INTT, coefficient domain
     const uint64_t *key = keys[ct];
     const int gbase = sl << logS;                               // global index of local coefficient 0
+    const int P = (gbase >> kLastR) + threadIdx.x;              // global index of this thread's group of 16
+    const bool active = threadIdx.x < (S >> kLastR);
+    const int NP = N >> kLastR;
+
+    // accumulators: registers for the 32-bit classes; thread-private shared-memory slots for the 64-bit class (register budget)
+    constexpr bool ACC_SMEM = A::kKind == kArW;
+    constexpr int NREG = ACC_SMEM ? 1 : kLastE;
+    T a0[NREG], a1[NREG];
+    T *s0a = s + S, *s1a = s0a + S;
+    const int abase = kLastE * threadIdx.x;
+#pragma unroll
+    for (int k = 0; k < kLastE; k++) {
+        if constexpr (ACC_SMEM) {
+            if (active) s0a[sidx<sizeof(T)>(abase + k)] = s1a[sidx<sizeof(T)>(abase + k)] = 0;
+        } else {
+            a0[k] = a1[k] = 0;
+        }
+    }
 
     for (int i = 0; i < beta; i++) {
         const BaseConv &bc = ks[(size_t)i * nt + tt];
-        const uint64_t *k0 = key + ((size_t)(i * 2 + 0) * nQP + tgt) * N;
-        const uint64_t *k1 = key + ((size_t)(i * 2 + 1) * nQP + tgt) * N;
-        const bool first = i == 0;
-        // multiply coefficient j (local) with the two key polynomials and accumulate (thread-private shared-memory slots)
-        auto mac = [&](int j, T v) {
-            const int kpos = tt_index(gbase + j, N), sj = sidx(j);
-            if constexpr (A::kKind == kArW) {
-                const uint64_t p0 = mred(v, __ldg(k0 + kpos), lc), p1 = mred(v, __ldg(k1 + kpos), lc);
-                a0[sj] = first ? p0 : add_mod(a0[sj], p0, lc.q);
-                a1[sj] = first ? p1 : add_mod(a1[sj], p1, lc.q);
+        const uint64_t *k0 = key + ((size_t)(i * 2 + 0) * nQP + tgt) * N + P;
+        const uint64_t *k1 = key + ((size_t)(i * 2 + 1) * nQP + tgt) * N + P;
+        // multiply coefficient 16 P + k with the two key polynomials (TT order: unit stride across lanes) and accumulate
+        auto mac = [&](int, T v, int k) {
+            if constexpr (ACC_SMEM) {
+                const int sj = sidx<sizeof(T)>(abase + k);
+                s0a[sj] = add_mod(s0a[sj], mred(v, __ldg(k0 + (size_t)k * NP), lc), lc.q);
+                s1a[sj] = add_mod(s1a[sj], mred(v, __ldg(k1 + (size_t)k * NP), lc), lc.q);
             } else {
-                const uint2 w0 = __ldg(reinterpret_cast<const uint2 *>(k0) + kpos), w1 = __ldg(reinterpret_cast<const uint2 *>(k1) + kpos);
+                const uint2 w0 = __ldg(reinterpret_cast<const uint2 *>(k0) + (size_t)k * NP);
+                const uint2 w1 = __ldg(reinterpret_cast<const uint2 *>(k1) + (size_t)k * NP);
                 uint32_t p0 = A::mul_lazy(v, w0, c), p1 = A::mul_lazy(v, w1, c);
-                p0 = min(p0, p0 - c.q);
-                p1 = min(p1, p1 - c.q);
-                if (!first) {
-                    p0 += a0[sj];
-                    p1 += a1[sj];
-                    p0 = min(p0, p0 - c.q);
-                    p1 = min(p1, p1 - c.q);
-                }
-                a0[sj] = p0;
-                a1[sj] = p1;
+                p0 = min(p0, p0 - c.q) + a0[k];
+                p1 = min(p1, p1 - c.q) + a1[k];
+                a0[k] = min(p0, p0 - c.q);
+                a1[k] = min(p1, p1 - c.q);
             }
         };
         const int ns = bc.ns;
         if (ns == 0) {  // target lies inside the digit: reuse the NTT-domain input limb (decomposeAndSplitNTT)
             const uint64_t *x = c1 + (size_t)tt * N + gbase;
-            for (int j = threadIdx.x; j < S; j += blockDim.x) s[sidx(j)] = A::from_canon(x[j], c);
+            for (int j = threadIdx.x; j < S; j += blockDim.x) s[sidx<sizeof(T)>(j)] = A::from_canon(x[j], c);
             __syncthreads();
-            for (int p = threadIdx.x; p < (S >> 5); p += blockDim.x) {
-#pragma unroll 8
-                for (int k = 0; k < 32; k++) mac(32 * p + k, s[sidx(32 * p + k)]);
+            if (active) {
+#pragma unroll
+                for (int k = 0; k < kLastE; k++) mac(0, s[sidx<sizeof(T)>(kLastE * threadIdx.x + k)], k);
             }
         } else {
             // coefficient-domain value of global coefficient g of this digit, reduced / base-converted to the target modulus
             auto digit = [&](int g) -> T {
-                if (ns == 1) return A::load_u64(c2ct[(size_t)bc.src_limb[0] * N + g], c);  // DecomposeAndSplit, single modulus
-                uint64_t xs[kMaxAlpha];
-                for (int j = 0; j < ns; j++) xs[j] = c2ct[(size_t)bc.src_limb[j] * N + g];
-                return A::load_u64(base_conv_coeff(bc, xs, lcs, lc.q), c);
+                if constexpr (A1) {
+                    return A::load_u64(c2ct[(size_t)bc.src_limb[0] * N + g], c);  // DecomposeAndSplit, single modulus
+                } else {
+                    uint64_t xs[kMaxAlpha];
+                    for (int j = 0; j < ns; j++) xs[j] = c2ct[(size_t)bc.src_limb[j] * N + g];
+                    return A::load_u64(base_conv_coeff(bc, xs, lcs, lc.q), c);
+                }
             };
-            auto ld0 = [&](int j) -> T {
+            auto ld0 = [&](int j, int) -> T {
                 if constexpr (CS == 0) {
                     return digit(j);
                 } else {  // the ring is cut into 2 slices: stage 0 is evaluated by both CTAs, each keeps its half
@@ -148,20 +164,24 @@ k_ks_inner2(const uint64_t *__restrict__ in, const long long *__restrict__ in_of
         }
         __syncthreads();
     }
-    uint64_t *o0 = accout + ((size_t)(ct * 2 + 0) * nt + tt) * N;
-    uint64_t *o1 = accout + ((size_t)(ct * 2 + 1) * nt + tt) * N;
-    for (int p = threadIdx.x; p < (S >> 5); p += blockDim.x) {
-#pragma unroll 8
-        for (int k = 0; k < 32; k++) {
-            const int j = 32 * p + k, kpos = tt_index(gbase + j, N);
-            o0[kpos] = a0[sidx(j)];
-            o1[kpos] = a1[sidx(j)];
+    if (active) {
+        uint64_t *o0 = accout + ((size_t)(ct * 2 + 0) * nt + tt) * N + P;
+        uint64_t *o1 = accout + ((size_t)(ct * 2 + 1) * nt + tt) * N + P;
+#pragma unroll
+        for (int k = 0; k < kLastE; k++) {
+            if constexpr (ACC_SMEM) {
+                o0[(size_t)k * NP] = s0a[sidx<sizeof(T)>(abase + k)];
+                o1[(size_t)k * NP] = s1a[sidx<sizeof(T)>(abase + k)];
+            } else {
+                o0[(size_t)k * NP] = a0[k];
+                o1[(size_t)k * NP] = a1[k];
+            }
         }
     }
 }
 
 // ---- 4. mod-down, + c0, automorphism, store / accumulate ---------------------------------------------------------------------
-template <class A>
+template <class A, bool A1>
 __global__ void __launch_bounds__(512, 1)
 k_ks_moddown2(const uint64_t *__restrict__ in, const long long *__restrict__ in_off, int in_nl, const uint64_t *__restrict__ acc,
               const BaseConv *__restrict__ md, const uint64_t *__restrict__ pinv, const uint32_t *const *__restrict__ perms, int level,
@@ -181,36 +201,42 @@ k_ks_moddown2(const uint64_t *__restrict__ in, const long long *__restrict__ in_
     const uint64_t pi = pinv[2 * l], pish = pinv[2 * l + 1];
     const uint32_t *perm = perms[ct];
 
-    auto ld0 = [&](int j) -> T {
-        if (nP == 1) return A::load_u64(accP[j], c);
-        uint64_t xs[kMaxAlpha];
-        for (int k = 0; k < nP; k++) xs[k] = accP[(size_t)k * N + j];
-        return A::load_u64(base_conv_coeff(bc, xs, lcs, lc.q), c);
+    auto ld0 = [&](int j, int) -> T {
+        if constexpr (A1) {
+            return A::load_u64(accP[j], c);
+        } else {
+            uint64_t xs[kMaxAlpha];
+            for (int k = 0; k < nP; k++) xs[k] = accP[(size_t)k * N + j];
+            return A::load_u64(base_conv_coeff(bc, xs, lcs, lc.q), c);
+        }
     };
-    auto fin = [&](int j, T v) {
+    auto fin = [&](int j, T v, int) {
         const uint64_t e = A::canon(v, c);
         const uint64_t r = mul_shoup(sub_mod(accQ[tt_index(j, N)], e, lc.q), pi, pish, lc.q);
-        s[sidx(j)] = (T)r;
+        s[sidx<sizeof(T)>(j)] = (T)r;
     };
     ntt_forward<A>(s, logN, logN, 0, plan, tab, c, ld0, fin);
     __syncthreads();
     if (comp == 0) {
         const uint64_t *c0 = in + in_off[ct] + (size_t)l * N;
-        for (int j = threadIdx.x; j < N; j += blockDim.x) s[sidx(j)] = (T)add_mod((uint64_t)s[sidx(j)], c0[j], lc.q);
+        for (int j = threadIdx.x; j < N; j += blockDim.x) {
+            const int sj = sidx<sizeof(T)>(j);
+            s[sj] = (T)add_mod((uint64_t)s[sj], c0[j], lc.q);
+        }
         __syncthreads();
     }
     unsigned char *ob = out + out_off[ct] + (size_t)comp * olay.bytes + olay.off[l];
     if (olay.es[l] == 4) {
         uint32_t *o = reinterpret_cast<uint32_t *>(ob);
         for (int k = threadIdx.x; k < N; k += blockDim.x) {
-            uint64_t v = s[sidx(perm[k])];  // PermuteNTTWithIndexLvl: out[k] = in[index[k]]
+            uint64_t v = s[sidx<sizeof(T)>(perm[k])];  // PermuteNTTWithIndexLvl: out[k] = in[index[k]]
             if (accumulate) v = add_mod(v, (uint64_t)o[k], lc.q);
             o[k] = (uint32_t)v;
         }
     } else {
         uint64_t *o = reinterpret_cast<uint64_t *>(ob);
         for (int k = threadIdx.x; k < N; k += blockDim.x) {
-            uint64_t v = s[sidx(perm[k])];
+            uint64_t v = s[sidx<sizeof(T)>(perm[k])];
             if (accumulate) v = add_mod(v, o[k], lc.q);
             o[k] = v;
         }
@@ -241,41 +267,44 @@ int launch_copy_add(Ctx *c, const KsBatch &b, cudaStream_t st) {
     return 0;
 }
 
-static int ntt_threads(int S) { return std::min(256, std::max(32, S >> 5)); }
+static int ntt_threads(int S) { return std::min(512, std::max(32, S >> kLastR)); }
 
-template <class A>
-static int inner_launch(Ctx *c, const KsBatch &b, BaseConv *ks, const TgtSel &sel, cudaStream_t st) {
-    if (sel.n == 0) return 0;
-    const int logN = c->logN, cs = logN > 13 ? 1 : 0, logS = logN - cs, S = 1 << logS;
-    const PassPlan plan = make_pass_plan(logS - 5);
-    const size_t smem = 3 * ntt_smem_elems(S) * sizeof(typename A::T);
-    dim3 g(sel.n << cs, b.nct);
-    if (cs == 0) {
-        SFG_CUDA(c, cudaFuncSetAttribute(k_ks_inner2<A, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_ks_inner2<A, 0><<<g, ntt_threads(S), smem, st>>>(b.in, b.in_off, b.in_nl, b.c2, b.c2_slot, b.keys, ks, b.level, c->nQ, c->nP, logN, plan, c->tw2, c->lc,
-                                                          b.acc, sel);
-    } else {
-        SFG_CUDA(c, cudaFuncSetAttribute(k_ks_inner2<A, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_ks_inner2<A, 1><<<g, ntt_threads(S), smem, st>>>(b.in, b.in_off, b.in_nl, b.c2, b.c2_slot, b.keys, ks, b.level, c->nQ, c->nP, logN, plan, c->tw2, c->lc,
-                                                          b.acc, sel);
-    }
+template <class A, int CS, bool A1>
+static int inner_launch2(Ctx *c, const KsBatch &b, BaseConv *ks, const TgtSel &sel, cudaStream_t st) {
+    const int logN = c->logN, logS = logN - CS, S = 1 << logS;
+    const PassPlan plan = make_pass_plan(logS - kLastR);
+    const size_t smem = (A::kKind == kArW ? 3 : 1) * ntt_smem_elems(S) * sizeof(typename A::T);
+    dim3 g(sel.n << CS, b.nct);
+    SFG_CUDA(c, cudaFuncSetAttribute(k_ks_inner2<A, CS, A1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_ks_inner2<A, CS, A1><<<g, ntt_threads(S), smem, st>>>(b.in, b.in_off, b.in_nl, b.c2, b.c2_slot, b.keys, ks, b.level, c->nQ, c->nP, logN, plan,
+                                                            c->tw2, c->lc, b.acc, sel);
     SFG_LAUNCHED(c, "k_ks_inner2", st);
     return 0;
 }
+template <class A>
+static int inner_launch(Ctx *c, const KsBatch &b, BaseConv *ks, const TgtSel &sel, cudaStream_t st) {
+    if (sel.n == 0) return 0;
+    const bool a1 = c->nP == 1;
+    if (c->logN > 13) return a1 ? inner_launch2<A, 1, true>(c, b, ks, sel, st) : inner_launch2<A, 1, false>(c, b, ks, sel, st);
+    return a1 ? inner_launch2<A, 0, true>(c, b, ks, sel, st) : inner_launch2<A, 0, false>(c, b, ks, sel, st);
+}
 
+template <class A, bool A1>
+static int moddown_launch2(Ctx *c, const KsBatch &b, BaseConv *md, uint64_t *pinv, const TgtSel &sel, cudaStream_t st) {
+    const int logN = c->logN, N = c->N;
+    const PassPlan plan = make_pass_plan(logN - kLastR);
+    const size_t smem = ntt_smem_elems(N) * sizeof(typename A::T);
+    SFG_CUDA(c, cudaFuncSetAttribute(k_ks_moddown2<A, A1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 g(sel.n, 2, b.nct);
+    k_ks_moddown2<A, A1><<<g, ntt_threads(N), smem, st>>>(b.in, b.in_off, b.in_nl, b.acc, md, pinv, b.perms, b.level, c->nQ, c->nP, logN, plan, c->tw2,
+                                                          c->lc, (unsigned char *)b.out, b.out_off, b.out_layout, b.accumulate ? 1 : 0, sel);
+    SFG_LAUNCHED(c, "k_ks_moddown2", st);
+    return 0;
+}
 template <class A>
 static int moddown_launch(Ctx *c, const KsBatch &b, BaseConv *md, uint64_t *pinv, const TgtSel &sel, cudaStream_t st) {
     if (sel.n == 0) return 0;
-    const int logN = c->logN, N = c->N;
-    const PassPlan plan = make_pass_plan(logN - 5);
-    const size_t smem = ntt_smem_elems(N) * sizeof(typename A::T);
-    SFG_CUDA(c, cudaFuncSetAttribute(k_ks_moddown2<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 g(sel.n, 2, b.nct);
-    k_ks_moddown2<A><<<g, std::min(512, std::max(32, N >> 5)), smem, st>>>(b.in, b.in_off, b.in_nl, b.acc, md, pinv, b.perms, b.level, c->nQ, c->nP, logN,
-                                                                           plan, c->tw2, c->lc, (unsigned char *)b.out, b.out_off, b.out_layout,
-                                                                           b.accumulate ? 1 : 0, sel);
-    SFG_LAUNCHED(c, "k_ks_moddown2", st);
-    return 0;
+    return c->nP == 1 ? moddown_launch2<A, true>(c, b, md, pinv, sel, st) : moddown_launch2<A, false>(c, b, md, pinv, sel, st);
 }
 
 static int rotate_chunk(Ctx *c, const KsBatch &b, BaseConv *ks, BaseConv *md, uint64_t *pinv, cudaStream_t st) {

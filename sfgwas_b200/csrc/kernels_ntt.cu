@@ -91,10 +91,10 @@ k_ntt2_fwd(const uint64_t *__restrict__ src, const long long *__restrict__ src_o
     const uint64_t *in = src + (src_off ? (size_t)src_off[g] : (size_t)g * src_gstride) + (size_t)k * N;
     uint64_t *out = dst + (size_t)g * dst_gstride + (size_t)k * N;
     const typename A::C c = A::make(lcs[limb]);
-    ntt_forward<A>(s, logN, logN, 0, plan, tabs[limb], c, [&](int j) { return A::from_canon(in[j], c); },
-                   [&](int j, T v) { s[sidx(j)] = A::canon(v, c); });
+    ntt_forward<A>(s, logN, logN, 0, plan, tabs[limb], c, [&](int j, int) { return A::from_canon(in[j], c); },
+                   [&](int j, T v, int) { s[sidx<sizeof(T)>(j)] = A::canon(v, c); });
     __syncthreads();
-    for (int j = threadIdx.x; j < N; j += blockDim.x) out[j] = s[sidx(j)];
+    for (int j = threadIdx.x; j < N; j += blockDim.x) out[j] = s[sidx<sizeof(T)>(j)];
 }
 
 template <class A>
@@ -108,13 +108,13 @@ k_ntt2_inv(const uint64_t *__restrict__ src, const long long *__restrict__ src_o
     const uint64_t *in = src + (src_off ? (size_t)src_off[g] : (size_t)g * src_gstride) + (size_t)k * N;
     uint64_t *out = dst + (size_t)g * dst_gstride + (size_t)k * N;
     const typename A::C c = A::make(lcs[limb]);
-    auto fin = [&](int j, T v) { out[j] = v; };
+    auto fin = [&](int j, T v, int) { out[j] = v; };
     if (in_tt) {
-        ntt_inverse<A>(s, logN, plan, tabs[limb], c, [&](int j) { return A::from_canon(in[tt_index(j, N)], c); }, fin);
+        ntt_inverse<A>(s, logN, plan, tabs[limb], c, [&](int j, int) { return A::from_canon(in[tt_index(j, N)], c); }, fin);
     } else {
-        for (int j = threadIdx.x; j < N; j += blockDim.x) s[sidx(j)] = A::from_canon(in[j], c);
+        for (int j = threadIdx.x; j < N; j += blockDim.x) s[sidx<sizeof(T)>(j)] = A::from_canon(in[j], c);
         __syncthreads();
-        ntt_inverse<A>(s, logN, plan, tabs[limb], c, [&](int j) { return s[sidx(j)]; }, fin);
+        ntt_inverse<A>(s, logN, plan, tabs[limb], c, [&](int j, int) { return s[sidx<sizeof(T)>(j)]; }, fin);
     }
 }
 
@@ -123,9 +123,9 @@ static int ntt2_launch(Ctx *c, const uint64_t *src, const long long *src_off, si
                        const SubSel &sub, bool inverse, bool in_tt, cudaStream_t st) {
     if (sub.n == 0 || ngroups == 0) return 0;
     const int logN = c->logN, N = c->N;
-    const PassPlan plan = make_pass_plan(logN - 5);
+    const PassPlan plan = make_pass_plan(logN - kLastR);
     const size_t smem = ntt_smem_elems(N) * sizeof(typename A::T);
-    const int threads = std::min(512, std::max(32, N >> 5));
+    const int threads = std::min(512, std::max(32, N >> kLastR));
     if (inverse) {
         SFG_CUDA(c, cudaFuncSetAttribute(k_ntt2_inv<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_ntt2_inv<A><<<ngroups * sub.n, threads, smem, st>>>(src, src_off, sgs, dst, dgs, sub, logN, plan, c->tw2, c->lc, in_tt ? 1 : 0);

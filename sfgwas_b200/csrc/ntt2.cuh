@@ -4,11 +4,11 @@
 // bit-reversed evaluation order a(psi^(2 brv(i)+1)), inverse Gentleman-Sande times N^-1; stage `s` has m = 2^s groups and uses
 // twiddle NttPsi[m + i] (NttPsiInv[m + i]).  Outputs are canonical, so any exact evaluation order is bit-identical.
 //
-// Organisation: a transform of 2^logS coefficients held in (padded) shared memory is a sequence of PASSES; a pass performs R <= 5
-// consecutive stages on 2^R coefficients held in registers (radix-2^R), so a 2^13-point transform is 3 passes (4 + 4 + 5 stages)
-// with 2 CTA barriers instead of 13.  The last forward pass (first inverse pass) works on 32 CONSECUTIVE coefficients per thread
-// and takes its 31 twiddles from a table transposed for coalesced access; polynomials that only feed such a pass can be kept in
-// global memory in the matching "TT" order (coefficient 32 P + k stored at k * N/32 + P).
+// Organisation: a transform of 2^logS coefficients held in (padded) shared memory is a sequence of PASSES; a pass performs R <= 4
+// consecutive stages on 2^R coefficients held in registers (radix-2^R), so a 2^13-point transform is 4 passes (3 + 3 + 3 + 4 stages)
+// with 3 CTA barriers instead of 13.  The last forward pass (first inverse pass) works on 16 CONSECUTIVE coefficients per thread
+// and takes its 15 twiddles from a table transposed for coalesced access; polynomials that only feed such a pass can be kept in
+// global memory in the matching "TT" order (coefficient 16 P + k stored at k * N/16 + P).
 //
 // Arithmetic policies (the integer pipe is the bound, B200: IMAD 64 lanes/clk/SM, IMAD.WIDE 32):
 //   ArW   q < 2^62 : u64, Shoup multiplication with 64-bit companions, lazy forward butterflies (no conditional subtraction:
@@ -24,19 +24,28 @@ namespace sfg {
 enum ArithKind : int { kArW = 0, kArN30 = 1, kArN31 = 2 };
 __host__ __device__ inline int arith_kind(uint64_t q) { return q < (1ULL << 30) ? kArN30 : (q < (1ULL << 31) ? kArN31 : kArW); }
 
-// shared-memory index with one pad element per 32: conflict-free for unit-stride AND for the stride-32 last pass
-__device__ __forceinline__ int sidx(int i) { return i + (i >> 5); }
-__host__ __device__ inline size_t ntt_smem_elems(int S) { return (size_t)S + (S >> 5) + 1; }
-// "TT" global order of a polynomial of N coefficients
-__device__ __forceinline__ int tt_index(int idx, int N) { return (idx & 31) * (N >> 5) + (idx >> 5); }
+// Stages per pass: at most kLastR = 4 (16 coefficients in registers per thread).
+constexpr int kLastR = 4;
+constexpr int kLastE = 1 << kLastR;
 
-struct PassPlan {  // stage counts of the passes before the 5-stage last pass (forward order); sum + 5 == logS
+// XOR-swizzled shared-memory index (no padding).  The three access patterns of the passes are conflict-free:
+//   unit stride across lanes (lobits >= 5), 16 lanes x 2 groups (the pass with lobits == 4), and stride 16 (last pass).
+template <int BYTES>
+__device__ __forceinline__ int sidx(int i) {
+    if (BYTES == 8) return i ^ ((i >> 4) & 15);
+    return i ^ (((i >> 5) & 15) | ((__popc((i >> 5) & 15) & 1) << 4));
+}
+__host__ __device__ inline size_t ntt_smem_elems(int S) { return (size_t)S; }
+// "TT" global order of a polynomial of N coefficients: coefficient 16 P + k stored at k * N/16 + P
+__device__ __forceinline__ int tt_index(int idx, int N) { return (idx & (kLastE - 1)) * (N >> kLastR) + (idx >> kLastR); }
+
+struct PassPlan {  // stage counts of the passes before the last pass (forward order); sum + kLastR == logS
     int n;
     int R[4];
 };
-inline PassPlan make_pass_plan(int nstages /* = logS - 5 >= 0 */) {
+inline PassPlan make_pass_plan(int nstages /* = logS - kLastR >= 0 */) {
     PassPlan p{0, {0, 0, 0, 0}};
-    const int np = (nstages + 4) / 5;
+    const int np = (nstages + kLastR - 1) / kLastR;
     for (int i = 0; i < np; i++) p.R[i] = nstages / np + (i < nstages % np ? 1 : 0);
     p.n = np;
     return p;
@@ -161,7 +170,7 @@ struct ArN31 {
 };
 
 // Twiddle tables of one modulus (device pointers, element type A::TW):
-//   fwd[m + i]  = NttPsi[m + i]           fwd_last[(2^r - 1 + g) * N/32 + P] = NttPsi[2^(logN-5+r) + (P << r) + g]
+//   fwd[m + i]  = NttPsi[m + i]           fwd_last[(2^r - 1 + g) * N/16 + P] = NttPsi[2^(logN-4+r) + (P << r) + g]
 //   inv / inv_last: the same for NttPsiInv
 struct TwTab {
     const void *fwd, *fwd_last, *inv, *inv_last;
@@ -185,21 +194,21 @@ __device__ __forceinline__ void fwd_pass(int s0, int logN, int logS, int sl, con
         const int hi = ((sl << logS) | base) >> (lobits + R);  // global group index at stage s0
         T v[E];
 #pragma unroll
-        for (int k = 0; k < E; k++) v[k] = ld(base + (k << lobits));
+        for (int k = 0; k < E; k++) v[k] = ld(base + (k << lobits), k);
 #pragma unroll
         for (int r = 0; r < R; r++) {
             const int half = E >> (r + 1);
 #pragma unroll
             for (int g = 0; g < (1 << r); g++) {
                 TW w;
-                if (LAST) w = __ldg(tw + (size_t)((1 << r) - 1 + g) * (size_t)(1 << (logN - 5)) + hi);
+                if (LAST) w = __ldg(tw + (size_t)((1 << r) - 1 + g) * (size_t)(1 << (logN - kLastR)) + hi);
                 else w = __ldg(tw + (1 << (s0 + r)) + (hi << r) + g);
 #pragma unroll
                 for (int j = 0; j < half; j++) A::fwd(v[g * 2 * half + j], v[g * 2 * half + j + half], w, c);
             }
         }
 #pragma unroll
-        for (int k = 0; k < E; k++) st(base + (k << lobits), v[k]);
+        for (int k = 0; k < E; k++) st(base + (k << lobits), v[k], k);
     }
 }
 
@@ -217,21 +226,21 @@ __device__ __forceinline__ void inv_pass(int s0, int logN, int logS, int sl, con
         const int hi = ((sl << logS) | base) >> (lobits + R);
         T v[E];
 #pragma unroll
-        for (int k = 0; k < E; k++) v[k] = ld(base + (k << lobits));
+        for (int k = 0; k < E; k++) v[k] = ld(base + (k << lobits), k);
 #pragma unroll
         for (int r = R - 1; r >= 0; r--) {
             const int half = E >> (r + 1);
 #pragma unroll
             for (int g = 0; g < (1 << r); g++) {
                 TW w;
-                if (LAST) w = __ldg(tw + (size_t)((1 << r) - 1 + g) * (size_t)(1 << (logN - 5)) + hi);
+                if (LAST) w = __ldg(tw + (size_t)((1 << r) - 1 + g) * (size_t)(1 << (logN - kLastR)) + hi);
                 else w = __ldg(tw + (1 << (s0 + r)) + (hi << r) + g);
 #pragma unroll
                 for (int j = 0; j < half; j++) A::inv(v[g * 2 * half + j], v[g * 2 * half + j + half], w, c);
             }
         }
 #pragma unroll
-        for (int k = 0; k < E; k++) st(base + (k << lobits), v[k]);
+        for (int k = 0; k < E; k++) st(base + (k << lobits), v[k], k);
     }
 }
 
@@ -243,25 +252,24 @@ __device__ __forceinline__ void mid_pass(int R, int s0, int logN, int logS, int 
         case 1: INV ? inv_pass<A, 1, false>(s0, logN, logS, sl, tw, c, ld, st) : fwd_pass<A, 1, false>(s0, logN, logS, sl, tw, c, ld, st); break;
         case 2: INV ? inv_pass<A, 2, false>(s0, logN, logS, sl, tw, c, ld, st) : fwd_pass<A, 2, false>(s0, logN, logS, sl, tw, c, ld, st); break;
         case 3: INV ? inv_pass<A, 3, false>(s0, logN, logS, sl, tw, c, ld, st) : fwd_pass<A, 3, false>(s0, logN, logS, sl, tw, c, ld, st); break;
-        case 4: INV ? inv_pass<A, 4, false>(s0, logN, logS, sl, tw, c, ld, st) : fwd_pass<A, 4, false>(s0, logN, logS, sl, tw, c, ld, st); break;
-        default: INV ? inv_pass<A, 5, false>(s0, logN, logS, sl, tw, c, ld, st) : fwd_pass<A, 5, false>(s0, logN, logS, sl, tw, c, ld, st); break;
+        default: INV ? inv_pass<A, 4, false>(s0, logN, logS, sl, tw, c, ld, st) : fwd_pass<A, 4, false>(s0, logN, logS, sl, tw, c, ld, st); break;
     }
 }
 
-// Forward transform of slice `sl`.  ld0(j) supplies the input of local coefficient j in the policy's input range, AFTER the
+// Forward transform of slice `sl`.  ld0(j, k) supplies the input of local coefficient j in the policy's input range, AFTER the
 // first (logN - logS) stages when the ring is sliced (see slice_input()).  The passes before the last one go through the padded
-// shared-memory array `s`; the results of the last pass are handed to fin(j, value) -- 32 consecutive j per thread, lazy range.
+// shared-memory array `s`; the results of the last pass are handed to fin(j, value, k), k = j mod 16 the register index -- 16 consecutive j per thread, lazy range.
 template <class A, class LD, class FIN>
 __device__ __forceinline__ void ntt_forward(typename A::T *s, int logN, int logS, int sl, const PassPlan &plan, const TwTab &tab,
                                             const typename A::C &c, LD ld0, FIN fin) {
     using T = typename A::T;
     using TW = typename A::TW;
     const TW *tw = reinterpret_cast<const TW *>(tab.fwd);
-    auto lds = [&](int j) { return s[sidx(j)]; };
-    auto sts = [&](int j, T v) { s[sidx(j)] = v; };
+    auto lds = [=](int j, int) { return s[sidx<sizeof(T)>(j)]; };
+    auto sts = [=](int j, T v, int) { s[sidx<sizeof(T)>(j)] = v; };
     int s0 = logN - logS;
     if (plan.n == 0) {
-        for (int j = threadIdx.x; j < (1 << logS); j += blockDim.x) sts(j, ld0(j));
+        for (int j = threadIdx.x; j < (1 << logS); j += blockDim.x) sts(j, ld0(j, 0), 0);
     }
     for (int i = 0; i < plan.n; i++) {
         if (i == 0) mid_pass<A, false>(plan.R[i], s0, logN, logS, sl, tw, c, ld0, sts);
@@ -270,26 +278,26 @@ __device__ __forceinline__ void ntt_forward(typename A::T *s, int logN, int logS
         __syncthreads();
     }
     if (plan.n == 0) __syncthreads();
-    fwd_pass<A, 5, true>(s0, logN, logS, sl, reinterpret_cast<const TW *>(tab.fwd_last), c, lds, fin);
+    fwd_pass<A, kLastR, true>(s0, logN, logS, sl, reinterpret_cast<const TW *>(tab.fwd_last), c, lds, fin);
 }
 
-// Inverse transform of a whole ring (logS == logN).  ld_last(j) supplies the canonical input of coefficient j for the first
-// (stride-32) pass; fin(j, v) receives v = canonical coefficient j of the result (times N^-1), unit-stride across lanes.
+// Inverse transform of a whole ring (logS == logN).  ld_last(j, k) supplies the canonical input of coefficient j for the first
+// (stride-16) pass; fin(j, v, k) receives v = canonical coefficient j of the result (times N^-1), unit-stride across lanes.
 template <class A, class LD, class FIN>
 __device__ __forceinline__ void ntt_inverse(typename A::T *s, int logN, const PassPlan &plan, const TwTab &tab, const typename A::C &c,
                                             LD ld_last, FIN fin) {
     using T = typename A::T;
     using TW = typename A::TW;
     const TW *tw = reinterpret_cast<const TW *>(tab.inv);
-    auto lds = [&](int j) { return s[sidx(j)]; };
-    auto sts = [&](int j, T v) { s[sidx(j)] = v; };
-    int s0 = logN - 5;
-    inv_pass<A, 5, true>(s0, logN, logN, 0, reinterpret_cast<const TW *>(tab.inv_last), c, ld_last, sts);
+    auto lds = [=](int j, int) { return s[sidx<sizeof(T)>(j)]; };
+    auto sts = [=](int j, T v, int) { s[sidx<sizeof(T)>(j)] = v; };
+    int s0 = logN - kLastR;
+    inv_pass<A, kLastR, true>(s0, logN, logN, 0, reinterpret_cast<const TW *>(tab.inv_last), c, ld_last, sts);
     __syncthreads();
     for (int i = plan.n - 1; i >= 0; i--) {
         s0 -= plan.R[i];
         if (i == 0) {
-            auto fin2 = [&](int j, T v) { fin(j, A::inv_final(v, c)); };
+            auto fin2 = [&](int j, T v, int k) { fin(j, A::inv_final(v, c), k); };
             mid_pass<A, true>(plan.R[i], s0, logN, logN, 0, tw, c, lds, fin2);
         } else {
             mid_pass<A, true>(plan.R[i], s0, logN, logN, 0, tw, c, lds, sts);
@@ -297,7 +305,7 @@ __device__ __forceinline__ void ntt_inverse(typename A::T *s, int logN, const Pa
         }
     }
     if (plan.n == 0) {
-        for (int j = threadIdx.x; j < (1 << logN); j += blockDim.x) fin(j, A::inv_final(lds(j), c));
+        for (int j = threadIdx.x; j < (1 << logN); j += blockDim.x) fin(j, A::inv_final(lds(j, 0), c), 0);
     }
 }
 
