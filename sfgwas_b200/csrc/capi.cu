@@ -273,7 +273,7 @@ void sfg_cache_destroy(sfg_cache *cache) {
 int sfg_cache_info(const sfg_cache *cache, size_t *num_polys, size_t *bytes, int *materialised, int *m_ct, int *nbr) {
     const Cache *ca = cache->ca;
     if (num_polys) *num_polys = ca->npoly;
-    if (bytes) *bytes = ca->materialised ? ca->npoly * (size_t)ca->lay.bytes : 0;
+    if (bytes) *bytes = ca->materialised ? ca->img_bytes : 0;
     if (materialised) *materialised = ca->materialised ? 1 : 0;
     if (m_ct) *m_ct = ca->m_ct;
     if (nbr) *nbr = ca->nbr;
@@ -283,22 +283,18 @@ int sfg_cache_get_diag(sfg_ctx *h, const sfg_cache *cache, int bi, int shift, in
     Ctx *c = &h->c;
     const Cache *ca = cache->ca;
     if (bi < 0 || bi >= ca->nbr || shift < 0 || shift >= ca->slots || bj < 0 || bj >= ca->m_ct) SFG_FAIL(c, "cache_get_diag: index out of range");
-    const int pi = ca->pidx[((size_t)bi * ca->slots + shift) * ca->m_ct + bj];
-    *present = pi >= 0;
-    if (pi < 0) return 0;
-    if (!ca->materialised) SFG_FAIL(c, "cache is not materialised (diagonals are regenerated on the fly)");
     SFG_CUDA(c, cudaSetDevice(c->device));
     const size_t N = c->N;
+    Buf tmp;
+    if (tmp.alloc(c, (size_t)ca->L * N * 8)) return -1;
+    if (cache_get_diag_dev(c, ca, bi, shift, bj, tmp.as<uint64_t>(), present)) return -1;
+    if (!*present) return 0;
+    SFG_CUDA(c, cudaMemcpyAsync(out, tmp.p, (size_t)ca->L * N * 8, cudaMemcpyDefault, c->stream));
+    SFG_CUDA(c, cudaStreamSynchronize(c->stream));
+    // the image holds plain residues; present them in the reference's cache form b*2^64 mod q (gwas/matmult.go:401-440)
     for (int l = 0; l < ca->L; l++) {
-        const unsigned char *src = ca->P + (size_t)pi * ca->lay.bytes + ca->lay.off[l];
-        if (ca->lay.es[l] == 8) {
-            SFG_CUDA(c, cudaMemcpy(out + l * N, src, N * 8, cudaMemcpyDefault));
-        } else {  // packed narrow limb (plain u32): present it in the reference's cache form b*2^64 mod q
-            std::vector<uint32_t> tmp(N);
-            SFG_CUDA(c, cudaMemcpy(tmp.data(), src, N * 4, cudaMemcpyDefault));
-            const uint64_t q = c->mod[l], r64 = c->lc_h[l].r64;
-            for (size_t k = 0; k < N; k++) out[l * N + k] = h_mulmod(tmp[k], r64, q);
-        }
+        const uint64_t q = c->mod[l], r64 = c->lc_h[l].r64;
+        for (size_t k = 0; k < N; k++) out[l * N + k] = h_mulmod(out[l * N + k], r64, q);
     }
     return 0;
 }

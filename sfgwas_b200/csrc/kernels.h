@@ -59,6 +59,37 @@ int launch_encode(Ctx *c, const int8_t *X, size_t ld, const EncJob *jobs_dev, in
 int launch_mac(Ctx *c, const void *R, const void *P, const int *pidx, int K, int nrows, int ncols, const PolyLayout &lay,
                uint64_t *cv, cudaStream_t st);
 
+// ---- tensor-core MAC (kernels_mactc.cu): byte-plane images + tcgen05 kind::i8 contraction ----
+constexpr int kTcLimbs = 8;
+struct TcGeomP {                 // geometry of the plaintext-diagonal image (fixed at preprocess time)
+    int L, N, K, ncols;
+    int ntiles;                  // column tiles of 128
+    int SBN;                     // coefficient groups (of 4) per superblock
+    int Kg, ngroups;             // K bytes per stage / K groups (one launch each)
+    int nb[kTcLimbs];            // byte planes per residue of limb l
+    long long pbase[kTcLimbs];   // byte offset of limb l inside one K-group image of `ntiles` tiles
+    long long group_bytes;
+};
+struct TcGeomR {                 // geometry of the rotated-ciphertext image (per call: depends on the number of rows)
+    int rows, RP;
+    int npad[kTcLimbs];
+    long long rbase[kTcLimbs];
+    long long group_bytes;
+    int tbuf_stride;
+};
+int tc_geom_p(Ctx *c, int L, int K, int ncols, TcGeomP *g);
+int tc_geom_r(Ctx *c, const TcGeomP &gp, int rows, TcGeomR *g);
+// records -> image.  src_off_dev: device [Kg][128] (P) / [Kg][rows] (R) byte offsets of the source records, -1 = zero.
+int launch_img_p(Ctx *c, const TcGeomP &g, const PolyLayout &lay, const void *records, const long long *src_off_dev, int img_ntiles,
+                 int ct_in_img, void *img_group, cudaStream_t st);
+int launch_img_r(Ctx *c, const TcGeomP &gp, const TcGeomR &gr, const PolyLayout &lay, const void *R, const long long *src_off_dev,
+                 void *img_group, cudaStream_t st);
+int launch_img_extract(Ctx *c, const TcGeomP &g, const void *img_group, int l, int col, int k_in_group, uint64_t *out_dev, cudaStream_t st);
+// cv[col - col_lo][row][l][n] (+)= sum_k R*P mod q for the columns of tiles [tile_lo, tile_hi) that lie in [col_lo, col_hi)
+int launch_mac_tc(Ctx *c, const TcGeomP &gp, const TcGeomR &gr, const void *Pimg_group, int img_ntiles, int img_tile0,
+                  const void *Rimg_group, int tile_lo, int tile_hi, int col_lo, int col_hi, bool accumulate, uint64_t *cv,
+                  cudaStream_t st);
+
 // ---- key-switch + automorphism (kernels_ks.cu) ----
 // A batch is a list of ciphertexts, each rotated with its own Galois key.  All arrays are DEVICE arrays of nct entries.
 struct KsBatch {

@@ -1,0 +1,683 @@
+// kernels_mactc.cu -- the dominant kernel on the 5th-generation tensor cores: output-stationary multiply-accumulate of the
+// rotated ciphertext residues with the NTT-domain plaintext diagonals, fused with the modular reduce
+// (K1 + K2 of SURVEY 2.2; gwas/matmult.go:247-324, 343-399, 1154-1168).
+//
+// Dense-contraction view: for every RNS limb l and coefficient n,
+//     CV[col][row] = sum_k  R[k][row] * P[col][k]      (mod q_l)
+// with row = (i, c) over the 2s ciphertext polynomials, k = (block row bi, baby step b), col = (giant g, block column bj):
+// a real (2s) x K x (d*m_ct) integer GEMM per (l, n), batch L'*N.  Only the canonical residue is observable (App. A.4), so
+// the residues are split into BYTE limbs and the contraction runs as u8 x u8 -> s32 tcgen05.mma (kind::i8):
+//     P[col][k] = sum_j P_j 2^(8j),  R[k][row] = sum_i R_i 2^(8i)   =>   sum_k R*P = sum_s 2^(8s) * T_s,
+//     T_s[col][row] = sum_{i+j=s} sum_k P_j[col][k] * R_i[k][row]
+//   A operand (M = 128 lanes)  : one byte plane P_j of 128 columns, K-major              (streamed from HBM, exactly once)
+//   B operand (N = nb*RP cols) : all byte planes of R stacked, row (i*RP + r), K-major    (L2-resident, 15-30 KB per (l, n))
+//   D (TMEM)                   : plane j accumulates at column offset j*RP, so that products with equal i+j land in the
+//                                same accumulator column: (2nb-1)*RP columns instead of nb*nb*RP, and the K-sum, the
+//                                (i+j)-sum and the zero padding all happen inside the tensor core.
+// The epilogue (4 warps, one TMEM lane = one column each) reads the 2nb-1 partial sums per output, recombines them with
+// the constants 2^(8s) mod q, Barrett/Montgomery-reduces to the canonical residue and stages NGF consecutive coefficients
+// in shared memory so that every global store is a full 32-byte sector of cv[col][row][l][n..n+3].
+//
+// Both operand images are laid out in HBM exactly as the UMMA shared-memory descriptors expect them (no-swizzle K-major
+// core matrices: 8 rows x 16 bytes contiguous, SBO = 128 B between 8-row groups, LBO = rows*16 B between 16-byte K chunks),
+// so one stage is ONE contiguous cp.async.bulk of 128*Kg bytes -- no tensor map, no swizzle, no address math on the SM.
+//
+// Warp roles (256 threads, 1 CTA/SM, persistent over (l, n-group, column tile) items):
+//   warp 0 lane 0 : bulk-copy producer (A ring of SA stages, B ring of 2 slots; mbarrier expect_tx)
+//   warp 1 lane 0 : tcgen05.mma issuer (zeroing MMA + nb*Kg/32 MMAs per tile), tcgen05.commit -> stage / TMEM barriers
+//   warp 2        : TMEM allocation (512 columns = 2 accumulator buffers)
+//   warps 4..7    : epilogue (tcgen05.ld -> recombine -> reduce -> smem -> 32-byte global stores)
+#include <algorithm>
+#include <cstring>
+
+#include "kernels.h"
+
+namespace sfg {
+
+namespace {
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// one contiguous global -> shared bulk copy (TMA engine, UBLKCP), completion counted in bytes on `bar`
+__device__ __forceinline__ void bulk_g2s(void *smem, const void *gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(smem)),
+                 "l"(gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, u8 x u8 -> s32, M = 128, K = 32 per instruction
+__device__ __forceinline__ void umma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// UMMA shared-memory descriptor, K-major, SWIZZLE_NONE: start address, LBO (between the 16-byte K chunks of one MMA),
+// SBO (between 8-row groups), version 1 (Blackwell)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ULL << 46);
+}
+// instruction descriptor: c = S32 (2 << 4), a/b = unsigned 8 bit (0), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+__device__ __forceinline__ uint32_t umma_idesc_u8(int n) { return (2u << 4) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24); }
+
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&v)[4]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
+
+constexpr int kTcMaxL = 8;     // limbs the tensor-core path carries per launch (maxLevel is 5 at every reference call site)
+constexpr int kTcMaxS = 11;    // 2*nb - 1 partial sums, nb <= 6 byte planes (q < 2^48)
+constexpr int kZeroBytes = 8192;
+
+}  // namespace
+
+struct MacTcParams {
+    const uint8_t *P;     // P image of this K group
+    const uint8_t *R;     // R image of this K group
+    uint64_t *cv;         // [col - col_lo][rows][L][N] canonical residues
+    const LimbConst *lc;
+    int L, N, rows, RP, Kg;
+    int img_ntiles, img_tile0;  // geometry of the P image: tiles it holds and the global index of its first tile
+    int tile_lo, tile_hi;       // global column tiles processed by this launch
+    int col_lo, col_hi;         // global columns written
+    int accumulate;             // cv += (mod q) instead of cv =
+    int SA, NGF, SBN;
+    int tbuf_stride;            // TMEM column stride between the two accumulator buffers (256) or 0 = single buffer
+    int bslot_bytes;
+    int nb[kTcMaxL], npad[kTcMaxL], fast[kTcMaxL];
+    long long pbase[kTcMaxL], rbase[kTcMaxL];
+    uint64_t cs[kTcMaxL][kTcMaxS];  // fast: 2^(8s) mod q ; otherwise 2^(8s) * 2^64 mod q (Montgomery form)
+};
+
+namespace {
+
+struct Item {
+    int l, n4, ct, sb, n4l;
+};
+__device__ __forceinline__ Item decode_item(const MacTcParams &p, long long item) {
+    const int ntr = p.tile_hi - p.tile_lo;
+    const int N4 = p.N >> 2;
+    const long long per_l = (long long)N4 * ntr;
+    Item it;
+    it.l = (int)(item / per_l);
+    const int rem = (int)(item - (long long)it.l * per_l);
+    const int per_sb = ntr * p.SBN;
+    it.sb = rem / per_sb;
+    const int rem2 = rem - it.sb * per_sb;
+    it.ct = p.tile_lo + rem2 / p.SBN;
+    it.n4l = rem2 % p.SBN;
+    it.n4 = it.sb * p.SBN + it.n4l;
+    return it;
+}
+
+// recombination + reduction of the partial sums of one output:  sum_s T_s * 2^(8s) mod q, canonical
+template <bool FAST>
+__device__ __forceinline__ uint64_t recombine(const uint32_t *T, int ns, const uint64_t *cs, const LimbConst &lc) {
+    if constexpr (FAST) {
+        uint64_t x = 0;
+#pragma unroll
+        for (int s = 0; s < kTcMaxS; s++)
+            if (s < ns) x += (uint64_t)T[s] * cs[s];  // host guarantees the sum stays below 2^64
+        return bred_add(x, lc);
+    } else {
+        u128 acc{0, 0};
+#pragma unroll
+        for (int s = 0; s < kTcMaxS; s++)
+            if (s < ns) mac128(acc, (uint64_t)T[s], cs[s]);
+        return mred128(acc, lc);
+    }
+}
+
+template <bool FAST>
+__device__ __forceinline__ void epilogue_tile(const MacTcParams &p, int l, uint32_t taddr, int slot, uint64_t *outb, int t) {
+    const int ns = 2 * p.nb[l] - 1, RP = p.RP, rows = p.rows, NGF = p.NGF;
+    const LimbConst lc = p.lc[l];
+    uint64_t cs[kTcMaxS];
+#pragma unroll
+    for (int s = 0; s < kTcMaxS; s++) cs[s] = p.cs[l][s];
+    for (int q = 0; q < RP / 4; q++) {
+        uint32_t v[kTcMaxS][4];
+#pragma unroll
+        for (int s = 0; s < kTcMaxS; s++)
+            if (s < ns) tmem_ld4(taddr + s * RP + 4 * q, v[s]);
+        tmem_wait_ld();
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const int row = 4 * q + r;
+            if (row < rows) {
+                uint32_t T[kTcMaxS];
+#pragma unroll
+                for (int s = 0; s < kTcMaxS; s++) T[s] = v[s][r];
+                outb[((size_t)row * NGF + slot) * 128 + t] = recombine<FAST>(T, ns, cs, lc);
+            }
+        }
+    }
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(256, 1) k_mac_tc(const __grid_constant__ MacTcParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int stage_bytes = 128 * p.Kg;
+    uint8_t *a_ring = smem;
+    uint8_t *b_ring = a_ring + (size_t)p.SA * stage_bytes;
+    uint8_t *zblk = b_ring + 2 * (size_t)p.bslot_bytes;
+    uint64_t *outb = reinterpret_cast<uint64_t *>(zblk + kZeroBytes);
+    uint64_t *bars = outb + (size_t)p.RP * p.NGF * 128;
+    uint64_t *a_full = bars, *a_empty = bars + p.SA;
+    uint64_t *b_full = bars + 2 * p.SA, *b_empty = b_full + 2;
+    uint64_t *t_full = b_empty + 2, *t_empty = t_full + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(t_empty + 2);
+
+    const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+    const int ntbuf = p.tbuf_stride ? 2 : 1;
+
+    if (tid == 0) {
+        for (int s = 0; s < p.SA; s++) {
+            mbar_init(&a_full[s], 1);
+            mbar_init(&a_empty[s], 1);
+        }
+        for (int s = 0; s < 2; s++) {
+            mbar_init(&b_full[s], 1);
+            mbar_init(&b_empty[s], 1);
+            mbar_init(&t_full[s], 1);
+            mbar_init(&t_empty[s], 128);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    for (int i = tid; i < kZeroBytes / 16; i += blockDim.x) reinterpret_cast<uint4 *>(zblk)[i] = make_uint4(0, 0, 0, 0);
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // generic-proxy zeros -> visible to the tensor core (async proxy)
+    if (wid == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int ntr = p.tile_hi - p.tile_lo;
+    const long long nitems = (long long)p.L * (p.N >> 2) * ntr;
+
+    if (wid == 0) {
+        // ===================== producer =====================
+        if (lane == 0) {
+            uint32_t as = 0, aph = 0, bs = 0, bph = 0;
+            for (long long item = blockIdx.x; item < nitems; item += gridDim.x) {
+                const Item it = decode_item(p, item);
+                const int nb = p.nb[it.l];
+                const uint32_t bbytes = (uint32_t)p.npad[it.l] * p.Kg;
+                const long long tg0 = (((long long)it.sb * p.img_ntiles + (it.ct - p.img_tile0)) * p.SBN + it.n4l) * 4;
+                for (int i = 0; i < 4; i++) {
+                    const int n = it.n4 * 4 + i;
+                    mbar_wait(&b_empty[bs], bph ^ 1u);
+                    mbar_arrive_expect_tx(&b_full[bs], bbytes);
+                    bulk_g2s(b_ring + (size_t)bs * p.bslot_bytes, p.R + p.rbase[it.l] + (long long)n * bbytes, bbytes, &b_full[bs]);
+                    bs ^= 1u;
+                    if (bs == 0) bph ^= 1u;
+                    const uint8_t *src = p.P + p.pbase[it.l] + (tg0 + i) * nb * (long long)stage_bytes;
+                    for (int j = 0; j < nb; j++) {
+                        mbar_wait(&a_empty[as], aph ^ 1u);
+                        mbar_arrive_expect_tx(&a_full[as], (uint32_t)stage_bytes);
+                        bulk_g2s(a_ring + (size_t)as * stage_bytes, src + (long long)j * stage_bytes, (uint32_t)stage_bytes, &a_full[as]);
+                        if (++as == (uint32_t)p.SA) {
+                            as = 0;
+                            aph ^= 1u;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (wid == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            uint32_t as = 0, aph = 0, bs = 0, bph = 0, tb = 0, tph = 0;
+            const uint32_t zaddr = smem_u32(zblk);
+            const int ksteps = p.Kg >> 5;
+            for (long long item = blockIdx.x; item < nitems; item += gridDim.x) {
+                const Item it = decode_item(p, item);
+                const int nb = p.nb[it.l], npad = p.npad[it.l];
+                const int region = (nb - 1) * p.RP + npad;
+                const uint32_t idesc = umma_idesc_u8(npad);
+                for (int i = 0; i < 4; i++) {
+                    mbar_wait(&t_empty[tb], tph ^ 1u);
+                    mbar_wait(&b_full[bs], bph);
+                    tc_fence_after();
+                    const uint32_t d_base = tmem_base + tb * (uint32_t)p.tbuf_stride;
+                    // zero the accumulator region: the byte planes overlap at different column offsets, so no single
+                    // MMA can carry the "overwrite" flag for all of it
+                    for (int c0 = 0; c0 < region; c0 += 256) {
+                        const int rem = region - c0;
+                        const int w = (((rem < 256 ? rem : 256) + 15) >> 4) << 4;
+                        umma_i8(d_base + c0, umma_desc(zaddr, 2048, 128), umma_desc(zaddr, 4096, 128), umma_idesc_u8(w), 0u);
+                    }
+                    const uint32_t baddr = smem_u32(b_ring + (size_t)bs * p.bslot_bytes);
+                    for (int j = 0; j < nb; j++) {
+                        mbar_wait(&a_full[as], aph);
+                        tc_fence_after();
+                        const uint32_t aaddr = smem_u32(a_ring + (size_t)as * stage_bytes);
+                        for (int ks = 0; ks < ksteps; ks++) {
+                            umma_i8(d_base + j * p.RP, umma_desc(aaddr + ks * 4096, 2048, 128),
+                                    umma_desc(baddr + ks * npad * 32, npad * 16, 128), idesc, 1u);
+                        }
+                        tc_commit(&a_empty[as]);
+                        if (++as == (uint32_t)p.SA) {
+                            as = 0;
+                            aph ^= 1u;
+                        }
+                    }
+                    tc_commit(&b_empty[bs]);
+                    tc_commit(&t_full[tb]);
+                    bs ^= 1u;
+                    if (bs == 0) bph ^= 1u;
+                    if (++tb == (uint32_t)ntbuf) {
+                        tb = 0;
+                        tph ^= 1u;
+                    }
+                }
+            }
+        }
+    } else if (wid >= 4) {
+        // ===================== epilogue =====================
+        const int t = tid - 128;
+        const uint32_t lane_base = (uint32_t)((wid & 3) * 32) << 16;
+        uint32_t tb = 0, tph = 0;
+        const size_t LN = (size_t)p.L * p.N;
+        for (long long item = blockIdx.x; item < nitems; item += gridDim.x) {
+            const Item it = decode_item(p, item);
+            const int l = it.l;
+            const uint64_t q = p.lc[l].q;
+            const int col = it.ct * 128 + t;
+            for (int i = 0; i < 4; i++) {
+                mbar_wait(&t_full[tb], tph);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + lane_base + tb * (uint32_t)p.tbuf_stride;
+                if (p.fast[l]) epilogue_tile<true>(p, l, taddr, i % p.NGF, outb, t);
+                else epilogue_tile<false>(p, l, taddr, i % p.NGF, outb, t);
+                tc_fence_before();
+                mbar_arrive(&t_empty[tb]);
+                if (++tb == (uint32_t)ntbuf) {
+                    tb = 0;
+                    tph ^= 1u;
+                }
+                if ((i + 1) % p.NGF == 0) {
+                    asm volatile("bar.sync 1, 128;\n" ::: "memory");
+                    if (col >= p.col_lo && col < p.col_hi) {
+                        const int n0 = it.n4 * 4 + (i + 1 - p.NGF);
+                        uint64_t *dst = p.cv + (size_t)(col - p.col_lo) * p.rows * LN + (size_t)l * p.N + n0;
+                        for (int row = 0; row < p.rows; row++, dst += LN) {
+                            const uint64_t *src = outb + (size_t)row * p.NGF * 128 + t;
+                            if (p.NGF == 4) {
+                                uint64_t v0 = src[0], v1 = src[128], v2 = src[256], v3 = src[384];
+                                if (p.accumulate) {
+                                    const ulonglong2 o0 = *reinterpret_cast<const ulonglong2 *>(dst);
+                                    const ulonglong2 o1 = *reinterpret_cast<const ulonglong2 *>(dst + 2);
+                                    v0 = add_mod(v0, o0.x, q);
+                                    v1 = add_mod(v1, o0.y, q);
+                                    v2 = add_mod(v2, o1.x, q);
+                                    v3 = add_mod(v3, o1.y, q);
+                                }
+                                *reinterpret_cast<ulonglong2 *>(dst) = make_ulonglong2(v0, v1);
+                                *reinterpret_cast<ulonglong2 *>(dst + 2) = make_ulonglong2(v2, v3);
+                            } else {
+                                for (int x = 0; x < p.NGF; x++) {
+                                    uint64_t v = src[x * 128];
+                                    if (p.accumulate) v = add_mod(v, dst[x], q);
+                                    dst[x] = v;
+                                }
+                            }
+                        }
+                    }
+                    asm volatile("bar.sync 1, 128;\n" ::: "memory");
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (wid == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// image builder: polynomial records -> K-major byte-plane image (P tiles at preprocess time, R once per call)
+// ---------------------------------------------------------------------------------------------------------------
+struct ImgParams {
+    const uint8_t *src;        // record base
+    const long long *src_off;  // device [Kg][NRS]: byte offset of the source record of (k, row), -1 = zero
+    uint8_t *dst;              // image base (of this K group)
+    int NRS;                   // source rows per k (128 columns of a P tile; `rows` ciphertext polynomials for R)
+    int Kg;
+    int mode;                  // 0 = P image, 1 = R image
+    int RP;                    // R: row pitch between byte planes
+    int img_ntiles, ct, SBN;   // P: tile position inside the image
+    int nlimbs;
+    int limb[kTcMaxL], nb[kTcMaxL], npad[kTcMaxL];
+    long long limb_off[kTcMaxL], base[kTcMaxL];
+};
+
+template <typename T>
+__global__ void __launch_bounds__(512, 1) k_img_build(const __grid_constant__ ImgParams p) {
+    constexpr int NCH = 32 / (int)sizeof(T);  // coefficients per CTA: one 32-byte sector of every source record
+    extern __shared__ __align__(16) uint8_t sm_raw[];
+    T *vals = reinterpret_cast<T *>(sm_raw);  // [Kg][NCH][16]
+    const int li = blockIdx.z;
+    const int nb = p.nb[li];
+    const int n0 = blockIdx.x * NCH, r0 = blockIdx.y * 16;
+    const int tid = threadIdx.x;
+    const uint8_t *src = p.src + p.limb_off[li] + (size_t)n0 * sizeof(T);
+    for (int idx = tid; idx < p.Kg * 16; idx += blockDim.x) {
+        const int c = idx & 15, k = idx >> 4;
+        const int row = r0 + c;
+        long long off = -1;
+        if (row < p.NRS) off = p.src_off[(size_t)k * p.NRS + row];
+        uint4 a = make_uint4(0, 0, 0, 0), b = a;
+        if (off >= 0) {
+            const uint4 *s4 = reinterpret_cast<const uint4 *>(src + off);
+            a = __ldg(s4);
+            b = __ldg(s4 + 1);
+        }
+        T *dstv = vals + (size_t)k * NCH * 16 + c;
+        if constexpr (sizeof(T) == 4) {
+            dstv[0 * 16] = a.x; dstv[1 * 16] = a.y; dstv[2 * 16] = a.z; dstv[3 * 16] = a.w;
+            dstv[4 * 16] = b.x; dstv[5 * 16] = b.y; dstv[6 * 16] = b.z; dstv[7 * 16] = b.w;
+        } else {
+            dstv[0 * 16] = ((uint64_t)a.y << 32) | a.x;
+            dstv[1 * 16] = ((uint64_t)a.w << 32) | a.z;
+            dstv[2 * 16] = ((uint64_t)b.y << 32) | b.x;
+            dstv[3 * 16] = ((uint64_t)b.w << 32) | b.z;
+        }
+    }
+    __syncthreads();
+    const int nkc = p.Kg >> 4;
+    const int total = NCH * nb * nkc * 16;
+    const int NR = p.mode == 0 ? 128 : p.npad[li];
+    for (int idx = tid; idx < total; idx += blockDim.x) {
+        const int c = idx & 15;
+        int rest = idx >> 4;
+        const int kc = rest % nkc;
+        rest /= nkc;
+        const int j = rest % nb, nn = rest / nb;
+        const int row = r0 + c;
+        if (row >= p.NRS) continue;
+        uint32_t w[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int kk = 0; kk < 16; kk++) {
+            const T v = vals[((size_t)(kc * 16 + kk) * NCH + nn) * 16 + c];
+            w[kk >> 2] |= (uint32_t)((v >> (8 * j)) & 0xff) << (8 * (kk & 3));
+        }
+        const int n = n0 + nn;
+        long long o;
+        int orow;
+        if (p.mode == 0) {
+            const int n4 = n >> 2, sb = n4 / p.SBN, n4l = n4 % p.SBN;
+            const long long tg = (((long long)sb * p.img_ntiles + p.ct) * p.SBN + n4l) * 4 + (n & 3);
+            o = p.base[li] + (tg * nb + j) * (128LL * p.Kg);
+            orow = row;
+        } else {
+            o = p.base[li] + (long long)n * NR * p.Kg;
+            orow = j * p.RP + row;
+        }
+        o += (long long)kc * NR * 16 + (orow >> 3) * 128 + (orow & 7) * 16;
+        *reinterpret_cast<uint4 *>(p.dst + o) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
+// one polynomial record back out of the P image (sfg_cache_get_diag: parity tests of the cached diagonals)
+__global__ void k_img_extract(const uint8_t *__restrict__ img, long long base, int nb, int Kg, int img_ntiles, int ct, int SBN, int c,
+                              int k, int N, uint64_t *__restrict__ out) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const int n4 = n >> 2, sb = n4 / SBN, n4l = n4 % SBN;
+    const long long tg = (((long long)sb * img_ntiles + ct) * SBN + n4l) * 4 + (n & 3);
+    uint64_t v = 0;
+    for (int j = 0; j < nb; j++) {
+        const long long o = base + (tg * nb + j) * (128LL * Kg) + (long long)(k >> 4) * 2048 + (c >> 3) * 128 + (c & 7) * 16 + (k & 15);
+        v |= (uint64_t)img[o] << (8 * j);
+    }
+    out[n] = v;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------
+static int bytes_of(uint64_t q) {
+    int b = 0;
+    while (q) {
+        b++;
+        q >>= 8;
+    }
+    return b;  // residues are < q
+}
+
+int tc_geom_p(Ctx *c, int L, int K, int ncols, TcGeomP *g) {
+    if (L > kTcMaxL) SFG_FAIL(c, "tensor-core MAC carries at most %d limbs per call (maxLevel = %d)", kTcMaxL, L);
+    if (c->N < 16) SFG_FAIL(c, "ring degree %d too small for the tensor-core MAC", c->N);
+    memset(g, 0, sizeof *g);
+    g->L = L;
+    g->N = c->N;
+    g->K = K;
+    g->ncols = ncols;
+    g->ntiles = (ncols + 127) / 128;
+    g->SBN = std::min(64, c->N / 4);
+    // K groups: Kg bytes of K per stage (multiple of 32, <= 256), as few padded K steps as possible
+    int best_ng = 0, best_kg = 0;
+    long long best = -1;
+    const int ng0 = (K + 255) / 256;
+    for (int ng = ng0; ng <= ng0 + 8; ng++) {
+        const int kg = (((K + ng - 1) / ng) + 31) / 32 * 32;
+        if (kg > 256) continue;
+        const long long tot = (long long)ng * kg + ng * 8;  // small penalty per extra group (one more launch, one more epilogue)
+        if (best < 0 || tot < best) best = tot, best_ng = ng, best_kg = kg;
+    }
+    g->ngroups = best_ng;
+    g->Kg = best_kg;
+    long long off = 0;
+    for (int l = 0; l < L; l++) {
+        g->nb[l] = bytes_of(c->mod[l] - 1);
+        if (g->nb[l] > 6) SFG_FAIL(c, "modulus %d has more than 48 bits: not supported by the tensor-core MAC", l);
+        g->pbase[l] = off;
+        off += (long long)c->N * g->ntiles * g->nb[l] * 128 * g->Kg;
+    }
+    g->group_bytes = off;
+    return 0;
+}
+
+int tc_geom_r(Ctx *c, const TcGeomP &gp, int rows, TcGeomR *g) {
+    memset(g, 0, sizeof *g);
+    g->rows = rows;
+    g->RP = (rows + 3) / 4 * 4;
+    long long off = 0;
+    int maxreg = 0;
+    for (int l = 0; l < gp.L; l++) {
+        const int nb = gp.nb[l];
+        g->npad[l] = (nb * g->RP + 15) / 16 * 16;
+        if (g->npad[l] > 256) SFG_FAIL(c, "%d ciphertext polynomials x %d byte planes exceed one MMA (N <= 256): split the call", rows, nb);
+        const int region = ((nb - 1) * g->RP + g->npad[l] + 15) / 16 * 16;
+        maxreg = std::max(maxreg, region);
+        g->rbase[l] = off;
+        off += (long long)c->N * g->npad[l] * gp.Kg;
+    }
+    if (maxreg > 512) SFG_FAIL(c, "accumulator region of %d TMEM columns exceeds 512: split the call", maxreg);
+    g->tbuf_stride = maxreg <= 256 ? 256 : 0;
+    g->group_bytes = off;
+    return 0;
+}
+
+static void split_limbs(const PolyLayout &lay, int L, int want_es, ImgParams &ip, const int *nb, const int *npad, const long long *base) {
+    ip.nlimbs = 0;
+    for (int l = 0; l < L; l++)
+        if (lay.es[l] == want_es) {
+            const int i = ip.nlimbs++;
+            ip.limb[i] = l;
+            ip.nb[i] = nb[l];
+            ip.npad[i] = npad ? npad[l] : 0;
+            ip.limb_off[i] = lay.off[l];
+            ip.base[i] = base[l];
+        }
+}
+
+static int launch_img(Ctx *c, ImgParams &ip, const PolyLayout &lay, int L, const int *nb, const int *npad, const long long *base,
+                      cudaStream_t st) {
+    for (int es : {4, 8}) {
+        split_limbs(lay, L, es, ip, nb, npad, base);
+        if (!ip.nlimbs) continue;
+        const int NCH = 32 / es;
+        const size_t smem = (size_t)ip.Kg * 512;
+        dim3 grid(c->N / NCH, (ip.NRS + 15) / 16, ip.nlimbs);
+        if (es == 4) {
+            SFG_CUDA(c, cudaFuncSetAttribute(k_img_build<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_img_build<uint32_t><<<grid, 512, smem, st>>>(ip);
+        } else {
+            SFG_CUDA(c, cudaFuncSetAttribute(k_img_build<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_img_build<uint64_t><<<grid, 512, smem, st>>>(ip);
+        }
+        SFG_LAUNCHED(c, "k_img_build", st);
+    }
+    return 0;
+}
+
+int launch_img_p(Ctx *c, const TcGeomP &g, const PolyLayout &lay, const void *records, const long long *src_off_dev, int img_ntiles,
+                 int ct_in_img, void *img_group, cudaStream_t st) {
+    if (c->N % 8) SFG_FAIL(c, "N must be a multiple of 8");
+    ImgParams ip{};
+    ip.src = (const uint8_t *)records;
+    ip.src_off = src_off_dev;
+    ip.dst = (uint8_t *)img_group;
+    ip.NRS = 128;
+    ip.Kg = g.Kg;
+    ip.mode = 0;
+    ip.img_ntiles = img_ntiles;
+    ip.ct = ct_in_img;
+    ip.SBN = g.SBN;
+    // limb bases scale with the number of tiles the image holds
+    long long base[kTcMaxL], off = 0;
+    for (int l = 0; l < g.L; l++) {
+        base[l] = off;
+        off += (long long)c->N * img_ntiles * g.nb[l] * 128 * g.Kg;
+    }
+    return launch_img(c, ip, lay, g.L, g.nb, nullptr, base, st);
+}
+
+int launch_img_r(Ctx *c, const TcGeomP &gp, const TcGeomR &gr, const PolyLayout &lay, const void *R, const long long *src_off_dev,
+                 void *img_group, cudaStream_t st) {
+    ImgParams ip{};
+    ip.src = (const uint8_t *)R;
+    ip.src_off = src_off_dev;
+    ip.dst = (uint8_t *)img_group;
+    ip.NRS = gr.rows;
+    ip.Kg = gp.Kg;
+    ip.mode = 1;
+    ip.RP = gr.RP;
+    SFG_CUDA(c, cudaMemsetAsync(img_group, 0, (size_t)gr.group_bytes, st));  // padding rows / planes / K steps are zero
+    return launch_img(c, ip, lay, gp.L, gp.nb, gr.npad, gr.rbase, st);
+}
+
+int launch_img_extract(Ctx *c, const TcGeomP &g, const void *img_group, int l, int col, int k_in_group, uint64_t *out_dev, cudaStream_t st) {
+    const int ct = col / 128, cc = col % 128;
+    k_img_extract<<<(c->N + 255) / 256, 256, 0, st>>>((const uint8_t *)img_group, g.pbase[l], g.nb[l], g.Kg, g.ntiles, ct, g.SBN, cc,
+                                                      k_in_group, c->N, out_dev);
+    SFG_LAUNCHED(c, "k_img_extract", st);
+    return 0;
+}
+
+int launch_mac_tc(Ctx *c, const TcGeomP &gp, const TcGeomR &gr, const void *Pimg_group, int img_ntiles, int img_tile0,
+                  const void *Rimg_group, int tile_lo, int tile_hi, int col_lo, int col_hi, bool accumulate, uint64_t *cv,
+                  cudaStream_t st) {
+    if (tile_hi <= tile_lo || col_hi <= col_lo) return 0;
+    MacTcParams p{};
+    p.P = (const uint8_t *)Pimg_group;
+    p.R = (const uint8_t *)Rimg_group;
+    p.cv = cv;
+    p.lc = c->lc;
+    p.L = gp.L;
+    p.N = c->N;
+    p.rows = gr.rows;
+    p.RP = gr.RP;
+    p.Kg = gp.Kg;
+    p.img_ntiles = img_ntiles;
+    p.img_tile0 = img_tile0;
+    p.tile_lo = tile_lo;
+    p.tile_hi = tile_hi;
+    p.col_lo = col_lo;
+    p.col_hi = col_hi;
+    p.accumulate = accumulate ? 1 : 0;
+    p.SBN = gp.SBN;
+    p.tbuf_stride = gr.tbuf_stride;
+    int maxnpad = 0;
+    long long off = 0;
+    for (int l = 0; l < gp.L; l++) {
+        const uint64_t q = c->mod[l];
+        const int nb = gp.nb[l];
+        p.nb[l] = nb;
+        p.npad[l] = gr.npad[l];
+        p.pbase[l] = off;
+        off += (long long)c->N * img_ntiles * nb * 128 * gp.Kg;
+        p.rbase[l] = gr.rbase[l];
+        maxnpad = std::max(maxnpad, gr.npad[l]);
+        // u64 recombination is exact iff (2nb-1) * [nb * Kg * 255^2] * q < 2^64
+        const long double bound = (long double)(2 * nb - 1) * nb * gp.Kg * 65025.0L * (long double)q;
+        p.fast[l] = bound < 18446744073709551616.0L ? 1 : 0;
+        if ((long double)nb * gp.Kg * 65025.0L >= 2147483648.0L) SFG_FAIL(c, "s32 accumulator overflow (Kg = %d)", gp.Kg);
+        for (int s = 0; s < 2 * nb - 1; s++) {
+            uint64_t v = h_powmod(2, 8 * s, q);
+            if (!p.fast[l]) v = h_mulmod(v, c->lc_h[l].r64, q);
+            p.cs[l][s] = v;
+        }
+    }
+    p.bslot_bytes = maxnpad * gp.Kg;
+    const int stage = 128 * gp.Kg;
+    const size_t fixed = 2 * (size_t)p.bslot_bytes + kZeroBytes + 512;
+    const size_t cap = 232448;  // 227 KB
+    int NGF = 4, SA = 0;
+    for (; NGF >= 1; NGF >>= 1) {
+        const size_t outb = (size_t)gr.RP * NGF * 128 * 8;
+        if (fixed + outb + 3 * (size_t)stage <= cap) {
+            SA = (int)std::min<size_t>(8, (cap - fixed - outb) / stage);
+            break;
+        }
+    }
+    if (SA < 3) SFG_FAIL(c, "tensor-core MAC does not fit shared memory (rows = %d, Kg = %d)", gr.rows, gp.Kg);
+    p.NGF = NGF;
+    p.SA = SA;
+    const size_t smem = (size_t)SA * stage + fixed + (size_t)gr.RP * NGF * 128 * 8;
+    SFG_CUDA(c, cudaFuncSetAttribute(k_mac_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int nsm = 0;
+    SFG_CUDA(c, cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->device));
+    const long long nitems = (long long)gp.L * (c->N / 4) * (tile_hi - tile_lo);
+    const int grid = (int)std::min<long long>(nsm, nitems);
+    k_mac_tc<<<grid, 256, smem, st>>>(p);
+    SFG_LAUNCHED(c, "k_mac_tc", st);
+    return 0;
+}
+
+}  // namespace sfg

@@ -76,15 +76,59 @@ static int block_cols(const Cache *ca, int bj) {
 // ---------------------------------------------------------------------------------------------------------------
 static int encode_jobs(Ctx *c, const Cache *ca, const std::vector<EncJob> &jobs, void *P) {
     if (jobs.empty()) return 0;
-    Buf dj;
-    if (dj.alloc(c, jobs.size() * sizeof(EncJob))) return -1;
-    SFG_CUDA(c, cudaMemcpyAsync(dj.p, jobs.data(), jobs.size() * sizeof(EncJob), cudaMemcpyDefault, c->stream));
-    const size_t chunk = 1 << 20;
-    for (size_t o = 0; o < jobs.size(); o += chunk) {
-        const int n = (int)std::min(chunk, jobs.size() - o);
-        if (launch_encode(c, ca->g->d, ca->ncols, dj.as<EncJob>() + o, n, ca->lay, true, P, nullptr, c->stream)) return -1;
-    }
-    SFG_CUDA(c, cudaStreamSynchronize(c->stream));
+    void *dj;
+    if (ws_get(c, WS_META2, jobs.size() * sizeof(EncJob), &dj)) return -1;
+    SFG_CUDA(c, cudaMemcpyAsync(dj, jobs.data(), jobs.size() * sizeof(EncJob), cudaMemcpyDefault, c->stream));
+    // plain residues (mont = false): the byte planes of the image are cut from the canonical value
+    if (launch_encode(c, ca->g->d, ca->ncols, (const EncJob *)dj, (int)jobs.size(), ca->lay, false, P, nullptr, c->stream)) return -1;
+    return 0;
+}
+
+// Encode the diagonals of column tiles [tile_lo, tile_hi) (columns = (active giant, block column) pairs, 128 per tile; all K
+// groups) and lay them out as a tensor-core image holding exactly those tiles.  img: ngroups * tc_group_bytes(ntiles) bytes.
+static long long tc_group_bytes(const Cache *ca, int ntiles) {
+    long long b = 0;
+    for (int l = 0; l < ca->tc.L; l++) b += (long long)ca->tc.N * ntiles * ca->tc.nb[l] * 128 * ca->tc.Kg;
+    return b;
+}
+static int build_p_tiles(Ctx *c, const Cache *ca, int tile_lo, int tile_hi, unsigned char *img) {
+    const TcGeomP &tc = ca->tc;
+    const int d = ca->d, m_ct = ca->m_ct, slots = ca->slots, Kg = tc.Kg, K = tc.K;
+    const int ntl = tile_hi - tile_lo;
+    const long long gbytes = tc_group_bytes(ca, ntl);
+    SFG_CUDA(c, cudaMemsetAsync(img, 0, (size_t)gbytes * tc.ngroups, c->stream));  // nil diagonals, padding columns / K steps
+    void *tmp, *dtab;
+    const size_t RB = (size_t)ca->lay.bytes;
+    if (ws_get(c, WS_TMPP, (size_t)128 * Kg * RB, &tmp)) return -1;
+    if (ws_get(c, WS_POFF, (size_t)128 * Kg * sizeof(long long), &dtab)) return -1;
+    std::vector<long long> tab((size_t)128 * Kg);
+    std::vector<EncJob> jobs;
+    for (int ct = tile_lo; ct < tile_hi; ct++)
+        for (int grp = 0; grp < tc.ngroups; grp++) {
+            jobs.clear();
+            std::fill(tab.begin(), tab.end(), -1LL);
+            for (int cc = 0; cc < 128; cc++) {
+                const int col = ct * 128 + cc;
+                if (col >= tc.ncols) break;
+                const int g = ca->gact[col / m_ct], bj = col % m_ct;
+                for (int kk = 0; kk < Kg; kk++) {
+                    const int k = grp * Kg + kk;
+                    if (k >= K) break;
+                    const int bi = ca->kbi[k], b = ca->kb[k];
+                    const int shift = g * d + b;
+                    if (shift >= slots) continue;
+                    if (ca->pidx[((size_t)bi * slots + shift) * m_ct + bj] < 0) continue;
+                    const long long off = (long long)((size_t)kk * 128 + cc) * (long long)RB;
+                    tab[(size_t)kk * 128 + cc] = off;
+                    // EncodeDiagWithEncoder(blockVec, -shift, d*giant, maxLevel, enc)  matmult.go:1024
+                    jobs.push_back(EncJob{bi * slots, bj * slots, block_rows(ca, bi), block_cols(ca, bj), shift, d * g, off});
+                }
+            }
+            if (jobs.empty()) continue;
+            SFG_CUDA(c, cudaMemcpyAsync(dtab, tab.data(), tab.size() * sizeof(long long), cudaMemcpyDefault, c->stream));
+            if (encode_jobs(c, ca, jobs, tmp)) return -1;
+            if (launch_img_p(c, tc, ca->lay, tmp, (const long long *)dtab, ntl, ct - tile_lo, img + (size_t)grp * gbytes, c->stream)) return -1;
+        }
     return 0;
 }
 
@@ -144,6 +188,11 @@ int cache_build(Ctx *c, Geno *g, int maxLevel, Cache **out) {
         for (int bi = 0; bi < nbr; bi++) any |= ca->giant[(size_t)bi * d + gi] != 0;
         if (any) ca->gact.push_back(gi);
     }
+    if (npoly > 0x7fffffffULL) SFG_FAIL(c, "too many diagonal polynomials");
+    if (tc_geom_p(c, ca->L, (int)ca->kbi.size(), (int)ca->gact.size() * m_ct, &ca->tc)) {
+        cache_destroy(ca);
+        return -1;
+    }
     // materialise if it fits the budget
     size_t budget = c->cache_budget;
     if (budget == 0) {
@@ -151,23 +200,13 @@ int cache_build(Ctx *c, Geno *g, int maxLevel, Cache **out) {
         SFG_CUDA(c, cudaMemGetInfo(&fr, &tot));
         budget = (size_t)(0.70 * (double)fr);
     }
-    if (npoly > 0x7fffffffULL) SFG_FAIL(c, "too many diagonal polynomials");
-    const size_t bytes = npoly * (size_t)ca->lay.bytes;
-    if (bytes <= budget) {
-        cudaError_t e = cudaMalloc(&ca->P, bytes);
+    const size_t bytes = (size_t)ca->tc.group_bytes * ca->tc.ngroups;
+    if (npoly > 0 && bytes <= budget) {
+        cudaError_t e = cudaMalloc(&ca->img, bytes);
         if (e == cudaSuccess) {
-            std::vector<EncJob> jobs;
-            jobs.reserve(npoly);
-            for (int bi = 0; bi < nbr; bi++)
-                for (int shift = 0; shift < slots; shift++)
-                    for (int bj = 0; bj < m_ct; bj++) {
-                        const int pi = ca->pidx[((size_t)bi * slots + shift) * m_ct + bj];
-                        if (pi < 0) continue;
-                        // EncodeDiagWithEncoder(blockVec, -shift, d*giant, maxLevel, enc)  matmult.go:1024
-                        jobs.push_back(EncJob{bi * slots, bj * slots, block_rows(ca, bi), block_cols(ca, bj), shift, d * (shift / d),
-                                              (long long)pi * ca->lay.bytes});
-                    }
-            if (encode_jobs(c, ca, jobs, ca->P)) {
+            ca->img_bytes = bytes;
+            if (build_p_tiles(c, ca, 0, ca->tc.ntiles, ca->img) || cudaStreamSynchronize(c->stream) != cudaSuccess) {
+                if (c->err.empty()) c->err = "diagonal cache build failed";
                 cache_destroy(ca);
                 return -1;
             }
@@ -183,7 +222,7 @@ int cache_build(Ctx *c, Geno *g, int maxLevel, Cache **out) {
 void cache_destroy(Cache *ca) {
     if (!ca) return;
     cudaSetDevice(ca->device);
-    cudaFree(ca->P);
+    cudaFree(ca->img);
     geno_release(ca->g);
     delete ca;
 }
@@ -385,45 +424,77 @@ static int build_rot_cache(Ctx *c, const Cache *ca, const uint64_t *d_A, int s, 
 // ---------------------------------------------------------------------------------------------------------------
 static int run_mac(Ctx *c, const Cache *ca, const void *R, const std::vector<int> &klist, int s, int gi_lo, int gi_hi,
                    uint64_t *d_cv) {
-    const int d = ca->d, m_ct = ca->m_ct, slots = ca->slots;
-    const int K = (int)klist.size(), ncols = (gi_hi - gi_lo) * m_ct;
-    if (K == 0 || ncols == 0) return 0;
-    std::vector<int> poff((size_t)ncols * K, -1);
-    std::vector<EncJob> jobs;  // only when the cache is not materialised
-    size_t ntmp = 0;
-    for (int gi = gi_lo; gi < gi_hi; gi++) {
-        const int g = ca->gact[gi];
-        for (int bj = 0; bj < m_ct; bj++) {
-            const size_t col = (size_t)(gi - gi_lo) * m_ct + bj;
-            for (int kk = 0; kk < K; kk++) {
-                const int bi = ca->kbi[klist[kk]], b = ca->kb[klist[kk]];
-                const int shift = g * d + b;
-                if (shift >= slots) continue;
-                const int pi = ca->pidx[((size_t)bi * slots + shift) * m_ct + bj];
-                if (pi < 0) continue;
-                if (ca->materialised) {
-                    poff[col * K + kk] = pi;
-                } else {
-                    poff[col * K + kk] = (int)ntmp;
-                    jobs.push_back(EncJob{bi * slots, bj * slots, block_rows(ca, bi), block_cols(ca, bj), shift, d * g,
-                                          (long long)ntmp * ca->lay.bytes});
-                    ntmp++;
-                }
-            }
+    const TcGeomP &tc = ca->tc;
+    const int m_ct = ca->m_ct, rows = 2 * s, Kg = tc.Kg, K = tc.K;
+    const int col_lo = gi_lo * m_ct, col_hi = gi_hi * m_ct;
+    if (klist.empty() || col_hi <= col_lo) return 0;
+    TcGeomR gr;
+    if (tc_geom_r(c, tc, rows, &gr)) return -1;
+    const int tile_lo = col_lo / 128, tile_hi = (col_hi + 127) / 128;
+    // source-record table of the R image: [group][Kg][rows]; k outside klist (other block rows / padding) contributes zero
+    std::vector<int> kpos((size_t)K, -1);
+    for (size_t i = 0; i < klist.size(); i++) kpos[klist[i]] = (int)i;
+    const size_t RB = (size_t)ca->lay.bytes;
+    std::vector<long long> tab((size_t)tc.ngroups * Kg * rows, -1);
+    for (int grp = 0; grp < tc.ngroups; grp++)
+        for (int kk = 0; kk < Kg; kk++) {
+            const int k = grp * Kg + kk;
+            if (k >= K || kpos[k] < 0) continue;
+            for (int r = 0; r < rows; r++) tab[((size_t)grp * Kg + kk) * rows + r] = (long long)(((size_t)kpos[k] * rows + r) * RB);
         }
+    void *dtab, *rimg;
+    if (ws_get(c, WS_META2, tab.size() * sizeof(long long), &dtab)) return -1;
+    SFG_CUDA(c, cudaMemcpyAsync(dtab, tab.data(), tab.size() * sizeof(long long), cudaMemcpyDefault, c->stream));
+    if (ws_get(c, WS_RIMG, (size_t)gr.group_bytes * tc.ngroups, &rimg)) return -1;
+    for (int grp = 0; grp < tc.ngroups; grp++)
+        if (launch_img_r(c, tc, gr, ca->lay, R, (const long long *)dtab + (size_t)grp * Kg * rows,
+                         (unsigned char *)rimg + (size_t)grp * gr.group_bytes, c->stream))
+            return -1;
+    if (ca->materialised) {
+        if (g_tm) g_tm->mark(3);  // the MAC kernel alone, on the stream it is launched on (bench.py roofline)
+        for (int grp = 0; grp < tc.ngroups; grp++)
+            if (launch_mac_tc(c, tc, gr, ca->img + (size_t)grp * tc.group_bytes, tc.ntiles, 0,
+                              (unsigned char *)rimg + (size_t)grp * gr.group_bytes, tile_lo, tile_hi, col_lo, col_hi, grp > 0, d_cv,
+                              c->stream))
+                return -1;
+        if (g_tm) g_tm->mark(1);
+        return 0;
     }
-    void *dpoff, *tmpP = nullptr;
-    if (ws_get(c, WS_POFF, poff.size() * sizeof(int), &dpoff)) return -1;
-    SFG_CUDA(c, cudaMemcpyAsync(dpoff, poff.data(), poff.size() * sizeof(int), cudaMemcpyDefault, c->stream));
-    const void *P = ca->P;
-    if (!ca->materialised) {
-        if (ws_get(c, WS_TMPP, std::max<size_t>(ntmp, 1) * (size_t)ca->lay.bytes, &tmpP)) return -1;
-        if (encode_jobs(c, ca, jobs, tmpP)) return -1;
-        P = tmpP;
+    // diagonals regenerated on the fly: tile chunks bounded by a temporary image of at most ~6 GiB
+    const long long per_tile = tc_group_bytes(ca, 1) * tc.ngroups;
+    const int tchunk = (int)std::max<long long>(1, std::min<long long>(tile_hi - tile_lo, ((long long)6 << 30) / per_tile));
+    void *pimg;
+    if (ws_get(c, WS_PIMG, (size_t)per_tile * tchunk, &pimg)) return -1;
+    for (int t0 = tile_lo; t0 < tile_hi; t0 += tchunk) {
+        const int t1 = std::min(tile_hi, t0 + tchunk);
+        if (build_p_tiles(c, ca, t0, t1, (unsigned char *)pimg)) return -1;
+        const long long gb = tc_group_bytes(ca, t1 - t0);
+        if (g_tm) g_tm->mark(3);
+        for (int grp = 0; grp < tc.ngroups; grp++)
+            if (launch_mac_tc(c, tc, gr, (unsigned char *)pimg + (size_t)grp * gb, t1 - t0, t0,
+                              (unsigned char *)rimg + (size_t)grp * gr.group_bytes, t0, t1, col_lo, col_hi, grp > 0, d_cv, c->stream))
+                return -1;
+        if (g_tm) g_tm->mark(1);
     }
-    if (g_tm) g_tm->mark(3);  // the MAC kernel alone, on the stream it is launched on (bench.py roofline)
-    if (launch_mac(c, R, P, (const int *)dpoff, K, 2 * s, ncols, ca->lay, d_cv, c->stream)) return -1;
-    if (g_tm) g_tm->mark(1);
+    return 0;
+}
+
+int cache_get_diag_dev(Ctx *c, const Cache *ca, int bi, int shift, int bj, uint64_t *d_out, int *present) {
+    const int pi = ca->pidx[((size_t)bi * ca->slots + shift) * ca->m_ct + bj];
+    *present = pi >= 0;
+    if (pi < 0) return 0;
+    if (!ca->materialised) SFG_FAIL(c, "cache is not materialised (diagonals are regenerated on the fly)");
+    const int g = shift / ca->d, b = shift % ca->d;
+    int gi = -1;
+    for (size_t i = 0; i < ca->gact.size(); i++)
+        if (ca->gact[i] == g) gi = (int)i;
+    const int k = ca->kidx[(size_t)bi * ca->d + b];
+    if (gi < 0 || k < 0) SFG_FAIL(c, "cache_get_diag: inconsistent activity tables");
+    const int grp = k / ca->tc.Kg, kk = k % ca->tc.Kg;
+    for (int l = 0; l < ca->L; l++)
+        if (launch_img_extract(c, ca->tc, ca->img + (size_t)grp * ca->tc.group_bytes, l, gi * ca->m_ct + bj, kk, d_out + (size_t)l * c->N,
+                               c->stream))
+            return -1;
     return 0;
 }
 

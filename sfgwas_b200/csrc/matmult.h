@@ -26,9 +26,13 @@ struct Cache {
     std::vector<uint8_t> baby, giant, shiftT;  // [nbr][d], [nbr][d], [nbr][slots]   (matmult.go:962-974)
     bool materialised = false;
     PolyLayout lay{};             // record layout of cached diagonals and of the rotation cache (packed narrow limbs)
-    unsigned char *P = nullptr;   // device compact [npoly] records of `lay` (wide limbs: NTT + Montgomery form; narrow: plain u32)
+    // Diagonals are kept as the byte-plane K-major image the tensor-core MAC streams (kernels_mactc.cu): `tc.ngroups` K groups,
+    // each [limb][coefficient superblock][column tile][coefficient][byte plane] blocks of 128 x Kg bytes.
+    TcGeomP tc{};
+    unsigned char *img = nullptr;
+    size_t img_bytes = 0;
     size_t npoly = 0;
-    std::vector<int> pidx;        // host [(bi*slots+shift)*m_ct+bj] -> record index into P or -1 (nil, matmult.go:703-705)
+    std::vector<int> pidx;        // host [(bi*slots+shift)*m_ct+bj] -> running index of the diagonal or -1 (nil, matmult.go:703-705)
     // K list: (bi, b) pairs with an active baby step, in (bi, b) order; kidx[bi*d+b] -> k or -1
     std::vector<int> kbi, kb, kidx;
     std::vector<int> gact;        // active giant indices (any block row)
@@ -59,6 +63,8 @@ int geno_push(Geno *g, const int8_t *rows, size_t n);
 void geno_release(Geno *g);
 
 int cache_build(Ctx *c, Geno *g, int maxLevel, Cache **out);
+// one cached diagonal polynomial (plain canonical residues, [L][N]) read back out of the image; 0 = nil
+int cache_get_diag_dev(Ctx *c, const Cache *ca, int bi, int shift, int bj, uint64_t *d_out, int *present);
 void cache_destroy(Cache *cache);
 
 // full single-GPU compute: d_A device [s][nbr][2][nlA][N] -> d_out device [s][m_ct][2][L][N]
