@@ -38,14 +38,13 @@ def launches(tag, per_step):
         for r in csv.reader(f):
             if hdr and len(r) == len(hdr):
                 rows.append(dict(zip(hdr, r)))
-    # the first rows are the preprocess (k_encode / k_pack); steps follow, `per_step` launches each
-    pre = [r for r in rows if "k_encode" in r["Kernel Name"] or "k_pack" in r["Kernel Name"] or "k_geno" in r["Kernel Name"]]
-    rest = [r for r in rows if r not in pre]
+    # a step is one period of the launch sequence: the distance between the last two MAC launches
+    pre = [r for r in rows if "k_encode" in r["Kernel Name"] or "k_geno" in r["Kernel Name"]]
+    macs = [i for i, r in enumerate(rows) if "k_mac" in r["Kernel Name"]]
     if per_step <= 0:
-        macs = [i for i, r in enumerate(rest) if "k_mac" in r["Kernel Name"] or "k_tcmac" in r["Kernel Name"]]
-        per_step = len(rest) // max(1, len(set(macs)) // max(1, sum(1 for i in macs if i < (macs[0] + 8))))
-    nsteps = len(rest) // per_step
-    step = rest[(nsteps - 1) * per_step: nsteps * per_step] if nsteps >= 1 else rest
+        per_step = macs[-1] - macs[-2] if len(macs) >= 2 else len(rows)
+    nsteps = len(macs)
+    step = rows[len(rows) - per_step:]
     agg = collections.OrderedDict()
     for r in step:
         nm = re.sub(r"\(.*", "", r["Kernel Name"]).replace("void ", "")
@@ -60,7 +59,7 @@ def launches(tag, per_step):
         out.append("%-44s %-16s %-12s %5d %10.3f %6.1f%% %10.1f" % (k[0][:44], k[1], k[2], a[0], a[1], 100 * a[1] / tot, 1e3 * a[1] / a[0]))
     if pre:
         out.append("# preprocess launches (outside the step):")
-        for r in pre:
+        for r in pre[:40]:
             out.append("%-44s %-16s %10.3f ms" % (re.sub(r"\(.*", "", r["Kernel Name"]).replace("void ", "")[:44], r["Grid Size"], float(r["Metric Value"]) / 1e6))
     d = os.path.join(ROOT, "profiles", tag)
     os.makedirs(d, exist_ok=True)
@@ -72,10 +71,9 @@ def launches(tag, per_step):
 def reports(tag):
     d = os.path.join(ROOT, "profiles", tag)
     os.makedirs(d, exist_ok=True)
-    for rep in sorted(glob.glob(os.path.join(ROOT, "gpurun_out", "prof_*.ncu-rep"))):
+    for rep in sorted(glob.glob(os.path.join(ROOT, "gpurun_out", "prof_*.raw.csv"))):
         name = os.path.basename(rep)[5:-8]
-        p = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True)
-        r = list(csv.reader(p.stdout.splitlines()))
+        r = list(csv.reader(open(rep).read().splitlines()))
         if len(r) < 3:
             continue
         h, units = r[0], r[1]

@@ -22,12 +22,13 @@
 // core matrices: 8 rows x 16 bytes contiguous, SBO = 128 B between 8-row groups, LBO = rows*16 B between 16-byte K chunks),
 // so one stage is ONE contiguous cp.async.bulk of 128*Kg bytes -- no tensor map, no swizzle, no address math on the SM.
 //
-// Warp roles (256 threads, 1 CTA/SM, persistent over (l, n-group, column tile) items):
+// Warp roles (384 threads, 1 CTA/SM, persistent over (l, n-group, column tile) items):
 //   warp 0 lane 0 : bulk-copy producer (A ring of SA stages, B ring of 2 slots; mbarrier expect_tx)
 //   warp 1 lane 0 : tcgen05.mma issuer (zeroing MMA + nb*Kg/32 MMAs per tile), tcgen05.commit -> stage / TMEM barriers
 //   warp 2        : TMEM allocation (512 columns = 2 accumulator buffers)
-//   warps 4..7    : epilogue (tcgen05.ld -> recombine -> reduce -> smem -> 32-byte global stores)
+//   warps 4..11   : epilogue, two warps per TMEM lane quadrant (tcgen05.ld -> recombine -> reduce -> smem -> 32-byte stores)
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "kernels.h"
@@ -62,6 +63,22 @@ __device__ __forceinline__ void bulk_g2s(void *smem, const void *gmem, uint32_t 
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(smem)),
                  "l"(gmem), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_hint(void *smem, const void *gmem, uint32_t bytes, uint64_t *bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;\n" ::"r"(
+                     smem_u32(smem)),
+                 "l"(gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+                 : "memory");
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;\n" : "=l"(p));
+    return p;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
@@ -111,6 +128,7 @@ struct MacTcParams {
     int SA, NGF, SBN;
     int tbuf_stride;            // TMEM column stride between the two accumulator buffers (256) or 0 = single buffer
     int bslot_bytes;
+    int dbg;                    // debug knobs (SFG_TC_DBG): 1 = no global stores, 2 = no epilogue math
     int nb[kTcMaxL], npad[kTcMaxL], fast[kTcMaxL];
     long long pbase[kTcMaxL], rbase[kTcMaxL];
     uint64_t cs[kTcMaxL][kTcMaxS];  // fast: 2^(8s) mod q ; otherwise 2^(8s) * 2^64 mod q (Montgomery form)
@@ -137,53 +155,84 @@ __device__ __forceinline__ Item decode_item(const MacTcParams &p, long long item
     return it;
 }
 
-// recombination + reduction of the partial sums of one output:  sum_s T_s * 2^(8s) mod q, canonical
-template <bool FAST>
-__device__ __forceinline__ uint64_t recombine(const uint32_t *T, int ns, const uint64_t *cs, const LimbConst &lc) {
-    if constexpr (FAST) {
+// recombination + reduction of the partial sums of one output:  sum_s T_s * 2^(8s) mod q, canonical.
+//   FAST 2: q < 2^31.  cs[s] = 2^(8s) 2^32 mod q (u32); x = sum T_s cs[s] < q 2^32 (host-checked), one IMAD.WIDE.U32 per term,
+//           then a 32-bit Montgomery reduction: (x + ((x qinv') mod 2^32) q) >> 32 with qinv' = -q^-1 mod 2^32.
+//   FAST 1: cs[s] = 2^(8s) mod q (u64), x < 2^64 (host-checked), Barrett (Lattigo BRedAdd).
+//   FAST 0: cs[s] = 2^(8s) 2^64 mod q, 128-bit accumulate, the reference's Montgomery reduce (gwas/matmult.go:291-324).
+template <int NS, int FAST>
+__device__ __forceinline__ uint64_t recombine(const uint32_t *T, const uint64_t *cs, const LimbConst &lc, uint32_t nqinv32) {
+    if constexpr (FAST == 2) {
         uint64_t x = 0;
 #pragma unroll
-        for (int s = 0; s < kTcMaxS; s++)
-            if (s < ns) x += (uint64_t)T[s] * cs[s];  // host guarantees the sum stays below 2^64
+        for (int s = 0; s < NS; s++) x += (uint64_t)T[s] * (uint32_t)cs[s];
+        const uint32_t q = (uint32_t)lc.q;
+        const uint32_t m = (uint32_t)x * nqinv32;
+        const uint32_t t = (uint32_t)((x + (uint64_t)m * q) >> 32);  // < 2q, exact: the low word cancels
+        return min(t, t - q);
+    } else if constexpr (FAST == 1) {
+        uint64_t x = 0;
+#pragma unroll
+        for (int s = 0; s < NS; s++) x += (uint64_t)T[s] * cs[s];  // host guarantees the sum stays below 2^64
         return bred_add(x, lc);
     } else {
         u128 acc{0, 0};
 #pragma unroll
-        for (int s = 0; s < kTcMaxS; s++)
-            if (s < ns) mac128(acc, (uint64_t)T[s], cs[s]);
+        for (int s = 0; s < NS; s++) mac128(acc, (uint64_t)T[s], cs[s]);
         return mred128(acc, lc);
     }
 }
 
-template <bool FAST>
-__device__ __forceinline__ void epilogue_tile(const MacTcParams &p, int l, uint32_t taddr, int slot, uint64_t *outb, int t) {
-    const int ns = 2 * p.nb[l] - 1, RP = p.RP, rows = p.rows, NGF = p.NGF;
+// One accumulator tile: straight-line code per chunk of 4 rows (NB and the reduction class are compile-time, the four rows
+// are independent dependency chains), results staged in shared memory as outb[row][slot][column].
+template <int NB, int FAST>
+__device__ __forceinline__ void epilogue_tile(const MacTcParams &p, int l, uint32_t taddr, int slot, uint64_t *outb, int t, int half) {
+    constexpr int NS = 2 * NB - 1;
+    const int RP = p.RP, rows = p.rows, NGF = p.NGF;
     const LimbConst lc = p.lc[l];
-    uint64_t cs[kTcMaxS];
+    const uint32_t nqinv32 = 0u - (uint32_t)lc.qinv;  // -q^-1 mod 2^32
+    uint64_t cs[NS];
 #pragma unroll
-    for (int s = 0; s < kTcMaxS; s++) cs[s] = p.cs[l][s];
-    for (int q = 0; q < RP / 4; q++) {
-        uint32_t v[kTcMaxS][4];
+    for (int s = 0; s < NS; s++) cs[s] = p.cs[l][s];
+    for (int q = half; q < RP / 4; q += 2) {  // the two epilogue warps of a TMEM lane quadrant take alternate row chunks
+        uint32_t v[NS][4];
 #pragma unroll
-        for (int s = 0; s < kTcMaxS; s++)
-            if (s < ns) tmem_ld4(taddr + s * RP + 4 * q, v[s]);
+        for (int s = 0; s < NS; s++) tmem_ld4(taddr + s * RP + 4 * q, v[s]);
         tmem_wait_ld();
+        if (p.dbg & 4) {  // TMEM reads only
+            uint32_t x = 0;
+#pragma unroll
+            for (int s = 0; s < NS; s++) x ^= v[s][0] ^ v[s][1] ^ v[s][2] ^ v[s][3];
+            if (x == 0xdeadbeef) outb[t] = x;
+            continue;
+        }
+        uint64_t val[4];
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            uint32_t T[NS];
+#pragma unroll
+            for (int s = 0; s < NS; s++) T[s] = v[s][r];
+            val[r] = recombine<NS, FAST>(T, cs, lc, nqinv32);
+        }
 #pragma unroll
         for (int r = 0; r < 4; r++) {
             const int row = 4 * q + r;
-            if (row < rows) {
-                uint32_t T[kTcMaxS];
-#pragma unroll
-                for (int s = 0; s < kTcMaxS; s++) T[s] = v[s][r];
-                outb[((size_t)row * NGF + slot) * 128 + t] = recombine<FAST>(T, ns, cs, lc);
-            }
+            if (row < rows && (!(p.dbg & 8) || val[r] == 0xdeadbeefULL)) outb[((size_t)row * NGF + slot) * 128 + t] = val[r];
         }
     }
 }
 
+template <int NB>
+__device__ __forceinline__ void epilogue_nb(const MacTcParams &p, int l, uint32_t taddr, int slot, uint64_t *outb, int t, int half) {
+    const int f = p.fast[l];
+    if (f == 2) epilogue_tile<NB, 2>(p, l, taddr, slot, outb, t, half);
+    else if (f == 1) epilogue_tile<NB, 1>(p, l, taddr, slot, outb, t, half);
+    else epilogue_tile<NB, 0>(p, l, taddr, slot, outb, t, half);
+}
+
 }  // namespace
 
-__global__ void __launch_bounds__(256, 1) k_mac_tc(const __grid_constant__ MacTcParams p) {
+__global__ void __launch_bounds__(384, 1) k_mac_tc(const __grid_constant__ MacTcParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int stage_bytes = 128 * p.Kg;
     uint8_t *a_ring = smem;
@@ -208,7 +257,7 @@ __global__ void __launch_bounds__(256, 1) k_mac_tc(const __grid_constant__ MacTc
             mbar_init(&b_full[s], 1);
             mbar_init(&b_empty[s], 1);
             mbar_init(&t_full[s], 1);
-            mbar_init(&t_empty[s], 128);
+            mbar_init(&t_empty[s], 256);
         }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
@@ -230,6 +279,8 @@ __global__ void __launch_bounds__(256, 1) k_mac_tc(const __grid_constant__ MacTc
         // ===================== producer =====================
         if (lane == 0) {
             uint32_t as = 0, aph = 0, bs = 0, bph = 0;
+            // the diagonals are read exactly once (evict first); the rotated ciphertext image is re-read by every column tile
+            const uint64_t pol_p = policy_evict_first(), pol_r = policy_evict_last();
             for (long long item = blockIdx.x; item < nitems; item += gridDim.x) {
                 const Item it = decode_item(p, item);
                 const int nb = p.nb[it.l];
@@ -239,14 +290,14 @@ __global__ void __launch_bounds__(256, 1) k_mac_tc(const __grid_constant__ MacTc
                     const int n = it.n4 * 4 + i;
                     mbar_wait(&b_empty[bs], bph ^ 1u);
                     mbar_arrive_expect_tx(&b_full[bs], bbytes);
-                    bulk_g2s(b_ring + (size_t)bs * p.bslot_bytes, p.R + p.rbase[it.l] + (long long)n * bbytes, bbytes, &b_full[bs]);
+                    bulk_g2s_hint(b_ring + (size_t)bs * p.bslot_bytes, p.R + p.rbase[it.l] + (long long)n * bbytes, bbytes, &b_full[bs], pol_r);
                     bs ^= 1u;
                     if (bs == 0) bph ^= 1u;
                     const uint8_t *src = p.P + p.pbase[it.l] + (tg0 + i) * nb * (long long)stage_bytes;
                     for (int j = 0; j < nb; j++) {
                         mbar_wait(&a_empty[as], aph ^ 1u);
                         mbar_arrive_expect_tx(&a_full[as], (uint32_t)stage_bytes);
-                        bulk_g2s(a_ring + (size_t)as * stage_bytes, src + (long long)j * stage_bytes, (uint32_t)stage_bytes, &a_full[as]);
+                        bulk_g2s_hint(a_ring + (size_t)as * stage_bytes, src + (long long)j * stage_bytes, (uint32_t)stage_bytes, &a_full[as], pol_p);
                         if (++as == (uint32_t)p.SA) {
                             as = 0;
                             aph ^= 1u;
@@ -306,7 +357,7 @@ __global__ void __launch_bounds__(256, 1) k_mac_tc(const __grid_constant__ MacTc
         }
     } else if (wid >= 4) {
         // ===================== epilogue =====================
-        const int t = tid - 128;
+        const int t = (wid & 3) * 32 + lane, half = (wid - 4) >> 2;  // TMEM lane = column of the tile; 2 warps per lane quadrant
         const uint32_t lane_base = (uint32_t)((wid & 3) * 32) << 16;
         uint32_t tb = 0, tph = 0;
         const size_t LN = (size_t)p.L * p.N;
@@ -319,8 +370,21 @@ __global__ void __launch_bounds__(256, 1) k_mac_tc(const __grid_constant__ MacTc
                 mbar_wait(&t_full[tb], tph);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + lane_base + tb * (uint32_t)p.tbuf_stride;
-                if (p.fast[l]) epilogue_tile<true>(p, l, taddr, i % p.NGF, outb, t);
-                else epilogue_tile<false>(p, l, taddr, i % p.NGF, outb, t);
+                if (p.dbg & 2) {
+                    uint32_t v[4];
+                    tmem_ld4(taddr, v);
+                    tmem_wait_ld();
+                    outb[t] = v[0];
+                } else {
+                    switch (p.nb[l]) {  // uniform across the CTA
+                        case 1: epilogue_nb<1>(p, l, taddr, i % p.NGF, outb, t, half); break;
+                        case 2: epilogue_nb<2>(p, l, taddr, i % p.NGF, outb, t, half); break;
+                        case 3: epilogue_nb<3>(p, l, taddr, i % p.NGF, outb, t, half); break;
+                        case 4: epilogue_nb<4>(p, l, taddr, i % p.NGF, outb, t, half); break;
+                        case 5: epilogue_nb<5>(p, l, taddr, i % p.NGF, outb, t, half); break;
+                        default: epilogue_nb<6>(p, l, taddr, i % p.NGF, outb, t, half); break;
+                    }
+                }
                 tc_fence_before();
                 mbar_arrive(&t_empty[tb]);
                 if (++tb == (uint32_t)ntbuf) {
@@ -328,24 +392,24 @@ __global__ void __launch_bounds__(256, 1) k_mac_tc(const __grid_constant__ MacTc
                     tph ^= 1u;
                 }
                 if ((i + 1) % p.NGF == 0) {
-                    asm volatile("bar.sync 1, 128;\n" ::: "memory");
-                    if (col >= p.col_lo && col < p.col_hi) {
+                    asm volatile("bar.sync 1, 256;\n" ::: "memory");
+                    if (col >= p.col_lo && col < p.col_hi && !(p.dbg & 1)) {
                         const int n0 = it.n4 * 4 + (i + 1 - p.NGF);
-                        uint64_t *dst = p.cv + (size_t)(col - p.col_lo) * p.rows * LN + (size_t)l * p.N + n0;
-                        for (int row = 0; row < p.rows; row++, dst += LN) {
+                        uint64_t *dst = p.cv + ((size_t)(col - p.col_lo) * p.rows + half) * LN + (size_t)l * p.N + n0;
+                        for (int row = half; row < p.rows; row += 2, dst += 2 * LN) {
                             const uint64_t *src = outb + (size_t)row * p.NGF * 128 + t;
                             if (p.NGF == 4) {
                                 uint64_t v0 = src[0], v1 = src[128], v2 = src[256], v3 = src[384];
                                 if (p.accumulate) {
-                                    const ulonglong2 o0 = *reinterpret_cast<const ulonglong2 *>(dst);
-                                    const ulonglong2 o1 = *reinterpret_cast<const ulonglong2 *>(dst + 2);
-                                    v0 = add_mod(v0, o0.x, q);
-                                    v1 = add_mod(v1, o0.y, q);
-                                    v2 = add_mod(v2, o1.x, q);
-                                    v3 = add_mod(v3, o1.y, q);
+                                    uint64_t o0, o1, o2, o3;
+                                    asm volatile("ld.global.v4.b64 {%0, %1, %2, %3}, [%4];\n" : "=l"(o0), "=l"(o1), "=l"(o2), "=l"(o3) : "l"(dst));
+                                    v0 = add_mod(v0, o0, q);
+                                    v1 = add_mod(v1, o1, q);
+                                    v2 = add_mod(v2, o2, q);
+                                    v3 = add_mod(v3, o3, q);
                                 }
-                                *reinterpret_cast<ulonglong2 *>(dst) = make_ulonglong2(v0, v1);
-                                *reinterpret_cast<ulonglong2 *>(dst + 2) = make_ulonglong2(v2, v3);
+                                // one full 32-byte sector per store (STG.256)
+                                asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};\n" ::"l"(dst), "l"(v0), "l"(v1), "l"(v2), "l"(v3) : "memory");
                             } else {
                                 for (int x = 0; x < p.NGF; x++) {
                                     uint64_t v = src[x * 128];
@@ -355,7 +419,7 @@ __global__ void __launch_bounds__(256, 1) k_mac_tc(const __grid_constant__ MacTc
                             }
                         }
                     }
-                    asm volatile("bar.sync 1, 128;\n" ::: "memory");
+                    asm volatile("bar.sync 1, 256;\n" ::: "memory");
                 }
             }
         }
@@ -647,10 +711,13 @@ int launch_mac_tc(Ctx *c, const TcGeomP &gp, const TcGeomR &gr, const void *Pimg
         // u64 recombination is exact iff (2nb-1) * [nb * Kg * 255^2] * q < 2^64
         const long double bound = (long double)(2 * nb - 1) * nb * gp.Kg * 65025.0L * (long double)q;
         p.fast[l] = bound < 18446744073709551616.0L ? 1 : 0;
+        // 32-bit Montgomery: terms T_s * c_s with c_s < q < 2^31 and the sum below q * 2^32
+        if (q < (1ULL << 31) && (long double)(2 * nb - 1) * nb * gp.Kg * 65025.0L < 4294967296.0L) p.fast[l] = 2;
         if ((long double)nb * gp.Kg * 65025.0L >= 2147483648.0L) SFG_FAIL(c, "s32 accumulator overflow (Kg = %d)", gp.Kg);
         for (int s = 0; s < 2 * nb - 1; s++) {
             uint64_t v = h_powmod(2, 8 * s, q);
-            if (!p.fast[l]) v = h_mulmod(v, c->lc_h[l].r64, q);
+            if (p.fast[l] == 0) v = h_mulmod(v, c->lc_h[l].r64, q);
+            if (p.fast[l] == 2) v = h_mulmod(v, (1ULL << 32) % q, q);
             p.cs[l][s] = v;
         }
     }
@@ -668,6 +735,8 @@ int launch_mac_tc(Ctx *c, const TcGeomP &gp, const TcGeomR &gr, const void *Pimg
     }
     if (SA < 3) SFG_FAIL(c, "tensor-core MAC does not fit shared memory (rows = %d, Kg = %d)", gr.rows, gp.Kg);
     p.NGF = NGF;
+    if (const char *e = getenv("SFG_TC_DBG")) p.dbg = atoi(e);
+    if (const char *e = getenv("SFG_TC_SA")) SA = std::min(SA, atoi(e));
     p.SA = SA;
     const size_t smem = (size_t)SA * stage + fixed + (size_t)gr.RP * NGF * 128 * 8;
     SFG_CUDA(c, cudaFuncSetAttribute(k_mac_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -675,7 +744,7 @@ int launch_mac_tc(Ctx *c, const TcGeomP &gp, const TcGeomR &gr, const void *Pimg
     SFG_CUDA(c, cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->device));
     const long long nitems = (long long)gp.L * (c->N / 4) * (tile_hi - tile_lo);
     const int grid = (int)std::min<long long>(nsm, nitems);
-    k_mac_tc<<<grid, 256, smem, st>>>(p);
+    k_mac_tc<<<grid, 384, smem, st>>>(p);
     SFG_LAUNCHED(c, "k_mac_tc", st);
     return 0;
 }
