@@ -114,6 +114,13 @@ struct KsBatch {
     int acc_cap;            // ciphertexts the acc scratch holds; larger batches are processed in chunks
 };
 int launch_rotate(Ctx *c, const KsBatch &b, cudaStream_t st);
+// Sum of rotations: entries a*nout + o (a < nct/nout), each with its own key, summed into output o with the mod-down hoisted out
+// of the sum (exact; kernels_ks.cu).  ginv_dev: device [nct] galEl^-1 mod 2N of every entry.  S1 / C0 / E: device
+// [nout][2][L][N] partial sums carried across calls (first = overwrite); launch_rotate_sum_final adds the result into out[o].
+int launch_rotate_sum(Ctx *c, const KsBatch &b, int nout, const uint32_t *ginv_dev, uint64_t *S1, uint64_t *C0, uint64_t *E, bool first,
+                      cudaStream_t st);
+int launch_rotate_sum_final(Ctx *c, int level, int nout, const uint64_t *S1, const uint64_t *C0, const uint64_t *E, void *out,
+                            const long long *out_off, const PolyLayout &olay, cudaStream_t st);
 // out (+)= in, limb-wise mod q, same offset conventions (used for rotation by 0)
 int launch_copy_add(Ctx *c, const KsBatch &b, cudaStream_t st);
 // Lattigo SwitchingKey [beta][2][nQP][N] (NTT + Montgomery) -> device format of k_ks_inner2 (TT order; narrow moduli as Shoup pairs)

@@ -243,6 +243,123 @@ k_ks_moddown2(const uint64_t *__restrict__ in, const long long *__restrict__ in_
     }
 }
 
+// ---- 4'. giant-step sum: mod-down hoisted out of the sum over the giant steps ------------------------------------------------
+// out[o] = sum_a perm_a( (accQ_a - NTT(Ext(accP_a))) * P^-1 + c0_a )   over the entries a*nout + o of one output ciphertext.
+// Every operation is exact arithmetic mod q_l, the NTT is linear, and the NTT-domain permutation perm_a is the automorphism
+// X -> X^galEl_a, so   sum_a perm_a(NTT(e_a)) = NTT( sum_a sigma_a(e_a) ):  ONE forward transform per output polynomial instead
+// of one per entry.  k_md_accum gathers  S1 = sum perm(accQ),  C0 = sum perm(c0)  (NTT domain) and  E = sum sigma(Ext(accP))
+// (coefficient domain: E[j'] += +-e[u mod N], u = j' * galEl^-1 mod 2N, minus iff u >= N);  k_md_final adds
+// (S1 - NTT(E)) * P^-1 + C0 into the output.  The result is bit-identical to per-entry mod-down (canonical residues).
+__global__ void __launch_bounds__(512, 1)
+k_md_accum(const uint64_t *__restrict__ in, const long long *__restrict__ in_off, int in_nl, const uint64_t *__restrict__ acc,
+           const BaseConv *__restrict__ md, const uint32_t *const *__restrict__ perms, const uint32_t *__restrict__ ginv, int level, int nQ,
+           int nP, int logN, const LimbConst *__restrict__ lcs, int nout, int nacc, uint64_t *__restrict__ S1o, uint64_t *__restrict__ C0o,
+           uint64_t *__restrict__ Eo, int L, int first) {
+    extern __shared__ __align__(16) uint64_t sst[];
+    const int N = 1 << logN, nl = level + 1, nt = nl + nP;
+    // rings larger than 2^13 are cut into coefficient ranges of 2^13 owned by different CTAs (the sources are staged whole)
+    const int nsplit = N > 8192 ? N / 8192 : 1;
+    const int l = blockIdx.x / nsplit, comp = blockIdx.y, o = blockIdx.z, tid = threadIdx.x;
+    const LimbConst lc = lcs[l];
+    const uint64_t q = lc.q;
+    constexpr int E16 = 16;
+    const int per = (N / nsplit) / E16;  // threads that own coefficients (<= blockDim.x)
+    uint64_t s1[E16], c0s[E16], es[E16];
+    const size_t obase = (((size_t)o * 2 + comp) * L + l) * N + (size_t)(blockIdx.x % nsplit) * (N / nsplit);
+    const int kbase = (blockIdx.x % nsplit) * (N / nsplit);
+#pragma unroll
+    for (int m = 0; m < E16; m++) {
+        const int k = tid + per * m;
+        const bool ld = !first && tid < per;
+        s1[m] = ld ? S1o[obase + k] : 0;
+        c0s[m] = (ld && comp == 0) ? C0o[obase + k] : 0;
+        es[m] = ld ? Eo[obase + k] : 0;
+    }
+    for (int a = 0; a < nacc; a++) {
+        const int ct = a * nout + o;
+        const uint32_t *perm = perms[ct];
+        const uint64_t *accQ = acc + ((size_t)(ct * 2 + comp) * nt + l) * N;   // NTT domain, TT order
+        const uint64_t *accP = acc + ((size_t)(ct * 2 + comp) * nt + nl) * N;  // P limbs, coefficient domain, natural order
+        uint32_t pk[E16];
+#pragma unroll
+        for (int m = 0; m < E16; m++) pk[m] = tid < per ? __ldg(perm + kbase + tid + per * m) : 0;
+        for (int j = tid; j < N; j += blockDim.x) sst[j] = accQ[j];
+        __syncthreads();
+        if (tid < per) {
+#pragma unroll
+            for (int m = 0; m < E16; m++) s1[m] = add_mod(s1[m], sst[tt_index((int)pk[m], N)], q);
+        }
+        __syncthreads();
+        if (comp == 0) {
+            const uint64_t *c0 = in + in_off[ct] + (size_t)l * N;
+            for (int j = tid; j < N; j += blockDim.x) sst[j] = c0[j];
+            __syncthreads();
+            if (tid < per) {
+#pragma unroll
+                for (int m = 0; m < E16; m++) c0s[m] = add_mod(c0s[m], sst[pk[m]], q);
+            }
+            __syncthreads();
+        }
+        const uint32_t gi = ginv[ct];
+        if (nP == 1) {
+            for (int j = tid; j < N; j += blockDim.x) sst[j] = accP[j];
+            __syncthreads();
+            if (tid < per) {
+#pragma unroll
+                for (int m = 0; m < E16; m++) {
+                    const uint32_t u = ((uint32_t)(kbase + tid + per * m) * gi) & (uint32_t)(2 * N - 1);
+                    const uint64_t e = bred_add(sst[u & (N - 1)], lc);
+                    es[m] = u < (uint32_t)N ? add_mod(es[m], e, q) : sub_mod(es[m], e, q);
+                }
+            }
+            __syncthreads();
+        } else if (tid < per) {
+            const BaseConv &bc = md[l];
+            for (int m = 0; m < E16; m++) {
+                const uint32_t u = ((uint32_t)(kbase + tid + per * m) * gi) & (uint32_t)(2 * N - 1);
+                uint64_t xs[kMaxAlpha];
+                for (int k = 0; k < nP; k++) xs[k] = accP[(size_t)k * N + (u & (N - 1))];
+                const uint64_t e = base_conv_coeff(bc, xs, lcs, q);
+                es[m] = u < (uint32_t)N ? add_mod(es[m], e, q) : sub_mod(es[m], e, q);
+            }
+        }
+    }
+    if (tid < per) {
+#pragma unroll
+        for (int m = 0; m < E16; m++) {
+            const int k = tid + per * m;
+            S1o[obase + k] = s1[m];
+            if (comp == 0) C0o[obase + k] = c0s[m];
+            Eo[obase + k] = es[m];
+        }
+    }
+}
+
+template <class A>
+__global__ void __launch_bounds__(512, 1)
+k_md_final(const uint64_t *__restrict__ S1, const uint64_t *__restrict__ C0, const uint64_t *__restrict__ E, const uint64_t *__restrict__ pinv,
+           int logN, PassPlan plan, const TwTab *__restrict__ tabs, const LimbConst *__restrict__ lcs, unsigned char *__restrict__ out,
+           const long long *__restrict__ out_off, PolyLayout olay, int L, TgtSel sel) {
+    using T = typename A::T;
+    extern __shared__ __align__(16) unsigned char smraw[];
+    T *s = reinterpret_cast<T *>(smraw);
+    const int N = 1 << logN;
+    const int l = sel.tt[blockIdx.x], comp = blockIdx.y, o = blockIdx.z;
+    const LimbConst lc = lcs[l];
+    const typename A::C c = A::make(lc);
+    const size_t obase = (((size_t)o * 2 + comp) * L + l) * N;
+    const uint64_t pi = pinv[2 * l], pish = pinv[2 * l + 1];
+    uint64_t *ob = reinterpret_cast<uint64_t *>(out + out_off[o] + (size_t)comp * olay.bytes + olay.off[l]);  // u64 output layout
+    auto ld0 = [&](int j, int) -> T { return A::load_u64(E[obase + j], c); };
+    auto fin = [&](int j, T v, int) {
+        const uint64_t e = A::canon(v, c);
+        uint64_t r = mul_shoup(sub_mod(S1[obase + j], e, lc.q), pi, pish, lc.q);
+        if (comp == 0) r = add_mod(r, C0[obase + j], lc.q);
+        ob[j] = add_mod(ob[j], r, lc.q);
+    };
+    ntt_forward<A>(s, logN, logN, 0, plan, tabs[l], c, ld0, fin);
+}
+
 __global__ void k_copy_add(const uint64_t *__restrict__ in, const long long *__restrict__ in_off, int in_nl,
                            unsigned char *__restrict__ out, const long long *__restrict__ out_off, PolyLayout olay, int N,
                            const LimbConst *__restrict__ lcs, int accumulate) {
@@ -307,7 +424,7 @@ static int moddown_launch(Ctx *c, const KsBatch &b, BaseConv *md, uint64_t *pinv
     return c->nP == 1 ? moddown_launch2<A, true>(c, b, md, pinv, sel, st) : moddown_launch2<A, false>(c, b, md, pinv, sel, st);
 }
 
-static int rotate_chunk(Ctx *c, const KsBatch &b, BaseConv *ks, BaseConv *md, uint64_t *pinv, cudaStream_t st) {
+static int rotate_chunk(Ctx *c, const KsBatch &b, BaseConv *ks, BaseConv *md, uint64_t *pinv, cudaStream_t st, bool moddown = true) {
     const int N = c->N, nl = b.level + 1, nt = nl + c->nP;
     // 2. inner products with the switching keys, one launch per arithmetic class of the target modulus
     TgtSel ts[3] = {{0, {}}, {0, {}}, {0, {}}};
@@ -325,6 +442,7 @@ static int rotate_chunk(Ctx *c, const KsBatch &b, BaseConv *ks, BaseConv *md, ui
     if (launch_ntt_gather(c, b.acc + (size_t)nl * N, nullptr, (size_t)nt * N, b.acc + (size_t)nl * N, (size_t)nt * N, b.nct * 2 * c->nP, selp, true,
                           true, st))
         return -1;
+    if (!moddown) return 0;
     // 4. mod-down, + c0, automorphism, store / accumulate
     TgtSel ls[3] = {{0, {}}, {0, {}}, {0, {}}};
     for (int l = 0; l < b.out_layout.nl; l++) {
@@ -361,6 +479,77 @@ int launch_rotate(Ctx *c, const KsBatch &b, cudaStream_t st) {
         ch.out_off += k0;
         if (rotate_chunk(c, ch, ks, md, pinv, st)) return -1;
     }
+    return 0;
+}
+
+// Giant-step sums (gwas/matmult.go:1203-1227): entries a*nout + o (a < nacc) are rotated with their own keys and summed into
+// output o.  Steps 1-3 run over all entries at once; the mod-down is hoisted out of the sum (k_md_accum / k_md_final).
+int launch_rotate_sum(Ctx *c, const KsBatch &b, int nout, const uint32_t *ginv_dev, uint64_t *S1, uint64_t *C0, uint64_t *E, bool first,
+                      cudaStream_t st) {
+    if (b.nct <= 0) return 0;
+    if (c->logN > 14 || c->logN < 6) SFG_FAIL(c, "fused key-switch kernels support 6 <= logN <= 14 (got %d)", c->logN);
+    if (b.nct % nout) SFG_FAIL(c, "rotate_sum: %d entries do not divide into %d outputs", b.nct, nout);
+    const int N = c->N, nl = b.level + 1, L = b.out_layout.nl;
+    const int cap = (b.acc_cap / nout) * nout;
+    if (cap < nout) SFG_FAIL(c, "key-switch scratch holds %d ciphertexts, one giant step needs %d", b.acc_cap, nout);
+    BaseConv *ks, *md;
+    uint64_t *pinv;
+    if (ctx_get_ks_tables(c, b.level, &ks, &md, &pinv)) return -1;
+    LimbSel sel;
+    sel.n = nl;
+    for (int i = 0; i < nl; i++) sel.idx[i] = i;
+    if (launch_ntt_gather(c, b.in + (size_t)b.in_nl * N, b.c2_src_off, 0, b.c2, (size_t)nl * N, b.n_c2 * nl, sel, true, false, st)) return -1;
+    const size_t smem = (size_t)N * 8;
+    SFG_CUDA(c, cudaFuncSetAttribute(k_md_accum, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    for (int k0 = 0; k0 < b.nct; k0 += cap) {
+        KsBatch ch = b;
+        ch.nct = std::min(cap, b.nct - k0);
+        ch.in_off += k0;
+        ch.c2_slot += k0;
+        ch.keys += k0;
+        ch.perms += k0;
+        ch.out_off += k0;
+        if (rotate_chunk(c, ch, ks, md, pinv, st, false)) return -1;
+        const int nsplit = N > 8192 ? N / 8192 : 1;
+        dim3 g(L * nsplit, 2, nout);
+        k_md_accum<<<g, std::min(512, std::max(32, N / nsplit / 16)), smem, st>>>(ch.in, ch.in_off, ch.in_nl, ch.acc, md, ch.perms, ginv_dev + k0, ch.level, c->nQ, c->nP,
+                                                                  c->logN, c->lc, nout, ch.nct / nout, S1, C0, E, L, (first && k0 == 0) ? 1 : 0);
+        SFG_LAUNCHED(c, "k_md_accum", st);
+    }
+    return 0;
+}
+
+template <class A>
+static int md_final_launch(Ctx *c, int level, int nout, const uint64_t *S1, const uint64_t *C0, const uint64_t *E, uint64_t *pinv, void *out,
+                           const long long *out_off, const PolyLayout &olay, const TgtSel &sel, cudaStream_t st) {
+    if (sel.n == 0) return 0;
+    const int logN = c->logN, N = c->N;
+    const PassPlan plan = make_pass_plan(logN - kLastR);
+    const size_t smem = ntt_smem_elems(N) * sizeof(typename A::T);
+    SFG_CUDA(c, cudaFuncSetAttribute(k_md_final<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 g(sel.n, 2, nout);
+    k_md_final<A><<<g, ntt_threads(N), smem, st>>>(S1, C0, E, pinv, logN, plan, c->tw2, c->lc, (unsigned char *)out, out_off, olay, olay.nl, sel);
+    SFG_LAUNCHED(c, "k_md_final", st);
+    return 0;
+}
+
+// out[o] += (S1 - NTT(E)) * P^-1 + C0   (out in the plain u64 layout)
+int launch_rotate_sum_final(Ctx *c, int level, int nout, const uint64_t *S1, const uint64_t *C0, const uint64_t *E, void *out,
+                            const long long *out_off, const PolyLayout &olay, cudaStream_t st) {
+    BaseConv *ks, *md;
+    uint64_t *pinv;
+    if (ctx_get_ks_tables(c, level, &ks, &md, &pinv)) return -1;
+    for (int l = 0; l < olay.nl; l++)
+        if (olay.es[l] != 8) SFG_FAIL(c, "rotate_sum_final writes the u64 layout only");
+    TgtSel ls[3] = {{0, {}}, {0, {}}, {0, {}}};
+    for (int l = 0; l < olay.nl; l++) {
+        TgtSel &t = ls[arith_kind(c->mod[l])];
+        t.tt[t.n++] = l;
+    }
+    if (md_final_launch<ArW>(c, level, nout, S1, C0, E, pinv, out, out_off, olay, ls[kArW], st) ||
+        md_final_launch<ArN30>(c, level, nout, S1, C0, E, pinv, out, out_off, olay, ls[kArN30], st) ||
+        md_final_launch<ArN31>(c, level, nout, S1, C0, E, pinv, out, out_off, olay, ls[kArN31], st))
+        return -1;
     return 0;
 }
 

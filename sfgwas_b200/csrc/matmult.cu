@@ -288,11 +288,13 @@ struct RotMeta {
     std::vector<const uint64_t *> keys;
     std::vector<const uint32_t *> perms;
     std::vector<int> c2_slot;
+    std::vector<uint32_t> ginv;  // galEl^-1 mod 2N of every entry (giant-step sums)
     // device pointers after upload
     const long long *d_in_off = nullptr, *d_out_off = nullptr, *d_c2_src = nullptr;
     const uint64_t *const *d_keys = nullptr;
     const uint32_t *const *d_perms = nullptr;
     const int *d_c2_slot = nullptr;
+    const uint32_t *d_ginv = nullptr;
     void add(const RotEntry &e) {
         in_off.push_back(e.in_off);
         out_off.push_back(e.out_off);
@@ -302,7 +304,7 @@ struct RotMeta {
     }
     int upload(Ctx *c, int slot) {
         const size_t n = in_off.size(), m = c2_src.size();
-        const size_t bytes = (2 * n + m) * 8 + 2 * n * 8 + n * 4 + 64;
+        const size_t bytes = (2 * n + m) * 8 + 2 * n * 8 + n * 4 + ginv.size() * 4 + 64;
         std::vector<unsigned char> h(bytes);
         unsigned char *p = h.data();
         size_t o_in = 0, o_out = n * 8, o_src = 2 * n * 8, o_keys = (2 * n + m) * 8, o_perms = o_keys + n * 8, o_slot = o_perms + n * 8;
@@ -312,6 +314,8 @@ struct RotMeta {
         memcpy(p + o_keys, keys.data(), n * 8);
         memcpy(p + o_perms, perms.data(), n * 8);
         memcpy(p + o_slot, c2_slot.data(), n * 4);
+        const size_t o_ginv = o_slot + n * 4;
+        if (!ginv.empty()) memcpy(p + o_ginv, ginv.data(), ginv.size() * 4);
         void *d;
         if (ws_get(c, slot, bytes, &d)) return -1;
         SFG_CUDA(c, cudaMemcpyAsync(d, p, bytes, cudaMemcpyDefault, c->stream));
@@ -322,6 +326,7 @@ struct RotMeta {
         d_keys = (const uint64_t *const *)(db + o_keys);
         d_perms = (const uint32_t *const *)(db + o_perms);
         d_c2_slot = (const int *)(db + o_slot);
+        d_ginv = (const uint32_t *)(db + o_ginv);
         return 0;
     }
 };
@@ -331,7 +336,7 @@ static int fill_scratch(Ctx *c, KsBatch &kb, int max_nct, int max_c2) {
     const size_t N = c->N;
     const int nl = kb.level + 1, nt = nl + c->nP;
     const size_t per_ct = (size_t)2 * nt * N * 8;
-    const int cap = (int)std::max<size_t>(1, std::min<size_t>((size_t)max_nct, ((size_t)2 << 30) / per_ct));
+    const int cap = (int)std::max<size_t>(1, std::min<size_t>((size_t)max_nct, ((size_t)4 << 30) / per_ct));
     void *pc2, *pacc;
     if (ws_get(c, WS_C2, (size_t)max_c2 * nl * N * 8, &pc2) || ws_get(c, WS_ACC, (size_t)cap * per_ct, &pacc)) return -1;
     kb.c2 = (uint64_t *)pc2;
@@ -503,24 +508,36 @@ int cache_get_diag_dev(Ctx *c, const Cache *ca, int bi, int shift, int bj, uint6
 //     out[i][bj] += RotateRightWithEvaluator(cv[i][g][bj], -g*d)   for g in gact[gi_lo .. gi_hi)
 //     one batch per giant step (entries of a batch must target distinct outputs), metadata uploaded once for all of them
 // ---------------------------------------------------------------------------------------------------------------
+static uint32_t inv_mod_pow2(uint64_t a, int bits) {  // a odd
+    uint64_t x = 1;
+    for (int i = 0; i < 6; i++) x *= 2 - a * x;
+    return (uint32_t)(x & ((1ULL << bits) - 1));
+}
+
 static int run_giant(Ctx *c, const Cache *ca, int s, const uint64_t *d_cv, int gi_lo, int gi_hi, uint64_t *d_out) {
     const int d = ca->d, m_ct = ca->m_ct, L = ca->L, N = c->N, nrows = 2 * s;
     const size_t LN = (size_t)L * N;
-    const int nct = m_ct * s;
+    const int nout = m_ct * s;
     if (gi_hi <= gi_lo) return 0;
-    RotMeta rot;
+    RotMeta rot, cpy;
+    int nrot = 0;
     for (int gi = gi_lo; gi < gi_hi; gi++) {
         const int g = ca->gact[gi];
         const GaloisKey *key = nullptr;
         if (g > 0 && find_key(c, (g * d) % ca->slots, &key)) return -1;
-        for (int t = 0; t < nct; t++) {  // t = bj*s + i : consecutive ciphertexts of the cv image
+        for (int t = 0; t < nout; t++) {  // t = bj*s + i : consecutive ciphertexts of the cv image
             const int bj = t / s, i = t % s;
             const long long in_off = (long long)((((size_t)(gi - gi_lo) * m_ct + bj) * nrows + 2 * i) * LN);
-            rot.add(RotEntry{in_off, (long long)(((size_t)i * m_ct + bj) * 2 * LN * 8), t, key});
+            const RotEntry e{in_off, (long long)(((size_t)i * m_ct + bj) * 2 * LN * 8), 0, key};
+            if (g == 0) {
+                cpy.add(e);
+            } else {
+                rot.add(e);
+                rot.ginv.push_back(inv_mod_pow2(key->galEl, c->logN + 1));
+            }
         }
+        if (g > 0) nrot++;
     }
-    rot.c2_src = rot.in_off;  // every entry is its own INTT slot (slot index restarts at 0 for every giant step)
-    if (rot.upload(c, WS_META)) return -1;
     KsBatch kb{};
     kb.level = L - 1;  // ModularReduceV2 creates the ct at level len(acc0)-1 (gwas/matmult.go:350)
     kb.in = d_cv;
@@ -528,24 +545,42 @@ static int run_giant(Ctx *c, const Cache *ca, int s, const uint64_t *d_cv, int g
     kb.out = d_out;
     kb.out_layout = make_layout(c, L, false);
     kb.accumulate = true;
-    kb.nct = nct;
-    kb.n_c2 = nct;
-    if (fill_scratch(c, kb, nct, nct)) return -1;
-    for (int gi = gi_lo; gi < gi_hi; gi++) {
-        const size_t o = (size_t)(gi - gi_lo) * nct;
+    if (!cpy.in_off.empty()) {  // giant step 0: no rotation (crypto/basics.go:203)
+        if (cpy.upload(c, WS_META2)) return -1;
+        kb.nct = (int)cpy.in_off.size();
+        kb.in_off = cpy.d_in_off;
+        kb.out_off = cpy.d_out_off;
+        if (launch_copy_add(c, kb, c->stream)) return -1;
+    }
+    if (nrot == 0) return 0;
+    // chunks of G giant steps go through one sequence of launches; every entry is its own INTT slot (numbered inside its chunk)
+    kb.nct = nout;
+    kb.n_c2 = nout;
+    if (fill_scratch(c, kb, nrot * nout, 1)) return -1;
+    const int G = std::max(1, std::min(nrot, kb.acc_cap / nout));
+    if (kb.acc_cap < nout) SFG_FAIL(c, "key-switch scratch too small for one giant step (%d ciphertexts)", nout);
+    if (fill_scratch(c, kb, G * nout, G * nout)) return -1;
+    for (size_t k = 0; k < rot.in_off.size(); k++) rot.c2_slot[k] = (int)(k % ((size_t)G * nout));
+    rot.c2_src = rot.in_off;
+    if (rot.upload(c, WS_META)) return -1;
+    void *mdbuf;
+    const size_t msz = (size_t)nout * 2 * LN;
+    if (ws_get(c, WS_MD, 3 * msz * 8, &mdbuf)) return -1;
+    uint64_t *S1 = (uint64_t *)mdbuf, *C0 = S1 + msz, *E = C0 + msz;
+    for (int a0 = 0; a0 < nrot; a0 += G) {
+        const int na = std::min(G, nrot - a0);
+        const size_t o = (size_t)a0 * nout;
+        kb.nct = na * nout;
+        kb.n_c2 = na * nout;
         kb.in_off = rot.d_in_off + o;
         kb.out_off = rot.d_out_off + o;
         kb.c2_src_off = rot.d_c2_src + o;
         kb.c2_slot = rot.d_c2_slot + o;
         kb.keys = rot.d_keys + o;
         kb.perms = rot.d_perms + o;
-        if (ca->gact[gi] == 0) {
-            if (launch_copy_add(c, kb, c->stream)) return -1;
-        } else if (launch_rotate(c, kb, c->stream)) {
-            return -1;
-        }
+        if (launch_rotate_sum(c, kb, nout, rot.d_ginv + o, S1, C0, E, a0 == 0, c->stream)) return -1;
     }
-    return 0;
+    return launch_rotate_sum_final(c, L - 1, nout, S1, C0, E, d_out, rot.d_out_off, kb.out_layout, c->stream);
 }
 
 static int check_args(Ctx *c, const Cache *ca, int s, int nbr, int levelA, int maxLevel) {
