@@ -250,77 +250,132 @@ k_ks_moddown2(const uint64_t *__restrict__ in, const long long *__restrict__ in_
 // of one per entry.  k_md_accum gathers  S1 = sum perm(accQ),  C0 = sum perm(c0)  (NTT domain) and  E = sum sigma(Ext(accP))
 // (coefficient domain: E[j'] += +-e[u mod N], u = j' * galEl^-1 mod 2N, minus iff u >= N);  k_md_final adds
 // (S1 - NTT(E)) * P^-1 + C0 into the output.  The result is bit-identical to per-entry mod-down (canonical residues).
+// Sources are staged whole (N x 8 bytes) by cp.async.bulk into a ring of three shared-memory buffers, prefetched two stages
+// ahead of the gathers, so the kernel streams acc / cv at memory speed instead of paying one load latency per source.
+__device__ __forceinline__ uint32_t md_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void md_bulk(void *smem, const void *gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(md_smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(md_smem_u32(smem)), "l"(gmem),
+                 "r"(bytes), "r"(md_smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void md_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "MD_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra MD_DONE;\n\t"
+        "bra MD_WAIT;\n\t"
+        "MD_DONE:\n\t}\n" ::"r"(md_smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+template <typename T>  // accumulator type: uint32_t for q < 2^31, uint64_t otherwise
 __global__ void __launch_bounds__(512, 1)
 k_md_accum(const uint64_t *__restrict__ in, const long long *__restrict__ in_off, int in_nl, const uint64_t *__restrict__ acc,
            const BaseConv *__restrict__ md, const uint32_t *const *__restrict__ perms, const uint32_t *__restrict__ ginv, int level, int nQ,
            int nP, int logN, const LimbConst *__restrict__ lcs, int nout, int nacc, uint64_t *__restrict__ S1o, uint64_t *__restrict__ C0o,
-           uint64_t *__restrict__ Eo, int L, int first) {
-    extern __shared__ __align__(16) uint64_t sst[];
+           uint64_t *__restrict__ Eo, int L, int first, TgtSel sel) {
+    extern __shared__ __align__(128) uint64_t sst[];
+    constexpr int NBUF = 3;
     const int N = 1 << logN, nl = level + 1, nt = nl + nP;
+    uint64_t *bars = sst + (size_t)NBUF * N;
     // rings larger than 2^13 are cut into coefficient ranges of 2^13 owned by different CTAs (the sources are staged whole)
     const int nsplit = N > 8192 ? N / 8192 : 1;
-    const int l = blockIdx.x / nsplit, comp = blockIdx.y, o = blockIdx.z, tid = threadIdx.x;
+    const int l = sel.tt[blockIdx.x / nsplit], comp = blockIdx.y, o = blockIdx.z, tid = threadIdx.x;
     const LimbConst lc = lcs[l];
-    const uint64_t q = lc.q;
+    const T q = (T)lc.q;
     constexpr int E16 = 16;
     const int per = (N / nsplit) / E16;  // threads that own coefficients (<= blockDim.x)
-    uint64_t s1[E16], c0s[E16], es[E16];
-    const size_t obase = (((size_t)o * 2 + comp) * L + l) * N + (size_t)(blockIdx.x % nsplit) * (N / nsplit);
+    T s1[E16], c0s[E16], es[E16];
     const int kbase = (blockIdx.x % nsplit) * (N / nsplit);
+    const size_t obase = (((size_t)o * 2 + comp) * L + l) * N + kbase;
+    auto addm = [&](T a, T b2) { const T r = a + b2; return r >= q ? r - q : r; };
+    auto subm = [&](T a, T b2) { return a >= b2 ? a - b2 : a + q - b2; };
 #pragma unroll
     for (int m = 0; m < E16; m++) {
         const int k = tid + per * m;
         const bool ld = !first && tid < per;
-        s1[m] = ld ? S1o[obase + k] : 0;
-        c0s[m] = (ld && comp == 0) ? C0o[obase + k] : 0;
-        es[m] = ld ? Eo[obase + k] : 0;
+        s1[m] = ld ? (T)S1o[obase + k] : 0;
+        c0s[m] = (ld && comp == 0) ? (T)C0o[obase + k] : 0;
+        es[m] = ld ? (T)Eo[obase + k] : 0;
     }
+    // stage sequence: per entry  [accQ] [c0 if comp == 0] [accP if nP == 1]
+    const bool stageP = nP == 1;
+    const int spe = 1 + (comp == 0 ? 1 : 0) + (stageP ? 1 : 0);
+    const int nstage = nacc * spe;
+    const uint32_t bytes = (uint32_t)N * 8;
+    auto src_of = [&](int st) -> const uint64_t * {
+        const int a = st / spe, w = st % spe, ct = a * nout + o;
+        if (w == 0) return acc + ((size_t)(ct * 2 + comp) * nt + l) * N;              // accQ: NTT domain, TT order
+        if (w == 1 && comp == 0) return in + in_off[ct] + (size_t)l * N;               // c0: NTT domain, natural order
+        return acc + ((size_t)(ct * 2 + comp) * nt + nl) * N;                          // accP: coefficient domain, natural order
+    };
+    if (tid == 0) {
+        for (int i = 0; i < NBUF; i++) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(md_smem_u32(&bars[i])), "r"(1));
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        for (int st = 0; st < NBUF && st < nstage; st++) md_bulk(sst + (size_t)st * N, src_of(st), bytes, &bars[st]);
+    }
+    __syncthreads();
+    int st = 0;
+    auto next_stage = [&]() -> const uint64_t * {  // wait for stage st; returns its buffer
+        md_wait(&bars[st % NBUF], (uint32_t)(st / NBUF) & 1u);
+        return sst + (size_t)(st % NBUF) * N;
+    };
+    auto release_stage = [&]() {  // all threads are done with stage st: refill its buffer with stage st + NBUF
+        __syncthreads();
+        if (tid == 0 && st + NBUF < nstage) {
+            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+            md_bulk(sst + (size_t)(st % NBUF) * N, src_of(st + NBUF), bytes, &bars[st % NBUF]);
+        }
+        st++;
+    };
     for (int a = 0; a < nacc; a++) {
         const int ct = a * nout + o;
         const uint32_t *perm = perms[ct];
-        const uint64_t *accQ = acc + ((size_t)(ct * 2 + comp) * nt + l) * N;   // NTT domain, TT order
-        const uint64_t *accP = acc + ((size_t)(ct * 2 + comp) * nt + nl) * N;  // P limbs, coefficient domain, natural order
         uint32_t pk[E16];
 #pragma unroll
         for (int m = 0; m < E16; m++) pk[m] = tid < per ? __ldg(perm + kbase + tid + per * m) : 0;
-        for (int j = tid; j < N; j += blockDim.x) sst[j] = accQ[j];
-        __syncthreads();
-        if (tid < per) {
-#pragma unroll
-            for (int m = 0; m < E16; m++) s1[m] = add_mod(s1[m], sst[tt_index((int)pk[m], N)], q);
-        }
-        __syncthreads();
-        if (comp == 0) {
-            const uint64_t *c0 = in + in_off[ct] + (size_t)l * N;
-            for (int j = tid; j < N; j += blockDim.x) sst[j] = c0[j];
-            __syncthreads();
+        {
+            const uint64_t *sq = next_stage();
             if (tid < per) {
 #pragma unroll
-                for (int m = 0; m < E16; m++) c0s[m] = add_mod(c0s[m], sst[pk[m]], q);
+                for (int m = 0; m < E16; m++) s1[m] = addm(s1[m], (T)sq[tt_index((int)pk[m], N)]);
             }
-            __syncthreads();
+            release_stage();
+        }
+        if (comp == 0) {
+            const uint64_t *sc = next_stage();
+            if (tid < per) {
+#pragma unroll
+                for (int m = 0; m < E16; m++) c0s[m] = addm(c0s[m], (T)sc[pk[m]]);
+            }
+            release_stage();
         }
         const uint32_t gi = ginv[ct];
-        if (nP == 1) {
-            for (int j = tid; j < N; j += blockDim.x) sst[j] = accP[j];
-            __syncthreads();
+        if (stageP) {
+            const uint64_t *sp = next_stage();
             if (tid < per) {
 #pragma unroll
                 for (int m = 0; m < E16; m++) {
                     const uint32_t u = ((uint32_t)(kbase + tid + per * m) * gi) & (uint32_t)(2 * N - 1);
-                    const uint64_t e = bred_add(sst[u & (N - 1)], lc);
-                    es[m] = u < (uint32_t)N ? add_mod(es[m], e, q) : sub_mod(es[m], e, q);
+                    const T e = (T)bred_add(sp[u & (N - 1)], lc);
+                    es[m] = u < (uint32_t)N ? addm(es[m], e) : subm(es[m], e);
                 }
             }
-            __syncthreads();
+            release_stage();
         } else if (tid < per) {
+            const uint64_t *accP = acc + ((size_t)(ct * 2 + comp) * nt + nl) * N;
             const BaseConv &bc = md[l];
             for (int m = 0; m < E16; m++) {
                 const uint32_t u = ((uint32_t)(kbase + tid + per * m) * gi) & (uint32_t)(2 * N - 1);
                 uint64_t xs[kMaxAlpha];
                 for (int k = 0; k < nP; k++) xs[k] = accP[(size_t)k * N + (u & (N - 1))];
-                const uint64_t e = base_conv_coeff(bc, xs, lcs, q);
-                es[m] = u < (uint32_t)N ? add_mod(es[m], e, q) : sub_mod(es[m], e, q);
+                const T e = (T)base_conv_coeff(bc, xs, lcs, lc.q);
+                es[m] = u < (uint32_t)N ? addm(es[m], e) : subm(es[m], e);
             }
         }
     }
@@ -499,8 +554,14 @@ int launch_rotate_sum(Ctx *c, const KsBatch &b, int nout, const uint32_t *ginv_d
     sel.n = nl;
     for (int i = 0; i < nl; i++) sel.idx[i] = i;
     if (launch_ntt_gather(c, b.in + (size_t)b.in_nl * N, b.c2_src_off, 0, b.c2, (size_t)nl * N, b.n_c2 * nl, sel, true, false, st)) return -1;
-    const size_t smem = (size_t)N * 8;
-    SFG_CUDA(c, cudaFuncSetAttribute(k_md_accum, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t smem = (size_t)3 * N * 8 + 64;
+    SFG_CUDA(c, cudaFuncSetAttribute(k_md_accum<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SFG_CUDA(c, cudaFuncSetAttribute(k_md_accum<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TgtSel nar{0, {}}, wid{0, {}};
+    for (int l = 0; l < L; l++) {
+        TgtSel &t = c->mod[l] < (1ULL << 31) ? nar : wid;
+        t.tt[t.n++] = l;
+    }
     for (int k0 = 0; k0 < b.nct; k0 += cap) {
         KsBatch ch = b;
         ch.nct = std::min(cap, b.nct - k0);
@@ -511,9 +572,16 @@ int launch_rotate_sum(Ctx *c, const KsBatch &b, int nout, const uint32_t *ginv_d
         ch.out_off += k0;
         if (rotate_chunk(c, ch, ks, md, pinv, st, false)) return -1;
         const int nsplit = N > 8192 ? N / 8192 : 1;
-        dim3 g(L * nsplit, 2, nout);
-        k_md_accum<<<g, std::min(512, std::max(32, N / nsplit / 16)), smem, st>>>(ch.in, ch.in_off, ch.in_nl, ch.acc, md, ch.perms, ginv_dev + k0, ch.level, c->nQ, c->nP,
-                                                                  c->logN, c->lc, nout, ch.nct / nout, S1, C0, E, L, (first && k0 == 0) ? 1 : 0);
+        const int thr = std::min(512, std::max(32, N / nsplit / 16));
+        const int fst = (first && k0 == 0) ? 1 : 0;
+        if (wid.n) {
+            k_md_accum<uint64_t><<<dim3(wid.n * nsplit, 2, nout), thr, smem, st>>>(ch.in, ch.in_off, ch.in_nl, ch.acc, md, ch.perms, ginv_dev + k0, ch.level,
+                                                                                 c->nQ, c->nP, c->logN, c->lc, nout, ch.nct / nout, S1, C0, E, L, fst, wid);
+            SFG_LAUNCHED(c, "k_md_accum", st);
+        }
+        if (nar.n)
+            k_md_accum<uint32_t><<<dim3(nar.n * nsplit, 2, nout), thr, smem, st>>>(ch.in, ch.in_off, ch.in_nl, ch.acc, md, ch.perms, ginv_dev + k0, ch.level,
+                                                                                 c->nQ, c->nP, c->logN, c->lc, nout, ch.nct / nout, S1, C0, E, L, fst, nar);
         SFG_LAUNCHED(c, "k_md_accum", st);
     }
     return 0;
