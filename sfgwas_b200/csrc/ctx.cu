@@ -87,11 +87,12 @@ int ctx_build_tables(Ctx *c, const uint64_t *psi_opt) {
         for (int i = 0; i < nQP; i++) {
             const uint64_t q = c->mod[i];
             const uint64_t *w = &tw[(size_t)i * 4 * N], *wi = w + 2 * N;
-            const bool wide = arith_kind(q) == kArW;
-            const size_t es = wide ? sizeof(ulonglong2) : sizeof(uint2);
+            const int kind = arith_kind(q);
+            const size_t es = kind == kArW ? sizeof(ulonglong2) : 8;
             std::vector<unsigned char> h((size_t)(2 * N + 2 * NL * P) * es);
             auto put = [&](size_t pos, uint64_t x) {
-                if (wide) reinterpret_cast<ulonglong2 *>(h.data())[pos] = ArW::make_tw(x, q);
+                if (kind == kArW) reinterpret_cast<ulonglong2 *>(h.data())[pos] = ArW::make_tw(x, q);
+                else if (kind == kArD) reinterpret_cast<double *>(h.data())[pos] = ArD::make_tw(x, q);
                 else reinterpret_cast<uint2 *>(h.data())[pos] = ArN30::make_tw(x, q);
             };
             for (int j = 0; j < N; j++) {

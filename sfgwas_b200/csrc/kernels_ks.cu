@@ -44,7 +44,8 @@ struct TgtSel {  // targets (or limbs) of one arithmetic class
 // ---- Galois key conversion (once per key upload) ----------------------------------------------------------------------
 // in : Lattigo SwitchingKey [beta][2][nQP][N] u64, NTT + Montgomery form.
 // out: same shape, every polynomial in TT order; wide moduli keep the Montgomery u64, narrow moduli (q < 2^31) become
-//      (k, floor(k 2^32 / q)) pairs with k the plain residue, for the 32-bit Shoup multiplication.
+//      (k, floor(k 2^32 / q)) pairs with k the plain residue, for the 32-bit Shoup multiplication; FP64-class moduli the plain
+//      residue as a double.
 __global__ void k_key_convert(const uint64_t *__restrict__ in, uint64_t *__restrict__ out, int N, int nQP, const LimbConst *__restrict__ lcs) {
     const int poly = blockIdx.y, limb = poly % nQP;
     const LimbConst lc = lcs[limb];
@@ -54,7 +55,9 @@ __global__ void k_key_convert(const uint64_t *__restrict__ in, uint64_t *__restr
     for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < N; j += gridDim.x * blockDim.x) {
         const uint64_t km = src[j];
         uint64_t o = km;
-        if (kind != kArW) {
+        if (kind == kArD) {
+            o = (uint64_t)__double_as_longlong((double)(long long)mred(km, 1, lc));  // plain residue as an FP64 integer
+        } else if (kind != kArW) {
             const uint64_t k = mred(km, 1, lc);  // InvMForm
             o = k | (((k << 32) / lc.q) << 32);
         }
@@ -97,7 +100,7 @@ k_ks_inner2(const uint64_t *__restrict__ in, const long long *__restrict__ in_of
     const int NP = N >> kLastR;
 
     // accumulators: registers for the 32-bit classes; thread-private shared-memory slots for the 64-bit class (register budget)
-    constexpr bool ACC_SMEM = A::kKind == kArW;
+    constexpr bool ACC_SMEM = A::kKind == kArW || A::kKind == kArD;
     constexpr int NREG = ACC_SMEM ? 1 : kLastE;
     T a0[NREG], a1[NREG];
     T *s0a = s + S, *s1a = s0a + S;
@@ -117,7 +120,11 @@ k_ks_inner2(const uint64_t *__restrict__ in, const long long *__restrict__ in_of
         const uint64_t *k1 = key + ((size_t)(i * 2 + 1) * nQP + tgt) * N + P;
         // multiply coefficient 16 P + k with the two key polynomials (TT order: unit stride across lanes) and accumulate
         auto mac = [&](int, T v, int k) {
-            if constexpr (ACC_SMEM) {
+            if constexpr (A::kKind == kArD) {  // lazy FP64 accumulation: every product is in (-q, q)
+                const int sj = sidx<sizeof(T)>(abase + k);
+                s0a[sj] += A::mul_lazy(v, __ldg(reinterpret_cast<const double *>(k0) + (size_t)k * NP), c);
+                s1a[sj] += A::mul_lazy(v, __ldg(reinterpret_cast<const double *>(k1) + (size_t)k * NP), c);
+            } else if constexpr (ACC_SMEM) {
                 const int sj = sidx<sizeof(T)>(abase + k);
                 s0a[sj] = add_mod(s0a[sj], mred(v, __ldg(k0 + (size_t)k * NP), lc), lc.q);
                 s1a[sj] = add_mod(s1a[sj], mred(v, __ldg(k1 + (size_t)k * NP), lc), lc.q);
@@ -169,7 +176,10 @@ k_ks_inner2(const uint64_t *__restrict__ in, const long long *__restrict__ in_of
         uint64_t *o1 = accout + ((size_t)(ct * 2 + 1) * nt + tt) * N + P;
 #pragma unroll
         for (int k = 0; k < kLastE; k++) {
-            if constexpr (ACC_SMEM) {
+            if constexpr (A::kKind == kArD) {
+                o0[(size_t)k * NP] = (uint64_t)A::canon(s0a[sidx<sizeof(T)>(abase + k)], c);
+                o1[(size_t)k * NP] = (uint64_t)A::canon(s1a[sidx<sizeof(T)>(abase + k)], c);
+            } else if constexpr (ACC_SMEM) {
                 o0[(size_t)k * NP] = s0a[sidx<sizeof(T)>(abase + k)];
                 o1[(size_t)k * NP] = s1a[sidx<sizeof(T)>(abase + k)];
             } else {
@@ -445,7 +455,7 @@ template <class A, int CS, bool A1>
 static int inner_launch2(Ctx *c, const KsBatch &b, BaseConv *ks, const TgtSel &sel, cudaStream_t st) {
     const int logN = c->logN, logS = logN - CS, S = 1 << logS;
     const PassPlan plan = make_pass_plan(logS - kLastR);
-    const size_t smem = (A::kKind == kArW ? 3 : 1) * ntt_smem_elems(S) * sizeof(typename A::T);
+    const size_t smem = ((A::kKind == kArW || A::kKind == kArD) ? 3 : 1) * ntt_smem_elems(S) * sizeof(typename A::T);
     dim3 g(sel.n << CS, b.nct);
     SFG_CUDA(c, cudaFuncSetAttribute(k_ks_inner2<A, CS, A1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_ks_inner2<A, CS, A1><<<g, ntt_threads(S), smem, st>>>(b.in, b.in_off, b.in_nl, b.c2, b.c2_slot, b.keys, ks, b.level, c->nQ, c->nP, logN, plan,
@@ -482,13 +492,13 @@ static int moddown_launch(Ctx *c, const KsBatch &b, BaseConv *md, uint64_t *pinv
 static int rotate_chunk(Ctx *c, const KsBatch &b, BaseConv *ks, BaseConv *md, uint64_t *pinv, cudaStream_t st, bool moddown = true) {
     const int N = c->N, nl = b.level + 1, nt = nl + c->nP;
     // 2. inner products with the switching keys, one launch per arithmetic class of the target modulus
-    TgtSel ts[3] = {{0, {}}, {0, {}}, {0, {}}};
+    TgtSel ts[kNumArith] = {{0, {}}, {0, {}}, {0, {}}, {0, {}}};
     for (int tt = 0; tt < nt; tt++) {
         const int tgt = tt < nl ? tt : c->nQ + (tt - nl);
         TgtSel &t = ts[arith_kind(c->mod[tgt])];
         t.tt[t.n++] = tt;
     }
-    if (inner_launch<ArW>(c, b, ks, ts[kArW], st) || inner_launch<ArN30>(c, b, ks, ts[kArN30], st) || inner_launch<ArN31>(c, b, ks, ts[kArN31], st))
+    if (inner_launch<ArW>(c, b, ks, ts[kArW], st) || inner_launch<ArD>(c, b, ks, ts[kArD], st) || inner_launch<ArN30>(c, b, ks, ts[kArN30], st) || inner_launch<ArN31>(c, b, ks, ts[kArN31], st))
         return -1;
     // 3. INTT of the P limbs of acc (TT order in, natural order out, in place): groups = (ct, comp)
     LimbSel selp;
@@ -499,12 +509,12 @@ static int rotate_chunk(Ctx *c, const KsBatch &b, BaseConv *ks, BaseConv *md, ui
         return -1;
     if (!moddown) return 0;
     // 4. mod-down, + c0, automorphism, store / accumulate
-    TgtSel ls[3] = {{0, {}}, {0, {}}, {0, {}}};
+    TgtSel ls[kNumArith] = {{0, {}}, {0, {}}, {0, {}}, {0, {}}};
     for (int l = 0; l < b.out_layout.nl; l++) {
         TgtSel &t = ls[arith_kind(c->mod[l])];
         t.tt[t.n++] = l;
     }
-    if (moddown_launch<ArW>(c, b, md, pinv, ls[kArW], st) || moddown_launch<ArN30>(c, b, md, pinv, ls[kArN30], st) ||
+    if (moddown_launch<ArW>(c, b, md, pinv, ls[kArW], st) || moddown_launch<ArD>(c, b, md, pinv, ls[kArD], st) || moddown_launch<ArN30>(c, b, md, pinv, ls[kArN30], st) ||
         moddown_launch<ArN31>(c, b, md, pinv, ls[kArN31], st))
         return -1;
     return 0;
@@ -609,12 +619,13 @@ int launch_rotate_sum_final(Ctx *c, int level, int nout, const uint64_t *S1, con
     if (ctx_get_ks_tables(c, level, &ks, &md, &pinv)) return -1;
     for (int l = 0; l < olay.nl; l++)
         if (olay.es[l] != 8) SFG_FAIL(c, "rotate_sum_final writes the u64 layout only");
-    TgtSel ls[3] = {{0, {}}, {0, {}}, {0, {}}};
+    TgtSel ls[kNumArith] = {{0, {}}, {0, {}}, {0, {}}, {0, {}}};
     for (int l = 0; l < olay.nl; l++) {
         TgtSel &t = ls[arith_kind(c->mod[l])];
         t.tt[t.n++] = l;
     }
     if (md_final_launch<ArW>(c, level, nout, S1, C0, E, pinv, out, out_off, olay, ls[kArW], st) ||
+        md_final_launch<ArD>(c, level, nout, S1, C0, E, pinv, out, out_off, olay, ls[kArD], st) ||
         md_final_launch<ArN30>(c, level, nout, S1, C0, E, pinv, out, out_off, olay, ls[kArN30], st) ||
         md_final_launch<ArN31>(c, level, nout, S1, C0, E, pinv, out, out_off, olay, ls[kArN31], st))
         return -1;

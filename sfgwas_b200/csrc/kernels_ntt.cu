@@ -150,7 +150,7 @@ int launch_ntt_gather(Ctx *c, const uint64_t *src, const long long *src_off, siz
         if (src_off || in_tt) SFG_FAIL(c, "gathered / TT transforms support logN <= 14 (got %d)", c->logN);
         return launch_ntt_old(c, src, src_gstride, dst, dst_gstride, npoly, sel, inverse, st);
     }
-    SubSel sub[3] = {{0, {}, {}}, {0, {}, {}}, {0, {}, {}}};
+    SubSel sub[kNumArith] = {{0, {}, {}}, {0, {}, {}}, {0, {}, {}}, {0, {}, {}}};
     for (int k = 0; k < sel.n; k++) {
         SubSel &s = sub[arith_kind(c->mod[sel.idx[k]])];
         s.pos[s.n] = k;
@@ -158,6 +158,7 @@ int launch_ntt_gather(Ctx *c, const uint64_t *src, const long long *src_off, siz
     }
     const int ngroups = npoly / sel.n;
     if (ntt2_launch<ArW>(c, src, src_off, src_gstride, dst, dst_gstride, ngroups, sub[kArW], inverse, in_tt, st)) return -1;
+    if (ntt2_launch<ArD>(c, src, src_off, src_gstride, dst, dst_gstride, ngroups, sub[kArD], inverse, in_tt, st)) return -1;
     if (ntt2_launch<ArN30>(c, src, src_off, src_gstride, dst, dst_gstride, ngroups, sub[kArN30], inverse, in_tt, st)) return -1;
     if (ntt2_launch<ArN31>(c, src, src_off, src_gstride, dst, dst_gstride, ngroups, sub[kArN31], inverse, in_tt, st)) return -1;
     return 0;

@@ -14,6 +14,10 @@
 //   ArW   q < 2^62 : u64, Shoup multiplication with 64-bit companions, lazy forward butterflies (no conditional subtraction:
 //                    values grow by 2q per stage and fit 64 bits for q < 2^57; larger q fall back to Harvey's [0, 4q) form),
 //                    Harvey [0, 2q) inverse butterflies.                                  ~16 FMA-pipe slots per butterfly
+//   ArD   q < 2^45 : residues kept as exact integers in FP64 (the 64 lanes/clk FP64 pipe is otherwise idle): product by a twiddle
+//                    = DMUL + DFMA (exact two-product), quotient by the magic-number round, remainder by DFMA; values stay in
+//                    (-q, q) after a multiplication and grow by q per forward stage, so no conditional corrections at all.
+//                                                                                        8 FP64 ops per forward butterfly
 //   ArN30 q < 2^30 : u32, 32-bit Shoup, Harvey lazy butterflies in [0, 4q) / [0, 2q).      3 IMAD + 4 ALU per butterfly
 //   ArN31 q < 2^31 : u32, canonical butterflies (4q does not fit 32 bits).                 3 IMAD + 8 ALU per butterfly
 #pragma once
@@ -21,8 +25,10 @@
 
 namespace sfg {
 
-enum ArithKind : int { kArW = 0, kArN30 = 1, kArN31 = 2 };
-__host__ __device__ inline int arith_kind(uint64_t q) { return q < (1ULL << 30) ? kArN30 : (q < (1ULL << 31) ? kArN31 : kArW); }
+enum ArithKind : int { kArW = 0, kArN30 = 1, kArN31 = 2, kArD = 3, kNumArith = 4 };
+__host__ __device__ inline int arith_kind(uint64_t q) {
+    return q < (1ULL << 30) ? kArN30 : (q < (1ULL << 31) ? kArN31 : (q < (1ULL << 45) ? kArD : kArW));
+}
 
 // Stages per pass: at most kLastR = 4 (16 coefficients in registers per thread).
 constexpr int kLastR = 4;
@@ -90,6 +96,58 @@ struct ArW {
     }
     __device__ static __forceinline__ T from_canon(uint64_t x, const C &) { return x; }  // residue of THIS modulus
     __host__ static TW make_tw(uint64_t w, uint64_t q) { return make_ulonglong2(w, h_shoup(w, q)); }
+};
+
+struct ArD {
+    using T = double;
+    using TW = double;  // w, plain residue
+    static constexpr int kKind = kArD;
+    struct C {
+        double q, qinv, ninv;
+        uint64_t q64, bred_hi;
+        int red_inv;  // inverse butterflies: reduce the sum at every stage (q * N would leave the exact-integer range otherwise)
+    };
+    __device__ static __forceinline__ C make(const LimbConst &lc) {
+        return C{(double)lc.q, 1.0 / (double)lc.q, (double)lc.ninv, lc.q, lc.bred_hi, lc.q >= (1ULL << 34)};
+    }
+    // x mod q in (-q, q) (|x| < 2^50): nearest-integer quotient by the 1.5 * 2^52 magic constant, exact remainder by FMA
+    __device__ static __forceinline__ T red(T x, const C &c) {
+        const double k = __fma_rn(x, c.qinv, 6755399441055744.0) - 6755399441055744.0;
+        return __fma_rn(-k, c.q, x);
+    }
+    // y * w mod q in (-q, q) for integer-valued |y| < 2^50, 0 <= w < q: (h, l) is the exact product
+    __device__ static __forceinline__ T mul_lazy(T y, TW w, const C &c) {
+        const double h = y * w;
+        const double l = __fma_rn(y, w, -h);
+        const double k = __fma_rn(h, c.qinv, 6755399441055744.0) - 6755399441055744.0;
+        return __fma_rn(-k, c.q, h) + l;
+    }
+    __device__ static __forceinline__ T load_u64(uint64_t x, const C &c) {  // any 64-bit value
+        if (x >= (1ULL << 49)) x -= __umul64hi(x, c.bred_hi) * c.q64;
+        return (double)(long long)x;
+    }
+    __device__ static __forceinline__ void fwd(T &x, T &y, TW w, const C &c) {
+        const T v = mul_lazy(y, w, c);
+        y = x - v;
+        x = x + v;
+    }
+    __device__ static __forceinline__ void inv(T &x, T &y, TW w, const C &c) {
+        T u = x + y;
+        const T d = x - y;
+        if (c.red_inv) u = red(u, c);
+        y = mul_lazy(d, w, c);
+        x = u;
+    }
+    __device__ static __forceinline__ T canon(T x, const C &c) {  // -> [0, q)
+        const T r = red(x, c);
+        return r < 0.0 ? r + c.q : r;
+    }
+    __device__ static __forceinline__ T inv_final(T x, const C &c) {
+        const T r = mul_lazy(x, c.ninv, c);
+        return r < 0.0 ? r + c.q : r;
+    }
+    __device__ static __forceinline__ T from_canon(uint64_t x, const C &) { return (double)(long long)x; }
+    __host__ static TW make_tw(uint64_t w, uint64_t) { return (double)w; }
 };
 
 struct ArN30 {
