@@ -1,3 +1,5 @@
+// NOT BUILT: the round-1 IMAD.WIDE multiply-accumulate kernel that k_mac_tc (sfgwas_b200/csrc/kernels_mactc.cu) replaced; kept as the
+// design record behind profiles/r1_baseline (89.8 ms on config 2 vs 13.4 ms on the tensor cores).
 // kernels_mac.cu -- the dominant kernel: output-stationary lazy multiply-accumulate of rotated ciphertext residues with
 // NTT-domain plaintext diagonals, fused with the modular reduce (K1 + K2 of SURVEY 2.2; gwas/matmult.go:247-324,
 // 343-399, 1154-1168).

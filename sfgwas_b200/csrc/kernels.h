@@ -53,12 +53,6 @@ struct EncJob {
 int launch_encode(Ctx *c, const int8_t *X, size_t ld, const EncJob *jobs_dev, int njobs, const PolyLayout &lay, bool mont, void *out,
                   long long *coeff_out /* optional [njobs][N] int64 coefficient-domain message, may be null */, cudaStream_t st);
 
-// ---- output-stationary MAC + Montgomery reduce (kernels_mac.cu) ----
-// R: rotation cache, record (k*nrows + row) of layout `lay`; P: plaintext diagonal records of the same layout, record index
-// pidx[col*K + k] (-1 = nil);  cv: [ncols][nrows][lay.nl][N] canonical uint64 residues.
-int launch_mac(Ctx *c, const void *R, const void *P, const int *pidx, int K, int nrows, int ncols, const PolyLayout &lay,
-               uint64_t *cv, cudaStream_t st);
-
 // ---- tensor-core MAC (kernels_mactc.cu): byte-plane images + tcgen05 kind::i8 contraction ----
 constexpr int kTcLimbs = 8;
 struct TcGeomP {                 // geometry of the plaintext-diagonal image (fixed at preprocess time)

@@ -1,0 +1,150 @@
+"""Multi-GPU sharding of the MatMult hot path on one box: one process per GPU, torch.distributed for the plumbing.
+
+Two shardings, both bit-identical to the single-GPU result:
+
+* ``ColumnSharded`` -- SNP-block (= block-column) sharding for Q.X-shaped products with X = nind x nsnp: rank r owns a contiguous
+  range of block columns; every accumulator (i, giant, bj), its reduce, its giant rotations and the final add are independent
+  across bj, so there is NO data-path collective (weak scaling; this is what ``bench.py --gpus N`` measures).  ``gather()`` is an
+  optional all-gather of the finished output ciphertexts.
+
+* ``RowSharded`` -- block-row sharding: rank r multiplies only the block rows [bi_lo, bi_hi) (its baby rotations and its part of
+  the K loop).  Partial sums must be combined BEFORE the giant-step rotations (key-switching is not bit-linear), i.e. between K2
+  and K6: an integer SUM all-reduce of canonical residues (at most 2^8 ranks of residues < 2^56 fit a u64 -- NCCL ``ncclSum`` on
+  int64 is exactly that) followed by one ``mod q`` pass (``sfg_cv_mod_reduce``), then every rank rotates and adds its own range
+  of giant steps (``sfg_matmult4_finish``) and the per-rank outputs are summed the same way.
+  In this round every rank still builds the diagonal cache of the whole matrix (the partial entry point masks the other block
+  rows out of the R operand); a per-rank cache of only its block rows is the next step.
+
+Reference context: the reference has no intra-box parallelism beyond goroutines (gwas/matmult.go:983-1036, 1138-1169); the
+cross-party sum stays in Go (mpc/aggregate.go:466-500).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Sequence, Tuple
+
+import numpy as np
+
+from .gwas import CryptoParams, DiagCache, GenoFileStream, MatMult4StreamCompute, MatMult4StreamPreprocess, SfgError, _p
+
+
+def partition(n: int, world: int) -> List[Tuple[int, int]]:
+    """Contiguous, balanced ranges [lo, hi) of n units over `world` ranks (the first n % world ranks get one more)."""
+    if world < 1:
+        raise ValueError("world must be >= 1")
+    base, extra = divmod(n, world)
+    out, lo = [], 0
+    for r in range(world):
+        hi = lo + base + (1 if r < extra else 0)
+        out.append((lo, hi))
+        lo = hi
+    return out
+
+
+def mod_allreduce_(t, moduli: Sequence[int], N: int, group=None, cps: CryptoParams = None, cache: DiagCache = None, s: int = 0,
+                   max_level: int = 0):
+    """In-place modular sum over ranks of a tensor of canonical residues laid out [..., L, N] (int64 view of u64).
+
+    Integer SUM all-reduce + one canonicalisation pass.  CUDA tensors are reduced by NCCL and canonicalised by the library
+    (``sfg_cv_mod_reduce``); CPU tensors (gloo, tests) are canonicalised with torch ops.
+    """
+    import torch
+    import torch.distributed as dist
+
+    L = len(moduli)
+    world = dist.get_world_size(group)
+    if max(moduli) * world >= 1 << 63:
+        raise SfgError("sum of %d residues may overflow int64 for a %d-bit modulus" % (world, max(moduli).bit_length()))
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    if t.is_cuda:
+        if cps is None or cache is None:
+            raise SfgError("CUDA tensors need the context and cache handles for the canonicalisation pass")
+        torch.cuda.current_stream().synchronize()
+        cps._check(cps.L.sfg_cv_mod_reduce(cps.h, cache.h, s, max_level, C.c_void_p(t.data_ptr()), 0, t.numel()), "sfg_cv_mod_reduce")
+    else:
+        v = t.view(-1, L, N)
+        for l, q in enumerate(moduli):
+            v[:, l, :] %= q
+    return t
+
+
+class ColumnSharded:
+    """SNP-block sharding: rank `rank` of `world` owns block columns [c_lo, c_hi) of the genotype matrix."""
+
+    def __init__(self, cps: CryptoParams, X_local_cols: np.ndarray, ncols_total: int, rank: int, world: int, max_level: int = 5):
+        self.cps, self.rank, self.world, self.max_level = cps, rank, world, max_level
+        self.m_ct_total = (ncols_total - 1) // cps.slots + 1
+        self.ranges = partition(self.m_ct_total, world)
+        lo, hi = self.ranges[rank]
+        want = min(hi * cps.slots, ncols_total) - lo * cps.slots
+        if hi > lo and X_local_cols.shape[1] != want:
+            raise SfgError("rank %d owns %d columns, got %d" % (rank, want, X_local_cols.shape[1]))
+        self.empty = hi <= lo
+        if not self.empty:
+            self.gfs = GenoFileStream.from_matrix(cps, X_local_cols)
+            self.cache = MatMult4StreamPreprocess(cps, self.gfs, max_level)
+
+    @staticmethod
+    def local_columns(ncols_total: int, slots: int, rank: int, world: int) -> Tuple[int, int]:
+        m_ct = (ncols_total - 1) // slots + 1
+        lo, hi = partition(m_ct, world)[rank]
+        return min(lo * slots, ncols_total), min(hi * slots, ncols_total)
+
+    def compute(self, A: np.ndarray) -> np.ndarray:
+        """out[:, c_lo:c_hi] of MatMult4StreamCompute(A, X): [s][hi-lo][2][maxLevel][N]."""
+        if self.empty:
+            return np.zeros((A.shape[0], 0, 2, self.max_level, self.cps.N), dtype=np.uint64)
+        return MatMult4StreamCompute(self.cps, A, self.max_level, self.cache)
+
+    def gather(self, out_local: np.ndarray, group=None) -> np.ndarray:
+        """All ranks get the full [s][m_ct][2][maxLevel][N] output (all-gather of equal-sized padded pieces)."""
+        import torch
+        import torch.distributed as dist
+
+        s = out_local.shape[0]
+        width = max(hi - lo for lo, hi in self.ranges)
+        dev = torch.device("cuda", self.cps.device) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+        piece = torch.zeros((s, width, 2, self.max_level, self.cps.N), dtype=torch.int64, device=dev)
+        if out_local.shape[1]:
+            piece[:, : out_local.shape[1]] = torch.from_numpy(out_local.view(np.int64)).to(dev)
+        pieces = [torch.empty_like(piece) for _ in range(self.world)]
+        dist.all_gather(pieces, piece, group=group)
+        full = np.zeros((s, self.m_ct_total, 2, self.max_level, self.cps.N), dtype=np.uint64)
+        for r, (lo, hi) in enumerate(self.ranges):
+            full[:, lo:hi] = pieces[r][:, : hi - lo].cpu().numpy().view(np.uint64)
+        return full
+
+
+class RowSharded:
+    """Block-row sharding with a modular-add all-reduce between the MAC (K1 + K2) and the giant-step rotations (K6)."""
+
+    def __init__(self, cps: CryptoParams, X: np.ndarray, rank: int, world: int, max_level: int = 5):
+        self.cps, self.rank, self.world, self.max_level = cps, rank, world, max_level
+        self.gfs = GenoFileStream.from_matrix(cps, X)
+        self.cache = MatMult4StreamPreprocess(cps, self.gfs, max_level)
+        self.row_ranges = partition(self.cache.num_block_rows, world)
+
+    def compute(self, A: np.ndarray, group=None) -> np.ndarray:
+        import torch
+        import torch.distributed as dist
+
+        cps, L = self.cps, self.cps.L
+        A = np.ascontiguousarray(A, dtype=np.uint64)
+        s, nbr, _, nlA, _ = A.shape
+        dev = torch.device("cuda", cps.device)
+        n_cv = int(L.sfg_cv_elems(cps.h, self.cache.h, s, self.max_level))
+        cv = torch.empty(n_cv, dtype=torch.int64, device=dev)
+        lo, hi = self.row_ranges[self.rank]
+        cps._check(L.sfg_matmult4_partial(cps.h, _p(A), s, nbr, nlA - 1, self.max_level, self.cache.h, lo, hi, C.c_void_p(cv.data_ptr())),
+                   "sfg_matmult4_partial")
+        moduli = cps.Q[: self.max_level]
+        mod_allreduce_(cv, moduli, cps.N, group, cps, self.cache, s, self.max_level)
+        per_g = self.cache.m_ct * 2 * s * self.max_level * cps.N
+        ng = n_cv // per_g
+        g_lo, g_hi = partition(ng, self.world)[self.rank]
+        out = np.zeros((s, self.cache.m_ct, 2, self.max_level, cps.N), dtype=np.uint64)
+        cps._check(L.sfg_matmult4_finish(cps.h, self.cache.h, s, self.max_level, C.c_void_p(cv.data_ptr()), g_lo, g_hi, _p(out)),
+                   "sfg_matmult4_finish")
+        t = torch.from_numpy(out.view(np.int64)).to(dev)
+        mod_allreduce_(t, moduli, cps.N, group, cps, self.cache, s, self.max_level)
+        return t.cpu().numpy().view(np.uint64)

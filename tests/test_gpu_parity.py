@@ -432,3 +432,62 @@ def test_linearity_property_full_size_pn13():
     o.cache_free(dc)
     assert (out == want).all()
     cps.close()
+
+
+@pytest.mark.gpu
+def test_many_block_rows_multiple_k_groups(small13):
+    """17 block rows -> K = 17*d = 272 > 256 baby-step slots: the tensor-core MAC runs 2 K groups and accumulates mod q."""
+    from sfgwas_b200 import GenoFileStream, MatMult4StreamCompute, MatMult4StreamPreprocess
+
+    o, cps, sk, keys = small13
+    rng = np.random.default_rng(17)
+    nr, nc, s = 16 * o.slots + 9, 40, 2
+    X = rng.integers(0, 3, (nr, nc)).astype(np.int8)
+    A = enc_matrix(o, sk, rng.normal(size=(s, nr)))
+    cache = MatMult4StreamPreprocess(cps, GenoFileStream.from_matrix(cps, X), 5)
+    out = MatMult4StreamCompute(cps, A, 5, cache)
+    dc = o.preprocess(X, 5, nproc=8)
+    want = o.compute(A, dc, keys, 5, nproc=8)
+    o.cache_free(dc)
+    assert (out == want).all()
+
+
+@pytest.mark.gpu
+def test_partial_mod_reduce_finish_equals_compute(small13):
+    """The multi-GPU pieces on one GPU: partial sums per block-row range, integer sum + mod q, giant ranges, modular output sum."""
+    import ctypes as C
+
+    import torch
+
+    from sfgwas_b200 import GenoFileStream, MatMult4StreamCompute, MatMult4StreamPreprocess
+    from sfgwas_b200.gwas import _p
+
+    o, cps, sk, keys = small13
+    rng = np.random.default_rng(23)
+    nr, nc, s = 600, 300, 2
+    X = rng.integers(0, 3, (nr, nc)).astype(np.int8)
+    A = enc_matrix(o, sk, rng.normal(size=(s, nr)))
+    cache = MatMult4StreamPreprocess(cps, GenoFileStream.from_matrix(cps, X), 5)
+    single = MatMult4StreamCompute(cps, A, 5, cache)
+    L = cps.L
+    nbr = A.shape[1]
+    n_cv = int(L.sfg_cv_elems(cps.h, cache.h, s, 5))
+    dev = torch.device("cuda", cps.device)
+    parts = []
+    for lo, hi in ((0, 1), (1, nbr)):
+        cv = torch.empty(n_cv, dtype=torch.int64, device=dev)
+        cps._check(L.sfg_matmult4_partial(cps.h, _p(A), s, nbr, 5, 5, cache.h, lo, hi, C.c_void_p(cv.data_ptr())), "partial")
+        parts.append(cv)
+    cv = parts[0] + parts[1]
+    torch.cuda.synchronize()
+    cps._check(L.sfg_cv_mod_reduce(cps.h, cache.h, s, 5, C.c_void_p(cv.data_ptr()), 0, n_cv), "mod_reduce")
+    per_g = cache.m_ct * 2 * s * 5 * cps.N
+    ng = n_cv // per_g
+    total = np.zeros(single.shape, dtype=object)
+    for g_lo, g_hi in ((0, ng // 2), (ng // 2, ng)):
+        out = np.zeros(single.shape, dtype=np.uint64)
+        cps._check(L.sfg_matmult4_finish(cps.h, cache.h, s, 5, C.c_void_p(cv.data_ptr()), g_lo, g_hi, _p(out)), "finish")
+        total = total + out.astype(object)
+    for l in range(5):
+        total[:, :, :, l, :] %= cps.Q[l]
+    assert (total.astype(np.uint64) == single).all()
