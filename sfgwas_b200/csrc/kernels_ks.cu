@@ -76,7 +76,7 @@ int launch_key_convert(Ctx *c, const uint64_t *in, uint64_t *out, cudaStream_t s
 // both accumulators in REGISTERS for the whole digit loop (the last forward pass delivers exactly those).  A1: nP == 1 (every
 // digit is a single modulus: plain reduction of the representative, Lattigo DecomposeAndSplit).
 template <class A, int CS, bool A1>
-__global__ void __launch_bounds__(512, 1)
+__global__ void __launch_bounds__(512, A::kMinBlocks)
 k_ks_inner2(const uint64_t *__restrict__ in, const long long *__restrict__ in_off, int in_nl, const uint64_t *__restrict__ c2,
             const int *__restrict__ c2_slot, const uint64_t *const *__restrict__ keys, const BaseConv *__restrict__ ks, int level, int nQ,
             int nP, int logN, PassPlan plan, const TwTab *__restrict__ tabs, const LimbConst *__restrict__ lcs, uint64_t *__restrict__ accout,
@@ -100,7 +100,7 @@ k_ks_inner2(const uint64_t *__restrict__ in, const long long *__restrict__ in_of
     const int NP = N >> kLastR;
 
     // accumulators: registers for the 32-bit classes; thread-private shared-memory slots for the 64-bit class (register budget)
-    constexpr bool ACC_SMEM = A::kKind == kArW || A::kKind == kArD;
+    constexpr bool ACC_SMEM = true;  // thread-private shared-memory slots: keeps every class within its register budget
     constexpr int NREG = ACC_SMEM ? 1 : kLastE;
     T a0[NREG], a1[NREG];
     T *s0a = s + S, *s1a = s0a + S;
@@ -124,18 +124,19 @@ k_ks_inner2(const uint64_t *__restrict__ in, const long long *__restrict__ in_of
                 const int sj = sidx<sizeof(T)>(abase + k);
                 s0a[sj] += A::mul_lazy(v, __ldg(reinterpret_cast<const double *>(k0) + (size_t)k * NP), c);
                 s1a[sj] += A::mul_lazy(v, __ldg(reinterpret_cast<const double *>(k1) + (size_t)k * NP), c);
-            } else if constexpr (ACC_SMEM) {
+            } else if constexpr (A::kKind == kArW) {
                 const int sj = sidx<sizeof(T)>(abase + k);
                 s0a[sj] = add_mod(s0a[sj], mred(v, __ldg(k0 + (size_t)k * NP), lc), lc.q);
                 s1a[sj] = add_mod(s1a[sj], mred(v, __ldg(k1 + (size_t)k * NP), lc), lc.q);
             } else {
+                const int sj = sidx<sizeof(T)>(abase + k);
                 const uint2 w0 = __ldg(reinterpret_cast<const uint2 *>(k0) + (size_t)k * NP);
                 const uint2 w1 = __ldg(reinterpret_cast<const uint2 *>(k1) + (size_t)k * NP);
                 uint32_t p0 = A::mul_lazy(v, w0, c), p1 = A::mul_lazy(v, w1, c);
-                p0 = min(p0, p0 - c.q) + a0[k];
-                p1 = min(p1, p1 - c.q) + a1[k];
-                a0[k] = min(p0, p0 - c.q);
-                a1[k] = min(p1, p1 - c.q);
+                p0 = min(p0, p0 - c.q) + s0a[sj];
+                p1 = min(p1, p1 - c.q) + s1a[sj];
+                s0a[sj] = min(p0, p0 - c.q);
+                s1a[sj] = min(p1, p1 - c.q);
             }
         };
         const int ns = bc.ns;
@@ -192,7 +193,7 @@ k_ks_inner2(const uint64_t *__restrict__ in, const long long *__restrict__ in_of
 
 // ---- 4. mod-down, + c0, automorphism, store / accumulate ---------------------------------------------------------------------
 template <class A, bool A1>
-__global__ void __launch_bounds__(512, 1)
+__global__ void __launch_bounds__(512, A::kMinBlocks)
 k_ks_moddown2(const uint64_t *__restrict__ in, const long long *__restrict__ in_off, int in_nl, const uint64_t *__restrict__ acc,
               const BaseConv *__restrict__ md, const uint64_t *__restrict__ pinv, const uint32_t *const *__restrict__ perms, int level,
               int nQ, int nP, int logN, PassPlan plan, const TwTab *__restrict__ tabs, const LimbConst *__restrict__ lcs,
@@ -401,7 +402,7 @@ k_md_accum(const uint64_t *__restrict__ in, const long long *__restrict__ in_off
 }
 
 template <class A>
-__global__ void __launch_bounds__(512, 1)
+__global__ void __launch_bounds__(512, A::kMinBlocks)
 k_md_final(const uint64_t *__restrict__ S1, const uint64_t *__restrict__ C0, const uint64_t *__restrict__ E, const uint64_t *__restrict__ pinv,
            int logN, PassPlan plan, const TwTab *__restrict__ tabs, const LimbConst *__restrict__ lcs, unsigned char *__restrict__ out,
            const long long *__restrict__ out_off, PolyLayout olay, int L, TgtSel sel) {
@@ -455,7 +456,7 @@ template <class A, int CS, bool A1>
 static int inner_launch2(Ctx *c, const KsBatch &b, BaseConv *ks, const TgtSel &sel, cudaStream_t st) {
     const int logN = c->logN, logS = logN - CS, S = 1 << logS;
     const PassPlan plan = make_pass_plan(logS - kLastR);
-    const size_t smem = ((A::kKind == kArW || A::kKind == kArD) ? 3 : 1) * ntt_smem_elems(S) * sizeof(typename A::T);
+    const size_t smem = 3 * ntt_smem_elems(S) * sizeof(typename A::T);
     dim3 g(sel.n << CS, b.nct);
     SFG_CUDA(c, cudaFuncSetAttribute(k_ks_inner2<A, CS, A1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_ks_inner2<A, CS, A1><<<g, ntt_threads(S), smem, st>>>(b.in, b.in_off, b.in_nl, b.c2, b.c2_slot, b.keys, ks, b.level, c->nQ, c->nP, logN, plan,

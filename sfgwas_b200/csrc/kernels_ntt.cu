@@ -81,7 +81,7 @@ struct SubSel {  // the polynomials of a group that belong to one arithmetic cla
 };
 
 template <class A>
-__global__ void __launch_bounds__(512, 1)
+__global__ void __launch_bounds__(512, A::kMinBlocks)
 k_ntt2_fwd(const uint64_t *__restrict__ src, const long long *__restrict__ src_off, size_t src_gstride, uint64_t *__restrict__ dst,
            size_t dst_gstride, SubSel sub, int logN, PassPlan plan, const TwTab *__restrict__ tabs, const LimbConst *__restrict__ lcs) {
     using T = typename A::T;
@@ -98,7 +98,7 @@ k_ntt2_fwd(const uint64_t *__restrict__ src, const long long *__restrict__ src_o
 }
 
 template <class A>
-__global__ void __launch_bounds__(512, 1)
+__global__ void __launch_bounds__(512, A::kMinBlocks)
 k_ntt2_inv(const uint64_t *__restrict__ src, const long long *__restrict__ src_off, size_t src_gstride, uint64_t *__restrict__ dst,
            size_t dst_gstride, SubSel sub, int logN, PassPlan plan, const TwTab *__restrict__ tabs, const LimbConst *__restrict__ lcs, int in_tt) {
     using T = typename A::T;

@@ -61,6 +61,7 @@ inline PassPlan make_pass_plan(int nstages /* = logS - kLastR >= 0 */) {
 // arithmetic policies
 // ---------------------------------------------------------------------------------------------------------------
 struct ArW {
+    static constexpr int kMinBlocks = 1;
     using T = uint64_t;
     using TW = ulonglong2;  // (w, floor(w 2^64 / q))
     static constexpr int kKind = kArW;
@@ -99,6 +100,7 @@ struct ArW {
 };
 
 struct ArD {
+    static constexpr int kMinBlocks = 1;
     using T = double;
     using TW = double;  // w, plain residue
     static constexpr int kKind = kArD;
@@ -151,6 +153,7 @@ struct ArD {
 };
 
 struct ArN30 {
+    static constexpr int kMinBlocks = 2;  // 32-bit classes: 64 registers per thread -> two 512-thread CTAs per SM
     using T = uint32_t;
     using TW = uint2;  // (w, floor(w 2^32 / q))
     static constexpr int kKind = kArN30;
@@ -191,6 +194,7 @@ struct ArN30 {
 };
 
 struct ArN31 {
+    static constexpr int kMinBlocks = 2;
     using T = uint32_t;
     using TW = uint2;
     static constexpr int kKind = kArN31;
