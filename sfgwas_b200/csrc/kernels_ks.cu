@@ -142,7 +142,14 @@ k_ks_inner2(const uint64_t *__restrict__ in, const long long *__restrict__ in_of
         const int ns = bc.ns;
         if (ns == 0) {  // target lies inside the digit: reuse the NTT-domain input limb (decomposeAndSplitNTT)
             const uint64_t *x = c1 + (size_t)tt * N + gbase;
-            for (int j = threadIdx.x; j < S; j += blockDim.x) s[sidx<sizeof(T)>(j)] = A::from_canon(x[j], c);
+            for (int j0 = threadIdx.x; j0 < S; j0 += 8 * blockDim.x) {  // 8 independent loads in flight per thread
+                uint64_t xv[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) xv[u] = (j0 + u * (int)blockDim.x < S) ? __ldg(x + j0 + u * blockDim.x) : 0;
+#pragma unroll
+                for (int u = 0; u < 8; u++)
+                    if (j0 + u * (int)blockDim.x < S) s[sidx<sizeof(T)>(j0 + u * blockDim.x)] = A::from_canon(xv[u], c);
+            }
             __syncthreads();
             if (active) {
 #pragma unroll

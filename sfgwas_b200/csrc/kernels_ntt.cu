@@ -112,7 +112,14 @@ k_ntt2_inv(const uint64_t *__restrict__ src, const long long *__restrict__ src_o
     if (in_tt) {
         ntt_inverse<A>(s, logN, plan, tabs[limb], c, [&](int j, int) { return A::from_canon(in[tt_index(j, N)], c); }, fin);
     } else {
-        for (int j = threadIdx.x; j < N; j += blockDim.x) s[sidx<sizeof(T)>(j)] = A::from_canon(in[j], c);
+        for (int j0 = threadIdx.x; j0 < N; j0 += 8 * blockDim.x) {  // 8 independent loads in flight per thread
+            uint64_t xv[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) xv[u] = (j0 + u * (int)blockDim.x < N) ? __ldg(in + j0 + u * blockDim.x) : 0;
+#pragma unroll
+            for (int u = 0; u < 8; u++)
+                if (j0 + u * (int)blockDim.x < N) s[sidx<sizeof(T)>(j0 + u * blockDim.x)] = A::from_canon(xv[u], c);
+        }
         __syncthreads();
         ntt_inverse<A>(s, logN, plan, tabs[limb], c, [&](int j, int) { return s[sidx<sizeof(T)>(j)]; }, fin);
     }
