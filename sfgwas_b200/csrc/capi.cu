@@ -311,11 +311,11 @@ int sfg_matmult4_stream_compute(sfg_ctx *h, const uint64_t *A, int s, int nbr, i
     SFG_CUDA(c, cudaSetDevice(c->device));
     const size_t abytes = (size_t)s * nbr * 2 * (level_a + 1) * c->N * 8;
     const size_t obytes = (size_t)s * cache->ca->m_ct * 2 * max_level * c->N * 8;
-    Buf dA, dO;
-    if (dA.alloc(c, abytes) || dO.alloc(c, obytes)) return -1;
-    SFG_CUDA(c, cudaMemcpyAsync(dA.p, A, abytes, cudaMemcpyDefault, c->stream));
-    if (mm_compute_dev(c, dA.as<uint64_t>(), s, nbr, level_a, max_level, cache->ca, dO.as<uint64_t>())) return -1;
-    SFG_CUDA(c, cudaMemcpyAsync(out, dO.p, obytes, cudaMemcpyDefault, c->stream));
+    void *dA, *dO;  // grow-only workspace: no cudaMalloc / cudaFree in the steady state
+    if (ws_get(c, WS_A, abytes, &dA) || ws_get(c, WS_OUT, obytes, &dO)) return -1;
+    SFG_CUDA(c, cudaMemcpyAsync(dA, A, abytes, cudaMemcpyDefault, c->stream));
+    if (mm_compute_dev(c, (const uint64_t *)dA, s, nbr, level_a, max_level, cache->ca, (uint64_t *)dO)) return -1;
+    SFG_CUDA(c, cudaMemcpyAsync(out, dO, obytes, cudaMemcpyDefault, c->stream));
     SFG_CUDA(c, cudaStreamSynchronize(c->stream));
     return 0;
 }
