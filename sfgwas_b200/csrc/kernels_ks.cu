@@ -103,7 +103,7 @@ k_ks_inner2(const uint64_t *__restrict__ in, const long long *__restrict__ in_of
     constexpr bool ACC_SMEM = true;  // thread-private shared-memory slots: keeps every class within its register budget
     constexpr int NREG = ACC_SMEM ? 1 : kLastE;
     T a0[NREG], a1[NREG];
-    T *s0a = s + S, *s1a = s0a + S;
+    T *s0a = s + ntt_smem_elems(S), *s1a = s0a + ntt_smem_elems(S);
     const int abase = kLastE * threadIdx.x;
 #pragma unroll
     for (int k = 0; k < kLastE; k++) {

@@ -34,14 +34,15 @@ __host__ __device__ inline int arith_kind(uint64_t q) {
 constexpr int kLastR = 4;
 constexpr int kLastE = 1 << kLastR;
 
-// XOR-swizzled shared-memory index (no padding).  The three access patterns of the passes are conflict-free:
-//   unit stride across lanes (lobits >= 5), 16 lanes x 2 groups (the pass with lobits == 4), and stride 16 (last pass).
+// Padded shared-memory index: one pad element per 32 (4-byte classes) / per 16 (8-byte classes).  Unit stride across lanes and
+// the stride-16 pattern of the last pass are conflict-free; the address costs 2 instructions (an XOR swizzle that also made the
+// 16 x 2 pattern of the lobits == 4 pass conflict-free cost 6 and measured 7 % slower end to end).
 template <int BYTES>
 __device__ __forceinline__ int sidx(int i) {
-    if (BYTES == 8) return i ^ ((i >> 4) & 15);
-    return i ^ (((i >> 5) & 15) | ((__popc((i >> 5) & 15) & 1) << 4));
+    if (BYTES == 8) return i + (i >> 4);
+    return i + (i >> 5);
 }
-__host__ __device__ inline size_t ntt_smem_elems(int S) { return (size_t)S; }
+__host__ __device__ inline size_t ntt_smem_elems(int S) { return (size_t)S + ((size_t)S >> 4) + 32; }
 // "TT" global order of a polynomial of N coefficients: coefficient 16 P + k stored at k * N/16 + P
 __device__ __forceinline__ int tt_index(int idx, int N) { return (idx & (kLastE - 1)) * (N >> kLastR) + (idx >> kLastR); }
 
