@@ -103,6 +103,14 @@ func b200Context(cps *crypto.CryptoParams) *b200Ctx {
 			upload(k * d)
 		}
 	}
+	for k := 1; k < slots; k *= 2 { // power-of-two keys of crypto.InnerSumAll (crypto/crypto.go:232-249), used by lazynorm_b200.go
+		if C.sfg_ctx_has_rotation_key(c.h, C.int(k)) == 0 {
+			upload(k)
+		}
+	}
+	if cps.Rlk != nil {
+		b200UploadRlk(c, cps)
+	}
 	runtime.SetFinalizer(c, func(c *b200Ctx) { C.sfg_ctx_destroy(c.h) })
 	b200Ctxs[cps] = c
 	return c

@@ -114,6 +114,34 @@ int sfg_matmult4_finish(sfg_ctx *ctx, const sfg_cache *cache, int s, int max_lev
 /* out = (a + b) mod q limb-wise on host buffers of ncts ciphertexts [2][nl][N] (combining per-rank partial sums) */
 int sfg_ct_add(sfg_ctx *ctx, const uint64_t *a, const uint64_t *b, int ncts, int nl, uint64_t *out);
 
+/* ---- ciphertext algebra of the callers around the path --------------------------------------------
+ * QXLazyNormStream / QXtLazyNormStream (gwas/matmult.go:27-77,83-116) wrap MatMult4StreamCompute in crypto.CMult, InnerProd,
+ * InnerSumAll, CMultScalar, MaskTrunc and eval.Sub (crypto/basics.go:110-127,236-293,386-427,553-566); the network bootstrap
+ * between them (mpcObj.Network.BootstrapMatAll) stays in Go.  Host buffers; ciphertext k of an operand is [2][nl][N] uint64 with
+ * nl >= level+1 stored limbs (limbs above `level` are ignored = DropLevel); a count of 1 broadcasts like the reference does.
+ * Scale bookkeeping (ct.Scale, the Rescale threshold loop) is metadata and stays with the caller: `nrescale` is the number of
+ * ring.DivRoundByLastModulusNTT steps evaluator.Rescale(ct, params.Scale) performs (1 for two operands at params.Scale). */
+/* relinearisation key cryptoParams.Rlk.Keys[0] (switching key s^2 -> s), same layout as a rotation key */
+int sfg_ctx_set_relin_key(sfg_ctx *ctx, const uint64_t *key);
+int sfg_ctx_set_relin_key_ptrs(sfg_ctx *ctx, const uint64_t *const *limbs /* beta*2*(nQ+nP) pointers */);
+/* crypto.CMult / CMultScalar: out[k] = Rescale^nrescale(eval.MulRelinNew(x[k or 0], y[k or 0])), n = max(nx, ny) results at
+ * level - nrescale, each [2][level+1-nrescale][N] */
+int sfg_ct_mul_relin(sfg_ctx *ctx, int level, const uint64_t *x, int nx, int x_nl, const uint64_t *y, int ny, int y_nl, int nrescale,
+                     uint64_t *out);
+/* eval.MulRelinNew(plaintext, ct) + Rescale (crypto.MaskTrunc): pt k is [pt_nl][N], NTT domain, NOT Montgomery form */
+int sfg_ct_mul_plain(sfg_ctx *ctx, int level, const uint64_t *pt, int npt, int pt_nl, const uint64_t *cts, int nct, int ct_nl, int nrescale,
+                     uint64_t *out);
+/* evaluator.Rescale: nrescale steps of ring.DivRoundByLastModulusNTT on cts [nct][2][level+1][N] -> [nct][2][level+1-nrescale][N] */
+int sfg_ct_rescale(sfg_ctx *ctx, int level, const uint64_t *cts, int nct, int nrescale, uint64_t *out);
+/* eval.Sub / eval.Add on operands of matching scale: out[k] = a[k or 0] -+ b[k or 0] at `level` ([2][level+1][N] each) */
+int sfg_ct_sub(sfg_ctx *ctx, int level, const uint64_t *a, int na, int a_nl, const uint64_t *b, int nb, int b_nl, uint64_t *out);
+int sfg_ct_add2(sfg_ctx *ctx, int level, const uint64_t *a, int na, int a_nl, const uint64_t *b, int nb, int b_nl, uint64_t *out);
+/* crypto.InnerSumAll for nvec vectors of cnt ciphertexts ([nvec][cnt][2][level+1][N]): out [nvec][2][level+1][N]; needs the
+ * power-of-two left-rotation keys 1, 2, 4, .. slots/2 (crypto/crypto.go:232-249) */
+int sfg_inner_sum_all(sfg_ctx *ctx, int level, const uint64_t *cts, int nvec, int cnt, uint64_t *out);
+/* EncodeNTT of an int8 slot vector v[slots] at params.Scale (the 0/1 mask of crypto.MaskTrunc), correctly rounded: out [level+1][N] */
+int sfg_encode_slots_i8(sfg_ctx *ctx, const int8_t *v, int level, int mont, uint64_t *out);
+
 /* synchronise the context's stream (timing helper) */
 int sfg_ctx_sync(sfg_ctx *ctx);
 /* device-resident variant used by bench.py to time the kernels with inputs already in HBM:

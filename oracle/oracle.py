@@ -79,6 +79,10 @@ def lib():
         L.orc_permute_ntt_index.argtypes = [C.c_int, C.c_uint64, vp]
         L.orc_keyswitch.argtypes = [vp, C.c_int, vp, vp, vp, vp]
         L.orc_rotate_right.argtypes = [vp, C.c_int, vp, C.c_int, vp, vp]
+        L.orc_mul_relin.argtypes = [vp, C.c_int, vp, vp, vp, vp]
+        L.orc_mul_plain.argtypes = [vp, C.c_int, vp, vp, vp]
+        L.orc_rescale_once.argtypes = [vp, C.c_int, vp, vp]
+        L.orc_ct_addsub.argtypes = [vp, C.c_int, vp, vp, C.c_int, vp]
         L.orc_matmult4_stream_preprocess.restype = vp
         L.orc_matmult4_stream_preprocess.argtypes = [vp, vp, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int]
         L.orc_diag_cache_free.argtypes = [vp]
@@ -377,6 +381,134 @@ class Oracle:
         out = np.zeros_like(ct)
         self.L.orc_rotate_right(self.ctx, ct.shape[1] - 1, _p(ct), nrot, _p(swk) if swk is not None else None, _p(out))
         return out
+
+    # -- ct x ct / ct x pt algebra of the callers (gwas/matmult.go:27-116, crypto/basics.go) ----------------
+    # A ciphertext is a pair (value [2][level+1][N] uint64, scale float) like *ckks.Ciphertext's Value / Scale.
+    def gen_relin_key(self, sk, seed=13) -> np.ndarray:
+        """Lattigo keygen.GenRelinearizationKey: switching key s^2 -> s, [beta][2][nQP][N], NTT + Montgomery form."""
+        mods = self.Q + self.P
+        sk2 = np.zeros_like(sk)
+        for l in range(self.nQP):
+            v = sk[l].astype(object)
+            sk2[l] = np.array((v * v) % mods[l], dtype=np.uint64)
+        swk = np.zeros((self.beta, 2, self.nQP, self.N), dtype=np.uint64)
+        self.L.orc_gen_switching_key(self.ctx, _p(sk2), _p(np.ascontiguousarray(sk)), seed, _p(swk))
+        return swk
+
+    def pow2_rotations(self):
+        """Left rotations 1, 2, 4, .. < slots that InnerSumAll needs (crypto/crypto.go:232-249)."""
+        return [1 << i for i in range(self.logN - 1)]
+
+    @staticmethod
+    def _at_level(ct, level):
+        return np.ascontiguousarray(ct[:, : level + 1])
+
+    def mul_relin(self, a, b, rlk):
+        """evaluator.MulRelinNew(a, b): level = min level, scale = product."""
+        (va, sa), (vb, sb) = a, b
+        level = min(va.shape[1], vb.shape[1]) - 1
+        out = np.zeros((2, level + 1, self.N), dtype=np.uint64)
+        self.L.orc_mul_relin(self.ctx, level, _p(self._at_level(va, level)), _p(self._at_level(vb, level)), _p(rlk), _p(out))
+        return out, sa * sb
+
+    def mul_plain(self, pt, ct):
+        """evaluator.MulRelinNew(plaintext, ct); pt = (value [nl][N], scale)."""
+        (vp_, sp), (vc, sc) = pt, ct
+        level = min(vp_.shape[0], vc.shape[1]) - 1
+        out = np.zeros((2, level + 1, self.N), dtype=np.uint64)
+        self.L.orc_mul_plain(self.ctx, level, _p(np.ascontiguousarray(vp_[: level + 1])), _p(self._at_level(vc, level)), _p(out))
+        return out, sp * sc
+
+    def rescale(self, ct, threshold=None):
+        """evaluator.Rescale(ct, threshold, ct) (Lattigo v2.1): divide by the last modulus while scale >= threshold*q_level/2."""
+        v, sc = ct
+        threshold = self.scale if threshold is None else threshold
+        while v.shape[1] - 1 > 0 and sc >= threshold * float(self.Q[v.shape[1] - 1]) / 2:
+            level = v.shape[1] - 1
+            out = np.zeros((2, level, self.N), dtype=np.uint64)
+            self.L.orc_rescale_once(self.ctx, level, _p(np.ascontiguousarray(v)), _p(out))
+            v, sc = out, sc / float(self.Q[level])
+        return v, sc
+
+    def addsub(self, a, b, sub=False):
+        """evaluator.Add / Sub for operands whose scales differ by less than a factor 2 (Lattigo v2.1 evaluateInPlace: no
+        scale matching unless floor(ratio) > 1): level = min, scale = max."""
+        (va, sa), (vb, sb) = a, b
+        r = max(sa, sb) / min(sa, sb)
+        assert math.floor(r) <= 1, "scale matching by constant multiplication is not restated"
+        level = min(va.shape[1], vb.shape[1]) - 1
+        out = np.zeros((2, level + 1, self.N), dtype=np.uint64)
+        self.L.orc_ct_addsub(self.ctx, level + 1, _p(self._at_level(va, level)), _p(self._at_level(vb, level)), int(sub), _p(out))
+        return out, max(sa, sb)
+
+    def CMult(self, X, Y, rlk):
+        """crypto.CMult (crypto/basics.go:386-427): element-wise MulRelinNew + Rescale(params.Scale), broadcasting a length-1 side."""
+        n = max(len(X), len(Y))
+        if len(X) == 1:
+            return [self.rescale(self.mul_relin(Y[i], X[0], rlk)) for i in range(len(Y))]
+        if len(Y) == 1:
+            return [self.rescale(self.mul_relin(X[i], Y[0], rlk)) for i in range(len(X))]
+        return [self.rescale(self.mul_relin(X[i], Y[i], rlk)) for i in range(n)]
+
+    def CMultScalar(self, X, ct, rlk):
+        """crypto.CMultScalar (crypto/basics.go:553-566)."""
+        return [self.rescale(self.mul_relin(x, ct, rlk)) for x in X]
+
+    def rotate_left(self, ct, k, keys):
+        v, sc = ct
+        return self.rotate_right(v, self.slots - k, keys[k]), sc
+
+    def InnerSumAll(self, X, keys):
+        """crypto.InnerSumAll (crypto/basics.go:278-293) -> RotateAndAdd (:236-246): sum of the vector's ciphertexts, then
+        ct += RotL_r(ct) for r = 1, 2, 4, .. < slots."""
+        acc = X[0]
+        for x in X[1:]:
+            acc = self.addsub(x, acc)
+        r = 1
+        while r < self.slots:
+            acc = self.addsub(self.rotate_left(acc, r, keys), acc)
+            r *= 2
+        return acc
+
+    def InnerProd(self, X, Y, rlk, keys):
+        return self.InnerSumAll(self.CMult(X, Y, rlk), keys)
+
+    def MaskTrunc(self, ct, n_keep, mask_pt=None):
+        """crypto.MaskTrunc (crypto/basics.go:110-127): keep the first n_keep slots.  mask_pt: NTT-domain plaintext of the 0/1 mask at
+        the maximum level (the reference encodes it with the float64 encoder; here the correctly rounded encoding)."""
+        if n_keep == self.slots:
+            return ct
+        if mask_pt is None:
+            m = np.zeros(self.slots)
+            m[:n_keep] = 1.0
+            mask_pt = self.encode_ntt(m, 0, self.nQ - 1)
+        return self.rescale(self.mul_plain((mask_pt, self.scale), ct))
+
+    def QXLazyNormStream(self, Q, compute, bootstrap, XMean, XStdInv, numInd, rlk, keys):
+        """gwas/matmult.go:27-77.  Q: list of CipherVectors; compute(QS) -> out (MatMult4StreamCompute), bootstrap(out) -> out."""
+        QS = [self.CMult(q, XStdInv, rlk) for q in Q]
+        out = bootstrap(compute(QS))
+        QSm = [self.InnerProd(qs, XMean, rlk, keys) for qs in QS]
+        res = []
+        for i in range(len(QS)):
+            row = []
+            for j in range(len(out[i])):
+                t = self.addsub(out[i][j], QSm[i], sub=True)
+                n = self.slots if j < len(out[i]) - 1 else ((numInd - 1) % self.slots) + 1
+                row.append(self.MaskTrunc(t, n))
+            res.append(row)
+        return res
+
+    def QXtLazyNormStream(self, Q, compute, bootstrap, XMean, XStdInv, rlk, keys):
+        """gwas/matmult.go:83-116."""
+        out = bootstrap(compute(Q))
+        res = []
+        for i in range(len(out)):
+            rowSum = self.InnerSumAll(Q[i], keys)
+            Q1m = self.CMultScalar(XMean, rowSum, rlk)
+            row = [self.addsub(out[i][j], Q1m[j], sub=True) for j in range(len(out[i]))]
+            res.append(self.CMult(row, XStdInv, rlk))
+        return res
 
     # -- hot path ------------------------------------------------------------------------------------
     def bsgs_rotations(self):

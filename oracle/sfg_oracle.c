@@ -990,3 +990,85 @@ double orc_bench_mac(int N, int limbs, int s, int ndiag, int nthreads) {
     free(jobs); free(mux); free(rot); free(pt); free(acc);
     return dt;
 }
+
+/* ------------------------------------------------------------------------------------------ */
+/* ct x ct / ct x pt algebra of the callers around the path:            */
+/* crypto.CMult / CMultScalar / MaskTrunc / InnerSumAll / Sub as used by QXLazyNormStream and    */
+/* QXtLazyNormStream (gwas/matmult.go:27-116, crypto/basics.go:110-127,236-293,386-427,553-566). */
+/* Lattigo v2.1 evaluator.mulRelin / Rescale / ring.DivRoundByLastModulusNTT, [UNVERIFIED vs the  */
+/* fork]: every step is exact arithmetic mod q on canonical residues except the key-switch.       */
+/* ------------------------------------------------------------------------------------------ */
+
+/* evaluator.MulRelinNew(ctA, ctB) for two degree-1 ciphertexts at `level`, relinearised with rlk = swk(s^2 -> s):
+ *   d0 = a0*b0, d1 = a0*b1 + a1*b0, d2 = a1*b1 ; (p0, p1) = switchKeys(d2, rlk) ; out = (d0 + p0, d1 + p1).
+ * The reference multiplies MForm(a) by b with MRed, i.e. the plain modular product. */
+void orc_mul_relin(const orc_ctx *c, int level, const uint64_t *ctA, const uint64_t *ctB, const uint64_t *rlk, uint64_t *out) {
+    int N = c->N, nl = level + 1;
+    size_t PS = (size_t)nl * N;
+    uint64_t *d2 = (uint64_t *)malloc(sizeof(uint64_t) * PS), *p0 = (uint64_t *)malloc(sizeof(uint64_t) * PS), *p1 = (uint64_t *)malloc(sizeof(uint64_t) * PS);
+    for (int l = 0; l < nl; l++) {
+        uint64_t q = c->mod[l], qInv = c->mred[l];
+        for (int j = 0; j < N; j++) {
+            size_t o = (size_t)l * N + j;
+            uint64_t a0 = orc_mform(ctA[o], q, c->bred[l]), a1 = orc_mform(ctA[PS + o], q, c->bred[l]);
+            out[o] = orc_mred(a0, ctB[o], q, qInv);
+            out[PS + o] = addmod(orc_mred(a0, ctB[PS + o], q, qInv), orc_mred(a1, ctB[o], q, qInv), q);
+            d2[o] = orc_mred(a1, ctB[PS + o], q, qInv);
+        }
+    }
+    orc_keyswitch(c, level, d2, rlk, p0, p1);
+    for (int l = 0; l < nl; l++)
+        for (int j = 0; j < N; j++) {
+            size_t o = (size_t)l * N + j;
+            out[o] = addmod(out[o], p0[o], c->mod[l]);
+            out[PS + o] = addmod(out[PS + o], p1[o], c->mod[l]);
+        }
+    free(d2); free(p0); free(p1);
+}
+
+/* evaluator.MulRelinNew(plaintext, ct): both components multiplied by the NTT-domain plaintext (crypto/basics.go:121) */
+void orc_mul_plain(const orc_ctx *c, int level, const uint64_t *pt, const uint64_t *ct, uint64_t *out) {
+    int N = c->N, nl = level + 1;
+    size_t PS = (size_t)nl * N;
+    for (int comp = 0; comp < 2; comp++)
+        for (int l = 0; l < nl; l++)
+            for (int j = 0; j < N; j++) {
+                size_t o = (size_t)l * N + j;
+                out[comp * PS + o] = orc_mred(orc_mform(pt[o], c->mod[l], c->bred[l]), ct[comp * PS + o], c->mod[l], c->mred[l]);
+            }
+}
+
+/* ring.DivRoundByLastModulusNTT on both components: ct [2][level+1][N] -> out [2][level][N]  (one step of evaluator.Rescale):
+ *   t = InvNTT(x_L); t = (t + (qL-1)/2) mod qL; for l < L: z = NTT_l(t - (qL-1)/2 mod q_l); out_l = (x_l - z) * qL^-1 mod q_l */
+void orc_rescale_once(const orc_ctx *c, int level, const uint64_t *ct, uint64_t *out) {
+    int N = c->N, nl = level + 1;
+    uint64_t qL = c->mod[level], half = (qL - 1) >> 1;
+    uint64_t *t = (uint64_t *)malloc(sizeof(uint64_t) * N), *z = (uint64_t *)malloc(sizeof(uint64_t) * N);
+    for (int comp = 0; comp < 2; comp++) {
+        const uint64_t *x = ct + (size_t)comp * nl * N;
+        uint64_t *o = out + (size_t)comp * level * N;
+        memcpy(t, x + (size_t)level * N, sizeof(uint64_t) * N);
+        orc_intt(c, level, t);
+        for (int j = 0; j < N; j++) { t[j] += half; if (t[j] >= qL) t[j] -= qL; }
+        for (int l = 0; l < level; l++) {
+            uint64_t q = c->mod[l];
+            uint64_t halfNeg = q - orc_bred_add(half, q, c->bred[l]);
+            uint64_t inv = invmod(qL % q, q);
+            for (int j = 0; j < N; j++) z[j] = orc_bred_add(t[j] + halfNeg, q, c->bred[l]);
+            orc_ntt(c, l, z);
+            for (int j = 0; j < N; j++) o[(size_t)l * N + j] = mulmod(submod(x[(size_t)l * N + j], z[j], q), inv, q);
+        }
+    }
+    free(t); free(z);
+}
+
+/* evaluator.Add / Sub on equal-scale operands: limb-wise, nl limbs of each of the two components */
+void orc_ct_addsub(const orc_ctx *c, int nl, const uint64_t *a, const uint64_t *b, int sub, uint64_t *out) {
+    int N = c->N;
+    for (int comp = 0; comp < 2; comp++)
+        for (int l = 0; l < nl; l++)
+            for (int j = 0; j < N; j++) {
+                size_t o = ((size_t)comp * nl + l) * N + j;
+                out[o] = sub ? submod(a[o], b[o], c->mod[l]) : addmod(a[o], b[o], c->mod[l]);
+            }
+}

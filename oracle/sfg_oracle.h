@@ -122,6 +122,14 @@ void orc_matmult4_stream(const orc_ctx *c, const uint64_t *A, int s, int levelA,
                          size_t ncols, int maxLevel, int computeSquaredSum, int square,
                          const uint64_t *const *swk_for_rot, int nproc, uint64_t *S, double *sum, double *sqSum);
 
+
+/* ---- ct x ct / ct x pt algebra of the callers (QXLazyNormStream / QXtLazyNormStream, gwas/matmult.go:27-116;
+ *      crypto.CMult / CMultScalar / MaskTrunc / InnerSumAll, crypto/basics.go) -- Lattigo v2.1 mulRelin, Rescale ---- */
+void orc_mul_relin(const orc_ctx *c, int level, const uint64_t *ctA, const uint64_t *ctB, const uint64_t *rlk, uint64_t *out);
+void orc_mul_plain(const orc_ctx *c, int level, const uint64_t *pt, const uint64_t *ct, uint64_t *out);
+void orc_rescale_once(const orc_ctx *c, int level, const uint64_t *ct /* [2][level+1][N] */, uint64_t *out /* [2][level][N] */);
+void orc_ct_addsub(const orc_ctx *c, int nl, const uint64_t *a, const uint64_t *b, int sub, uint64_t *out);
+
 /* pure MAC micro-benchmark used by bench.py cpu_baseline: nthreads, returns seconds */
 double orc_bench_mac(int N, int limbs, int s, int ndiag, int nthreads);
 

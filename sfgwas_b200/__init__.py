@@ -4,5 +4,6 @@ Only what the path needs lives here: ``csrc/`` (CUDA kernels + the C ABI of incl
 host-side mirror of the reference interface (``gwas.py``).  There is no CPU fallback.
 """
 from ._lib import LIB_PATH, SYMBOLS, SfgError, load  # noqa: F401
-from .gwas import (CryptoParams, DiagCache, GenoFileStream, MatMult4Stream, MatMult4StreamCompute,  # noqa: F401
-                   MatMult4StreamPreprocess)
+from .gwas import (CAdd, Ciphertext, CMult, CMultScalar, CryptoParams, CSub, DiagCache, GenoFileStream,  # noqa: F401
+                   InnerProd, InnerSumAll, MaskTrunc, MatMult4Stream, MatMult4StreamCompute, MatMult4StreamPreprocess,
+                   QXLazyNormStream, QXtLazyNormStream, SetRelinKey)

@@ -20,7 +20,9 @@ SYMBOLS = [
     "sfg_geno_destroy", "sfg_encode_diag", "sfg_matmult4_stream_preprocess", "sfg_cache_destroy", "sfg_cache_info",
     "sfg_cache_get_diag", "sfg_matmult4_stream_compute", "sfg_matmult4_stream_compute_ptrs", "sfg_matmult4_stream",
     "sfg_cv_elems", "sfg_matmult4_partial", "sfg_cv_mod_reduce", "sfg_matmult4_finish", "sfg_ct_add", "sfg_ctx_sync",
-    "sfg_matmult4_stream_compute_dev", "sfg_ctx_last_timings", "sfg_ctx_stream",
+    "sfg_matmult4_stream_compute_dev", "sfg_ctx_last_timings", "sfg_ctx_stream", "sfg_ctx_set_relin_key",
+    "sfg_ctx_set_relin_key_ptrs", "sfg_ct_mul_relin", "sfg_ct_mul_plain", "sfg_ct_rescale", "sfg_ct_sub", "sfg_ct_add2",
+    "sfg_inner_sum_all", "sfg_encode_slots_i8",
 ]
 
 _lib = None
@@ -79,6 +81,15 @@ def load():
     L.sfg_cv_mod_reduce.argtypes = [vp, vp, i32, i32, vp, sz, sz]
     L.sfg_matmult4_finish.argtypes = [vp, vp, i32, i32, vp, i32, i32, vp]
     L.sfg_ct_add.argtypes = [vp, vp, vp, i32, i32, vp]
+    L.sfg_ctx_set_relin_key.argtypes = [vp, vp]
+    L.sfg_ctx_set_relin_key_ptrs.argtypes = [vp, vp]
+    L.sfg_ct_mul_relin.argtypes = [vp, i32, vp, i32, i32, vp, i32, i32, i32, vp]
+    L.sfg_ct_mul_plain.argtypes = [vp, i32, vp, i32, i32, vp, i32, i32, i32, vp]
+    L.sfg_ct_rescale.argtypes = [vp, i32, vp, i32, i32, vp]
+    L.sfg_ct_sub.argtypes = [vp, i32, vp, i32, i32, vp, i32, i32, vp]
+    L.sfg_ct_add2.argtypes = [vp, i32, vp, i32, i32, vp, i32, i32, vp]
+    L.sfg_inner_sum_all.argtypes = [vp, i32, vp, i32, i32, vp]
+    L.sfg_encode_slots_i8.argtypes = [vp, vp, i32, i32, vp]
     L.sfg_ctx_sync.argtypes = [vp]
     L.sfg_ctx_last_timings.argtypes = [vp, C.POINTER(C.c_float)]
     L.sfg_ctx_stream.restype = vp

@@ -447,4 +447,86 @@ int sfg_ct_add(sfg_ctx *h, const uint64_t *a, const uint64_t *b, int ncts, int n
     return 0;
 }
 
+// ---- ciphertext algebra of the callers (gwas/matmult.go:27-116) ----
+int sfg_ctx_set_relin_key(sfg_ctx *h, const uint64_t *key) {
+    // stored as the "rotation by 0" key: galEl = 1, whose NTT permutation is the identity (rotation by 0 itself never key-switches)
+    return sfg_ctx_set_rotation_key(h, 0, key);
+}
+int sfg_ctx_set_relin_key_ptrs(sfg_ctx *h, const uint64_t *const *limbs) { return sfg_ctx_set_rotation_key_ptrs(h, 0, limbs); }
+
+namespace {
+struct DevIO {  // host operand -> device, device result -> host
+    Ctx *c;
+    Buf in[2], out;
+    int up(int k, const void *src, size_t bytes) {
+        if (in[k].alloc(c, bytes)) return -1;
+        SFG_CUDA(c, cudaMemcpyAsync(in[k].p, src, bytes, cudaMemcpyDefault, c->stream));
+        return 0;
+    }
+    int down(void *dst, size_t bytes) {
+        SFG_CUDA(c, cudaMemcpyAsync(dst, out.p, bytes, cudaMemcpyDefault, c->stream));
+        SFG_CUDA(c, cudaStreamSynchronize(c->stream));
+        return 0;
+    }
+};
+}  // namespace
+
+int sfg_ct_mul_relin(sfg_ctx *h, int level, const uint64_t *x, int nx, int x_nl, const uint64_t *y, int ny, int y_nl, int nrescale, uint64_t *out) {
+    Ctx *c = &h->c;
+    if (nx < 1 || ny < 1 || x_nl < 1 || y_nl < 1 || nrescale < 0 || nrescale > level) SFG_FAIL(c, "sfg_ct_mul_relin: bad counts");
+    SFG_CUDA(c, cudaSetDevice(c->device));
+    const size_t N = c->N, n = std::max(nx, ny), ob = n * 2 * (size_t)(level + 1 - nrescale) * N * 8;
+    DevIO io{c};
+    if (io.up(0, x, (size_t)nx * 2 * x_nl * N * 8) || io.up(1, y, (size_t)ny * 2 * y_nl * N * 8) || io.out.alloc(c, n * 2 * (size_t)(level + 1) * N * 8)) return -1;
+    if (mul_relin_dev(c, level, io.in[0].as<uint64_t>(), nx, x_nl, io.in[1].as<uint64_t>(), ny, y_nl, nrescale, io.out.as<uint64_t>())) return -1;
+    return io.down(out, ob);
+}
+int sfg_ct_mul_plain(sfg_ctx *h, int level, const uint64_t *pt, int npt, int pt_nl, const uint64_t *cts, int nct, int ct_nl, int nrescale, uint64_t *out) {
+    Ctx *c = &h->c;
+    if (npt < 1 || nct < 1 || pt_nl < 1 || ct_nl < 1 || nrescale < 0 || nrescale > level) SFG_FAIL(c, "sfg_ct_mul_plain: bad counts");
+    SFG_CUDA(c, cudaSetDevice(c->device));
+    const size_t N = c->N, ob = (size_t)nct * 2 * (size_t)(level + 1 - nrescale) * N * 8;
+    DevIO io{c};
+    if (io.up(0, pt, (size_t)npt * pt_nl * N * 8) || io.up(1, cts, (size_t)nct * 2 * ct_nl * N * 8) || io.out.alloc(c, (size_t)nct * 2 * (level + 1) * N * 8)) return -1;
+    if (mul_plain_dev(c, level, io.in[0].as<uint64_t>(), npt, pt_nl, io.in[1].as<uint64_t>(), nct, ct_nl, nrescale, io.out.as<uint64_t>())) return -1;
+    return io.down(out, ob);
+}
+int sfg_ct_rescale(sfg_ctx *h, int level, const uint64_t *cts, int nct, int nrescale, uint64_t *out) {
+    Ctx *c = &h->c;
+    if (nct < 1 || level < 0 || level >= c->nQ || nrescale < 0 || nrescale > level) SFG_FAIL(c, "sfg_ct_rescale: bad level / counts");
+    SFG_CUDA(c, cudaSetDevice(c->device));
+    const size_t N = c->N;
+    DevIO io{c};
+    if (io.up(0, cts, (size_t)nct * 2 * (level + 1) * N * 8) || io.out.alloc(c, (size_t)nct * 2 * (level + 1) * N * 8)) return -1;
+    if (rescale_dev(c, level, io.in[0].as<uint64_t>(), nct, nrescale, io.out.as<uint64_t>())) return -1;
+    return io.down(out, (size_t)nct * 2 * (level + 1 - nrescale) * N * 8);
+}
+static int ct_addsub_host(sfg_ctx *h, int level, const uint64_t *a, int na, int a_nl, const uint64_t *b, int nb, int b_nl, bool sub, uint64_t *out) {
+    Ctx *c = &h->c;
+    if (na < 1 || nb < 1 || a_nl < 1 || b_nl < 1) SFG_FAIL(c, "ct add/sub: bad counts");
+    SFG_CUDA(c, cudaSetDevice(c->device));
+    const size_t N = c->N, n = std::max(na, nb), ob = n * 2 * (size_t)(level + 1) * N * 8;
+    DevIO io{c};
+    if (io.up(0, a, (size_t)na * 2 * a_nl * N * 8) || io.up(1, b, (size_t)nb * 2 * b_nl * N * 8) || io.out.alloc(c, ob)) return -1;
+    if (addsub_dev(c, level, io.in[0].as<uint64_t>(), na, a_nl, io.in[1].as<uint64_t>(), nb, b_nl, sub, io.out.as<uint64_t>())) return -1;
+    return io.down(out, ob);
+}
+int sfg_ct_sub(sfg_ctx *h, int level, const uint64_t *a, int na, int a_nl, const uint64_t *b, int nb, int b_nl, uint64_t *out) {
+    return ct_addsub_host(h, level, a, na, a_nl, b, nb, b_nl, true, out);
+}
+int sfg_ct_add2(sfg_ctx *h, int level, const uint64_t *a, int na, int a_nl, const uint64_t *b, int nb, int b_nl, uint64_t *out) {
+    return ct_addsub_host(h, level, a, na, a_nl, b, nb, b_nl, false, out);
+}
+int sfg_inner_sum_all(sfg_ctx *h, int level, const uint64_t *cts, int nvec, int cnt, uint64_t *out) {
+    Ctx *c = &h->c;
+    if (nvec < 1 || cnt < 1 || level < 0 || level >= c->nQ) SFG_FAIL(c, "sfg_inner_sum_all: bad level / counts");
+    SFG_CUDA(c, cudaSetDevice(c->device));
+    const size_t N = c->N, ct = (size_t)2 * (level + 1) * N * 8;
+    DevIO io{c};
+    if (io.up(0, cts, (size_t)nvec * cnt * ct) || io.out.alloc(c, (size_t)nvec * ct)) return -1;
+    if (inner_sum_all_dev(c, level, io.in[0].as<uint64_t>(), nvec, cnt, io.out.as<uint64_t>())) return -1;
+    return io.down(out, (size_t)nvec * ct);
+}
+int sfg_encode_slots_i8(sfg_ctx *h, const int8_t *v, int level, int mont, uint64_t *out) { return encode_slots_host(&h->c, v, level, mont != 0, out); }
+
 }  // extern "C"

@@ -120,6 +120,18 @@ int launch_copy_add(Ctx *c, const KsBatch &b, cudaStream_t st);
 // Lattigo SwitchingKey [beta][2][nQP][N] (NTT + Montgomery) -> device format of k_ks_inner2 (TT order; narrow moduli as Shoup pairs)
 int launch_key_convert(Ctx *c, const uint64_t *in, uint64_t *out, cudaStream_t st);
 
+// ---- ciphertext algebra of the callers around the path (kernels_ctalg.cu; gwas/matmult.go:27-116, crypto/basics.go) ----
+// ct k of an operand lives at base + k*stride (stride 0 = broadcast), stored as [2][*_nl][N]; results are dense [nct][2][nl][N]
+int launch_ct_tensor(Ctx *c, const uint64_t *a, long long a_stride, int a_nl, const uint64_t *b, long long b_stride, int b_nl, int nl, int nct,
+                     uint64_t *tmp /* (d0, d2) */, uint64_t *out /* (0, d1) */, cudaStream_t st);
+int launch_pt_mul(Ctx *c, const uint64_t *pt, long long pt_stride, const uint64_t *ct, long long ct_stride, int ct_nl, int nl, int nct,
+                  uint64_t *out, cudaStream_t st);
+int launch_ct_addsub(Ctx *c, const uint64_t *a, long long a_stride, int a_nl, const uint64_t *b, long long b_stride, int b_nl, int nl, int nct,
+                     bool sub, uint64_t *out, cudaStream_t st);
+int launch_ct_sum(Ctx *c, const uint64_t *in, int nvec, int cnt, int nl, uint64_t *out, cudaStream_t st);
+// ring.DivRoundByLastModulusNTT: npoly polynomials [level+1][N] -> [level][N]; scratch T [npoly][N], U [npoly][level][N]
+int launch_rescale(Ctx *c, int level, const uint64_t *in, int npoly, uint64_t *out, uint64_t *T, uint64_t *U, cudaStream_t st);
+
 // modular canonicalisation of sums of residues: x[l][n] = x[l][n] mod q_l over npoly*[L][N] (multi-GPU reduce epilogue)
 int launch_mod_reduce(Ctx *c, uint64_t *x, size_t npoly, int L, cudaStream_t st);
 

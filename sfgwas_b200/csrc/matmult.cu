@@ -744,4 +744,146 @@ int encode_diag_host(Ctx *c, const Geno *g, int bi, int shift, int nrot, int lev
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Ciphertext algebra of the callers around the path: the device side of crypto.CMult / CMultScalar /
+// MaskTrunc / InnerSumAll / CSub as QXLazyNormStream and QXtLazyNormStream use them (gwas/matmult.go:27-116).
+// All pointers are device pointers; ct k of an operand is [2][*_nl][N] at base + k * 2 * *_nl * N (count 1 = broadcast).
+// ---------------------------------------------------------------------------------------------------------------
+
+// evaluator.Rescale, `times` steps of ring.DivRoundByLastModulusNTT: d_in nct cts at `level` -> d_out nct cts at level - times
+int rescale_dev(Ctx *c, int level, const uint64_t *d_in, int nct, int times, uint64_t *d_out) {
+    SFG_CUDA(c, cudaSetDevice(c->device));
+    if (times < 0 || level - times < 0) SFG_FAIL(c, "rescale: cannot drop %d levels from level %d", times, level);
+    const size_t N = c->N;
+    const int npoly = 2 * nct;
+    if (times == 0) {
+        SFG_CUDA(c, cudaMemcpyAsync(d_out, d_in, (size_t)npoly * (level + 1) * N * 8, cudaMemcpyDefault, c->stream));
+        return 0;
+    }
+    Buf T, U, ping, pong;
+    if (T.alloc(c, (size_t)npoly * N * 8) || U.alloc(c, (size_t)npoly * level * N * 8)) return -1;
+    if (times > 1 && (ping.alloc(c, (size_t)npoly * level * N * 8) || pong.alloc(c, (size_t)npoly * level * N * 8))) return -1;
+    const uint64_t *src = d_in;
+    for (int t = 0; t < times; t++) {
+        uint64_t *dst = (t == times - 1) ? d_out : ((t & 1) ? pong.as<uint64_t>() : ping.as<uint64_t>());
+        if (launch_rescale(c, level - t, src, npoly, dst, T.as<uint64_t>(), U.as<uint64_t>(), c->stream)) return -1;
+        src = dst;
+    }
+    SFG_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// evaluator.MulRelinNew on n = max(nx, ny) pairs (a side of 1 is broadcast, crypto/basics.go:386-427) + `times` rescale steps
+int mul_relin_dev(Ctx *c, int level, const uint64_t *d_x, int nx, int x_nl, const uint64_t *d_y, int ny, int y_nl, int times, uint64_t *d_out) {
+    SFG_CUDA(c, cudaSetDevice(c->device));
+    const int N = c->N, nl = level + 1, n = std::max(nx, ny);
+    if (level < 0 || level >= c->nQ || x_nl < nl || y_nl < nl) SFG_FAIL(c, "mul_relin: level %d needs %d limbs (operands have %d / %d)", level, nl, x_nl, y_nl);
+    if (!((nx == n || nx == 1) && (ny == n || ny == 1)) || n < 1) SFG_FAIL(c, "mul_relin: %d x %d ciphertexts do not broadcast", nx, ny);
+    const GaloisKey *rlk = nullptr;
+    if (find_key(c, 0, &rlk)) SFG_FAIL(c, "relinearisation key not loaded (sfg_ctx_set_relin_key)");
+    const size_t ct = (size_t)2 * nl * N;
+    Buf tmp, prod;
+    if (tmp.alloc(c, n * ct * 8)) return -1;
+    uint64_t *dprod = d_out;
+    if (times > 0) {
+        if (prod.alloc(c, n * ct * 8)) return -1;
+        dprod = prod.as<uint64_t>();
+    }
+    if (launch_ct_tensor(c, d_x, nx == 1 ? 0 : (long long)2 * x_nl * N, x_nl, d_y, ny == 1 ? 0 : (long long)2 * y_nl * N, y_nl, nl, n,
+                         tmp.as<uint64_t>(), dprod, c->stream))
+        return -1;
+    // relinearise: key-switch d2 with rlk (galEl 1: the identity permutation) and accumulate (d0 + ks0, ks1) into (0, d1)
+    RotMeta rot;
+    for (int t = 0; t < n; t++) rot.add(RotEntry{(long long)(t * ct), (long long)(t * ct * 8), t, rlk});
+    rot.c2_src = rot.in_off;
+    if (rot.upload(c, WS_META)) return -1;
+    KsBatch kb{};
+    kb.level = level;
+    kb.nct = n;
+    kb.in = tmp.as<uint64_t>();
+    kb.in_off = rot.d_in_off;
+    kb.in_nl = nl;
+    kb.n_c2 = n;
+    kb.c2_src_off = rot.d_c2_src;
+    kb.c2_slot = rot.d_c2_slot;
+    kb.keys = rot.d_keys;
+    kb.perms = rot.d_perms;
+    kb.out = dprod;
+    kb.out_off = rot.d_out_off;
+    kb.out_layout = make_layout(c, nl, false);
+    kb.accumulate = true;
+    if (fill_scratch(c, kb, n, n)) return -1;
+    if (launch_rotate(c, kb, c->stream)) return -1;
+    if (times > 0) return rescale_dev(c, level, dprod, n, times, d_out);
+    SFG_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// evaluator.MulRelinNew(plaintext, ct) (crypto.MaskTrunc, crypto/basics.go:110-127) + `times` rescale steps
+int mul_plain_dev(Ctx *c, int level, const uint64_t *d_pt, int npt, int pt_nl, const uint64_t *d_ct, int nct, int ct_nl, int times, uint64_t *d_out) {
+    SFG_CUDA(c, cudaSetDevice(c->device));
+    const int N = c->N, nl = level + 1;
+    if (level < 0 || level >= c->nQ || pt_nl < nl || ct_nl < nl) SFG_FAIL(c, "mul_plain: level %d needs %d limbs (operands have %d / %d)", level, nl, pt_nl, ct_nl);
+    if (!(npt == nct || npt == 1) || nct < 1) SFG_FAIL(c, "mul_plain: %d plaintexts x %d ciphertexts do not broadcast", npt, nct);
+    Buf prod;
+    uint64_t *dprod = d_out;
+    if (times > 0) {
+        if (prod.alloc(c, (size_t)nct * 2 * nl * N * 8)) return -1;
+        dprod = prod.as<uint64_t>();
+    }
+    if (launch_pt_mul(c, d_pt, npt == 1 ? 0 : (long long)pt_nl * N, d_ct, (long long)2 * ct_nl * N, ct_nl, nl, nct, dprod, c->stream)) return -1;
+    if (times > 0) return rescale_dev(c, level, dprod, nct, times, d_out);
+    SFG_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// evaluator.Add / Sub, operands of matching scale: n = max(na, nb) results at `level`
+int addsub_dev(Ctx *c, int level, const uint64_t *d_a, int na, int a_nl, const uint64_t *d_b, int nb, int b_nl, bool sub, uint64_t *d_out) {
+    SFG_CUDA(c, cudaSetDevice(c->device));
+    const int N = c->N, nl = level + 1, n = std::max(na, nb);
+    if (level < 0 || level >= c->nQ || a_nl < nl || b_nl < nl) SFG_FAIL(c, "ct add/sub: level %d needs %d limbs (operands have %d / %d)", level, nl, a_nl, b_nl);
+    if (!((na == n || na == 1) && (nb == n || nb == 1)) || n < 1) SFG_FAIL(c, "ct add/sub: %d and %d ciphertexts do not broadcast", na, nb);
+    if (launch_ct_addsub(c, d_a, na == 1 ? 0 : (long long)2 * a_nl * N, a_nl, d_b, nb == 1 ? 0 : (long long)2 * b_nl * N, b_nl, nl, n, sub, d_out,
+                         c->stream))
+        return -1;
+    SFG_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// crypto.InnerSumAll (crypto/basics.go:278-293) for nvec vectors of cnt ciphertexts each (all [2][level+1][N]):
+// out[v] = sum of the vector, then out[v] += RotL_r(out[v]) for r = 1, 2, 4, .. < slots (RotateAndAdd :236-246); the nvec rotations of one
+// round go through one batched key-switch.
+int inner_sum_all_dev(Ctx *c, int level, const uint64_t *d_in, int nvec, int cnt, uint64_t *d_out) {
+    SFG_CUDA(c, cudaSetDevice(c->device));
+    const int N = c->N, nl = level + 1;
+    if (level < 0 || level >= c->nQ || nvec < 1 || cnt < 1) SFG_FAIL(c, "inner_sum_all: bad level / counts");
+    Buf rt;
+    if (rt.alloc(c, (size_t)nvec * 2 * nl * N * 8)) return -1;
+    if (launch_ct_sum(c, d_in, nvec, cnt, nl, d_out, c->stream)) return -1;
+    const long long ct = (long long)2 * nl * N;
+    for (int r = 1; r < c->slots; r *= 2) {
+        if (rotate_right_dev(c, level, d_out, nvec, c->slots - r, rt.as<uint64_t>())) return -1;  // RotateNew(ct, r): left rotation by r
+        if (launch_ct_addsub(c, rt.as<uint64_t>(), ct, nl, d_out, ct, nl, nl, nvec, false, d_out, c->stream)) return -1;
+    }
+    SFG_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// EncodeNTT of an int8 slot vector (e.g. the 0/1 mask of crypto.MaskTrunc) with the diagonal encoder: correctly rounded
+// scale * sigma^-1(v), NTT domain, limbs 0..level, plain or Montgomery form.
+int encode_slots_host(Ctx *c, const int8_t *v, int level, bool mont, uint64_t *out) {
+    SFG_CUDA(c, cudaSetDevice(c->device));
+    const int slots = c->slots, N = c->N, nl = level + 1;
+    if (level < 0 || level >= c->nQ) SFG_FAIL(c, "encode_slots: level %d out of range", level);
+    Buf dv, dj, dout;
+    if (dv.alloc(c, slots) || dj.alloc(c, sizeof(EncJob)) || dout.alloc(c, (size_t)nl * N * 8)) return -1;
+    SFG_CUDA(c, cudaMemcpyAsync(dv.p, v, slots, cudaMemcpyDefault, c->stream));
+    const EncJob job{0, 0, slots, slots, 0, 0, 0};  // diagonal 0 of a block whose every row is v (leading dimension 0)
+    SFG_CUDA(c, cudaMemcpyAsync(dj.p, &job, sizeof job, cudaMemcpyDefault, c->stream));
+    if (launch_encode(c, dv.as<int8_t>(), 0, dj.as<EncJob>(), 1, make_layout(c, nl, false), mont, dout.p, nullptr, c->stream)) return -1;
+    SFG_CUDA(c, cudaMemcpyAsync(out, dout.p, (size_t)nl * N * 8, cudaMemcpyDefault, c->stream));
+    SFG_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
 }  // namespace sfg

@@ -77,6 +77,14 @@ int rotate_right_dev(Ctx *c, int level, const uint64_t *d_in, int nct, int nrot,
 int encode_diag_host(Ctx *c, const Geno *g, int bi, int shift, int nrot, int level, bool mont, uint64_t *out, uint8_t *present,
                      int64_t *coeffs);
 
+// ciphertext algebra of the callers (gwas/matmult.go:27-116); device pointers, see matmult.cu
+int rescale_dev(Ctx *c, int level, const uint64_t *d_in, int nct, int times, uint64_t *d_out);
+int mul_relin_dev(Ctx *c, int level, const uint64_t *d_x, int nx, int x_nl, const uint64_t *d_y, int ny, int y_nl, int times, uint64_t *d_out);
+int mul_plain_dev(Ctx *c, int level, const uint64_t *d_pt, int npt, int pt_nl, const uint64_t *d_ct, int nct, int ct_nl, int times, uint64_t *d_out);
+int addsub_dev(Ctx *c, int level, const uint64_t *d_a, int na, int a_nl, const uint64_t *d_b, int nb, int b_nl, bool sub, uint64_t *d_out);
+int inner_sum_all_dev(Ctx *c, int level, const uint64_t *d_in, int nvec, int cnt, uint64_t *d_out);
+int encode_slots_host(Ctx *c, const int8_t *v, int level, bool mont, uint64_t *out);
+
 extern thread_local float g_last_ms[5];  // baby, mac phase, giant, total, mac kernel only
 
 }  // namespace sfg

@@ -22,7 +22,8 @@ from ._lib import SfgError, load
 
 __all__ = [
     "CryptoParams", "GenoFileStream", "DiagCache", "MatMult4StreamPreprocess", "MatMult4StreamCompute", "MatMult4Stream",
-    "SfgError",
+    "SfgError", "Ciphertext", "SetRelinKey", "CMult", "CMultScalar", "CSub", "CAdd", "InnerSumAll", "InnerProd", "MaskTrunc",
+    "QXLazyNormStream", "QXtLazyNormStream",
 ]
 
 
@@ -264,3 +265,185 @@ def MatMult4Stream(cryptoParams: CryptoParams, A: np.ndarray, gfs: GenoFileStrea
                                            _p(out), _p(sm) if computeSquaredSum else None, _p(sq) if computeSquaredSum else None),
         "MatMult4Stream")
     return out, sm, sq
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# The callers' ciphertext algebra around the path (SURVEY 8 rows a4 / f2): crypto.CMult, CMultScalar, InnerSumAll, InnerProd,
+# MaskTrunc, CSub and the two lazy-normalisation wrappers QXLazyNormStream / QXtLazyNormStream (gwas/matmult.go:27-116).
+# A ciphertext carries its limbs and its scale like *ckks.Ciphertext; CipherVector = list[Ciphertext], CipherMatrix = list of those.
+# ------------------------------------------------------------------------------------------------------------------------
+class Ciphertext:
+    """*ckks.Ciphertext of degree 1: ``value`` [2][level+1][N] uint64 (Value()[k].Coeffs[l][j]) and ``scale``."""
+
+    __slots__ = ("value", "scale")
+
+    def __init__(self, value: np.ndarray, scale: float):
+        self.value = np.ascontiguousarray(value, dtype=np.uint64)
+        self.scale = float(scale)
+
+    def Level(self) -> int:
+        return self.value.shape[1] - 1
+
+    def Scale(self) -> float:
+        return self.scale
+
+    def CopyNew(self) -> "Ciphertext":
+        return Ciphertext(self.value.copy(), self.scale)
+
+
+def SetRelinKey(cps: CryptoParams, rlk: np.ndarray):
+    """cryptoParams.Rlk.Keys[0]: [beta][2][nQ+nP][N], NTT + Montgomery form."""
+    rlk = np.ascontiguousarray(rlk, dtype=np.uint64)
+    if rlk.shape != (cps.beta, 2, cps.nQP, cps.N):
+        raise SfgError(f"relinearisation key shape {rlk.shape} != {(cps.beta, 2, cps.nQP, cps.N)}")
+    cps._check(cps.L.sfg_ctx_set_relin_key(cps.h, _p(rlk)), "sfg_ctx_set_relin_key")
+
+
+def _nrescale(cps: CryptoParams, scale: float, level: int, threshold=None):
+    """evaluator.Rescale(ct, threshold, ct) (Lattigo v2.1): steps taken while scale >= threshold*q_level/2 and level > 0."""
+    threshold = cps.scale if threshold is None else threshold
+    n = 0
+    while level - n > 0 and scale >= threshold * float(cps.Q[level - n]) / 2:
+        scale /= float(cps.Q[level - n])
+        n += 1
+    return n, scale
+
+
+def _stack(cts, level):
+    """cts (same stored limb count or not) -> one array [n][2][level+1][N]: DropLevel to `level` = limb truncation."""
+    return np.ascontiguousarray(np.stack([c.value[:, : level + 1] for c in cts]))
+
+
+def _mul_relin_batch(cps, X, Y):
+    n = max(len(X), len(Y))
+    if not ((len(X) in (1, n)) and (len(Y) in (1, n))):
+        raise SfgError("CMult: vector lengths %d and %d do not broadcast" % (len(X), len(Y)))
+    xs = [X[i if len(X) > 1 else 0] for i in range(n)]
+    ys = [Y[i if len(Y) > 1 else 0] for i in range(n)]
+    out = [None] * n
+    groups = {}
+    for i in range(n):  # one device batch per (level, scale product)
+        lvl = min(xs[i].Level(), ys[i].Level())
+        groups.setdefault((lvl, xs[i].scale * ys[i].scale), []).append(i)
+    for (lvl, sc), idx in groups.items():
+        k, sc2 = _nrescale(cps, sc, lvl)
+        bx = len(X) == 1
+        by = len(Y) == 1
+        ax = _stack([X[0]] if bx else [xs[i] for i in idx], lvl)
+        ay = _stack([Y[0]] if by else [ys[i] for i in idx], lvl)
+        res = np.zeros((len(idx), 2, lvl + 1 - k, cps.N), dtype=np.uint64)
+        cps._check(cps.L.sfg_ct_mul_relin(cps.h, lvl, _p(ax), ax.shape[0], lvl + 1, _p(ay), ay.shape[0], lvl + 1, k, _p(res)), "sfg_ct_mul_relin")
+        for j, i in enumerate(idx):
+            out[i] = Ciphertext(res[j], sc2)
+    return out
+
+
+def CMult(cryptoParams: CryptoParams, X, Y):
+    """crypto.CMult (crypto/basics.go:386-427): element-wise MulRelinNew + Rescale(params.Scale); a length-1 side is broadcast."""
+    return _mul_relin_batch(cryptoParams, X, Y)
+
+
+def CMultScalar(cryptoParams: CryptoParams, X, ct: Ciphertext):
+    """crypto.CMultScalar (crypto/basics.go:553-566)."""
+    return _mul_relin_batch(cryptoParams, X, [ct])
+
+
+def _addsub(cps, a: Ciphertext, b: Ciphertext, sub: bool) -> Ciphertext:
+    r = max(a.scale, b.scale) / min(a.scale, b.scale)
+    if math.floor(r) > 1:  # Lattigo v2.1 evaluateInPlace would first multiply the smaller-scale operand by floor(ratio)
+        raise SfgError("ciphertext add/sub with scales %g and %g needs scale matching, which this path never does" % (a.scale, b.scale))
+    lvl = min(a.Level(), b.Level())
+    out = np.zeros((2, lvl + 1, cps.N), dtype=np.uint64)
+    fn = cps.L.sfg_ct_sub if sub else cps.L.sfg_ct_add2
+    cps._check(fn(cps.h, lvl, _p(a.value), 1, a.Level() + 1, _p(b.value), 1, b.Level() + 1, _p(out)), "sfg_ct_sub" if sub else "sfg_ct_add2")
+    return Ciphertext(out, max(a.scale, b.scale))
+
+
+def CSub(cryptoParams: CryptoParams, X, Y):
+    """crypto.CSub (crypto/basics.go:580-590)."""
+    return [_addsub(cryptoParams, X[i], Y[i], True) for i in range(len(Y))]
+
+
+def CAdd(cryptoParams: CryptoParams, X, Y):
+    """crypto.CAdd (crypto/basics.go:568-578)."""
+    return [_addsub(cryptoParams, X[i], Y[i], False) for i in range(max(len(X), len(Y)))]
+
+
+def InnerSumAll(cryptoParams: CryptoParams, X) -> Ciphertext:
+    """crypto.InnerSumAll (crypto/basics.go:278-293): every slot of the result holds the sum of all slots of all ciphertexts of X."""
+    cps = cryptoParams
+    lvl = min(c.Level() for c in X)
+    a = _stack(X, lvl)
+    out = np.zeros((1, 2, lvl + 1, cps.N), dtype=np.uint64)
+    cps._check(cps.L.sfg_inner_sum_all(cps.h, lvl, _p(a), 1, len(X), _p(out)), "sfg_inner_sum_all")
+    return Ciphertext(out[0], max(c.scale for c in X))
+
+
+def InnerProd(cryptoParams: CryptoParams, X, Y) -> Ciphertext:
+    """crypto.InnerProd (crypto/basics.go:274-276)."""
+    return InnerSumAll(cryptoParams, CMult(cryptoParams, X, Y))
+
+
+def MaskTrunc(cryptoParams: CryptoParams, ct: Ciphertext, N: int, mask_pt: np.ndarray = None) -> Ciphertext:
+    """crypto.MaskTrunc (crypto/basics.go:110-127): retain the first N slots (consumes a level).  ``mask_pt`` lets the caller pass the
+    reference-encoded mask plaintext ([nQ][N], NTT domain); by default the mask is encoded on the device (correctly rounded)."""
+    cps = cryptoParams
+    if N == cps.slots:
+        return ct
+    if mask_pt is None:
+        m = np.zeros(cps.slots, dtype=np.int8)
+        m[:N] = 1
+        mask_pt = np.zeros((cps.nQ, cps.N), dtype=np.uint64)
+        cps._check(cps.L.sfg_encode_slots_i8(cps.h, _p(m), cps.nQ - 1, 0, _p(mask_pt)), "sfg_encode_slots_i8")
+    mask_pt = np.ascontiguousarray(mask_pt, dtype=np.uint64)
+    lvl = min(ct.Level(), mask_pt.shape[0] - 1)
+    k, sc = _nrescale(cps, ct.scale * cps.scale, lvl)
+    out = np.zeros((1, 2, lvl + 1 - k, cps.N), dtype=np.uint64)
+    cps._check(cps.L.sfg_ct_mul_plain(cps.h, lvl, _p(mask_pt), 1, mask_pt.shape[0], _p(ct.value), 1, ct.Level() + 1, k, _p(out)), "sfg_ct_mul_plain")
+    return Ciphertext(out[0], sc)
+
+
+def _matmult_cm(cps, M, cache: DiagCache, maxLevel=5):
+    """MatMult4StreamCompute on a CipherMatrix (list of CipherVectors): DropLevel to maxLevel, run, re-wrap with the output scale."""
+    lvl = min(c.Level() for row in M for c in row)
+    if lvl < maxLevel:
+        raise SfgError("input level %d is smaller than the requested level %d" % (lvl, maxLevel))  # crypto/basics.go:806-824
+    A = np.ascontiguousarray(np.stack([_stack(row, maxLevel) for row in M]))
+    out = MatMult4StreamCompute(cps, A, maxLevel, cache)
+    sc = M[0][0].scale * cps.scale  # gwas/matmult.go:1045
+    return [[Ciphertext(out[i, j], sc) for j in range(out.shape[1])] for i in range(out.shape[0])]
+
+
+def QXLazyNormStream(cps: CryptoParams, mpcObj, Q, Xcache: DiagCache, XMean, XStdInv, numInd: int):
+    """gwas/matmult.go:27-77: Q*S*(X - m*1^T) = (Q*S)*X - ((Q*S)*m)*1^T.  ``mpcObj`` supplies GetPid() and Network.BootstrapMatAll(cps, M)
+    (the collective bootstrap is the reference's network protocol and stays outside this library)."""
+    if mpcObj.GetPid() == 0:
+        return None
+    slots = cps.GetSlots()
+    QS = [CMult(cps, Q[i], XStdInv) for i in range(len(Q))]
+    out = _matmult_cm(cps, QS, Xcache, 5)
+    out = mpcObj.Network.BootstrapMatAll(cps, out)
+    QSm = [InnerProd(cps, QS[i], XMean) for i in range(len(Q))]
+    for i in range(len(QS)):
+        for j in range(len(out[i])):
+            out[i][j] = _addsub(cps, out[i][j], QSm[i], True)
+        for j in range(len(out[i])):
+            n = slots if j < len(out[i]) - 1 else ((numInd - 1) % slots) + 1
+            out[i][j] = MaskTrunc(cps, out[i][j], n)
+    return out
+
+
+def QXtLazyNormStream(cps: CryptoParams, mpcObj, Q, XTcache: DiagCache, XMean, XStdInv):
+    """gwas/matmult.go:83-116: Q*(X^T - 1*m^T)*S = ((Q*X^T) - ((Q*1)*m^T))*S."""
+    if mpcObj.GetPid() == 0:
+        return None
+    out = _matmult_cm(cps, Q, XTcache, 5)
+    out = mpcObj.Network.BootstrapMatAll(cps, out)
+    for i in range(len(out)):
+        rowSum = InnerSumAll(cps, Q[i])
+        Q1m = CMultScalar(cps, XMean, rowSum)
+        for j in range(len(out[i])):
+            out[i][j] = _addsub(cps, out[i][j], Q1m[j], True)
+    for i in range(len(out)):
+        out[i] = CMult(cps, out[i], XStdInv)
+    return out
