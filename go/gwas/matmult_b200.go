@@ -175,7 +175,17 @@ func MatMult4StreamCompute(cryptoParams *crypto.CryptoParams, A crypto.CipherMat
 	cache, ok := b200Caches[cacheFilePrefix]
 	b200Mu.Unlock()
 	if !ok {
-		panic("open " + cacheFilePrefix + "_0.bin: no such diagonal cache") // NewDiagCacheStream panics (gwas/filestream.go:56-61)
+		// no HBM cache under this prefix: build it from the reference's <prefix>_<bi>.bin files (written by an earlier run or by the
+		// CPU path); a missing file fails like NewDiagCacheStream's panic (gwas/filestream.go:56-61)
+		cp := C.CString(cacheFilePrefix)
+		c.mu.Lock()
+		rc := C.sfg_cache_load_files(c.h, cp, 0, 0, C.int(maxLevel), &cache)
+		c.mu.Unlock()
+		C.free(unsafe.Pointer(cp))
+		b200Check(c, rc, "NewDiagCacheStream")
+		b200Mu.Lock()
+		b200Caches[cacheFilePrefix] = cache
+		b200Mu.Unlock()
 	}
 	var mct, nbr C.int
 	C.sfg_cache_info(cache, nil, nil, nil, &mct, &nbr)

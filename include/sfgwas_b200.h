@@ -84,6 +84,13 @@ void sfg_cache_destroy(sfg_cache *cache);
 int sfg_cache_info(const sfg_cache *cache, size_t *num_polys, size_t *bytes, int *materialised, int *m_ct, int *num_block_rows);
 /* copy one cached plaintext to the host: out [max_level][N] (the used limbs, NTT + Montgomery form); *present = 0 if nil */
 int sfg_cache_get_diag(sfg_ctx *ctx, const sfg_cache *cache, int block_row, int shift, int block_col, uint64_t *out, int *present);
+/* The reference's on-disk cache, `<prefix>_<bi>.bin` per block row (DiagCacheStream, gwas/filestream.go:19-282):
+ * write = what MatMult4StreamPreprocess leaves on disk (all maxLevel+1 limbs, Montgomery form, big-endian coefficients), so a CPU run
+ * of the reference can consume a GPU preprocess; load = build the HBM cache from files the reference wrote for an nrows x ncols
+ * matrix (records in any order; nrows = ncols = 0: take the block structure from the files alone, which is all the reference's
+ * MatMult4StreamCompute has in hand).  A missing file fails like NewDiagCacheStream's panic. */
+int sfg_cache_write_files(sfg_ctx *ctx, const sfg_cache *cache, const char *prefix);
+int sfg_cache_load_files(sfg_ctx *ctx, const char *prefix, size_t nrows, size_t ncols, int max_level, sfg_cache **out);
 
 /* MatMult4StreamCompute(cryptoParams, A, maxLevel, cacheFilePrefix) (gwas/matmult.go:1043-1236).
  * A: [s][num_block_rows][2][level_a+1][N]; out: [s][m_ct][2][max_level][N] = the deterministic sum

@@ -540,6 +540,10 @@ class Oracle:
         n = (maxLevel + 1) * self.N
         return np.ctypeslib.as_array(C.cast(ptr, u64p), shape=(n,)).reshape(maxLevel + 1, self.N).copy()
 
+    def cache_write_files(self, dc, prefix: str):
+        """DiagCacheStream.WriteDiag for every active shift (gwas/filestream.go:140-234): <prefix>_<bi>.bin."""
+        assert self.L.orc_diag_cache_write_files(self.ctx, dc, str(prefix).encode()) == 0
+
     def cache_free(self, dc):
         self.L.orc_diag_cache_free(dc)
 

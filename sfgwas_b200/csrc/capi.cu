@@ -447,6 +447,15 @@ int sfg_ct_add(sfg_ctx *h, const uint64_t *a, const uint64_t *b, int ncts, int n
     return 0;
 }
 
+int sfg_cache_write_files(sfg_ctx *h, const sfg_cache *cache, const char *prefix) { return cache_write_files(&h->c, cache->ca, prefix); }
+int sfg_cache_load_files(sfg_ctx *h, const char *prefix, size_t nrows, size_t ncols, int max_level, sfg_cache **out) {
+    *out = nullptr;
+    Cache *ca = nullptr;
+    if (cache_load_files(&h->c, prefix, nrows, ncols, max_level, &ca)) return -1;
+    *out = new sfg_cache{ca};
+    return 0;
+}
+
 // ---- ciphertext algebra of the callers (gwas/matmult.go:27-116) ----
 int sfg_ctx_set_relin_key(sfg_ctx *h, const uint64_t *key) {
     // stored as the "rotation by 0" key: galEl = 1, whose NTT permutation is the identity (rotation by 0 itself never key-switches)

@@ -132,6 +132,11 @@ int launch_ct_sum(Ctx *c, const uint64_t *in, int nvec, int cnt, int nl, uint64_
 // ring.DivRoundByLastModulusNTT: npoly polynomials [level+1][N] -> [level][N]; scratch T [npoly][N], U [npoly][level][N]
 int launch_rescale(Ctx *c, int level, const uint64_t *in, int npoly, uint64_t *out, uint64_t *T, uint64_t *U, cudaStream_t st);
 
+// ---- on-disk diagonal cache records (kernels_cachefile.cu; gwas/filestream.go:42-282) ----
+int launch_bswap64(Ctx *c, uint64_t *x, size_t n, cudaStream_t st);  // little <-> big endian in place
+int launch_file_to_rec(Ctx *c, const uint64_t *raw, const long long *dst_off_dev, int npoly, int file_nl, const PolyLayout &lay, void *out,
+                       cudaStream_t st);
+
 // modular canonicalisation of sums of residues: x[l][n] = x[l][n] mod q_l over npoly*[L][N] (multi-GPU reduce epilogue)
 int launch_mod_reduce(Ctx *c, uint64_t *x, size_t npoly, int L, cudaStream_t st);
 

@@ -12,8 +12,12 @@
 //                emits canonical residues (K1+K2 fused); (3) giant rotations batched per giant step over every (i, bj),
 //                accumulated into out in place (K6+K7 fused).
 #include <algorithm>
+#include <cerrno>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <string>
 
 #include "matmult.h"
 
@@ -132,30 +136,31 @@ static int build_p_tiles(Ctx *c, const Cache *ca, int tile_lo, int tile_hi, unsi
     return 0;
 }
 
-int cache_build(Ctx *c, Geno *g, int maxLevel, Cache **out) {
-    if (g->filled != g->nrows) SFG_FAIL(c, "genotype matrix incomplete: %zu of %zu rows pushed", g->filled, g->nrows);
-    if (maxLevel < 1 || maxLevel > c->nQ - 1) SFG_FAIL(c, "maxLevel %d needs %d Q limbs, parameters have %d", maxLevel, maxLevel + 1, c->nQ);
-    SFG_CUDA(c, cudaSetDevice(c->device));
-    Cache *ca = new Cache();
+static int cache_meta_finish(Ctx *c, Cache *ca);
+// shapes, index tables (gwas/matmult.go:962-974) and image geometry of a cache over an nrows x ncols matrix
+static int cache_meta_base(Ctx *c, Cache *ca, size_t nrows, size_t ncols, int maxLevel) {
     ca->c = c;
     ca->device = c->device;
-    ca->g = g;
-    g->refs++;
     ca->maxLevel = maxLevel;
     ca->L = maxLevel;  // limb-COUNT quirk: accumulators cover limbs 0..maxLevel-1 (gwas/matmult.go:1125 -> :231, App. A.4)
     if (maxLevel > kMaxLayoutLimbs) SFG_FAIL(c, "maxLevel %d > %d not supported", maxLevel, kMaxLayoutLimbs);
     ca->lay = make_layout(c, ca->L, true);
     ca->slots = c->slots;
     ca->d = c->d;
-    ca->nrows = g->nrows;
-    ca->ncols = g->ncols;
-    ca->m_ct = (int)((g->ncols - 1) / c->slots) + 1;   // matmult.go:920
-    ca->nbr = (int)((g->nrows - 1) / c->slots) + 1;    // matmult.go:921
+    ca->nrows = nrows;
+    ca->ncols = ncols;
+    ca->m_ct = (int)((ncols - 1) / c->slots) + 1;   // matmult.go:920
+    ca->nbr = (int)((nrows - 1) / c->slots) + 1;    // matmult.go:921
     const int slots = ca->slots, d = ca->d, m_ct = ca->m_ct, nbr = ca->nbr;
     ca->baby.assign((size_t)nbr * d, 0);
     ca->giant.assign((size_t)nbr * d, 0);
     ca->shiftT.assign((size_t)nbr * slots, 0);
     ca->pidx.assign((size_t)nbr * slots * m_ct, -1);
+    return 0;
+}
+static int cache_init_meta(Ctx *c, Cache *ca, size_t nrows, size_t ncols, int maxLevel) {
+    if (cache_meta_base(c, ca, nrows, ncols, maxLevel)) return -1;
+    const int slots = ca->slots, d = ca->d, m_ct = ca->m_ct, nbr = ca->nbr;
     size_t npoly = 0;
     for (int bi = 0; bi < nbr; bi++) {
         const int nr = block_rows(ca, bi);
@@ -175,6 +180,12 @@ int cache_build(Ctx *c, Geno *g, int maxLevel, Cache **out) {
         }
     }
     ca->npoly = npoly;
+    return cache_meta_finish(c, ca);
+}
+// K list, active giants and image geometry from the baby / giant tables
+static int cache_meta_finish(Ctx *c, Cache *ca) {
+    const int d = ca->d, m_ct = ca->m_ct, nbr = ca->nbr;
+    const size_t npoly = ca->npoly;
     ca->kidx.assign((size_t)nbr * d, -1);
     for (int bi = 0; bi < nbr; bi++)
         for (int b = 0; b < d; b++)
@@ -189,10 +200,21 @@ int cache_build(Ctx *c, Geno *g, int maxLevel, Cache **out) {
         if (any) ca->gact.push_back(gi);
     }
     if (npoly > 0x7fffffffULL) SFG_FAIL(c, "too many diagonal polynomials");
-    if (tc_geom_p(c, ca->L, (int)ca->kbi.size(), (int)ca->gact.size() * m_ct, &ca->tc)) {
+    return tc_geom_p(c, ca->L, (int)ca->kbi.size(), (int)ca->gact.size() * m_ct, &ca->tc);
+}
+
+int cache_build(Ctx *c, Geno *g, int maxLevel, Cache **out) {
+    if (g->filled != g->nrows) SFG_FAIL(c, "genotype matrix incomplete: %zu of %zu rows pushed", g->filled, g->nrows);
+    if (maxLevel < 1 || maxLevel > c->nQ - 1) SFG_FAIL(c, "maxLevel %d needs %d Q limbs, parameters have %d", maxLevel, maxLevel + 1, c->nQ);
+    SFG_CUDA(c, cudaSetDevice(c->device));
+    Cache *ca = new Cache();
+    ca->g = g;
+    g->refs++;
+    if (cache_init_meta(c, ca, g->nrows, g->ncols, maxLevel)) {
         cache_destroy(ca);
         return -1;
     }
+    const size_t npoly = ca->npoly;
     // materialise if it fits the budget
     size_t budget = c->cache_budget;
     if (budget == 0) {
@@ -883,6 +905,257 @@ int encode_slots_host(Ctx *c, const int8_t *v, int level, bool mont, uint64_t *o
     if (launch_encode(c, dv.as<int8_t>(), 0, dj.as<EncJob>(), 1, make_layout(c, nl, false), mont, dout.p, nullptr, c->stream)) return -1;
     SFG_CUDA(c, cudaMemcpyAsync(out, dout.p, (size_t)nl * N * 8, cudaMemcpyDefault, c->stream));
     SFG_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// The reference's on-disk diagonal cache (gwas/filestream.go:19-282, App. D.2): one file `<prefix>_<bi>.bin` per
+// block row = header {vectorLen = m_ct, level = maxLevel, scale, n = N, numModuli = maxLevel+1, rowSize} (6 x u64 LE) + baby / giant
+// tables (d bytes each) + records {u64 LE length, u32 LE shift, per block column: u8 isEmpty [, numModuli x N BIG-endian u64]}.
+// cache_write_files lets a CPU run of the reference consume a GPU preprocess; cache_load_files builds the HBM image from files the
+// reference wrote (records may come in any order: the reference's writer receives them from nproc goroutines).
+// ---------------------------------------------------------------------------------------------------------------
+static size_t env_size(const char *name, size_t dflt) {
+    const char *e = getenv(name);
+    return (e && *e) ? (size_t)strtoull(e, nullptr, 10) : dflt;
+}
+
+int cache_write_files(Ctx *c, const Cache *ca, const char *prefix) {
+    if (!ca->g) SFG_FAIL(c, "cache_write_files: this cache was loaded from files (no genotype matrix to encode limb %d from)", ca->maxLevel);
+    SFG_CUDA(c, cudaSetDevice(c->device));
+    const int slots = ca->slots, d = ca->d, m_ct = ca->m_ct, N = c->N, nlF = ca->maxLevel + 1;
+    const size_t polyB = (size_t)nlF * N * 8;
+    const PolyLayout layF = make_layout(c, nlF, false);
+    const size_t cap = std::max<size_t>((size_t)m_ct, env_size("SFG_CACHEFILE_CHUNK_POLYS", ((size_t)512 << 20) / polyB));
+    Buf dbuf, djobs;
+    if (dbuf.alloc(c, cap * polyB) || djobs.alloc(c, cap * sizeof(EncJob))) return -1;
+    std::vector<unsigned char> host(cap * polyB);
+    for (int bi = 0; bi < ca->nbr; bi++) {
+        const std::string fn = std::string(prefix) + "_" + std::to_string(bi) + ".bin";
+        FILE *f = fopen(fn.c_str(), "wb");
+        if (!f) SFG_FAIL(c, "create %s: %s", fn.c_str(), strerror(errno));
+        uint64_t hdr[6] = {(uint64_t)m_ct, (uint64_t)ca->maxLevel, 0, (uint64_t)N, (uint64_t)nlF, 4 + (1 + (uint64_t)polyB) * (uint64_t)m_ct};
+        memcpy(&hdr[2], &c->scale, 8);
+        bool ok = fwrite(hdr, 8, 6, f) == 6 && fwrite(&ca->baby[(size_t)bi * d], 1, d, f) == (size_t)d && fwrite(&ca->giant[(size_t)bi * d], 1, d, f) == (size_t)d;
+        int shift = 0;
+        while (ok && shift < slots) {
+            // batch of consecutive active shifts whose polynomials fit the staging buffers
+            std::vector<EncJob> jobs;
+            std::vector<int> shifts;
+            while (shift < slots && jobs.size() + m_ct <= cap) {
+                if (ca->shiftT[(size_t)bi * slots + shift]) {
+                    shifts.push_back(shift);
+                    for (int bj = 0; bj < m_ct; bj++)
+                        if (ca->pidx[((size_t)bi * slots + shift) * m_ct + bj] >= 0)  // EncodeDiagWithEncoder(blockVec, -shift, d*giant, maxLevel) :1024
+                            jobs.push_back(EncJob{bi * slots, bj * slots, block_rows(ca, bi), block_cols(ca, bj), shift, d * (shift / d),
+                                                  (long long)(jobs.size() * polyB)});
+                }
+                shift++;
+            }
+            if (jobs.empty()) continue;
+            SFG_CUDA(c, cudaMemcpyAsync(djobs.p, jobs.data(), jobs.size() * sizeof(EncJob), cudaMemcpyDefault, c->stream));
+            if (launch_encode(c, ca->g->d, ca->ncols, djobs.as<EncJob>(), (int)jobs.size(), layF, true /* ToMontgomeryForm :401-409 */, dbuf.p, nullptr,
+                              c->stream) ||
+                launch_bswap64(c, dbuf.as<uint64_t>(), jobs.size() * (size_t)nlF * N, c->stream)) {
+                fclose(f);
+                return -1;
+            }
+            SFG_CUDA(c, cudaMemcpyAsync(host.data(), dbuf.p, jobs.size() * polyB, cudaMemcpyDefault, c->stream));
+            SFG_CUDA(c, cudaStreamSynchronize(c->stream));
+            size_t k = 0;
+            for (int sh : shifts) {
+                uint64_t len = 4;
+                for (int bj = 0; bj < m_ct; bj++) len += 1 + (ca->pidx[((size_t)bi * slots + sh) * m_ct + bj] >= 0 ? polyB : 0);
+                const uint32_t sh32 = (uint32_t)sh;
+                ok = ok && fwrite(&len, 8, 1, f) == 1 && fwrite(&sh32, 4, 1, f) == 1;
+                for (int bj = 0; bj < m_ct && ok; bj++) {
+                    const bool present = ca->pidx[((size_t)bi * slots + sh) * m_ct + bj] >= 0;
+                    const unsigned char empty = present ? 0 : 1;
+                    ok = fwrite(&empty, 1, 1, f) == 1;
+                    if (present && ok) ok = fwrite(host.data() + (k++) * polyB, 1, polyB, f) == polyB;
+                }
+            }
+        }
+        if (fclose(f) != 0) ok = false;
+        if (!ok) SFG_FAIL(c, "write %s failed: %s", fn.c_str(), strerror(errno));
+    }
+    return 0;
+}
+
+int cache_load_files(Ctx *c, const char *prefix, size_t nrows, size_t ncols, int maxLevel, Cache **out) {
+    const bool infer = nrows == 0 || ncols == 0;  // shape unknown (the reference's Compute only has the prefix): take it from the files
+    if (maxLevel < 1 || maxLevel > c->nQ - 1) SFG_FAIL(c, "maxLevel %d needs %d Q limbs, parameters have %d", maxLevel, maxLevel + 1, c->nQ);
+    SFG_CUDA(c, cudaSetDevice(c->device));
+    Cache *ca = new Cache();
+    std::vector<FILE *> files;
+    auto fail = [&](const std::string &m) {
+        for (FILE *f : files)
+            if (f) fclose(f);
+        cache_destroy(ca);
+        if (!m.empty()) c->err = m;
+        return -1;
+    };
+    const int N = c->N, nlF = maxLevel + 1;
+    const size_t polyB = (size_t)nlF * N * 8;
+    if (infer) {  // number of block rows = number of files, number of block columns = vectorLen of the first header
+        int nf = 0;
+        uint64_t vlen = 0;
+        for (;; nf++) {
+            FILE *f = fopen((std::string(prefix) + "_" + std::to_string(nf) + ".bin").c_str(), "rb");
+            if (!f) break;
+            if (nf == 0 && fread(&vlen, 8, 1, f) != 1) vlen = 0;
+            fclose(f);
+        }
+        if (nf == 0) return fail("open " + std::string(prefix) + "_0.bin: " + strerror(ENOENT));
+        if (vlen == 0 || vlen > (1u << 20)) return fail(std::string(prefix) + "_0.bin: bad header");
+        if (cache_meta_base(c, ca, (size_t)nf * c->slots, (size_t)vlen * c->slots, maxLevel)) return fail("");
+    } else if (cache_init_meta(c, ca, nrows, ncols, maxLevel)) {
+        return fail("");
+    }
+    const int slots = ca->slots, d = ca->d, m_ct = ca->m_ct, nbr = ca->nbr;
+    size_t npoly_files = 0;
+    struct Rec {
+        long long pos = -1;  // file offset of the record payload (after the 8-byte length)
+        uint64_t len = 0;
+    };
+    std::vector<Rec> recs((size_t)nbr * slots);
+    for (int bi = 0; bi < nbr; bi++) {
+        const std::string fn = std::string(prefix) + "_" + std::to_string(bi) + ".bin";
+        FILE *f = fopen(fn.c_str(), "rb");
+        if (!f) return fail("open " + fn + ": " + strerror(errno));  // the reference panics in NewDiagCacheStream (gwas/filestream.go:56-61)
+        files.push_back(f);
+        uint64_t hdr[6];
+        std::vector<unsigned char> tab(2 * (size_t)d);
+        if (fread(hdr, 8, 6, f) != 6 || fread(tab.data(), 1, tab.size(), f) != tab.size()) return fail(fn + ": truncated header");
+        if (hdr[0] != (uint64_t)m_ct || hdr[1] != (uint64_t)maxLevel || hdr[3] != (uint64_t)N || hdr[4] != (uint64_t)nlF)
+            return fail(fn + ": header (vectorLen " + std::to_string(hdr[0]) + ", level " + std::to_string(hdr[1]) + ", n " + std::to_string(hdr[3]) +
+                        ", numModuli " + std::to_string(hdr[4]) + ") does not match the " + std::to_string(nrows) + " x " + std::to_string(ncols) +
+                        " matrix / parameters");
+        if (infer) {
+            for (int k = 0; k < d; k++) {
+                ca->baby[(size_t)bi * d + k] = tab[k] != 0;
+                ca->giant[(size_t)bi * d + k] = tab[d + k] != 0;
+            }
+        } else if (memcmp(tab.data(), &ca->baby[(size_t)bi * d], d) || memcmp(tab.data() + d, &ca->giant[(size_t)bi * d], d)) {
+            return fail(fn + ": baby / giant tables do not match the matrix shape");
+        }
+        long long pos = 48 + 2 * (long long)d;
+        for (;;) {
+            uint64_t len;
+            uint32_t sh;
+            if (fread(&len, 8, 1, f) != 1) break;  // EOF
+            if (len < 4 || fread(&sh, 4, 1, f) != 1) return fail(fn + ": truncated record");
+            if (sh >= (uint32_t)slots || (!infer && !ca->shiftT[(size_t)bi * slots + sh])) return fail(fn + ": unexpected diagonal " + std::to_string(sh));
+            if (recs[(size_t)bi * slots + sh].pos >= 0) return fail(fn + ": diagonal " + std::to_string(sh) + " appears twice");
+            recs[(size_t)bi * slots + sh] = Rec{pos + 8, len};
+            // nil flags of the block columns (isEmpty bytes sit between the polynomials)
+            long long p = pos + 12;
+            for (int bj = 0; bj < m_ct; bj++) {
+                unsigned char empty;
+                if (p + 1 > pos + 8 + (long long)len || fseeko(f, p, SEEK_SET) || fread(&empty, 1, 1, f) != 1) return fail(fn + ": malformed record");
+                p += 1 + (empty == 1 ? 0 : (long long)polyB);
+                int &pi = ca->pidx[((size_t)bi * slots + sh) * m_ct + bj];
+                if (infer) {
+                    if (empty != 1) pi = 0;  // numbered below
+                } else if ((pi >= 0) != (empty != 1)) {
+                    return fail(fn + ": diagonal " + std::to_string(sh) + ", block column " + std::to_string(bj) + ": nil flag does not match the matrix shape");
+                }
+                npoly_files += empty != 1;
+            }
+            if (p != pos + 8 + (long long)len) return fail(fn + ": record length does not match its contents");
+            if (infer) ca->shiftT[(size_t)bi * slots + sh] = 1;
+            pos += 8 + (long long)len;
+            if (fseeko(f, pos, SEEK_SET)) return fail(fn + ": seek failed");
+        }
+        for (int sh = 0; sh < slots; sh++)
+            if (ca->shiftT[(size_t)bi * slots + sh] && recs[(size_t)bi * slots + sh].pos < 0) return fail(fn + ": diagonal " + std::to_string(sh) + " missing");
+    }
+    if (infer) {
+        int n = 0;
+        for (int &pi : ca->pidx)
+            if (pi >= 0) pi = n++;
+        ca->npoly = (size_t)n;
+        if (cache_meta_finish(c, ca)) return fail("");
+    }
+    if (npoly_files != ca->npoly) return fail("cache files hold " + std::to_string(npoly_files) + " diagonals, expected " + std::to_string(ca->npoly));
+    // the image must be resident: there is no genotype matrix to regenerate it from
+    const TcGeomP &tc = ca->tc;
+    const size_t bytes = (size_t)tc.group_bytes * tc.ngroups;
+    if (ca->npoly == 0) return fail("cache_load_files: no diagonals");
+    if (cudaMalloc(&ca->img, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return fail("cache_load_files: the " + std::to_string(bytes >> 20) + " MiB image does not fit in HBM (loaded caches must be resident)");
+    }
+    ca->img_bytes = bytes;
+    if (cudaMemsetAsync(ca->img, 0, bytes, c->stream) != cudaSuccess) return fail("cudaMemset failed");
+    const int Kg = tc.Kg, K = tc.K;
+    const long long gbytes = tc_group_bytes(ca, tc.ntiles);
+    const size_t RB = (size_t)ca->lay.bytes;
+    const size_t cap = std::max<size_t>(1, env_size("SFG_CACHEFILE_CHUNK_POLYS", ((size_t)1 << 30) / polyB));
+    void *tmp, *dtab;
+    if (ws_get(c, WS_TMPP, (size_t)128 * Kg * RB, &tmp) || ws_get(c, WS_POFF, (size_t)128 * Kg * sizeof(long long), &dtab)) return fail("");
+    Buf draw, doff;
+    if (draw.alloc(c, cap * polyB) || doff.alloc(c, cap * sizeof(long long))) return fail("");
+    std::vector<unsigned char> hraw(cap * polyB), rec;
+    std::vector<long long> tab((size_t)128 * Kg), hoff;
+    auto flush = [&]() -> int {
+        if (hoff.empty()) return 0;
+        SFG_CUDA(c, cudaMemcpyAsync(draw.p, hraw.data(), hoff.size() * polyB, cudaMemcpyDefault, c->stream));
+        SFG_CUDA(c, cudaMemcpyAsync(doff.p, hoff.data(), hoff.size() * sizeof(long long), cudaMemcpyDefault, c->stream));
+        if (launch_file_to_rec(c, draw.as<uint64_t>(), doff.as<long long>(), (int)hoff.size(), nlF, ca->lay, tmp, c->stream)) return -1;
+        SFG_CUDA(c, cudaStreamSynchronize(c->stream));  // the staging buffers are reused
+        hoff.clear();
+        return 0;
+    };
+    for (int ct = 0; ct < tc.ntiles; ct++)
+        for (int grp = 0; grp < tc.ngroups; grp++) {
+            std::fill(tab.begin(), tab.end(), -1LL);
+            bool any = false;
+            for (int kk = 0; kk < Kg && grp * Kg + kk < K; kk++) {
+                const int k = grp * Kg + kk, bi = ca->kbi[k], b = ca->kb[k];
+                int cur_g = -1;
+                std::vector<long long> bjpos;  // payload offset of block column bj inside the current record, -1 = nil
+                for (int cc = 0; cc < 128; cc++) {
+                    const int col = ct * 128 + cc;
+                    if (col >= tc.ncols) break;
+                    const int g = ca->gact[col / m_ct], bj = col % m_ct, shift = g * d + b;
+                    if (shift >= slots || ca->pidx[((size_t)bi * slots + shift) * m_ct + bj] < 0) continue;
+                    if (g != cur_g) {  // read the record of (bi, shift) once for all its block columns in this tile
+                        const Rec &r = recs[(size_t)bi * slots + shift];
+                        rec.resize(r.len);
+                        if (fseeko(files[bi], r.pos, SEEK_SET) || fread(rec.data(), 1, r.len, files[bi]) != r.len) return fail("cache file: short read");
+                        bjpos.assign(m_ct, -1);
+                        uint64_t p = 4;
+                        for (int j = 0; j < m_ct; j++) {
+                            if (p >= r.len) return fail("cache file: malformed record");
+                            const bool empty = rec[p++] == 1;
+                            if (!empty) {
+                                if (p + polyB > r.len) return fail("cache file: malformed record");
+                                bjpos[j] = (long long)p;
+                                p += polyB;
+                            }
+                        }
+                        cur_g = g;
+                    }
+                    if (bjpos[bj] < 0) return fail("cache file: a diagonal the matrix shape requires is nil in the file");
+                    const long long off = (long long)((size_t)kk * 128 + cc) * (long long)RB;
+                    tab[(size_t)kk * 128 + cc] = off;
+                    memcpy(hraw.data() + hoff.size() * polyB, rec.data() + bjpos[bj], polyB);
+                    hoff.push_back(off);
+                    any = true;
+                    if (hoff.size() == cap && flush()) return fail("");
+                }
+            }
+            if (!any) continue;
+            if (flush()) return fail("");
+            if (cudaMemcpyAsync(dtab, tab.data(), tab.size() * sizeof(long long), cudaMemcpyDefault, c->stream) != cudaSuccess) return fail("cudaMemcpy failed");
+            if (launch_img_p(c, tc, ca->lay, tmp, (const long long *)dtab, tc.ntiles, ct, ca->img + (size_t)grp * gbytes, c->stream)) return fail("");
+            if (cudaStreamSynchronize(c->stream) != cudaSuccess) return fail("image build failed");  // tab / tmp are reused
+        }
+    for (FILE *f : files) fclose(f);
+    files.clear();
+    ca->materialised = true;
+    *out = ca;
     return 0;
 }
 

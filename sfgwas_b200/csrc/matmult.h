@@ -66,6 +66,9 @@ int cache_build(Ctx *c, Geno *g, int maxLevel, Cache **out);
 // one cached diagonal polynomial (plain canonical residues, [L][N]) read back out of the image; 0 = nil
 int cache_get_diag_dev(Ctx *c, const Cache *ca, int bi, int shift, int bj, uint64_t *d_out, int *present);
 void cache_destroy(Cache *cache);
+// the reference's on-disk cache format (gwas/filestream.go:19-282): <prefix>_<bi>.bin per block row
+int cache_write_files(Ctx *c, const Cache *ca, const char *prefix);
+int cache_load_files(Ctx *c, const char *prefix, size_t nrows, size_t ncols, int maxLevel, Cache **out);
 
 // full single-GPU compute: d_A device [s][nbr][2][nlA][N] -> d_out device [s][m_ct][2][L][N]
 int mm_compute_dev(Ctx *c, const uint64_t *d_A, int s, int nbr, int levelA, int maxLevel, Cache *cache, uint64_t *d_out);

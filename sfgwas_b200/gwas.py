@@ -215,6 +215,19 @@ class DiagCache:
         self.cps._check(self.cps.L.sfg_cache_get_diag(self.cps.h, self.h, bi, shift, bj, _p(out), C.byref(pr)), "sfg_cache_get_diag")
         return out if pr.value else None
 
+    def write_files(self, cacheFilePrefix: str):
+        """Write ``<prefix>_<bi>.bin`` in the reference's DiagCacheStream format (gwas/filestream.go:19-282), i.e. what the reference's
+        MatMult4StreamPreprocess leaves on disk for MatMult4StreamCompute."""
+        self.cps._check(self.cps.L.sfg_cache_write_files(self.cps.h, self.h, str(cacheFilePrefix).encode()), "sfg_cache_write_files")
+
+    @classmethod
+    def load_files(cls, cps: "CryptoParams", cacheFilePrefix: str, nrows: int, ncols: int, maxLevel: int = 5) -> "DiagCache":
+        """Build the HBM cache from DiagCacheStream files written by the reference for an nrows x ncols matrix."""
+        h = C.c_void_p()
+        cps._check(cps.L.sfg_cache_load_files(cps.h, str(cacheFilePrefix).encode(), int(nrows), int(ncols), int(maxLevel), C.byref(h)),
+                   "sfg_cache_load_files")
+        return cls(cps, h)
+
     def close(self):
         if getattr(self, "h", None):
             self.cps.L.sfg_cache_destroy(self.h)
@@ -228,11 +241,18 @@ class DiagCache:
 
 
 def MatMult4StreamPreprocess(cryptoParams: CryptoParams, gfs: GenoFileStream, maxLevel: int, cacheFilePrefix=None) -> DiagCache:
-    """gwas/matmult.go:914-1041. ``cacheFilePrefix`` is accepted for signature parity; the cache lives in HBM."""
+    """gwas/matmult.go:914-1041.  The cache lives in HBM; when ``cacheFilePrefix`` is given the reference's ``<prefix>_<bi>.bin``
+    files are written as well (skipped, like the reference does, when the first file already exists: gwas/filestream.go:47-53)."""
     h = C.c_void_p()
     cryptoParams._check(cryptoParams.L.sfg_matmult4_stream_preprocess(cryptoParams.h, gfs.h, maxLevel, C.byref(h)),
                         "MatMult4StreamPreprocess")
-    return DiagCache(cryptoParams, h)
+    dc = DiagCache(cryptoParams, h)
+    if cacheFilePrefix is not None:
+        import os
+
+        if not os.path.exists("%s_0.bin" % cacheFilePrefix):
+            dc.write_files(cacheFilePrefix)
+    return dc
 
 
 def MatMult4StreamCompute(cryptoParams: CryptoParams, A: np.ndarray, maxLevel: int, cache: DiagCache) -> np.ndarray:

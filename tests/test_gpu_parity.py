@@ -491,3 +491,54 @@ def test_partial_mod_reduce_finish_equals_compute(small13):
     for l in range(5):
         total[:, :, :, l, :] %= cps.Q[l]
     assert (total.astype(np.uint64) == single).all()
+
+
+@pytest.mark.parametrize("nr,nc", [(300, 520), (128, 77), (700, 130)])
+def test_diag_cache_files_interop(small13, tmp_path, nr, nc, monkeypatch):
+    """the reference's on-disk cache format (gwas/filestream.go:19-282).  GPU-written files are byte-identical to
+    the oracle's, and a cache loaded from the oracle's files (records shuffled, as the reference's goroutines may write them, and
+    staged in small chunks) computes the same ciphertexts bit for bit."""
+    from sfgwas_b200 import DiagCache, GenoFileStream, MatMult4StreamCompute, MatMult4StreamPreprocess, SfgError
+
+    o, cps, sk, keys = small13
+    rng = np.random.default_rng(nr * 1000 + nc)
+    X = rng.integers(0, 3, (nr, nc)).astype(np.int8)
+    dc = o.preprocess(X, 5, nproc=4)
+    ref_prefix, gpu_prefix = str(tmp_path / "ref"), str(tmp_path / "gpu")
+    o.cache_write_files(dc, ref_prefix)
+    o.cache_free(dc)
+    monkeypatch.setenv("SFG_CACHEFILE_CHUNK_POLYS", "7")  # exercise the chunked staging on small inputs
+    cache = MatMult4StreamPreprocess(cps, GenoFileStream.from_matrix(cps, X), 5, gpu_prefix)
+    nbr = (nr - 1) // o.slots + 1
+    for bi in range(nbr):
+        a = open("%s_%d.bin" % (ref_prefix, bi), "rb").read()
+        b = open("%s_%d.bin" % (gpu_prefix, bi), "rb").read()
+        assert len(a) == len(b) and a == b, "block row %d: files differ" % bi
+    # shuffle the records of the reference files (header + tables stay)
+    d = o.d
+    for bi in range(nbr):
+        raw = open("%s_%d.bin" % (ref_prefix, bi), "rb").read()
+        head, pos, recs = raw[: 48 + 2 * d], 48 + 2 * d, []
+        while pos < len(raw):
+            n = int.from_bytes(raw[pos:pos + 8], "little")
+            recs.append(raw[pos:pos + 8 + n])
+            pos += 8 + n
+        random.Random(bi).shuffle(recs)
+        open("%s_%d.bin" % (ref_prefix, bi), "wb").write(head + b"".join(recs))
+    loaded = DiagCache.load_files(cps, ref_prefix, nr, nc, 5)
+    assert loaded.num_polys == cache.num_polys and loaded.materialised
+    s = 2
+    A = np.zeros((s, nbr, 2, 6, o.N), dtype=np.uint64)
+    for i in range(s):
+        for b in range(nbr):
+            A[i, b] = o.encrypt_vector(sk, rng.normal(size=o.slots), 5, seed=50 + 7 * i + b)
+    want = MatMult4StreamCompute(cps, A, 5, cache)
+    assert (MatMult4StreamCompute(cps, A, 5, loaded) == want).all()
+    # shape taken from the files alone (what the reference's MatMult4StreamCompute has in hand: only the prefix)
+    inferred = DiagCache.load_files(cps, ref_prefix, 0, 0, 5)
+    assert inferred.num_polys == cache.num_polys and inferred.m_ct == cache.m_ct and inferred.num_block_rows == nbr
+    assert (MatMult4StreamCompute(cps, A, 5, inferred) == want).all()
+    with pytest.raises(SfgError, match="open .*missing_0.bin"):
+        DiagCache.load_files(cps, str(tmp_path / "missing"), nr, nc, 5)
+    with pytest.raises(SfgError, match="does not match"):
+        DiagCache.load_files(cps, ref_prefix, nr, nc + o.slots, 5)
