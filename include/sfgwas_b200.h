@@ -121,6 +121,13 @@ int sfg_matmult4_finish(sfg_ctx *ctx, const sfg_cache *cache, int s, int max_lev
 /* out = (a + b) mod q limb-wise on host buffers of ncts ciphertexts [2][nl][N] (combining per-rank partial sums) */
 int sfg_ct_add(sfg_ctx *ctx, const uint64_t *a, const uint64_t *b, int ncts, int nl, uint64_t *out);
 
+/* ---- genotype scan of the randomized-PCA sketch (gwas/pca.go:124-162) on the HBM-resident matrix ----
+ * localSketch[rand_index[i]][j] += sgn[i] * row_i[j];  xsum[j] += row_i[j];  x2sum[j] += row_i[j]^2   (rows with dosages 0/1/2).
+ * rand_index[nrows] in [0, kp), sgn[nrows] = +-1 (drawn by the caller's PRG); sketch [kp][ncols] float64 (exact integers), xsum /
+ * x2sum [ncols] uint64.  scan_ms (optional): device time of the scan. */
+int sfg_geno_count_sketch(sfg_ctx *ctx, const sfg_geno *g, const int32_t *rand_index, const int8_t *sgn, int kp, double *sketch,
+                          uint64_t *xsum, uint64_t *x2sum, float *scan_ms);
+
 /* ---- ciphertext algebra of the callers around the path --------------------------------------------
  * QXLazyNormStream / QXtLazyNormStream (gwas/matmult.go:27-77,83-116) wrap MatMult4StreamCompute in crypto.CMult, InnerProd,
  * InnerSumAll, CMultScalar, MaskTrunc and eval.Sub (crypto/basics.go:110-127,236-293,386-427,553-566); the network bootstrap

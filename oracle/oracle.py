@@ -184,6 +184,21 @@ def small_params(logN: int, shape: str = "pn13") -> dict:
     raise ValueError(shape)
 
 
+def count_sketch(X: np.ndarray, randIndex, sgn, kp: int):
+    """gwas/pca.go:152-162 restated: localSketch[randIndex[i]][j] += sgn[i] * float64(row[j]); xsum[j] += uint64(row[j]);
+    x2sum[j] += uint64(row[j] * row[j]) (int8 product, like the Go expression)."""
+    nind, nsnp = X.shape
+    sketch = np.zeros((kp, nsnp), dtype=np.float64)
+    xsum = np.zeros(nsnp, dtype=np.uint64)
+    x2sum = np.zeros(nsnp, dtype=np.uint64)
+    for i in range(nind):
+        row = X[i]
+        sketch[randIndex[i]] += float(sgn[i]) * row.astype(np.float64)
+        xsum += row.astype(np.int64).astype(np.uint64)
+        x2sum += (row * row).astype(np.int8).astype(np.int64).astype(np.uint64)
+    return sketch, xsum, x2sum
+
+
 class Oracle:
     """One CKKS ring context of the oracle (Lattigo ring.Ring + ckks.Parameters restated)."""
 

@@ -456,6 +456,11 @@ int sfg_cache_load_files(sfg_ctx *h, const char *prefix, size_t nrows, size_t nc
     return 0;
 }
 
+int sfg_geno_count_sketch(sfg_ctx *h, const sfg_geno *g, const int32_t *rand_index, const int8_t *sgn, int kp, double *sketch, uint64_t *xsum,
+                          uint64_t *x2sum, float *scan_ms) {
+    return geno_count_sketch(&h->c, g->g, rand_index, sgn, kp, sketch, xsum, x2sum, scan_ms);
+}
+
 // ---- ciphertext algebra of the callers (gwas/matmult.go:27-116) ----
 int sfg_ctx_set_relin_key(sfg_ctx *h, const uint64_t *key) {
     // stored as the "rotation by 0" key: galEl = 1, whose NTT permutation is the identity (rotation by 0 itself never key-switches)

@@ -40,6 +40,11 @@ int launch_mform(Ctx *c, uint64_t *p, int nlimbs, cudaStream_t st);  // [nlimbs]
 // optional squaring.  X is rows x ncols row-major.
 int launch_geno_prep(Ctx *c, int8_t *X, size_t rows, size_t ncols, double *sum, double *sqsum, bool square, cudaStream_t st);
 
+// count sketch + column sums of the PCA sketch (kernels_geno.cu; gwas/pca.go:152-162), see the kernel for the argument layout
+int launch_count_sketch(Ctx *c, const int8_t *X, size_t nrows, size_t ncols, const int *rows_sorted, const int8_t *sgn_sorted,
+                        const int *bucket_off, int kp, long long *sketch_i64, double *sketch_f64, unsigned long long *xsum,
+                        unsigned long long *x2sum, int *bad, cudaStream_t st);
+
 // ---- diagonal encoder (kernels_encode.cu) ----
 struct EncJob {
     int row0;        // first matrix row of the block row (bi*slots)

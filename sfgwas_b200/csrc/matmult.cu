@@ -1159,4 +1159,65 @@ int cache_load_files(Ctx *c, const char *prefix, size_t nrows, size_t ncols, int
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Count sketch + column sums of the randomized PCA (gwas/pca.go:124-162) on the HBM-resident genotype matrix.
+// rand_index[i] in [0, kp), sgn[i] = +-1 per row (the PRG draws stay with the caller: mpcObj.Network.Rand.CurPRG()).
+// d_ms: optional, time of the scan in milliseconds (CUDA events on the context's stream).
+// ---------------------------------------------------------------------------------------------------------------
+int geno_count_sketch(Ctx *c, const Geno *g, const int32_t *rand_index, const int8_t *sgn, int kp, double *sketch, uint64_t *xsum, uint64_t *x2sum,
+                      float *ms) {
+    if (g->filled != g->nrows) SFG_FAIL(c, "genotype matrix incomplete: %zu of %zu rows pushed", g->filled, g->nrows);
+    if (kp < 1) SFG_FAIL(c, "count sketch: kp = %d", kp);
+    SFG_CUDA(c, cudaSetDevice(c->device));
+    const size_t nrows = g->nrows, ncols = g->ncols;
+    std::vector<int> off(kp + 1, 0), rows(nrows);
+    std::vector<int8_t> sg(nrows);
+    for (size_t i = 0; i < nrows; i++) {
+        if (rand_index[i] < 0 || rand_index[i] >= kp) SFG_FAIL(c, "count sketch: randIndex[%zu] = %d outside [0, %d)", i, rand_index[i], kp);
+        if (sgn[i] != 1 && sgn[i] != -1) SFG_FAIL(c, "count sketch: sgn[%zu] = %d is not +-1", i, (int)sgn[i]);
+        off[rand_index[i] + 1]++;
+    }
+    for (int b = 0; b < kp; b++) off[b + 1] += off[b];
+    {
+        std::vector<int> cur(off.begin(), off.end() - 1);
+        for (size_t i = 0; i < nrows; i++) {
+            const int p = cur[rand_index[i]]++;
+            rows[p] = (int)i;
+            sg[p] = sgn[i];
+        }
+    }
+    Buf drows, dsg, doff, dsk, dskf, dx, dbad;
+    if (drows.alloc(c, nrows * 4) || dsg.alloc(c, nrows) || doff.alloc(c, (size_t)(kp + 1) * 4) || dsk.alloc(c, (size_t)kp * ncols * 8) ||
+        dskf.alloc(c, (size_t)kp * ncols * 8) || dx.alloc(c, 2 * ncols * 8) || dbad.alloc(c, 4))
+        return -1;
+    SFG_CUDA(c, cudaMemcpyAsync(drows.p, rows.data(), nrows * 4, cudaMemcpyDefault, c->stream));
+    SFG_CUDA(c, cudaMemcpyAsync(dsg.p, sg.data(), nrows, cudaMemcpyDefault, c->stream));
+    SFG_CUDA(c, cudaMemcpyAsync(doff.p, off.data(), (size_t)(kp + 1) * 4, cudaMemcpyDefault, c->stream));
+    SFG_CUDA(c, cudaMemsetAsync(dsk.p, 0, (size_t)kp * ncols * 8, c->stream));
+    SFG_CUDA(c, cudaMemsetAsync(dx.p, 0, 2 * ncols * 8, c->stream));
+    SFG_CUDA(c, cudaMemsetAsync(dbad.p, 0, 4, c->stream));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaEventRecord(e0, c->stream);
+    const int rc = launch_count_sketch(c, g->d, nrows, ncols, drows.as<int>(), dsg.as<int8_t>(), doff.as<int>(), kp, dsk.as<long long>(), dskf.as<double>(),
+                                       dx.as<unsigned long long>(), dx.as<unsigned long long>() + ncols, dbad.as<int>(), c->stream);
+    cudaEventRecord(e1, c->stream);
+    int bad = 0;
+    cudaError_t e = rc ? cudaSuccess : cudaMemcpyAsync(&bad, dbad.p, 4, cudaMemcpyDefault, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    float t = 0;
+    if (!rc && e == cudaSuccess) cudaEventElapsedTime(&t, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (rc) return -1;
+    SFG_CUDA(c, e);
+    if (bad) SFG_FAIL(c, "count sketch: a genotype outside {0, 1, 2} (missing values must already be replaced, gwas/filestream.go:349-351)");
+    if (ms) *ms = t;
+    SFG_CUDA(c, cudaMemcpy(sketch, dskf.p, (size_t)kp * ncols * 8, cudaMemcpyDefault));
+    SFG_CUDA(c, cudaMemcpy(xsum, dx.p, ncols * 8, cudaMemcpyDefault));
+    SFG_CUDA(c, cudaMemcpy(x2sum, dx.as<uint64_t>() + ncols, ncols * 8, cudaMemcpyDefault));
+    return 0;
+}
+
 }  // namespace sfg

@@ -86,6 +86,8 @@ int mul_relin_dev(Ctx *c, int level, const uint64_t *d_x, int nx, int x_nl, cons
 int mul_plain_dev(Ctx *c, int level, const uint64_t *d_pt, int npt, int pt_nl, const uint64_t *d_ct, int nct, int ct_nl, int times, uint64_t *d_out);
 int addsub_dev(Ctx *c, int level, const uint64_t *d_a, int na, int a_nl, const uint64_t *d_b, int nb, int b_nl, bool sub, uint64_t *d_out);
 int inner_sum_all_dev(Ctx *c, int level, const uint64_t *d_in, int nvec, int cnt, uint64_t *d_out);
+int geno_count_sketch(Ctx *c, const Geno *g, const int32_t *rand_index, const int8_t *sgn, int kp, double *sketch, uint64_t *xsum, uint64_t *x2sum,
+                      float *ms);
 int encode_slots_host(Ctx *c, const int8_t *v, int level, bool mont, uint64_t *out);
 
 extern thread_local float g_last_ms[5];  // baby, mac phase, giant, total, mac kernel only

@@ -187,6 +187,21 @@ class GenoFileStream:
             return out, present.astype(bool), co
         return out, present.astype(bool)
 
+    def CountSketch(self, randIndex, sgn, kp: int, want_ms: bool = False):
+        """The sketching loop of gwas/pca.go:152-162 over all rows: returns (localSketch [kp][ncols] float64, xsum, x2sum [ncols] uint64).
+        ``randIndex[i]`` in [0, kp) and ``sgn[i]`` = +-1 are the caller's PRG draws (pca.go:129-131)."""
+        ri = np.ascontiguousarray(randIndex, dtype=np.int32)
+        sg = np.ascontiguousarray(sgn, dtype=np.int8)
+        if ri.shape != (self.nrows,) or sg.shape != (self.nrows,):
+            raise SfgError("randIndex / sgn must have one entry per row")
+        sk = np.zeros((kp, self.ncols), dtype=np.float64)
+        xs = np.zeros(self.ncols, dtype=np.uint64)
+        x2 = np.zeros(self.ncols, dtype=np.uint64)
+        ms = C.c_float()
+        self.cps._check(self.cps.L.sfg_geno_count_sketch(self.cps.h, self.h, _p(ri), _p(sg), int(kp), _p(sk), _p(xs), _p(x2), C.byref(ms)),
+                        "sfg_geno_count_sketch")
+        return (sk, xs, x2, ms.value) if want_ms else (sk, xs, x2)
+
     def close(self):
         if getattr(self, "h", None):
             self.cps.L.sfg_geno_destroy(self.h)

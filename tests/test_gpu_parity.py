@@ -542,3 +542,57 @@ def test_diag_cache_files_interop(small13, tmp_path, nr, nc, monkeypatch):
         DiagCache.load_files(cps, str(tmp_path / "missing"), nr, nc, 5)
     with pytest.raises(SfgError, match="does not match"):
         DiagCache.load_files(cps, ref_prefix, nr, nc + o.slots, 5)
+
+
+@pytest.mark.parametrize("nr,nc,kp", [(300, 520, 7), (1000, 4096 + 48, 15), (77, 131, 3), (5, 16, 20)])
+def test_count_sketch_bit_exact(small13, nr, nc, kp):
+    """SURVEY 8f row 1 (gwas/pca.go:152-162): count sketch + column sums, exact integers; aligned (ncols % 16 == 0) and ragged widths,
+    empty buckets, more buckets than rows."""
+    from oracle.oracle import count_sketch
+    from sfgwas_b200 import GenoFileStream, SfgError
+
+    o, cps, sk, keys = small13
+    rng = np.random.default_rng(nr + nc + kp)
+    X = rng.integers(0, 3, (nr, nc)).astype(np.int8)
+    ri = rng.integers(0, kp, nr).astype(np.int32)
+    if kp > 2:
+        ri[ri == 1] = 0  # an empty bucket
+    sg = (rng.integers(0, 2, nr) * 2 - 1).astype(np.int8)
+    gfs = GenoFileStream.from_matrix(cps, X)
+    got = gfs.CountSketch(ri, sg, kp)
+    want = count_sketch(X, ri, sg, kp)
+    for g, w in zip(got, want):
+        assert g.dtype == w.dtype and (g == w).all()
+    Xbad = X.copy()
+    Xbad[nr // 2, nc // 2] = -1  # a missing value that was not replaced
+    with pytest.raises(SfgError, match="outside"):
+        GenoFileStream.from_matrix(cps, Xbad).CountSketch(ri, sg, kp)
+    with pytest.raises(SfgError, match="randIndex"):
+        gfs.CountSketch(np.full(nr, kp, dtype=np.int32), sg, kp)
+
+
+def test_count_sketch_full_size_properties(small13):
+    """Config-2 shaped scan (10 000 x 100 000 int8, kp = 10): checked through size-independent properties -- the bucket rows of the sketch
+    with all signs +1 sum to xsum, x2sum = xsum + 2 * (#twos), and the signed sketch equals (sum of + rows) - (sum of - rows) on a column
+    sample computed by numpy."""
+    from sfgwas_b200 import GenoFileStream
+
+    o, cps, sk, keys = small13
+    rng = np.random.default_rng(7)
+    nr, nc, kp = 10000, 100000, 10
+    X = rng.integers(0, 3, (nr, nc), dtype=np.int8)
+    ri = rng.integers(0, kp, nr).astype(np.int32)
+    sg = (rng.integers(0, 2, nr) * 2 - 1).astype(np.int8)
+    gfs = GenoFileStream.from_matrix(cps, X)
+    sk1, xs, x2, ms = gfs.CountSketch(ri, np.ones(nr, dtype=np.int8), kp, want_ms=True)
+    assert (sk1.sum(axis=0) == xs.astype(np.float64)).all()
+    cols = rng.choice(nc, 64, replace=False)
+    Xc = X[:, cols].astype(np.int64)
+    assert (xs[cols] == Xc.sum(axis=0).astype(np.uint64)).all()
+    assert (x2[cols] == (Xc * Xc).sum(axis=0).astype(np.uint64)).all()
+    sk2, xs2, x22, ms2 = gfs.CountSketch(ri, sg, kp, want_ms=True)
+    assert (xs2 == xs).all() and (x22 == x2).all()
+    for b in range(kp):
+        m = ri == b
+        assert (sk2[b, cols] == (Xc[m] * sg[m, None].astype(np.int64)).sum(axis=0)).all()
+    print("count sketch scan: %.3f ms -> %.0f GB/s of int8 genotypes" % (ms2, nr * nc / ms2 / 1e6))
