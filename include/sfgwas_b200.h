@@ -162,6 +162,10 @@ int sfg_ctx_sync(sfg_ctx *ctx);
  * d_A [s][nbr][2][level_a+1][N] and d_out [s][m_ct][2][max_level][N] are DEVICE pointers. */
 int sfg_matmult4_stream_compute_dev(sfg_ctx *ctx, const uint64_t *d_A, int s, int num_block_rows, int level_a, int max_level,
                                     const sfg_cache *cache, uint64_t *d_out);
+/* device-resident variants of sfg_ntt / sfg_rotate_right (d_* are DEVICE pointers; same layouts) for the NTT / key-switch throughput
+ * sweep of BASELINE config 3 (profiles/sweep_ntt_ks.py) */
+int sfg_ntt_dev(sfg_ctx *ctx, uint64_t *d_polys, int npoly, const int *limb_idx, int nsel, int inverse);
+int sfg_rotate_right_dev(sfg_ctx *ctx, int level, const uint64_t *d_cts, int nct, int nrot, uint64_t *d_out);
 /* last call's phase timings in milliseconds (CUDA events on the context stream):
  * {baby rotations, MAC phase, giant rotations, total, MAC kernel alone} */
 int sfg_ctx_last_timings(const sfg_ctx *ctx, float out_ms[5]);

@@ -199,6 +199,19 @@ def count_sketch(X: np.ndarray, randIndex, sgn, kp: int):
     return sketch, xsum, x2sum
 
 
+def sweep_params(logN: int) -> dict:
+    """Full modulus chains of the BASELINE sweep (config 3: logN 12-16), shaped like the recalled Lattigo v2 defaults PN12QP109 ..
+    PN16QP1761 ([UNVERIFIED]): (nQ, nP) = (2,1), (6,1), (10,2), (18,3), (34,4).  Primes are generated here (q = 1
+    mod 2N) with the default sets' bit widths; the library always takes the chain from the caller."""
+    shape = {12: (37, 32, 2, 38, 1, 32), 13: (33, 30, 6, 36, 1, 30), 14: (45, 34, 10, 43, 2, 34), 15: (50, 40, 18, 50, 3, 40),
+             16: (55, 45, 34, 55, 4, 45)}[logN]
+    q0b, qb, nQ, pb, nP, sc = shape
+    q0 = gen_primes(logN, q0b, 1)
+    q = q0 + gen_primes(logN, qb, nQ - 1, avoid=q0)
+    p = gen_primes(logN, pb, nP, avoid=q)
+    return dict(logN=logN, Q=q, P=p, scale=float(1 << sc))
+
+
 class Oracle:
     """One CKKS ring context of the oracle (Lattigo ring.Ring + ckks.Parameters restated)."""
 

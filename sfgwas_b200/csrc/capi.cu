@@ -461,6 +461,24 @@ int sfg_geno_count_sketch(sfg_ctx *h, const sfg_geno *g, const int32_t *rand_ind
     return geno_count_sketch(&h->c, g->g, rand_index, sgn, kp, sketch, xsum, x2sum, scan_ms);
 }
 
+int sfg_ntt_dev(sfg_ctx *h, uint64_t *d_polys, int npoly, const int *limb_idx, int nsel, int inverse) {
+    Ctx *c = &h->c;
+    if (nsel < 1 || nsel > kMaxLimbs || npoly % nsel) SFG_FAIL(c, "sfg_ntt_dev: npoly must be a multiple of nsel (<= %d)", kMaxLimbs);
+    SFG_CUDA(c, cudaSetDevice(c->device));
+    LimbSel sel;
+    sel.n = nsel;
+    for (int i = 0; i < nsel; i++) {
+        if (limb_idx[i] < 0 || limb_idx[i] >= c->nQP) SFG_FAIL(c, "sfg_ntt_dev: modulus index %d out of range", limb_idx[i]);
+        sel.idx[i] = limb_idx[i];
+    }
+    return launch_ntt(c, d_polys, (size_t)nsel * c->N, d_polys, (size_t)nsel * c->N, npoly, sel, inverse != 0, c->stream);
+}
+int sfg_rotate_right_dev(sfg_ctx *h, int level, const uint64_t *d_cts, int nct, int nrot, uint64_t *d_out) {
+    Ctx *c = &h->c;
+    if (level < 0 || level >= c->nQ || nct < 1) SFG_FAIL(c, "sfg_rotate_right_dev: bad level / count");
+    return rotate_right_dev(c, level, d_cts, nct, nrot, d_out);
+}
+
 // ---- ciphertext algebra of the callers (gwas/matmult.go:27-116) ----
 int sfg_ctx_set_relin_key(sfg_ctx *h, const uint64_t *key) {
     // stored as the "rotation by 0" key: galEl = 1, whose NTT permutation is the identity (rotation by 0 itself never key-switches)

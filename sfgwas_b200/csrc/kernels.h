@@ -11,7 +11,7 @@ struct LimbSel {
 
 // Byte layout of one [nl][N] polynomial record with a per-limb element size: 8 = uint64 residues (the reference's
 // layout; plaintext diagonals in Montgomery form), 4 = PACKED uint32 residues for moduli < 2^32 (plain, not Montgomery).
-constexpr int kMaxLayoutLimbs = 16;
+constexpr int kMaxLayoutLimbs = kMaxLimbs;  // full chains of the logN 15 / 16 sweep: 18 and 34 Q limbs
 struct PolyLayout {
     int nl;
     int es[kMaxLayoutLimbs];

@@ -41,6 +41,13 @@ struct TgtSel {  // targets (or limbs) of one arithmetic class
     int tt[kMaxLimbs];
 };
 
+// rings larger than one CTA's shared memory take the unfused key-switch (rotate_big); SFG_KS_UNFUSED=1 forces it for any ring so
+// that the tests can run both implementations against each other on the same inputs
+static bool ks_unfused(const Ctx *c) {
+    static const bool forced = [] { const char *e = getenv("SFG_KS_UNFUSED"); return e && *e == '1'; }();
+    return c->logN > 14 || forced;
+}
+
 // ---- Galois key conversion (once per key upload) ----------------------------------------------------------------------
 // in : Lattigo SwitchingKey [beta][2][nQP][N] u64, NTT + Montgomery form.
 // out: same shape, every polynomial in TT order; wide moduli keep the Montgomery u64, narrow moduli (q < 2^31) become
@@ -65,6 +72,10 @@ __global__ void k_key_convert(const uint64_t *__restrict__ in, uint64_t *__restr
     }
 }
 int launch_key_convert(Ctx *c, const uint64_t *in, uint64_t *out, cudaStream_t st) {
+    if (ks_unfused(c)) {  // the unfused key-switch of large rings reads Lattigo's layout directly
+        SFG_CUDA(c, cudaMemcpyAsync(out, in, (size_t)c->beta * 2 * c->nQP * c->N * 8, cudaMemcpyDefault, st));
+        return 0;
+    }
     dim3 g(std::max(1, c->N / 256), c->beta * 2 * c->nQP);
     k_key_convert<<<g, 256, 0, st>>>(in, out, c->N, c->nQP, c->lc);
     SFG_LAUNCHED(c, "k_key_convert", st);
@@ -528,15 +539,130 @@ static int rotate_chunk(Ctx *c, const KsBatch &b, BaseConv *ks, BaseConv *md, ui
     return 0;
 }
 
+// ---- rings larger than one CTA's shared memory (logN 15, 16): the same algorithm, unfused ----------------------------------------
+// The BASELINE sweep runs NTT / rotation / key-switch up to logN = 16 with the full modulus chain (18 + 3 and 34 + 4 moduli).  A ring of
+// 2^15 64-bit residues does not fit one CTA, so the steps of switchKeysInPlace run as separate streaming kernels around the
+// global-memory transforms of kernels_ntt.cu; keys stay in Lattigo's layout ([beta][2][nQP][N], NTT + Montgomery form).
+__global__ void k_ksb_gather_c1(const uint64_t *__restrict__ in, const long long *__restrict__ src_off, int in_nl, int nl, int N, uint64_t *__restrict__ c2) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, l = blockIdx.y, t = blockIdx.z;
+    if (j < N) c2[((size_t)t * nl + l) * N + j] = in[src_off[t] + ((size_t)in_nl + l) * N + j];
+}
+// digit i of every ciphertext, reduced / base-converted to every target modulus (coefficient domain); a target inside the digit
+// takes the NTT-domain input limb as it is (decomposeAndSplitNTT)
+__global__ void k_ksb_extend(const uint64_t *__restrict__ in, const long long *__restrict__ in_off, int in_nl, const uint64_t *__restrict__ c2,
+                             const int *__restrict__ c2_slot, const BaseConv *__restrict__ ks, int digit, int nl, int nt, int nQ, int N,
+                             const LimbConst *__restrict__ lcs, uint64_t *__restrict__ ext) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, tt = blockIdx.y, ct = blockIdx.z;
+    if (j >= N) return;
+    const BaseConv &bc = ks[(size_t)digit * nt + tt];
+    uint64_t v;
+    if (bc.ns == 0) {
+        v = in[in_off[ct] + ((size_t)in_nl + tt) * N + j];
+    } else {
+        const int tgt = tt < nl ? tt : nQ + (tt - nl);
+        const uint64_t *c2ct = c2 + (size_t)c2_slot[ct] * nl * N;
+        uint64_t xs[kMaxAlpha];
+        for (int k = 0; k < bc.ns; k++) xs[k] = c2ct[(size_t)bc.src_limb[k] * N + j];
+        v = base_conv_coeff(bc, xs, lcs, lcs[tgt].q);
+    }
+    ext[((size_t)ct * nt + tt) * N + j] = v;
+}
+__global__ void k_ksb_mac(const uint64_t *__restrict__ ext, const uint64_t *const *__restrict__ keys, int digit, int nl, int nt, int nQ, int nQP, int N,
+                          const LimbConst *__restrict__ lcs, int first, uint64_t *__restrict__ acc) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, tt = blockIdx.y, ct = blockIdx.z;
+    if (j >= N) return;
+    const int tgt = tt < nl ? tt : nQ + (tt - nl);
+    const LimbConst lc = lcs[tgt];
+    const uint64_t d = ext[((size_t)ct * nt + tt) * N + j];
+    const uint64_t *key = keys[ct];
+#pragma unroll
+    for (int comp = 0; comp < 2; comp++) {
+        const uint64_t p = mred(d, key[((size_t)(digit * 2 + comp) * nQP + tgt) * N + j], lc);
+        uint64_t *a = acc + ((size_t)(ct * 2 + comp) * nt + tt) * N + j;
+        *a = first ? p : add_mod(*a, p, lc.q);
+    }
+}
+__global__ void k_ksb_mdext(const uint64_t *__restrict__ acc, const BaseConv *__restrict__ md, int nl, int nt, int nP, int L, int N,
+                            const LimbConst *__restrict__ lcs, uint64_t *__restrict__ E) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, l = blockIdx.y, p = blockIdx.z;  // p = ct * 2 + comp
+    if (j >= N) return;
+    const uint64_t *accP = acc + ((size_t)p * nt + nl) * N;
+    uint64_t xs[kMaxAlpha];
+    for (int k = 0; k < nP; k++) xs[k] = accP[(size_t)k * N + j];
+    E[((size_t)p * L + l) * N + j] = base_conv_coeff(md[l], xs, lcs, lcs[l].q);
+}
+__global__ void k_ksb_final(const uint64_t *__restrict__ in, const long long *__restrict__ in_off, const uint64_t *__restrict__ acc,
+                            const uint64_t *__restrict__ E, const uint64_t *__restrict__ pinv, const uint32_t *const *__restrict__ perms, int nt, int L,
+                            int N, const LimbConst *__restrict__ lcs, unsigned char *__restrict__ out, const long long *__restrict__ out_off,
+                            PolyLayout olay, int accumulate) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x, l = blockIdx.y, p = blockIdx.z, ct = p >> 1, comp = p & 1;
+    if (k >= N) return;
+    const uint64_t q = lcs[l].q;
+    const int j = (int)perms[ct][k];  // PermuteNTTWithIndexLvl: out[k] = in[index[k]]
+    uint64_t v = mul_shoup(sub_mod(acc[((size_t)p * nt + l) * N + j], E[((size_t)p * L + l) * N + j], q), pinv[2 * l], pinv[2 * l + 1], q);
+    if (comp == 0) v = add_mod(v, in[in_off[ct] + (size_t)l * N + j], q);
+    uint64_t *o = reinterpret_cast<uint64_t *>(out + out_off[ct] + (size_t)comp * olay.bytes + olay.off[l]) + k;
+    *o = accumulate ? add_mod(*o, v, q) : v;
+}
+
+static int rotate_big(Ctx *c, const KsBatch &b, BaseConv *ks, BaseConv *md, uint64_t *pinv, cudaStream_t st) {
+    const int N = c->N, nl = b.level + 1, nP = c->nP, nt = nl + nP, nQ = c->nQ, L = b.out_layout.nl, alpha = nP, beta = (nl + alpha - 1) / alpha;
+    for (int l = 0; l < L; l++)
+        if (b.out_layout.es[l] != 8) SFG_FAIL(c, "key-switch for logN > 14 writes the u64 layout only");
+    const unsigned gx = (unsigned)((N + 255) / 256);
+    k_ksb_gather_c1<<<dim3(gx, nl, b.n_c2), 256, 0, st>>>(b.in, b.c2_src_off, b.in_nl, nl, N, b.c2);
+    SFG_LAUNCHED(c, "k_ksb_gather_c1", st);
+    LimbSel selq;
+    selq.n = nl;
+    for (int i = 0; i < nl; i++) selq.idx[i] = i;
+    if (launch_ntt(c, b.c2, (size_t)nl * N, b.c2, (size_t)nl * N, b.n_c2 * nl, selq, true, st)) return -1;
+    for (int k0 = 0; k0 < b.nct; k0 += b.acc_cap) {
+        const int n = std::min(b.acc_cap, b.nct - k0);
+        void *pe;
+        if (ws_get(c, WS_KSB, (size_t)n * std::max(nt, 2 * L) * N * 8, &pe)) return -1;
+        uint64_t *ext = (uint64_t *)pe;
+        for (int i = 0; i < beta; i++) {
+            k_ksb_extend<<<dim3(gx, nt, n), 256, 0, st>>>(b.in, b.in_off + k0, b.in_nl, b.c2, b.c2_slot + k0, ks, i, nl, nt, nQ, N, c->lc, ext);
+            SFG_LAUNCHED(c, "k_ksb_extend", st);
+            // forward NTT of every target outside the digit: the ranges [0, lo) and [hi, nt)
+            const int lo = i * alpha, hi = std::min((i + 1) * alpha, nl);
+            for (int part = 0; part < 2; part++) {
+                const int t0 = part ? hi : 0, t1 = part ? nt : lo;
+                if (t1 <= t0) continue;
+                LimbSel sel;
+                sel.n = t1 - t0;
+                for (int tt = t0; tt < t1; tt++) sel.idx[tt - t0] = tt < nl ? tt : nQ + (tt - nl);
+                if (launch_ntt(c, ext + (size_t)t0 * N, (size_t)nt * N, ext + (size_t)t0 * N, (size_t)nt * N, n * sel.n, sel, false, st)) return -1;
+            }
+            k_ksb_mac<<<dim3(gx, nt, n), 256, 0, st>>>(ext, b.keys + k0, i, nl, nt, nQ, c->nQP, N, c->lc, i == 0 ? 1 : 0, b.acc);
+            SFG_LAUNCHED(c, "k_ksb_mac", st);
+        }
+        LimbSel selp;
+        selp.n = nP;
+        for (int i = 0; i < nP; i++) selp.idx[i] = nQ + i;
+        if (launch_ntt(c, b.acc + (size_t)nl * N, (size_t)nt * N, b.acc + (size_t)nl * N, (size_t)nt * N, n * 2 * nP, selp, true, st)) return -1;
+        k_ksb_mdext<<<dim3(gx, L, n * 2), 256, 0, st>>>(b.acc, md, nl, nt, nP, L, N, c->lc, ext);
+        SFG_LAUNCHED(c, "k_ksb_mdext", st);
+        LimbSel sell;
+        sell.n = L;
+        for (int i = 0; i < L; i++) sell.idx[i] = i;
+        if (launch_ntt(c, ext, (size_t)L * N, ext, (size_t)L * N, n * 2 * L, sell, false, st)) return -1;
+        k_ksb_final<<<dim3(gx, L, n * 2), 256, 0, st>>>(b.in, b.in_off + k0, b.acc, ext, pinv, b.perms + k0, nt, L, N, c->lc, (unsigned char *)b.out,
+                                                         b.out_off + k0, b.out_layout, b.accumulate ? 1 : 0);
+        SFG_LAUNCHED(c, "k_ksb_final", st);
+    }
+    return 0;
+}
+
 int launch_rotate(Ctx *c, const KsBatch &b, cudaStream_t st) {
     if (b.nct <= 0) return 0;
-    if (c->logN > 14) SFG_FAIL(c, "fused key-switch kernels support logN <= 14 (got %d)", c->logN);
     if (c->logN < 6) SFG_FAIL(c, "logN >= 6 required");
     if (b.acc_cap < 1) SFG_FAIL(c, "key-switch scratch is empty");
     const int N = c->N, nl = b.level + 1;
     BaseConv *ks, *md;
     uint64_t *pinv;
     if (ctx_get_ks_tables(c, b.level, &ks, &md, &pinv)) return -1;
+    if (ks_unfused(c)) return rotate_big(c, b, ks, md, pinv, st);
     // 1. c2 = INTT(c1), once per distinct input ciphertext
     LimbSel sel;
     sel.n = nl;

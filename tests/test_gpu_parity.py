@@ -596,3 +596,45 @@ def test_count_sketch_full_size_properties(small13):
         m = ri == b
         assert (sk2[b, cols] == (Xc[m] * sg[m, None].astype(np.int64)).sum(axis=0)).all()
     print("count sketch scan: %.3f ms -> %.0f GB/s of int8 genotypes" % (ms2, nr * nc / ms2 / 1e6))
+
+
+@pytest.mark.parametrize("logN", [12, 13, 14, 15, 16])
+def test_sweep_full_chain_ntt_and_rotation(logN):
+    """BASELINE config 3: NTT / INTT and rotation (hybrid key-switch + automorphism) at logN 12-16 with the FULL modulus chain
+    ((nQ, nP) = (2,1), (6,1), (10,2), (18,3), (34,4)), top level, bit-exact against the oracle.  logN 15 and 16 run the unfused
+    large-ring key-switch (a 2^15-coefficient limb does not fit one CTA's shared memory)."""
+    from oracle.oracle import sweep_params
+
+    o, cps = make(sweep_params(logN))
+    rng = np.random.default_rng(logN)
+    top = o.nQ - 1
+    # NTT / INTT over every modulus of the chain (Q and P)
+    idx = list(range(o.nQP))
+    mods = o.Q + o.P
+    polys = np.stack([rng.integers(0, mods[l], o.N, dtype=np.uint64) for l in idx])
+    fw = cps.NTT(polys, idx)
+    assert (fw == np.stack([o.ntt(l, polys[l].copy()) for l in idx])).all()
+    assert (cps.NTT(fw, idx, inverse=True) == polys).all()
+    # rotation by 1 and by d with random keys of the right shape, a batch of 2 ciphertexts at the top level
+    sk = o.keygen_secret(5)
+    cts = np.stack([np.stack([np.stack([rng.integers(0, o.Q[l], o.N, dtype=np.uint64) for l in range(top + 1)]) for _ in range(2)])
+                    for _ in range(2)])
+    for k in (1, o.d):
+        swk = o.gen_rotation_key(sk, k)
+        cps.SetRotKey(k, swk)
+        got = cps.RotateRightWithEvaluator(cts, -k)
+        for t in range(2):
+            assert (got[t] == o.rotate_right(cts[t], -k, swk)).all(), (logN, k, t)
+    cps.close()
+
+
+def test_unfused_keyswitch_equals_fused_on_small_rings():
+    """The large-ring (logN 15 / 16) key-switch kernels, forced onto small rings (SFG_KS_UNFUSED=1 is read once per process, hence the
+    subprocess), must pass the same oracle / Python-bignum rotation tests as the fused kernels."""
+    import subprocess
+    import sys
+
+    env = dict(os.environ, SFG_KS_UNFUSED="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-k",
+                        "test_rotate_vs_oracle or test_rotate_vs_python_bignum_tiny"], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
