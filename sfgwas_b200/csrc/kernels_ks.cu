@@ -65,8 +65,11 @@ __global__ void k_key_convert(const uint64_t *__restrict__ in, uint64_t *__restr
         if (kind == kArD) {
             o = (uint64_t)__double_as_longlong((double)(long long)mred(km, 1, lc));  // plain residue as an FP64 integer
         } else if (kind != kArW) {
+            // 32-bit Montgomery form k * 2^32 mod q in the FIRST HALF of the polynomial's slot (4 bytes per coefficient: half the
+            // L2 -> SM traffic of a (k, floor(k 2^32 / q)) Shoup pair; the product costs one more IMAD)
             const uint64_t k = mred(km, 1, lc);  // InvMForm
-            o = k | (((k << 32) / lc.q) << 32);
+            reinterpret_cast<uint32_t *>(dst)[tt_index(j, N)] = (uint32_t)((k << 32) % lc.q);
+            continue;
         }
         dst[tt_index(j, N)] = o;
     }
@@ -141,9 +144,9 @@ k_ks_inner2(const uint64_t *__restrict__ in, const long long *__restrict__ in_of
                 s1a[sj] = add_mod(s1a[sj], mred(v, __ldg(k1 + (size_t)k * NP), lc), lc.q);
             } else {
                 const int sj = sidx<sizeof(T)>(abase + k);
-                const uint2 w0 = __ldg(reinterpret_cast<const uint2 *>(k0) + (size_t)k * NP);
-                const uint2 w1 = __ldg(reinterpret_cast<const uint2 *>(k1) + (size_t)k * NP);
-                uint32_t p0 = A::mul_lazy(v, w0, c), p1 = A::mul_lazy(v, w1, c);
+                const uint32_t w0 = __ldg(reinterpret_cast<const uint32_t *>(k0 - P) + P + (size_t)k * NP);
+                const uint32_t w1 = __ldg(reinterpret_cast<const uint32_t *>(k1 - P) + P + (size_t)k * NP);
+                uint32_t p0 = ArN30::mul_mont(v, w0, c), p1 = ArN30::mul_mont(v, w1, c);
                 p0 = min(p0, p0 - c.q) + s0a[sj];
                 p1 = min(p1, p1 - c.q) + s1a[sj];
                 s0a[sj] = min(p0, p0 - c.q);
@@ -163,8 +166,13 @@ k_ks_inner2(const uint64_t *__restrict__ in, const long long *__restrict__ in_of
             }
             __syncthreads();
             if (active) {
+                if constexpr (A::kKind == kArN30 || A::kKind == kArN31) {  // 64-register classes: bound the loads in flight
+#pragma unroll 4
+                    for (int k = 0; k < kLastE; k++) mac(0, s[sidx<sizeof(T)>(kLastE * threadIdx.x + k)], k);
+                } else {
 #pragma unroll
-                for (int k = 0; k < kLastE; k++) mac(0, s[sidx<sizeof(T)>(kLastE * threadIdx.x + k)], k);
+                    for (int k = 0; k < kLastE; k++) mac(0, s[sidx<sizeof(T)>(kLastE * threadIdx.x + k)], k);
+                }
             }
         } else {
             // coefficient-domain value of global coefficient g of this digit, reduced / base-converted to the target modulus

@@ -159,11 +159,18 @@ struct ArN30 {
     using TW = uint2;  // (w, floor(w 2^32 / q))
     static constexpr int kKind = kArN30;
     struct C {
-        uint32_t q, q2, ninv, ninv_sh;
+        uint32_t q, q2, ninv, ninv_sh, qinv;
         uint64_t q64, bred_hi;
     };
     __device__ static __forceinline__ C make(const LimbConst &lc) {
-        return C{(uint32_t)lc.q, (uint32_t)(2 * lc.q), (uint32_t)lc.ninv, (uint32_t)(lc.ninv_sh >> 32), lc.q, lc.bred_hi};
+        return C{(uint32_t)lc.q, (uint32_t)(2 * lc.q), (uint32_t)lc.ninv, (uint32_t)(lc.ninv_sh >> 32), (uint32_t)lc.qinv, lc.q, lc.bred_hi};
+    }
+    // y * k mod q in [0, 2q) for any 32-bit y, km = k * 2^32 mod q (32-bit Montgomery form), qinv = q^-1 mod 2^32
+    __device__ static __forceinline__ T mul_mont(T y, uint32_t km, const C &c) {
+        const uint32_t lo = y * km, hi = __umulhi(y, km);
+        uint32_t m;  // opaque to the optimiser: it would otherwise precompute km * qinv for every key word ahead of time and spill them
+        asm("mul.lo.u32 %0, %1, %2;" : "=r"(m) : "r"(lo), "r"(c.qinv));
+        return hi - __umulhi(m, c.q) + c.q;
     }
     __device__ static __forceinline__ T mul_lazy(T y, TW w, const C &c) { return y * w.x - __umulhi(y, w.y) * c.q; }  // [0, 2q), any y
     __device__ static __forceinline__ T load_u64(uint64_t x, const C &c) {  // any 64-bit value -> [0, 4q)
