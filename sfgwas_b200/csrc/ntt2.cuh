@@ -50,7 +50,7 @@ struct PassPlan {  // stage counts of the passes before the last pass (forward o
     int n;
     int R[4];
 };
-inline PassPlan make_pass_plan(int nstages /* = logS - kLastR >= 0 */) {
+__host__ __device__ inline PassPlan make_pass_plan(int nstages /* = logS - kLastR >= 0 */) {
     PassPlan p{0, {0, 0, 0, 0}};
     const int np = (nstages + kLastR - 1) / kLastR;
     for (int i = 0; i < np; i++) p.R[i] = nstages / np + (i < nstages % np ? 1 : 0);
@@ -341,6 +341,7 @@ __device__ __forceinline__ void ntt_forward(typename A::T *s, int logN, int logS
     if (plan.n == 0) {
         for (int j = threadIdx.x; j < (1 << logS); j += blockDim.x) sts(j, ld0(j, 0), 0);
     }
+#pragma unroll
     for (int i = 0; i < plan.n; i++) {
         if (i == 0) mid_pass<A, false>(plan.R[i], s0, logN, logS, sl, tw, c, ld0, sts);
         else mid_pass<A, false>(plan.R[i], s0, logN, logS, sl, tw, c, lds, sts);
