@@ -222,15 +222,17 @@ k_ks_inner2(const uint64_t *__restrict__ in, const long long *__restrict__ in_of
 }
 
 // ---- 4. mod-down, + c0, automorphism, store / accumulate ---------------------------------------------------------------------
-template <class A, bool A1>
+template <class A, bool A1, int LOGN>
 __global__ void __launch_bounds__(512, A::kMinBlocks)
 k_ks_moddown2(const uint64_t *__restrict__ in, const long long *__restrict__ in_off, int in_nl, const uint64_t *__restrict__ acc,
               const BaseConv *__restrict__ md, const uint64_t *__restrict__ pinv, const uint32_t *const *__restrict__ perms, int level,
-              int nQ, int nP, int logN, PassPlan plan, const TwTab *__restrict__ tabs, const LimbConst *__restrict__ lcs,
+              int nQ, int nP, int logN_arg, PassPlan plan_arg, const TwTab *__restrict__ tabs, const LimbConst *__restrict__ lcs,
               unsigned char *__restrict__ out, const long long *__restrict__ out_off, PolyLayout olay, int accumulate, TgtSel sel) {
     using T = typename A::T;
     extern __shared__ __align__(16) unsigned char smraw[];
     T *s = reinterpret_cast<T *>(smraw);
+    const int logN = LOGN ? LOGN : logN_arg;
+    const PassPlan plan = LOGN ? make_pass_plan(LOGN - kLastR) : plan_arg;
     const int N = 1 << logN, nl = level + 1, nt = nl + nP;
     const int l = sel.tt[blockIdx.x], comp = blockIdx.y, ct = blockIdx.z;
     const LimbConst lc = lcs[l];
@@ -312,14 +314,15 @@ __device__ __forceinline__ void md_wait(uint64_t *bar, uint32_t parity) {
         : "memory");
 }
 
-template <typename T>  // accumulator type: uint32_t for q < 2^31, uint64_t otherwise
+template <typename T, int LOGN>  // accumulator type: uint32_t for q < 2^31, uint64_t otherwise; LOGN > 0: compile-time ring size
 __global__ void __launch_bounds__(512, 1)
 k_md_accum(const uint64_t *__restrict__ in, const long long *__restrict__ in_off, int in_nl, const uint64_t *__restrict__ acc,
            const BaseConv *__restrict__ md, const uint32_t *const *__restrict__ perms, const uint32_t *__restrict__ ginv, int level, int nQ,
-           int nP, int logN, const LimbConst *__restrict__ lcs, int nout, int nacc, uint64_t *__restrict__ S1o, uint64_t *__restrict__ C0o,
+           int nP, int logN_arg, const LimbConst *__restrict__ lcs, int nout, int nacc, uint64_t *__restrict__ S1o, uint64_t *__restrict__ C0o,
            uint64_t *__restrict__ Eo, int L, int first, TgtSel sel) {
     extern __shared__ __align__(128) uint64_t sst[];
     constexpr int NBUF = 3;
+    const int logN = LOGN ? LOGN : logN_arg;
     const int N = 1 << logN, nl = level + 1, nt = nl + nP;
     uint64_t *bars = sst + (size_t)NBUF * N;
     // rings larger than 2^13 are cut into coefficient ranges of 2^13 owned by different CTAs (the sources are staged whole)
@@ -516,12 +519,17 @@ static int moddown_launch2(Ctx *c, const KsBatch &b, BaseConv *md, uint64_t *pin
     const int logN = c->logN, N = c->N;
     const PassPlan plan = make_pass_plan(logN - kLastR);
     const size_t smem = ntt_smem_elems(N) * sizeof(typename A::T);
-    SFG_CUDA(c, cudaFuncSetAttribute(k_ks_moddown2<A, A1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 g(sel.n, 2, b.nct);
-    k_ks_moddown2<A, A1><<<g, ntt_threads(N), smem, st>>>(b.in, b.in_off, b.in_nl, b.acc, md, pinv, b.perms, b.level, c->nQ, c->nP, logN, plan, c->tw2,
-                                                          c->lc, (unsigned char *)b.out, b.out_off, b.out_layout, b.accumulate ? 1 : 0, sel);
-    SFG_LAUNCHED(c, "k_ks_moddown2", st);
-    return 0;
+    auto go = [&](auto kern) -> int {
+        SFG_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<g, ntt_threads(N), smem, st>>>(b.in, b.in_off, b.in_nl, b.acc, md, pinv, b.perms, b.level, c->nQ, c->nP, logN, plan, c->tw2, c->lc,
+                                              (unsigned char *)b.out, b.out_off, b.out_layout, b.accumulate ? 1 : 0, sel);
+        SFG_LAUNCHED(c, "k_ks_moddown2", st);
+        return 0;
+    };
+    if (logN == 13) return go(k_ks_moddown2<A, A1, 13>);
+    if (logN == 14) return go(k_ks_moddown2<A, A1, 14>);
+    return go(k_ks_moddown2<A, A1, 0>);
 }
 template <class A>
 static int moddown_launch(Ctx *c, const KsBatch &b, BaseConv *md, uint64_t *pinv, const TgtSel &sel, cudaStream_t st) {
@@ -720,8 +728,13 @@ int launch_rotate_sum(Ctx *c, const KsBatch &b, int nout, const uint32_t *ginv_d
     for (int i = 0; i < nl; i++) sel.idx[i] = i;
     if (launch_ntt_gather(c, b.in + (size_t)b.in_nl * N, b.c2_src_off, 0, b.c2, (size_t)nl * N, b.n_c2 * nl, sel, true, false, st)) return -1;
     const size_t smem = (size_t)3 * N * 8 + 64;
-    SFG_CUDA(c, cudaFuncSetAttribute(k_md_accum<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    SFG_CUDA(c, cudaFuncSetAttribute(k_md_accum<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    auto accum = [&](auto kern, const TgtSel &ts, const KsBatch &ch, int k0, int nsplit, int thr, int fst) -> int {
+        SFG_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<dim3(ts.n * nsplit, 2, nout), thr, smem, st>>>(ch.in, ch.in_off, ch.in_nl, ch.acc, md, ch.perms, ginv_dev + k0, ch.level, c->nQ, c->nP,
+                                                              c->logN, c->lc, nout, ch.nct / nout, S1, C0, E, L, fst, ts);
+        SFG_LAUNCHED(c, "k_md_accum", st);
+        return 0;
+    };
     TgtSel nar{0, {}}, wid{0, {}};
     for (int l = 0; l < L; l++) {
         TgtSel &t = c->mod[l] < (1ULL << 31) ? nar : wid;
@@ -739,15 +752,10 @@ int launch_rotate_sum(Ctx *c, const KsBatch &b, int nout, const uint32_t *ginv_d
         const int nsplit = N > 8192 ? N / 8192 : 1;
         const int thr = std::min(512, std::max(32, N / nsplit / 16));
         const int fst = (first && k0 == 0) ? 1 : 0;
-        if (wid.n) {
-            k_md_accum<uint64_t><<<dim3(wid.n * nsplit, 2, nout), thr, smem, st>>>(ch.in, ch.in_off, ch.in_nl, ch.acc, md, ch.perms, ginv_dev + k0, ch.level,
-                                                                                 c->nQ, c->nP, c->logN, c->lc, nout, ch.nct / nout, S1, C0, E, L, fst, wid);
-            SFG_LAUNCHED(c, "k_md_accum", st);
-        }
-        if (nar.n)
-            k_md_accum<uint32_t><<<dim3(nar.n * nsplit, 2, nout), thr, smem, st>>>(ch.in, ch.in_off, ch.in_nl, ch.acc, md, ch.perms, ginv_dev + k0, ch.level,
-                                                                                 c->nQ, c->nP, c->logN, c->lc, nout, ch.nct / nout, S1, C0, E, L, fst, nar);
-        SFG_LAUNCHED(c, "k_md_accum", st);
+        if (wid.n && (c->logN == 13 ? accum(k_md_accum<uint64_t, 13>, wid, ch, k0, nsplit, thr, fst) : accum(k_md_accum<uint64_t, 0>, wid, ch, k0, nsplit, thr, fst)))
+            return -1;
+        if (nar.n && (c->logN == 13 ? accum(k_md_accum<uint32_t, 13>, nar, ch, k0, nsplit, thr, fst) : accum(k_md_accum<uint32_t, 0>, nar, ch, k0, nsplit, thr, fst)))
+            return -1;
     }
     return 0;
 }

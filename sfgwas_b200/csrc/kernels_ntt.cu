@@ -80,13 +80,16 @@ struct SubSel {  // the polynomials of a group that belong to one arithmetic cla
     int limb[kMaxLimbs];  // modulus index
 };
 
-template <class A>
+// LOGN > 0: ring size known at compile time (indices and the pass plan fold into immediates); LOGN == 0: generic
+template <class A, int LOGN>
 __global__ void __launch_bounds__(512, A::kMinBlocks)
 k_ntt2_fwd(const uint64_t *__restrict__ src, const long long *__restrict__ src_off, size_t src_gstride, uint64_t *__restrict__ dst,
-           size_t dst_gstride, SubSel sub, int logN, PassPlan plan, const TwTab *__restrict__ tabs, const LimbConst *__restrict__ lcs) {
+           size_t dst_gstride, SubSel sub, int logN_arg, PassPlan plan_arg, const TwTab *__restrict__ tabs, const LimbConst *__restrict__ lcs) {
     using T = typename A::T;
     extern __shared__ __align__(16) unsigned char smraw[];
     T *s = reinterpret_cast<T *>(smraw);
+    const int logN = LOGN ? LOGN : logN_arg;
+    const PassPlan plan = LOGN ? make_pass_plan(LOGN - kLastR) : plan_arg;
     const int N = 1 << logN, g = blockIdx.x / sub.n, kk = blockIdx.x % sub.n, k = sub.pos[kk], limb = sub.limb[kk];
     const uint64_t *in = src + (src_off ? (size_t)src_off[g] : (size_t)g * src_gstride) + (size_t)k * N;
     uint64_t *out = dst + (size_t)g * dst_gstride + (size_t)k * N;
@@ -97,13 +100,16 @@ k_ntt2_fwd(const uint64_t *__restrict__ src, const long long *__restrict__ src_o
     for (int j = threadIdx.x; j < N; j += blockDim.x) out[j] = s[sidx<sizeof(T)>(j)];
 }
 
-template <class A>
+template <class A, int LOGN>
 __global__ void __launch_bounds__(512, A::kMinBlocks)
 k_ntt2_inv(const uint64_t *__restrict__ src, const long long *__restrict__ src_off, size_t src_gstride, uint64_t *__restrict__ dst,
-           size_t dst_gstride, SubSel sub, int logN, PassPlan plan, const TwTab *__restrict__ tabs, const LimbConst *__restrict__ lcs, int in_tt) {
+           size_t dst_gstride, SubSel sub, int logN_arg, PassPlan plan_arg, const TwTab *__restrict__ tabs, const LimbConst *__restrict__ lcs,
+           int in_tt) {
     using T = typename A::T;
     extern __shared__ __align__(16) unsigned char smraw[];
     T *s = reinterpret_cast<T *>(smraw);
+    const int logN = LOGN ? LOGN : logN_arg;
+    const PassPlan plan = LOGN ? make_pass_plan(LOGN - kLastR) : plan_arg;
     const int N = 1 << logN, g = blockIdx.x / sub.n, kk = blockIdx.x % sub.n, k = sub.pos[kk], limb = sub.limb[kk];
     const uint64_t *in = src + (src_off ? (size_t)src_off[g] : (size_t)g * src_gstride) + (size_t)k * N;
     uint64_t *out = dst + (size_t)g * dst_gstride + (size_t)k * N;
@@ -133,15 +139,26 @@ static int ntt2_launch(Ctx *c, const uint64_t *src, const long long *src_off, si
     const PassPlan plan = make_pass_plan(logN - kLastR);
     const size_t smem = ntt_smem_elems(N) * sizeof(typename A::T);
     const int threads = std::min(512, std::max(32, N >> kLastR));
-    if (inverse) {
-        SFG_CUDA(c, cudaFuncSetAttribute(k_ntt2_inv<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_ntt2_inv<A><<<ngroups * sub.n, threads, smem, st>>>(src, src_off, sgs, dst, dgs, sub, logN, plan, c->tw2, c->lc, in_tt ? 1 : 0);
+    auto inv = [&](auto kern) -> int {
+        SFG_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<ngroups * sub.n, threads, smem, st>>>(src, src_off, sgs, dst, dgs, sub, logN, plan, c->tw2, c->lc, in_tt ? 1 : 0);
         SFG_LAUNCHED(c, "k_ntt2_inv", st);
-    } else {
-        SFG_CUDA(c, cudaFuncSetAttribute(k_ntt2_fwd<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_ntt2_fwd<A><<<ngroups * sub.n, threads, smem, st>>>(src, src_off, sgs, dst, dgs, sub, logN, plan, c->tw2, c->lc);
+        return 0;
+    };
+    auto fwd = [&](auto kern) -> int {
+        SFG_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<ngroups * sub.n, threads, smem, st>>>(src, src_off, sgs, dst, dgs, sub, logN, plan, c->tw2, c->lc);
         SFG_LAUNCHED(c, "k_ntt2_fwd", st);
+        return 0;
+    };
+    if (inverse) {
+        if (logN == 13) return inv(k_ntt2_inv<A, 13>);
+        if (logN == 14) return inv(k_ntt2_inv<A, 14>);
+        return inv(k_ntt2_inv<A, 0>);
     }
+    if (logN == 13) return fwd(k_ntt2_fwd<A, 13>);
+    if (logN == 14) return fwd(k_ntt2_fwd<A, 14>);
+    return fwd(k_ntt2_fwd<A, 0>);
     return 0;
 }
 

@@ -365,6 +365,7 @@ __device__ __forceinline__ void ntt_inverse(typename A::T *s, int logN, const Pa
     int s0 = logN - kLastR;
     inv_pass<A, kLastR, true>(s0, logN, logN, 0, reinterpret_cast<const TW *>(tab.inv_last), c, ld_last, sts);
     __syncthreads();
+#pragma unroll
     for (int i = plan.n - 1; i >= 0; i--) {
         s0 -= plan.R[i];
         if (i == 0) {

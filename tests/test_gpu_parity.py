@@ -312,7 +312,23 @@ def test_preprocess_compute_bit_exact(small13, nr, nc, s):
     want = o.compute(A, dc, keys, 5, nproc=8)
     o.cache_free(dc)
     assert out.shape == want.shape
-    assert (out == want).all()
+    if not (out == want).all():
+        # say where, and which side is unstable, before failing (a one-in-dozens mismatch was seen once in this test and never
+        # reproduced under compute-sanitizer initcheck / racecheck or in 60 repetitions; the single-thread oracle is the arbiter)
+        bad = out != want
+        again = MatMult4StreamCompute(cps, A, 5, cache)
+        dc1 = o.preprocess(X, 5, nproc=1)
+        want1 = o.compute(A, dc1, keys, 5, nproc=1)
+        o.cache_free(dc1)
+        msg = ("CUDA != oracle(8 threads): %d of %d words, first %s; cuda repeatable=%s, oracle(1 thread)==oracle(8 threads)=%s, "
+               "cuda==oracle(1 thread)=%s" % (int(bad.sum()), bad.size, np.argwhere(bad)[:3].tolist(), bool((again == out).all()),
+                                              bool((want1 == want).all()), bool((out == want1).all())))
+        if (again == out).all() and (out == want1).all():
+            import warnings
+
+            warnings.warn("multi-threaded oracle run was not reproducible: " + msg)
+        else:
+            raise AssertionError(msg)
     # numerical meaning (the reference's CPMatMult0 notion): decrypt(out) ~= A_plain . X ; tolerance 1e-4 relative
     ref = Ap @ X.astype(float)
     tol = 1e-4 * max(1.0, np.abs(ref).max())
