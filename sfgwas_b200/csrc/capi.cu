@@ -314,10 +314,8 @@ int sfg_matmult4_stream_compute(sfg_ctx *h, const uint64_t *A, int s, int nbr, i
     void *dA, *dO;  // grow-only workspace: no cudaMalloc / cudaFree in the steady state
     if (ws_get(c, WS_A, abytes, &dA) || ws_get(c, WS_OUT, obytes, &dO)) return -1;
     SFG_CUDA(c, cudaMemcpyAsync(dA, A, abytes, cudaMemcpyDefault, c->stream));
-    if (mm_compute_dev(c, (const uint64_t *)dA, s, nbr, level_a, max_level, cache->ca, (uint64_t *)dO)) return -1;
-    SFG_CUDA(c, cudaMemcpyAsync(out, dO, obytes, cudaMemcpyDefault, c->stream));
-    SFG_CUDA(c, cudaStreamSynchronize(c->stream));
-    return 0;
+    // device -> host copies of the output rows overlap the giant-step rotations of the following rows (matmult.cu: HostSink)
+    return mm_compute_dev(c, (const uint64_t *)dA, s, nbr, level_a, max_level, cache->ca, (uint64_t *)dO, out);
 }
 
 int sfg_matmult4_stream_compute_ptrs(sfg_ctx *h, const uint64_t *const *A_limbs, int s, int nbr, int level_a, int max_level,

@@ -353,12 +353,12 @@ struct RotMeta {
     }
 };
 
-// scratch for a batch: c2 [n_c2][nl][N], acc [cap][2][nl+nP][N] with cap bounded by a 2 GiB budget
+// scratch for a batch: c2 [n_c2][nl][N], acc [cap][2][nl+nP][N] with cap bounded by an 8 GiB budget
 static int fill_scratch(Ctx *c, KsBatch &kb, int max_nct, int max_c2) {
     const size_t N = c->N;
     const int nl = kb.level + 1, nt = nl + c->nP;
     const size_t per_ct = (size_t)2 * nt * N * 8;
-    const int cap = (int)std::max<size_t>(1, std::min<size_t>((size_t)max_nct, ((size_t)4 << 30) / per_ct));
+    const int cap = (int)std::max<size_t>(1, std::min<size_t>((size_t)max_nct, ((size_t)8 << 30) / per_ct));
     void *pc2, *pacc;
     if (ws_get(c, WS_C2, (size_t)max_c2 * nl * N * 8, &pc2) || ws_get(c, WS_ACC, (size_t)cap * per_ct, &pacc)) return -1;
     kb.c2 = (uint64_t *)pc2;
@@ -536,30 +536,35 @@ static uint32_t inv_mod_pow2(uint64_t a, int bits) {  // a odd
     return (uint32_t)(x & ((1ULL << bits) - 1));
 }
 
-static int run_giant(Ctx *c, const Cache *ca, int s, const uint64_t *d_cv, int gi_lo, int gi_hi, uint64_t *d_out) {
+// Optional host destination of the result: rows of `out` are copied back on a second stream as soon as their giant-step sums are
+// final, so the device -> host transfer of the reference-facing entry points overlaps the remaining key-switches.
+struct HostSink {
+    uint64_t *host = nullptr;    // [s][m_ct][2][L][N]
+    cudaStream_t copy = nullptr;
+    cudaEvent_t ev = nullptr;
+    bool used = false;           // set when run_giant issued the copies itself
+};
+
+static int run_giant(Ctx *c, const Cache *ca, int s, const uint64_t *d_cv, int gi_lo, int gi_hi, uint64_t *d_out, HostSink *sink = nullptr) {
     const int d = ca->d, m_ct = ca->m_ct, L = ca->L, N = c->N, nrows = 2 * s;
     const size_t LN = (size_t)L * N;
     const int nout = m_ct * s;
     if (gi_hi <= gi_lo) return 0;
-    RotMeta rot, cpy;
-    int nrot = 0;
+    // giant steps with a rotation, and the entries of giant step 0 (no rotation, crypto/basics.go:203)
+    std::vector<int> grot;
+    RotMeta cpy;
     for (int gi = gi_lo; gi < gi_hi; gi++) {
         const int g = ca->gact[gi];
-        const GaloisKey *key = nullptr;
-        if (g > 0 && find_key(c, (g * d) % ca->slots, &key)) return -1;
+        if (g > 0) {
+            grot.push_back(gi);
+            continue;
+        }
         for (int t = 0; t < nout; t++) {  // t = bj*s + i : consecutive ciphertexts of the cv image
             const int bj = t / s, i = t % s;
-            const long long in_off = (long long)((((size_t)(gi - gi_lo) * m_ct + bj) * nrows + 2 * i) * LN);
-            const RotEntry e{in_off, (long long)(((size_t)i * m_ct + bj) * 2 * LN * 8), 0, key};
-            if (g == 0) {
-                cpy.add(e);
-            } else {
-                rot.add(e);
-                rot.ginv.push_back(inv_mod_pow2(key->galEl, c->logN + 1));
-            }
+            cpy.add(RotEntry{(long long)((((size_t)(gi - gi_lo) * m_ct + bj) * nrows + 2 * i) * LN), (long long)(((size_t)i * m_ct + bj) * 2 * LN * 8), 0, nullptr});
         }
-        if (g > 0) nrot++;
     }
+    const int nrot = (int)grot.size();
     KsBatch kb{};
     kb.level = L - 1;  // ModularReduceV2 creates the ct at level len(acc0)-1 (gwas/matmult.go:350)
     kb.in = d_cv;
@@ -567,7 +572,7 @@ static int run_giant(Ctx *c, const Cache *ca, int s, const uint64_t *d_cv, int g
     kb.out = d_out;
     kb.out_layout = make_layout(c, L, false);
     kb.accumulate = true;
-    if (!cpy.in_off.empty()) {  // giant step 0: no rotation (crypto/basics.go:203)
+    if (!cpy.in_off.empty()) {
         if (cpy.upload(c, WS_META2)) return -1;
         kb.nct = (int)cpy.in_off.size();
         kb.in_off = cpy.d_in_off;
@@ -575,34 +580,69 @@ static int run_giant(Ctx *c, const Cache *ca, int s, const uint64_t *d_cv, int g
         if (launch_copy_add(c, kb, c->stream)) return -1;
     }
     if (nrot == 0) return 0;
-    // chunks of G giant steps go through one sequence of launches; every entry is its own INTT slot (numbered inside its chunk)
-    kb.nct = nout;
-    kb.n_c2 = nout;
+    // Output-major schedule: the rows i of A are cut into chunks whose nrot * rows * m_ct rotations fit the key-switch scratch, so that a
+    // chunk's sums over ALL giant steps finish in one launch sequence (no partial sums carried in HBM) and its rows of `out` are final
+    // -- and can start their way to the host -- while the next chunk is computed.  If even one row does not fit, the giant steps of a
+    // chunk are processed in groups with the partial sums carried (S1, C0, E).
+    kb.nct = m_ct;
+    kb.n_c2 = m_ct;
     if (fill_scratch(c, kb, nrot * nout, 1)) return -1;
-    const int G = std::max(1, std::min(nrot, kb.acc_cap / nout));
-    if (kb.acc_cap < nout) SFG_FAIL(c, "key-switch scratch too small for one giant step (%d ciphertexts)", nout);
-    if (fill_scratch(c, kb, G * nout, G * nout)) return -1;
-    for (size_t k = 0; k < rot.in_off.size(); k++) rot.c2_slot[k] = (int)(k % ((size_t)G * nout));
+    if (kb.acc_cap < m_ct) SFG_FAIL(c, "key-switch scratch too small for one giant step of one row (%d ciphertexts)", m_ct);
+    const int rows_fit = kb.acc_cap / (nrot * m_ct);
+    const int nchunk = (s + std::max(1, rows_fit) - 1) / std::max(1, rows_fit);
+    const int rpc = (s + nchunk - 1) / nchunk;                                // rows of A per chunk, balanced (k_md_accum's grid = 10 * rows * m_ct
+                                                                              // CTAs on 148 SMs: few large chunks quantise better than many small ones)
+    const int G = rows_fit >= 1 ? nrot : std::max(1, kb.acc_cap / m_ct);      // giant steps per launch sequence
+    if (fill_scratch(c, kb, std::min(G, nrot) * rpc * m_ct, std::min(G, nrot) * rpc * m_ct)) return -1;
+    RotMeta rot;
+    std::vector<size_t> chunk_base;
+    for (int ch = 0; ch < nchunk; ch++) {
+        const int i_lo = ch * rpc, i_hi = std::min(s, i_lo + rpc), nout_c = (i_hi - i_lo) * m_ct;
+        chunk_base.push_back(rot.in_off.size());
+        for (int a = 0; a < nrot; a++) {
+            const int gi = grot[a], g = ca->gact[gi];
+            const GaloisKey *key = nullptr;
+            if (find_key(c, (g * d) % ca->slots, &key)) return -1;
+            const uint32_t gin = inv_mod_pow2(key->galEl, c->logN + 1);
+            for (int o = 0; o < nout_c; o++) {  // o = (i - i_lo) * m_ct + bj: the chunk's outputs are contiguous in `out`
+                const int i = i_lo + o / m_ct, bj = o % m_ct;
+                const long long in_off = (long long)((((size_t)(gi - gi_lo) * m_ct + bj) * nrows + 2 * i) * LN);
+                rot.add(RotEntry{in_off, (long long)(((size_t)i * m_ct + bj) * 2 * LN * 8), (int)(((size_t)(a % G) * nout_c + o)), key});
+                rot.ginv.push_back(gin);
+            }
+        }
+    }
     rot.c2_src = rot.in_off;
     if (rot.upload(c, WS_META)) return -1;
     void *mdbuf;
-    const size_t msz = (size_t)nout * 2 * LN;
+    const size_t msz = (size_t)rpc * m_ct * 2 * LN;
     if (ws_get(c, WS_MD, 3 * msz * 8, &mdbuf)) return -1;
     uint64_t *S1 = (uint64_t *)mdbuf, *C0 = S1 + msz, *E = C0 + msz;
-    for (int a0 = 0; a0 < nrot; a0 += G) {
-        const int na = std::min(G, nrot - a0);
-        const size_t o = (size_t)a0 * nout;
-        kb.nct = na * nout;
-        kb.n_c2 = na * nout;
-        kb.in_off = rot.d_in_off + o;
-        kb.out_off = rot.d_out_off + o;
-        kb.c2_src_off = rot.d_c2_src + o;
-        kb.c2_slot = rot.d_c2_slot + o;
-        kb.keys = rot.d_keys + o;
-        kb.perms = rot.d_perms + o;
-        if (launch_rotate_sum(c, kb, nout, rot.d_ginv + o, S1, C0, E, a0 == 0, c->stream)) return -1;
+    for (int ch = 0; ch < nchunk; ch++) {
+        const int i_lo = ch * rpc, i_hi = std::min(s, i_lo + rpc), nout_c = (i_hi - i_lo) * m_ct;
+        for (int a0 = 0; a0 < nrot; a0 += G) {
+            const int na = std::min(G, nrot - a0);
+            const size_t o = chunk_base[ch] + (size_t)a0 * nout_c;
+            kb.nct = na * nout_c;
+            kb.n_c2 = na * nout_c;
+            kb.in_off = rot.d_in_off + o;
+            kb.out_off = rot.d_out_off + o;
+            kb.c2_src_off = rot.d_c2_src + o;
+            kb.c2_slot = rot.d_c2_slot + o;
+            kb.keys = rot.d_keys + o;
+            kb.perms = rot.d_perms + o;
+            if (launch_rotate_sum(c, kb, nout_c, rot.d_ginv + o, S1, C0, E, a0 == 0, c->stream)) return -1;
+        }
+        if (launch_rotate_sum_final(c, L - 1, nout_c, S1, C0, E, d_out, rot.d_out_off + chunk_base[ch], kb.out_layout, c->stream)) return -1;
+        if (sink && sink->host) {  // rows [i_lo, i_hi) of out are final
+            const size_t off = (size_t)i_lo * m_ct * 2 * LN, cnt = (size_t)(i_hi - i_lo) * m_ct * 2 * LN;
+            SFG_CUDA(c, cudaEventRecord(sink->ev, c->stream));
+            SFG_CUDA(c, cudaStreamWaitEvent(sink->copy, sink->ev, 0));
+            SFG_CUDA(c, cudaMemcpyAsync(sink->host + off, d_out + off, cnt * 8, cudaMemcpyDefault, sink->copy));
+            sink->used = true;
+        }
     }
-    return launch_rotate_sum_final(c, L - 1, nout, S1, C0, E, d_out, rot.d_out_off, kb.out_layout, c->stream);
+    return 0;
 }
 
 static int check_args(Ctx *c, const Cache *ca, int s, int nbr, int levelA, int maxLevel) {
@@ -615,7 +655,7 @@ static int check_args(Ctx *c, const Cache *ca, int s, int nbr, int levelA, int m
     return 0;
 }
 
-int mm_compute_dev(Ctx *c, const uint64_t *d_A, int s, int nbr, int levelA, int maxLevel, Cache *ca, uint64_t *d_out) {
+int mm_compute_dev(Ctx *c, const uint64_t *d_A, int s, int nbr, int levelA, int maxLevel, Cache *ca, uint64_t *d_out, uint64_t *host_out) {
     if (check_args(c, ca, s, nbr, levelA, maxLevel)) return -1;
     SFG_CUDA(c, cudaSetDevice(c->device));
     const int L = ca->L, N = c->N, m_ct = ca->m_ct;
@@ -625,6 +665,8 @@ int mm_compute_dev(Ctx *c, const uint64_t *d_A, int s, int nbr, int levelA, int 
     struct Reset { ~Reset() { g_tm = nullptr; } } reset;
     void *R;
     std::vector<int> klist;
+    HostSink sink;
+    sink.host = host_out;
     tm.mark(0);
     if (build_rot_cache(c, ca, d_A, s, levelA, 0, nbr, klist, &R)) return -1;
     SFG_CUDA(c, cudaMemsetAsync(d_out, 0, (size_t)s * m_ct * 2 * LN * 8, c->stream));
@@ -645,11 +687,29 @@ int mm_compute_dev(Ctx *c, const uint64_t *d_A, int s, int nbr, int levelA, int 
         tm.mark(1);
         if (run_mac(c, ca, R, klist, s, g0, g1, (uint64_t *)cv)) return -1;
         tm.mark(2);
-        if (run_giant(c, ca, s, (const uint64_t *)cv, g0, g1, d_out)) return -1;
+        // the rows of out can leave for the host chunk by chunk only when this call sees every giant step
+        HostSink *sk = (host_out && g0 == 0 && g1 == ng) ? &sink : nullptr;
+        if (sk && !sk->copy) {
+            SFG_CUDA(c, cudaStreamCreateWithFlags(&sk->copy, cudaStreamNonBlocking));
+            SFG_CUDA(c, cudaEventCreateWithFlags(&sk->ev, cudaEventDisableTiming));
+        }
+        const int rc = run_giant(c, ca, s, (const uint64_t *)cv, g0, g1, d_out, sk);
+        if (rc) {
+            if (sink.copy) { cudaStreamSynchronize(sink.copy); cudaStreamDestroy(sink.copy); cudaEventDestroy(sink.ev); }
+            return -1;
+        }
     }
     tm.mark(-1);
     tm.finish(g_last_ms);
-    SFG_CUDA(c, cudaStreamSynchronize(c->stream));
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    if (sink.copy) {
+        if (e == cudaSuccess) e = cudaStreamSynchronize(sink.copy);
+        cudaStreamDestroy(sink.copy);
+        cudaEventDestroy(sink.ev);
+    }
+    SFG_CUDA(c, e);
+    if (host_out && !sink.used)  // several giant chunks (or nothing to rotate): one copy at the end
+        SFG_CUDA(c, cudaMemcpy(host_out, d_out, (size_t)s * m_ct * 2 * LN * 8, cudaMemcpyDefault));
     return 0;
 }
 

@@ -71,7 +71,9 @@ int cache_write_files(Ctx *c, const Cache *ca, const char *prefix);
 int cache_load_files(Ctx *c, const char *prefix, size_t nrows, size_t ncols, int maxLevel, Cache **out);
 
 // full single-GPU compute: d_A device [s][nbr][2][nlA][N] -> d_out device [s][m_ct][2][L][N]
-int mm_compute_dev(Ctx *c, const uint64_t *d_A, int s, int nbr, int levelA, int maxLevel, Cache *cache, uint64_t *d_out);
+// host_out (optional): the result is also copied to this HOST buffer, rows leaving as soon as their giant-step sums are final
+int mm_compute_dev(Ctx *c, const uint64_t *d_A, int s, int nbr, int levelA, int maxLevel, Cache *cache, uint64_t *d_out,
+                   uint64_t *host_out = nullptr);
 // multi-GPU pieces
 int mm_partial_dev(Ctx *c, const uint64_t *d_A, int s, int nbr, int levelA, int maxLevel, Cache *cache, int bi_lo, int bi_hi,
                    uint64_t *d_cv);
