@@ -110,6 +110,7 @@ struct KsBatch {
     bool accumulate;        // out += result (mod q) instead of out = result; entries of one batch must target distinct outputs
     // scratch (device): c2 [n_c2][nl][N], acc [nct][2][nl+nP][N]
     uint64_t *c2, *acc;
+    uint64_t *dout = nullptr;  // internal: digit-transform output of the shared-decomposition path (kernels_ks.cu)
     int acc_cap;            // ciphertexts the acc scratch holds; larger batches are processed in chunks
 };
 int launch_rotate(Ctx *c, const KsBatch &b, cudaStream_t st);

@@ -91,12 +91,16 @@ int launch_key_convert(Ctx *c, const uint64_t *in, uint64_t *out, cudaStream_t s
 // digit is a single modulus: plain reduction of the representative, Lattigo DecomposeAndSplit).
 // LOGN > 0: the ring size is a compile-time constant (every index, stride and pass shape folds into immediates: ~30 % of the executed
 // instructions of the generic version are address arithmetic); LOGN == 0: generic, ring size and pass plan from the arguments.
-template <class A, int CS, bool A1, int LOGN>
+template <class A, int CS, bool A1, int LOGN, bool DM>
 __global__ void __launch_bounds__(512, A::kMinBlocks)
 k_ks_inner2(const uint64_t *__restrict__ in, const long long *__restrict__ in_off, int in_nl, const uint64_t *__restrict__ c2,
             const int *__restrict__ c2_slot, const uint64_t *const *__restrict__ keys, const BaseConv *__restrict__ ks, int level, int nQ,
             int nP, int logN_arg, PassPlan plan_arg, const TwTab *__restrict__ tabs, const LimbConst *__restrict__ lcs,
-            uint64_t *__restrict__ accout, TgtSel sel) {
+            uint64_t *__restrict__ accout, TgtSel sel, uint64_t *__restrict__ dout) {
+    // DM (dout != nullptr): DIGIT mode.  The transforms NTT_t(Ext(digit_i(c1))) do not depend on the switching key, so rotations of the SAME
+    // ciphertext by different amounts (the d-1 baby steps of every A[i][bi]) share them: the kernel then runs once per distinct input
+    // (ct = slot, c2_slot == keys == nullptr) and stores the canonical transforms D[slot][i][tt] in TT order instead of multiplying
+    // them with a key; k_ks_macd does the key products per rotation.  Bit-identical: the same values enter the same modular sums.
     using T = typename A::T;
     extern __shared__ __align__(16) unsigned char smraw[];
     const int logN = LOGN ? LOGN : logN_arg;
@@ -110,8 +114,8 @@ k_ks_inner2(const uint64_t *__restrict__ in, const long long *__restrict__ in_of
     const typename A::C c = A::make(lc);
     const TwTab tab = tabs[tgt];
     const uint64_t *c1 = in + in_off[ct] + (size_t)in_nl * N;  // second polynomial of the input ct (NTT domain)
-    const uint64_t *c2ct = c2 + (size_t)c2_slot[ct] * nl * N;  // its INTT, coefficient domain
-    const uint64_t *key = keys[ct];
+    const uint64_t *c2ct = c2 + (size_t)(c2_slot ? c2_slot[ct] : ct) * nl * N;  // its INTT, coefficient domain
+    const uint64_t *key = keys ? keys[ct] : nullptr;
     const int gbase = sl << logS;                               // global index of local coefficient 0
     const int P = (gbase >> kLastR) + threadIdx.x;              // global index of this thread's group of 16
     const bool active = threadIdx.x < (S >> kLastR);
@@ -138,6 +142,10 @@ k_ks_inner2(const uint64_t *__restrict__ in, const long long *__restrict__ in_of
         const uint64_t *k1 = key + ((size_t)(i * 2 + 1) * nQP + tgt) * N + P;
         // multiply coefficient 16 P + k with the two key polynomials (TT order: unit stride across lanes) and accumulate
         auto mac = [&](int, T v, int k) {
+            if constexpr (DM) {
+                dout[(((size_t)ct * beta + i) * nt + tt) * N + P + (size_t)k * NP] = (uint64_t)A::canon(v, c);
+                return;
+            }
             if constexpr (A::kKind == kArD) {  // lazy FP64 accumulation: every product is in (-q, q)
                 const int sj = sidx<sizeof(T)>(abase + k);
                 s0a[sj] += A::mul_lazy(v, __ldg(reinterpret_cast<const double *>(k0) + (size_t)k * NP), c);
@@ -202,7 +210,7 @@ k_ks_inner2(const uint64_t *__restrict__ in, const long long *__restrict__ in_of
         }
         __syncthreads();
     }
-    if (active) {
+    if (active && !DM) {
         uint64_t *o0 = accout + ((size_t)(ct * 2 + 0) * nt + tt) * N + P;
         uint64_t *o1 = accout + ((size_t)(ct * 2 + 1) * nt + tt) * N + P;
 #pragma unroll
@@ -483,6 +491,43 @@ int launch_copy_add(Ctx *c, const KsBatch &b, cudaStream_t st) {
     return 0;
 }
 
+// ---- 2'. key products over shared digit transforms: acc[ct][comp][tt] = sum_i D[slot(ct)][i][tt] * key_ct[i][comp][tt]  (TT order) -------
+// Pure streaming (unit stride in the TT position): per output pair beta transforms and 2 beta key words are read once.
+__global__ void k_ks_macd(const uint64_t *__restrict__ D, const int *__restrict__ c2_slot, const uint64_t *const *__restrict__ keys, int level,
+                          int nQ, int nP, int N, const LimbConst *__restrict__ lcs, uint64_t *__restrict__ accout) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x, tt = blockIdx.y, ct = blockIdx.z;
+    if (p >= N) return;
+    const int nl = level + 1, nt = nl + nP, nQP = nQ + nP, beta = (nl + nP - 1) / nP;
+    const int tgt = tt < nl ? tt : nQ + (tt - nl);
+    const LimbConst lc = lcs[tgt];
+    const int kind = arith_kind(lc.q);
+    const ArN30::C c32 = ArN30::make(lc);
+    const uint64_t *d = D + ((size_t)c2_slot[ct] * beta * nt + tt) * N + p;
+    const uint64_t *key = keys[ct] + (size_t)tgt * N;
+    uint64_t a0 = 0, a1 = 0;
+    for (int i = 0; i < beta; i++) {
+        const uint64_t v = d[(size_t)i * nt * N];
+        const uint64_t *k0 = key + (size_t)(i * 2 + 0) * nQP * N, *k1 = key + (size_t)(i * 2 + 1) * nQP * N;
+        uint64_t p0, p1;
+        if (kind == kArW) {  // Montgomery form, as uploaded
+            p0 = mred(v, k0[p], lc);
+            p1 = mred(v, k1[p], lc);
+        } else if (kind == kArD) {  // plain residue stored as an FP64 integer
+            p0 = mul_mod(v, (uint64_t)(long long)__longlong_as_double((long long)k0[p]), lc);
+            p1 = mul_mod(v, (uint64_t)(long long)__longlong_as_double((long long)k1[p]), lc);
+        } else {  // 32-bit Montgomery form in the first half of the slot
+            const uint32_t r0 = ArN30::mul_mont((uint32_t)v, reinterpret_cast<const uint32_t *>(k0)[p], c32);
+            const uint32_t r1 = ArN30::mul_mont((uint32_t)v, reinterpret_cast<const uint32_t *>(k1)[p], c32);
+            p0 = min(r0, r0 - c32.q);
+            p1 = min(r1, r1 - c32.q);
+        }
+        a0 = add_mod(a0, p0, lc.q);
+        a1 = add_mod(a1, p1, lc.q);
+    }
+    accout[((size_t)(ct * 2 + 0) * nt + tt) * N + p] = a0;
+    accout[((size_t)(ct * 2 + 1) * nt + tt) * N + p] = a1;
+}
+
 static int ntt_threads(int S) { return std::min(512, std::max(32, S >> kLastR)); }
 
 template <class A, int CS, bool A1>
@@ -494,17 +539,23 @@ static int inner_launch2(Ctx *c, const KsBatch &b, BaseConv *ks, const TgtSel &s
     auto go = [&](auto kern) -> int {
         SFG_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<g, ntt_threads(S), smem, st>>>(b.in, b.in_off, b.in_nl, b.c2, b.c2_slot, b.keys, ks, b.level, c->nQ, c->nP, logN, plan, c->tw2, c->lc,
-                                              b.acc, sel);
+                                              b.acc, sel, b.dout);
         SFG_LAUNCHED(c, "k_ks_inner2", st);
         return 0;
     };
     // rings of the reference's parameter sets are compiled with constant shapes; anything else takes the generic kernel
-    if constexpr (CS == 0) {
-        if (logN == 13) return go(k_ks_inner2<A, CS, A1, 13>);
-    } else {
-        if (logN == 14) return go(k_ks_inner2<A, CS, A1, 14>);
+    if (b.dout) {  // digit mode (shared decomposition of the baby steps): the generic-shape kernel is enough for logN != 13
+        if constexpr (CS == 0) {
+            if (logN == 13) return go(k_ks_inner2<A, CS, A1, 13, true>);
+        }
+        return go(k_ks_inner2<A, CS, A1, 0, true>);
     }
-    return go(k_ks_inner2<A, CS, A1, 0>);
+    if constexpr (CS == 0) {
+        if (logN == 13) return go(k_ks_inner2<A, CS, A1, 13, false>);
+    } else {
+        if (logN == 14) return go(k_ks_inner2<A, CS, A1, 14, false>);
+    }
+    return go(k_ks_inner2<A, CS, A1, 0, false>);
 }
 template <class A>
 static int inner_launch(Ctx *c, const KsBatch &b, BaseConv *ks, const TgtSel &sel, cudaStream_t st) {
@@ -537,9 +588,8 @@ static int moddown_launch(Ctx *c, const KsBatch &b, BaseConv *md, uint64_t *pinv
     return c->nP == 1 ? moddown_launch2<A, true>(c, b, md, pinv, sel, st) : moddown_launch2<A, false>(c, b, md, pinv, sel, st);
 }
 
-static int rotate_chunk(Ctx *c, const KsBatch &b, BaseConv *ks, BaseConv *md, uint64_t *pinv, cudaStream_t st, bool moddown = true) {
-    const int N = c->N, nl = b.level + 1, nt = nl + c->nP;
-    // 2. inner products with the switching keys, one launch per arithmetic class of the target modulus
+static int inner_all(Ctx *c, const KsBatch &b, BaseConv *ks, cudaStream_t st) {
+    const int nl = b.level + 1, nt = nl + c->nP;
     TgtSel ts[kNumArith] = {{0, {}}, {0, {}}, {0, {}}, {0, {}}};
     for (int tt = 0; tt < nt; tt++) {
         const int tgt = tt < nl ? tt : c->nQ + (tt - nl);
@@ -548,6 +598,20 @@ static int rotate_chunk(Ctx *c, const KsBatch &b, BaseConv *ks, BaseConv *md, ui
     }
     if (inner_launch<ArW>(c, b, ks, ts[kArW], st) || inner_launch<ArD>(c, b, ks, ts[kArD], st) || inner_launch<ArN30>(c, b, ks, ts[kArN30], st) || inner_launch<ArN31>(c, b, ks, ts[kArN31], st))
         return -1;
+    return 0;
+}
+
+// D != nullptr: the digit transforms of the batch's distinct inputs are already in D (shared-decomposition path)
+static int rotate_chunk(Ctx *c, const KsBatch &b, BaseConv *ks, BaseConv *md, uint64_t *pinv, cudaStream_t st, bool moddown = true,
+                        const uint64_t *D = nullptr) {
+    const int N = c->N, nl = b.level + 1, nt = nl + c->nP;
+    // 2. inner products with the switching keys, one launch per arithmetic class of the target modulus
+    if (D) {
+        k_ks_macd<<<dim3((N + 255) / 256, nt, b.nct), 256, 0, st>>>(D, b.c2_slot, b.keys, b.level, c->nQ, c->nP, N, c->lc, b.acc);
+        SFG_LAUNCHED(c, "k_ks_macd", st);
+    } else if (inner_all(c, b, ks, st)) {
+        return -1;
+    }
     // 3. INTT of the P limbs of acc (TT order in, natural order out, in place): groups = (ct, comp)
     LimbSel selp;
     selp.n = c->nP;
@@ -697,6 +761,21 @@ int launch_rotate(Ctx *c, const KsBatch &b, cudaStream_t st) {
     sel.n = nl;
     for (int i = 0; i < nl; i++) sel.idx[i] = i;
     if (launch_ntt_gather(c, b.in + (size_t)b.in_nl * N, b.c2_src_off, 0, b.c2, (size_t)nl * N, b.n_c2 * nl, sel, true, false, st)) return -1;
+    // many rotations of few ciphertexts (the baby steps: d-1 rotations of every A[i][bi]): transform the digits once per ciphertext
+    const uint64_t *D = nullptr;
+    if (b.n_c2 * 4 <= b.nct && b.nct <= 65535) {
+        const int nt = nl + c->nP, beta = (nl + c->nP - 1) / c->nP;
+        void *pd;
+        if (ws_get(c, WS_KSB, (size_t)b.n_c2 * beta * nt * N * 8, &pd)) return -1;
+        KsBatch bd = b;
+        bd.nct = b.n_c2;
+        bd.in_off = b.c2_src_off;
+        bd.c2_slot = nullptr;
+        bd.keys = nullptr;
+        bd.dout = (uint64_t *)pd;
+        if (inner_all(c, bd, ks, st)) return -1;
+        D = (const uint64_t *)pd;
+    }
     for (int k0 = 0; k0 < b.nct; k0 += b.acc_cap) {
         KsBatch ch = b;
         ch.nct = std::min(b.acc_cap, b.nct - k0);
@@ -705,7 +784,7 @@ int launch_rotate(Ctx *c, const KsBatch &b, cudaStream_t st) {
         ch.keys += k0;
         ch.perms += k0;
         ch.out_off += k0;
-        if (rotate_chunk(c, ch, ks, md, pinv, st)) return -1;
+        if (rotate_chunk(c, ch, ks, md, pinv, st, true, D)) return -1;
     }
     return 0;
 }
