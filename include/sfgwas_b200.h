@@ -79,6 +79,9 @@ int sfg_encode_diag(sfg_ctx *ctx, const sfg_geno *g, int block_row, int shift, i
 /* MatMult4StreamPreprocess(cryptoParams, gfs, maxLevel, cacheFilePrefix): builds the diagonal cache in HBM (or, when it
  * exceeds the budget, a handle that regenerates diagonals on the fly; results are identical). */
 int sfg_matmult4_stream_preprocess(sfg_ctx *ctx, const sfg_geno *g, int max_level, sfg_cache **out);
+/* block-row sharding: the cache of a rank holds the diagonals of its own block rows [bi_lo, bi_hi) only (HBM and
+ * preprocessing time proportional to the rank's share); it serves sfg_matmult4_partial over that range and sfg_matmult4_finish */
+int sfg_matmult4_stream_preprocess_rows(sfg_ctx *ctx, const sfg_geno *g, int max_level, int bi_lo, int bi_hi, sfg_cache **out);
 void sfg_cache_destroy(sfg_cache *cache);
 /* number of non-nil diagonal polynomials, bytes resident, and whether they are materialised */
 int sfg_cache_info(const sfg_cache *cache, size_t *num_polys, size_t *bytes, int *materialised, int *m_ct, int *num_block_rows);

@@ -265,6 +265,13 @@ int sfg_matmult4_stream_preprocess(sfg_ctx *h, const sfg_geno *g, int max_level,
     *out = new sfg_cache{ca};
     return 0;
 }
+int sfg_matmult4_stream_preprocess_rows(sfg_ctx *h, const sfg_geno *g, int max_level, int bi_lo, int bi_hi, sfg_cache **out) {
+    *out = nullptr;
+    Cache *ca = nullptr;
+    if (cache_build(&h->c, g->g, max_level, &ca, bi_lo, bi_hi)) return -1;
+    *out = new sfg_cache{ca};
+    return 0;
+}
 void sfg_cache_destroy(sfg_cache *cache) {
     if (!cache) return;
     cache_destroy(cache->ca);

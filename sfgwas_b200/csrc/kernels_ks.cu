@@ -492,40 +492,56 @@ int launch_copy_add(Ctx *c, const KsBatch &b, cudaStream_t st) {
 }
 
 // ---- 2'. key products over shared digit transforms: acc[ct][comp][tt] = sum_i D[slot(ct)][i][tt] * key_ct[i][comp][tt]  (TT order) -------
-// Pure streaming (unit stride in the TT position): per output pair beta transforms and 2 beta key words are read once.
-__global__ void k_ks_macd(const uint64_t *__restrict__ D, const int *__restrict__ c2_slot, const uint64_t *const *__restrict__ keys, int level,
-                          int nQ, int nP, int N, const LimbConst *__restrict__ lcs, uint64_t *__restrict__ accout) {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x, tt = blockIdx.y, ct = blockIdx.z;
+// Pure streaming (unit stride in the TT position): per output pair beta transforms and 2 beta key words are read once.  One launch per
+// arithmetic class of the target modulus: 32-bit Montgomery products for the narrow classes, exact FP64 two-products for ArD, u64
+// Montgomery for ArW (a single generic u64 kernel spent 600 instructions per thread, most of them 64-bit mul.hi sequences).
+template <int KIND>
+__global__ void __launch_bounds__(256)
+k_ks_macd(const uint64_t *__restrict__ D, const int *__restrict__ c2_slot, const uint64_t *const *__restrict__ keys, int level, int nQ,
+          int nP, int N, const LimbConst *__restrict__ lcs, uint64_t *__restrict__ accout, TgtSel sel) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x, tt = sel.tt[blockIdx.y], ct = blockIdx.z;
     if (p >= N) return;
     const int nl = level + 1, nt = nl + nP, nQP = nQ + nP, beta = (nl + nP - 1) / nP;
     const int tgt = tt < nl ? tt : nQ + (tt - nl);
     const LimbConst lc = lcs[tgt];
-    const int kind = arith_kind(lc.q);
-    const ArN30::C c32 = ArN30::make(lc);
     const uint64_t *d = D + ((size_t)c2_slot[ct] * beta * nt + tt) * N + p;
     const uint64_t *key = keys[ct] + (size_t)tgt * N;
-    uint64_t a0 = 0, a1 = 0;
-    for (int i = 0; i < beta; i++) {
-        const uint64_t v = d[(size_t)i * nt * N];
-        const uint64_t *k0 = key + (size_t)(i * 2 + 0) * nQP * N, *k1 = key + (size_t)(i * 2 + 1) * nQP * N;
-        uint64_t p0, p1;
-        if (kind == kArW) {  // Montgomery form, as uploaded
-            p0 = mred(v, k0[p], lc);
-            p1 = mred(v, k1[p], lc);
-        } else if (kind == kArD) {  // plain residue stored as an FP64 integer
-            p0 = mul_mod(v, (uint64_t)(long long)__longlong_as_double((long long)k0[p]), lc);
-            p1 = mul_mod(v, (uint64_t)(long long)__longlong_as_double((long long)k1[p]), lc);
-        } else {  // 32-bit Montgomery form in the first half of the slot
-            const uint32_t r0 = ArN30::mul_mont((uint32_t)v, reinterpret_cast<const uint32_t *>(k0)[p], c32);
-            const uint32_t r1 = ArN30::mul_mont((uint32_t)v, reinterpret_cast<const uint32_t *>(k1)[p], c32);
-            p0 = min(r0, r0 - c32.q);
-            p1 = min(r1, r1 - c32.q);
+    uint64_t *o0 = accout + ((size_t)(ct * 2 + 0) * nt + tt) * N + p, *o1 = accout + ((size_t)(ct * 2 + 1) * nt + tt) * N + p;
+    if constexpr (KIND == kArN30 || KIND == kArN31) {
+        const ArN30::C c = ArN30::make(lc);
+        uint32_t a0 = 0, a1 = 0;
+        for (int i = 0; i < beta; i++) {
+            const uint32_t v = (uint32_t)__ldg(d + (size_t)i * nt * N);
+            const uint32_t k0 = __ldg(reinterpret_cast<const uint32_t *>(key + (size_t)(i * 2 + 0) * nQP * N) + p);  // 32-bit Montgomery form,
+            const uint32_t k1 = __ldg(reinterpret_cast<const uint32_t *>(key + (size_t)(i * 2 + 1) * nQP * N) + p);  // first half of the slot
+            uint32_t r0 = ArN30::mul_mont(v, k0, c), r1 = ArN30::mul_mont(v, k1, c);
+            r0 = min(r0, r0 - c.q) + a0;
+            r1 = min(r1, r1 - c.q) + a1;
+            a0 = min(r0, r0 - c.q);
+            a1 = min(r1, r1 - c.q);
         }
-        a0 = add_mod(a0, p0, lc.q);
-        a1 = add_mod(a1, p1, lc.q);
+        *o0 = a0;
+        *o1 = a1;
+    } else if constexpr (KIND == kArD) {
+        const ArD::C c = ArD::make(lc);
+        double a0 = 0.0, a1 = 0.0;  // every product is in (-q, q): the sums stay exact integers far below 2^53
+        for (int i = 0; i < beta; i++) {
+            const double v = (double)(long long)__ldg(d + (size_t)i * nt * N);
+            a0 += ArD::mul_lazy(v, __ldg(reinterpret_cast<const double *>(key + (size_t)(i * 2 + 0) * nQP * N) + p), c);  // plain residue as FP64
+            a1 += ArD::mul_lazy(v, __ldg(reinterpret_cast<const double *>(key + (size_t)(i * 2 + 1) * nQP * N) + p), c);
+        }
+        *o0 = (uint64_t)ArD::canon(a0, c);
+        *o1 = (uint64_t)ArD::canon(a1, c);
+    } else {
+        uint64_t a0 = 0, a1 = 0;
+        for (int i = 0; i < beta; i++) {
+            const uint64_t v = __ldg(d + (size_t)i * nt * N);
+            a0 = add_mod(a0, mred(v, __ldg(key + (size_t)(i * 2 + 0) * nQP * N + p), lc), lc.q);  // Montgomery form, as uploaded
+            a1 = add_mod(a1, mred(v, __ldg(key + (size_t)(i * 2 + 1) * nQP * N + p), lc), lc.q);
+        }
+        *o0 = a0;
+        *o1 = a1;
     }
-    accout[((size_t)(ct * 2 + 0) * nt + tt) * N + p] = a0;
-    accout[((size_t)(ct * 2 + 1) * nt + tt) * N + p] = a1;
 }
 
 static int ntt_threads(int S) { return std::min(512, std::max(32, S >> kLastR)); }
@@ -607,7 +623,19 @@ static int rotate_chunk(Ctx *c, const KsBatch &b, BaseConv *ks, BaseConv *md, ui
     const int N = c->N, nl = b.level + 1, nt = nl + c->nP;
     // 2. inner products with the switching keys, one launch per arithmetic class of the target modulus
     if (D) {
-        k_ks_macd<<<dim3((N + 255) / 256, nt, b.nct), 256, 0, st>>>(D, b.c2_slot, b.keys, b.level, c->nQ, c->nP, N, c->lc, b.acc);
+        TgtSel ts[kNumArith] = {{0, {}}, {0, {}}, {0, {}}, {0, {}}};
+        for (int tt = 0; tt < nt; tt++) {
+            TgtSel &t = ts[arith_kind(c->mod[tt < nl ? tt : c->nQ + (tt - nl)])];
+            t.tt[t.n++] = tt;
+        }
+        const unsigned gx = (unsigned)((N + 255) / 256);
+        if (ts[kArW].n) k_ks_macd<kArW><<<dim3(gx, ts[kArW].n, b.nct), 256, 0, st>>>(D, b.c2_slot, b.keys, b.level, c->nQ, c->nP, N, c->lc, b.acc, ts[kArW]);
+        if (ts[kArD].n) k_ks_macd<kArD><<<dim3(gx, ts[kArD].n, b.nct), 256, 0, st>>>(D, b.c2_slot, b.keys, b.level, c->nQ, c->nP, N, c->lc, b.acc, ts[kArD]);
+        if (ts[kArN30].n)
+            k_ks_macd<kArN30><<<dim3(gx, ts[kArN30].n, b.nct), 256, 0, st>>>(D, b.c2_slot, b.keys, b.level, c->nQ, c->nP, N, c->lc, b.acc, ts[kArN30]);
+        if (ts[kArN31].n)
+            k_ks_macd<kArN31><<<dim3(gx, ts[kArN31].n, b.nct), 256, 0, st>>>(D, b.c2_slot, b.keys, b.level, c->nQ, c->nP, N, c->lc, b.acc, ts[kArN31]);
+        c->launches += (ts[kArW].n > 0) + (ts[kArD].n > 0) + (ts[kArN30].n > 0) + (ts[kArN31].n > 0) - 1;
         SFG_LAUNCHED(c, "k_ks_macd", st);
     } else if (inner_all(c, b, ks, st)) {
         return -1;

@@ -187,7 +187,8 @@ static int cache_meta_finish(Ctx *c, Cache *ca) {
     const int d = ca->d, m_ct = ca->m_ct, nbr = ca->nbr;
     const size_t npoly = ca->npoly;
     ca->kidx.assign((size_t)nbr * d, -1);
-    for (int bi = 0; bi < nbr; bi++)
+    if (ca->bi_hi < 0) ca->bi_hi = nbr;
+    for (int bi = ca->bi_lo; bi < ca->bi_hi; bi++)  // the K list (and with it the image) covers the cache's own block rows only
         for (int b = 0; b < d; b++)
             if (ca->baby[(size_t)bi * d + b]) {
                 ca->kidx[(size_t)bi * d + b] = (int)ca->kbi.size();
@@ -203,13 +204,18 @@ static int cache_meta_finish(Ctx *c, Cache *ca) {
     return tc_geom_p(c, ca->L, (int)ca->kbi.size(), (int)ca->gact.size() * m_ct, &ca->tc);
 }
 
-int cache_build(Ctx *c, Geno *g, int maxLevel, Cache **out) {
+int cache_build(Ctx *c, Geno *g, int maxLevel, Cache **out, int bi_lo, int bi_hi) {
     if (g->filled != g->nrows) SFG_FAIL(c, "genotype matrix incomplete: %zu of %zu rows pushed", g->filled, g->nrows);
     if (maxLevel < 1 || maxLevel > c->nQ - 1) SFG_FAIL(c, "maxLevel %d needs %d Q limbs, parameters have %d", maxLevel, maxLevel + 1, c->nQ);
+    const int nbr_all = (int)((g->nrows - 1) / c->slots) + 1;
+    if (bi_hi < 0) bi_hi = nbr_all;
+    if (bi_lo < 0 || bi_hi > nbr_all || bi_lo > bi_hi) SFG_FAIL(c, "block-row range [%d, %d) out of [0, %d)", bi_lo, bi_hi, nbr_all);
     SFG_CUDA(c, cudaSetDevice(c->device));
     Cache *ca = new Cache();
     ca->g = g;
     g->refs++;
+    ca->bi_lo = bi_lo;
+    ca->bi_hi = bi_hi;
     if (cache_init_meta(c, ca, g->nrows, g->ncols, maxLevel)) {
         cache_destroy(ca);
         return -1;
@@ -654,9 +660,15 @@ static int check_args(Ctx *c, const Cache *ca, int s, int nbr, int levelA, int m
     if (levelA > c->nQ - 1) SFG_FAIL(c, "input level %d exceeds the parameter chain", levelA);
     return 0;
 }
+static int check_rows(Ctx *c, const Cache *ca, int bi_lo, int bi_hi) {
+    if (bi_lo < ca->bi_lo || bi_hi > ca->bi_hi)
+        SFG_FAIL(c, "the cache holds block rows [%d, %d) only (built for block-row sharding); block rows [%d, %d) were requested", ca->bi_lo, ca->bi_hi,
+                 bi_lo, bi_hi);
+    return 0;
+}
 
 int mm_compute_dev(Ctx *c, const uint64_t *d_A, int s, int nbr, int levelA, int maxLevel, Cache *ca, uint64_t *d_out, uint64_t *host_out) {
-    if (check_args(c, ca, s, nbr, levelA, maxLevel)) return -1;
+    if (check_args(c, ca, s, nbr, levelA, maxLevel) || check_rows(c, ca, 0, nbr)) return -1;
     SFG_CUDA(c, cudaSetDevice(c->device));
     const int L = ca->L, N = c->N, m_ct = ca->m_ct;
     const size_t LN = (size_t)L * N;
@@ -717,6 +729,7 @@ int mm_partial_dev(Ctx *c, const uint64_t *d_A, int s, int nbr, int levelA, int 
                    uint64_t *d_cv) {
     if (check_args(c, ca, s, nbr, levelA, maxLevel)) return -1;
     if (bi_lo < 0 || bi_hi > nbr || bi_lo > bi_hi) SFG_FAIL(c, "block-row range [%d, %d) out of [0, %d)", bi_lo, bi_hi, nbr);
+    if (bi_lo < bi_hi && check_rows(c, ca, bi_lo, bi_hi)) return -1;
     SFG_CUDA(c, cudaSetDevice(c->device));
     const size_t LN = (size_t)ca->L * c->N;
     const size_t total = ca->gact.size() * (size_t)ca->m_ct * 2 * s * LN;

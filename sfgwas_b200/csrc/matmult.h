@@ -36,6 +36,7 @@ struct Cache {
     // K list: (bi, b) pairs with an active baby step, in (bi, b) order; kidx[bi*d+b] -> k or -1
     std::vector<int> kbi, kb, kidx;
     std::vector<int> gact;        // active giant indices (any block row)
+    int bi_lo = 0, bi_hi = -1;    // block rows whose diagonals the image holds (-1 = all): block-row sharding builds only a rank's own
 };
 
 struct Buf {  // RAII device buffer
@@ -62,7 +63,8 @@ int geno_create(Ctx *c, size_t nrows, size_t ncols, Geno **out);
 int geno_push(Geno *g, const int8_t *rows, size_t n);
 void geno_release(Geno *g);
 
-int cache_build(Ctx *c, Geno *g, int maxLevel, Cache **out);
+// bi_lo / bi_hi: build only the diagonals of block rows [bi_lo, bi_hi) (block-row sharding; such a cache serves mm_partial_dev only)
+int cache_build(Ctx *c, Geno *g, int maxLevel, Cache **out, int bi_lo = 0, int bi_hi = -1);
 // one cached diagonal polynomial (plain canonical residues, [L][N]) read back out of the image; 0 = nil
 int cache_get_diag_dev(Ctx *c, const Cache *ca, int bi, int shift, int bj, uint64_t *d_out, int *present);
 void cache_destroy(Cache *cache);

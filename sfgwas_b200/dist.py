@@ -12,8 +12,8 @@ Two shardings, both bit-identical to the single-GPU result:
   and K6: an integer SUM all-reduce of canonical residues (at most 2^8 ranks of residues < 2^56 fit a u64 -- NCCL ``ncclSum`` on
   int64 is exactly that) followed by one ``mod q`` pass (``sfg_cv_mod_reduce``), then every rank rotates and adds its own range
   of giant steps (``sfg_matmult4_finish``) and the per-rank outputs are summed the same way.
-  In this round every rank still builds the diagonal cache of the whole matrix (the partial entry point masks the other block
-  rows out of the R operand); a per-rank cache of only its block rows is the next step.
+  Every rank builds the diagonal cache of its own block rows only (``sfg_matmult4_stream_preprocess_rows``): HBM and preprocessing
+  time are proportional to the rank's share.
 
 Reference context: the reference has no intra-box parallelism beyond goroutines (gwas/matmult.go:983-1036, 1138-1169); the
 cross-party sum stays in Go (mpc/aggregate.go:466-500).
@@ -120,9 +120,14 @@ class RowSharded:
 
     def __init__(self, cps: CryptoParams, X: np.ndarray, rank: int, world: int, max_level: int = 5):
         self.cps, self.rank, self.world, self.max_level = cps, rank, world, max_level
-        self.gfs = GenoFileStream.from_matrix(cps, X)
-        self.cache = MatMult4StreamPreprocess(cps, self.gfs, max_level)
-        self.row_ranges = partition(self.cache.num_block_rows, world)
+        self.gfs = GenoFileStream.from_matrix(cps, X)  # int8, 1 byte per genotype: every rank holds the matrix, but encodes only its rows
+        nbr = (X.shape[0] - 1) // cps.slots + 1
+        self.row_ranges = partition(nbr, world)
+        lo, hi = self.row_ranges[rank]
+        h = C.c_void_p()
+        cps._check(cps.L.sfg_matmult4_stream_preprocess_rows(cps.h, self.gfs.h, max_level, lo, hi, C.byref(h)),
+                   "sfg_matmult4_stream_preprocess_rows")
+        self.cache = DiagCache(cps, h)  # diagonals of block rows [lo, hi) only
 
     def compute(self, A: np.ndarray, group=None) -> np.ndarray:
         import torch

@@ -509,6 +509,49 @@ def test_partial_mod_reduce_finish_equals_compute(small13):
     assert (total.astype(np.uint64) == single).all()
 
 
+def test_row_restricted_caches_equal_compute(small13):
+    """Block-row sharding with per-rank caches (sfg_matmult4_stream_preprocess_rows): each 'rank' holds the diagonals of its own block
+    rows only; partial sums + mod q + finish equal the single-cache result bit for bit, and a restricted cache refuses what it cannot do."""
+    import ctypes as C
+
+    import torch
+
+    from sfgwas_b200 import DiagCache, GenoFileStream, MatMult4StreamCompute, MatMult4StreamPreprocess, SfgError
+    from sfgwas_b200.gwas import _p
+
+    o, cps, sk, keys = small13
+    rng = np.random.default_rng(29)
+    nr, nc, s = 3 * o.slots + 17, 300, 2  # 4 block rows, the last one ragged
+    X = rng.integers(0, 3, (nr, nc)).astype(np.int8)
+    A = enc_matrix(o, sk, rng.normal(size=(s, nr)))
+    gfs = GenoFileStream.from_matrix(cps, X)
+    full = MatMult4StreamPreprocess(cps, gfs, 5)
+    single = MatMult4StreamCompute(cps, A, 5, full)
+    L, nbr = cps.L, A.shape[1]
+    dev = torch.device("cuda", cps.device)
+    n_cv = int(L.sfg_cv_elems(cps.h, full.h, s, 5))
+    acc, caches = None, []
+    for lo, hi in ((0, 1), (1, 3), (3, nbr)):
+        h = C.c_void_p()
+        cps._check(L.sfg_matmult4_stream_preprocess_rows(cps.h, gfs.h, 5, lo, hi, C.byref(h)), "preprocess_rows")
+        ca = DiagCache(cps, h)
+        caches.append(ca)
+        assert ca.bytes < full.bytes and int(L.sfg_cv_elems(cps.h, ca.h, s, 5)) == n_cv  # smaller image, same accumulator layout
+        cv = torch.empty(n_cv, dtype=torch.int64, device=dev)
+        cps._check(L.sfg_matmult4_partial(cps.h, _p(A), s, nbr, 5, 5, ca.h, lo, hi, C.c_void_p(cv.data_ptr())), "partial")
+        acc = cv if acc is None else acc + cv
+    torch.cuda.synchronize()
+    cps._check(L.sfg_cv_mod_reduce(cps.h, caches[0].h, s, 5, C.c_void_p(acc.data_ptr()), 0, n_cv), "mod_reduce")
+    per_g = full.m_ct * 2 * s * 5 * cps.N
+    out = np.zeros(single.shape, dtype=np.uint64)
+    cps._check(L.sfg_matmult4_finish(cps.h, caches[1].h, s, 5, C.c_void_p(acc.data_ptr()), 0, n_cv // per_g, _p(out)), "finish")
+    assert (out == single).all()
+    with pytest.raises(SfgError, match="holds block rows"):
+        MatMult4StreamCompute(cps, A, 5, caches[0])
+    cv = torch.empty(n_cv, dtype=torch.int64, device=dev)
+    assert L.sfg_matmult4_partial(cps.h, _p(A), s, nbr, 5, 5, caches[0].h, 0, 2, C.c_void_p(cv.data_ptr())) != 0
+
+
 @pytest.mark.parametrize("nr,nc", [(300, 520), (128, 77), (700, 130)])
 def test_diag_cache_files_interop(small13, tmp_path, nr, nc, monkeypatch):
     """the reference's on-disk cache format (gwas/filestream.go:19-282).  GPU-written files are byte-identical to
