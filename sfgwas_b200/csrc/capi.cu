@@ -75,6 +75,8 @@ void sfg_ctx_destroy(sfg_ctx *h) {
     cudaFree(c->roots);
     cudaFree(c->ddcos);
     cudaFree(c->rot5);
+    cudaFree(c->dlog_pos);
+    cudaFree(c->dlog_src);
     cudaFree(c->enc_stats);
     for (auto &kv : c->bc_ks) cudaFree(kv.second);
     for (auto &kv : c->bc_md) cudaFree(kv.second);

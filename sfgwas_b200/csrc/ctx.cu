@@ -132,6 +132,24 @@ int ctx_build_tables(Ctx *c, const uint64_t *psi_opt) {
     SFG_CUDA(c, cudaMemcpy(c->ddcos, dd.data(), sizeof(double) * dd.size(), cudaMemcpyHostToDevice));
     SFG_CUDA(c, cudaMalloc(&c->rot5, sizeof(int) * rot5.size()));
     SFG_CUDA(c, cudaMemcpy(c->rot5, rot5.data(), sizeof(int) * rot5.size(), cudaMemcpyHostToDevice));
+    {
+        const uint64_t twoN = 2 * (uint64_t)N, n2 = (uint64_t)N / 2;
+        std::vector<uint32_t> of_exp(twoN, 0), pos(N), src(N);
+        uint64_t p5 = 1;
+        for (uint64_t t = 0; t < n2; t++) {
+            of_exp[p5] = (uint32_t)t;
+            of_exp[twoN - p5] = (uint32_t)(n2 + t);
+            p5 = p5 * 5 % twoN;
+        }
+        for (int i = 0; i < N; i++) {
+            pos[i] = of_exp[2 * h_bitrev((uint64_t)i, c->logN) + 1];
+            src[pos[i]] = (uint32_t)i;
+        }
+        SFG_CUDA(c, cudaMalloc(&c->dlog_pos, sizeof(uint32_t) * N));
+        SFG_CUDA(c, cudaMemcpy(c->dlog_pos, pos.data(), sizeof(uint32_t) * N, cudaMemcpyHostToDevice));
+        SFG_CUDA(c, cudaMalloc(&c->dlog_src, sizeof(uint32_t) * N));
+        SFG_CUDA(c, cudaMemcpy(c->dlog_src, src.data(), sizeof(uint32_t) * N, cudaMemcpyHostToDevice));
+    }
     SFG_CUDA(c, cudaMalloc(&c->enc_stats, sizeof(unsigned long long) * 2));
     SFG_CUDA(c, cudaMemset(c->enc_stats, 0, sizeof(unsigned long long) * 2));
     // FP64 special-FFT error model for slot values |v| <= 4: scale * eps * log2(n) * 4 / sqrt(n); the window is 64x that

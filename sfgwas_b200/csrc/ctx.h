@@ -50,6 +50,10 @@ struct Ctx {
     // encoder (special inverse FFT)
     double2 *roots = nullptr;              // device [2N+1] exp(2 pi i k / 2N)
     int *rot5 = nullptr;                   // device [slots] 5^j mod 2N
+    // discrete-log order of the NTT evaluation points: coefficient i of an NTT-domain polynomial is the value at psi^(2 brv(i) + 1) =
+    // psi^(+-5^t); position q = s * N/2 + t (s = sign = top bit of i).  In that order the automorphism X -> X^(5^r) is a cyclic
+    // shift by r inside each half (kernels_ks.cu: the giant-step sums).  dlog_pos[i] = q, dlog_src[q] = i.
+    uint32_t *dlog_pos = nullptr, *dlog_src = nullptr;  // device [N]
     double2 *ddcos = nullptr;              // device [2N] cos(2 pi t / 2N) as double-double (hi, lo)
     double enc_delta = 0;                  // half-integer ambiguity window for the FP64 path
     unsigned long long *enc_stats = nullptr;  // device [2]: {rechecked coefficients, unresolved ties}

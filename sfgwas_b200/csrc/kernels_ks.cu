@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(512, A::kMinBlocks)
 k_ks_inner2(const uint64_t *__restrict__ in, const long long *__restrict__ in_off, int in_nl, const uint64_t *__restrict__ c2,
             const int *__restrict__ c2_slot, const uint64_t *const *__restrict__ keys, const BaseConv *__restrict__ ks, int level, int nQ,
             int nP, int logN_arg, PassPlan plan_arg, const TwTab *__restrict__ tabs, const LimbConst *__restrict__ lcs,
-            uint64_t *__restrict__ accout, TgtSel sel, uint64_t *__restrict__ dout) {
+            uint64_t *__restrict__ accout, TgtSel sel, uint64_t *__restrict__ dout, const uint32_t *__restrict__ dlog_src) {
     // DM (dout != nullptr): DIGIT mode.  The transforms NTT_t(Ext(digit_i(c1))) do not depend on the switching key, so rotations of the SAME
     // ciphertext by different amounts (the d-1 baby steps of every A[i][bi]) share them: the kernel then runs once per distinct input
     // (ct = slot, c2_slot == keys == nullptr) and stores the canonical transforms D[slot][i][tt] in TT order instead of multiplying
@@ -210,7 +210,22 @@ k_ks_inner2(const uint64_t *__restrict__ in, const long long *__restrict__ in_of
         }
         __syncthreads();
     }
-    if (active && !DM) {
+    if (!DM && dlog_src && tt < nl) {
+        // giant-step sums: Q limbs leave in discrete-log order (position q holds the coefficient dlog_src[q]; a half-ring slice is
+        // exactly one sign class, i.e. a contiguous half), so that k_md_accum can add rotated polynomials as shifted contiguous reads
+        // (the digit loop ended with a barrier: every accumulator slot is final and visible)
+        uint64_t *o0 = accout + ((size_t)(ct * 2 + 0) * nt + tt) * N + gbase, *o1 = accout + ((size_t)(ct * 2 + 1) * nt + tt) * N + gbase;
+        for (int j = threadIdx.x; j < S; j += blockDim.x) {
+            const int sj = sidx<sizeof(T)>((int)__ldg(dlog_src + gbase + j) - gbase);
+            if constexpr (A::kKind == kArD) {
+                o0[j] = (uint64_t)A::canon(s0a[sj], c);
+                o1[j] = (uint64_t)A::canon(s1a[sj], c);
+            } else {
+                o0[j] = s0a[sj];
+                o1[j] = s1a[sj];
+            }
+        }
+    } else if (active && !DM) {
         uint64_t *o0 = accout + ((size_t)(ct * 2 + 0) * nt + tt) * N + P;
         uint64_t *o1 = accout + ((size_t)(ct * 2 + 1) * nt + tt) * N + P;
 #pragma unroll
@@ -353,15 +368,15 @@ k_md_accum(const uint64_t *__restrict__ in, const long long *__restrict__ in_off
         c0s[m] = (ld && comp == 0) ? (T)C0o[obase + k] : 0;
         es[m] = ld ? (T)Eo[obase + k] : 0;
     }
-    // stage sequence: per entry  [accQ] [c0 if comp == 0] [accP if nP == 1]
+    // accQ is in discrete-log order (k_ks_inner2): perm_a is a cyclic shift inside each half, read straight from global memory.
+    // stage sequence of the ring: per entry  [c0 if comp == 0] [accP if nP == 1]
     const bool stageP = nP == 1;
-    const int spe = 1 + (comp == 0 ? 1 : 0) + (stageP ? 1 : 0);
+    const int spe = (comp == 0 ? 1 : 0) + (stageP ? 1 : 0);
     const int nstage = nacc * spe;
     const uint32_t bytes = (uint32_t)N * 8;
     auto src_of = [&](int st) -> const uint64_t * {
         const int a = st / spe, w = st % spe, ct = a * nout + o;
-        if (w == 0) return acc + ((size_t)(ct * 2 + comp) * nt + l) * N;              // accQ: NTT domain, TT order
-        if (w == 1 && comp == 0) return in + in_off[ct] + (size_t)l * N;               // c0: NTT domain, natural order
+        if (w == 0 && comp == 0) return in + in_off[ct] + (size_t)l * N;               // c0: NTT domain, natural order
         return acc + ((size_t)(ct * 2 + comp) * nt + nl) * N;                          // accP: coefficient domain, natural order
     };
     if (tid == 0) {
@@ -391,13 +406,18 @@ k_md_accum(const uint64_t *__restrict__ in, const long long *__restrict__ in_off
         uint32_t pk[E16];
 #pragma unroll
         for (int m = 0; m < E16; m++) pk[m] = tid < per ? __ldg(perm + kbase + tid + per * m) : 0;
-        {
-            const uint64_t *sq = next_stage();
-            if (tid < per) {
+        const uint32_t gw = ginv[ct];  // galEl^-1 mod 2N in the low 18 bits, the rotation amount r (galEl = 5^r) above
+        if (tid < per) {
+            const uint64_t *aq = acc + ((size_t)(ct * 2 + comp) * nt + l) * N;
+            const uint32_t r = gw >> 18, n2m = (uint32_t)(N >> 1) - 1;
+            T q1[E16];
 #pragma unroll
-                for (int m = 0; m < E16; m++) s1[m] = addm(s1[m], (T)sq[tt_index((int)pk[m], N)]);
+            for (int m = 0; m < E16; m++) {
+                const uint32_t k = (uint32_t)(kbase + tid + per * m);
+                q1[m] = (T)__ldg(aq + ((k & ~n2m) | ((k + r) & n2m)));
             }
-            release_stage();
+#pragma unroll
+            for (int m = 0; m < E16; m++) s1[m] = addm(s1[m], q1[m]);
         }
         if (comp == 0) {
             const uint64_t *sc = next_stage();
@@ -407,7 +427,7 @@ k_md_accum(const uint64_t *__restrict__ in, const long long *__restrict__ in_off
             }
             release_stage();
         }
-        const uint32_t gi = ginv[ct];
+        const uint32_t gi = gw & 0x3FFFFu;
         if (stageP) {
             const uint64_t *sp = next_stage();
             if (tid < per) {
@@ -446,7 +466,7 @@ template <class A>
 __global__ void __launch_bounds__(512, A::kMinBlocks)
 k_md_final(const uint64_t *__restrict__ S1, const uint64_t *__restrict__ C0, const uint64_t *__restrict__ E, const uint64_t *__restrict__ pinv,
            int logN, PassPlan plan, const TwTab *__restrict__ tabs, const LimbConst *__restrict__ lcs, unsigned char *__restrict__ out,
-           const long long *__restrict__ out_off, PolyLayout olay, int L, TgtSel sel) {
+           const long long *__restrict__ out_off, PolyLayout olay, int L, TgtSel sel, const uint32_t *__restrict__ dlog_pos) {
     using T = typename A::T;
     extern __shared__ __align__(16) unsigned char smraw[];
     T *s = reinterpret_cast<T *>(smraw);
@@ -460,7 +480,7 @@ k_md_final(const uint64_t *__restrict__ S1, const uint64_t *__restrict__ C0, con
     auto ld0 = [&](int j, int) -> T { return A::load_u64(E[obase + j], c); };
     auto fin = [&](int j, T v, int) {
         const uint64_t e = A::canon(v, c);
-        uint64_t r = mul_shoup(sub_mod(S1[obase + j], e, lc.q), pi, pish, lc.q);
+        uint64_t r = mul_shoup(sub_mod(S1[obase + __ldg(dlog_pos + j)], e, lc.q), pi, pish, lc.q);  // S1 is kept in discrete-log order
         if (comp == 0) r = add_mod(r, C0[obase + j], lc.q);
         ob[j] = add_mod(ob[j], r, lc.q);
     };
@@ -555,7 +575,7 @@ static int inner_launch2(Ctx *c, const KsBatch &b, BaseConv *ks, const TgtSel &s
     auto go = [&](auto kern) -> int {
         SFG_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<g, ntt_threads(S), smem, st>>>(b.in, b.in_off, b.in_nl, b.c2, b.c2_slot, b.keys, ks, b.level, c->nQ, c->nP, logN, plan, c->tw2, c->lc,
-                                              b.acc, sel, b.dout);
+                                              b.acc, sel, b.dout, b.acc_dlog ? c->dlog_src : nullptr);
         SFG_LAUNCHED(c, "k_ks_inner2", st);
         return 0;
     };
@@ -855,6 +875,7 @@ int launch_rotate_sum(Ctx *c, const KsBatch &b, int nout, const uint32_t *ginv_d
         ch.keys += k0;
         ch.perms += k0;
         ch.out_off += k0;
+        ch.acc_dlog = true;
         if (rotate_chunk(c, ch, ks, md, pinv, st, false)) return -1;
         const int nsplit = N > 8192 ? N / 8192 : 1;
         const int thr = std::min(512, std::max(32, N / nsplit / 16));
@@ -876,7 +897,8 @@ static int md_final_launch(Ctx *c, int level, int nout, const uint64_t *S1, cons
     const size_t smem = ntt_smem_elems(N) * sizeof(typename A::T);
     SFG_CUDA(c, cudaFuncSetAttribute(k_md_final<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 g(sel.n, 2, nout);
-    k_md_final<A><<<g, ntt_threads(N), smem, st>>>(S1, C0, E, pinv, logN, plan, c->tw2, c->lc, (unsigned char *)out, out_off, olay, olay.nl, sel);
+    k_md_final<A><<<g, ntt_threads(N), smem, st>>>(S1, C0, E, pinv, logN, plan, c->tw2, c->lc, (unsigned char *)out, out_off, olay, olay.nl, sel,
+                                                   c->dlog_pos);
     SFG_LAUNCHED(c, "k_md_final", st);
     return 0;
 }

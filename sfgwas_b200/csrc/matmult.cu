@@ -609,7 +609,8 @@ static int run_giant(Ctx *c, const Cache *ca, int s, const uint64_t *d_cv, int g
             const int gi = grot[a], g = ca->gact[gi];
             const GaloisKey *key = nullptr;
             if (find_key(c, (g * d) % ca->slots, &key)) return -1;
-            const uint32_t gin = inv_mod_pow2(key->galEl, c->logN + 1);
+            // galEl^-1 mod 2N (low 18 bits) and the rotation amount r, galEl = 5^r (k_md_accum: cyclic shift in discrete-log order)
+            const uint32_t gin = inv_mod_pow2(key->galEl, c->logN + 1) | ((uint32_t)((g * d) % ca->slots) << 18);
             for (int o = 0; o < nout_c; o++) {  // o = (i - i_lo) * m_ct + bj: the chunk's outputs are contiguous in `out`
                 const int i = i_lo + o / m_ct, bj = o % m_ct;
                 const long long in_off = (long long)((((size_t)(gi - gi_lo) * m_ct + bj) * nrows + 2 * i) * LN);
