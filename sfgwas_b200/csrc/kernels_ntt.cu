@@ -300,7 +300,7 @@ int launch_mod_reduce(Ctx *c, uint64_t *x, size_t npoly, int L, cudaStream_t st)
 
 // ---------------------------------------------------------------------------------------------------------------
 // Genotype preparation: gwas/matmult.go:1289-1304 (missing -> 0, sum / sqSum before squaring, optional square).
-// One thread per 16 consecutive columns of a row slab; per-column partial sums are reduced over a slab of rows in
+// One thread per column (k_geno_prep) or per 16 consecutive columns (k_geno_prep16) of a row slab; partial sums are reduced over the slab in
 // registers and flushed with one atomicAdd per (slab, column).  The sums are exact: every partial is a small integer.
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void k_geno_prep(int8_t *__restrict__ X, size_t rows, size_t ncols, double *__restrict__ sum, double *__restrict__ sqsum,
@@ -322,8 +322,56 @@ __global__ void k_geno_prep(int8_t *__restrict__ X, size_t rows, size_t ncols, d
     if (sqsum) atomicAdd(&sqsum[col], (double)s2);
 }
 
+// The same scan with 16-byte accesses (ncols % 16 == 0): a thread owns 16 consecutive columns of a slab of rows; a row segment is
+// written back only when it changes (a missing value, or squaring).  HBM-bound: rows * ncols bytes read once.
+__global__ void __launch_bounds__(256)
+k_geno_prep16(int8_t *__restrict__ X, size_t rows, size_t ncols, double *__restrict__ sum, double *__restrict__ sqsum, int square,
+              int rows_per_slab) {
+    const size_t col0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 16;
+    if (col0 >= ncols) return;
+    const size_t r0 = (size_t)blockIdx.y * rows_per_slab;
+    const size_t r1 = r0 + rows_per_slab < rows ? r0 + rows_per_slab : rows;
+    int s1[16], s2[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) s1[k] = s2[k] = 0;
+    for (size_t r = r0; r < r1; r++) {
+        uint4 *p = reinterpret_cast<uint4 *>(X + r * ncols + col0);
+        const uint4 in = *p;
+        uint32_t w[4] = {in.x, in.y, in.z, in.w}, o[4];
+        bool changed = false;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            uint32_t ow = 0;
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                int8_t v = (int8_t)(w[q] >> (8 * b));
+                if (v < 0) v = 0;
+                const int8_t v2 = (int8_t)(v * v);  // int8 arithmetic like the reference (row[rj]*row[rj])
+                s1[4 * q + b] += v;
+                s2[4 * q + b] += v2;
+                ow |= (uint32_t)(uint8_t)(square ? v2 : v) << (8 * b);
+            }
+            o[q] = ow;
+            changed |= ow != w[q];
+        }
+        if (changed) *p = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        if (sum && s1[k]) atomicAdd(&sum[col0 + k], (double)s1[k]);
+        if (sqsum && s2[k]) atomicAdd(&sqsum[col0 + k], (double)s2[k]);
+    }
+}
+
 int launch_geno_prep(Ctx *c, int8_t *X, size_t rows, size_t ncols, double *sum, double *sqsum, bool square, cudaStream_t st) {
     if (rows == 0 || ncols == 0) return 0;
+    if (ncols % 16 == 0 && ((uintptr_t)X % 16) == 0) {
+        const int rows_per_slab = 64;
+        dim3 g((unsigned)((ncols / 16 + 255) / 256), (unsigned)((rows + rows_per_slab - 1) / rows_per_slab));
+        k_geno_prep16<<<g, 256, 0, st>>>(X, rows, ncols, sum, sqsum, square ? 1 : 0, rows_per_slab);
+        SFG_LAUNCHED(c, "k_geno_prep16", st);
+        return 0;
+    }
     const int rows_per_slab = 256;
     dim3 g((unsigned)((ncols + 255) / 256), (unsigned)((rows + rows_per_slab - 1) / rows_per_slab));
     k_geno_prep<<<g, 256, 0, st>>>(X, rows, ncols, sum, sqsum, square ? 1 : 0, rows_per_slab);

@@ -370,12 +370,13 @@ def test_pn14_shape_bit_exact(small14):
     assert (out == want).all()
 
 
-def test_matmult4_stream_fused(small13):
+@pytest.mark.parametrize("nc", [140, 144])  # 144: the 16-byte genotype scan (ncols % 16 == 0); 140: the byte-wise one
+def test_matmult4_stream_fused(small13, nc):
     from sfgwas_b200 import GenoFileStream, MatMult4Stream
 
     o, cps, sk, keys = small13
     rng = np.random.default_rng(21)
-    X = rng.integers(-1, 3, (150, 140)).astype(np.int8)  # -1 = missing
+    X = rng.integers(-1, 3, (150, nc)).astype(np.int8)  # -1 = missing
     A = enc_matrix(o, sk, rng.normal(size=(2, 150)))
     gfs = GenoFileStream.from_matrix(cps, X)
     for sq_sum, square in ((True, True), (True, False), (False, False)):
