@@ -30,10 +30,15 @@ sys.path.insert(0, ROOT)
 
 PN13 = dict(logN=13, Q=[0x1FFFEC001, 0x3FFF4001, 0x3FFE8001, 0x40020001, 0x40038001, 0x3FFC0001], P=[0x800004001],
             scale=float(1 << 30))
+PN14 = dict(logN=14, Q=[0x200000008001, 0x400018001, 0x3FFFD0001, 0x400060001, 0x400068001, 0x3FFF90001, 0x400080001, 0x4000A8001,
+                         0x400108001, 0x3FFEB8001], P=[0x7FFFFFD8001, 0x7FFFFFC8001], scale=float(1 << 34))
+CKKS = {"PN13QP218": PN13, "PN14QP438": PN14}
 WORKLOADS = {
-    # name: (nrows, ncols, s)
-    "mm_10k_x_100k_k10_logN13": (10000, 100000, 10),
-    "mm_2k_x_20k_k10_logN13": (2000, 20000, 10),   # quick check only
+    # name: (nrows, ncols, s, CKKS parameter set)
+    "mm_10k_x_100k_k10_logN13": (10000, 100000, 10, "PN13QP218"),
+    "mm_2k_x_20k_k10_logN13": (2000, 20000, 10, "PN13QP218"),   # quick check only
+    # a PCA-shaped block (BASELINE configs 4/5 run at logN 14, kp = 15): extra data point, not the default bench line
+    "mm_16k_x_64k_k15_logN14": (16384, 65536, 15, "PN14QP438"),
 }
 
 
@@ -134,7 +139,7 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------------------------
 # CPU baseline: the reference's algorithm (oracle port, gwas/matmult.go:1138-1236) on a BOUNDED sample of the workload
 # ------------------------------------------------------------------------------------------------------------------
-def cpu_sample(wf, s, nthreads, mac_diags=12288, rots_per_thread=12):
+def cpu_sample(wf, s, nthreads, mac_diags=12288, rots_per_thread=12, P=None):
     """Times (i) the K1 lazy-MAC loop with the reference's per-(row, giant) locks on `mac_diags` diagonal polynomials
     resident in RAM, and (ii) level-5 / level-4 rotations (key-switch + automorphism) on all threads; extrapolates linearly
     to the full call.  Returns (GB/s, description)."""
@@ -142,7 +147,7 @@ def cpu_sample(wf, s, nthreads, mac_diags=12288, rots_per_thread=12):
 
     from oracle.oracle import Oracle
 
-    o = Oracle.from_params(PN13)
+    o = Oracle.from_params(P or PN13)
     t_mac = o.L.orc_bench_mac(o.N, 5, s, mac_diags, nthreads)
     mac_rate = mac_diags * s * 2 * 5 * o.N / t_mac
     sk = o.keygen_secret(1)
@@ -177,12 +182,12 @@ def cpu_sample(wf, s, nthreads, mac_diags=12288, rots_per_thread=12):
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    nrows, ncols, s = WORKLOADS[args.workload]
-    wf = work_figures(nrows, ncols, s, PN13["logN"])
+    nrows, ncols, s, pname = WORKLOADS[args.workload]
+    wf = work_figures(nrows, ncols, s, CKKS[pname]["logN"])
     nthreads = os.cpu_count() or 1
     vals, t0 = [], time.perf_counter()
     for it in range(args.warmup + args.steps):
-        v, t_full, desc = cpu_sample(wf, s, nthreads)
+        v, t_full, desc = cpu_sample(wf, s, nthreads, P=CKKS[pname])
         if it >= args.warmup:
             vals.append((v, t_full))
     v = sum(x[0] for x in vals) / len(vals)
@@ -190,7 +195,7 @@ def run_reference(args, rank, world):
     line = dict(metric="genotype x ciphertext MatMult GB/s (B_alg / t)", value=v, unit="GB/s", n_gpus=args.gpus, steps=args.steps,
                 warmup=args.warmup, ms_per_step=t_full * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="u64",
                 data="synthetic", impl="reference",
-                config=dict(workload=args.workload, ckks_params="PN13QP218", orientation="A.X", s=s, note="CPU arm: the per-GPU workload timed on the host cores of the box (rank 0 only)"),
+                config=dict(workload=args.workload, ckks_params=pname, orientation="A.X", s=s, note="CPU arm: the per-GPU workload timed on the host cores of the box (rank 0 only)"),
                 cpu_baseline=dict(value=v, unit="GB/s", cores=nthreads, kind="port", sample=desc),
                 e2e=dict(value=v, unit="GB/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 wall_s=time.perf_counter() - t0)
@@ -209,8 +214,8 @@ def run_ours(args, rank, local_rank, world):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    nrows, ncols, s = WORKLOADS[args.workload]
-    P = PN13
+    nrows, ncols, s, pname = WORKLOADS[args.workload]
+    P = CKKS[pname]
     wf = work_figures(nrows, ncols, s, P["logN"])
     N, slots, d, nbr, m_ct = wf["N"], wf["slots"], wf["d"], wf["nbr"], wf["m_ct"]
     cps = CryptoParams(P["logN"], P["Q"], P["P"], P["scale"], device=local_rank)
@@ -317,7 +322,7 @@ def run_ours(args, rank, local_rank, world):
             metric="genotype x ciphertext MatMult GB/s (B_alg / t)", value=value, unit="GB/s", n_gpus=world, steps=args.steps,
             warmup=args.warmup, ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="u64",
             data="synthetic",
-            config=dict(workload=args.workload, ckks_params="PN13QP218", logN=13, s=s, orientation="A.X", max_level=5,
+            config=dict(workload=args.workload, ckks_params=pname, logN=P["logN"], s=s, orientation="A.X", max_level=5,
                         num_block_rows=nbr, m_ct=m_ct, diag_polys=wf["diag_polys"], b_alg_bytes=wf["b_alg"], mac_alg=wf["mac_alg"],
                         key_switches=[wf["ks_baby"], wf["ks_giant"]], step="MatMult4StreamCompute over the HBM-resident diagonal cache",
                         cache_bytes=cbytes.value, cache_materialised=bool(mat.value), preprocess_s=t_prep,
@@ -328,7 +333,8 @@ def run_ours(args, rank, local_rank, world):
                      d2h_bytes_per_step=int(h_out.numel() * 8)),
             gpu_launches=int(launches),
             roofline=dict(bound="hbm", kernel="k_mac_tc (K1+K2: tcgen05 kind::i8 byte-plane MAC + recombine + modular reduce)",
-                          achieved=mac_gbs, peak=peak, unit="GB/s", frac=mac_gbs / peak, traffic=read_traffic(),
+                          achieved=mac_gbs, peak=peak, unit="GB/s", frac=mac_gbs / peak,
+                          traffic=read_traffic() if args.workload == "mm_10k_x_100k_k10_logN13" else None,  # the capture is of the default workload
                           traffic_source="ncu --set full, profiles/r1_final/ncu_k_mac_tc.txt (dram read + write per launch)",
                           peak_source=peak_src + " (MEASURED_PEAKS.json hbm_gbs)",
                           algorithmic_bytes_per_launch=wf["b_diag"], stored_bytes_per_launch=int(cbytes.value),
@@ -342,7 +348,7 @@ def run_ours(args, rank, local_rank, world):
         )
         if world == 1 and not args.no_cpu_baseline:
             nthreads = os.cpu_count() or 1
-            v, t_full, desc = cpu_sample(wf, s, nthreads)
+            v, t_full, desc = cpu_sample(wf, s, nthreads, P=P)
             line["cpu_baseline"] = dict(value=v, unit="GB/s", cores=nthreads, kind="port", sample=desc, est_s_per_step=t_full)
         print(json.dumps(line), flush=True)
     L.sfg_cache_destroy(cache)

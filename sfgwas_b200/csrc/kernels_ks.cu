@@ -342,9 +342,8 @@ __global__ void __launch_bounds__(512, 1)
 k_md_accum(const uint64_t *__restrict__ in, const long long *__restrict__ in_off, int in_nl, const uint64_t *__restrict__ acc,
            const BaseConv *__restrict__ md, const uint32_t *const *__restrict__ perms, const uint32_t *__restrict__ ginv, int level, int nQ,
            int nP, int logN_arg, const LimbConst *__restrict__ lcs, int nout, int nacc, uint64_t *__restrict__ S1o, uint64_t *__restrict__ C0o,
-           uint64_t *__restrict__ Eo, int L, int first, TgtSel sel) {
+           uint64_t *__restrict__ Eo, int L, int first, TgtSel sel, int NBUF /* ring depth: 3, or what fits (2^14-coefficient rings: 1) */) {
     extern __shared__ __align__(128) uint64_t sst[];
-    constexpr int NBUF = 3;
     const int logN = LOGN ? LOGN : logN_arg;
     const int N = 1 << logN, nl = level + 1, nt = nl + nP;
     uint64_t *bars = sst + (size_t)NBUF * N;
@@ -854,11 +853,14 @@ int launch_rotate_sum(Ctx *c, const KsBatch &b, int nout, const uint32_t *ginv_d
     sel.n = nl;
     for (int i = 0; i < nl; i++) sel.idx[i] = i;
     if (launch_ntt_gather(c, b.in + (size_t)b.in_nl * N, b.c2_src_off, 0, b.c2, (size_t)nl * N, b.n_c2 * nl, sel, true, false, st)) return -1;
-    const size_t smem = (size_t)3 * N * 8 + 64;
+    // whole source polynomials are staged (the permutation reaches anywhere): as many ring buffers as fit one CTA, at most 3
+    const int nbuf = (int)std::max<size_t>(1, std::min<size_t>(3, ((size_t)220 << 10) / ((size_t)N * 8)));
+    const size_t smem = (size_t)nbuf * N * 8 + 64;
+    if (smem > ((size_t)227 << 10)) SFG_FAIL(c, "giant-step sums: a ring of 2^%d coefficients does not fit one CTA's shared memory", c->logN);
     auto accum = [&](auto kern, const TgtSel &ts, const KsBatch &ch, int k0, int nsplit, int thr, int fst) -> int {
         SFG_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<dim3(ts.n * nsplit, 2, nout), thr, smem, st>>>(ch.in, ch.in_off, ch.in_nl, ch.acc, md, ch.perms, ginv_dev + k0, ch.level, c->nQ, c->nP,
-                                                              c->logN, c->lc, nout, ch.nct / nout, S1, C0, E, L, fst, ts);
+                                                              c->logN, c->lc, nout, ch.nct / nout, S1, C0, E, L, fst, ts, nbuf);
         SFG_LAUNCHED(c, "k_md_accum", st);
         return 0;
     };

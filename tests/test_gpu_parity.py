@@ -406,14 +406,15 @@ def test_error_behaviour(small13):
         MatMult4StreamPreprocess(cps, g2, 5)
 
 
-def test_linearity_property_full_size_pn13():
-    """Size-independent property at the real logN=13 ring: MatMult(A1 + A2) == MatMult(A1) + MatMult(A2) is NOT bitwise
+@pytest.mark.parametrize("pname", ["PN13QP218", "PN14QP438"])
+def test_linearity_property_full_size_pn13(pname):
+    """Size-independent property at the real logN=13 / logN=14 rings: MatMult(A1 + A2) == MatMult(A1) + MatMult(A2) is NOT bitwise
     (key-switch rounding), but the MAC stage is: cv is linear mod q. Checked through one block with s=2 rows where row 1 =
     2*row 0 (mod q): out row 1 decrypts to twice row 0; and idempotence: the same call twice gives identical bits."""
     from oracle.oracle import PARAMS
     from sfgwas_b200 import GenoFileStream, MatMult4StreamCompute, MatMult4StreamPreprocess
 
-    o, cps = make(PARAMS["PN13QP218"])
+    o, cps = make(PARAMS[pname])
     sk = o.keygen_secret(5)
     d = o.d
     # a narrow matrix keeps the number of needed keys small: nr = 40 rows -> shifts 0..39 and 4096-c+1.. ; use c = 1 column block
