@@ -250,7 +250,8 @@ __global__ void __launch_bounds__(512, A::kMinBlocks)
 k_ks_moddown2(const uint64_t *__restrict__ in, const long long *__restrict__ in_off, int in_nl, const uint64_t *__restrict__ acc,
               const BaseConv *__restrict__ md, const uint64_t *__restrict__ pinv, const uint32_t *const *__restrict__ perms, int level,
               int nQ, int nP, int logN_arg, PassPlan plan_arg, const TwTab *__restrict__ tabs, const LimbConst *__restrict__ lcs,
-              unsigned char *__restrict__ out, const long long *__restrict__ out_off, PolyLayout olay, int accumulate, TgtSel sel) {
+              unsigned char *__restrict__ out, const long long *__restrict__ out_off, PolyLayout olay, int accumulate, TgtSel sel,
+              const uint64_t *__restrict__ extP /* nP > 1: Ext(accP) per (ct, comp, limb < olay.nl) from k_md_extp, else null */) {
     using T = typename A::T;
     extern __shared__ __align__(16) unsigned char smraw[];
     T *s = reinterpret_cast<T *>(smraw);
@@ -271,6 +272,7 @@ k_ks_moddown2(const uint64_t *__restrict__ in, const long long *__restrict__ in_
         if constexpr (A1) {
             return A::load_u64(accP[j], c);
         } else {
+            if (extP) return A::load_u64(extP[((size_t)(ct * 2 + comp) * olay.nl + l) * N + j], c);
             uint64_t xs[kMaxAlpha];
             for (int k = 0; k < nP; k++) xs[k] = accP[(size_t)k * N + j];
             return A::load_u64(base_conv_coeff(bc, xs, lcs, lc.q), c);
@@ -337,12 +339,41 @@ __device__ __forceinline__ void md_wait(uint64_t *bar, uint32_t parity) {
         : "memory");
 }
 
+// nP > 1: the exact base conversion of the P limbs to every Q modulus, once per (entry, component, coefficient) with unit stride --
+// k_md_accum then stages ext[l] like a single P limb.  (Evaluated inside k_md_accum it ran per limb CTA, at permuted -- uncoalesced --
+// positions, with its float64 divisions in the innermost loop: 52 of the 285 ms of a logN = 14 step.)
+__global__ void k_md_extp(const uint64_t *__restrict__ acc, const BaseConv *__restrict__ md, int nl, int nt, int nP, int L, int N,
+                          const LimbConst *__restrict__ lcs, uint64_t *__restrict__ ext) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, p = blockIdx.y;  // p = ct * 2 + comp
+    if (j >= N) return;
+    const uint64_t *accP = acc + ((size_t)p * nt + nl) * N + j;
+    const BaseConv &b0 = md[0];  // the source-side constants are the same for every target
+    uint64_t ys[kMaxAlpha];
+    double vi = 0.0;
+#pragma unroll 1
+    for (int k = 0; k < nP; k++) {
+        const uint64_t sk = lcs[b0.src_limb[k]].q;
+        ys[k] = mul_shoup(accP[(size_t)k * N], b0.sinv[k], b0.sinv_sh[k], sk);
+        vi += __ddiv_rn((double)ys[k], b0.sf[k]);
+    }
+    const uint64_t v = (uint64_t)vi;
+    for (int l = 0; l < L; l++) {
+        const BaseConv &bc = md[l];
+        const uint64_t t = lcs[l].q;
+        uint64_t a = 0;
+#pragma unroll 1
+        for (int k = 0; k < nP; k++) a = add_mod(a, mul_shoup(ys[k], bc.fac[k], bc.fac_sh[k], t), t);
+        ext[((size_t)p * L + l) * N + j] = sub_mod(a, mul_shoup(v, bc.smod, bc.smod_sh, t), t);
+    }
+}
+
 template <typename T, int LOGN>  // accumulator type: uint32_t for q < 2^31, uint64_t otherwise; LOGN > 0: compile-time ring size
 __global__ void __launch_bounds__(512, 1)
 k_md_accum(const uint64_t *__restrict__ in, const long long *__restrict__ in_off, int in_nl, const uint64_t *__restrict__ acc,
            const BaseConv *__restrict__ md, const uint32_t *const *__restrict__ perms, const uint32_t *__restrict__ ginv, int level, int nQ,
            int nP, int logN_arg, const LimbConst *__restrict__ lcs, int nout, int nacc, uint64_t *__restrict__ S1o, uint64_t *__restrict__ C0o,
-           uint64_t *__restrict__ Eo, int L, int first, TgtSel sel, int NBUF /* ring depth: 3, or what fits (2^14-coefficient rings: 1) */) {
+           uint64_t *__restrict__ Eo, int L, int first, TgtSel sel, int NBUF /* ring depth: 3, or what fits (2^14-coefficient rings: 1) */,
+           const uint64_t *__restrict__ extP /* nP > 1: Ext(accP) per (entry, comp, limb), k_md_extp */) {
     extern __shared__ __align__(128) uint64_t sst[];
     const int logN = LOGN ? LOGN : logN_arg;
     const int N = 1 << logN, nl = level + 1, nt = nl + nP;
@@ -369,13 +400,14 @@ k_md_accum(const uint64_t *__restrict__ in, const long long *__restrict__ in_off
     }
     // accQ is in discrete-log order (k_ks_inner2): perm_a is a cyclic shift inside each half, read straight from global memory.
     // stage sequence of the ring: per entry  [c0 if comp == 0] [accP if nP == 1]
-    const bool stageP = nP == 1;
+    const bool stageP = nP == 1 || extP != nullptr;
     const int spe = (comp == 0 ? 1 : 0) + (stageP ? 1 : 0);
     const int nstage = nacc * spe;
     const uint32_t bytes = (uint32_t)N * 8;
     auto src_of = [&](int st) -> const uint64_t * {
         const int a = st / spe, w = st % spe, ct = a * nout + o;
         if (w == 0 && comp == 0) return in + in_off[ct] + (size_t)l * N;               // c0: NTT domain, natural order
+        if (extP) return extP + ((size_t)(ct * 2 + comp) * L + l) * N;                 // Ext(accP) mod q_l: coefficient domain, natural order
         return acc + ((size_t)(ct * 2 + comp) * nt + nl) * N;                          // accP: coefficient domain, natural order
     };
     if (tid == 0) {
@@ -601,7 +633,7 @@ static int inner_launch(Ctx *c, const KsBatch &b, BaseConv *ks, const TgtSel &se
 }
 
 template <class A, bool A1>
-static int moddown_launch2(Ctx *c, const KsBatch &b, BaseConv *md, uint64_t *pinv, const TgtSel &sel, cudaStream_t st) {
+static int moddown_launch2(Ctx *c, const KsBatch &b, BaseConv *md, uint64_t *pinv, const TgtSel &sel, const uint64_t *extP, cudaStream_t st) {
     const int logN = c->logN, N = c->N;
     const PassPlan plan = make_pass_plan(logN - kLastR);
     const size_t smem = ntt_smem_elems(N) * sizeof(typename A::T);
@@ -609,7 +641,7 @@ static int moddown_launch2(Ctx *c, const KsBatch &b, BaseConv *md, uint64_t *pin
     auto go = [&](auto kern) -> int {
         SFG_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<g, ntt_threads(N), smem, st>>>(b.in, b.in_off, b.in_nl, b.acc, md, pinv, b.perms, b.level, c->nQ, c->nP, logN, plan, c->tw2, c->lc,
-                                              (unsigned char *)b.out, b.out_off, b.out_layout, b.accumulate ? 1 : 0, sel);
+                                              (unsigned char *)b.out, b.out_off, b.out_layout, b.accumulate ? 1 : 0, sel, extP);
         SFG_LAUNCHED(c, "k_ks_moddown2", st);
         return 0;
     };
@@ -618,9 +650,9 @@ static int moddown_launch2(Ctx *c, const KsBatch &b, BaseConv *md, uint64_t *pin
     return go(k_ks_moddown2<A, A1, 0>);
 }
 template <class A>
-static int moddown_launch(Ctx *c, const KsBatch &b, BaseConv *md, uint64_t *pinv, const TgtSel &sel, cudaStream_t st) {
+static int moddown_launch(Ctx *c, const KsBatch &b, BaseConv *md, uint64_t *pinv, const TgtSel &sel, const uint64_t *extP, cudaStream_t st) {
     if (sel.n == 0) return 0;
-    return c->nP == 1 ? moddown_launch2<A, true>(c, b, md, pinv, sel, st) : moddown_launch2<A, false>(c, b, md, pinv, sel, st);
+    return c->nP == 1 ? moddown_launch2<A, true>(c, b, md, pinv, sel, extP, st) : moddown_launch2<A, false>(c, b, md, pinv, sel, extP, st);
 }
 
 static int inner_all(Ctx *c, const KsBatch &b, BaseConv *ks, cudaStream_t st) {
@@ -673,8 +705,17 @@ static int rotate_chunk(Ctx *c, const KsBatch &b, BaseConv *ks, BaseConv *md, ui
         TgtSel &t = ls[arith_kind(c->mod[l])];
         t.tt[t.n++] = l;
     }
-    if (moddown_launch<ArW>(c, b, md, pinv, ls[kArW], st) || moddown_launch<ArD>(c, b, md, pinv, ls[kArD], st) || moddown_launch<ArN30>(c, b, md, pinv, ls[kArN30], st) ||
-        moddown_launch<ArN31>(c, b, md, pinv, ls[kArN31], st))
+    const uint64_t *extP = nullptr;
+    if (c->nP > 1) {  // the base conversion of the P limbs once per coefficient, not once per Q-limb CTA (k_md_extp)
+        void *pe;
+        const int Lo = b.out_layout.nl;
+        if (ws_get(c, WS_MD, (size_t)b.nct * 2 * Lo * N * 8, &pe)) return -1;
+        k_md_extp<<<dim3((N + 255) / 256, b.nct * 2), 256, 0, st>>>(b.acc, md, nl, nt, c->nP, Lo, N, c->lc, (uint64_t *)pe);
+        SFG_LAUNCHED(c, "k_md_extp", st);
+        extP = (const uint64_t *)pe;
+    }
+    if (moddown_launch<ArW>(c, b, md, pinv, ls[kArW], extP, st) || moddown_launch<ArD>(c, b, md, pinv, ls[kArD], extP, st) ||
+        moddown_launch<ArN30>(c, b, md, pinv, ls[kArN30], extP, st) || moddown_launch<ArN31>(c, b, md, pinv, ls[kArN31], extP, st))
         return -1;
     return 0;
 }
@@ -857,10 +898,11 @@ int launch_rotate_sum(Ctx *c, const KsBatch &b, int nout, const uint32_t *ginv_d
     const int nbuf = (int)std::max<size_t>(1, std::min<size_t>(3, ((size_t)220 << 10) / ((size_t)N * 8)));
     const size_t smem = (size_t)nbuf * N * 8 + 64;
     if (smem > ((size_t)227 << 10)) SFG_FAIL(c, "giant-step sums: a ring of 2^%d coefficients does not fit one CTA's shared memory", c->logN);
+    const uint64_t *extP = nullptr;
     auto accum = [&](auto kern, const TgtSel &ts, const KsBatch &ch, int k0, int nsplit, int thr, int fst) -> int {
         SFG_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<dim3(ts.n * nsplit, 2, nout), thr, smem, st>>>(ch.in, ch.in_off, ch.in_nl, ch.acc, md, ch.perms, ginv_dev + k0, ch.level, c->nQ, c->nP,
-                                                              c->logN, c->lc, nout, ch.nct / nout, S1, C0, E, L, fst, ts, nbuf);
+                                                              c->logN, c->lc, nout, ch.nct / nout, S1, C0, E, L, fst, ts, nbuf, extP);
         SFG_LAUNCHED(c, "k_md_accum", st);
         return 0;
     };
@@ -879,6 +921,13 @@ int launch_rotate_sum(Ctx *c, const KsBatch &b, int nout, const uint32_t *ginv_d
         ch.out_off += k0;
         ch.acc_dlog = true;
         if (rotate_chunk(c, ch, ks, md, pinv, st, false)) return -1;
+        if (c->nP > 1) {
+            void *pe;
+            if (ws_get(c, WS_KSB, (size_t)ch.nct * 2 * L * N * 8, &pe)) return -1;
+            k_md_extp<<<dim3((N + 255) / 256, ch.nct * 2), 256, 0, st>>>(ch.acc, md, nl, nl + c->nP, c->nP, L, N, c->lc, (uint64_t *)pe);
+            SFG_LAUNCHED(c, "k_md_extp", st);
+            extP = (const uint64_t *)pe;
+        }
         const int nsplit = N > 8192 ? N / 8192 : 1;
         const int thr = std::min(512, std::max(32, N / nsplit / 16));
         const int fst = (first && k0 == 0) ? 1 : 0;
