@@ -111,6 +111,7 @@ struct KsBatch {
     // scratch (device): c2 [n_c2][nl][N], acc [nct][2][nl+nP][N]
     uint64_t *c2, *acc;
     uint64_t *dout = nullptr;  // internal: digit-transform output of the shared-decomposition path (kernels_ks.cu)
+    const uint32_t *vq = nullptr;  // internal, nP > 1: quotient estimates of the digit base conversion, [n_c2][beta][N] (k_ks_bcprep)
     bool acc_dlog = false;     // internal: the Q limbs of acc are written in discrete-log order (giant-step sums)
     int acc_cap;            // ciphertexts the acc scratch holds; larger batches are processed in chunks
 };

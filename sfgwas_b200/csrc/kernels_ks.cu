@@ -36,6 +36,34 @@ __device__ __forceinline__ uint64_t base_conv_coeff(const BaseConv &bc, const ui
     return sub_mod(acc, mul_shoup(v, bc.smod, bc.smod_sh, t), t);
 }
 
+// The target-independent half of that conversion, once per (ciphertext, digit, coefficient) instead of once per target modulus (and
+// per half-ring CTA):  y_k = x_k * (S/s_k)^-1 mod s_k  (written over c2)  and  v = floor(sum_k y_k / s_k)  (float64, the same operations
+// in the same order).  The per-target half is  sum_k y_k * (S/s_k mod t) - v * (S mod t)  mod t  (base_conv_target).
+__global__ void k_ks_bcprep(uint64_t *__restrict__ c2, const BaseConv *__restrict__ ks, int nl, int nt, int beta, int N,
+                            const LimbConst *__restrict__ lcs, uint32_t *__restrict__ vq) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y, slot = blockIdx.z;
+    if (j >= N) return;
+    const BaseConv &bc = ks[(size_t)i * nt + nl];  // any target outside the digit carries the source-side constants: the first P modulus
+    uint64_t *x = c2 + (size_t)slot * nl * N + j;
+    double vi = 0.0;
+#pragma unroll 1
+    for (int k = 0; k < bc.ns; k++) {
+        const uint64_t sk = lcs[bc.src_limb[k]].q;
+        const uint64_t y = mul_shoup(x[(size_t)bc.src_limb[k] * N], bc.sinv[k], bc.sinv_sh[k], sk);
+        vi += __ddiv_rn((double)y, bc.sf[k]);
+        x[(size_t)bc.src_limb[k] * N] = y;
+    }
+    vq[((size_t)slot * beta + i) * N + j] = (uint32_t)(uint64_t)vi;
+}
+// (deliberately NOT inlined: a radix-8 pass evaluates 16 conversions per thread, and inlined they are interleaved into ~2 KB of
+// spills per thread; a call keeps one conversion's registers live at a time)
+__device__ __noinline__ uint64_t base_conv_target(const BaseConv *bc, const uint64_t *y, size_t ystride, uint64_t v, uint64_t t) {
+    uint64_t acc = 0;
+#pragma unroll 1
+    for (int k = 0; k < bc->ns; k++) acc = add_mod(acc, mul_shoup(y[(size_t)bc->src_limb[k] * ystride], bc->fac[k], bc->fac_sh[k], t), t);
+    return sub_mod(acc, mul_shoup(v, bc->smod, bc->smod_sh, t), t);
+}
+
 struct TgtSel {  // targets (or limbs) of one arithmetic class
     int n;
     int tt[kMaxLimbs];
@@ -96,7 +124,8 @@ __global__ void __launch_bounds__(512, A::kMinBlocks)
 k_ks_inner2(const uint64_t *__restrict__ in, const long long *__restrict__ in_off, int in_nl, const uint64_t *__restrict__ c2,
             const int *__restrict__ c2_slot, const uint64_t *const *__restrict__ keys, const BaseConv *__restrict__ ks, int level, int nQ,
             int nP, int logN_arg, PassPlan plan_arg, const TwTab *__restrict__ tabs, const LimbConst *__restrict__ lcs,
-            uint64_t *__restrict__ accout, TgtSel sel, uint64_t *__restrict__ dout, const uint32_t *__restrict__ dlog_src) {
+            uint64_t *__restrict__ accout, TgtSel sel, uint64_t *__restrict__ dout, const uint32_t *__restrict__ dlog_src,
+            const uint32_t *__restrict__ vq /* nP > 1: c2 holds y_k and vq the quotient estimates (k_ks_bcprep) */) {
     // DM (dout != nullptr): DIGIT mode.  The transforms NTT_t(Ext(digit_i(c1))) do not depend on the switching key, so rotations of the SAME
     // ciphertext by different amounts (the d-1 baby steps of every A[i][bi]) share them: the kernel then runs once per distinct input
     // (ct = slot, c2_slot == keys == nullptr) and stores the canonical transforms D[slot][i][tt] in TT order instead of multiplying
@@ -192,9 +221,8 @@ k_ks_inner2(const uint64_t *__restrict__ in, const long long *__restrict__ in_of
                 if constexpr (A1) {
                     return A::load_u64(c2ct[(size_t)bc.src_limb[0] * N + g], c);  // DecomposeAndSplit, single modulus
                 } else {
-                    uint64_t xs[kMaxAlpha];
-                    for (int j = 0; j < ns; j++) xs[j] = c2ct[(size_t)bc.src_limb[j] * N + g];
-                    return A::load_u64(base_conv_coeff(bc, xs, lcs, lc.q), c);
+                    const size_t slot = c2_slot ? (size_t)c2_slot[ct] : (size_t)ct;
+                    return A::load_u64(base_conv_target(&bc, c2ct + g, (size_t)N, vq[(slot * beta + i) * N + g], lc.q), c);
                 }
             };
             auto ld0 = [&](int j, int) -> T {
@@ -606,7 +634,7 @@ static int inner_launch2(Ctx *c, const KsBatch &b, BaseConv *ks, const TgtSel &s
     auto go = [&](auto kern) -> int {
         SFG_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<g, ntt_threads(S), smem, st>>>(b.in, b.in_off, b.in_nl, b.c2, b.c2_slot, b.keys, ks, b.level, c->nQ, c->nP, logN, plan, c->tw2, c->lc,
-                                              b.acc, sel, b.dout, b.acc_dlog ? c->dlog_src : nullptr);
+                                              b.acc, sel, b.dout, b.acc_dlog ? c->dlog_src : nullptr, b.vq);
         SFG_LAUNCHED(c, "k_ks_inner2", st);
         return 0;
     };
@@ -835,6 +863,17 @@ static int rotate_big(Ctx *c, const KsBatch &b, BaseConv *ks, BaseConv *md, uint
     return 0;
 }
 
+static int bc_prep(Ctx *c, KsBatch &b, BaseConv *ks, cudaStream_t st) {
+    if (c->nP == 1) return 0;  // single-modulus digits: plain reduction of the representative, nothing to hoist
+    const int N = c->N, nl = b.level + 1, nt = nl + c->nP, beta = (nl + c->nP - 1) / c->nP;
+    void *pv;
+    if (ws_get(c, WS_VQ, (size_t)b.n_c2 * beta * N * 4, &pv)) return -1;
+    k_ks_bcprep<<<dim3((N + 255) / 256, beta, b.n_c2), 256, 0, st>>>(b.c2, ks, nl, nt, beta, N, c->lc, (uint32_t *)pv);
+    SFG_LAUNCHED(c, "k_ks_bcprep", st);
+    b.vq = (const uint32_t *)pv;
+    return 0;
+}
+
 int launch_rotate(Ctx *c, const KsBatch &b, cudaStream_t st) {
     if (b.nct <= 0) return 0;
     if (c->logN < 6) SFG_FAIL(c, "logN >= 6 required");
@@ -849,13 +888,15 @@ int launch_rotate(Ctx *c, const KsBatch &b, cudaStream_t st) {
     sel.n = nl;
     for (int i = 0; i < nl; i++) sel.idx[i] = i;
     if (launch_ntt_gather(c, b.in + (size_t)b.in_nl * N, b.c2_src_off, 0, b.c2, (size_t)nl * N, b.n_c2 * nl, sel, true, false, st)) return -1;
+    KsBatch bq = b;
+    if (bc_prep(c, bq, ks, st)) return -1;
     // many rotations of few ciphertexts (the baby steps: d-1 rotations of every A[i][bi]): transform the digits once per ciphertext
     const uint64_t *D = nullptr;
     if (b.n_c2 * 4 <= b.nct && b.nct <= 65535) {
         const int nt = nl + c->nP, beta = (nl + c->nP - 1) / c->nP;
         void *pd;
         if (ws_get(c, WS_KSB, (size_t)b.n_c2 * beta * nt * N * 8, &pd)) return -1;
-        KsBatch bd = b;
+        KsBatch bd = bq;
         bd.nct = b.n_c2;
         bd.in_off = b.c2_src_off;
         bd.c2_slot = nullptr;
@@ -865,7 +906,7 @@ int launch_rotate(Ctx *c, const KsBatch &b, cudaStream_t st) {
         D = (const uint64_t *)pd;
     }
     for (int k0 = 0; k0 < b.nct; k0 += b.acc_cap) {
-        KsBatch ch = b;
+        KsBatch ch = bq;
         ch.nct = std::min(b.acc_cap, b.nct - k0);
         ch.in_off += k0;
         ch.c2_slot += k0;
@@ -894,6 +935,8 @@ int launch_rotate_sum(Ctx *c, const KsBatch &b, int nout, const uint32_t *ginv_d
     sel.n = nl;
     for (int i = 0; i < nl; i++) sel.idx[i] = i;
     if (launch_ntt_gather(c, b.in + (size_t)b.in_nl * N, b.c2_src_off, 0, b.c2, (size_t)nl * N, b.n_c2 * nl, sel, true, false, st)) return -1;
+    KsBatch bq = b;
+    if (bc_prep(c, bq, ks, st)) return -1;
     // whole source polynomials are staged (the permutation reaches anywhere): as many ring buffers as fit one CTA, at most 3
     const int nbuf = (int)std::max<size_t>(1, std::min<size_t>(3, ((size_t)220 << 10) / ((size_t)N * 8)));
     const size_t smem = (size_t)nbuf * N * 8 + 64;
@@ -912,7 +955,7 @@ int launch_rotate_sum(Ctx *c, const KsBatch &b, int nout, const uint32_t *ginv_d
         t.tt[t.n++] = l;
     }
     for (int k0 = 0; k0 < b.nct; k0 += cap) {
-        KsBatch ch = b;
+        KsBatch ch = bq;
         ch.nct = std::min(cap, b.nct - k0);
         ch.in_off += k0;
         ch.c2_slot += k0;
