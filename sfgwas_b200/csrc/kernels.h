@@ -71,6 +71,7 @@ struct TcGeomP {                 // geometry of the plaintext-diagonal image (fi
 };
 struct TcGeomR {                 // geometry of the rotated-ciphertext image (per call: depends on the number of rows)
     int rows, RP;
+    int cv_rows = 0, cv_row0 = 0;  // this launch's rows are rows [cv_row0, cv_row0 + rows) of a cv image with cv_rows rows per column (0 = rows)
     int npad[kTcLimbs];
     long long rbase[kTcLimbs];
     long long group_bytes;

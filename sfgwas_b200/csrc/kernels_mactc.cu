@@ -121,6 +121,7 @@ struct MacTcParams {
     uint64_t *cv;         // [col - col_lo][rows][L][N] canonical residues
     const LimbConst *lc;
     int L, N, rows, RP, Kg;
+    int cv_rows, cv_row0;       // rows per column of the cv image and the first row this launch writes
     int img_ntiles, img_tile0;  // geometry of the P image: tiles it holds and the global index of its first tile
     int tile_lo, tile_hi;       // global column tiles processed by this launch
     int col_lo, col_hi;         // global columns written
@@ -395,7 +396,7 @@ __global__ void __launch_bounds__(384, 1) k_mac_tc(const __grid_constant__ MacTc
                     asm volatile("bar.sync 1, 256;\n" ::: "memory");
                     if (col >= p.col_lo && col < p.col_hi && !(p.dbg & 1)) {
                         const int n0 = it.n4 * 4 + (i + 1 - p.NGF);
-                        uint64_t *dst = p.cv + ((size_t)(col - p.col_lo) * p.rows + half) * LN + (size_t)l * p.N + n0;
+                        uint64_t *dst = p.cv + ((size_t)(col - p.col_lo) * p.cv_rows + p.cv_row0 + half) * LN + (size_t)l * p.N + n0;
                         for (int row = half; row < p.rows; row += 2, dst += 2 * LN) {
                             const uint64_t *src = outb + (size_t)row * p.NGF * 128 + t;
                             if (p.NGF == 4) {
@@ -686,6 +687,8 @@ int launch_mac_tc(Ctx *c, const TcGeomP &gp, const TcGeomR &gr, const void *Pimg
     p.L = gp.L;
     p.N = c->N;
     p.rows = gr.rows;
+    p.cv_rows = gr.cv_rows ? gr.cv_rows : gr.rows;
+    p.cv_row0 = gr.cv_row0;
     p.RP = gr.RP;
     p.Kg = gp.Kg;
     p.img_ntiles = img_ntiles;

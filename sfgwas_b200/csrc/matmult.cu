@@ -455,14 +455,36 @@ static int build_rot_cache(Ctx *c, const Cache *ca, const uint64_t *d_A, int s, 
 // (2) MAC for the giant steps gact[gi_lo .. gi_hi) -> d_cv [(gi-gi_lo)*m_ct + bj][row][l][N]
 //     gwas/matmult.go:1154-1168 (CPMultAccWithoutMRedV2) + :1203 (ModularReduceV2)
 // ---------------------------------------------------------------------------------------------------------------
+static int run_mac_rows(Ctx *c, const Cache *ca, const void *R, const std::vector<int> &klist, int s, int gi_lo, int gi_hi, uint64_t *d_cv,
+                        int row0, int nrows_part);
+
 static int run_mac(Ctx *c, const Cache *ca, const void *R, const std::vector<int> &klist, int s, int gi_lo, int gi_hi,
                    uint64_t *d_cv) {
+    // When the accumulator region of all 2s rows exceeds half of TMEM the kernel runs single-buffered (MMA stream and epilogue do not
+    // overlap).  Two row halves that each fit 256 columns are faster even though the P image is streamed twice (kp = 15 at logN 14:
+    // 9 x 32 = 288 columns for 30 rows, 9 x 16 = 144 for 16).
+    const int rows = 2 * s;
+    TcGeomR gr, gh;
+    if (tc_geom_r(c, ca->tc, rows, &gr)) return -1;
+    const int h = (rows / 2 + 1) / 2 * 2;  // even: a ciphertext's two polynomials stay together
+    if (gr.tbuf_stride == 0 && rows >= 4 && getenv("SFG_MAC_NOSPLIT") == nullptr && !tc_geom_r(c, ca->tc, h, &gh) && gh.tbuf_stride != 0) {
+        if (run_mac_rows(c, ca, R, klist, s, gi_lo, gi_hi, d_cv, 0, h)) return -1;
+        return run_mac_rows(c, ca, R, klist, s, gi_lo, gi_hi, d_cv, h, rows - h);
+    }
+    return run_mac_rows(c, ca, R, klist, s, gi_lo, gi_hi, d_cv, 0, rows);
+}
+
+// rows [row0, row0 + nrows_part) of the 2s ciphertext polynomials
+static int run_mac_rows(Ctx *c, const Cache *ca, const void *R, const std::vector<int> &klist, int s, int gi_lo, int gi_hi, uint64_t *d_cv,
+                        int row0, int nrows_part) {
     const TcGeomP &tc = ca->tc;
-    const int m_ct = ca->m_ct, rows = 2 * s, Kg = tc.Kg, K = tc.K;
+    const int m_ct = ca->m_ct, rows_all = 2 * s, rows = nrows_part, Kg = tc.Kg, K = tc.K;
     const int col_lo = gi_lo * m_ct, col_hi = gi_hi * m_ct;
     if (klist.empty() || col_hi <= col_lo) return 0;
     TcGeomR gr;
     if (tc_geom_r(c, tc, rows, &gr)) return -1;
+    gr.cv_rows = rows_all;
+    gr.cv_row0 = row0;
     const int tile_lo = col_lo / 128, tile_hi = (col_hi + 127) / 128;
     // source-record table of the R image: [group][Kg][rows]; k outside klist (other block rows / padding) contributes zero
     std::vector<int> kpos((size_t)K, -1);
@@ -473,7 +495,7 @@ static int run_mac(Ctx *c, const Cache *ca, const void *R, const std::vector<int
         for (int kk = 0; kk < Kg; kk++) {
             const int k = grp * Kg + kk;
             if (k >= K || kpos[k] < 0) continue;
-            for (int r = 0; r < rows; r++) tab[((size_t)grp * Kg + kk) * rows + r] = (long long)(((size_t)kpos[k] * rows + r) * RB);
+            for (int r = 0; r < rows; r++) tab[((size_t)grp * Kg + kk) * rows + r] = (long long)(((size_t)kpos[k] * rows_all + row0 + r) * RB);
         }
     void *dtab, *rimg;
     if (ws_get(c, WS_META2, tab.size() * sizeof(long long), &dtab)) return -1;

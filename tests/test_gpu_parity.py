@@ -354,13 +354,14 @@ def test_compute_on_the_fly_cache_identical(small13):
     assert (MatMult4StreamCompute(cps, A, 5, c1) == MatMult4StreamCompute(cps, A, 5, c2)).all()
 
 
-def test_pn14_shape_bit_exact(small14):
+@pytest.mark.parametrize("s", [3, 15])  # 15 (kp = 15): 30 rows x 5-6 byte planes exceed half of TMEM -> the MAC runs as two row halves
+def test_pn14_shape_bit_exact(small14, s):
     from sfgwas_b200 import GenoFileStream, MatMult4StreamCompute, MatMult4StreamPreprocess
 
     o, cps, sk, keys = small14
     rng = np.random.default_rng(14)
     X = rng.integers(0, 3, (300, 520)).astype(np.int8)
-    A = enc_matrix(o, sk, rng.normal(size=(3, 300)), level=7)  # level 7 input is dropped to 5
+    A = enc_matrix(o, sk, rng.normal(size=(s, 300)), level=7)  # level 7 input is dropped to 5
     gfs = GenoFileStream.from_matrix(cps, X)
     cache = MatMult4StreamPreprocess(cps, gfs, 5)
     out = MatMult4StreamCompute(cps, A, 5, cache)
