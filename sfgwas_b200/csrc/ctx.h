@@ -103,7 +103,7 @@ int launch_check(Ctx *c, const char *what, cudaStream_t st);
     } while (0)
 
 // workspace slots
-enum WsSlot { WS_C2 = 0, WS_ACC, WS_META, WS_R, WS_CV, WS_POFF, WS_TMPP, WS_A, WS_OUT, WS_META2, WS_RIMG, WS_PIMG, WS_MD, WS_KSB, WS_VQ, WS_COUNT };
+enum WsSlot { WS_C2 = 0, WS_ACC, WS_META, WS_R, WS_CV, WS_POFF, WS_TMPP, WS_A, WS_OUT, WS_META2, WS_RIMG, WS_PIMG, WS_MD, WS_KSB, WS_VQ, WS_EXTD, WS_COUNT };
 int ws_get(Ctx *c, int slot, size_t bytes, void **out);  // returns a buffer of at least `bytes` (contents undefined)
 void ws_release(Ctx *c);
 

@@ -113,6 +113,7 @@ struct KsBatch {
     uint64_t *c2, *acc;
     uint64_t *dout = nullptr;  // internal: digit-transform output of the shared-decomposition path (kernels_ks.cu)
     const uint32_t *vq = nullptr;  // internal, nP > 1: quotient estimates of the digit base conversion, [n_c2][beta][N] (k_ks_bcprep)
+    const uint64_t *extd = nullptr;  // internal, nP > 1: every digit extended to every target, [n_c2][beta][nt][N] (k_ks_extd)
     bool acc_dlog = false;     // internal: the Q limbs of acc are written in discrete-log order (giant-step sums)
     int acc_cap;            // ciphertexts the acc scratch holds; larger batches are processed in chunks
 };

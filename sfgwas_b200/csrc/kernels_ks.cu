@@ -64,6 +64,25 @@ __device__ __noinline__ uint64_t base_conv_target(const BaseConv *bc, const uint
     return sub_mod(acc, mul_shoup(v, bc->smod, bc->smod_sh, t), t);
 }
 
+// nP > 1: all digits of a ciphertext extended to all target moduli in one coalesced pass (coefficient domain, canonical), so that
+// k_ks_inner2 -- where every (target, half-ring) CTA used to redo the conversion for both of its stage-0 inputs -- only loads them.
+__global__ void k_ks_extd(const uint64_t *__restrict__ c2, const uint32_t *__restrict__ vq, const BaseConv *__restrict__ ks, int nl, int nt,
+                          int nQ, int beta, int N, const LimbConst *__restrict__ lcs, uint64_t *__restrict__ extd) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y, slot = blockIdx.z;
+    if (j >= N) return;
+    const uint64_t *y = c2 + (size_t)slot * nl * N + j;
+    const uint64_t v = vq[((size_t)slot * beta + i) * N + j];
+    for (int tt = 0; tt < nt; tt++) {
+        const BaseConv &bc = ks[(size_t)i * nt + tt];
+        if (bc.ns == 0) continue;  // target inside the digit: the NTT-domain input limb is reused
+        const uint64_t t = lcs[tt < nl ? tt : nQ + (tt - nl)].q;
+        uint64_t a = 0;
+#pragma unroll 1
+        for (int k = 0; k < bc.ns; k++) a = add_mod(a, mul_shoup(y[(size_t)bc.src_limb[k] * N], bc.fac[k], bc.fac_sh[k], t), t);
+        extd[(((size_t)slot * beta + i) * nt + tt) * N + j] = sub_mod(a, mul_shoup(v, bc.smod, bc.smod_sh, t), t);
+    }
+}
+
 struct TgtSel {  // targets (or limbs) of one arithmetic class
     int n;
     int tt[kMaxLimbs];
@@ -125,7 +144,8 @@ k_ks_inner2(const uint64_t *__restrict__ in, const long long *__restrict__ in_of
             const int *__restrict__ c2_slot, const uint64_t *const *__restrict__ keys, const BaseConv *__restrict__ ks, int level, int nQ,
             int nP, int logN_arg, PassPlan plan_arg, const TwTab *__restrict__ tabs, const LimbConst *__restrict__ lcs,
             uint64_t *__restrict__ accout, TgtSel sel, uint64_t *__restrict__ dout, const uint32_t *__restrict__ dlog_src,
-            const uint32_t *__restrict__ vq /* nP > 1: c2 holds y_k and vq the quotient estimates (k_ks_bcprep) */) {
+            const uint32_t *__restrict__ vq /* nP > 1: c2 holds y_k and vq the quotient estimates (k_ks_bcprep) */,
+            const uint64_t *__restrict__ extd /* nP > 1: the digits already extended to every target (k_ks_extd), or null */) {
     // DM (dout != nullptr): DIGIT mode.  The transforms NTT_t(Ext(digit_i(c1))) do not depend on the switching key, so rotations of the SAME
     // ciphertext by different amounts (the d-1 baby steps of every A[i][bi]) share them: the kernel then runs once per distinct input
     // (ct = slot, c2_slot == keys == nullptr) and stores the canonical transforms D[slot][i][tt] in TT order instead of multiplying
@@ -222,6 +242,7 @@ k_ks_inner2(const uint64_t *__restrict__ in, const long long *__restrict__ in_of
                     return A::load_u64(c2ct[(size_t)bc.src_limb[0] * N + g], c);  // DecomposeAndSplit, single modulus
                 } else {
                     const size_t slot = c2_slot ? (size_t)c2_slot[ct] : (size_t)ct;
+                    if (extd) return A::load_u64(extd[((slot * beta + i) * nt + tt) * N + g], c);
                     return A::load_u64(base_conv_target(&bc, c2ct + g, (size_t)N, vq[(slot * beta + i) * N + g], lc.q), c);
                 }
             };
@@ -634,7 +655,7 @@ static int inner_launch2(Ctx *c, const KsBatch &b, BaseConv *ks, const TgtSel &s
     auto go = [&](auto kern) -> int {
         SFG_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<g, ntt_threads(S), smem, st>>>(b.in, b.in_off, b.in_nl, b.c2, b.c2_slot, b.keys, ks, b.level, c->nQ, c->nP, logN, plan, c->tw2, c->lc,
-                                              b.acc, sel, b.dout, b.acc_dlog ? c->dlog_src : nullptr, b.vq);
+                                              b.acc, sel, b.dout, b.acc_dlog ? c->dlog_src : nullptr, b.vq, b.extd);
         SFG_LAUNCHED(c, "k_ks_inner2", st);
         return 0;
     };
@@ -871,6 +892,15 @@ static int bc_prep(Ctx *c, KsBatch &b, BaseConv *ks, cudaStream_t st) {
     k_ks_bcprep<<<dim3((N + 255) / 256, beta, b.n_c2), 256, 0, st>>>(b.c2, ks, nl, nt, beta, N, c->lc, (uint32_t *)pv);
     SFG_LAUNCHED(c, "k_ks_bcprep", st);
     b.vq = (const uint32_t *)pv;
+    // all digits x all targets, when the buffer is affordable (<= 16 GiB); otherwise k_ks_inner2 converts on the fly
+    const size_t eb = (size_t)b.n_c2 * beta * nt * N * 8;
+    if (eb <= ((size_t)16 << 30) && getenv("SFG_KS_NOEXTD") == nullptr) {
+        void *pe;
+        if (ws_get(c, WS_EXTD, eb, &pe)) return -1;
+        k_ks_extd<<<dim3((N + 255) / 256, beta, b.n_c2), 256, 0, st>>>(b.c2, b.vq, ks, nl, nt, c->nQ, beta, N, c->lc, (uint64_t *)pe);
+        SFG_LAUNCHED(c, "k_ks_extd", st);
+        b.extd = (const uint64_t *)pe;
+    }
     return 0;
 }
 
