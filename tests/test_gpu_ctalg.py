@@ -182,11 +182,11 @@ def test_qx_lazy_norm_stream(env):
             QXLazyNormStream(cps, _Mpc(_Net(o, sk, Ciphertext)), [[Ciphertext(c, o.scale) for c in q] for q in Q], cache,
                              [Ciphertext(c, o.scale) for c in XMean], [Ciphertext(c, o.scale) for c in XStdInv], nind)
         return
-    dc = o.preprocess(X, 5, nproc=4)
+    dc = o.preprocess(X, 5, nproc=1)
 
     def compute(QS):  # the oracle's MatMult4StreamCompute on (value, scale) pairs
         A = np.ascontiguousarray(np.stack([np.stack([v[:, :6] for v, _ in row]) for row in QS]))
-        out = o.compute(A, dc, keys, 5, nproc=4)
+        out = o.compute(A, dc, keys, 5, nproc=1)
         sc = QS[0][0][1] * o.scale
         return [[(out[i, j], sc) for j in range(out.shape[1])] for i in range(out.shape[0])]
 
@@ -223,11 +223,11 @@ def test_qxt_lazy_norm_stream(env):
     Q = [_enc_vec(o, sk, Qp[i], top, 400 + 10 * i) for i in range(kp)]
     XMean, XStdInv = _enc_vec(o, sk, mean, top, 500), _enc_vec(o, sk, stdinv, top, 600)
     cache = MatMult4StreamPreprocess(cps, GenoFileStream.from_matrix(cps, XT), 5)
-    dc = o.preprocess(XT, 5, nproc=4)
+    dc = o.preprocess(XT, 5, nproc=1)
 
     def compute(QQ):
         A = np.ascontiguousarray(np.stack([np.stack([v[:, :6] for v, _ in row]) for row in QQ]))
-        out = o.compute(A, dc, keys, 5, nproc=4)
+        out = o.compute(A, dc, keys, 5, nproc=1)
         sc = QQ[0][0][1] * o.scale
         return [[(out[i, j], sc) for j in range(out.shape[1])] for i in range(out.shape[0])]
 
