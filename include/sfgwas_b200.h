@@ -82,6 +82,14 @@ int sfg_matmult4_stream_preprocess(sfg_ctx *ctx, const sfg_geno *g, int max_leve
 /* block-row sharding: the cache of a rank holds the diagonals of its own block rows [bi_lo, bi_hi) only (HBM and
  * preprocessing time proportional to the rank's share); it serves sfg_matmult4_partial over that range and sfg_matmult4_finish */
 int sfg_matmult4_stream_preprocess_rows(sfg_ctx *ctx, const sfg_geno *g, int max_level, int bi_lo, int bi_hi, sfg_cache **out);
+/* giant-step sharding (strong scaling of ONE product over the GPUs of a box; SURVEY 8e, north_star "modular-add allreduce"): the
+ * cache of share `part` of `nparts` holds the diagonals P[bi][g*d+b][bj] of its own contiguous share of the active giant steps g only
+ * (HBM and preprocessing time / nparts).  sfg_matmult4_stream_compute* on it returns the partial sum over those giant steps,
+ * S_part[i][bj] = sum_{g in share} RotL_{g d}(reduce(acc[i][g])[bj]) (gwas/matmult.go:1203-1227 is a mod-q sum over g, so the shares
+ * add up bit-exactly): combine with an integer SUM all-reduce of the canonical residues + sfg_ct_mod_reduce. */
+int sfg_matmult4_stream_preprocess_giants(sfg_ctx *ctx, const sfg_geno *g, int max_level, int part, int nparts, sfg_cache **out);
+/* x mod q_l on npoly DEVICE polynomials [nl][N] (sums of up to 2^8 canonical residues after an integer all-reduce) */
+int sfg_ct_mod_reduce(sfg_ctx *ctx, uint64_t *d_polys, size_t npoly, int nl);
 void sfg_cache_destroy(sfg_cache *cache);
 /* number of non-nil diagonal polynomials, bytes resident, and whether they are materialised */
 int sfg_cache_info(const sfg_cache *cache, size_t *num_polys, size_t *bytes, int *materialised, int *m_ct, int *num_block_rows);
@@ -121,6 +129,10 @@ int sfg_cv_mod_reduce(sfg_ctx *ctx, const sfg_cache *cache, int s, int max_level
 /* giant-step rotations and sum for giant indices [g_lo, g_hi): out [s][m_ct][2][max_level][N] on the HOST (partial over g) */
 int sfg_matmult4_finish(sfg_ctx *ctx, const sfg_cache *cache, int s, int max_level, const uint64_t *d_cv, int g_lo, int g_hi,
                         uint64_t *out);
+/* device-resident variant for a reduce-scattered image: d_cv_share holds the giants [g_lo, g_hi) ONLY (what this rank received), d_out
+ * [s][m_ct][2][max_level][N] is a DEVICE buffer (partial over g; combine with an integer all-reduce + sfg_ct_mod_reduce) */
+int sfg_matmult4_finish_dev(sfg_ctx *ctx, const sfg_cache *cache, int s, int max_level, const uint64_t *d_cv_share, int g_lo, int g_hi,
+                            uint64_t *d_out);
 /* out = (a + b) mod q limb-wise on host buffers of ncts ciphertexts [2][nl][N] (combining per-rank partial sums) */
 int sfg_ct_add(sfg_ctx *ctx, const uint64_t *a, const uint64_t *b, int ncts, int nl, uint64_t *out);
 

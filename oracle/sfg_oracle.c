@@ -880,7 +880,10 @@ void orc_matmult4_stream_compute(const orc_ctx *c, const uint64_t *A, int s, int
     int nlimbAcc = maxLevel; /* the limb-COUNT quirk, matmult.go:1125 -> :231 (App. A.4) */
     int nlOut = nlimbAcc;    /* output level = nlimbAcc - 1 (matmult.go:350) */
     if (nproc < 1) nproc = 1;
-    if (levelA < maxLevel) { fprintf(stderr, "DropLevel: requested level %d when input is %d\n", maxLevel, levelA); abort(); }
+    /* matmult.go:1053-1056: A is dropped only when Level() > maxLevel; an input at maxLevel-1 still has the nlimbAcc limbs the MAC
+     * reads (:393) and is rotated at its own level; fewer limbs index past Coeffs[] in the reference (panic) */
+    if (levelA < maxLevel - 1) { fprintf(stderr, "input level %d has fewer than %d limbs (index out of range)\n", levelA, maxLevel); abort(); }
+    int lvRot = levelA < maxLevel ? levelA : maxLevel;
     double tr = 0, tm = 0, tp = 0;
 
     acc_ct **acc = (acc_ct **)calloc((size_t)s * d, sizeof(acc_ct *));
@@ -892,7 +895,7 @@ void orc_matmult4_stream_compute(const orc_ctx *c, const uint64_t *A, int s, int
         double t0 = now_s();
         rot_job *rj = (rot_job *)malloc(sizeof(rot_job) * nproc);
         for (int t = 0; t < nproc; t++)
-            rj[t] = (rot_job){ c, nproc, t, s, d, levelA, A, numBlockRows, bi, levelA + 1, dc->babyTable + (size_t)bi * d, swk, rot, maxLevel };
+            rj[t] = (rot_job){ c, nproc, t, s, d, levelA, A, numBlockRows, bi, levelA + 1, dc->babyTable + (size_t)bi * d, swk, rot, lvRot };
         run_threads(rot_worker, rj, sizeof(rot_job), nproc);
         free(rj);
         double t1 = now_s(); tr += t1 - t0;
@@ -901,7 +904,7 @@ void orc_matmult4_stream_compute(const orc_ctx *c, const uint64_t *A, int s, int
                 for (int i = 0; i < s; i++)
                     if (!acc[i * d + g]) acc[i * d + g] = new_acc(m_ct, nlimbAcc, N);
         mac_job *mj = (mac_job *)malloc(sizeof(mac_job) * nproc);
-        for (int t = 0; t < nproc; t++) mj[t] = (mac_job){ c, dc, bi, nproc, t, s, nlimbAcc, levelA, rot, acc, mux, maxLevel + 1 };
+        for (int t = 0; t < nproc; t++) mj[t] = (mac_job){ c, dc, bi, nproc, t, s, nlimbAcc, levelA, rot, acc, mux, lvRot + 1 };
         run_threads(mac_worker, mj, sizeof(mac_job), nproc);
         free(mj);
         tm += now_s() - t1;

@@ -24,7 +24,8 @@ SYMBOLS = [
     "sfg_ctx_set_relin_key_ptrs", "sfg_ct_mul_relin", "sfg_ct_mul_plain", "sfg_ct_rescale", "sfg_ct_sub", "sfg_ct_add2",
     "sfg_inner_sum_all", "sfg_encode_slots_i8", "sfg_cache_write_files", "sfg_cache_load_files",
     "sfg_geno_count_sketch", "sfg_ntt_dev", "sfg_rotate_right_dev",
-    "sfg_matmult4_stream_preprocess_rows",
+    "sfg_matmult4_stream_preprocess_rows", "sfg_matmult4_stream_preprocess_giants", "sfg_ct_mod_reduce",
+    "sfg_matmult4_finish_dev",
 ]
 
 _lib = None
@@ -98,6 +99,9 @@ def load():
     L.sfg_ntt_dev.argtypes = [vp, vp, i32, C.POINTER(i32), i32, i32]
     L.sfg_rotate_right_dev.argtypes = [vp, i32, vp, i32, i32, vp]
     L.sfg_matmult4_stream_preprocess_rows.argtypes = [vp, vp, i32, i32, i32, C.POINTER(vp)]
+    L.sfg_matmult4_stream_preprocess_giants.argtypes = [vp, vp, i32, i32, i32, C.POINTER(vp)]
+    L.sfg_ct_mod_reduce.argtypes = [vp, vp, sz, i32]
+    L.sfg_matmult4_finish_dev.argtypes = [vp, vp, i32, i32, vp, i32, i32, vp]
     L.sfg_ctx_sync.argtypes = [vp]
     L.sfg_ctx_last_timings.argtypes = [vp, C.POINTER(C.c_float)]
     L.sfg_ctx_stream.restype = vp

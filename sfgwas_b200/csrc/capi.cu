@@ -71,6 +71,7 @@ void sfg_ctx_destroy(sfg_ctx *h) {
     cudaFree(c->tw);
     cudaFree(c->tw2);
     ws_release(c);
+    pinned_release(c);
     for (void *p : c->tw2_bufs) cudaFree(p);
     cudaFree(c->roots);
     cudaFree(c->ddcos);
@@ -122,9 +123,9 @@ static int set_key_dev(Ctx *c, int rot_left, uint64_t *draw) {
     // convert to the device format of the key-switch kernels (TT order, Shoup pairs for narrow moduli)
     const size_t n = (size_t)c->beta * 2 * c->nQP * c->N;
     uint64_t *dkey = nullptr;
-    if (cudaMalloc(&dkey, n * 8) != cudaSuccess) {
+    if (dev_alloc(c, (void **)&dkey, n * 8, "Galois key")) {
         cudaFree(draw);
-        SFG_FAIL(c, "cudaMalloc of a Galois key failed");
+        return -1;
     }
     if (launch_key_convert(c, draw, dkey, c->stream)) return -1;
     SFG_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -133,8 +134,7 @@ static int set_key_dev(Ctx *c, int rot_left, uint64_t *draw) {
     std::vector<uint32_t> idx(c->N);
     h_permute_ntt_index(c->logN, galEl, idx.data());
     uint32_t *dperm = nullptr;
-    SFG_CUDA(c, cudaMalloc(&dperm, sizeof(uint32_t) * c->N));
-    SFG_CUDA(c, cudaMemcpy(dperm, idx.data(), sizeof(uint32_t) * c->N, cudaMemcpyDefault));
+    if (dev_alloc(c, (void **)&dperm, sizeof(uint32_t) * c->N, "permutation table") || upload(c, dperm, idx.data(), sizeof(uint32_t) * c->N)) return -1;
     std::lock_guard<std::mutex> g(c->mu);
     auto it = c->keys.find(galEl);
     if (it != c->keys.end()) {
@@ -150,8 +150,11 @@ int sfg_ctx_set_rotation_key(sfg_ctx *h, int rot_left, const uint64_t *key) {
     SFG_CUDA(c, cudaSetDevice(c->device));
     const size_t n = (size_t)c->beta * 2 * c->nQP * c->N;
     uint64_t *d = nullptr;
-    SFG_CUDA(c, cudaMalloc(&d, n * 8));
-    SFG_CUDA(c, cudaMemcpy(d, key, n * 8, cudaMemcpyDefault));
+    if (dev_alloc(c, (void **)&d, n * 8, "Galois key staging")) return -1;
+    if (upload(c, d, key, n * 8)) {  // ordered on the context stream: k_key_convert runs there (see ctx.h: upload)
+        cudaFree(d);
+        return -1;
+    }
     return set_key_dev(c, rot_left, d);
 }
 int sfg_ctx_set_rotation_key_ptrs(sfg_ctx *h, int rot_left, const uint64_t *const *limbs) {
@@ -159,8 +162,12 @@ int sfg_ctx_set_rotation_key_ptrs(sfg_ctx *h, int rot_left, const uint64_t *cons
     SFG_CUDA(c, cudaSetDevice(c->device));
     const size_t np = (size_t)c->beta * 2 * c->nQP;
     uint64_t *d = nullptr;
-    SFG_CUDA(c, cudaMalloc(&d, np * c->N * 8));
-    for (size_t p = 0; p < np; p++) SFG_CUDA(c, cudaMemcpy(d + p * c->N, limbs[p], (size_t)c->N * 8, cudaMemcpyDefault));
+    if (dev_alloc(c, (void **)&d, np * c->N * 8, "Galois key staging")) return -1;
+    // one Go slice per limb (cgo): gathered through the pinned bounce buffer, ordered on the context stream
+    if (gather_limbs_to_device(c, limbs, np, d)) {
+        cudaFree(d);
+        return -1;
+    }
     return set_key_dev(c, rot_left, d);
 }
 int sfg_ctx_has_rotation_key(const sfg_ctx *h, int rot_left) {
@@ -274,6 +281,13 @@ int sfg_matmult4_stream_preprocess_rows(sfg_ctx *h, const sfg_geno *g, int max_l
     *out = new sfg_cache{ca};
     return 0;
 }
+int sfg_matmult4_stream_preprocess_giants(sfg_ctx *h, const sfg_geno *g, int max_level, int part, int nparts, sfg_cache **out) {
+    *out = nullptr;
+    Cache *ca = nullptr;
+    if (cache_build(&h->c, g->g, max_level, &ca, 0, -1, part, nparts)) return -1;
+    *out = new sfg_cache{ca};
+    return 0;
+}
 void sfg_cache_destroy(sfg_cache *cache) {
     if (!cache) return;
     cache_destroy(cache->ca);
@@ -334,13 +348,12 @@ int sfg_matmult4_stream_compute_ptrs(sfg_ctx *h, const uint64_t *const *A_limbs,
     SFG_CUDA(c, cudaSetDevice(c->device));
     const size_t N = c->N;
     const size_t na = (size_t)s * nbr * 2 * (level_a + 1), no = (size_t)s * cache->ca->m_ct * 2 * max_level;
-    Buf dA, dO;
-    if (dA.alloc(c, na * N * 8) || dO.alloc(c, no * N * 8)) return -1;
-    for (size_t p = 0; p < na; p++) SFG_CUDA(c, cudaMemcpyAsync(dA.as<uint64_t>() + p * N, A_limbs[p], N * 8, cudaMemcpyDefault, c->stream));
-    if (mm_compute_dev(c, dA.as<uint64_t>(), s, nbr, level_a, max_level, cache->ca, dO.as<uint64_t>())) return -1;
-    for (size_t p = 0; p < no; p++) SFG_CUDA(c, cudaMemcpyAsync(out_limbs[p], dO.as<uint64_t>() + p * N, N * 8, cudaMemcpyDefault, c->stream));
-    SFG_CUDA(c, cudaStreamSynchronize(c->stream));
-    return 0;
+    void *dA, *dO;  // grow-only workspace, like the flat entry point
+    if (ws_get(c, WS_A, na * N * 8, &dA) || ws_get(c, WS_OUT, no * N * 8, &dO)) return -1;
+    // one pageable Go slice per limb: gathered into pinned staging by a few host threads, ONE transfer each way; the result rows are
+    // scattered back to the limb pointers while the giant-step sums of the following rows run (matmult.cu: HostSink)
+    if (gather_limbs_to_device(c, A_limbs, na, (uint64_t *)dA)) return -1;
+    return mm_compute_dev(c, (const uint64_t *)dA, s, nbr, level_a, max_level, cache->ca, (uint64_t *)dO, nullptr, out_limbs);
 }
 
 int sfg_matmult4_stream(sfg_ctx *h, const uint64_t *A, int s, int level_a, const sfg_geno *g, int max_level, int compute_squared_sum,
@@ -414,6 +427,14 @@ int sfg_cv_mod_reduce(sfg_ctx *h, const sfg_cache *cache, int s, int max_level, 
     SFG_CUDA(c, cudaStreamSynchronize(c->stream));
     return 0;
 }
+int sfg_ct_mod_reduce(sfg_ctx *h, uint64_t *d_polys, size_t npoly, int nl) {
+    Ctx *c = &h->c;
+    if (nl < 1 || nl > c->nQ) SFG_FAIL(c, "ct_mod_reduce: bad limb count %d", nl);
+    SFG_CUDA(c, cudaSetDevice(c->device));
+    if (launch_mod_reduce(c, d_polys, npoly * (size_t)nl, nl, c->stream)) return -1;
+    SFG_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
 int sfg_matmult4_finish(sfg_ctx *h, const sfg_cache *cache, int s, int max_level, const uint64_t *d_cv, int g_lo, int g_hi, uint64_t *out) {
     Ctx *c = &h->c;
     SFG_CUDA(c, cudaSetDevice(c->device));
@@ -423,6 +444,14 @@ int sfg_matmult4_finish(sfg_ctx *h, const sfg_cache *cache, int s, int max_level
     if (mm_finish_dev(c, cache->ca, s, max_level, d_cv, g_lo, g_hi, dO.as<uint64_t>())) return -1;
     SFG_CUDA(c, cudaMemcpy(out, dO.p, obytes, cudaMemcpyDefault));
     return 0;
+}
+int sfg_matmult4_finish_dev(sfg_ctx *h, const sfg_cache *cache, int s, int max_level, const uint64_t *d_cv_share, int g_lo, int g_hi,
+                            uint64_t *d_out) {
+    Ctx *c = &h->c;
+    const Cache *ca = cache->ca;
+    // mm_finish_dev addresses giant gi at d_cv + gi * per_g: rebase the share so that its first giant lands at g_lo
+    const size_t per_g = (size_t)ca->m_ct * 2 * s * ca->L * c->N;
+    return mm_finish_dev(c, cache->ca, s, max_level, d_cv_share - (size_t)g_lo * per_g, g_lo, g_hi, d_out);
 }
 int sfg_ct_add(sfg_ctx *h, const uint64_t *a, const uint64_t *b, int ncts, int nl, uint64_t *out) {
     Ctx *c = &h->c;

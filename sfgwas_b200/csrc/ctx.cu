@@ -20,6 +20,32 @@ int launch_check(Ctx *c, const char *what, cudaStream_t st) {
     return 0;
 }
 
+bool poison_enabled() {
+    static const bool on = [] { const char *e = getenv("SFG_POISON"); return e && *e && *e != '0'; }();
+    return on;
+}
+void poison_fill(Ctx *c, void *p, size_t bytes) {
+    if (poison_enabled() && p && bytes) cudaMemsetAsync(p, 0xA5, bytes, c->stream);
+}
+int upload(Ctx *c, void *dst, const void *src, size_t bytes) {
+    if (bytes == 0) return 0;
+    SFG_CUDA(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, c->stream));
+    SFG_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+int dev_alloc(Ctx *c, void **p, size_t bytes, const char *what) {
+    *p = nullptr;
+    if (bytes == 0) bytes = 16;
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        *p = nullptr;
+        SFG_FAIL(c, "cudaMalloc of %zu bytes (%s) failed: %s", bytes, what, cudaGetErrorString(e));
+    }
+    poison_fill(c, *p, bytes);
+    return 0;
+}
+
 int ws_get(Ctx *c, int slot, size_t bytes, void **out) {
     Ctx::WsBuf &b = c->ws[slot];
     if (bytes == 0) bytes = 16;
@@ -39,6 +65,7 @@ int ws_get(Ctx *c, int slot, size_t bytes, void **out) {
         b.bytes = bytes;
     }
     *out = b.p;
+    poison_fill(c, b.p, bytes);  // contents are undefined by contract: under SFG_POISON=1 every hand-out is re-poisoned (stream-ordered)
     return 0;
 }
 void ws_release(Ctx *c) {
@@ -76,10 +103,8 @@ int ctx_build_tables(Ctx *c, const uint64_t *psi_opt) {
             pi = h_mulmod(pi, psiInv, q);
         }
     }
-    SFG_CUDA(c, cudaMalloc(&c->lc, sizeof(LimbConst) * nQP));
-    SFG_CUDA(c, cudaMemcpy(c->lc, c->lc_h.data(), sizeof(LimbConst) * nQP, cudaMemcpyHostToDevice));
-    SFG_CUDA(c, cudaMalloc(&c->tw, sizeof(uint64_t) * tw.size()));
-    SFG_CUDA(c, cudaMemcpy(c->tw, tw.data(), sizeof(uint64_t) * tw.size(), cudaMemcpyHostToDevice));
+    if (dev_alloc(c, (void **)&c->lc, sizeof(LimbConst) * nQP, "table") || upload(c, c->lc, c->lc_h.data(), sizeof(LimbConst) * nQP)) return -1;
+    if (dev_alloc(c, (void **)&c->tw, sizeof(uint64_t) * tw.size(), "table") || upload(c, c->tw, tw.data(), sizeof(uint64_t) * tw.size())) return -1;
     // per-class tables of the register-tiled transforms (ntt2.cuh): [N] in Lattigo's order + the last-pass table in TT order
     if (logN <= 14) {
         std::vector<TwTab> tabs(nQP);
@@ -107,13 +132,11 @@ int ctx_build_tables(Ctx *c, const uint64_t *psi_opt) {
                         put((size_t)2 * N + NL * P + (size_t)((1 << r) - 1 + g) * P + p, wi[idx]);
                     }
             unsigned char *d = nullptr;
-            SFG_CUDA(c, cudaMalloc(&d, h.size()));
-            SFG_CUDA(c, cudaMemcpy(d, h.data(), h.size(), cudaMemcpyHostToDevice));
+            if (dev_alloc(c, (void **)&d, h.size(), "table") || upload(c, d, h.data(), h.size())) return -1;
             c->tw2_bufs.push_back(d);
             tabs[i] = TwTab{d, d + (size_t)N * es, d + (size_t)(N + NL * P) * es, d + (size_t)(2 * N + NL * P) * es};
         }
-        SFG_CUDA(c, cudaMalloc(&c->tw2, sizeof(TwTab) * nQP));
-        SFG_CUDA(c, cudaMemcpy(c->tw2, tabs.data(), sizeof(TwTab) * nQP, cudaMemcpyHostToDevice));
+        if (dev_alloc(c, (void **)&c->tw2, sizeof(TwTab) * nQP, "table") || upload(c, c->tw2, tabs.data(), sizeof(TwTab) * nQP)) return -1;
     }
 
     // encoder tables (Lattigo ckks encoder: m = 2N, rotGroup[j] = 5^j mod m, roots[k] = exp(2 pi i k / m); App. B.6)
@@ -126,12 +149,9 @@ int ctx_build_tables(Ctx *c, const uint64_t *psi_opt) {
         rot5[j] = (int)five;
         five = five * 5 % (uint64_t)M;
     }
-    SFG_CUDA(c, cudaMalloc(&c->roots, sizeof(double) * roots.size()));
-    SFG_CUDA(c, cudaMemcpy(c->roots, roots.data(), sizeof(double) * roots.size(), cudaMemcpyHostToDevice));
-    SFG_CUDA(c, cudaMalloc(&c->ddcos, sizeof(double) * dd.size()));
-    SFG_CUDA(c, cudaMemcpy(c->ddcos, dd.data(), sizeof(double) * dd.size(), cudaMemcpyHostToDevice));
-    SFG_CUDA(c, cudaMalloc(&c->rot5, sizeof(int) * rot5.size()));
-    SFG_CUDA(c, cudaMemcpy(c->rot5, rot5.data(), sizeof(int) * rot5.size(), cudaMemcpyHostToDevice));
+    if (dev_alloc(c, (void **)&c->roots, sizeof(double) * roots.size(), "table") || upload(c, c->roots, roots.data(), sizeof(double) * roots.size())) return -1;
+    if (dev_alloc(c, (void **)&c->ddcos, sizeof(double) * dd.size(), "table") || upload(c, c->ddcos, dd.data(), sizeof(double) * dd.size())) return -1;
+    if (dev_alloc(c, (void **)&c->rot5, sizeof(int) * rot5.size(), "table") || upload(c, c->rot5, rot5.data(), sizeof(int) * rot5.size())) return -1;
     {
         const uint64_t twoN = 2 * (uint64_t)N, n2 = (uint64_t)N / 2;
         std::vector<uint32_t> of_exp(twoN, 0), pos(N), src(N);
@@ -145,13 +165,12 @@ int ctx_build_tables(Ctx *c, const uint64_t *psi_opt) {
             pos[i] = of_exp[2 * h_bitrev((uint64_t)i, c->logN) + 1];
             src[pos[i]] = (uint32_t)i;
         }
-        SFG_CUDA(c, cudaMalloc(&c->dlog_pos, sizeof(uint32_t) * N));
-        SFG_CUDA(c, cudaMemcpy(c->dlog_pos, pos.data(), sizeof(uint32_t) * N, cudaMemcpyHostToDevice));
-        SFG_CUDA(c, cudaMalloc(&c->dlog_src, sizeof(uint32_t) * N));
-        SFG_CUDA(c, cudaMemcpy(c->dlog_src, src.data(), sizeof(uint32_t) * N, cudaMemcpyHostToDevice));
+        if (dev_alloc(c, (void **)&c->dlog_pos, sizeof(uint32_t) * N, "table") || upload(c, c->dlog_pos, pos.data(), sizeof(uint32_t) * N)) return -1;
+        if (dev_alloc(c, (void **)&c->dlog_src, sizeof(uint32_t) * N, "table") || upload(c, c->dlog_src, src.data(), sizeof(uint32_t) * N)) return -1;
     }
-    SFG_CUDA(c, cudaMalloc(&c->enc_stats, sizeof(unsigned long long) * 2));
-    SFG_CUDA(c, cudaMemset(c->enc_stats, 0, sizeof(unsigned long long) * 2));
+    if (dev_alloc(c, (void **)&c->enc_stats, sizeof(unsigned long long) * 2, "encoder statistics")) return -1;
+    SFG_CUDA(c, cudaMemsetAsync(c->enc_stats, 0, sizeof(unsigned long long) * 2, c->stream));
+    SFG_CUDA(c, cudaStreamSynchronize(c->stream));
     // FP64 special-FFT error model for slot values |v| <= 4: scale * eps * log2(n) * 4 / sqrt(n); the window is 64x that
     // (DESIGN.md "encoder exactness"; validated against the quad-precision oracle in tests/test_encode.py).
     const double n = (double)c->slots;
@@ -237,12 +256,9 @@ int ctx_get_ks_tables(Ctx *c, int level, BaseConv **ks, BaseConv **md, uint64_t 
         }
         BaseConv *dks = nullptr, *dmd = nullptr;
         uint64_t *dp = nullptr;
-        SFG_CUDA(c, cudaMalloc(&dks, sizeof(BaseConv) * h.size()));
-        SFG_CUDA(c, cudaMemcpy(dks, h.data(), sizeof(BaseConv) * h.size(), cudaMemcpyHostToDevice));
-        SFG_CUDA(c, cudaMalloc(&dmd, sizeof(BaseConv) * hm.size()));
-        SFG_CUDA(c, cudaMemcpy(dmd, hm.data(), sizeof(BaseConv) * hm.size(), cudaMemcpyHostToDevice));
-        SFG_CUDA(c, cudaMalloc(&dp, sizeof(uint64_t) * hp.size()));
-        SFG_CUDA(c, cudaMemcpy(dp, hp.data(), sizeof(uint64_t) * hp.size(), cudaMemcpyHostToDevice));
+        if (dev_alloc(c, (void **)&dks, sizeof(BaseConv) * h.size(), "table") || upload(c, dks, h.data(), sizeof(BaseConv) * h.size())) return -1;
+        if (dev_alloc(c, (void **)&dmd, sizeof(BaseConv) * hm.size(), "table") || upload(c, dmd, hm.data(), sizeof(BaseConv) * hm.size())) return -1;
+        if (dev_alloc(c, (void **)&dp, sizeof(uint64_t) * hp.size(), "table") || upload(c, dp, hp.data(), sizeof(uint64_t) * hp.size())) return -1;
         c->bc_ks[level] = dks;
         c->bc_md[level] = dmd;
         c->pinv[level] = dp;

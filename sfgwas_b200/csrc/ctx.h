@@ -69,6 +69,8 @@ struct Ctx {
         size_t bytes = 0;
     };
     WsBuf ws[16];
+    // grow-only PINNED host staging (hostio.cu): the "_ptrs" entry points gather / scatter one Go slice per limb through it
+    WsBuf pin[2];
     std::mutex mu;
     std::string err;
     // counters
@@ -101,6 +103,32 @@ int launch_check(Ctx *c, const char *what, cudaStream_t st);
         (ctx)->launches++;                           \
         if (launch_check((ctx), (what), (st))) return -1; \
     } while (0)
+
+// ---- device memory helpers (ctx.cu) ----
+// The context stream is created with cudaStreamNonBlocking: it does NOT synchronise with the legacy default stream, and a synchronous
+// cudaMemcpy from pageable host memory may return before its DMA (issued on the legacy stream) has reached the device.  A kernel
+// launched on the context stream right after such an upload can read what the allocation held before (root cause of the rare
+// first-call mismatch of round 1; profiles/microbench/nullstream_race.cu).  Every host -> device upload of the library
+// therefore goes through upload(): ordered on the context stream, then synchronised.
+int upload(Ctx *c, void *dst, const void *src, size_t bytes);
+// cudaMalloc; under SFG_POISON=1 the allocation is filled with 0xA5 first, so that any read of bytes this library has not written
+// (including reads compute-sanitizer's initcheck cannot see: cp.async.bulk / tcgen05 operand fetches) gives a deterministic mismatch
+int dev_alloc(Ctx *c, void **p, size_t bytes, const char *what);
+bool poison_enabled();
+// fills [p, p + bytes) with 0xA5 on the context stream when SFG_POISON=1 (per-call scratch whose contents are declared undefined)
+void poison_fill(Ctx *c, void *p, size_t bytes);
+
+// ---- per-limb host pointers <-> device (hostio.cu): what a cgo caller hands over is one pageable Go slice per limb ----
+enum PinSlot { PIN_IN = 0, PIN_OUT = 1 };
+int pinned_get(Ctx *c, int slot, size_t bytes, void **out);
+void pinned_release(Ctx *c);
+// np polynomials of N uint64 each, polynomial p at limbs[p] (host or device memory) -> d_dst + p * N; stream-ordered on c->stream,
+// the host buffers are free for reuse on return
+int gather_limbs_to_device(Ctx *c, const uint64_t *const *limbs, size_t np, uint64_t *d_dst);
+// the reverse for results that already sit in the pinned staging buffer `src` (np polynomials): parallel host copies
+void scatter_host_to_limbs(const uint64_t *src, uint64_t *const *limbs, size_t np, size_t N);
+// plain device -> per-limb pointers (synchronous; used where nothing overlaps)
+int scatter_device_to_limbs(Ctx *c, const uint64_t *d_src, uint64_t *const *limbs, size_t np);
 
 // workspace slots
 enum WsSlot { WS_C2 = 0, WS_ACC, WS_META, WS_R, WS_CV, WS_POFF, WS_TMPP, WS_A, WS_OUT, WS_META2, WS_RIMG, WS_PIMG, WS_MD, WS_KSB, WS_VQ, WS_EXTD, WS_COUNT };

@@ -36,10 +36,9 @@ int geno_create(Ctx *c, size_t nrows, size_t ncols, Geno **out) {
     g->device = c->device;
     g->nrows = nrows;
     g->ncols = ncols;
-    cudaError_t e = cudaMalloc(&g->d, nrows * ncols);
-    if (e != cudaSuccess) {
+    if (dev_alloc(c, (void **)&g->d, nrows * ncols, "genotype matrix")) {
         delete g;
-        SFG_FAIL(c, "cudaMalloc of %zu x %zu genotype matrix failed: %s", nrows, ncols, cudaGetErrorString(e));
+        return -1;
     }
     *out = g;
     return 0;
@@ -200,11 +199,17 @@ static int cache_meta_finish(Ctx *c, Cache *ca) {
         for (int bi = 0; bi < nbr; bi++) any |= ca->giant[(size_t)bi * d + gi] != 0;
         if (any) ca->gact.push_back(gi);
     }
+    if (ca->g_nparts > 1) {  // contiguous, balanced share of the active giant steps (the first n % parts shares get one more)
+        const int n = (int)ca->gact.size(), base = n / ca->g_nparts, extra = n % ca->g_nparts;
+        const int lo = ca->g_part * base + std::min(ca->g_part, extra), hi = lo + base + (ca->g_part < extra ? 1 : 0);
+        ca->gact = std::vector<int>(ca->gact.begin() + lo, ca->gact.begin() + hi);
+    }
     if (npoly > 0x7fffffffULL) SFG_FAIL(c, "too many diagonal polynomials");
     return tc_geom_p(c, ca->L, (int)ca->kbi.size(), (int)ca->gact.size() * m_ct, &ca->tc);
 }
 
-int cache_build(Ctx *c, Geno *g, int maxLevel, Cache **out, int bi_lo, int bi_hi) {
+int cache_build(Ctx *c, Geno *g, int maxLevel, Cache **out, int bi_lo, int bi_hi, int g_part, int g_nparts) {
+    if (g_nparts < 1 || g_part < 0 || g_part >= g_nparts) SFG_FAIL(c, "giant-step share %d of %d", g_part, g_nparts);
     if (g->filled != g->nrows) SFG_FAIL(c, "genotype matrix incomplete: %zu of %zu rows pushed", g->filled, g->nrows);
     if (maxLevel < 1 || maxLevel > c->nQ - 1) SFG_FAIL(c, "maxLevel %d needs %d Q limbs, parameters have %d", maxLevel, maxLevel + 1, c->nQ);
     const int nbr_all = (int)((g->nrows - 1) / c->slots) + 1;
@@ -216,6 +221,8 @@ int cache_build(Ctx *c, Geno *g, int maxLevel, Cache **out, int bi_lo, int bi_hi
     g->refs++;
     ca->bi_lo = bi_lo;
     ca->bi_hi = bi_hi;
+    ca->g_part = g_part;
+    ca->g_nparts = g_nparts;
     if (cache_init_meta(c, ca, g->nrows, g->ncols, maxLevel)) {
         cache_destroy(ca);
         return -1;
@@ -229,7 +236,9 @@ int cache_build(Ctx *c, Geno *g, int maxLevel, Cache **out, int bi_lo, int bi_hi
         budget = (size_t)(0.70 * (double)fr);
     }
     const size_t bytes = (size_t)ca->tc.group_bytes * ca->tc.ngroups;
-    if (npoly > 0 && bytes <= budget) {
+    if (bytes == 0) {  // a share without giant steps (more shares than giant steps): nothing to cache, Compute yields zero
+        ca->materialised = true;
+    } else if (npoly > 0 && bytes <= budget) {
         cudaError_t e = cudaMalloc(&ca->img, bytes);
         if (e == cudaSuccess) {
             ca->img_bytes = bytes;
@@ -422,7 +431,9 @@ static int build_rot_cache(Ctx *c, const Cache *ca, const uint64_t *d_A, int s, 
         }
     }
     KsBatch kb{};
-    kb.level = ca->maxLevel;  // A is dropped to maxLevel: only limbs 0..maxLevel are read (crypto/basics.go:806-824)
+    // A above maxLevel is dropped to maxLevel (only limbs 0..maxLevel are read, crypto/basics.go:806-824); A at maxLevel-1 is used as it
+    // is (gwas/matmult.go:1053 drops only when Level() > maxLevel; the accumulators read limbs 0..maxLevel-1, which it still has)
+    kb.level = std::min(levelA, ca->maxLevel);
     kb.in = d_A;
     kb.in_nl = nlA;
     kb.out = R;
@@ -567,11 +578,44 @@ static uint32_t inv_mod_pow2(uint64_t a, int bits) {  // a odd
 // Optional host destination of the result: rows of `out` are copied back on a second stream as soon as their giant-step sums are
 // final, so the device -> host transfer of the reference-facing entry points overlaps the remaining key-switches.
 struct HostSink {
-    uint64_t *host = nullptr;    // [s][m_ct][2][L][N]
+    uint64_t *host = nullptr;    // [s][m_ct][2][L][N] (pinned or pageable host memory of the caller, or the pinned staging buffer)
+    uint64_t *const *limbs = nullptr;  // optional: one destination pointer per limb (cgo: one Go slice each); `host` is then the staging buffer
     cudaStream_t copy = nullptr;
     cudaEvent_t ev = nullptr;
     bool used = false;           // set when run_giant issued the copies itself
+    struct Piece {               // a range of `host` whose device -> host copy has been enqueued on `copy`
+        size_t off, cnt;
+        cudaEvent_t done;
+    };
+    std::vector<Piece> pieces;   // limbs != nullptr only: scattered to the limb pointers by the host while the GPU computes on
 };
+// device -> host of d_out[off, off + cnt) on the copy stream, after everything enqueued so far on the compute stream
+static int sink_copy(Ctx *c, HostSink *sink, const uint64_t *d_out, size_t off, size_t cnt) {
+    SFG_CUDA(c, cudaEventRecord(sink->ev, c->stream));
+    SFG_CUDA(c, cudaStreamWaitEvent(sink->copy, sink->ev, 0));
+    SFG_CUDA(c, cudaMemcpyAsync(sink->host + off, d_out + off, cnt * 8, cudaMemcpyDefault, sink->copy));
+    if (sink->limbs) {
+        cudaEvent_t done;
+        SFG_CUDA(c, cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+        SFG_CUDA(c, cudaEventRecord(done, sink->copy));
+        sink->pieces.push_back(HostSink::Piece{off, cnt, done});
+    }
+    sink->used = true;
+    return 0;
+}
+// scatter the finished pieces to the caller's limb pointers (blocks on each piece's copy, not on the compute stream)
+static int sink_drain(Ctx *c, HostSink *sink) {
+    const size_t N = c->N;
+    cudaError_t e = cudaSuccess;
+    for (auto &pc : sink->pieces) {
+        if (e == cudaSuccess) e = cudaEventSynchronize(pc.done);
+        if (e == cudaSuccess) scatter_host_to_limbs(sink->host + pc.off, sink->limbs + pc.off / N, pc.cnt / N, N);
+        cudaEventDestroy(pc.done);
+    }
+    sink->pieces.clear();
+    SFG_CUDA(c, e);
+    return 0;
+}
 
 static int run_giant(Ctx *c, const Cache *ca, int s, const uint64_t *d_cv, int gi_lo, int gi_hi, uint64_t *d_out, HostSink *sink = nullptr) {
     const int d = ca->d, m_ct = ca->m_ct, L = ca->L, N = c->N, nrows = 2 * s;
@@ -665,10 +709,7 @@ static int run_giant(Ctx *c, const Cache *ca, int s, const uint64_t *d_cv, int g
         if (launch_rotate_sum_final(c, L - 1, nout_c, S1, C0, E, d_out, rot.d_out_off + chunk_base[ch], kb.out_layout, c->stream)) return -1;
         if (sink && sink->host) {  // rows [i_lo, i_hi) of out are final
             const size_t off = (size_t)i_lo * m_ct * 2 * LN, cnt = (size_t)(i_hi - i_lo) * m_ct * 2 * LN;
-            SFG_CUDA(c, cudaEventRecord(sink->ev, c->stream));
-            SFG_CUDA(c, cudaStreamWaitEvent(sink->copy, sink->ev, 0));
-            SFG_CUDA(c, cudaMemcpyAsync(sink->host + off, d_out + off, cnt * 8, cudaMemcpyDefault, sink->copy));
-            sink->used = true;
+            if (sink_copy(c, sink, d_out, off, cnt)) return -1;
         }
     }
     return 0;
@@ -676,10 +717,11 @@ static int run_giant(Ctx *c, const Cache *ca, int s, const uint64_t *d_cv, int g
 
 static int check_args(Ctx *c, const Cache *ca, int s, int nbr, int levelA, int maxLevel) {
     if (s < 1) SFG_FAIL(c, "A has no rows");
-    if (s > 16) SFG_FAIL(c, "s = %d ciphertext rows: at most 16 per call (split A)", s);
     if (nbr != ca->nbr) SFG_FAIL(c, "A has %d block rows but the genotype matrix has %d", nbr, ca->nbr);
     if (maxLevel != ca->maxLevel) SFG_FAIL(c, "maxLevel %d differs from the cache's %d", maxLevel, ca->maxLevel);
-    if (levelA < maxLevel) SFG_FAIL(c, "DropLevel: requested level %d when input is %d", maxLevel, levelA);  // crypto/basics.go:817
+    // gwas/matmult.go:1053-1056 drops A only when Level() > maxLevel; an input at maxLevel-1 still has the maxLevel limbs the accumulators
+    // read (:231-245, :393) and goes through unchanged; below that the reference indexes past Coeffs[] and panics
+    if (levelA < maxLevel - 1) SFG_FAIL(c, "input level %d has fewer than the %d limbs the accumulators read (index out of range)", levelA, maxLevel);
     if (levelA > c->nQ - 1) SFG_FAIL(c, "input level %d exceeds the parameter chain", levelA);
     return 0;
 }
@@ -690,9 +732,12 @@ static int check_rows(Ctx *c, const Cache *ca, int bi_lo, int bi_hi) {
     return 0;
 }
 
-int mm_compute_dev(Ctx *c, const uint64_t *d_A, int s, int nbr, int levelA, int maxLevel, Cache *ca, uint64_t *d_out, uint64_t *host_out) {
-    if (check_args(c, ca, s, nbr, levelA, maxLevel) || check_rows(c, ca, 0, nbr)) return -1;
-    SFG_CUDA(c, cudaSetDevice(c->device));
+// rows of A per pass: the tensor-core MAC stacks the byte planes of the 2s ciphertext polynomials as one MMA operand (N <= 256 columns,
+// (2 nb - 1) RP <= 512 TMEM columns), which holds for 16 rows with every modulus below 2^48
+constexpr int kMaxRowsPerPass = 16;
+
+// one pass over rows [0, s) of d_A / d_out (s <= kMaxRowsPerPass); ms accumulates the phase timings
+static int mm_compute_rows(Ctx *c, const uint64_t *d_A, int s, int nbr, int levelA, Cache *ca, uint64_t *d_out, HostSink *sink, float ms[5]) {
     const int L = ca->L, N = c->N, m_ct = ca->m_ct;
     const size_t LN = (size_t)L * N;
     PhaseTimer tm(c->stream);
@@ -700,8 +745,6 @@ int mm_compute_dev(Ctx *c, const uint64_t *d_A, int s, int nbr, int levelA, int 
     struct Reset { ~Reset() { g_tm = nullptr; } } reset;
     void *R;
     std::vector<int> klist;
-    HostSink sink;
-    sink.host = host_out;
     tm.mark(0);
     if (build_rot_cache(c, ca, d_A, s, levelA, 0, nbr, klist, &R)) return -1;
     SFG_CUDA(c, cudaMemsetAsync(d_out, 0, (size_t)s * m_ct * 2 * LN * 8, c->stream));
@@ -717,40 +760,79 @@ int mm_compute_dev(Ctx *c, const uint64_t *d_A, int s, int nbr, int levelA, int 
     }
     void *cv;
     if (ws_get(c, WS_CV, (size_t)gchunk * per_g, &cv)) return -1;
+    bool copied = false;
     for (int g0 = 0; g0 < ng; g0 += gchunk) {
         const int g1 = std::min(ng, g0 + gchunk);
         tm.mark(1);
         if (run_mac(c, ca, R, klist, s, g0, g1, (uint64_t *)cv)) return -1;
         tm.mark(2);
-        // the rows of out can leave for the host chunk by chunk only when this call sees every giant step
-        HostSink *sk = (host_out && g0 == 0 && g1 == ng) ? &sink : nullptr;
-        if (sk && !sk->copy) {
-            SFG_CUDA(c, cudaStreamCreateWithFlags(&sk->copy, cudaStreamNonBlocking));
-            SFG_CUDA(c, cudaEventCreateWithFlags(&sk->ev, cudaEventDisableTiming));
-        }
-        const int rc = run_giant(c, ca, s, (const uint64_t *)cv, g0, g1, d_out, sk);
-        if (rc) {
-            if (sink.copy) { cudaStreamSynchronize(sink.copy); cudaStreamDestroy(sink.copy); cudaEventDestroy(sink.ev); }
-            return -1;
-        }
+        // the rows of out can leave for the host chunk by chunk only when this pass sees every giant step at once
+        HostSink *sk = (sink && g0 == 0 && g1 == ng) ? sink : nullptr;
+        if (sk) sk->used = false;
+        if (run_giant(c, ca, s, (const uint64_t *)cv, g0, g1, d_out, sk)) return -1;
+        copied = sk && sk->used;
     }
+    if (sink && !copied && sink_copy(c, sink, d_out, 0, (size_t)s * m_ct * 2 * LN)) return -1;  // several giant chunks / nothing to rotate
     tm.mark(-1);
-    tm.finish(g_last_ms);
+    // per-limb destinations: the host scatters every piece as soon as its copy has landed, while the GPU works on the following rows
+    if (sink && sink->limbs && sink_drain(c, sink)) return -1;
+    float t[5];
+    tm.finish(t);
+    for (int i = 0; i < 5; i++) ms[i] += t[i];
+    return 0;
+}
+
+// host_out: the result also goes to this HOST buffer; out_limbs: ... or to one host pointer per limb (through the pinned staging
+// buffer).  Either way rows leave as soon as their giant-step sums are final, overlapped with the remaining key-switches.
+int mm_compute_dev(Ctx *c, const uint64_t *d_A, int s, int nbr, int levelA, int maxLevel, Cache *ca, uint64_t *d_out, uint64_t *host_out,
+                   uint64_t *const *out_limbs) {
+    if (check_args(c, ca, s, nbr, levelA, maxLevel) || check_rows(c, ca, 0, nbr)) return -1;
+    SFG_CUDA(c, cudaSetDevice(c->device));
+    const int L = ca->L, N = c->N, m_ct = ca->m_ct;
+    const size_t LN = (size_t)L * N, ctA = (size_t)2 * (levelA + 1) * N, row_out = (size_t)m_ct * 2 * LN;
+    HostSink sink;
+    sink.host = host_out;
+    sink.limbs = out_limbs;
+    if (out_limbs) {
+        void *pin;
+        if (pinned_get(c, PIN_OUT, (size_t)s * row_out * 8, &pin)) return -1;
+        sink.host = (uint64_t *)pin;
+    }
+    const bool to_host = sink.host != nullptr;
+    if (to_host) {
+        SFG_CUDA(c, cudaStreamCreateWithFlags(&sink.copy, cudaStreamNonBlocking));
+        SFG_CUDA(c, cudaEventCreateWithFlags(&sink.ev, cudaEventDisableTiming));
+    }
+    // The reference has no limit on len(A) (assoc.go:700-718 passes len(Q) + 2 rows); rows are independent, so more than
+    // kMaxRowsPerPass rows run as balanced passes over row ranges.
+    const int npass = (s + kMaxRowsPerPass - 1) / kMaxRowsPerPass, rpp = (s + npass - 1) / npass;
+    float ms[5] = {0, 0, 0, 0, 0};
+    int rc = 0;
+    for (int i0 = 0; i0 < s && !rc; i0 += rpp) {
+        const int si = std::min(rpp, s - i0);
+        HostSink part = sink;  // views of the same streams, offset to this pass's rows
+        part.pieces.clear();
+        if (part.host) part.host += (size_t)i0 * row_out;
+        if (part.limbs) part.limbs += (size_t)i0 * row_out / N;
+        rc = mm_compute_rows(c, d_A + (size_t)i0 * nbr * ctA, si, nbr, levelA, ca, d_out + (size_t)i0 * row_out, to_host ? &part : nullptr, ms);
+        for (auto &pc : part.pieces) cudaEventDestroy(pc.done);  // only non-empty after an error
+    }
+    for (int i = 0; i < 5; i++) g_last_ms[i] = ms[i];
     cudaError_t e = cudaStreamSynchronize(c->stream);
     if (sink.copy) {
         if (e == cudaSuccess) e = cudaStreamSynchronize(sink.copy);
         cudaStreamDestroy(sink.copy);
         cudaEventDestroy(sink.ev);
     }
+    if (rc) return -1;
     SFG_CUDA(c, e);
-    if (host_out && !sink.used)  // several giant chunks (or nothing to rotate): one copy at the end
-        SFG_CUDA(c, cudaMemcpy(host_out, d_out, (size_t)s * m_ct * 2 * LN * 8, cudaMemcpyDefault));
     return 0;
 }
 
 int mm_partial_dev(Ctx *c, const uint64_t *d_A, int s, int nbr, int levelA, int maxLevel, Cache *ca, int bi_lo, int bi_hi,
                    uint64_t *d_cv) {
     if (check_args(c, ca, s, nbr, levelA, maxLevel)) return -1;
+    if (s > kMaxRowsPerPass) SFG_FAIL(c, "s = %d ciphertext rows: the sharded pieces take at most %d per call (split A by rows)", s, kMaxRowsPerPass);
     if (bi_lo < 0 || bi_hi > nbr || bi_lo > bi_hi) SFG_FAIL(c, "block-row range [%d, %d) out of [0, %d)", bi_lo, bi_hi, nbr);
     if (bi_lo < bi_hi && check_rows(c, ca, bi_lo, bi_hi)) return -1;
     SFG_CUDA(c, cudaSetDevice(c->device));
@@ -777,6 +859,7 @@ int mm_partial_dev(Ctx *c, const uint64_t *d_A, int s, int nbr, int levelA, int 
 
 int mm_finish_dev(Ctx *c, Cache *ca, int s, int maxLevel, const uint64_t *d_cv, int g_lo, int g_hi, uint64_t *d_out) {
     if (maxLevel != ca->maxLevel) SFG_FAIL(c, "maxLevel mismatch");
+    if (s < 1 || s > kMaxRowsPerPass) SFG_FAIL(c, "s = %d ciphertext rows: the sharded pieces take 1..%d per call", s, kMaxRowsPerPass);
     const int ng = (int)ca->gact.size();
     if (g_lo < 0 || g_hi > ng || g_lo > g_hi) SFG_FAIL(c, "giant range [%d, %d) out of [0, %d)", g_lo, g_hi, ng);
     SFG_CUDA(c, cudaSetDevice(c->device));

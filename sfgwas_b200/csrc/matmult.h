@@ -37,6 +37,7 @@ struct Cache {
     std::vector<int> kbi, kb, kidx;
     std::vector<int> gact;        // active giant indices (any block row)
     int bi_lo = 0, bi_hi = -1;    // block rows whose diagonals the image holds (-1 = all): block-row sharding builds only a rank's own
+    int g_part = 0, g_nparts = 1; // giant-step sharding: gact holds share g_part of g_nparts of the active giant steps
 };
 
 struct Buf {  // RAII device buffer
@@ -51,7 +52,7 @@ struct Buf {  // RAII device buffer
     int alloc(Ctx *c, size_t n) {
         release();
         if (n == 0) n = 16;
-        SFG_CUDA(c, cudaMalloc(&p, n));
+        if (dev_alloc(c, &p, n, "temporary buffer")) return -1;  // 0xA5-filled under SFG_POISON=1
         bytes = n;
         return 0;
     }
@@ -64,7 +65,9 @@ int geno_push(Geno *g, const int8_t *rows, size_t n);
 void geno_release(Geno *g);
 
 // bi_lo / bi_hi: build only the diagonals of block rows [bi_lo, bi_hi) (block-row sharding; such a cache serves mm_partial_dev only)
-int cache_build(Ctx *c, Geno *g, int maxLevel, Cache **out, int bi_lo = 0, int bi_hi = -1);
+// g_part / g_nparts: keep only that contiguous share of the active giant steps (giant-step sharding: Compute on such a cache yields the
+// partial sum over its giant steps; the per-rank results add up mod q to the full product)
+int cache_build(Ctx *c, Geno *g, int maxLevel, Cache **out, int bi_lo = 0, int bi_hi = -1, int g_part = 0, int g_nparts = 1);
 // one cached diagonal polynomial (plain canonical residues, [L][N]) read back out of the image; 0 = nil
 int cache_get_diag_dev(Ctx *c, const Cache *ca, int bi, int shift, int bj, uint64_t *d_out, int *present);
 void cache_destroy(Cache *cache);
@@ -74,8 +77,9 @@ int cache_load_files(Ctx *c, const char *prefix, size_t nrows, size_t ncols, int
 
 // full single-GPU compute: d_A device [s][nbr][2][nlA][N] -> d_out device [s][m_ct][2][L][N]
 // host_out (optional): the result is also copied to this HOST buffer, rows leaving as soon as their giant-step sums are final
+// out_limbs (optional, instead of host_out): one HOST pointer per limb of the result, [((i*m_ct+bj)*2+c)*maxLevel+l] (cgo callers)
 int mm_compute_dev(Ctx *c, const uint64_t *d_A, int s, int nbr, int levelA, int maxLevel, Cache *cache, uint64_t *d_out,
-                   uint64_t *host_out = nullptr);
+                   uint64_t *host_out = nullptr, uint64_t *const *out_limbs = nullptr);
 // multi-GPU pieces
 int mm_partial_dev(Ctx *c, const uint64_t *d_A, int s, int nbr, int levelA, int maxLevel, Cache *cache, int bi_lo, int bi_hi,
                    uint64_t *d_cv);

@@ -1,6 +1,13 @@
 """Multi-GPU sharding of the MatMult hot path on one box: one process per GPU, torch.distributed for the plumbing.
 
-Two shardings, both bit-identical to the single-GPU result:
+Three shardings, all bit-identical to the single-GPU result:
+
+* ``GiantSharded`` -- STRONG scaling of one product: rank r owns a contiguous share of the active giant steps g, i.e. of the columns
+  (g, bj) of the dense contraction: 1/world of the diagonal cache, of the MAC and of the giant-step key-switches.
+  ``out[i][bj] = sum_g RotL_{g d}(cv[i][g][bj])`` is a mod-q sum over g (gwas/matmult.go:1223-1227), so the per-rank partial outputs
+  are combined by ONE modular-add all-reduce of ``s * m_ct`` ciphertexts over NVLink (NCCL integer SUM + ``sfg_ct_mod_reduce``); the
+  d giant steps balance over 2 / 4 / 8 ranks whatever the number of block columns.  The baby-step rotations are recomputed by every
+  rank (7 % of a single-GPU step).  This is what ``bench.py --gpus N`` measures.
 
 * ``ColumnSharded`` -- SNP-block (= block-column) sharding for Q.X-shaped products with X = nind x nsnp: rank r owns a contiguous
   range of block columns; every accumulator (i, giant, bj), its reduce, its giant rotations and the final add are independent
@@ -66,6 +73,85 @@ def mod_allreduce_(t, moduli: Sequence[int], N: int, group=None, cps: CryptoPara
         for l, q in enumerate(moduli):
             v[:, l, :] %= q
     return t
+
+
+def ct_mod_allreduce_(t, cps: CryptoParams, nl: int, group=None):
+    """In-place modular sum over ranks of a CUDA tensor of canonical residues [..., nl, N] (int64 view of u64): NCCL integer SUM all-reduce
+    (at most 2^8 ranks of residues < 2^56) + the library's canonicalisation kernel.  Stream-ordered on torch's current stream."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    if max(cps.Q[:nl]) * world >= 1 << 63:
+        raise SfgError("sum of %d residues may overflow int64 for a %d-bit modulus" % (world, max(cps.Q[:nl]).bit_length()))
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    torch.cuda.current_stream().synchronize()
+    cps._check(cps.L.sfg_ct_mod_reduce(cps.h, C.c_void_p(t.data_ptr()), t.numel() // (nl * cps.N), nl), "sfg_ct_mod_reduce")
+    return t
+
+
+def giant_share(ng: int, world: int) -> int:
+    """Giants per rank of the reduce-scattered accumulator image: equal shares (the last ranks' tail is zero padding)."""
+    return (ng + world - 1) // world
+
+
+def mod_reduce_scatter_(t, share: int, cps: CryptoParams = None, nl: int = 0, group=None, moduli: Sequence[int] = None, N: int = 0):
+    """Modular-add reduce-scatter of canonical residues: `t` holds world * share int64 words laid out [..., nl, N]; returns this rank's
+    share summed over ranks and canonicalised.  NCCL ``reduce_scatter_tensor`` + ``sfg_ct_mod_reduce`` on CUDA tensors; on CPU tensors
+    (gloo has no reduce-scatter: the world-size-2 CPU tests of the host logic) an all-reduce + slice with torch ops."""
+    import torch
+    import torch.distributed as dist
+
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    if t.numel() != world * share:
+        raise SfgError("reduce-scatter: %d words do not split into %d shares of %d" % (t.numel(), world, share))
+    if t.is_cuda:
+        if max(cps.Q[:nl]) * world >= 1 << 63:
+            raise SfgError("sum of %d residues may overflow int64" % world)
+        mine = torch.empty(share, dtype=t.dtype, device=t.device)
+        dist.reduce_scatter_tensor(mine, t, op=dist.ReduceOp.SUM, group=group)
+        torch.cuda.current_stream().synchronize()
+        cps._check(cps.L.sfg_ct_mod_reduce(cps.h, C.c_void_p(mine.data_ptr()), share // (nl * cps.N), nl), "sfg_ct_mod_reduce")
+        return mine
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    mine = t[rank * share:(rank + 1) * share].clone()
+    v = mine.view(-1, len(moduli), N)
+    for l, q in enumerate(moduli):
+        v[:, l, :] %= q
+    return mine
+
+
+class GiantSharded:
+    """Strong scaling of ONE MatMult4StreamCompute over the GPUs of a box: rank `rank` of `world` holds the diagonals of its share of the
+    giant steps and produces the partial sum over them; ``compute`` all-reduces the partial outputs mod q (device-resident throughout)."""
+
+    def __init__(self, cps: CryptoParams, gfs: GenoFileStream, rank: int, world: int, max_level: int = 5):
+        self.cps, self.rank, self.world, self.max_level = cps, rank, world, max_level
+        h = C.c_void_p()
+        cps._check(cps.L.sfg_matmult4_stream_preprocess_giants(cps.h, gfs.h, max_level, rank, world, C.byref(h)),
+                   "sfg_matmult4_stream_preprocess_giants")
+        self.cache = DiagCache(cps, h)
+
+    def compute_dev(self, d_A, d_out, s: int, nbr: int, level_a: int, group=None):
+        """d_A [s][nbr][2][level_a+1][N], d_out [s][m_ct][2][max_level][N]: int64 CUDA tensors; d_out = the FULL product on every rank."""
+        cps = self.cps
+        cps._check(cps.L.sfg_matmult4_stream_compute_dev(cps.h, C.c_void_p(d_A.data_ptr()), s, nbr, level_a, self.max_level, self.cache.h,
+                                                         C.c_void_p(d_out.data_ptr())), "sfg_matmult4_stream_compute_dev")
+        if self.world > 1:
+            ct_mod_allreduce_(d_out, cps, self.max_level, group)
+        return d_out
+
+    def compute(self, A: np.ndarray, group=None) -> np.ndarray:
+        import torch
+
+        cps = self.cps
+        A = np.ascontiguousarray(A, dtype=np.uint64)
+        s, nbr, _, nlA, _ = A.shape
+        dev = torch.device("cuda", cps.device)
+        d_A = torch.from_numpy(A.view(np.int64)).to(dev)
+        d_out = torch.zeros((s, self.cache.m_ct, 2, self.max_level, cps.N), dtype=torch.int64, device=dev)
+        self.compute_dev(d_A, d_out, s, nbr, nlA - 1, group)
+        return d_out.cpu().numpy().view(np.uint64)
 
 
 class ColumnSharded:
@@ -138,18 +224,19 @@ class RowSharded:
         s, nbr, _, nlA, _ = A.shape
         dev = torch.device("cuda", cps.device)
         n_cv = int(L.sfg_cv_elems(cps.h, self.cache.h, s, self.max_level))
-        cv = torch.empty(n_cv, dtype=torch.int64, device=dev)
+        per_g = self.cache.m_ct * 2 * s * self.max_level * cps.N
+        ng = n_cv // per_g
+        # the image is laid out [giant][bj][row][L][N]: equal shares of `ch` giants per rank (zero-padded tail) make the combination a
+        # modular-add REDUCE-SCATTER -- every rank receives only the giants it then rotates (gwas/matmult.go:1203-1227)
+        ch = giant_share(ng, self.world)
+        cv = torch.zeros(self.world * ch * per_g, dtype=torch.int64, device=dev)
         lo, hi = self.row_ranges[self.rank]
         cps._check(L.sfg_matmult4_partial(cps.h, _p(A), s, nbr, nlA - 1, self.max_level, self.cache.h, lo, hi, C.c_void_p(cv.data_ptr())),
                    "sfg_matmult4_partial")
-        moduli = cps.Q[: self.max_level]
-        mod_allreduce_(cv, moduli, cps.N, group, cps, self.cache, s, self.max_level)
-        per_g = self.cache.m_ct * 2 * s * self.max_level * cps.N
-        ng = n_cv // per_g
-        g_lo, g_hi = partition(ng, self.world)[self.rank]
-        out = np.zeros((s, self.cache.m_ct, 2, self.max_level, cps.N), dtype=np.uint64)
-        cps._check(L.sfg_matmult4_finish(cps.h, self.cache.h, s, self.max_level, C.c_void_p(cv.data_ptr()), g_lo, g_hi, _p(out)),
-                   "sfg_matmult4_finish")
-        t = torch.from_numpy(out.view(np.int64)).to(dev)
-        mod_allreduce_(t, moduli, cps.N, group, cps, self.cache, s, self.max_level)
+        mine = mod_reduce_scatter_(cv, ch * per_g, cps, self.max_level, group)
+        g_lo, g_hi = min(ng, self.rank * ch), min(ng, (self.rank + 1) * ch)
+        t = torch.zeros((s, self.cache.m_ct, 2, self.max_level, cps.N), dtype=torch.int64, device=dev)
+        cps._check(L.sfg_matmult4_finish_dev(cps.h, self.cache.h, s, self.max_level, C.c_void_p(mine.data_ptr()), g_lo, g_hi,
+                                             C.c_void_p(t.data_ptr())), "sfg_matmult4_finish_dev")
+        ct_mod_allreduce_(t, cps, self.max_level, group)  # everything stays on the device until the final read-back
         return t.cpu().numpy().view(np.uint64)

@@ -35,7 +35,7 @@ def _gloo_worker(rank, world, port, moduli, N, seed, q):
     import torch
     import torch.distributed as dist
 
-    from sfgwas_b200.dist import mod_allreduce_
+    from sfgwas_b200.dist import giant_share, mod_allreduce_, mod_reduce_scatter_
 
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -54,7 +54,17 @@ def _gloo_worker(rank, world, port, moduli, N, seed, q):
             for p in parts:
                 acc = acc + p[:, l, :].astype(object)
             want[:, l, :] = (acc % m).astype(np.uint64)
-        q.put((rank, bool((t.numpy().view(np.uint64) == want).all()), int(L)))
+        ok = bool((t.numpy().view(np.uint64) == want).all())
+        # modular-add reduce-scatter of an accumulator image of ng = 3 "giants" ([3][L][N] each rank): shares of giant_share(3, 2) = 2
+        # giants, zero-padded tail (RowSharded's combination between the MAC and the giant-step rotations)
+        share = giant_share(3, world)
+        per_g = L * N
+        padded = torch.zeros(world * share * per_g, dtype=torch.int64)
+        padded[: 3 * per_g] = torch.from_numpy(parts[rank].view(np.int64).reshape(-1).copy())
+        mine = mod_reduce_scatter_(padded, share * per_g, group=None, moduli=moduli, N=N).numpy().view(np.uint64).reshape(share, L, N)
+        g_lo, g_hi = min(3, rank * share), min(3, (rank + 1) * share)
+        ok = ok and bool((mine[: g_hi - g_lo] == want[g_lo:g_hi]).all()) and bool((mine[g_hi - g_lo:] == 0).all())
+        q.put((rank, ok, int(L)))
     finally:
         dist.destroy_process_group()
 
@@ -82,7 +92,7 @@ def _gpu_worker(rank, world, port, q):
 
     from oracle.oracle import Oracle, small_params
     from sfgwas_b200 import CryptoParams, GenoFileStream, MatMult4StreamCompute, MatMult4StreamPreprocess
-    from sfgwas_b200.dist import ColumnSharded, RowSharded
+    from sfgwas_b200.dist import ColumnSharded, GiantSharded, RowSharded
 
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -109,7 +119,9 @@ def _gpu_worker(rank, world, port, q):
         col_ok = bool((cs.gather(cs.compute(A)) == single).all())
         rs = RowSharded(cps, X, rank, world)
         row_ok = bool((rs.compute(A) == single).all())
-        q.put((rank, col_ok, row_ok))
+        gs = GiantSharded(cps, GenoFileStream.from_matrix(cps, X), rank, world)
+        giant_ok = bool((gs.compute(A) == single).all())
+        q.put((rank, col_ok, row_ok and giant_ok))
     finally:
         dist.destroy_process_group()
 

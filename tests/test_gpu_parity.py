@@ -313,23 +313,16 @@ def test_preprocess_compute_bit_exact(small13, nr, nc, s):
     o.cache_free(dc)
     assert out.shape == want.shape
     if not (out == want).all():
-        # say where, and which side is unstable, before failing (a rare mismatch in the first test process on a fresh box, never
-        # reproduced under compute-sanitizer; the parity tests now run the oracle single-threaded -- its pthread mode is for the
-        # CPU-baseline timing only -- and this arbiter reports which side moved if it ever happens again)
+        # A mismatch is a HARD failure.  Before failing, say where and which side moved (round 1 saw a rare first-call mismatch whose
+        # root cause was a legacy-stream table upload racing the non-blocking context stream: DESIGN.md 6b).
         bad = out != want
         again = MatMult4StreamCompute(cps, A, 5, cache)
         dc1 = o.preprocess(X, 5, nproc=1)
         want1 = o.compute(A, dc1, keys, 5, nproc=1)
         o.cache_free(dc1)
-        msg = ("CUDA != oracle(8 threads): %d of %d words, first %s; cuda repeatable=%s, oracle(1 thread)==oracle(8 threads)=%s, "
-               "cuda==oracle(1 thread)=%s" % (int(bad.sum()), bad.size, np.argwhere(bad)[:3].tolist(), bool((again == out).all()),
-                                              bool((want1 == want).all()), bool((out == want1).all())))
-        if (again == out).all() and (out == want1).all():
-            import warnings
-
-            warnings.warn("multi-threaded oracle run was not reproducible: " + msg)
-        else:
-            raise AssertionError(msg)
+        raise AssertionError("CUDA != oracle: %d of %d words, first %s; cuda repeatable=%s, oracle repeatable=%s, cuda==oracle(rerun)=%s"
+                             % (int(bad.sum()), bad.size, np.argwhere(bad)[:3].tolist(), bool((again == out).all()),
+                                bool((want1 == want).all()), bool((out == want1).all())))
     # numerical meaning (the reference's CPMatMult0 notion): decrypt(out) ~= A_plain . X ; tolerance 1e-4 relative
     ref = Ap @ X.astype(float)
     tol = 1e-4 * max(1.0, np.abs(ref).max())
@@ -398,14 +391,176 @@ def test_error_behaviour(small13):
     X = np.ones((10, 10), dtype=np.int8)
     gfs = GenoFileStream.from_matrix(cps, X)
     cache = MatMult4StreamPreprocess(cps, gfs, 5)
-    with pytest.raises(SfgError):  # input level below maxLevel: DropLevel is fatal in the reference (crypto/basics.go:817)
-        MatMult4StreamCompute(cps, np.zeros((1, 1, 2, 5, o.N), dtype=np.uint64), 5, cache)
+    with pytest.raises(SfgError):  # fewer than maxLevel limbs: the reference indexes past Coeffs[] (gwas/matmult.go:393) and panics
+        MatMult4StreamCompute(cps, np.zeros((1, 1, 2, 4, o.N), dtype=np.uint64), 5, cache)
     with pytest.raises(SfgError):  # wrong number of block rows
         MatMult4StreamCompute(cps, np.zeros((1, 2, 2, 6, o.N), dtype=np.uint64), 5, cache)
     g2 = GenoFileStream(cps, 4, 4)
     g2.push_rows(np.zeros((2, 4), dtype=np.int8))
     with pytest.raises(SfgError):  # incomplete stream
         MatMult4StreamPreprocess(cps, g2, 5)
+
+
+def test_input_one_level_below_maxlevel(small13):
+    """gwas/matmult.go:1053-1056 drops A only when Level() > maxLevel: an input at level maxLevel-1 (e.g. QS = CMult(Q, XStdInv) landing one
+    level lower) is valid in the reference -- rotated at its own level, output at level maxLevel-1 (ADVICE r1)."""
+    from sfgwas_b200 import GenoFileStream, MatMult4StreamCompute, MatMult4StreamPreprocess
+
+    o, cps, sk, keys = small13
+    rng = np.random.default_rng(41)
+    X = rng.integers(0, 3, (200, 300)).astype(np.int8)
+    Ap = rng.normal(size=(2, 200))
+    A = enc_matrix(o, sk, Ap, level=4)
+    cache = MatMult4StreamPreprocess(cps, GenoFileStream.from_matrix(cps, X), 5)
+    out = MatMult4StreamCompute(cps, A, 5, cache)
+    dc = o.preprocess(X, 5, nproc=1)
+    want = o.compute(A, dc, keys, 5, nproc=1)
+    o.cache_free(dc)
+    assert (out == want).all()
+    got = o.decrypt_vector(sk, out[1, 0], o.scale * o.scale).real
+    ref = (Ap @ X.astype(float))[1, : o.slots]
+    assert np.abs(got[: len(ref)] - ref).max() < 1e-4 * max(1.0, np.abs(ref).max())
+
+
+@pytest.mark.parametrize("s", [17, 35])
+def test_more_than_16_rows(small13, s):
+    """The reference has no limit on len(A) (gwas/assoc.go:700-718 passes len(Q)+2 rows; a PCA with kp > 16): more rows than one
+    tensor-core pass holds run as balanced row passes with identical bits (ADVICE r1)."""
+    from sfgwas_b200 import GenoFileStream, MatMult4StreamCompute, MatMult4StreamPreprocess
+
+    o, cps, sk, keys = small13
+    rng = np.random.default_rng(1000 + s)
+    X = rng.integers(0, 3, (150, 260)).astype(np.int8)
+    A = enc_matrix(o, sk, rng.normal(size=(s, 150)))
+    cache = MatMult4StreamPreprocess(cps, GenoFileStream.from_matrix(cps, X), 5)
+    out = MatMult4StreamCompute(cps, A, 5, cache)
+    dc = o.preprocess(X, 5, nproc=1)
+    want = o.compute(A, dc, keys, 5, nproc=1)
+    o.cache_free(dc)
+    assert out.shape == want.shape and (out == want).all()
+
+
+def test_ptrs_entry_points_equal_flat(small13):
+    """The entry points the cgo shim binds (go/gwas/matmult_b200.go): one PAGEABLE array per limb for A, the result, the rotation keys
+    and the relinearisation key -- exactly what Go hands over ([][]uint64 Coeffs).  Bit-equal to the flat entry points."""
+    import ctypes as C
+
+    from sfgwas_b200 import CryptoParams, GenoFileStream, MatMult4StreamCompute, MatMult4StreamPreprocess
+
+    o, cps, sk, keys = small13
+    p = dict(logN=o.logN, Q=o.Q, P=o.P, scale=o.scale)
+    cps2 = CryptoParams(p["logN"], p["Q"], p["P"], p["scale"])
+    L = cps2.L
+    keep = []
+
+    def limb_ptrs(arr):  # every limb a separate heap allocation, like a Go slice
+        flat = arr.reshape(-1, o.N)
+        limbs = [np.array(flat[k], dtype=np.uint64, copy=True) for k in range(flat.shape[0])]
+        keep.append(limbs)
+        return (C.c_void_p * len(limbs))(*[x.ctypes.data for x in limbs]), limbs
+
+    for k, v in keys.items():
+        ptrs, _ = limb_ptrs(v)
+        cps2._check(L.sfg_ctx_set_rotation_key_ptrs(cps2.h, k, ptrs), "set_rotation_key_ptrs")
+    rlk = o.gen_relin_key(sk)
+    ptrs, _ = limb_ptrs(rlk)
+    cps2._check(L.sfg_ctx_set_relin_key_ptrs(cps2.h, ptrs), "set_relin_key_ptrs")
+    assert L.sfg_ctx_has_rotation_key(cps2.h, 1) == 1
+
+    rng = np.random.default_rng(77)
+    for nr, nc, s in ((260, 520, 10), (130, 77, 3), (150, 260, 18)):
+        X = rng.integers(0, 3, (nr, nc)).astype(np.int8)
+        A = enc_matrix(o, sk, rng.normal(size=(s, nr)))
+        want = MatMult4StreamCompute(cps, A, 5, MatMult4StreamPreprocess(cps, GenoFileStream.from_matrix(cps, X), 5))
+        cache = MatMult4StreamPreprocess(cps2, GenoFileStream.from_matrix(cps2, X), 5)
+        a_ptrs, _ = limb_ptrs(A)
+        out = np.full((s, cache.m_ct, 2, 5, o.N), 0xA5A5A5A5A5A5A5A5, dtype=np.uint64)
+        o_ptrs, o_limbs = limb_ptrs(out)
+        for rep in range(2):  # twice: the staging buffers are reused
+            cps2._check(L.sfg_matmult4_stream_compute_ptrs(cps2.h, a_ptrs, s, A.shape[1], 5, 5, cache.h, o_ptrs), "compute_ptrs")
+            got = np.stack(o_limbs).reshape(want.shape)
+            assert (got == want).all(), (nr, nc, s, rep)
+    # the relinearisation key uploaded through _ptrs multiplies like the flat one
+    from sfgwas_b200 import Ciphertext, CMult, SetRelinKey
+
+    SetRelinKey(cps, rlk)
+    v = rng.normal(size=o.slots)
+    ct = Ciphertext(o.encrypt_vector(sk, v, 5, seed=5), o.scale)
+    assert (CMult(cps, [ct], [ct])[0].value == CMult(cps2, [ct], [ct])[0].value).all()
+    cps2.close()
+
+
+def test_seven_k_groups_transposed_shape(small13):
+    """The transposed orientation of BASELINE config 2 (100k x 10k: 25 block rows, K = 1 600 baby-step slots = 7 K groups of the
+    tensor-core MAC) at the same SHAPE on a small ring: enough block rows for 7 K groups, 3 block columns, s = 10 (VERDICT r1 item 7)."""
+    from sfgwas_b200 import GenoFileStream, MatMult4StreamCompute, MatMult4StreamPreprocess
+
+    o, cps, sk, keys = small13
+    nbr = (6 * 256) // o.d + 1  # K = nbr * d > 6 * 256  ->  7 K groups
+    nr, nc, s = (nbr - 1) * o.slots + 17, 2 * o.slots + 30, 10
+    rng = np.random.default_rng(7)
+    X = rng.integers(0, 3, (nr, nc)).astype(np.int8)
+    A = enc_matrix(o, sk, rng.normal(size=(s, nr)))
+    cache = MatMult4StreamPreprocess(cps, GenoFileStream.from_matrix(cps, X), 5)
+    assert cache.num_block_rows == nbr and nbr * o.d > 6 * 256
+    out = MatMult4StreamCompute(cps, A, 5, cache)
+    dc = o.preprocess(X, 5, nproc=8)
+    want = o.compute(A, dc, keys, 5, nproc=8)
+    o.cache_free(dc)
+    assert (out == want).all()
+
+
+@pytest.mark.parametrize("case", ["pn13_2x4_s10", "pn14_2x2_s15"])
+def test_benchmarked_geometry_golden(case):
+    """Preprocess + Compute at the REAL parameter sets and the benchmarked geometry (several block rows, full 128-column tiles, giant
+    chunks, row chunks; PN14: two-half MAC, half-ring key-switch, nP = 2) against the CPU oracle: the oracle ran offline
+    (tests/golden/gen_parity_big.py, minutes on 8 cores) and left SHA-256 digests of every output ciphertext; the same seeded inputs are
+    regenerated here and ALL of `out` must hash identically (VERDICT r1 weak #2)."""
+    import importlib.util
+
+    from oracle.oracle import PARAMS, Oracle
+    from sfgwas_b200 import CryptoParams, GenoFileStream, MatMult4StreamCompute, MatMult4StreamPreprocess
+
+    path = os.path.join(G, "parity_%s.json" % case)
+    if not os.path.exists(path):
+        pytest.skip("fixture %s not generated" % path)
+    spec = importlib.util.spec_from_file_location("gen_parity_big", os.path.join(G, "gen_parity_big.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    with open(path) as f:
+        gold = json.load(f)
+    cs = gold["case"]
+    prm = PARAMS[cs["params"]]
+    o = Oracle.from_params(prm)
+    X, Ap, sk, keys, A = gen.inputs(o, cs)
+    assert hashlib.sha256(X.tobytes()).hexdigest() == gold["input_digests"]["X"], "seeded genotypes differ from the fixture's"
+    assert gen.digest(A) == gold["input_digests"]["A"], "seeded ciphertexts differ from the fixture's"
+    cps = CryptoParams(prm["logN"], prm["Q"], prm["P"], prm["scale"])
+    cps.SetRotKeys(keys)
+    cache = MatMult4StreamPreprocess(cps, GenoFileStream.from_matrix(cps, X), 5)
+    assert cache.materialised and cache.num_polys == gold["num_polys"]
+    for key, want in gold["diag_sha256"].items():
+        bi, shift, bj = (int(x) for x in key.split(","))
+        got = cache.get_diag(bi, shift, bj)
+        assert (got is None) == (want is None), key
+        if want is not None:
+            assert gen.digest(got) == want, "cached diagonal %s differs from the oracle's" % key
+    out = MatMult4StreamCompute(cps, A, 5, cache)
+    assert list(out.shape) == gold["shape"]
+    s, m_ct = out.shape[:2]
+    bad = [(i, bj) for i in range(s) for bj in range(m_ct) if gen.digest(out[i, bj]) != gold["out_sha256"][i][bj]]
+    assert not bad, "output ciphertexts differ from the oracle's: %s" % bad[:8]
+    ref = Ap @ X.astype(float)
+    got = o.decrypt_vector(sk, out[s - 1, m_ct - 1], o.scale * o.scale).real
+    w = ref[s - 1, (m_ct - 1) * o.slots:]
+    assert np.abs(got[: len(w)] - w).max() < 1e-3 * max(1.0, np.abs(ref).max())  # CKKS tolerance (DESIGN.md 3)
+    # the non-materialised path (diagonals regenerated per chunk: the config 4 / 5 regime) gives the same bits at this geometry
+    cps.set_cache_budget(1)
+    c2 = MatMult4StreamPreprocess(cps, GenoFileStream.from_matrix(cps, X), 5)
+    cps.set_cache_budget(0)
+    assert not c2.materialised
+    assert (MatMult4StreamCompute(cps, A, 5, c2) == out).all()
+    cps.close()
 
 
 @pytest.mark.parametrize("pname", ["PN13QP218", "PN14QP438"])
@@ -470,6 +625,35 @@ def test_many_block_rows_multiple_k_groups(small13):
     want = o.compute(A, dc, keys, 5, nproc=1)
     o.cache_free(dc)
     assert (out == want).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nparts", [2, 5, 16])
+def test_giant_sharded_partials_sum_to_compute(small13, nparts):
+    """Giant-step sharding (bench.py --gpus N, dist.GiantSharded) on ONE GPU: the caches of the `nparts` shares are built one after the
+    other, every share's Compute is a partial sum over its giant steps, and the shares add up mod q to the unsharded result bit for
+    bit (16 shares > 12 giant steps: some shares are empty)."""
+    import ctypes as C
+
+    from sfgwas_b200 import DiagCache, GenoFileStream, MatMult4StreamCompute, MatMult4StreamPreprocess
+
+    o, cps, sk, keys = small13
+    rng = np.random.default_rng(400 + nparts)
+    nr, nc, s = 300, 260, 3
+    X = rng.integers(0, 3, (nr, nc)).astype(np.int8)
+    A = enc_matrix(o, sk, rng.normal(size=(s, nr)))
+    gfs = GenoFileStream.from_matrix(cps, X)
+    full = MatMult4StreamCompute(cps, A, 5, MatMult4StreamPreprocess(cps, gfs, 5))
+    acc = np.zeros(full.shape, dtype=object)
+    for part in range(nparts):
+        h = C.c_void_p()
+        cps._check(cps.L.sfg_matmult4_stream_preprocess_giants(cps.h, gfs.h, 5, part, nparts, C.byref(h)), "preprocess_giants")
+        cache = DiagCache(cps, h)
+        acc = acc + MatMult4StreamCompute(cps, A, 5, cache).astype(object)
+        cache.close()
+    for l in range(5):
+        acc[:, :, :, l] %= o.Q[l]
+    assert (acc.astype(np.uint64) == full).all()
 
 
 @pytest.mark.gpu
