@@ -1,19 +1,27 @@
 #!/usr/bin/env python3
 """bench.py -- genotype x CKKS-ciphertext MatMult throughput (BASELINE.json metric) on B200.
 
-  python bench.py --gpus N --steps K --warmup W              # this repo's CUDA path
+  python bench.py --gpus N --steps K --warmup W              # this repo's CUDA path (torchrun for N > 1)
   python bench.py --impl reference --gpus N --steps K ...    # the reference's CPU algorithm (oracle port) on the host cores
 
-Workload (BASELINE.json configs[1]): X = 10 000 samples x 100 000 SNPs int8 (Binomial(2, p_j), p_j ~ U(0.05, 0.5)),
+Default workload (BASELINE.json configs[1]): X = 10 000 samples x 100 000 SNPs int8 (Binomial(2, p_j), p_j ~ U(0.05, 0.5)),
 A = 10 rows x 3 ciphertexts at level 5, PN13QP218 (logN = 13, scale 2^30), orientation A.X -> 10 x 25 ciphertexts at level 4.
-A "step" is one MatMult4StreamCompute call over the preprocessed, HBM-resident diagonal cache (the reference calls
-Compute ~40x per Preprocess inside the PCA power iterations, gwas/pca.go:112-113,288-352).
+A "step" is one MatMult4StreamCompute call over the preprocessed diagonal cache (the reference calls Compute ~40x per
+Preprocess inside the PCA power iterations, gwas/pca.go:112-113,288-352).  Other workloads (--workload): the transposed
+orientation of config 2 (25 block rows, 7 K groups), PCA-shaped logN-14 slices (configs 4/5), and "_otf" variants that force the
+diagonals to be re-encoded on the fly inside every call (the regime of configs 4/5, whose cache exceeds HBM).
 
-metric  = B_alg / t  in GB/s with B_alg = diag_polys*L'*N*8 + s*nbr*2*6*N*8 + s*m_ct*2*L'*N*8
-value   = inputs already resident in HBM; e2e = the same call through the C ABI with pinned HOST buffers for A and out.
-Synthetic data: ciphertext and Galois-key residues are uniformly random (which is what real ones look like); the
-kernels have no data-dependent control flow, so the work is identical.  Multi-GPU: every rank owns its own block of
-100 000 SNP columns of a 10 000 x (N*100 000) matrix (SNP-block sharding, no data-path collective) -> weak scaling.
+metric   = B_alg / t in GB/s, B_alg = diag_polys*L'*N*8 + s*nbr*2*6*N*8 + s*m_ct*2*L'*N*8
+value    = inputs already resident in HBM
+e2e      = the same call through the C ABI with pinned HOST buffers for A and out (H2D + D2H inside the timed region)
+e2e_ptrs = the same through the entry point the cgo shim binds: one PAGEABLE host array per limb (what Go hands over)
+verify   = inputs are REAL encryptions of a known matrix A under seeded keys; after the timed region a few output ciphertexts are
+           decrypted and compared with A.X (tolerance 1e-3 relative to max |A.X|): the number carries its own correctness proof.
+           Key generation / encryption / decryption are the Go side's job in the reference; here they come from the CPU oracle in its
+           checker role (never inside a timed region).
+Multi-GPU (--gpus N under torchrun): STRONG scaling of the same product -- giant-step sharding (sfgwas_b200.dist.GiantSharded): every
+rank holds 1/N of the diagonal cache, computes the partial sum over its giant steps and the partial outputs are combined by a
+modular-add all-reduce over NVLink (NCCL integer SUM + canonicalisation kernel) inside the timed region.
 """
 import argparse
 import ctypes as C
@@ -34,12 +42,20 @@ PN14 = dict(logN=14, Q=[0x200000008001, 0x400018001, 0x3FFFD0001, 0x400060001, 0
                          0x400108001, 0x3FFEB8001], P=[0x7FFFFFD8001, 0x7FFFFFC8001], scale=float(1 << 34))
 CKKS = {"PN13QP218": PN13, "PN14QP438": PN14}
 WORKLOADS = {
-    # name: (nrows, ncols, s, CKKS parameter set)
-    "mm_10k_x_100k_k10_logN13": (10000, 100000, 10, "PN13QP218"),
-    "mm_2k_x_20k_k10_logN13": (2000, 20000, 10, "PN13QP218"),   # quick check only
-    # a PCA-shaped block (BASELINE configs 4/5 run at logN 14, kp = 15): extra data point, not the default bench line
-    "mm_16k_x_64k_k15_logN14": (16384, 65536, 15, "PN14QP438"),
+    # name: nrows, ncols, s, CKKS parameter set, orientation label, otf = force the non-materialised (encode-on-the-fly) path
+    "mm_10k_x_100k_k10_logN13": dict(nrows=10000, ncols=100000, s=10, params="PN13QP218", orientation="A.X"),
+    # config 2 transposed (SURVEY 8d-2 "both orientations"): 25 block rows -> K = 1 600 baby-step slots = 7 K groups, 15 750 baby rotations
+    "mm_100k_x_10k_k10_logN13_T": dict(nrows=100000, ncols=10000, s=10, params="PN13QP218", orientation="A'.X^T"),
+    "mm_2k_x_20k_k10_logN13": dict(nrows=2000, ncols=20000, s=10, params="PN13QP218", orientation="A.X"),   # quick check only
+    # PCA-shaped blocks (BASELINE configs 4 / 5 run at logN 14, kp = 15)
+    "mm_16k_x_64k_k15_logN14": dict(nrows=16384, ncols=65536, s=15, params="PN14QP438", orientation="Q.X^T slice"),
+    # the regime of configs 4 / 5: the cache cannot be HBM-resident, every call re-encodes the diagonals chunk by chunk
+    "mm_10k_x_100k_k10_logN13_otf": dict(nrows=10000, ncols=100000, s=10, params="PN13QP218", orientation="A.X", otf=True),
+    "mm_16k_x_64k_k15_logN14_otf": dict(nrows=16384, ncols=65536, s=15, params="PN14QP438", orientation="Q.X^T slice", otf=True),
+    "mm_32k_x_128k_k15_logN14_otf": dict(nrows=32768, ncols=131072, s=15, params="PN14QP438", orientation="Q.X^T slice (config 4, 4 x 16 of 13 x 62 blocks)", otf=True),
 }
+# complete small call the CPU arm times (same parameter set and s; one block row): (nrows, ncols)
+CPU_SAMPLE = {"PN13QP218": (4096, 8192), "PN14QP438": (8192, 8192)}
 
 
 def work_figures(nrows, ncols, s, logN, maxLevel=5):
@@ -72,20 +88,24 @@ def read_peaks():
 
 
 def read_traffic():
-    """dram__bytes_read.sum + dram__bytes_write.sum of one k_mac_tc launch from the committed ncu --set full capture
-    (profiles/r1_final/ncu_k_mac_tc.txt, same workload); None when the summary is missing."""
-    try:
-        rd = wr = None
-        with open(os.path.join(ROOT, "profiles", "r1_final", "ncu_k_mac_tc.txt")) as f:
-            for ln in f:
-                t = ln.split()
-                if len(t) >= 3 and t[0] == "dram__bytes_read.sum" and rd is None:
-                    rd = float(t[1]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}[t[2]]
-                if len(t) >= 3 and t[0] == "dram__bytes_write.sum" and wr is None:
-                    wr = float(t[1]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}[t[2]]
-        return None if rd is None or wr is None else rd + wr
-    except Exception:
-        return None
+    """dram__bytes_read.sum + dram__bytes_write.sum of one k_mac_tc launch from the committed ncu --set full capture of the default
+    workload (newest round first); None when no summary is found."""
+    for tag in ("r2", "r1_final"):
+        path = os.path.join(ROOT, "profiles", tag, "ncu_k_mac_tc.txt")
+        try:
+            rd = wr = None
+            with open(path) as f:
+                for ln in f:
+                    t = ln.split()
+                    if len(t) >= 3 and t[0] == "dram__bytes_read.sum" and rd is None:
+                        rd = float(t[1]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}[t[2]]
+                    if len(t) >= 3 and t[0] == "dram__bytes_write.sum" and wr is None:
+                        wr = float(t[1]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}[t[2]]
+            if rd is not None and wr is not None:
+                return rd + wr, "ncu --set full, profiles/%s/ncu_k_mac_tc.txt (dram read + write per launch)" % tag
+        except Exception:
+            pass
+    return None, None
 
 
 class ClockSampler:
@@ -137,68 +157,123 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------------------------
-# CPU baseline: the reference's algorithm (oracle port, gwas/matmult.go:1138-1236) on a BOUNDED sample of the workload
+# Checker role of the CPU oracle: what the Go side of the reference supplies (keys, encryption) and verifies (decryption)
 # ------------------------------------------------------------------------------------------------------------------
-def cpu_sample(wf, s, nthreads, mac_diags=12288, rots_per_thread=12, P=None):
-    """Times (i) the K1 lazy-MAC loop with the reference's per-(row, giant) locks on `mac_diags` diagonal polynomials
-    resident in RAM, and (ii) level-5 / level-4 rotations (key-switch + automorphism) on all threads; extrapolates linearly
-    to the full call.  Returns (GB/s, description)."""
+def real_inputs(P, nrows, s, seed=1):
+    """Seeded secret key, BSGS Galois keys and a real encryption A of a known s x nrows matrix (level 5, scale = params.Scale)."""
     import numpy as np
 
     from oracle.oracle import Oracle
 
-    o = Oracle.from_params(P or PN13)
-    t_mac = o.L.orc_bench_mac(o.N, 5, s, mac_diags, nthreads)
-    mac_rate = mac_diags * s * 2 * 5 * o.N / t_mac
-    sk = o.keygen_secret(1)
-    swk = o.gen_rotation_key(sk, 1)
-    rng = np.random.default_rng(0)
-    times = {}
-    for level in (5, 4):
-        cts = [np.stack([np.stack([rng.integers(0, o.Q[l], o.N, dtype=np.uint64) for l in range(level + 1)]) for _ in range(2)])
-               for _ in range(nthreads)]
+    o = Oracle.from_params(P)
+    sk = o.keygen_secret(seed)
+    keys = o.gen_bsgs_keys(sk)
+    rng = np.random.default_rng(seed)
+    Ap = rng.normal(size=(s, nrows))
+    nbr = (nrows - 1) // o.slots + 1
+    A = np.zeros((s, nbr, 2, 6, o.N), dtype=np.uint64)
+    for i in range(s):
+        for b in range(nbr):
+            A[i, b] = o.encrypt_vector(sk, Ap[i, b * o.slots:(b + 1) * o.slots], 5, seed=1000 + 131 * i + b)
+    return o, sk, keys, Ap, A
 
-        def work(t):
-            for _ in range(rots_per_thread):
-                o.rotate_right(cts[t], -1, swk)
 
-        th = [threading.Thread(target=work, args=(t,)) for t in range(nthreads)]
+def verify_decrypt(o, sk, Ap, xcols, out, picks):
+    """decrypt(out[i][bj]) ~= (A_plain . X)[i, columns of bj] for the picked (i, bj); xcols[bj] = those columns of X as float64."""
+    import numpy as np
+
+    worst, scale_ref = 0.0, 1.0
+    for i, bj in picks:
+        ref = Ap[i] @ xcols[bj]
+        got = o.decrypt_vector(sk, out[i, bj], o.scale * o.scale).real[: len(ref)]
+        worst = max(worst, float(np.abs(got - ref).max()))
+        scale_ref = max(scale_ref, float(np.abs(ref).max()))
+    tol = 1e-3 * scale_ref
+    return dict(decrypt_max_abs_err=worst, tolerance=tol, max_abs_reference=scale_ref, checked=[list(p) for p in picks], ok=bool(worst < tol))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# CPU arm: the reference's algorithm (oracle port of gwas/matmult.go:1043-1236) -- ONE COMPLETE MatMult4StreamCompute per step on a
+# bounded sample of the workload (same parameter set, same s, one block row), cache resident in RAM, all host cores
+# ------------------------------------------------------------------------------------------------------------------
+class CpuSample:
+    def __init__(self, pname, s):
+        import numpy as np
+
+        from oracle.oracle import Oracle
+
+        self.P = CKKS[pname]
+        self.nthreads = os.cpu_count() or 1
+        self.nrows, self.ncols = CPU_SAMPLE[pname]
+        self.s = s
+        o = self.o = Oracle.from_params(self.P)
+        self.wf = work_figures(self.nrows, self.ncols, s, self.P["logN"])
+        rng = np.random.default_rng(7)
+        maf = rng.uniform(0.05, 0.5, self.ncols)
+        X = (rng.random((self.nrows, self.ncols)) < maf).astype(np.int8) + (rng.random((self.nrows, self.ncols)) < maf).astype(np.int8)
+        sk = o.keygen_secret(3)
+        self.keys = o.gen_bsgs_keys(sk)
+        nbr = self.wf["nbr"]
+        self.A = np.zeros((s, nbr, 2, 6, o.N), dtype=np.uint64)
+        for i in range(s):
+            for b in range(nbr):
+                self.A[i, b] = o.encrypt_vector(sk, rng.normal(size=o.slots), 5, seed=50 + 13 * i + b)
         t0 = time.perf_counter()
-        for x in th:
-            x.start()
-        for x in th:
-            x.join()
-        times[level] = (time.perf_counter() - t0) / (nthreads * rots_per_thread)  # seconds per rotation at full occupancy
-    t_full = wf["mac_alg"] / mac_rate + wf["ks_baby"] * times[5] + wf["ks_giant"] * times[4]
-    desc = ("oracle port of MatMult4StreamCompute: K1 lazy MAC on %d of %d diagonal polys (RAM-resident, %d threads, per-(row,giant) "
-            "mutex) = %.2f GMAC/s; %d+%d rotations timed (%.1f / %.1f ms each at level 5 / 4 with all threads busy); extrapolated "
-            "linearly to %d MAC-polys + %d + %d rotations" % (mac_diags, wf["diag_polys"], nthreads, mac_rate / 1e9,
-                                                              nthreads * rots_per_thread, nthreads * rots_per_thread,
-                                                              times[5] * 1e3 * nthreads, times[4] * 1e3 * nthreads,
-                                                              wf["diag_polys"], wf["ks_baby"], wf["ks_giant"]))
-    return wf["b_alg"] / t_full / 1e9, t_full, desc
+        self.dc = o.preprocess(X, 5, nproc=self.nthreads)  # MatMult4StreamPreprocess: not part of a step (like the GPU arm's cache)
+        self.t_prep = time.perf_counter() - t0
+
+    def step(self):
+        t0 = time.perf_counter()
+        _, ph = self.o.compute(self.A, self.dc, self.keys, 5, nproc=self.nthreads, timings=True)
+        return time.perf_counter() - t0, ph
+
+    def describe(self, full_wf, t, ph):
+        wf = self.wf
+        ksb = (wf["ks_baby"] + wf["ks_giant"]) / wf["diag_polys"]
+        ksf = (full_wf["ks_baby"] + full_wf["ks_giant"]) / full_wf["diag_polys"]
+        # the same measured phases scaled to the full workload's structure (context only; `value` is the measured sample itself)
+        t_full = (ph[0] * full_wf["ks_baby"] / wf["ks_baby"] + ph[1] * full_wf["diag_polys"] / wf["diag_polys"]
+                  + ph[2] * full_wf["ks_giant"] / wf["ks_giant"])
+        desc = ("ONE COMPLETE MatMult4StreamCompute of the oracle port (gwas/matmult.go:1043-1236: baby rotations, K1 lazy MAC under the "
+                "per-(row, giant) mutexes, K2 reduce, giant rotations, sum) per step on a %d x %d sample (same CKKS set, s = %d, %d x %d "
+                "blocks, %d diagonal polys resident in RAM, %d + %d key-switches), %d threads: %.2f s = baby %.2f + MAC %.2f + giant %.2f; "
+                "value = B_alg(sample) / t(sample), nothing extrapolated.  The sample has %.1fx more key-switches per algorithmic byte than "
+                "the full workload, so it UNDERSTATES the CPU: scaling the measured phases to the full workload's structure gives %.2f GB/s "
+                "(est_full_workload_gbs)." % (self.nrows, self.ncols, self.s, wf["nbr"], wf["m_ct"], wf["diag_polys"], wf["ks_baby"],
+                                              wf["ks_giant"], self.nthreads, t, ph[0], ph[1], ph[2], ksb / ksf, full_wf["b_alg"] / t_full / 1e9))
+        return desc, full_wf["b_alg"] / t_full / 1e9
+
+    def close(self):
+        self.o.cache_free(self.dc)
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    nrows, ncols, s, pname = WORKLOADS[args.workload]
-    wf = work_figures(nrows, ncols, s, CKKS[pname]["logN"])
-    nthreads = os.cpu_count() or 1
-    vals, t0 = [], time.perf_counter()
+    w = WORKLOADS[args.workload]
+    full_wf = work_figures(w["nrows"], w["ncols"], w["s"], CKKS[w["params"]]["logN"])
+    t_start = time.perf_counter()
+    cs = CpuSample(w["params"], w["s"])
+    times, phases = [], []
     for it in range(args.warmup + args.steps):
-        v, t_full, desc = cpu_sample(wf, s, nthreads, P=CKKS[pname])
+        t, ph = cs.step()
         if it >= args.warmup:
-            vals.append((v, t_full))
-    v = sum(x[0] for x in vals) / len(vals)
-    t_full = sum(x[1] for x in vals) / len(vals)
+            times.append(t)
+            phases.append(ph)
+    t = sum(times) / len(times)
+    ph = [sum(p[k] for p in phases) / len(phases) for k in range(3)]
+    v = cs.wf["b_alg"] / t / 1e9
+    desc, est_full = cs.describe(full_wf, t, ph)
     line = dict(metric="genotype x ciphertext MatMult GB/s (B_alg / t)", value=v, unit="GB/s", n_gpus=args.gpus, steps=args.steps,
-                warmup=args.warmup, ms_per_step=t_full * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="u64",
+                warmup=args.warmup, ms_per_step=t * 1e3, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="u64",
                 data="synthetic", impl="reference",
-                config=dict(workload=args.workload, ckks_params=pname, orientation="A.X", s=s, note="CPU arm: the per-GPU workload timed on the host cores of the box (rank 0 only)"),
-                cpu_baseline=dict(value=v, unit="GB/s", cores=nthreads, kind="port", sample=desc),
+                config=dict(workload=args.workload, ckks_params=w["params"], orientation=w["orientation"], s=w["s"],
+                            note="CPU arm (rank 0 only): a complete call on a bounded sample of the workload, see cpu_baseline.sample",
+                            sample_rows=cs.nrows, sample_cols=cs.ncols, sample_b_alg_bytes=cs.wf["b_alg"], preprocess_s=cs.t_prep),
+                cpu_baseline=dict(value=v, unit="GB/s", cores=cs.nthreads, kind="port", sample=desc, est_full_workload_gbs=est_full),
                 e2e=dict(value=v, unit="GB/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
-                wall_s=time.perf_counter() - t0)
+                wall_s=time.perf_counter() - t_start)
+    cs.close()
     print(json.dumps(line), flush=True)
 
 
@@ -208,69 +283,126 @@ def run_ours(args, rank, local_rank, world):
     import torch
     import torch.distributed as dist
 
-    from sfgwas_b200 import CryptoParams, SfgError
+    from sfgwas_b200 import CryptoParams
+    from sfgwas_b200.dist import ct_mod_allreduce_, partition
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    nrows, ncols, s, pname = WORKLOADS[args.workload]
+    w = WORKLOADS[args.workload]
+    nrows, ncols, s, pname = w["nrows"], w["ncols"], w["s"], w["params"]
     P = CKKS[pname]
     wf = work_figures(nrows, ncols, s, P["logN"])
     N, slots, d, nbr, m_ct = wf["N"], wf["slots"], wf["d"], wf["nbr"], wf["m_ct"]
     cps = CryptoParams(P["logN"], P["Q"], P["P"], P["scale"], device=local_rank)
     L = cps.L
     mods = P["Q"] + P["P"]
-    gen = torch.Generator(device=dev)
-    gen.manual_seed(1234 + rank)
+    # The library's stream is NON-BLOCKING: it is not ordered after torch's default stream.  Everything torch produces for the library
+    # (the genotype chunks, synthetic keys) is therefore generated ON the library's stream.  (Round 1 generated the genotypes on torch's
+    # stream and pushed them unsynchronised: the pushes raced the generator -- harmless for random data, caught by the decrypt check.)
+    ext = torch.cuda.ExternalStream(L.sfg_ctx_stream(cps.h), device=dev)
+    torch.cuda.set_stream(ext)
+    otf = bool(w.get("otf")) or args.cache_budget_gb is not None
+    if otf:
+        cps.set_cache_budget(int((args.cache_budget_gb if args.cache_budget_gb is not None else 0.001) * 1e9))
 
-    def rand_res(shape_prefix, limb_ids):
-        out = torch.empty(*shape_prefix, len(limb_ids), N, dtype=torch.int64, device=dev)
-        for k, li in enumerate(limb_ids):
-            out[..., k, :] = torch.randint(0, mods[li], (*shape_prefix, N), generator=gen, device=dev, dtype=torch.int64)
-        return out
+    # ---- inputs: real keys and a real encryption of a known A (identical on every rank: same seeds), or uniformly random residues ----
+    real = not args.synthetic_inputs
+    t0 = time.perf_counter()
+    if real:
+        o, sk, keys, Ap, A_np = real_inputs(P, nrows, s)
+        for k, v in keys.items():
+            cps.SetRotKey(k, v)
+        del keys
+        d_A = torch.from_numpy(A_np.view(np.int64)).to(dev)
+    else:
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(1234)
 
-    # Galois keys for the BSGS rotations (crypto/crypto.go:251-264): left rotations 1..d-1 and d, 2d, ...
-    rots = sorted(set(range(1, d)) | {g * d for g in range(1, d) if g * d < slots})
-    for k in rots:
-        key = rand_res((cps.beta, 2), list(range(cps.nQP)))
-        cps._check(L.sfg_ctx_set_rotation_key(cps.h, k, C.c_void_p(key.data_ptr())), "set_rotation_key")
-    del key
-    # genotype matrix on the device, pushed through the ABI in row chunks
+        def rand_res(shape_prefix, limb_ids):
+            out = torch.empty(*shape_prefix, len(limb_ids), N, dtype=torch.int64, device=dev)
+            for k, li in enumerate(limb_ids):
+                out[..., k, :] = torch.randint(0, mods[li], (*shape_prefix, N), generator=gen, device=dev, dtype=torch.int64)
+            return out
+
+        # Galois keys for the BSGS rotations (crypto/crypto.go:251-264): left rotations 1..d-1 and d, 2d, ...
+        for k in sorted(set(range(1, d)) | {g * d for g in range(1, d) if g * d < slots}):
+            key = rand_res((cps.beta, 2), list(range(cps.nQP)))
+            cps._check(L.sfg_ctx_set_rotation_key(cps.h, k, C.c_void_p(key.data_ptr())), "set_rotation_key")
+        d_A = rand_res((s, nbr, 2), list(range(6)))
+    t_inputs = time.perf_counter() - t0
+
+    # ---- genotype matrix on the device (same on every rank), pushed through the ABI in row chunks; the block columns used by the
+    #      decrypt check are kept on the host ----
     g = C.c_void_p()
     cps._check(L.sfg_geno_create(cps.h, nrows, ncols, C.byref(g)), "geno_create")
     gx = torch.Generator(device=dev)
-    gx.manual_seed(1 + rank)
+    gx.manual_seed(1)
     maf = torch.rand(ncols, generator=gx, device=dev) * 0.45 + 0.05
+    picks = sorted({(0, 0), (s // 2, m_ct // 2), (s - 1, m_ct - 1)})
+    xcols = {bj: [] for _, bj in picks}
     for r0 in range(0, nrows, 512):
         r1 = min(nrows, r0 + 512)
         x = (torch.rand(r1 - r0, ncols, generator=gx, device=dev) < maf).to(torch.int8) + \
             (torch.rand(r1 - r0, ncols, generator=gx, device=dev) < maf).to(torch.int8)
         cps._check(L.sfg_geno_push_rows(g, C.c_void_p(x.data_ptr()), r1 - r0), "geno_push_rows")
+        if real and rank == 0:
+            for bj in xcols:
+                xcols[bj].append(x[:, bj * slots:(bj + 1) * slots].cpu().numpy().astype(np.float64))
     del x
+    xcols = {bj: np.concatenate(v) for bj, v in xcols.items()} if real and rank == 0 else {}
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     cache = C.c_void_p()
-    cps._check(L.sfg_matmult4_stream_preprocess(cps.h, g, 5, C.byref(cache)), "preprocess")
+    if world > 1:
+        cps._check(L.sfg_matmult4_stream_preprocess_giants(cps.h, g, 5, rank, world, C.byref(cache)), "preprocess_giants")
+    else:
+        cps._check(L.sfg_matmult4_stream_preprocess(cps.h, g, 5, C.byref(cache)), "preprocess")
     t_prep = time.perf_counter() - t0
     npoly, cbytes, mat = C.c_size_t(), C.c_size_t(), C.c_int()
     L.sfg_cache_info(cache, C.byref(npoly), C.byref(cbytes), C.byref(mat), None, None)
     assert npoly.value == wf["diag_polys"], (npoly.value, wf["diag_polys"])
+    assert bool(mat.value) != otf or cbytes.value == 0, "cache materialisation does not match the workload (otf=%s)" % otf
 
-    d_A = rand_res((s, nbr, 2), list(range(6)))
     d_out = torch.zeros(s, m_ct, 2, 5, N, dtype=torch.int64, device=dev)
     h_A = torch.empty(d_A.shape, dtype=torch.int64, pin_memory=True)
     h_A.copy_(d_A)
     h_out = torch.empty(d_out.shape, dtype=torch.int64, pin_memory=True)
-    ext = torch.cuda.ExternalStream(L.sfg_ctx_stream(cps.h), device=dev)
+    row_lo, row_hi = partition(s, world)[rank]  # e2e at N > 1: every rank reads back its stripe of output rows
 
-    def step_dev():
+    def compute_dev():
         cps._check(L.sfg_matmult4_stream_compute_dev(cps.h, C.c_void_p(d_A.data_ptr()), s, nbr, 5, 5, cache, C.c_void_p(d_out.data_ptr())),
                    "compute_dev")
 
+    def step_dev():
+        compute_dev()
+        if world > 1:  # partial sums over this rank's giant steps -> the full product on every rank (modular-add all-reduce over NVLink)
+            ct_mod_allreduce_(d_out, cps, 5)
+
     def step_e2e():
-        cps._check(L.sfg_matmult4_stream_compute(cps.h, C.c_void_p(h_A.data_ptr()), s, nbr, 5, 5, cache, C.c_void_p(h_out.data_ptr())),
-                   "compute")
+        if world == 1:
+            cps._check(L.sfg_matmult4_stream_compute(cps.h, C.c_void_p(h_A.data_ptr()), s, nbr, 5, 5, cache, C.c_void_p(h_out.data_ptr())),
+                       "compute")
+            return
+        d_A.copy_(h_A, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        step_dev()
+        if row_hi > row_lo:
+            h_out[row_lo:row_hi].copy_(d_out[row_lo:row_hi], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    # the entry point the cgo shim binds: one pageable array per limb for A and for the result
+    a_limbs = o_limbs = None
+    if world == 1:
+        a_host = h_A.numpy().reshape(-1, N)
+        a_limbs = [np.array(a_host[k], copy=True) for k in range(a_host.shape[0])]
+        o_limbs = [np.empty(N, dtype=np.int64) for _ in range(s * m_ct * 2 * 5)]
+        a_ptrs = (C.c_void_p * len(a_limbs))(*[x.ctypes.data for x in a_limbs])
+        o_ptrs = (C.c_void_p * len(o_limbs))(*[x.ctypes.data for x in o_limbs])
+
+    def step_ptrs():
+        cps._check(L.sfg_matmult4_stream_compute_ptrs(cps.h, a_ptrs, s, nbr, 5, 5, cache, o_ptrs), "compute_ptrs")
 
     def barrier():
         torch.cuda.synchronize()
@@ -303,53 +435,95 @@ def run_ours(args, rank, local_rank, world):
             ms = float(tt.item())
         return ms, cps.launch_count() - launches0, mac_ms, phases, clocks
 
+    # torch copies and NCCL collectives are ordered on (and timed with) the library's stream (set as torch's current stream above)
     for _ in range(args.warmup):
         step_dev()
     ms, launches, mac_ms, phases, clocks = timed(step_dev, args.steps, sample_clocks=True)
     for _ in range(max(1, args.warmup - 2)):
         step_e2e()
     ms_e2e, _, _, _, _ = timed(step_e2e, args.steps)
+    ms_ptrs = None
+    if world == 1:
+        for _ in range(max(1, args.warmup - 2)):
+            step_ptrs()
+        ms_ptrs, _, _, _, _ = timed(step_ptrs, args.steps)
+    barrier()
     enc_stats = cps.encoder_stats()
+
+    # ---- correctness of what was just timed (outside the timed region) ----
+    verify = None
+    if world > 1:  # the host copy is striped over the ranks: gather the stripes on rank 0 for the check
+        h_full = d_out.cpu()
+    if real and rank == 0:
+        out_np = (h_out if world == 1 else h_full).numpy().view(np.uint64)
+        verify = verify_decrypt(o, sk, Ap, xcols, out_np, picks)
+        verify["dev_equals_e2e"] = bool((d_out.cpu().numpy().view(np.uint64) == out_np).all())
+        if world == 1:
+            verify["ptrs_equals_flat"] = bool((np.stack(o_limbs).reshape(out_np.shape).view(np.uint64) == out_np).all())
+        if not (verify["ok"] and verify["dev_equals_e2e"] and verify.get("ptrs_equals_flat", True)):
+            print(json.dumps(dict(error="verification failed", verify=verify)), flush=True)
+            sys.exit(1)
 
     if rank == 0:
         peak, peak_src = read_peaks()
         t_step = ms / args.steps / 1e3
-        value = world * wf["b_alg"] / t_step / 1e9
-        e2e_v = world * wf["b_alg"] / (ms_e2e / args.steps / 1e3) / 1e9
+        value = wf["b_alg"] / t_step / 1e9
+        e2e_v = wf["b_alg"] / (ms_e2e / args.steps / 1e3) / 1e9
         mac_avg_s = mac_ms / args.steps / 1e3
-        mac_gbs = wf["b_diag"] / mac_avg_s / 1e9
+        # the roofline kernel streams this rank's share of the diagonals (1 / world of them under giant-step sharding)
+        mac_gbs = wf["b_diag"] / world / mac_avg_s / 1e9
+        traffic, traffic_src = read_traffic()
+        ph = {k: v / args.steps for k, v in phases.items()}
+        if otf:
+            ph["encode_ms"] = ph["mac_ms"] - mac_ms / args.steps  # diagonal re-encoding + image build inside the MAC phase
         line = dict(
             metric="genotype x ciphertext MatMult GB/s (B_alg / t)", value=value, unit="GB/s", n_gpus=world, steps=args.steps,
-            warmup=args.warmup, ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="u64",
+            warmup=args.warmup, ms_per_step=ms / args.steps, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="u64",
             data="synthetic",
-            config=dict(workload=args.workload, ckks_params=pname, logN=P["logN"], s=s, orientation="A.X", max_level=5,
+            config=dict(workload=args.workload, ckks_params=pname, logN=P["logN"], s=s, orientation=w["orientation"], max_level=5,
                         num_block_rows=nbr, m_ct=m_ct, diag_polys=wf["diag_polys"], b_alg_bytes=wf["b_alg"], mac_alg=wf["mac_alg"],
-                        key_switches=[wf["ks_baby"], wf["ks_giant"]], step="MatMult4StreamCompute over the HBM-resident diagonal cache",
-                        cache_bytes=cbytes.value, cache_materialised=bool(mat.value), preprocess_s=t_prep,
-                        l2_policy="inputs (%.1f GB cache) larger than L2; no flush needed" % (cbytes.value / 1e9),
-                        sharding="SNP-block (block-column) per rank, no collective" if world > 1 else "single GPU",
+                        key_switches=[wf["ks_baby"], wf["ks_giant"]],
+                        step="MatMult4StreamCompute over the HBM-resident diagonal cache" if not otf else
+                             "MatMult4StreamCompute with the diagonals re-encoded from the int8 genotypes inside every call (cache over budget)",
+                        cache_bytes=cbytes.value, cache_materialised=bool(mat.value), preprocess_s=t_prep, input_setup_s=t_inputs,
+                        inputs="real encryptions of a known matrix under seeded keys (decrypt-checked, see verify)" if real else
+                               "uniformly random residues",
+                        l2_policy="inputs (%.1f GB cache per rank) larger than L2; no flush needed" % (cbytes.value / 1e9) if not otf else
+                                  "every call streams freshly encoded diagonals (GBs per chunk) through HBM; larger than L2",
+                        sharding=("giant-step sharding of ONE product over %d ranks: 1/%d of the cache, MAC and giant-step key-switches per "
+                                  "rank, baby steps replicated, modular-add all-reduce of the %d output ciphertexts (NCCL SUM + mod q) inside "
+                                  "the timed region" % (world, world, s * m_ct)) if world > 1 else "single GPU",
                         encoder_rechecked_coeffs=enc_stats[0], encoder_unresolved=enc_stats[1]),
             e2e=dict(value=e2e_v, unit="GB/s", ms_per_step=ms_e2e / args.steps, h2d_bytes_per_step=int(h_A.numel() * 8),
-                     d2h_bytes_per_step=int(h_out.numel() * 8)),
+                     d2h_bytes_per_step=int(h_out.numel() * 8) if world == 1 else int(h_out[row_lo:row_hi].numel() * 8),
+                     path="sfg_matmult4_stream_compute (pinned host A and out, D2H overlapped with the giant-step sums)" if world == 1 else
+                          "per rank: pinned A -> device, compute + all-reduce, this rank's stripe of output rows -> pinned host"),
             gpu_launches=int(launches),
             roofline=dict(bound="hbm", kernel="k_mac_tc (K1+K2: tcgen05 kind::i8 byte-plane MAC + recombine + modular reduce)",
                           achieved=mac_gbs, peak=peak, unit="GB/s", frac=mac_gbs / peak,
-                          traffic=read_traffic() if args.workload == "mm_10k_x_100k_k10_logN13" else None,  # the capture is of the default workload
-                          traffic_source="ncu --set full, profiles/r1_final/ncu_k_mac_tc.txt (dram read + write per launch)",
-                          peak_source=peak_src + " (MEASURED_PEAKS.json hbm_gbs)",
-                          algorithmic_bytes_per_launch=wf["b_diag"], stored_bytes_per_launch=int(cbytes.value),
+                          traffic=traffic if args.workload == "mm_10k_x_100k_k10_logN13" and world == 1 else None,  # the capture is of the default workload
+                          traffic_source=traffic_src, peak_source=peak_src + " (MEASURED_PEAKS.json hbm_gbs)",
+                          algorithmic_bytes_per_launch=wf["b_diag"] // world, stored_bytes_per_launch=int(cbytes.value),
                           avg_launch_ms=mac_avg_s * 1e3, share_of_step=mac_ms / ms,
                           note="algorithmic bytes count 8 B per cached residue (the reference's streamed volume); the image stores "
-                               "4-5 byte planes per residue, so achieved can exceed the copy peak; stored+written bytes / time is "
+                               "4-6 byte planes per residue, so achieved can exceed the copy peak; stored+written bytes / time is "
                                "the physical HBM rate"),
-            phases_ms_per_step={k: v / args.steps for k, v in phases.items()},
-            int8_genotype_gbs=world * nrows * ncols / t_step / 1e9, gmacs_per_s=world * wf["mac_alg"] / t_step / 1e9,
-            clocks=clocks,
+            phases_ms_per_step=ph,
+            whole_step_hbm_frac=value / world / peak,
+            int8_genotype_gbs=nrows * ncols / t_step / 1e9, gmacs_per_s=wf["mac_alg"] / t_step / 1e9,
+            clocks=clocks, verify=verify,
         )
+        if ms_ptrs is not None:
+            line["e2e_ptrs"] = dict(value=wf["b_alg"] / (ms_ptrs / args.steps / 1e3) / 1e9, unit="GB/s", ms_per_step=ms_ptrs / args.steps,
+                                    path="sfg_matmult4_stream_compute_ptrs: one PAGEABLE host array per limb (%d in, %d out), the Go-side figure"
+                                         % (len(a_limbs), len(o_limbs)))
         if world == 1 and not args.no_cpu_baseline:
-            nthreads = os.cpu_count() or 1
-            v, t_full, desc = cpu_sample(wf, s, nthreads, P=P)
-            line["cpu_baseline"] = dict(value=v, unit="GB/s", cores=nthreads, kind="port", sample=desc, est_s_per_step=t_full)
+            cs = CpuSample(pname, s)
+            t, phs = cs.step()
+            desc, est_full = cs.describe(wf, t, phs)
+            line["cpu_baseline"] = dict(value=cs.wf["b_alg"] / t / 1e9, unit="GB/s", cores=cs.nthreads, kind="port", sample=desc,
+                                        est_full_workload_gbs=est_full)
+            cs.close()
         print(json.dumps(line), flush=True)
     L.sfg_cache_destroy(cache)
     L.sfg_geno_destroy(g)
@@ -366,6 +540,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="mm_10k_x_100k_k10_logN13", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--synthetic-inputs", action="store_true", help="uniformly random residues instead of real keys / encryptions (no decrypt check)")
+    ap.add_argument("--cache-budget-gb", type=float, default=None, help="HBM budget of the diagonal cache; below the image size the diagonals are re-encoded on the fly")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

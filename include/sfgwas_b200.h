@@ -103,6 +103,15 @@ int sfg_cache_get_diag(sfg_ctx *ctx, const sfg_cache *cache, int block_row, int 
 int sfg_cache_write_files(sfg_ctx *ctx, const sfg_cache *cache, const char *prefix);
 int sfg_cache_load_files(sfg_ctx *ctx, const char *prefix, size_t nrows, size_t ncols, int max_level, sfg_cache **out);
 
+/* crypto.SaveCipherMatrixToFile / LoadCipherMatrixFromFile (crypto/utilities.go:82-141): the on-disk CipherMatrix of
+ * `assoc_cache_mult.%d.bin` (gwas/assoc.go:317-333,434-437) and `Qcomb.bin` -- {u32 nrows, u32 ncols, u64 len(sizes), sizes, u64 len(blob),
+ * blob = concatenated Ciphertext.MarshalBinary()}, coefficients big-endian -- so MatMult outputs of a GPU run and of a CPU run of the
+ * reference interoperate.  Host-only (no context, no device): cts [nrows][ncols][2][level+1][N], scales [nrows][ncols] (ct.Scale());
+ * all ciphertexts of degree 1 at one level.  Errors: non-zero return, message from sfg_last_error(NULL). */
+int sfg_cipher_matrix_save(const char *filename, int logN, const uint64_t *cts, const double *scales, int nrows, int ncols, int level);
+int sfg_cipher_matrix_info(const char *filename, int *nrows, int *ncols, int *level, int *logN);
+int sfg_cipher_matrix_load(const char *filename, int logN, uint64_t *cts, double *scales, int nrows, int ncols, int level);
+
 /* MatMult4StreamCompute(cryptoParams, A, maxLevel, cacheFilePrefix) (gwas/matmult.go:1043-1236).
  * A: [s][num_block_rows][2][level_a+1][N]; out: [s][m_ct][2][max_level][N] = the deterministic sum
  * S[i][bj] = sum_g RotL_{g d}(reduce(acc[i][g])[bj]) at level max_level-1; the Go shim adds it into

@@ -212,6 +212,36 @@ def sweep_params(logN: int) -> dict:
     return dict(logN=logN, Q=q, P=p, scale=float(1 << sc))
 
 
+def marshal_ciphertext(value: np.ndarray, scale: float) -> bytes:
+    """Lattigo v2.1 ckks.Element.MarshalBinary [UNVERIFIED vs the fork; SURVEY App. B.8]: u8 degree+1, f64 LE scale, u8 isNTT, then per
+    polynomial ring.Poly.WriteTo = u8 log2(N), u8 numModuli, coefficients limb-major as 8-byte BIG-endian words (ring.WriteCoeffsTo)."""
+    import struct
+
+    deg1, nl, N = value.shape
+    out = [struct.pack("<BdB", deg1, float(scale), 1)]
+    for k in range(deg1):
+        out.append(struct.pack("<BB", int(N).bit_length() - 1, nl))
+        out.append(np.ascontiguousarray(value[k], dtype=">u8").tobytes())
+    return b"".join(out)
+
+
+def save_cipher_matrix(cm, filename: str):
+    """crypto.SaveCipherMatrixToFile (crypto/utilities.go:82-113) with MarshalCM (:35-56) and CipherMatrix/CipherVector.MarshalBinary
+    (crypto/crypto.go:542-595): cm[i][j] = (value [2][nl][N] uint64, scale)."""
+    import struct
+
+    blobs = [[marshal_ciphertext(v, sc) for (v, sc) in row] for row in cm]
+    sbytes = b"".join(struct.pack("<Q", len(b)) for row in blobs for b in row)      # MarshalCM: ctSizes as little-endian u64
+    cmbytes = b"".join(b for row in blobs for b in row)
+    with open(filename, "wb") as f:
+        f.write(struct.pack("<I", len(cm)))          # nrbuf
+        f.write(struct.pack("<I", len(cm[0])))       # ncbuf
+        f.write(struct.pack("<Q", len(sbytes)))      # sbuf
+        f.write(sbytes)
+        f.write(struct.pack("<Q", len(cmbytes)))     # cmbuf
+        f.write(cmbytes)
+
+
 class Oracle:
     """One CKKS ring context of the oracle (Lattigo ring.Ring + ckks.Parameters restated)."""
 

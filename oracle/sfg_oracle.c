@@ -173,8 +173,17 @@ uint64_t orc_ctx_psi(const orc_ctx *c, int i) { return c->psi[i]; }
 /* NTT: Lattigo ring.NTT / ring.InvNTT (App. B.3). Cooley-Tukey forward, Gentleman-Sande      */
 /* inverse, twiddles bit-reversed in Montgomery form, outputs canonical.                      */
 /* ------------------------------------------------------------------------------------------ */
+/* Evaluated like Lattigo's NTTLazy / InvNTTLazy: Harvey butterflies on values kept in [0, 4q) (forward) / [0, 2q) (inverse) with
+ * MRedConstant (no conditional subtraction inside the transform), one canonicalising pass at the end.  Outputs are the same canonical
+ * residues as the textbook butterflies (exact arithmetic mod q); only the CPU time differs, which matters for the CPU-baseline arm. */
+static inline uint64_t mred_lazy(uint64_t x, uint64_t y, uint64_t q, uint64_t qInv) { /* x*y*2^-64 mod q in (0, 2q), x*y < q*2^64 */
+    u128 m = (u128)x * y;
+    uint64_t hhi = (uint64_t)(((u128)((uint64_t)m * qInv) * q) >> 64);
+    return (uint64_t)(m >> 64) - hhi + q;
+}
+static inline uint64_t csub(uint64_t x, uint64_t m) { return x - (m & (0 - (uint64_t)(x >= m))); } /* branch-free x >= m ? x - m : x */
 void orc_ntt(const orc_ctx *c, int idx, uint64_t *a) {
-    const uint64_t q = c->mod[idx], qInv = c->mred[idx];
+    const uint64_t q = c->mod[idx], qInv = c->mred[idx], q2 = 2 * q;
     const uint64_t *psi = c->nttPsi[idx];
     int N = c->N, t = N;
     for (int m = 1; m < N; m <<= 1) {
@@ -183,15 +192,16 @@ void orc_ntt(const orc_ctx *c, int idx, uint64_t *a) {
             int j1 = 2 * i * t, j2 = j1 + t;
             uint64_t F = psi[m + i];
             for (int j = j1; j < j2; j++) {
-                uint64_t U = a[j], V = orc_mred(a[j + t], F, q, qInv);
-                a[j] = addmod(U, V, q);
-                a[j + t] = submod(U, V, q);
+                uint64_t U = csub(a[j], q2), V = mred_lazy(a[j + t], F, q, qInv); /* U, V in [0, 2q) */
+                a[j] = U + V;
+                a[j + t] = U - V + q2;
             }
         }
     }
+    for (int j = 0; j < N; j++) a[j] = csub(csub(a[j], q2), q);
 }
 void orc_intt(const orc_ctx *c, int idx, uint64_t *a) {
-    const uint64_t q = c->mod[idx], qInv = c->mred[idx];
+    const uint64_t q = c->mod[idx], qInv = c->mred[idx], q2 = 2 * q;
     const uint64_t *psi = c->nttPsiInv[idx];
     int N = c->N, t = 1;
     for (int m = N; m > 1; m >>= 1) {
@@ -200,9 +210,9 @@ void orc_intt(const orc_ctx *c, int idx, uint64_t *a) {
             int j2 = j1 + t;
             uint64_t F = psi[h + i];
             for (int j = j1; j < j2; j++) {
-                uint64_t U = a[j], V = a[j + t];
-                a[j] = addmod(U, V, q);
-                a[j + t] = orc_mred(submod(U, V, q), F, q, qInv);
+                uint64_t U = a[j], V = a[j + t]; /* in [0, 2q) */
+                a[j] = csub(U + V, q2);
+                a[j + t] = mred_lazy(U - V + q2, F, q, qInv);
             }
             j1 += t << 1;
         }
@@ -490,26 +500,30 @@ void orc_decrypt_coeffs(const orc_ctx *c, const uint64_t *sk, const uint64_t *ct
  * src residues x_k mod s_k (k < ns), coefficient-wise; y_k = x_k*(S/s_k)^-1 mod s_k;
  * v = (uint64) sum_k float64(y_k)/float64(s_k)  (float64, index order);
  * out_t = sum_k y_k*(S/s_k mod t) - v*S mod t.  */
-static void base_convert(const uint64_t *const *src, const uint64_t *smod, int ns, int N,
-                         uint64_t tmod, uint64_t *dst) {
-    uint64_t sOverSkInv[ORC_MAXMOD], sOverSkModT[ORC_MAXMOD], SmodT = 1;
+static void base_convert(const orc_ctx *c, const uint64_t *const *src, const int *sidx, int ns, int N, int tidx, uint64_t *dst) {
+    /* constants in Montgomery form so that every product is one MRed (as Lattigo's ring arithmetic does) instead of a 128/64 division;
+     * the float64 quotient estimate is evaluated exactly as before (division and sum in index order) */
+    uint64_t tmod = c->mod[tidx], tInv = c->mred[tidx];
+    uint64_t smod[ORC_MAXMOD], sOverSkInvM[ORC_MAXMOD], sOverSkModTM[ORC_MAXMOD], SmodT = 1;
+    for (int k = 0; k < ns; k++) smod[k] = c->mod[sidx[k]];
     for (int k = 0; k < ns; k++) {
         uint64_t prod = 1, prodT = 1;
         for (int j = 0; j < ns; j++) if (j != k) { prod = mulmod(prod, smod[j] % smod[k], smod[k]); prodT = mulmod(prodT, smod[j] % tmod, tmod); }
-        sOverSkInv[k] = invmod(prod, smod[k]);
-        sOverSkModT[k] = prodT;
+        sOverSkInvM[k] = orc_mform(invmod(prod, smod[k]), smod[k], c->bred[sidx[k]]);
+        sOverSkModTM[k] = orc_mform(prodT, tmod, c->bred[tidx]);
         SmodT = mulmod(SmodT, smod[k] % tmod, tmod);
     }
+    uint64_t SmodTM = orc_mform(SmodT, tmod, c->bred[tidx]);
     for (int x = 0; x < N; x++) {
         double vi = 0.0;
         uint64_t acc = 0;
         for (int k = 0; k < ns; k++) {
-            uint64_t y = mulmod(src[k][x] % smod[k], sOverSkInv[k], smod[k]);
+            uint64_t y = orc_mred(src[k][x], sOverSkInvM[k], smod[k], c->mred[sidx[k]]); /* src is canonical mod s_k */
             vi += (double)y / (double)smod[k];
-            acc = addmod(acc, mulmod(y % tmod, sOverSkModT[k], tmod), tmod);
+            acc = addmod(acc, orc_mred(orc_bred_add(y, tmod, c->bred[tidx]), sOverSkModTM[k], tmod, tInv), tmod);
         }
         uint64_t v = (uint64_t)vi;
-        dst[x] = submod(acc, mulmod(v % tmod, SmodT, tmod), tmod);
+        dst[x] = submod(acc, orc_mred(orc_bred_add(v, tmod, c->bred[tidx]), SmodTM, tmod, tInv), tmod);
     }
 }
 
@@ -528,8 +542,8 @@ void orc_keyswitch(const orc_ctx *c, int level, const uint64_t *c1, const uint64
     for (int i = 0; i < beta; i++) {
         int st = i * alpha, ed = st + alpha; if (ed > nl) ed = nl;
         int cnt = ed - st;
-        const uint64_t *src[ORC_MAXMOD]; uint64_t smod[ORC_MAXMOD];
-        for (int k = 0; k < cnt; k++) { src[k] = c2 + (size_t)(st + k) * PN; smod[k] = c->mod[st + k]; }
+        const uint64_t *src[ORC_MAXMOD]; int sidx[ORC_MAXMOD];
+        for (int k = 0; k < cnt; k++) { src[k] = c2 + (size_t)(st + k) * PN; sidx[k] = st + k; }
         const uint64_t *k0 = swk + ((size_t)i * 2 + 0) * nQP * PN;
         const uint64_t *k1 = swk + ((size_t)i * 2 + 1) * nQP * PN;
         for (int t = 0; t < nl + nP; t++) {
@@ -542,7 +556,7 @@ void orc_keyswitch(const orc_ctx *c, int level, const uint64_t *c1, const uint64
                 if (cnt == 1) { /* Decomposer.DecomposeAndSplit single-modulus path: BRedAdd of the representative */
                     for (int x = 0; x < N; x++) d[x] = orc_bred_add(src[0][x], q, c->bred[midx]);
                 } else {
-                    base_convert(src, smod, cnt, N, q, d);
+                    base_convert(c, src, sidx, cnt, N, midx, d);
                 }
                 orc_ntt(c, midx, d);
                 dn = d;
@@ -558,16 +572,16 @@ void orc_keyswitch(const orc_ctx *c, int level, const uint64_t *c1, const uint64
     /* ModDownSplitNTTPQ: out = (accQ - ext_{P->Q}(INTT(accP))) * P^-1 mod q */
     for (int comp = 0; comp < 2; comp++) {
         uint64_t *acc = comp ? acc1 : acc0, *out = comp ? out1 : out0;
-        const uint64_t *psrc[ORC_MAXMOD]; uint64_t pm[ORC_MAXMOD];
-        for (int p = 0; p < nP; p++) { orc_intt(c, nQ + p, acc + (size_t)(nl + p) * PN); psrc[p] = acc + (size_t)(nl + p) * PN; pm[p] = c->mod[nQ + p]; }
+        const uint64_t *psrc[ORC_MAXMOD]; int pidx[ORC_MAXMOD];
+        for (int p = 0; p < nP; p++) { orc_intt(c, nQ + p, acc + (size_t)(nl + p) * PN); psrc[p] = acc + (size_t)(nl + p) * PN; pidx[p] = nQ + p; }
         for (int l = 0; l < nl; l++) {
             uint64_t q = c->mod[l];
-            base_convert(psrc, pm, nP, N, q, d);
+            base_convert(c, psrc, pidx, nP, N, l, d);
             orc_ntt(c, l, d);
             uint64_t Pmod = 1;
-            for (int p = 0; p < nP; p++) Pmod = mulmod(Pmod, pm[p] % q, q);
-            uint64_t Pinv = invmod(Pmod, q);
-            for (int x = 0; x < N; x++) out[(size_t)l * PN + x] = mulmod(submod(acc[(size_t)l * PN + x], d[x], q), Pinv, q);
+            for (int p = 0; p < nP; p++) Pmod = mulmod(Pmod, c->mod[nQ + p] % q, q);
+            uint64_t PinvM = orc_mform(invmod(Pmod, q), q, c->bred[l]);
+            for (int x = 0; x < N; x++) out[(size_t)l * PN + x] = orc_mred(submod(acc[(size_t)l * PN + x], d[x], q), PinvM, q, c->mred[l]);
         }
     }
     free(c2); free(d); free(acc0); free(acc1);

@@ -25,7 +25,7 @@ SYMBOLS = [
     "sfg_inner_sum_all", "sfg_encode_slots_i8", "sfg_cache_write_files", "sfg_cache_load_files",
     "sfg_geno_count_sketch", "sfg_ntt_dev", "sfg_rotate_right_dev",
     "sfg_matmult4_stream_preprocess_rows", "sfg_matmult4_stream_preprocess_giants", "sfg_ct_mod_reduce",
-    "sfg_matmult4_finish_dev",
+    "sfg_matmult4_finish_dev", "sfg_cipher_matrix_save", "sfg_cipher_matrix_info", "sfg_cipher_matrix_load",
 ]
 
 _lib = None
@@ -102,6 +102,9 @@ def load():
     L.sfg_matmult4_stream_preprocess_giants.argtypes = [vp, vp, i32, i32, i32, C.POINTER(vp)]
     L.sfg_ct_mod_reduce.argtypes = [vp, vp, sz, i32]
     L.sfg_matmult4_finish_dev.argtypes = [vp, vp, i32, i32, vp, i32, i32, vp]
+    L.sfg_cipher_matrix_save.argtypes = [C.c_char_p, i32, vp, vp, i32, i32, i32]
+    L.sfg_cipher_matrix_info.argtypes = [C.c_char_p, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
+    L.sfg_cipher_matrix_load.argtypes = [C.c_char_p, i32, vp, vp, i32, i32, i32]
     L.sfg_ctx_sync.argtypes = [vp]
     L.sfg_ctx_last_timings.argtypes = [vp, C.POINTER(C.c_float)]
     L.sfg_ctx_stream.restype = vp

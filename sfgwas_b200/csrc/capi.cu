@@ -19,6 +19,12 @@ struct sfg_cache {
 
 static std::string g_create_err;
 
+namespace sfg {  // cmfile.cpp
+int cm_save(const char *filename, int logN, const uint64_t *cts, const double *scales, int nrows, int ncols, int nl, std::string &err);
+int cm_info(const char *filename, int *nrows, int *ncols, int *nl, int *logN, std::string &err);
+int cm_load(const char *filename, int logN, uint64_t *cts, double *scales, int nrows, int ncols, int nl, std::string &err);
+}  // namespace sfg
+
 extern "C" {
 
 int sfg_version(void) { return 1; }
@@ -490,6 +496,20 @@ int sfg_cache_load_files(sfg_ctx *h, const char *prefix, size_t nrows, size_t nc
     if (cache_load_files(&h->c, prefix, nrows, ncols, max_level, &ca)) return -1;
     *out = new sfg_cache{ca};
     return 0;
+}
+
+// crypto.SaveCipherMatrixToFile / LoadCipherMatrixFromFile: host-only (no device, no context needed); errors via sfg_last_error(NULL)
+int sfg_cipher_matrix_save(const char *filename, int logN, const uint64_t *cts, const double *scales, int nrows, int ncols, int level) {
+    return cm_save(filename, logN, cts, scales, nrows, ncols, level + 1, g_create_err);
+}
+int sfg_cipher_matrix_info(const char *filename, int *nrows, int *ncols, int *level, int *logN) {
+    int nl = 0;
+    if (cm_info(filename, nrows, ncols, &nl, logN, g_create_err)) return -1;
+    *level = nl - 1;
+    return 0;
+}
+int sfg_cipher_matrix_load(const char *filename, int logN, uint64_t *cts, double *scales, int nrows, int ncols, int level) {
+    return cm_load(filename, logN, cts, scales, nrows, ncols, level + 1, g_create_err);
 }
 
 int sfg_geno_count_sketch(sfg_ctx *h, const sfg_geno *g, const int32_t *rand_index, const int8_t *sgn, int kp, double *sketch, uint64_t *xsum,

@@ -21,6 +21,7 @@ import numpy as np
 from ._lib import SfgError, load
 
 __all__ = [
+    "SaveCipherMatrixToFile", "LoadCipherMatrixFromFile",
     "CryptoParams", "GenoFileStream", "DiagCache", "MatMult4StreamPreprocess", "MatMult4StreamCompute", "MatMult4Stream",
     "SfgError", "Ciphertext", "SetRelinKey", "CMult", "CMultScalar", "CSub", "CAdd", "InnerSumAll", "InnerProd", "MaskTrunc",
     "QXLazyNormStream", "QXtLazyNormStream",
@@ -324,6 +325,36 @@ class Ciphertext:
 
     def CopyNew(self) -> "Ciphertext":
         return Ciphertext(self.value.copy(), self.scale)
+
+
+def SaveCipherMatrixToFile(cps, cm, filename: str):
+    """crypto.SaveCipherMatrixToFile (crypto/utilities.go:82-113): ``cm`` is a CipherMatrix (list of CipherVectors) of degree-1 ciphertexts
+    at one level -- what MatMult4StreamCompute returns and gwas/assoc.go:317-333 caches as ``assoc_cache_mult.%d.bin``."""
+    L = load()
+    nr, nc = len(cm), len(cm[0])
+    lvl = cm[0][0].Level()
+    if any(len(row) != nc or any(c.Level() != lvl for c in row) for row in cm):
+        raise SfgError("SaveCipherMatrixToFile: ragged matrix or mixed levels")
+    cts = np.ascontiguousarray(np.stack([np.stack([c.value for c in row]) for row in cm]), dtype=np.uint64)
+    sc = np.ascontiguousarray([[c.scale for c in row] for row in cm], dtype=np.float64)
+    logN = int(cts.shape[-1]).bit_length() - 1
+    if L.sfg_cipher_matrix_save(str(filename).encode(), logN, _p(cts), _p(sc), nr, nc, lvl) != 0:
+        raise SfgError("SaveCipherMatrixToFile: " + L.sfg_last_error(None).decode())
+
+
+def LoadCipherMatrixFromFile(cps, filename: str):
+    """crypto.LoadCipherMatrixFromFile (crypto/utilities.go:115-141) -> CipherMatrix (list of lists of Ciphertext)."""
+    L = load()
+    nr, nc, lvl, logN = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+    if L.sfg_cipher_matrix_info(str(filename).encode(), C.byref(nr), C.byref(nc), C.byref(lvl), C.byref(logN)) != 0:
+        raise SfgError("LoadCipherMatrixFromFile: " + L.sfg_last_error(None).decode())
+    if cps is not None and logN.value != cps.logN:
+        raise SfgError("LoadCipherMatrixFromFile: file has logN %d, parameters have %d" % (logN.value, cps.logN))
+    cts = np.zeros((nr.value, nc.value, 2, lvl.value + 1, 1 << logN.value), dtype=np.uint64)
+    sc = np.zeros((nr.value, nc.value), dtype=np.float64)
+    if L.sfg_cipher_matrix_load(str(filename).encode(), logN.value, _p(cts), _p(sc), nr.value, nc.value, lvl.value) != 0:
+        raise SfgError("LoadCipherMatrixFromFile: " + L.sfg_last_error(None).decode())
+    return [[Ciphertext(cts[i, j], sc[i, j]) for j in range(nc.value)] for i in range(nr.value)]
 
 
 def SetRelinKey(cps: CryptoParams, rlk: np.ndarray):
