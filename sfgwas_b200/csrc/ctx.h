@@ -68,7 +68,7 @@ struct Ctx {
         void *p = nullptr;
         size_t bytes = 0;
     };
-    WsBuf ws[16];
+    WsBuf ws[20];
     // grow-only PINNED host staging (hostio.cu): the "_ptrs" entry points gather / scatter one Go slice per limb through it
     WsBuf pin[2];
     std::mutex mu;
@@ -131,7 +131,7 @@ void scatter_host_to_limbs(const uint64_t *src, uint64_t *const *limbs, size_t n
 int scatter_device_to_limbs(Ctx *c, const uint64_t *d_src, uint64_t *const *limbs, size_t np);
 
 // workspace slots
-enum WsSlot { WS_C2 = 0, WS_ACC, WS_META, WS_R, WS_CV, WS_POFF, WS_TMPP, WS_A, WS_OUT, WS_META2, WS_RIMG, WS_PIMG, WS_MD, WS_KSB, WS_VQ, WS_EXTD, WS_COUNT };
+enum WsSlot { WS_C2 = 0, WS_ACC, WS_META, WS_R, WS_CV, WS_POFF, WS_TMPP, WS_A, WS_OUT, WS_META2, WS_RIMG, WS_PIMG, WS_MD, WS_KSB, WS_VQ, WS_EXTD, WS_RTAB, WS_COUNT };
 int ws_get(Ctx *c, int slot, size_t bytes, void **out);  // returns a buffer of at least `bytes` (contents undefined)
 void ws_release(Ctx *c);
 

@@ -85,10 +85,12 @@ int launch_img_p(Ctx *c, const TcGeomP &g, const PolyLayout &lay, const void *re
 int launch_img_r(Ctx *c, const TcGeomP &gp, const TcGeomR &gr, const PolyLayout &lay, const void *R, const long long *src_off_dev,
                  void *img_group, cudaStream_t st);
 int launch_img_extract(Ctx *c, const TcGeomP &g, const void *img_group, int l, int col, int k_in_group, uint64_t *out_dev, cudaStream_t st);
-// cv[col - col_lo][row][l][n] (+)= sum_k R*P mod q for the columns of tiles [tile_lo, tile_hi) that lie in [col_lo, col_hi)
-int launch_mac_tc(Ctx *c, const TcGeomP &gp, const TcGeomR &gr, const void *Pimg_group, int img_ntiles, int img_tile0,
-                  const void *Rimg_group, int tile_lo, int tile_hi, int col_lo, int col_hi, bool accumulate, uint64_t *cv,
-                  cudaStream_t st);
+// cv[col - col_lo][row][l][n] (+)= sum_k R*P mod q for the columns of tiles [tile_lo, tile_hi) that lie in [col_lo, col_hi), over `ngroups`
+// consecutive K groups (images p_gstride / r_gstride bytes apart) accumulated in TMEM by ONE launch (<= tc_max_fused_groups)
+int tc_max_fused_groups(const TcGeomP &gp);
+int launch_mac_tc(Ctx *c, const TcGeomP &gp, const TcGeomR &gr, const void *Pimg_group, long long p_gstride, int img_ntiles, int img_tile0,
+                  const void *Rimg_group, long long r_gstride, int ngroups, int tile_lo, int tile_hi, int col_lo, int col_hi, bool accumulate,
+                  uint64_t *cv, cudaStream_t st);
 
 // ---- key-switch + automorphism (kernels_ks.cu) ----
 // A batch is a list of ciphertexts, each rotated with its own Galois key.  All arrays are DEVICE arrays of nct entries.

@@ -8,8 +8,11 @@
 // `delta` of a half-integer is recomputed exactly-enough by a direct double-double sum of the n terms
 // v_j * cos/sin(2 pi 5^j k / 2N) (error ~1e-25), which resolves the rounding.  Coefficients that are still within
 // 1e-13 of a tie after that are counted in stats[1] (never observed; a genuine tie needs an exact half-integer).
+#include <cstdlib>
+
 #include "kernels.h"
 #include "ntt.cuh"
+#include "ntt2.cuh"
 
 namespace sfg {
 
@@ -36,14 +39,62 @@ __device__ __forceinline__ dd dd_mul_d(dd a, double b) {
     return two_sum(p, e);
 }
 
-constexpr int kMaxFlag = 2048;
+constexpr int kMaxFlag = 512;  // near-tie re-checks per polynomial (observed: ~0.1 at PN13QP218, ~2 at PN14QP438); more are counted as unresolved
+
+// Residue of the integer message coefficient v (exact in FP64, |v| < 2^50) in the input range of the class's forward butterflies.
+template <class A>
+__device__ __forceinline__ typename A::T msg_residue(double v, const typename A::C &c, const LimbConst &lc) {
+    if constexpr (A::kKind == kArD) {
+        return ArD::red(v, c);  // (-q, q): the FP64 class works on signed representatives
+    } else {
+        uint64_t r = bred_add((uint64_t)fabs(v), lc);
+        if (v < 0.0 && r != 0) r = lc.q - r;
+        return A::from_canon(r, c);
+    }
+}
+
+// NTT of the message over one limb with the register-tiled, class-specialised transform of ntt2.cuh (radix-8/16 passes: 3 CTA barriers
+// for 2^13 coefficients instead of 13), canonical residues out.  m: the integer message [N] in shared memory; s: transform scratch.
+// CS = 1: the ring is cut in two halves transformed one after the other (stage 0 folded into the first pass), which keeps the scratch at
+// 2^13 coefficients for logN = 14.  The result is staged in `s` and leaves with unit-stride stores.
+template <class A>
+__device__ __forceinline__ void encode_limb(const double *__restrict__ m, void *sraw, int logN, int CS, const TwTab &tab, const LimbConst &lc,
+                                            unsigned char *__restrict__ o, int es, int mont) {
+    using T = typename A::T;
+    T *s = reinterpret_cast<T *>(sraw);
+    const typename A::C c = A::make(lc);
+    const int logS = logN - CS, S = 1 << logS;
+    const PassPlan plan = make_pass_plan(logS - kLastR);
+    for (int sl = 0; sl < (1 << CS); sl++) {
+        auto ld0 = [&](int j, int) -> T {
+            if (CS == 0) return msg_residue<A>(m[j], c, lc);
+            T x = msg_residue<A>(m[j], c, lc), y = msg_residue<A>(m[j + S], c, lc);
+            A::fwd(x, y, __ldg(reinterpret_cast<const typename A::TW *>(tab.fwd) + 1), c);
+            return sl ? y : x;
+        };
+        auto fin = [&](int j, T v, int) { s[sidx<sizeof(T)>(j)] = (T)A::canon(v, c); };
+        ntt_forward<A>(s, logN, logS, sl, plan, tab, c, ld0, fin);
+        __syncthreads();
+        if (es == 4) {
+            uint32_t *o32 = reinterpret_cast<uint32_t *>(o) + (size_t)sl * S;
+            for (int k = threadIdx.x; k < S; k += blockDim.x) o32[k] = (uint32_t)s[sidx<sizeof(T)>(k)];
+        } else {
+            uint64_t *o64 = reinterpret_cast<uint64_t *>(o) + (size_t)sl * S;
+            for (int k = threadIdx.x; k < S; k += blockDim.x) {
+                const uint64_t x = (uint64_t)s[sidx<sizeof(T)>(k)];
+                o64[k] = mont ? mform(x, lc) : x;
+            }
+        }
+        __syncthreads();
+    }
+}
 
 template <int NPER>
 __global__ void __launch_bounds__(1024, 1)
 k_encode(const int8_t *__restrict__ X, size_t ld, const EncJob *__restrict__ jobs, int logN, PolyLayout lay, int mont, double sc,
          double delta, const double2 *__restrict__ roots, const int *__restrict__ rot5, const double2 *__restrict__ ddcos,
          const uint64_t *__restrict__ tw, const LimbConst *__restrict__ lcs, unsigned char *__restrict__ out,
-         long long *__restrict__ coeff_out, unsigned long long *__restrict__ stats) {
+         long long *__restrict__ coeff_out, unsigned long long *__restrict__ stats, const TwTab *__restrict__ tabs2, int CS) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int N = 1 << logN, n = N >> 1, M = N << 1, logn = logN - 1;
     double *re = reinterpret_cast<double *>(smem_raw);
@@ -53,6 +104,7 @@ k_encode(const int8_t *__restrict__ X, size_t ld, const EncJob *__restrict__ job
     int *flag_idx = reinterpret_cast<int *>(vals + n);
     long long *flag_val = reinterpret_cast<long long *>(flag_idx + kMaxFlag);
     dd *red = reinterpret_cast<dd *>(flag_val + kMaxFlag);  // [32] warp partials
+    void *s2 = reinterpret_cast<void *>(red + 32);          // scratch of the register-tiled limb transforms (tabs2 != nullptr)
     __shared__ int nflag;
 
     const EncJob job = jobs[blockIdx.x];
@@ -168,6 +220,26 @@ k_encode(const int8_t *__restrict__ X, size_t ld, const EncJob *__restrict__ job
     }
 
     // 5. RNS reduce, NTT per limb, Montgomery form, store
+    if (tabs2) {
+        // the message goes to shared memory as exact FP64 integers (over the FFT buffers: every thread has read its values), then one
+        // class-specialised register-tiled transform per limb
+        __syncthreads();
+        double *mm = reinterpret_cast<double *>(smem_raw);
+#pragma unroll
+        for (int r = 0; r < NPER; r++) mm[tid + r * T] = (double)m[r];
+        __syncthreads();
+        for (int l = 0; l < lay.nl; l++) {
+            const LimbConst lc = lcs[l];
+            unsigned char *o = out + job.out_off + lay.off[l];
+            switch (arith_kind(lc.q)) {  // uniform across the CTA
+                case kArN30: encode_limb<ArN30>(mm, s2, logN, CS, tabs2[l], lc, o, lay.es[l], mont); break;
+                case kArN31: encode_limb<ArN31>(mm, s2, logN, CS, tabs2[l], lc, o, lay.es[l], mont); break;
+                case kArD: encode_limb<ArD>(mm, s2, logN, CS, tabs2[l], lc, o, lay.es[l], mont); break;
+                default: encode_limb<ArW>(mm, s2, logN, CS, tabs2[l], lc, o, lay.es[l], mont); break;
+            }
+        }
+        return;
+    }
     for (int l = 0; l < lay.nl; l++) {
         const LimbConst lc = lcs[l];
         const NttTab tab = ntt_tab(tw, l, N);
@@ -202,16 +274,22 @@ int launch_encode(Ctx *c, const int8_t *X, size_t ld, const EncJob *jobs_dev, in
     if (logN < 8 || logN > 14) SFG_FAIL(c, "on-device diagonal encoder supports 8 <= logN <= 14 (got %d)", logN);
     const int NPER = logN == 14 ? 16 : 8;
     const int T = N / NPER;
-    const size_t smem = (size_t)N * 8 + n + kMaxFlag * (sizeof(int) + sizeof(long long)) + 32 * sizeof(dd) + 64;
+    // limb transforms: register-tiled passes of ntt2.cuh (SFG_ENC_OLDNTT=1 keeps the radix-2 shared-memory transform for A/B runs);
+    // logN = 14 transforms the ring as two halves so that message + scratch fit one CTA's shared memory
+    static const bool old_ntt = [] { const char *e = getenv("SFG_ENC_OLDNTT"); return e && *e == '1'; }();
+    const TwTab *tabs2 = old_ntt ? nullptr : c->tw2;
+    const int CS = logN > 13 ? 1 : 0;
+    const size_t scratch = tabs2 ? ntt_smem_elems(N >> CS) * 8 + 16 : 0;
+    const size_t smem = (size_t)N * 8 + n + kMaxFlag * (sizeof(int) + sizeof(long long)) + 32 * sizeof(dd) + 64 + scratch;
     const double sc = c->scale / (double)n;
     if (NPER == 16) {
         SFG_CUDA(c, cudaFuncSetAttribute(k_encode<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_encode<16><<<njobs, T, smem, st>>>(X, ld, jobs_dev, logN, lay, mont ? 1 : 0, sc, c->enc_delta, c->roots, c->rot5, c->ddcos,
-                                            c->tw, c->lc, (unsigned char *)out, coeff_out, c->enc_stats);
+                                            c->tw, c->lc, (unsigned char *)out, coeff_out, c->enc_stats, tabs2, CS);
     } else {
         SFG_CUDA(c, cudaFuncSetAttribute(k_encode<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_encode<8><<<njobs, T, smem, st>>>(X, ld, jobs_dev, logN, lay, mont ? 1 : 0, sc, c->enc_delta, c->roots, c->rot5, c->ddcos,
-                                           c->tw, c->lc, (unsigned char *)out, coeff_out, c->enc_stats);
+                                           c->tw, c->lc, (unsigned char *)out, coeff_out, c->enc_stats, tabs2, CS);
     }
     SFG_LAUNCHED(c, "k_encode", st);
     return 0;

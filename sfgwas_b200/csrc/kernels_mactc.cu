@@ -121,6 +121,8 @@ struct MacTcParams {
     uint64_t *cv;         // [col - col_lo][rows][L][N] canonical residues
     const LimbConst *lc;
     int L, N, rows, RP, Kg;
+    int ngroups;                // K groups accumulated in TMEM by this launch (the s32 partial sums hold nb * ngroups * Kg * 255^2)
+    long long p_gstride, r_gstride;  // bytes between consecutive K-group images of P / of R
     int cv_rows, cv_row0;       // rows per column of the cv image and the first row this launch writes
     int img_ntiles, img_tile0;  // geometry of the P image: tiles it holds and the global index of its first tile
     int tile_lo, tile_hi;       // global column tiles processed by this launch
@@ -289,19 +291,22 @@ __global__ void __launch_bounds__(384, 1) k_mac_tc(const __grid_constant__ MacTc
                 const long long tg0 = (((long long)it.sb * p.img_ntiles + (it.ct - p.img_tile0)) * p.SBN + it.n4l) * 4;
                 for (int i = 0; i < 4; i++) {
                     const int n = it.n4 * 4 + i;
-                    mbar_wait(&b_empty[bs], bph ^ 1u);
-                    mbar_arrive_expect_tx(&b_full[bs], bbytes);
-                    bulk_g2s_hint(b_ring + (size_t)bs * p.bslot_bytes, p.R + p.rbase[it.l] + (long long)n * bbytes, bbytes, &b_full[bs], pol_r);
-                    bs ^= 1u;
-                    if (bs == 0) bph ^= 1u;
-                    const uint8_t *src = p.P + p.pbase[it.l] + (tg0 + i) * nb * (long long)stage_bytes;
-                    for (int j = 0; j < nb; j++) {
-                        mbar_wait(&a_empty[as], aph ^ 1u);
-                        mbar_arrive_expect_tx(&a_full[as], (uint32_t)stage_bytes);
-                        bulk_g2s_hint(a_ring + (size_t)as * stage_bytes, src + (long long)j * stage_bytes, (uint32_t)stage_bytes, &a_full[as], pol_p);
-                        if (++as == (uint32_t)p.SA) {
-                            as = 0;
-                            aph ^= 1u;
+                    for (int g = 0; g < p.ngroups; g++) {  // every K group of this coefficient accumulates into the same TMEM tile
+                        mbar_wait(&b_empty[bs], bph ^ 1u);
+                        mbar_arrive_expect_tx(&b_full[bs], bbytes);
+                        bulk_g2s_hint(b_ring + (size_t)bs * p.bslot_bytes, p.R + g * p.r_gstride + p.rbase[it.l] + (long long)n * bbytes, bbytes,
+                                      &b_full[bs], pol_r);
+                        bs ^= 1u;
+                        if (bs == 0) bph ^= 1u;
+                        const uint8_t *src = p.P + g * p.p_gstride + p.pbase[it.l] + (tg0 + i) * nb * (long long)stage_bytes;
+                        for (int j = 0; j < nb; j++) {
+                            mbar_wait(&a_empty[as], aph ^ 1u);
+                            mbar_arrive_expect_tx(&a_full[as], (uint32_t)stage_bytes);
+                            bulk_g2s_hint(a_ring + (size_t)as * stage_bytes, src + (long long)j * stage_bytes, (uint32_t)stage_bytes, &a_full[as], pol_p);
+                            if (++as == (uint32_t)p.SA) {
+                                as = 0;
+                                aph ^= 1u;
+                            }
                         }
                     }
                 }
@@ -320,7 +325,6 @@ __global__ void __launch_bounds__(384, 1) k_mac_tc(const __grid_constant__ MacTc
                 const uint32_t idesc = umma_idesc_u8(npad);
                 for (int i = 0; i < 4; i++) {
                     mbar_wait(&t_empty[tb], tph ^ 1u);
-                    mbar_wait(&b_full[bs], bph);
                     tc_fence_after();
                     const uint32_t d_base = tmem_base + tb * (uint32_t)p.tbuf_stride;
                     // zero the accumulator region: the byte planes overlap at different column offsets, so no single
@@ -330,25 +334,29 @@ __global__ void __launch_bounds__(384, 1) k_mac_tc(const __grid_constant__ MacTc
                         const int w = (((rem < 256 ? rem : 256) + 15) >> 4) << 4;
                         umma_i8(d_base + c0, umma_desc(zaddr, 2048, 128), umma_desc(zaddr, 4096, 128), umma_idesc_u8(w), 0u);
                     }
-                    const uint32_t baddr = smem_u32(b_ring + (size_t)bs * p.bslot_bytes);
-                    for (int j = 0; j < nb; j++) {
-                        mbar_wait(&a_full[as], aph);
+                    for (int g = 0; g < p.ngroups; g++) {
+                        mbar_wait(&b_full[bs], bph);
                         tc_fence_after();
-                        const uint32_t aaddr = smem_u32(a_ring + (size_t)as * stage_bytes);
-                        for (int ks = 0; ks < ksteps; ks++) {
-                            umma_i8(d_base + j * p.RP, umma_desc(aaddr + ks * 4096, 2048, 128),
-                                    umma_desc(baddr + ks * npad * 32, npad * 16, 128), idesc, 1u);
+                        const uint32_t baddr = smem_u32(b_ring + (size_t)bs * p.bslot_bytes);
+                        for (int j = 0; j < nb; j++) {
+                            mbar_wait(&a_full[as], aph);
+                            tc_fence_after();
+                            const uint32_t aaddr = smem_u32(a_ring + (size_t)as * stage_bytes);
+                            for (int ks = 0; ks < ksteps; ks++) {
+                                umma_i8(d_base + j * p.RP, umma_desc(aaddr + ks * 4096, 2048, 128),
+                                        umma_desc(baddr + ks * npad * 32, npad * 16, 128), idesc, 1u);
+                            }
+                            tc_commit(&a_empty[as]);
+                            if (++as == (uint32_t)p.SA) {
+                                as = 0;
+                                aph ^= 1u;
+                            }
                         }
-                        tc_commit(&a_empty[as]);
-                        if (++as == (uint32_t)p.SA) {
-                            as = 0;
-                            aph ^= 1u;
-                        }
+                        tc_commit(&b_empty[bs]);
+                        bs ^= 1u;
+                        if (bs == 0) bph ^= 1u;
                     }
-                    tc_commit(&b_empty[bs]);
                     tc_commit(&t_full[tb]);
-                    bs ^= 1u;
-                    if (bs == 0) bph ^= 1u;
                     if (++tb == (uint32_t)ntbuf) {
                         tb = 0;
                         tph ^= 1u;
@@ -675,13 +683,25 @@ int launch_img_extract(Ctx *c, const TcGeomP &g, const void *img_group, int l, i
     return 0;
 }
 
-int launch_mac_tc(Ctx *c, const TcGeomP &gp, const TcGeomR &gr, const void *Pimg_group, int img_ntiles, int img_tile0,
-                  const void *Rimg_group, int tile_lo, int tile_hi, int col_lo, int col_hi, bool accumulate, uint64_t *cv,
-                  cudaStream_t st) {
-    if (tile_hi <= tile_lo || col_hi <= col_lo) return 0;
+// K groups one launch may accumulate in TMEM: the s32 partial sums hold nb * (groups * Kg) products of two bytes
+int tc_max_fused_groups(const TcGeomP &gp) {
+    int nbmax = 1;
+    for (int l = 0; l < gp.L; l++) nbmax = std::max(nbmax, gp.nb[l]);
+    return (int)std::max<long long>(1, 2147483647LL / ((long long)nbmax * gp.Kg * 65025LL));
+}
+
+int launch_mac_tc(Ctx *c, const TcGeomP &gp, const TcGeomR &gr, const void *Pimg_group, long long p_gstride, int img_ntiles, int img_tile0,
+                  const void *Rimg_group, long long r_gstride, int ngroups, int tile_lo, int tile_hi, int col_lo, int col_hi, bool accumulate,
+                  uint64_t *cv, cudaStream_t st) {
+    if (tile_hi <= tile_lo || col_hi <= col_lo || ngroups < 1) return 0;
+    if (ngroups > tc_max_fused_groups(gp)) SFG_FAIL(c, "tensor-core MAC: %d K groups exceed the s32 accumulator range", ngroups);
+    const int Ktot = ngroups * gp.Kg;  // products summed per accumulator by this launch
     MacTcParams p{};
     p.P = (const uint8_t *)Pimg_group;
     p.R = (const uint8_t *)Rimg_group;
+    p.ngroups = ngroups;
+    p.p_gstride = p_gstride;
+    p.r_gstride = r_gstride;
     p.cv = cv;
     p.lc = c->lc;
     p.L = gp.L;
@@ -712,11 +732,11 @@ int launch_mac_tc(Ctx *c, const TcGeomP &gp, const TcGeomR &gr, const void *Pimg
         p.rbase[l] = gr.rbase[l];
         maxnpad = std::max(maxnpad, gr.npad[l]);
         // u64 recombination is exact iff (2nb-1) * [nb * Kg * 255^2] * q < 2^64
-        const long double bound = (long double)(2 * nb - 1) * nb * gp.Kg * 65025.0L * (long double)q;
+        const long double bound = (long double)(2 * nb - 1) * nb * Ktot * 65025.0L * (long double)q;
         p.fast[l] = bound < 18446744073709551616.0L ? 1 : 0;
         // 32-bit Montgomery: terms T_s * c_s with c_s < q < 2^31 and the sum below q * 2^32
-        if (q < (1ULL << 31) && (long double)(2 * nb - 1) * nb * gp.Kg * 65025.0L < 4294967296.0L) p.fast[l] = 2;
-        if ((long double)nb * gp.Kg * 65025.0L >= 2147483648.0L) SFG_FAIL(c, "s32 accumulator overflow (Kg = %d)", gp.Kg);
+        if (q < (1ULL << 31) && (long double)(2 * nb - 1) * nb * Ktot * 65025.0L < 4294967296.0L) p.fast[l] = 2;
+        if ((long double)nb * Ktot * 65025.0L >= 2147483648.0L) SFG_FAIL(c, "s32 accumulator overflow (K = %d)", Ktot);
         for (int s = 0; s < 2 * nb - 1; s++) {
             uint64_t v = h_powmod(2, 8 * s, q);
             if (p.fast[l] == 0) v = h_mulmod(v, c->lc_h[l].r64, q);

@@ -466,67 +466,95 @@ static int build_rot_cache(Ctx *c, const Cache *ca, const uint64_t *d_A, int s, 
 // (2) MAC for the giant steps gact[gi_lo .. gi_hi) -> d_cv [(gi-gi_lo)*m_ct + bj][row][l][N]
 //     gwas/matmult.go:1154-1168 (CPMultAccWithoutMRedV2) + :1203 (ModularReduceV2)
 // ---------------------------------------------------------------------------------------------------------------
-static int run_mac_rows(Ctx *c, const Cache *ca, const void *R, const std::vector<int> &klist, int s, int gi_lo, int gi_hi, uint64_t *d_cv,
-                        int row0, int nrows_part);
+// One row part of the MAC: rows [row0, row0 + rows) of the 2s ciphertext polynomials with their own R image
+struct MacPart {
+    TcGeomR gr;
+    unsigned char *rimg;
+};
 
 static int run_mac(Ctx *c, const Cache *ca, const void *R, const std::vector<int> &klist, int s, int gi_lo, int gi_hi,
                    uint64_t *d_cv) {
-    // When the accumulator region of all 2s rows exceeds half of TMEM the kernel runs single-buffered (MMA stream and epilogue do not
-    // overlap).  Two row halves that each fit 256 columns are faster even though the P image is streamed twice (kp = 15 at logN 14:
-    // 9 x 32 = 288 columns for 30 rows, 9 x 16 = 144 for 16).
-    const int rows = 2 * s;
-    TcGeomR gr, gh;
-    if (tc_geom_r(c, ca->tc, rows, &gr)) return -1;
-    const int h = (rows / 2 + 1) / 2 * 2;  // even: a ciphertext's two polynomials stay together
-    if (gr.tbuf_stride == 0 && rows >= 4 && getenv("SFG_MAC_NOSPLIT") == nullptr && !tc_geom_r(c, ca->tc, h, &gh) && gh.tbuf_stride != 0) {
-        if (run_mac_rows(c, ca, R, klist, s, gi_lo, gi_hi, d_cv, 0, h)) return -1;
-        return run_mac_rows(c, ca, R, klist, s, gi_lo, gi_hi, d_cv, h, rows - h);
-    }
-    return run_mac_rows(c, ca, R, klist, s, gi_lo, gi_hi, d_cv, 0, rows);
-}
-
-// rows [row0, row0 + nrows_part) of the 2s ciphertext polynomials
-static int run_mac_rows(Ctx *c, const Cache *ca, const void *R, const std::vector<int> &klist, int s, int gi_lo, int gi_hi, uint64_t *d_cv,
-                        int row0, int nrows_part) {
     const TcGeomP &tc = ca->tc;
-    const int m_ct = ca->m_ct, rows_all = 2 * s, rows = nrows_part, Kg = tc.Kg, K = tc.K;
+    const int m_ct = ca->m_ct, rows_all = 2 * s, Kg = tc.Kg, K = tc.K;
     const int col_lo = gi_lo * m_ct, col_hi = gi_hi * m_ct;
     if (klist.empty() || col_hi <= col_lo) return 0;
-    TcGeomR gr;
-    if (tc_geom_r(c, tc, rows, &gr)) return -1;
-    gr.cv_rows = rows_all;
-    gr.cv_row0 = row0;
+    // When the accumulator region of all 2s rows exceeds half of TMEM the kernel would run single-buffered (MMA stream and epilogue do
+    // not overlap).  Two row halves that each fit 256 columns are faster even though the P image is streamed twice (kp = 15 at logN 14:
+    // 9 x 32 = 288 columns for 30 rows, 9 x 16 = 144 for 16).
+    std::vector<std::pair<int, int>> ranges;  // (row0, rows)
+    {
+        TcGeomR gr, gh;
+        if (tc_geom_r(c, tc, rows_all, &gr)) return -1;
+        const int h = (rows_all / 2 + 1) / 2 * 2;  // even: a ciphertext's two polynomials stay together
+        if (gr.tbuf_stride == 0 && rows_all >= 4 && getenv("SFG_MAC_NOSPLIT") == nullptr && !tc_geom_r(c, tc, h, &gh) && gh.tbuf_stride != 0) {
+            ranges.push_back({0, h});
+            ranges.push_back({h, rows_all - h});
+        } else {
+            ranges.push_back({0, rows_all});
+        }
+    }
     const int tile_lo = col_lo / 128, tile_hi = (col_hi + 127) / 128;
-    // source-record table of the R image: [group][Kg][rows]; k outside klist (other block rows / padding) contributes zero
+    // R images of the parts: source-record table [group][Kg][rows]; k outside klist (other block rows / padding) contributes zero
     std::vector<int> kpos((size_t)K, -1);
     for (size_t i = 0; i < klist.size(); i++) kpos[klist[i]] = (int)i;
     const size_t RB = (size_t)ca->lay.bytes;
-    std::vector<long long> tab((size_t)tc.ngroups * Kg * rows, -1);
-    for (int grp = 0; grp < tc.ngroups; grp++)
-        for (int kk = 0; kk < Kg; kk++) {
-            const int k = grp * Kg + kk;
-            if (k >= K || kpos[k] < 0) continue;
-            for (int r = 0; r < rows; r++) tab[((size_t)grp * Kg + kk) * rows + r] = (long long)(((size_t)kpos[k] * rows_all + row0 + r) * RB);
+    std::vector<MacPart> parts(ranges.size());
+    size_t rimg_total = 0, tab_total = 0;
+    for (size_t pi = 0; pi < ranges.size(); pi++) {
+        if (tc_geom_r(c, tc, ranges[pi].second, &parts[pi].gr)) return -1;
+        parts[pi].gr.cv_rows = rows_all;
+        parts[pi].gr.cv_row0 = ranges[pi].first;
+        rimg_total += (size_t)parts[pi].gr.group_bytes * tc.ngroups;
+        tab_total += (size_t)tc.ngroups * Kg * ranges[pi].second;
+    }
+    std::vector<long long> tab(tab_total, -1);
+    {
+        size_t o = 0;
+        for (size_t pi = 0; pi < ranges.size(); pi++) {
+            const int row0 = ranges[pi].first, rows = ranges[pi].second;
+            for (int grp = 0; grp < tc.ngroups; grp++)
+                for (int kk = 0; kk < Kg; kk++) {
+                    const int k = grp * Kg + kk;
+                    if (k < K && kpos[k] >= 0)
+                        for (int r = 0; r < rows; r++) tab[o + ((size_t)grp * Kg + kk) * rows + r] = (long long)(((size_t)kpos[k] * rows_all + row0 + r) * RB);
+                }
+            o += (size_t)tc.ngroups * Kg * rows;
         }
+    }
     void *dtab, *rimg;
-    if (ws_get(c, WS_META2, tab.size() * sizeof(long long), &dtab)) return -1;
+    if (ws_get(c, WS_RTAB, tab.size() * sizeof(long long), &dtab)) return -1;
     SFG_CUDA(c, cudaMemcpyAsync(dtab, tab.data(), tab.size() * sizeof(long long), cudaMemcpyDefault, c->stream));
-    if (ws_get(c, WS_RIMG, (size_t)gr.group_bytes * tc.ngroups, &rimg)) return -1;
-    for (int grp = 0; grp < tc.ngroups; grp++)
-        if (launch_img_r(c, tc, gr, ca->lay, R, (const long long *)dtab + (size_t)grp * Kg * rows,
-                         (unsigned char *)rimg + (size_t)grp * gr.group_bytes, c->stream))
-            return -1;
-    if (ca->materialised) {
+    if (ws_get(c, WS_RIMG, rimg_total, &rimg)) return -1;
+    {
+        size_t o = 0, ro = 0;
+        for (size_t pi = 0; pi < ranges.size(); pi++) {
+            const int rows = ranges[pi].second;
+            parts[pi].rimg = (unsigned char *)rimg + ro;
+            for (int grp = 0; grp < tc.ngroups; grp++)
+                if (launch_img_r(c, tc, parts[pi].gr, ca->lay, R, (const long long *)dtab + o + (size_t)grp * Kg * rows,
+                                 parts[pi].rimg + (size_t)grp * parts[pi].gr.group_bytes, c->stream))
+                    return -1;
+            o += (size_t)tc.ngroups * Kg * rows;
+            ro += (size_t)parts[pi].gr.group_bytes * tc.ngroups;
+        }
+    }
+    // all K groups accumulate in TMEM inside one launch (many block rows: the transposed orientation, PCA shapes); only when their
+    // products could overflow the s32 partial sums is the K range cut into several launches that add into cv mod q
+    const int gf = tc_max_fused_groups(tc);
+    auto mac = [&](const unsigned char *pimg, long long p_gstride, int img_ntiles, int img_tile0, int t0, int t1) -> int {
         if (g_tm) g_tm->mark(3);  // the MAC kernel alone, on the stream it is launched on (bench.py roofline)
-        for (int grp = 0; grp < tc.ngroups; grp++)
-            if (launch_mac_tc(c, tc, gr, ca->img + (size_t)grp * tc.group_bytes, tc.ntiles, 0,
-                              (unsigned char *)rimg + (size_t)grp * gr.group_bytes, tile_lo, tile_hi, col_lo, col_hi, grp > 0, d_cv,
-                              c->stream))
-                return -1;
+        for (const MacPart &pt : parts)
+            for (int grp = 0; grp < tc.ngroups; grp += gf)
+                if (launch_mac_tc(c, tc, pt.gr, pimg + (size_t)grp * p_gstride, p_gstride, img_ntiles, img_tile0,
+                                  pt.rimg + (size_t)grp * pt.gr.group_bytes, pt.gr.group_bytes, std::min(gf, tc.ngroups - grp), t0, t1, col_lo, col_hi,
+                                  grp > 0, d_cv, c->stream))
+                    return -1;
         if (g_tm) g_tm->mark(1);
         return 0;
-    }
-    // diagonals regenerated on the fly: tile chunks bounded by a temporary image of at most ~6 GiB
+    };
+    if (ca->materialised) return mac(ca->img, tc.group_bytes, tc.ntiles, 0, tile_lo, tile_hi);
+    // diagonals regenerated on the fly: tile chunks bounded by a temporary image of at most ~6 GiB; every chunk is encoded ONCE and
+    // consumed by all row parts
     const long long per_tile = tc_group_bytes(ca, 1) * tc.ngroups;
     const int tchunk = (int)std::max<long long>(1, std::min<long long>(tile_hi - tile_lo, ((long long)6 << 30) / per_tile));
     void *pimg;
@@ -534,13 +562,7 @@ static int run_mac_rows(Ctx *c, const Cache *ca, const void *R, const std::vecto
     for (int t0 = tile_lo; t0 < tile_hi; t0 += tchunk) {
         const int t1 = std::min(tile_hi, t0 + tchunk);
         if (build_p_tiles(c, ca, t0, t1, (unsigned char *)pimg)) return -1;
-        const long long gb = tc_group_bytes(ca, t1 - t0);
-        if (g_tm) g_tm->mark(3);
-        for (int grp = 0; grp < tc.ngroups; grp++)
-            if (launch_mac_tc(c, tc, gr, (unsigned char *)pimg + (size_t)grp * gb, t1 - t0, t0,
-                              (unsigned char *)rimg + (size_t)grp * gr.group_bytes, t0, t1, col_lo, col_hi, grp > 0, d_cv, c->stream))
-                return -1;
-        if (g_tm) g_tm->mark(1);
+        if (mac((const unsigned char *)pimg, tc_group_bytes(ca, t1 - t0), t1 - t0, t0, t0, t1)) return -1;
     }
     return 0;
 }
