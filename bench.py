@@ -375,8 +375,35 @@ def run_ours(args, rank, local_rank, world):
         cps._check(L.sfg_matmult4_stream_compute_dev(cps.h, C.c_void_p(d_A.data_ptr()), s, nbr, 5, 5, cache, C.c_void_p(d_out.data_ptr())),
                    "compute_dev")
 
+    R_buf = [None]
+    step_phases = dict(baby_ms=0.0, mac_ms=0.0, giant_ms=0.0, mac_kernel_ms=0.0)
+
+    def add_timings():
+        t = cps.last_timings()
+        for kx in step_phases:
+            step_phases[kx] += t[kx]
+
     def step_dev():
-        compute_dev()
+        for kx in step_phases:
+            step_phases[kx] = 0.0
+        if world == 1 or args.no_baby_sharding or s > 16:
+            compute_dev()
+            add_timings()
+        else:
+            # baby-step sharding: 1/world of the rotation-cache entries per rank, ONE all-gather over NVLink, then MAC + giant-step sums
+            chunk = int(L.sfg_matmult4_baby_chunk_bytes(cps.h, cache, s, world))
+            if R_buf[0] is None:
+                R_buf[0] = torch.empty(world * chunk, dtype=torch.uint8, device=dev)
+            R = R_buf[0]
+            cps._check(L.sfg_matmult4_baby_dev(cps.h, C.c_void_p(d_A.data_ptr()), s, nbr, 5, 5, cache, rank, world, C.c_void_p(R.data_ptr())),
+                       "baby_dev")
+            add_timings()
+            mine = R[rank * chunk:(rank + 1) * chunk].clone()
+            dist.all_gather_into_tensor(R, mine)
+            torch.cuda.current_stream().synchronize()
+            cps._check(L.sfg_matmult4_stream_compute_r_dev(cps.h, C.c_void_p(R.data_ptr()), s, 5, cache, C.c_void_p(d_out.data_ptr())),
+                       "compute_r_dev")
+            add_timings()
         if world > 1:  # partial sums over this rank's giant steps -> the full product on every rank (modular-add all-reduce over NVLink)
             ct_mod_allreduce_(d_out, cps, 5)
 
@@ -421,7 +448,7 @@ def run_ours(args, rank, local_rank, world):
         e0.record(ext)
         for _ in range(steps):
             fn()
-            t = cps.last_timings()
+            t = step_phases if fn is step_dev or world > 1 else cps.last_timings()
             mac_ms += t["mac_kernel_ms"]
             for kx in phases:
                 phases[kx] += t[kx]
@@ -491,8 +518,9 @@ def run_ours(args, rank, local_rank, world):
                         l2_policy="inputs (%.1f GB cache per rank) larger than L2; no flush needed" % (cbytes.value / 1e9) if not otf else
                                   "every call streams freshly encoded diagonals (GBs per chunk) through HBM; larger than L2",
                         sharding=("giant-step sharding of ONE product over %d ranks: 1/%d of the cache, MAC and giant-step key-switches per "
-                                  "rank, baby steps replicated, modular-add all-reduce of the %d output ciphertexts (NCCL SUM + mod q) inside "
-                                  "the timed region" % (world, world, s * m_ct)) if world > 1 else "single GPU",
+                                  "rank, baby-step rotations %s, modular-add all-reduce of the %d output ciphertexts (NCCL SUM + mod q) inside "
+                                  "the timed region" % (world, world, "replicated" if args.no_baby_sharding else
+                                                        "sharded 1/%d per rank + one all-gather of the rotation cache" % world, s * m_ct)) if world > 1 else "single GPU",
                         encoder_rechecked_coeffs=enc_stats[0], encoder_unresolved=enc_stats[1]),
             e2e=dict(value=e2e_v, unit="GB/s", ms_per_step=ms_e2e / args.steps, h2d_bytes_per_step=int(h_A.numel() * 8),
                      d2h_bytes_per_step=int(h_out.numel() * 8) if world == 1 else int(h_out[row_lo:row_hi].numel() * 8),
@@ -541,6 +569,7 @@ def main():
     ap.add_argument("--workload", default="mm_10k_x_100k_k10_logN13", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--synthetic-inputs", action="store_true", help="uniformly random residues instead of real keys / encryptions (no decrypt check)")
+    ap.add_argument("--no-baby-sharding", action="store_true", help="N > 1: every rank repeats all baby-step rotations (no all-gather)")
     ap.add_argument("--cache-budget-gb", type=float, default=None, help="HBM budget of the diagonal cache; below the image size the diagonals are re-encoded on the fly")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -15,6 +15,8 @@ package gwas
 import "C"
 
 import (
+	"fmt"
+	"math"
 	"unsafe"
 
 	"github.com/hhcho/sfgwas/crypto"
@@ -24,6 +26,12 @@ import (
 
 // flat copies a CipherVector into one C-layout buffer [n][2][nl][N], truncated to nl limbs (= DropLevel)
 func b200Flat(X crypto.CipherVector, nl int) []uint64 {
+	// every element must carry at least nl limbs and the vector one scale: the flat device calls take ONE level / scale per operand
+	for i, ct := range X {
+		if ct.Level()+1 < nl || math.Abs(ct.Scale()/X[0].Scale()-1) > 1e-9 {
+			panic(fmt.Sprintf("b200Flat: element %d has level %d / scale %g, the vector is used at %d limbs / scale %g", i, ct.Level(), ct.Scale(), nl, X[0].Scale()))
+		}
+	}
 	N := len(X[0].Value()[0].Coeffs[0])
 	buf := make([]uint64, 0, len(X)*2*nl*N)
 	for _, ct := range X {
@@ -120,6 +128,11 @@ func b200InnerSumAll(cps *crypto.CryptoParams, X crypto.CipherVector) *ckks.Ciph
 
 // eval.Sub(a, b, a) for operands of matching scale (gwas/matmult.go:54,100)
 func b200Sub(cps *crypto.CryptoParams, a, b *ckks.Ciphertext) *ckks.Ciphertext {
+	// Lattigo's evaluator.Sub first multiplies the lower-scale operand by floor(ratio) when the scales differ by 2x or more; the device
+	// path subtracts as-is, which is only the reference's result for matching scales -- refuse anything else instead of silently diverging
+	if r := math.Max(a.Scale(), b.Scale()) / math.Min(a.Scale(), b.Scale()); math.Floor(r) > 1 {
+		panic(fmt.Sprintf("b200Sub: scales %g and %g need Lattigo's scale matching (ratio %.3f)", a.Scale(), b.Scale(), r))
+	}
 	c := b200Context(cps)
 	level := minInt(a.Level(), b.Level())
 	fa, fb := b200Flat(crypto.CipherVector{a}, level+1), b200Flat(crypto.CipherVector{b}, level+1)

@@ -21,7 +21,9 @@ import "C"
 import (
 	"fmt"
 	"math"
+	"os"
 	"runtime"
+	"strconv"
 	"sync"
 	"unsafe"
 
@@ -50,7 +52,8 @@ func b200Check(c *b200Ctx, rc C.int, what string) {
 }
 
 // cPtrs copies a Go slice of per-limb pointers into C memory (cgo: no Go pointer to Go pointer). The limb backing arrays
-// are pinned for the duration of the call with runtime.Pinner.
+// are pinned for the duration of the call with runtime.Pinner (Go >= 1.21; the reference's go.mod says 1.18: with an older toolchain
+// replace the Pinner by C.malloc'ed staging copies of the limbs -- the library never retains the pointers after a call returns).
 func cPtrs(pin *runtime.Pinner, limbs [][]uint64) (**C.uint64_t, func()) {
 	n := len(limbs)
 	arr := (**C.uint64_t)(C.malloc(C.size_t(n) * C.size_t(unsafe.Sizeof(uintptr(0)))))
@@ -71,7 +74,14 @@ func b200Context(cps *crypto.CryptoParams) *b200Ctx {
 	p := cps.Params
 	qi, pi := p.Qi(), p.Pi() // never hard-code the chain (SURVEY App. B.1)
 	c := &b200Ctx{}
-	rc := C.sfg_ctx_create(0, C.int(p.LogN()), (*C.uint64_t)(unsafe.Pointer(&qi[0])), C.int(len(qi)),
+	// device: SFG_B200_DEVICE (one process per GPU, like the torch.distributed deployment of sfgwas_b200/dist.py), default 0
+	dev := 0
+	if v := os.Getenv("SFG_B200_DEVICE"); v != "" {
+		if d, err := strconv.Atoi(v); err == nil {
+			dev = d
+		}
+	}
+	rc := C.sfg_ctx_create(C.int(dev), C.int(p.LogN()), (*C.uint64_t)(unsafe.Pointer(&qi[0])), C.int(len(qi)),
 		(*C.uint64_t)(unsafe.Pointer(&pi[0])), C.int(len(pi)), C.double(p.Scale()), nil, &c.h)
 	if rc != 0 {
 		panic("sfg_ctx_create: " + C.GoString(C.sfg_last_error(nil)))
@@ -111,7 +121,7 @@ func b200Context(cps *crypto.CryptoParams) *b200Ctx {
 	if cps.Rlk != nil {
 		b200UploadRlk(c, cps)
 	}
-	runtime.SetFinalizer(c, func(c *b200Ctx) { C.sfg_ctx_destroy(c.h) })
+	// released explicitly with B200Release (b200Ctxs keeps the context reachable, so a finalizer would never run)
 	b200Ctxs[cps] = c
 	return c
 }
@@ -168,6 +178,33 @@ func MatMult4StreamPreprocess(cryptoParams *crypto.CryptoParams, gfs *GenoFileSt
 	b200Mu.Unlock()
 }
 
+// B200ReleaseCache frees the HBM-resident diagonal cache registered under cacheFilePrefix (the reference's cache lives in files and
+// costs no memory between calls; here a 10k x 100k cache is 55 GB of HBM, so the protocol driver releases X / XT caches when PCA ends).
+func B200ReleaseCache(cacheFilePrefix string) {
+	b200Mu.Lock()
+	defer b200Mu.Unlock()
+	if cache, ok := b200Caches[cacheFilePrefix]; ok {
+		C.sfg_cache_destroy(cache)
+		delete(b200Caches, cacheFilePrefix)
+	}
+}
+
+// B200Release destroys the GPU context of cps together with every cache (end of the protocol run; the finalizer alone never fires
+// because b200Ctxs keeps the context reachable).
+func B200Release(cps *crypto.CryptoParams) {
+	b200Mu.Lock()
+	defer b200Mu.Unlock()
+	for k, cache := range b200Caches {
+		C.sfg_cache_destroy(cache)
+		delete(b200Caches, k)
+	}
+	if c, ok := b200Ctxs[cps]; ok {
+		C.sfg_ctx_destroy(c.h)
+		c.h = nil
+		delete(b200Ctxs, cps)
+	}
+}
+
 // MatMult4StreamCompute: gwas/matmult.go:1043-1236.
 func MatMult4StreamCompute(cryptoParams *crypto.CryptoParams, A crypto.CipherMatrix, maxLevel int, cacheFilePrefix string) crypto.CipherMatrix {
 	c := b200Context(cryptoParams)
@@ -189,6 +226,7 @@ func MatMult4StreamCompute(cryptoParams *crypto.CryptoParams, A crypto.CipherMat
 	}
 	var mct, nbr C.int
 	C.sfg_cache_info(cache, nil, nil, nil, &mct, &nbr)
+	_ = nbr // the library checks len(A[0]) against the cache's block rows and reports the reference-style error
 	s := len(A)
 	outScale := A[0][0].Scale() * cryptoParams.Params.Scale() // gwas/matmult.go:1045
 	S := make(crypto.CipherMatrix, s)
@@ -205,7 +243,8 @@ func MatMult4StreamCompute(cryptoParams *crypto.CryptoParams, A crypto.CipherMat
 	oPtrs, freeO := cPtrs(&pin, ctLimbs(S))
 	defer freeO()
 	c.mu.Lock()
-	rc := C.sfg_matmult4_stream_compute_ptrs(c.h, aPtrs, C.int(s), nbr, C.int(A[0][0].Level()), C.int(maxLevel), cache, oPtrs)
+	// num_block_rows = len(A[0]): the pointer list is built from A, so a mismatch with the cache is caught by the library's check_args
+	rc := C.sfg_matmult4_stream_compute_ptrs(c.h, aPtrs, C.int(s), C.int(len(A[0])), C.int(A[0][0].Level()), C.int(maxLevel), cache, oPtrs)
 	c.mu.Unlock()
 	b200Check(c, rc, "MatMult4StreamCompute")
 	// reference semantics: out starts as a FRESH randomised encryption of zero and the sum is added with eva.Add

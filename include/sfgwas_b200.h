@@ -88,6 +88,15 @@ int sfg_matmult4_stream_preprocess_rows(sfg_ctx *ctx, const sfg_geno *g, int max
  * S_part[i][bj] = sum_{g in share} RotL_{g d}(reduce(acc[i][g])[bj]) (gwas/matmult.go:1203-1227 is a mod-q sum over g, so the shares
  * add up bit-exactly): combine with an integer SUM all-reduce of the canonical residues + sfg_ct_mod_reduce. */
 int sfg_matmult4_stream_preprocess_giants(sfg_ctx *ctx, const sfg_geno *g, int max_level, int part, int nparts, sfg_cache **out);
+/* baby-step sharding on top of it (the baby rotations RotL_b(A[i][bi]), gwas/matmult.go:1083-1119, are the part every rank would otherwise
+ * repeat): rank `part` of `nparts` rotates its share of the K = (block row, baby step) entries into the DEVICE buffer d_R, laid out as
+ * nparts chunks of sfg_matmult4_baby_chunk_bytes() -- chunk r is exactly rank r's share, so ONE all-gather over NVLink completes the buffer --
+ * and sfg_matmult4_stream_compute_r_dev runs the rest of Compute (MAC + giant-step sums over this rank's cache) on the complete buffer.
+ * d_A [s][nbr][2][level_a+1][N] is a DEVICE pointer; s <= 16. */
+size_t sfg_matmult4_baby_chunk_bytes(const sfg_ctx *ctx, const sfg_cache *cache, int s, int nparts);
+int sfg_matmult4_baby_dev(sfg_ctx *ctx, const uint64_t *d_A, int s, int num_block_rows, int level_a, int max_level, const sfg_cache *cache, int part,
+                          int nparts, void *d_R);
+int sfg_matmult4_stream_compute_r_dev(sfg_ctx *ctx, const void *d_R, int s, int max_level, const sfg_cache *cache, uint64_t *d_out);
 /* x mod q_l on npoly DEVICE polynomials [nl][N] (sums of up to 2^8 canonical residues after an integer all-reduce) */
 int sfg_ct_mod_reduce(sfg_ctx *ctx, uint64_t *d_polys, size_t npoly, int nl);
 void sfg_cache_destroy(sfg_cache *cache);
@@ -179,6 +188,24 @@ int sfg_ct_add2(sfg_ctx *ctx, int level, const uint64_t *a, int na, int a_nl, co
 int sfg_inner_sum_all(sfg_ctx *ctx, int level, const uint64_t *cts, int nvec, int cnt, uint64_t *out);
 /* EncodeNTT of an int8 slot vector v[slots] at params.Scale (the 0/1 mask of crypto.MaskTrunc), correctly rounded: out [level+1][N] */
 int sfg_encode_slots_i8(sfg_ctx *ctx, const int8_t *v, int level, int mont, uint64_t *out);
+
+/* ---- local arithmetic of the collective bootstrap (mpc/mhe.go:262-341: CollectiveBootstrap / CollectiveBootstrapMat) ----
+ * What every party computes per ciphertext around the two network aggregations (AggregateRefreshShare*, which stay in Go).  The random
+ * draws stay in Go as well -- the mask (ring.RandInt, crypto/rand), the Gaussian noise, the common reference polynomial `crp` of the
+ * shared PRG (crpGen.ReadNew()) -- and are handed over; the library does the exact arithmetic of dckks.RefreshProtocol
+ * (un-vendored Lattigo fork: restated from the published v2.1 algorithm, oracle/refresh.py, [UNVERIFIED vs the fork]).
+ * refProtocol.GenShares (mhe.go:303-311) for nct ciphertexts at `level`:
+ *   c1 [nct][level+1][N]; sk_mont [nQ][N] = cps.Sk.Value.Coeffs (NTT + Montgomery form, as Lattigo stores it); crp [nct][nQ][N];
+ *   mask as sign-magnitude big integers: mask_mag [nct][N][nwords] little-endian 64-bit words (big.Int.Bits()), mask_sign [nct][N] (big.Int.Sign());
+ *   in_scale = ct.Scale(), out_scale = targetScale = params.Scale() (the recrypt share carries the mask scaled by their ratio);
+ *   e0 / e1 [nct][N] the Gaussian noise coefficients  ->  share_decrypt [nct][level+1][N], share_recrypt [nct][nQ][N]. */
+int sfg_refresh_gen_shares(sfg_ctx *ctx, int level, int nct, const uint64_t *c1, const uint64_t *sk_mont, const uint64_t *crp,
+                           const uint64_t *mask_mag, const int8_t *mask_sign, int nwords, double in_scale, double out_scale, const int64_t *e0,
+                           const int64_t *e1, uint64_t *share_decrypt, uint64_t *share_recrypt);
+/* refProtocol.Decrypt + Recode + Recrypt (mhe.go:316-318): c0 [nct][c0_nl >= level+1][N] of the ciphertexts, the aggregated shares, the
+ * same crp; in_scale = ct.Scale(), out_scale = params.Scale()  ->  out [nct][2][nQ][N]: refreshed ciphertexts at the top level, scale out_scale */
+int sfg_refresh_finish(sfg_ctx *ctx, int level, int nct, const uint64_t *c0, int c0_nl, double in_scale, double out_scale,
+                       const uint64_t *agg_decrypt, const uint64_t *agg_recrypt, const uint64_t *crp, uint64_t *out);
 
 /* synchronise the context's stream (timing helper) */
 int sfg_ctx_sync(sfg_ctx *ctx);

@@ -6,4 +6,4 @@ host-side mirror of the reference interface (``gwas.py``).  There is no CPU fall
 from ._lib import LIB_PATH, SYMBOLS, SfgError, load  # noqa: F401
 from .gwas import (CAdd, Ciphertext, CMult, CMultScalar, CryptoParams, CSub, DiagCache, GenoFileStream,  # noqa: F401
                    InnerProd, InnerSumAll, LoadCipherMatrixFromFile, MaskTrunc, MatMult4Stream, MatMult4StreamCompute, MatMult4StreamPreprocess,
-                   QXLazyNormStream, QXtLazyNormStream, SaveCipherMatrixToFile, SetRelinKey)
+                   QXLazyNormStream, QXtLazyNormStream, RefreshFinish, RefreshGenShares, SaveCipherMatrixToFile, SetRelinKey)

@@ -26,6 +26,8 @@ SYMBOLS = [
     "sfg_geno_count_sketch", "sfg_ntt_dev", "sfg_rotate_right_dev",
     "sfg_matmult4_stream_preprocess_rows", "sfg_matmult4_stream_preprocess_giants", "sfg_ct_mod_reduce",
     "sfg_matmult4_finish_dev", "sfg_cipher_matrix_save", "sfg_cipher_matrix_info", "sfg_cipher_matrix_load",
+    "sfg_refresh_gen_shares", "sfg_refresh_finish", "sfg_matmult4_baby_chunk_bytes", "sfg_matmult4_baby_dev",
+    "sfg_matmult4_stream_compute_r_dev",
 ]
 
 _lib = None
@@ -105,6 +107,12 @@ def load():
     L.sfg_cipher_matrix_save.argtypes = [C.c_char_p, i32, vp, vp, i32, i32, i32]
     L.sfg_cipher_matrix_info.argtypes = [C.c_char_p, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
     L.sfg_cipher_matrix_load.argtypes = [C.c_char_p, i32, vp, vp, i32, i32, i32]
+    L.sfg_refresh_gen_shares.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp, i32, C.c_double, C.c_double, vp, vp, vp, vp]
+    L.sfg_refresh_finish.argtypes = [vp, i32, i32, vp, i32, C.c_double, C.c_double, vp, vp, vp, vp]
+    L.sfg_matmult4_baby_chunk_bytes.restype = sz
+    L.sfg_matmult4_baby_chunk_bytes.argtypes = [vp, vp, i32, i32]
+    L.sfg_matmult4_baby_dev.argtypes = [vp, vp, i32, i32, i32, i32, vp, i32, i32, vp]
+    L.sfg_matmult4_stream_compute_r_dev.argtypes = [vp, vp, i32, i32, vp, vp]
     L.sfg_ctx_sync.argtypes = [vp]
     L.sfg_ctx_last_timings.argtypes = [vp, C.POINTER(C.c_float)]
     L.sfg_ctx_stream.restype = vp

@@ -12,7 +12,7 @@ LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libsfgwas_b200.so")
 OBJ = os.path.join(HERE, "build")
 
-CU = ["ctx.cu", "hostio.cu", "kernels_ntt.cu", "kernels_encode.cu", "kernels_mactc.cu", "kernels_ks.cu", "kernels_ctalg.cu", "kernels_geno.cu", "kernels_cachefile.cu", "matmult.cu", "capi.cu"]
+CU = ["ctx.cu", "hostio.cu", "kernels_ntt.cu", "kernels_encode.cu", "kernels_mactc.cu", "kernels_ks.cu", "kernels_ctalg.cu", "kernels_geno.cu", "kernels_cachefile.cu", "kernels_refresh.cu", "matmult.cu", "capi.cu"]
 CPP = ["hostmath.cpp", "cmfile.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "-Xptxas", "-v"]

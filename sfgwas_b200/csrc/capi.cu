@@ -433,6 +433,16 @@ int sfg_cv_mod_reduce(sfg_ctx *h, const sfg_cache *cache, int s, int max_level, 
     SFG_CUDA(c, cudaStreamSynchronize(c->stream));
     return 0;
 }
+size_t sfg_matmult4_baby_chunk_bytes(const sfg_ctx *, const sfg_cache *cache, int s, int nparts) {
+    return nparts < 1 ? 0 : mm_baby_chunk_bytes(cache->ca, s, nparts);
+}
+int sfg_matmult4_baby_dev(sfg_ctx *h, const uint64_t *d_A, int s, int nbr, int level_a, int max_level, const sfg_cache *cache, int part, int nparts,
+                          void *d_R) {
+    return mm_baby_dev(&h->c, d_A, s, nbr, level_a, max_level, cache->ca, part, nparts, d_R);
+}
+int sfg_matmult4_stream_compute_r_dev(sfg_ctx *h, const void *d_R, int s, int max_level, const sfg_cache *cache, uint64_t *d_out) {
+    return mm_compute_r_dev(&h->c, d_R, s, max_level, cache->ca, d_out);
+}
 int sfg_ct_mod_reduce(sfg_ctx *h, uint64_t *d_polys, size_t npoly, int nl) {
     Ctx *c = &h->c;
     if (nl < 1 || nl > c->nQ) SFG_FAIL(c, "ct_mod_reduce: bad limb count %d", nl);
@@ -615,6 +625,53 @@ int sfg_inner_sum_all(sfg_ctx *h, int level, const uint64_t *cts, int nvec, int 
     if (inner_sum_all_dev(c, level, io.in[0].as<uint64_t>(), nvec, cnt, io.out.as<uint64_t>())) return -1;
     return io.down(out, (size_t)nvec * ct);
 }
+// ---- local arithmetic of the collective bootstrap (mpc/mhe.go:262-341) ----
+int sfg_refresh_gen_shares(sfg_ctx *h, int level, int nct, const uint64_t *c1, const uint64_t *sk_mont, const uint64_t *crp, const uint64_t *mask_mag,
+                           const int8_t *mask_sign, int nwords, double in_scale, double out_scale, const int64_t *e0, const int64_t *e1, uint64_t *share_decrypt,
+                           uint64_t *share_recrypt) {
+    Ctx *c = &h->c;
+    if (level < 0 || level >= c->nQ || nct < 1 || nwords < 1) SFG_FAIL(c, "sfg_refresh_gen_shares: bad level / counts");
+    SFG_CUDA(c, cudaSetDevice(c->device));
+    const size_t N = c->N, nl = level + 1, nQ = c->nQ, n = nct;
+    Buf dc1, dsk, dcrp, dm, dsg, de0, de1, dh0, dh1;
+    struct { Buf *b; const void *src; size_t bytes; } in[] = {{&dc1, c1, n * nl * N * 8}, {&dsk, sk_mont, nQ * N * 8}, {&dcrp, crp, n * nQ * N * 8},
+                                                              {&dm, mask_mag, n * N * nwords * 8}, {&dsg, mask_sign, n * N}, {&de0, e0, n * N * 8},
+                                                              {&de1, e1, n * N * 8}};
+    for (auto &x : in) {
+        if (x.b->alloc(c, x.bytes)) return -1;
+        SFG_CUDA(c, cudaMemcpyAsync(x.b->p, x.src, x.bytes, cudaMemcpyDefault, c->stream));
+    }
+    if (dh0.alloc(c, n * nl * N * 8) || dh1.alloc(c, n * nQ * N * 8)) return -1;
+    if (refresh_gen_shares_dev(c, level, nct, dc1.as<uint64_t>(), dsk.as<uint64_t>(), dcrp.as<uint64_t>(), dm.as<uint64_t>(), dsg.as<int8_t>(), nwords,
+                               in_scale, out_scale, de0.as<long long>(), de1.as<long long>(), dh0.as<uint64_t>(), dh1.as<uint64_t>()))
+        return -1;
+    SFG_CUDA(c, cudaMemcpyAsync(share_decrypt, dh0.p, n * nl * N * 8, cudaMemcpyDefault, c->stream));
+    SFG_CUDA(c, cudaMemcpyAsync(share_recrypt, dh1.p, n * nQ * N * 8, cudaMemcpyDefault, c->stream));
+    SFG_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+int sfg_refresh_finish(sfg_ctx *h, int level, int nct, const uint64_t *c0, int c0_nl, double in_scale, double out_scale, const uint64_t *agg_decrypt,
+                       const uint64_t *agg_recrypt, const uint64_t *crp, uint64_t *out) {
+    Ctx *c = &h->c;
+    if (level < 0 || level >= c->nQ || nct < 1 || c0_nl < level + 1) SFG_FAIL(c, "sfg_refresh_finish: bad level / counts");
+    SFG_CUDA(c, cudaSetDevice(c->device));
+    const size_t N = c->N, nl = level + 1, nQ = c->nQ, n = nct;
+    Buf dc0, da0, da1, dcrp, dout;
+    struct { Buf *b; const void *src; size_t bytes; } in[] = {{&dc0, c0, n * c0_nl * N * 8}, {&da0, agg_decrypt, n * nl * N * 8},
+                                                              {&da1, agg_recrypt, n * nQ * N * 8}, {&dcrp, crp, n * nQ * N * 8}};
+    for (auto &x : in) {
+        if (x.b->alloc(c, x.bytes)) return -1;
+        SFG_CUDA(c, cudaMemcpyAsync(x.b->p, x.src, x.bytes, cudaMemcpyDefault, c->stream));
+    }
+    if (dout.alloc(c, n * 2 * nQ * N * 8)) return -1;
+    if (refresh_finish_dev(c, level, nct, dc0.as<uint64_t>(), c0_nl, in_scale, out_scale, da0.as<uint64_t>(), da1.as<uint64_t>(), dcrp.as<uint64_t>(),
+                           dout.as<uint64_t>()))
+        return -1;
+    SFG_CUDA(c, cudaMemcpyAsync(out, dout.p, n * 2 * nQ * N * 8, cudaMemcpyDefault, c->stream));
+    SFG_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
 int sfg_encode_slots_i8(sfg_ctx *h, const int8_t *v, int level, int mont, uint64_t *out) { return encode_slots_host(&h->c, v, level, mont != 0, out); }
 
 }  // extern "C"

@@ -387,8 +387,10 @@ static int fill_scratch(Ctx *c, KsBatch &kb, int max_nct, int max_c2) {
 //     gwas/matmult.go:1083-1119 : rotCache[i][baby] = RotateRightWithEvaluator(A[i][bi], -baby)
 //     ONE batch over every (baby step, i, bi): each entry carries its own Galois key; INTT(c1) is shared by all baby steps.
 // ---------------------------------------------------------------------------------------------------------------
+// k_lo / k_hi: only the entries whose position in klist lies in [k_lo, k_hi) are computed (baby-step sharding: every rank rotates its share
+// and the shares are all-gathered); R_ext: write into this buffer (laid out like the workspace one) instead of the context's workspace
 static int build_rot_cache(Ctx *c, const Cache *ca, const uint64_t *d_A, int s, int levelA, int bi_lo, int bi_hi,
-                           std::vector<int> &klist, void **R_out) {
+                           std::vector<int> &klist, void **R_out, int k_lo = 0, int k_hi = 0x7fffffff, void *R_ext = nullptr) {
     const int d = ca->d, nbr = ca->nbr, N = c->N, nlA = levelA + 1, nrows = 2 * s;
     klist.clear();
     std::vector<int> klocal((size_t)nbr * d, -1);
@@ -398,8 +400,8 @@ static int build_rot_cache(Ctx *c, const Cache *ca, const uint64_t *d_A, int s, 
             klist.push_back((int)k);
         }
     const size_t RB = (size_t)ca->lay.bytes;  // bytes of one (k, row) record
-    void *R;
-    if (ws_get(c, WS_R, std::max<size_t>(klist.size(), 1) * nrows * RB, &R)) return -1;
+    void *R = R_ext;
+    if (!R && ws_get(c, WS_R, std::max<size_t>(klist.size(), 1) * nrows * RB, &R)) return -1;
     *R_out = R;
     const size_t ctA = (size_t)2 * nlA * N;
     RotMeta rot, cpy;
@@ -414,6 +416,7 @@ static int build_rot_cache(Ctx *c, const Cache *ca, const uint64_t *d_A, int s, 
         }
         for (int bi = bi_lo; bi < bi_hi; bi++) {
             if (!ca->baby[(size_t)bi * d + b]) continue;
+            if (klocal[(size_t)bi * d + b] < k_lo || klocal[(size_t)bi * d + b] >= k_hi) continue;
             for (int i = 0; i < s; i++) {
                 const long long in_off = (long long)(((size_t)i * nbr + bi) * ctA);
                 const long long out_off = (long long)(((size_t)klocal[(size_t)bi * d + b] * nrows + 2 * i) * RB);
@@ -759,7 +762,9 @@ static int check_rows(Ctx *c, const Cache *ca, int bi_lo, int bi_hi) {
 constexpr int kMaxRowsPerPass = 16;
 
 // one pass over rows [0, s) of d_A / d_out (s <= kMaxRowsPerPass); ms accumulates the phase timings
-static int mm_compute_rows(Ctx *c, const uint64_t *d_A, int s, int nbr, int levelA, Cache *ca, uint64_t *d_out, HostSink *sink, float ms[5]) {
+// R_ext (optional): the rotation cache was computed beforehand (baby-step sharding: sfg_matmult4_baby_dev + all-gather); d_A is then unused
+static int mm_compute_rows(Ctx *c, const uint64_t *d_A, int s, int nbr, int levelA, Cache *ca, uint64_t *d_out, HostSink *sink, float ms[5],
+                           const void *R_ext = nullptr) {
     const int L = ca->L, N = c->N, m_ct = ca->m_ct;
     const size_t LN = (size_t)L * N;
     PhaseTimer tm(c->stream);
@@ -768,7 +773,12 @@ static int mm_compute_rows(Ctx *c, const uint64_t *d_A, int s, int nbr, int leve
     void *R;
     std::vector<int> klist;
     tm.mark(0);
-    if (build_rot_cache(c, ca, d_A, s, levelA, 0, nbr, klist, &R)) return -1;
+    if (R_ext) {
+        R = const_cast<void *>(R_ext);
+        for (size_t k = 0; k < ca->kbi.size(); k++) klist.push_back((int)k);
+    } else if (build_rot_cache(c, ca, d_A, s, levelA, 0, nbr, klist, &R)) {
+        return -1;
+    }
     SFG_CUDA(c, cudaMemsetAsync(d_out, 0, (size_t)s * m_ct * 2 * LN * 8, c->stream));
     // giant chunks bounded by the cv image size (default 24 GiB)
     const size_t per_g = (size_t)m_ct * 2 * s * LN * 8;
@@ -848,6 +858,40 @@ int mm_compute_dev(Ctx *c, const uint64_t *d_A, int s, int nbr, int levelA, int 
     }
     if (rc) return -1;
     SFG_CUDA(c, e);
+    return 0;
+}
+
+// Baby-step sharding (strong scaling on top of the giant-step sharding: the baby rotations are the part every rank would otherwise
+// repeat): share `part` of `nparts` of the K rotation-cache entries, written at their global positions of d_R ([K_pad][2s][record]).
+size_t mm_baby_chunk_bytes(const Cache *ca, int s, int nparts) {
+    const size_t K = ca->kbi.size(), per = (K + nparts - 1) / nparts;
+    return per * 2 * s * (size_t)ca->lay.bytes;
+}
+int mm_baby_dev(Ctx *c, const uint64_t *d_A, int s, int nbr, int levelA, int maxLevel, Cache *ca, int part, int nparts, void *d_R) {
+    if (check_args(c, ca, s, nbr, levelA, maxLevel) || check_rows(c, ca, 0, nbr)) return -1;
+    if (s > kMaxRowsPerPass) SFG_FAIL(c, "s = %d ciphertext rows: the sharded pieces take at most %d per call (split A by rows)", s, kMaxRowsPerPass);
+    if (nparts < 1 || part < 0 || part >= nparts) SFG_FAIL(c, "baby-step share %d of %d", part, nparts);
+    SFG_CUDA(c, cudaSetDevice(c->device));
+    const int K = (int)ca->kbi.size(), per = (K + nparts - 1) / nparts;
+    PhaseTimer tm(c->stream);
+    tm.mark(0);
+    std::vector<int> klist;
+    void *R;
+    if (build_rot_cache(c, ca, d_A, s, levelA, 0, nbr, klist, &R, part * per, std::min(K, (part + 1) * per), d_R)) return -1;
+    tm.mark(-1);
+    tm.finish(g_last_ms);
+    SFG_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+// the rest of MatMult4StreamCompute on a complete rotation cache d_R (after the all-gather of the shares)
+int mm_compute_r_dev(Ctx *c, const void *d_R, int s, int maxLevel, Cache *ca, uint64_t *d_out) {
+    if (check_args(c, ca, s, ca->nbr, maxLevel, maxLevel) || check_rows(c, ca, 0, ca->nbr)) return -1;
+    if (s > kMaxRowsPerPass) SFG_FAIL(c, "s = %d ciphertext rows: the sharded pieces take at most %d per call (split A by rows)", s, kMaxRowsPerPass);
+    SFG_CUDA(c, cudaSetDevice(c->device));
+    float ms[5] = {0, 0, 0, 0, 0};
+    if (mm_compute_rows(c, nullptr, s, ca->nbr, maxLevel, ca, d_out, nullptr, ms, d_R)) return -1;
+    for (int i = 0; i < 5; i++) g_last_ms[i] = ms[i];
+    SFG_CUDA(c, cudaStreamSynchronize(c->stream));
     return 0;
 }
 

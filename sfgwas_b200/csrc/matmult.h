@@ -80,6 +80,10 @@ int cache_load_files(Ctx *c, const char *prefix, size_t nrows, size_t ncols, int
 // out_limbs (optional, instead of host_out): one HOST pointer per limb of the result, [((i*m_ct+bj)*2+c)*maxLevel+l] (cgo callers)
 int mm_compute_dev(Ctx *c, const uint64_t *d_A, int s, int nbr, int levelA, int maxLevel, Cache *cache, uint64_t *d_out,
                    uint64_t *host_out = nullptr, uint64_t *const *out_limbs = nullptr);
+// baby-step sharding (matmult.cu): share `part` of `nparts` of the rotation cache into d_R; the remainder of Compute on a complete d_R
+size_t mm_baby_chunk_bytes(const Cache *ca, int s, int nparts);
+int mm_baby_dev(Ctx *c, const uint64_t *d_A, int s, int nbr, int levelA, int maxLevel, Cache *cache, int part, int nparts, void *d_R);
+int mm_compute_r_dev(Ctx *c, const void *d_R, int s, int maxLevel, Cache *cache, uint64_t *d_out);
 // multi-GPU pieces
 int mm_partial_dev(Ctx *c, const uint64_t *d_A, int s, int nbr, int levelA, int maxLevel, Cache *cache, int bi_lo, int bi_hi,
                    uint64_t *d_cv);
@@ -97,6 +101,13 @@ int inner_sum_all_dev(Ctx *c, int level, const uint64_t *d_in, int nvec, int cnt
 int geno_count_sketch(Ctx *c, const Geno *g, const int32_t *rand_index, const int8_t *sgn, int kp, double *sketch, uint64_t *xsum, uint64_t *x2sum,
                       float *ms);
 int encode_slots_host(Ctx *c, const int8_t *v, int level, bool mont, uint64_t *out);
+
+// local arithmetic of the collective bootstrap (kernels_refresh.cu; mpc/mhe.go:262-341): device pointers
+int refresh_gen_shares_dev(Ctx *c, int level, int nct, const uint64_t *d_c1, const uint64_t *d_sk, const uint64_t *d_crp, const uint64_t *d_mask,
+                           const int8_t *d_sign, int nwords, double in_scale, double out_scale, const long long *d_e0, const long long *d_e1, uint64_t *d_h0,
+                           uint64_t *d_h1);
+int refresh_finish_dev(Ctx *c, int level, int nct, const uint64_t *d_c0, int c0_nl, double in_scale, double out_scale, const uint64_t *d_agg0,
+                       const uint64_t *d_agg1, const uint64_t *d_crp, uint64_t *d_out);
 
 extern thread_local float g_last_ms[5];  // baby, mac phase, giant, total, mac kernel only
 

@@ -6,8 +6,9 @@ Three shardings, all bit-identical to the single-GPU result:
   (g, bj) of the dense contraction: 1/world of the diagonal cache, of the MAC and of the giant-step key-switches.
   ``out[i][bj] = sum_g RotL_{g d}(cv[i][g][bj])`` is a mod-q sum over g (gwas/matmult.go:1223-1227), so the per-rank partial outputs
   are combined by ONE modular-add all-reduce of ``s * m_ct`` ciphertexts over NVLink (NCCL integer SUM + ``sfg_ct_mod_reduce``); the
-  d giant steps balance over 2 / 4 / 8 ranks whatever the number of block columns.  The baby-step rotations are recomputed by every
-  rank (7 % of a single-GPU step).  This is what ``bench.py --gpus N`` measures.
+  d giant steps balance over 2 / 4 / 8 ranks whatever the number of block columns.  The baby-step rotations (7 % of a single-GPU step,
+  but a third of an 8-GPU one if every rank repeated them) are sharded as well: 1/world of the (block row, baby step) entries per rank,
+  completed by one all-gather of the rotation cache.  This is what ``bench.py --gpus N`` measures.
 
 * ``ColumnSharded`` -- SNP-block (= block-column) sharding for Q.X-shaped products with X = nind x nsnp: rank r owns a contiguous
   range of block columns; every accumulator (i, giant, bj), its reduce, its giant rotations and the final add are independent
@@ -123,22 +124,54 @@ def mod_reduce_scatter_(t, share: int, cps: CryptoParams = None, nl: int = 0, gr
 
 class GiantSharded:
     """Strong scaling of ONE MatMult4StreamCompute over the GPUs of a box: rank `rank` of `world` holds the diagonals of its share of the
-    giant steps and produces the partial sum over them; ``compute`` all-reduces the partial outputs mod q (device-resident throughout)."""
+    giant steps and produces the partial sum over them; ``compute`` all-reduces the partial outputs mod q (device-resident throughout).
+    With ``shard_baby`` (default) the baby-step rotations -- which every rank would otherwise repeat -- are sharded too: every rank rotates
+    1/world of the (block row, baby step) entries and ONE all-gather over NVLink completes the rotation cache on every rank."""
 
-    def __init__(self, cps: CryptoParams, gfs: GenoFileStream, rank: int, world: int, max_level: int = 5):
+    def __init__(self, cps: CryptoParams, gfs: GenoFileStream, rank: int, world: int, max_level: int = 5, shard_baby: bool = True):
         self.cps, self.rank, self.world, self.max_level = cps, rank, world, max_level
+        self.shard_baby = shard_baby and world > 1
         h = C.c_void_p()
         cps._check(cps.L.sfg_matmult4_stream_preprocess_giants(cps.h, gfs.h, max_level, rank, world, C.byref(h)),
                    "sfg_matmult4_stream_preprocess_giants")
         self.cache = DiagCache(cps, h)
+        self._R = None
+        self.phases_ms = dict(baby_ms=0.0, mac_ms=0.0, giant_ms=0.0, mac_kernel_ms=0.0)  # of the last compute_dev
 
     def compute_dev(self, d_A, d_out, s: int, nbr: int, level_a: int, group=None):
         """d_A [s][nbr][2][level_a+1][N], d_out [s][m_ct][2][max_level][N]: int64 CUDA tensors; d_out = the FULL product on every rank."""
-        cps = self.cps
-        cps._check(cps.L.sfg_matmult4_stream_compute_dev(cps.h, C.c_void_p(d_A.data_ptr()), s, nbr, level_a, self.max_level, self.cache.h,
+        import torch
+        import torch.distributed as dist
+
+        cps, L = self.cps, self.cps.L
+        ph = dict(baby_ms=0.0, mac_ms=0.0, giant_ms=0.0, mac_kernel_ms=0.0)
+
+        def add_timings():
+            t = cps.last_timings()
+            for k in ph:
+                ph[k] += t[k]
+
+        if self.shard_baby and s <= 16:
+            chunk = int(L.sfg_matmult4_baby_chunk_bytes(cps.h, self.cache.h, s, self.world))
+            if self._R is None or self._R.numel() != self.world * chunk:
+                self._R = torch.empty(self.world * chunk, dtype=torch.uint8, device=d_A.device)
+            R = self._R
+            cps._check(L.sfg_matmult4_baby_dev(cps.h, C.c_void_p(d_A.data_ptr()), s, nbr, level_a, self.max_level, self.cache.h, self.rank,
+                                               self.world, C.c_void_p(R.data_ptr())), "sfg_matmult4_baby_dev")
+            add_timings()
+            mine = R[self.rank * chunk:(self.rank + 1) * chunk].clone()
+            dist.all_gather_into_tensor(R, mine, group=group)
+            torch.cuda.current_stream().synchronize()
+            cps._check(L.sfg_matmult4_stream_compute_r_dev(cps.h, C.c_void_p(R.data_ptr()), s, self.max_level, self.cache.h,
+                                                           C.c_void_p(d_out.data_ptr())), "sfg_matmult4_stream_compute_r_dev")
+            add_timings()
+        else:
+            cps._check(L.sfg_matmult4_stream_compute_dev(cps.h, C.c_void_p(d_A.data_ptr()), s, nbr, level_a, self.max_level, self.cache.h,
                                                          C.c_void_p(d_out.data_ptr())), "sfg_matmult4_stream_compute_dev")
+            add_timings()
         if self.world > 1:
             ct_mod_allreduce_(d_out, cps, self.max_level, group)
+        self.phases_ms = ph
         return d_out
 
     def compute(self, A: np.ndarray, group=None) -> np.ndarray:

@@ -21,7 +21,7 @@ import numpy as np
 from ._lib import SfgError, load
 
 __all__ = [
-    "SaveCipherMatrixToFile", "LoadCipherMatrixFromFile",
+    "SaveCipherMatrixToFile", "LoadCipherMatrixFromFile", "RefreshGenShares", "RefreshFinish",
     "CryptoParams", "GenoFileStream", "DiagCache", "MatMult4StreamPreprocess", "MatMult4StreamCompute", "MatMult4Stream",
     "SfgError", "Ciphertext", "SetRelinKey", "CMult", "CMultScalar", "CSub", "CAdd", "InnerSumAll", "InnerProd", "MaskTrunc",
     "QXLazyNormStream", "QXtLazyNormStream",
@@ -355,6 +355,61 @@ def LoadCipherMatrixFromFile(cps, filename: str):
     if L.sfg_cipher_matrix_load(str(filename).encode(), logN.value, _p(cts), _p(sc), nr.value, nc.value, lvl.value) != 0:
         raise SfgError("LoadCipherMatrixFromFile: " + L.sfg_last_error(None).decode())
     return [[Ciphertext(cts[i, j], sc[i, j]) for j in range(nc.value)] for i in range(nr.value)]
+
+
+def _bigints_to_words(vals, nwords=None):
+    """Python ints [nct][N] -> (magnitude words [nct][N][nwords] little-endian uint64, sign [nct][N] int8): big.Int.Bits() / Sign()."""
+    nct, N = len(vals), len(vals[0])
+    if nwords is None:
+        nwords = max(1, max((abs(int(v)).bit_length() + 63) // 64 for row in vals for v in row))
+    mag = np.zeros((nct, N, nwords), dtype=np.uint64)
+    sign = np.zeros((nct, N), dtype=np.int8)
+    mask64 = (1 << 64) - 1
+    for t in range(nct):
+        for j in range(N):
+            v = int(vals[t][j])
+            sign[t, j] = (v > 0) - (v < 0)
+            a = abs(v)
+            for w in range(nwords):
+                mag[t, j, w] = (a >> (64 * w)) & mask64
+    return mag, sign, nwords
+
+
+def RefreshGenShares(cps: CryptoParams, level: int, c1: np.ndarray, sk_mont: np.ndarray, crp: np.ndarray, mask, e0, e1, in_scale: float = None,
+                     out_scale: float = None):
+    """dckks.RefreshProtocol.GenShares for nct ciphertexts (mpc/mhe.go:303-311 inside CollectiveBootstrap / CollectiveBootstrapMat).
+    c1 [nct][level+1][N]; sk_mont [nQ][N] (cps.Sk.Value.Coeffs: NTT + Montgomery form); crp [nct][nQ][N] (crpGen.ReadNew()); mask [nct][N]
+    Python ints (ring.RandInt draws, centred); e0 / e1 [nct][N] Gaussian noise; in_scale = ct.Scale(), out_scale = targetScale.  Returns (shareDecrypt [nct][level+1][N], shareRecrypt
+    [nct][nQ][N]).  The random draws and the network aggregation stay with the caller."""
+    c1 = np.ascontiguousarray(c1, dtype=np.uint64)
+    nct = c1.shape[0]
+    mag, sign, nw = _bigints_to_words(mask)
+    sk_mont = np.ascontiguousarray(sk_mont[: cps.nQ], dtype=np.uint64)
+    crp = np.ascontiguousarray(crp, dtype=np.uint64)
+    e0 = np.ascontiguousarray(e0, dtype=np.int64)
+    e1 = np.ascontiguousarray(e1, dtype=np.int64)
+    h0 = np.zeros((nct, level + 1, cps.N), dtype=np.uint64)
+    h1 = np.zeros((nct, cps.nQ, cps.N), dtype=np.uint64)
+    cps._check(cps.L.sfg_refresh_gen_shares(cps.h, level, nct, _p(c1), _p(sk_mont), _p(crp), _p(mag), _p(sign), nw,
+                                            float(cps.scale if in_scale is None else in_scale), float(cps.scale if out_scale is None else out_scale),
+                                            _p(e0), _p(e1), _p(h0), _p(h1)),
+               "sfg_refresh_gen_shares")
+    return h0, h1
+
+
+def RefreshFinish(cps: CryptoParams, level: int, c0: np.ndarray, in_scale: float, agg_decrypt: np.ndarray, agg_recrypt: np.ndarray, crp: np.ndarray,
+                  out_scale: float = None):
+    """refProtocol.Decrypt + Recode + Recrypt (mpc/mhe.go:316-318) on nct ciphertexts: c0 [nct][>= level+1][N] and the aggregated shares ->
+    refreshed ciphertexts [nct][2][nQ][N] at the top level with scale ``out_scale`` (params.Scale())."""
+    c0 = np.ascontiguousarray(c0, dtype=np.uint64)
+    nct, c0_nl = c0.shape[0], c0.shape[1]
+    out = np.zeros((nct, 2, cps.nQ, cps.N), dtype=np.uint64)
+    a0 = np.ascontiguousarray(agg_decrypt, dtype=np.uint64)
+    a1 = np.ascontiguousarray(agg_recrypt, dtype=np.uint64)
+    crp = np.ascontiguousarray(crp, dtype=np.uint64)
+    cps._check(cps.L.sfg_refresh_finish(cps.h, level, nct, _p(c0), c0_nl, float(in_scale), float(cps.scale if out_scale is None else out_scale),
+                                        _p(a0), _p(a1), _p(crp), _p(out)), "sfg_refresh_finish")
+    return out
 
 
 def SetRelinKey(cps: CryptoParams, rlk: np.ndarray):

@@ -121,6 +121,8 @@ def _gpu_worker(rank, world, port, q):
         row_ok = bool((rs.compute(A) == single).all())
         gs = GiantSharded(cps, GenoFileStream.from_matrix(cps, X), rank, world)
         giant_ok = bool((gs.compute(A) == single).all())
+        gs2 = GiantSharded(cps, GenoFileStream.from_matrix(cps, X), rank, world, shard_baby=False)
+        giant_ok = giant_ok and bool((gs2.compute(A) == single).all())
         q.put((rank, col_ok, row_ok and giant_ok))
     finally:
         dist.destroy_process_group()

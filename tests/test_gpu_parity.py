@@ -657,6 +657,38 @@ def test_giant_sharded_partials_sum_to_compute(small13, nparts):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("nparts", [1, 3, 8])
+def test_baby_sharded_rotation_cache_equals_compute(small13, nparts):
+    """Baby-step sharding on ONE GPU: the shares of the rotation cache are computed one after the other into the same buffer (what the
+    all-gather assembles across ranks), then the rest of Compute runs on it: bit-identical to MatMult4StreamCompute."""
+    import ctypes as C
+
+    import torch
+
+    from sfgwas_b200 import GenoFileStream, MatMult4StreamCompute, MatMult4StreamPreprocess
+
+    o, cps, sk, keys = small13
+    rng = np.random.default_rng(900 + nparts)
+    nr, nc, s = 300, 260, 4
+    X = rng.integers(0, 3, (nr, nc)).astype(np.int8)
+    A = enc_matrix(o, sk, rng.normal(size=(s, nr)))
+    cache = MatMult4StreamPreprocess(cps, GenoFileStream.from_matrix(cps, X), 5)
+    full = MatMult4StreamCompute(cps, A, 5, cache)
+    L = cps.L
+    chunk = int(L.sfg_matmult4_baby_chunk_bytes(cps.h, cache.h, s, nparts))
+    R = torch.full((nparts * chunk,), 0xA5, dtype=torch.uint8, device="cuda")
+    d_A = torch.from_numpy(A.view(np.int64)).cuda()
+    torch.cuda.synchronize()
+    for part in range(nparts):
+        cps._check(L.sfg_matmult4_baby_dev(cps.h, C.c_void_p(d_A.data_ptr()), s, A.shape[1], 5, 5, cache.h, part, nparts, C.c_void_p(R.data_ptr())),
+                   "baby_dev")
+    d_out = torch.zeros((s, cache.m_ct, 2, 5, o.N), dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
+    cps._check(L.sfg_matmult4_stream_compute_r_dev(cps.h, C.c_void_p(R.data_ptr()), s, 5, cache.h, C.c_void_p(d_out.data_ptr())), "compute_r_dev")
+    assert (d_out.cpu().numpy().view(np.uint64) == full).all()
+
+
+@pytest.mark.gpu
 def test_partial_mod_reduce_finish_equals_compute(small13):
     """The multi-GPU pieces on one GPU: partial sums per block-row range, integer sum + mod q, giant ranges, modular output sum."""
     import ctypes as C
