@@ -82,6 +82,7 @@ void sfg_ctx_destroy(sfg_ctx *h) {
     cudaFree(c->roots);
     cudaFree(c->ddcos);
     cudaFree(c->rot5);
+    cudaFree(c->fft_tw);
     cudaFree(c->dlog_pos);
     cudaFree(c->dlog_src);
     cudaFree(c->enc_stats);

@@ -153,6 +153,21 @@ int ctx_build_tables(Ctx *c, const uint64_t *psi_opt) {
     if (dev_alloc(c, (void **)&c->ddcos, sizeof(double) * dd.size(), "table") || upload(c, c->ddcos, dd.data(), sizeof(double) * dd.size())) return -1;
     if (dev_alloc(c, (void **)&c->rot5, sizeof(int) * rot5.size(), "table") || upload(c, c->rot5, rot5.data(), sizeof(int) * rot5.size())) return -1;
     {
+        // per-stage twiddles of the special inverse FFT in the order the butterflies read them (unit stride in j): the stage of length
+        // len = 2h uses roots[(4 len - (5^j mod 4 len)) * (M / (4 len))] for j < h (Lattigo invfft); stored at [h + j]
+        const int n = c->slots;
+        std::vector<double> ft(2 * (size_t)n, 0.0);
+        for (int len = 2; len <= n; len <<= 1) {
+            const int lenh = len >> 1, lenq = len << 2, gap = M / lenq;
+            for (int j = 0; j < lenh; j++) {
+                const int idx = (lenq - (rot5[j] & (lenq - 1))) * gap;
+                ft[2 * (size_t)(lenh + j)] = roots[2 * (size_t)idx];
+                ft[2 * (size_t)(lenh + j) + 1] = roots[2 * (size_t)idx + 1];
+            }
+        }
+        if (dev_alloc(c, (void **)&c->fft_tw, sizeof(double) * ft.size(), "table") || upload(c, c->fft_tw, ft.data(), sizeof(double) * ft.size())) return -1;
+    }
+    {
         const uint64_t twoN = 2 * (uint64_t)N, n2 = (uint64_t)N / 2;
         std::vector<uint32_t> of_exp(twoN, 0), pos(N), src(N);
         uint64_t p5 = 1;

@@ -50,6 +50,7 @@ struct Ctx {
     // encoder (special inverse FFT)
     double2 *roots = nullptr;              // device [2N+1] exp(2 pi i k / 2N)
     int *rot5 = nullptr;                   // device [slots] 5^j mod 2N
+    double2 *fft_tw = nullptr;             // device [slots]: twiddles of the special inverse FFT per stage, stage with half-length h at [h, 2h)
     // discrete-log order of the NTT evaluation points: coefficient i of an NTT-domain polynomial is the value at psi^(2 brv(i) + 1) =
     // psi^(+-5^t); position q = s * N/2 + t (s = sign = top bit of i).  In that order the automorphism X -> X^(5^r) is a cyclic
     // shift by r inside each half (kernels_ks.cu: the giant-step sums).  dlog_pos[i] = q, dlog_src[q] = i.

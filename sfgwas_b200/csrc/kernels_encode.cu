@@ -57,12 +57,16 @@ __device__ __forceinline__ typename A::T msg_residue(double v, const typename A:
 // for 2^13 coefficients instead of 13), canonical residues out.  m: the integer message [N] in shared memory; s: transform scratch.
 // CS = 1: the ring is cut in two halves transformed one after the other (stage 0 folded into the first pass), which keeps the scratch at
 // 2^13 coefficients for logN = 14.  The result is staged in `s` and leaves with unit-stride stores.
-template <class A>
-__device__ __forceinline__ void encode_limb(const double *__restrict__ m, void *sraw, int logN, int CS, const TwTab &tab, const LimbConst &lc,
+// LOGN > 0: the ring size is a compile-time constant (13 -> whole ring, 14 -> two halves), so the pass plan, strides and indices fold
+// into immediates (a third of the executed instructions of the generic version are address arithmetic, as in the key-switch kernels).
+template <class A, int LOGN>
+__device__ __forceinline__ void encode_limb(const double *__restrict__ m, void *sraw, int logN_arg, int CS_arg, const TwTab &tab, const LimbConst &lc,
                                             unsigned char *__restrict__ o, int es, int mont) {
     using T = typename A::T;
     T *s = reinterpret_cast<T *>(sraw);
     const typename A::C c = A::make(lc);
+    const int logN = LOGN ? LOGN : logN_arg;
+    const int CS = LOGN ? (LOGN > 13 ? 1 : 0) : CS_arg;
     const int logS = logN - CS, S = 1 << logS;
     const PassPlan plan = make_pass_plan(logS - kLastR);
     for (int sl = 0; sl < (1 << CS); sl++) {
@@ -89,12 +93,13 @@ __device__ __forceinline__ void encode_limb(const double *__restrict__ m, void *
     }
 }
 
-template <int NPER>
+template <int NPER, int LOGN>
 __global__ void __launch_bounds__(1024, 1)
 k_encode(const int8_t *__restrict__ X, size_t ld, const EncJob *__restrict__ jobs, int logN, PolyLayout lay, int mont, double sc,
          double delta, const double2 *__restrict__ roots, const int *__restrict__ rot5, const double2 *__restrict__ ddcos,
          const uint64_t *__restrict__ tw, const LimbConst *__restrict__ lcs, unsigned char *__restrict__ out,
-         long long *__restrict__ coeff_out, unsigned long long *__restrict__ stats, const TwTab *__restrict__ tabs2, int CS) {
+         long long *__restrict__ coeff_out, unsigned long long *__restrict__ stats, const TwTab *__restrict__ tabs2, int CS,
+         const double2 *__restrict__ fft_tw) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int N = 1 << logN, n = N >> 1, M = N << 1, logn = logN - 1;
     double *re = reinterpret_cast<double *>(smem_raw);
@@ -125,22 +130,41 @@ k_encode(const int8_t *__restrict__ X, size_t ld, const EncJob *__restrict__ job
     }
     __syncthreads();
 
-    // 2. special inverse FFT (Lattigo invfft, App. B.6), decimation in frequency, result in bit-reversed order
-    for (int len = n, loglen = logn; len >= 2; len >>= 1, loglen--) {
-        const int lenh = len >> 1, lenq = len << 2, gap = M / lenq;
-        for (int b = tid; b < (n >> 1); b += T) {
-            const int grp = b >> (loglen - 1), j = b & (lenh - 1);
-            const int i0 = (grp << loglen) + j, i1 = i0 + lenh;
-            const int idx = (lenq - (rot5[j] & (lenq - 1))) * gap;
-            const double2 w = roots[idx];
-            const double ur = re[i0] + re[i1], ui = im[i0] + im[i1];
-            const double vr = re[i0] - re[i1], vi = im[i0] - im[i1];
-            re[i0] = ur;
-            im[i0] = ui;
-            re[i1] = vr * w.x - vi * w.y;
-            im[i1] = vr * w.y + vi * w.x;
+    // 2. special inverse FFT (Lattigo invfft, App. B.6), decimation in frequency, result in bit-reversed order.  Two stages per CTA
+    //    barrier (radix 4 in registers), twiddles from the per-stage table in butterfly order (unit stride: no 5^j / root gathers).
+    {
+        auto bfly = [](double &ar, double &ai, double &br, double &bi, const double2 w) {
+            const double ur = ar + br, ui = ai + bi, vr = ar - br, vi = ai - bi;
+            ar = ur;
+            ai = ui;
+            br = vr * w.x - vi * w.y;
+            bi = vr * w.y + vi * w.x;
+        };
+        int len = n, loglen = logn;
+        for (; len >= 4; len >>= 2, loglen -= 2) {
+            const int lenq4 = len >> 2, lenh = len >> 1;
+            for (int b = tid; b < (n >> 2); b += T) {
+                const int grp = b >> (loglen - 2), j = b & (lenq4 - 1);
+                const int i0 = (grp << loglen) + j, i1 = i0 + lenq4, i2 = i0 + lenh, i3 = i2 + lenq4;
+                double r0 = re[i0], m0 = im[i0], r1 = re[i1], m1 = im[i1], r2 = re[i2], m2 = im[i2], r3 = re[i3], m3 = im[i3];
+                const double2 wa = fft_tw[lenh + j], wb = fft_tw[lenh + j + lenq4], wc = fft_tw[lenq4 + j];
+                bfly(r0, m0, r2, m2, wa);  // stage of length len: pairs (i, i + len/2)
+                bfly(r1, m1, r3, m3, wb);
+                bfly(r0, m0, r1, m1, wc);  // stage of length len/2 inside both halves: pairs (i, i + len/4), same twiddle index j
+                bfly(r2, m2, r3, m3, wc);
+                re[i0] = r0; im[i0] = m0; re[i1] = r1; im[i1] = m1; re[i2] = r2; im[i2] = m2; re[i3] = r3; im[i3] = m3;
+            }
+            __syncthreads();
         }
-        __syncthreads();
+        if (len == 2) {  // odd number of stages: the last one alone
+            for (int b = tid; b < (n >> 1); b += T) {
+                const int i0 = b << 1, i1 = i0 + 1;
+                double r0 = re[i0], m0 = im[i0], r1 = re[i1], m1 = im[i1];
+                bfly(r0, m0, r1, m1, fft_tw[1]);
+                re[i0] = r0; im[i0] = m0; re[i1] = r1; im[i1] = m1;
+            }
+            __syncthreads();
+        }
     }
 
     // 3. scale, round half away from zero, flag near-ties
@@ -232,10 +256,10 @@ k_encode(const int8_t *__restrict__ X, size_t ld, const EncJob *__restrict__ job
             const LimbConst lc = lcs[l];
             unsigned char *o = out + job.out_off + lay.off[l];
             switch (arith_kind(lc.q)) {  // uniform across the CTA
-                case kArN30: encode_limb<ArN30>(mm, s2, logN, CS, tabs2[l], lc, o, lay.es[l], mont); break;
-                case kArN31: encode_limb<ArN31>(mm, s2, logN, CS, tabs2[l], lc, o, lay.es[l], mont); break;
-                case kArD: encode_limb<ArD>(mm, s2, logN, CS, tabs2[l], lc, o, lay.es[l], mont); break;
-                default: encode_limb<ArW>(mm, s2, logN, CS, tabs2[l], lc, o, lay.es[l], mont); break;
+                case kArN30: encode_limb<ArN30, LOGN>(mm, s2, logN, CS, tabs2[l], lc, o, lay.es[l], mont); break;
+                case kArN31: encode_limb<ArN31, LOGN>(mm, s2, logN, CS, tabs2[l], lc, o, lay.es[l], mont); break;
+                case kArD: encode_limb<ArD, LOGN>(mm, s2, logN, CS, tabs2[l], lc, o, lay.es[l], mont); break;
+                default: encode_limb<ArW, LOGN>(mm, s2, logN, CS, tabs2[l], lc, o, lay.es[l], mont); break;
             }
         }
         return;
@@ -282,15 +306,14 @@ int launch_encode(Ctx *c, const int8_t *X, size_t ld, const EncJob *jobs_dev, in
     const size_t scratch = tabs2 ? ntt_smem_elems(N >> CS) * 8 + 16 : 0;
     const size_t smem = (size_t)N * 8 + n + kMaxFlag * (sizeof(int) + sizeof(long long)) + 32 * sizeof(dd) + 64 + scratch;
     const double sc = c->scale / (double)n;
-    if (NPER == 16) {
-        SFG_CUDA(c, cudaFuncSetAttribute(k_encode<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_encode<16><<<njobs, T, smem, st>>>(X, ld, jobs_dev, logN, lay, mont ? 1 : 0, sc, c->enc_delta, c->roots, c->rot5, c->ddcos,
-                                            c->tw, c->lc, (unsigned char *)out, coeff_out, c->enc_stats, tabs2, CS);
-    } else {
-        SFG_CUDA(c, cudaFuncSetAttribute(k_encode<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_encode<8><<<njobs, T, smem, st>>>(X, ld, jobs_dev, logN, lay, mont ? 1 : 0, sc, c->enc_delta, c->roots, c->rot5, c->ddcos,
-                                           c->tw, c->lc, (unsigned char *)out, coeff_out, c->enc_stats, tabs2, CS);
-    }
+    auto go = [&](auto kern) -> int {
+        SFG_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<njobs, T, smem, st>>>(X, ld, jobs_dev, logN, lay, mont ? 1 : 0, sc, c->enc_delta, c->roots, c->rot5, c->ddcos, c->tw, c->lc,
+                                     (unsigned char *)out, coeff_out, c->enc_stats, tabs2, CS, c->fft_tw);
+        return 0;
+    };
+    // the rings of the reference's parameter sets are compiled with constant shapes; anything else takes the generic kernel
+    if (logN == 14 ? go(k_encode<16, 14>) : (logN == 13 && tabs2 ? go(k_encode<8, 13>) : go(k_encode<8, 0>))) return -1;
     SFG_LAUNCHED(c, "k_encode", st);
     return 0;
 }

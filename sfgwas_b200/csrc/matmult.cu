@@ -99,7 +99,8 @@ static int build_p_tiles(Ctx *c, const Cache *ca, int tile_lo, int tile_hi, unsi
     const int d = ca->d, m_ct = ca->m_ct, slots = ca->slots, Kg = tc.Kg, K = tc.K;
     const int ntl = tile_hi - tile_lo;
     const long long gbytes = tc_group_bytes(ca, ntl);
-    SFG_CUDA(c, cudaMemsetAsync(img, 0, (size_t)gbytes * tc.ngroups, c->stream));  // nil diagonals, padding columns / K steps
+    // no memset of the image: k_img_build writes EVERY byte of a (tile, K group) block -- zeros for nil diagonals, padding columns and
+    // padding K steps (table entry -1) -- so the 55 GB image of config 2 is written exactly once
     void *tmp, *dtab;
     const size_t RB = (size_t)ca->lay.bytes;
     if (ws_get(c, WS_TMPP, (size_t)128 * Kg * RB, &tmp)) return -1;
@@ -127,9 +128,8 @@ static int build_p_tiles(Ctx *c, const Cache *ca, int tile_lo, int tile_hi, unsi
                     jobs.push_back(EncJob{bi * slots, bj * slots, block_rows(ca, bi), block_cols(ca, bj), shift, d * g, off});
                 }
             }
-            if (jobs.empty()) continue;
             SFG_CUDA(c, cudaMemcpyAsync(dtab, tab.data(), tab.size() * sizeof(long long), cudaMemcpyDefault, c->stream));
-            if (encode_jobs(c, ca, jobs, tmp)) return -1;
+            if (!jobs.empty() && encode_jobs(c, ca, jobs, tmp)) return -1;  // (no diagonal in this block: the all -1 table writes zeros)
             if (launch_img_p(c, tc, ca->lay, tmp, (const long long *)dtab, ntl, ct - tile_lo, img + (size_t)grp * gbytes, c->stream)) return -1;
         }
     return 0;
@@ -242,6 +242,7 @@ int cache_build(Ctx *c, Geno *g, int maxLevel, Cache **out, int bi_lo, int bi_hi
         cudaError_t e = cudaMalloc(&ca->img, bytes);
         if (e == cudaSuccess) {
             ca->img_bytes = bytes;
+            poison_fill(c, ca->img, bytes);  // SFG_POISON=1: a byte the image builder failed to write would surface as a parity failure
             if (build_p_tiles(c, ca, 0, ca->tc.ntiles, ca->img) || cudaStreamSynchronize(c->stream) != cudaSuccess) {
                 if (c->err.empty()) c->err = "diagonal cache build failed";
                 cache_destroy(ca);
