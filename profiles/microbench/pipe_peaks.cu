@@ -102,15 +102,15 @@ int main() {
     const char *names[] = {"IMAD (mad.lo.u32)", "IMAD.WIDE.U32", "DFMA", "IMAD.HI.U32", "IADD3+IMNMX (2 ops)"};
     double ms;
     ms = time_ms([&] { k_ops<0><<<blocks, threads>>>(out, 3); });
-    printf("%-22s %8.3f ms  %7.2f Tops/s  %6.1f lanes/clk/SM\n", names[0], ms, ops / ms / 1e9, ops / ms / 1e3 / nsm / (clk / 1e3) / 1e3);
+    printf("%-22s %8.3f ms  %7.2f Tops/s  %6.1f lanes/clk/SM\n", names[0], ms, ops / ms / 1e9, ops / ms / nsm / (double)clk);
     ms = time_ms([&] { k_ops<1><<<blocks, threads>>>(out, 3); });
-    printf("%-22s %8.3f ms  %7.2f Tops/s  %6.1f lanes/clk/SM\n", names[1], ms, ops / ms / 1e9, ops / ms / 1e3 / nsm / (clk / 1e3) / 1e3);
+    printf("%-22s %8.3f ms  %7.2f Tops/s  %6.1f lanes/clk/SM\n", names[1], ms, ops / ms / 1e9, ops / ms / nsm / (double)clk);
     ms = time_ms([&] { k_ops<2><<<blocks, threads>>>(out, 3); });
-    printf("%-22s %8.3f ms  %7.2f Tops/s  %6.1f lanes/clk/SM\n", names[2], ms, ops / ms / 1e9, ops / ms / 1e3 / nsm / (clk / 1e3) / 1e3);
+    printf("%-22s %8.3f ms  %7.2f Tops/s  %6.1f lanes/clk/SM\n", names[2], ms, ops / ms / 1e9, ops / ms / nsm / (double)clk);
     ms = time_ms([&] { k_ops<3><<<blocks, threads>>>(out, 3); });
-    printf("%-22s %8.3f ms  %7.2f Tops/s  %6.1f lanes/clk/SM\n", names[3], ms, ops / ms / 1e9, ops / ms / 1e3 / nsm / (clk / 1e3) / 1e3);
+    printf("%-22s %8.3f ms  %7.2f Tops/s  %6.1f lanes/clk/SM\n", names[3], ms, ops / ms / 1e9, ops / ms / nsm / (double)clk);
     ms = time_ms([&] { k_ops<4><<<blocks, threads>>>(out, 3); });
-    printf("%-22s %8.3f ms  %7.2f Tops/s  %6.1f lanes/clk/SM\n", names[4], ms, 2 * ops / ms / 1e9, 2 * ops / ms / 1e3 / nsm / (clk / 1e3) / 1e3);
+    printf("%-22s %8.3f ms  %7.2f Tops/s  %6.1f lanes/clk/SM\n", names[4], ms, 2 * ops / ms / 1e9, 2 * ops / ms / nsm / (double)clk);
     printf("\nforward butterflies from registers (the roofline of the transform kernels), Gbutterfly/s over the whole GPU:\n");
     const LimbConst l30 = mk(0x3FFC0001ULL), l31 = mk(0x40020001ULL), ld33 = mk(0x1FFFEC001ULL), ld36 = mk(0x800004001ULL), lw46 = mk(0x200000008001ULL);
     ms = time_ms([&] { k_bfly<ArN30><<<blocks, threads>>>(out, l30, ArN30::make_tw(12345678, l30.q)); });

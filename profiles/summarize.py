@@ -25,8 +25,8 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "lts__t_bytes.sum", "dram__cycles_active.avg.pct_of_peak_sustained_elapsed"]
 
 
-def launches(tag, per_step):
-    path = os.path.join(ROOT, "gpurun_out", "launches.csv")
+def launches(tag, per_step, csv_name="launches.csv", out_name="launches_step.txt"):
+    path = os.path.join(ROOT, "gpurun_out", csv_name)
     if not os.path.exists(path):
         return
     rows, hdr = [], None
@@ -39,11 +39,15 @@ def launches(tag, per_step):
             if hdr and len(r) == len(hdr):
                 rows.append(dict(zip(hdr, r)))
     # a step is one period of the launch sequence: the distance between the last two MAC launches
-    pre = [r for r in rows if "k_encode" in r["Kernel Name"] or "k_geno" in r["Kernel Name"]]
+    pre = [r for r in rows[:len(rows) - 1] if ("k_encode" in r["Kernel Name"] or "k_geno" in r["Kernel Name"])]
+    if "otf" in csv_name:
+        pre = []
+    # a step starts with the rotation-by-0 copies of the baby phase: the k_copy_add launch that follows the previous step's last k_md_final
+    starts = [i for i, r in enumerate(rows) if "k_copy_add" in r["Kernel Name"] and (i == 0 or "k_md_final" in rows[i - 1]["Kernel Name"] or "k_img" in rows[i - 1]["Kernel Name"] or "k_encode" in rows[i - 1]["Kernel Name"])]
     macs = [i for i, r in enumerate(rows) if "k_mac" in r["Kernel Name"]]
     if per_step <= 0:
-        per_step = macs[-1] - macs[-2] if len(macs) >= 2 else len(rows)
-    nsteps = len(macs)
+        per_step = len(rows) - starts[-1] if starts else (macs[-1] - macs[-2] if len(macs) >= 2 else len(rows))
+    nsteps = len(starts) if starts else len(macs)
     step = rows[len(rows) - per_step:]
     agg = collections.OrderedDict()
     for r in step:
@@ -63,7 +67,7 @@ def launches(tag, per_step):
             out.append("%-44s %-16s %10.3f ms" % (re.sub(r"\(.*", "", r["Kernel Name"]).replace("void ", "")[:44], r["Grid Size"], float(r["Metric Value"]) / 1e6))
     d = os.path.join(ROOT, "profiles", tag)
     os.makedirs(d, exist_ok=True)
-    with open(os.path.join(d, "launches_step.txt"), "w") as f:
+    with open(os.path.join(d, out_name), "w") as f:
         f.write("\n".join(out) + "\n")
     print("\n".join(out))
 
@@ -93,4 +97,6 @@ if __name__ == "__main__":
     tag = sys.argv[1]
     per_step = int(sys.argv[2]) if len(sys.argv) > 2 else 0
     launches(tag, per_step)
+    launches(tag, 0, "launches_T.csv", "launches_step_transposed.txt")
+    launches(tag, 0, "launches_otf13.csv", "launches_step_on_the_fly_logN13.txt")
     reports(tag)

@@ -25,7 +25,7 @@ def main():
     from sfgwas_b200 import CryptoParams
 
     ap = argparse.ArgumentParser()
-    ap.add_argument("--out", default=os.path.join(ROOT, "profiles", "r1_final", "sweep_ntt_ks.json"))
+    ap.add_argument("--out", default=os.path.join(ROOT, "profiles", "r2", "sweep_ntt_ks.json"))
     ap.add_argument("--reps", type=int, default=5)
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
@@ -53,6 +53,7 @@ def main():
 
         cts = rand_res((batch, 2), list(range(nQ)))
         out = torch.empty_like(cts)
+        torch.cuda.synchronize()  # the library's stream is non-blocking: it is not ordered after torch's generator kernels
         ext = torch.cuda.ExternalStream(L.sfg_ctx_stream(cps.h), device=dev)
         idx = (C.c_int * nQ)(*range(nQ))
 
@@ -80,6 +81,7 @@ def main():
         d = cps.d
         for name, k in (("rot1", 1), ("rotd", d)):
             key = rand_res((cps.beta, 2), list(range(cps.nQP)))
+            torch.cuda.synchronize()
             cps._check(L.sfg_ctx_set_rotation_key(cps.h, k, C.c_void_p(key.data_ptr())), "set_rotation_key")
             del key
             ms = timed(lambda: cps._check(L.sfg_rotate_right_dev(cps.h, top, C.c_void_p(cts.data_ptr()), batch, -k, C.c_void_p(out.data_ptr())),
@@ -88,7 +90,7 @@ def main():
             row[name + "_per_s"] = batch / ms * 1e3
             row[name + "_us_each"] = ms * 1e3 / batch
         row["key_bytes"] = cps.beta * 2 * cps.nQP * N * 8
-        row["keyswitch_path"] = "fused (one CTA per ciphertext x target modulus)" if logN <= 14 else "unfused large-ring kernels"
+        row["keyswitch_path"] = "fused (one CTA per ciphertext x target modulus)" if logN <= 14 else "unfused large-ring kernels around the four-step transforms"
         rows.append(row)
         print(json.dumps(row), flush=True)
         del cts, out

@@ -106,7 +106,7 @@ int ctx_build_tables(Ctx *c, const uint64_t *psi_opt) {
     if (dev_alloc(c, (void **)&c->lc, sizeof(LimbConst) * nQP, "table") || upload(c, c->lc, c->lc_h.data(), sizeof(LimbConst) * nQP)) return -1;
     if (dev_alloc(c, (void **)&c->tw, sizeof(uint64_t) * tw.size(), "table") || upload(c, c->tw, tw.data(), sizeof(uint64_t) * tw.size())) return -1;
     // per-class tables of the register-tiled transforms (ntt2.cuh): [N] in Lattigo's order + the last-pass table in TT order
-    if (logN <= 14) {
+    if (logN <= 16) {  // logN 15 / 16: the four-step transforms of kernels_ntt.cu use the same tables
         std::vector<TwTab> tabs(nQP);
         const int P = N >> kLastR, s0 = logN - kLastR, NL = kLastE - 1;  // last-pass table: NL twiddles per group of 16
         for (int i = 0; i < nQP; i++) {

@@ -3,6 +3,8 @@
 //
 // NTT layout: one CTA owns one polynomial-limb (or a 2^14-coefficient sub-block of it for logN > 14) in shared memory;
 // stages run over smem; the first (forward) / last (inverse) log2(N/S) stages of logN > 14 run over global memory.
+#include <cstdlib>
+
 #include "kernels.h"
 #include "ntt.cuh"
 #include "ntt2.cuh"
@@ -165,15 +167,134 @@ static int ntt2_launch(Ctx *c, const uint64_t *src, const long long *src_off, si
 static int launch_ntt_old(Ctx *c, const uint64_t *src, size_t src_gstride, uint64_t *dst, size_t dst_gstride, int npoly, const LimbSel &sel,
                           bool inverse, cudaStream_t st);
 
+// ---------------------------------------------------------------------------------------------------------------
+// Four-step transforms for rings larger than one CTA's shared memory (logN 15, 16: the NTT / key-switch sweep of BASELINE config 3).
+// forward : ONE global-memory pass does the first CS = logN - 13 stages on 2^CS coefficients N / 2^CS apart per thread (registers,
+//           coalesced across threads), then every slice of 2^13 consecutive coefficients is an independent transform with the
+//           register-tiled passes of ntt2.cuh (one CTA per (polynomial, slice)).
+// inverse : the slices first, then the last CS Gentleman-Sande stages and N^-1 in one global pass.
+// 2 x (read + write) of the data instead of CS + 1 radix-2 global passes around a radix-2 shared-memory kernel.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kSliceLog = 13;
+
+template <class A, int R, bool INV>
+__global__ void __launch_bounds__(256)
+k_ntt_gpass(const uint64_t *__restrict__ src, size_t src_gstride, uint64_t *__restrict__ dst, size_t dst_gstride, SubSel sub, int logN,
+            const TwTab *__restrict__ tabs, const LimbConst *__restrict__ lcs) {
+    using T = typename A::T;
+    using TW = typename A::TW;
+    constexpr int E = 1 << R;
+    const int N = 1 << logN, lobits = logN - R;
+    const int g = blockIdx.y / sub.n, kk = blockIdx.y % sub.n, k = sub.pos[kk], limb = sub.limb[kk];
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= (N >> R)) return;
+    const uint64_t *in = src + (size_t)g * src_gstride + (size_t)k * N;
+    uint64_t *out = dst + (size_t)g * dst_gstride + (size_t)k * N;
+    const typename A::C c = A::make(lcs[limb]);
+    const TW *tw = reinterpret_cast<const TW *>(INV ? tabs[limb].inv : tabs[limb].fwd);
+    T v[E];
+#pragma unroll
+    for (int i = 0; i < E; i++) v[i] = A::from_canon(in[p + ((size_t)i << lobits)], c);
+    if (!INV) {
+#pragma unroll
+        for (int r = 0; r < R; r++) {  // global stage r: 2^r groups, twiddle NttPsi[2^r + group]
+            const int half = E >> (r + 1);
+#pragma unroll
+            for (int gg = 0; gg < (1 << r); gg++) {
+                const TW w = __ldg(tw + (1 << r) + gg);
+#pragma unroll
+                for (int j = 0; j < half; j++) A::fwd(v[gg * 2 * half + j], v[gg * 2 * half + j + half], w, c);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < E; i++) out[p + ((size_t)i << lobits)] = (uint64_t)A::canon(v[i], c);
+    } else {
+#pragma unroll
+        for (int r = R - 1; r >= 0; r--) {
+            const int half = E >> (r + 1);
+#pragma unroll
+            for (int gg = 0; gg < (1 << r); gg++) {
+                const TW w = __ldg(tw + (1 << r) + gg);
+#pragma unroll
+                for (int j = 0; j < half; j++) A::inv(v[gg * 2 * half + j], v[gg * 2 * half + j + half], w, c);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < E; i++) out[p + ((size_t)i << lobits)] = (uint64_t)A::inv_final(v[i], c);
+    }
+}
+
+template <class A, bool INV>
+__global__ void __launch_bounds__(512, 1)
+k_ntt2_slice(const uint64_t *__restrict__ src, size_t src_gstride, uint64_t *__restrict__ dst, size_t dst_gstride, SubSel sub, int logN,
+             PassPlan plan, const TwTab *__restrict__ tabs, const LimbConst *__restrict__ lcs) {
+    using T = typename A::T;
+    extern __shared__ __align__(16) unsigned char smraw[];
+    T *s = reinterpret_cast<T *>(smraw);
+    const int N = 1 << logN, CS = logN - kSliceLog, S = 1 << kSliceLog;
+    const int sl = blockIdx.x & ((1 << CS) - 1), pk = blockIdx.x >> CS;
+    const int g = pk / sub.n, kk = pk % sub.n, k = sub.pos[kk], limb = sub.limb[kk];
+    const uint64_t *in = src + (size_t)g * src_gstride + (size_t)k * N + (size_t)sl * S;
+    uint64_t *out = dst + (size_t)g * dst_gstride + (size_t)k * N + (size_t)sl * S;
+    const typename A::C c = A::make(lcs[limb]);
+    if (!INV) {
+        ntt_forward<A>(s, logN, kSliceLog, sl, plan, tabs[limb], c, [&](int j, int) { return A::from_canon(in[j], c); },
+                       [&](int j, T v, int) { s[sidx<sizeof(T)>(j)] = A::canon(v, c); });
+        __syncthreads();
+        for (int j = threadIdx.x; j < S; j += blockDim.x) out[j] = (uint64_t)s[sidx<sizeof(T)>(j)];
+    } else {
+        for (int j = threadIdx.x; j < S; j += blockDim.x) s[sidx<sizeof(T)>(j)] = A::from_canon(in[j], c);
+        __syncthreads();
+        ntt_inverse_slice<A>(s, logN, kSliceLog, sl, plan, tabs[limb], c, [&](int j, int) { return s[sidx<sizeof(T)>(j)]; },
+                             [&](int j, T v, int) { out[j] = (uint64_t)A::canon(v, c); });
+    }
+}
+
+template <class A>
+static int ntt4_launch(Ctx *c, const uint64_t *src, size_t sgs, uint64_t *dst, size_t dgs, int ngroups, const SubSel &sub, bool inverse,
+                       cudaStream_t st) {
+    if (sub.n == 0 || ngroups == 0) return 0;
+    const int logN = c->logN, N = c->N, CS = logN - kSliceLog;
+    const PassPlan plan = make_pass_plan(kSliceLog - kLastR);
+    const size_t smem = ntt_smem_elems(1 << kSliceLog) * sizeof(typename A::T);
+    const dim3 gp((unsigned)(((N >> CS) + 255) / 256), (unsigned)(ngroups * sub.n));
+    const unsigned nslice = (unsigned)(ngroups * sub.n) << CS;
+    auto gpass = [&](bool inv, const uint64_t *a, size_t as, uint64_t *b, size_t bs) -> int {
+        if (CS == 1) {
+            if (inv) k_ntt_gpass<A, 1, true><<<gp, 256, 0, st>>>(a, as, b, bs, sub, logN, c->tw2, c->lc);
+            else k_ntt_gpass<A, 1, false><<<gp, 256, 0, st>>>(a, as, b, bs, sub, logN, c->tw2, c->lc);
+        } else if (CS == 2) {
+            if (inv) k_ntt_gpass<A, 2, true><<<gp, 256, 0, st>>>(a, as, b, bs, sub, logN, c->tw2, c->lc);
+            else k_ntt_gpass<A, 2, false><<<gp, 256, 0, st>>>(a, as, b, bs, sub, logN, c->tw2, c->lc);
+        } else {
+            if (inv) k_ntt_gpass<A, 3, true><<<gp, 256, 0, st>>>(a, as, b, bs, sub, logN, c->tw2, c->lc);
+            else k_ntt_gpass<A, 3, false><<<gp, 256, 0, st>>>(a, as, b, bs, sub, logN, c->tw2, c->lc);
+        }
+        SFG_LAUNCHED(c, "k_ntt_gpass", st);
+        return 0;
+    };
+    if (!inverse) {
+        if (gpass(false, src, sgs, dst, dgs)) return -1;
+        SFG_CUDA(c, cudaFuncSetAttribute(k_ntt2_slice<A, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_ntt2_slice<A, false><<<nslice, 512, smem, st>>>(dst, dgs, dst, dgs, sub, logN, plan, c->tw2, c->lc);
+        SFG_LAUNCHED(c, "k_ntt2_slice", st);
+    } else {
+        SFG_CUDA(c, cudaFuncSetAttribute(k_ntt2_slice<A, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_ntt2_slice<A, true><<<nslice, 512, smem, st>>>(src, sgs, dst, dgs, sub, logN, plan, c->tw2, c->lc);
+        SFG_LAUNCHED(c, "k_ntt2_slice", st);
+        if (gpass(true, dst, dgs, dst, dgs)) return -1;
+    }
+    return 0;
+}
+
 // src_off (device, optional): element offset of every group's first polynomial (overrides g*src_gstride).
 // in_tt: the inputs are in TT order (inverse transforms only).
 int launch_ntt_gather(Ctx *c, const uint64_t *src, const long long *src_off, size_t src_gstride, uint64_t *dst, size_t dst_gstride, int npoly,
                       const LimbSel &sel, bool inverse, bool in_tt, cudaStream_t st) {
     if (npoly <= 0) return 0;
-    if (c->logN > 14) {
-        if (src_off || in_tt) SFG_FAIL(c, "gathered / TT transforms support logN <= 14 (got %d)", c->logN);
-        return launch_ntt_old(c, src, src_gstride, dst, dst_gstride, npoly, sel, inverse, st);
-    }
+    static const bool old_big = [] { const char *e = getenv("SFG_NTT_OLDBIG"); return e && *e == '1'; }();
+    if (c->logN > 14 && (src_off || in_tt)) SFG_FAIL(c, "gathered / TT transforms support logN <= 14 (got %d)", c->logN);
+    if (c->logN > 16 || (c->logN > 14 && old_big)) return launch_ntt_old(c, src, src_gstride, dst, dst_gstride, npoly, sel, inverse, st);
     SubSel sub[kNumArith] = {{0, {}, {}}, {0, {}, {}}, {0, {}, {}}, {0, {}, {}}};
     for (int k = 0; k < sel.n; k++) {
         SubSel &s = sub[arith_kind(c->mod[sel.idx[k]])];
@@ -181,6 +302,13 @@ int launch_ntt_gather(Ctx *c, const uint64_t *src, const long long *src_off, siz
         s.limb[s.n++] = sel.idx[k];
     }
     const int ngroups = npoly / sel.n;
+    if (c->logN > 14) {  // four-step: one global pass + register-tiled slices of 2^13 coefficients
+        if (ntt4_launch<ArW>(c, src, src_gstride, dst, dst_gstride, ngroups, sub[kArW], inverse, st)) return -1;
+        if (ntt4_launch<ArD>(c, src, src_gstride, dst, dst_gstride, ngroups, sub[kArD], inverse, st)) return -1;
+        if (ntt4_launch<ArN30>(c, src, src_gstride, dst, dst_gstride, ngroups, sub[kArN30], inverse, st)) return -1;
+        if (ntt4_launch<ArN31>(c, src, src_gstride, dst, dst_gstride, ngroups, sub[kArN31], inverse, st)) return -1;
+        return 0;
+    }
     if (ntt2_launch<ArW>(c, src, src_off, src_gstride, dst, dst_gstride, ngroups, sub[kArW], inverse, in_tt, st)) return -1;
     if (ntt2_launch<ArD>(c, src, src_off, src_gstride, dst, dst_gstride, ngroups, sub[kArD], inverse, in_tt, st)) return -1;
     if (ntt2_launch<ArN30>(c, src, src_off, src_gstride, dst, dst_gstride, ngroups, sub[kArN30], inverse, in_tt, st)) return -1;

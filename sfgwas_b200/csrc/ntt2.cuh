@@ -381,4 +381,34 @@ __device__ __forceinline__ void ntt_inverse(typename A::T *s, int logN, const Pa
     }
 }
 
+// Inverse transform of slice `sl` (2^logS consecutive coefficients) of a 2^logN ring: the Gentleman-Sande stages logN-1 .. logN-logS, i.e.
+// everything that stays inside the slice; the remaining logN-logS stages pair coefficients of different slices and run as one
+// global-memory pass (kernels_ntt.cu: four-step transforms of rings larger than one CTA).  fin(j, v, k) receives the lazy value of local
+// coefficient j (NOT multiplied by N^-1).
+template <class A, class LD, class FIN>
+__device__ __forceinline__ void ntt_inverse_slice(typename A::T *s, int logN, int logS, int sl, const PassPlan &plan, const TwTab &tab,
+                                                  const typename A::C &c, LD ld_last, FIN fin) {
+    using T = typename A::T;
+    using TW = typename A::TW;
+    const TW *tw = reinterpret_cast<const TW *>(tab.inv);
+    auto lds = [=](int j, int) { return s[sidx<sizeof(T)>(j)]; };
+    auto sts = [=](int j, T v, int) { s[sidx<sizeof(T)>(j)] = v; };
+    int s0 = logN - kLastR;
+    inv_pass<A, kLastR, true>(s0, logN, logS, sl, reinterpret_cast<const TW *>(tab.inv_last), c, ld_last, sts);
+    __syncthreads();
+#pragma unroll
+    for (int i = plan.n - 1; i >= 0; i--) {
+        s0 -= plan.R[i];
+        if (i == 0) {
+            mid_pass<A, true>(plan.R[i], s0, logN, logS, sl, tw, c, lds, fin);
+        } else {
+            mid_pass<A, true>(plan.R[i], s0, logN, logS, sl, tw, c, lds, sts);
+            __syncthreads();
+        }
+    }
+    if (plan.n == 0) {
+        for (int j = threadIdx.x; j < (1 << logS); j += blockDim.x) fin(j, lds(j, 0), 0);
+    }
+}
+
 }  // namespace sfg
