@@ -14,7 +14,7 @@
 //   ArW   q < 2^62 : u64, Shoup multiplication with 64-bit companions, lazy forward butterflies (no conditional subtraction:
 //                    values grow by 2q per stage and fit 64 bits for q < 2^57; larger q fall back to Harvey's [0, 4q) form),
 //                    Harvey [0, 2q) inverse butterflies.                                  ~16 FMA-pipe slots per butterfly
-//   ArD   q < 2^45 : residues kept as exact integers in FP64 (the 64 lanes/clk FP64 pipe is otherwise idle): product by a twiddle
+//   ArD   q < 2^46 : residues kept as exact integers in FP64 (the 64 lanes/clk FP64 pipe is otherwise idle): product by a twiddle
 //                    = DMUL + DFMA (exact two-product), quotient by the magic-number round, remainder by DFMA; values stay in
 //                    (-q, q) after a multiplication and grow by q per forward stage, so no conditional corrections at all.
 //                                                                                        8 FP64 ops per forward butterfly
@@ -27,7 +27,14 @@ namespace sfg {
 
 enum ArithKind : int { kArW = 0, kArN30 = 1, kArN31 = 2, kArD = 3, kNumArith = 4 };
 __host__ __device__ inline int arith_kind(uint64_t q) {
-    return q < (1ULL << 30) ? kArN30 : (q < (1ULL << 31) ? kArN31 : (q < (1ULL << 45) ? kArD : kArW));
+    // ArD up to 2^46 (round 2; was 2^45): PN14QP438's q0 = 2^45 + 2^15 + 1 and the 45-46-bit moduli of PN16QP1761 run on the FP64 pipe
+    // (3x the u64 butterfly rate).  Exactness bound, with Y = the largest magnitude a transform value can reach:
+    //   mul_lazy(y, w): h = RN(y w), l = y w - h exactly (FMA); k = rint(h * RN(1/q)) in ONE rounding (FMA onto 1.5 * 2^52), so
+    //   |k - h/q| <= 1/2 + |h/q| 2^-53 <= 1/2 + Y 2^-53;  h - k q and l are integers below 2^53, so r = fma(-k, q, h) + l is exact,
+    //   r = y w (mod q) and |r| <= q (1/2 + Y 2^-53) + Y q 2^-53 = q (1/2 + Y 2^-52).  Needs Y < 2^51 (the magic-number round) and
+    //   gives |r| < q as soon as Y <= 2^50.6.  Y <= 2^49 (load_u64 reduces anything larger) + 16 stages of growth by q < 2^46
+    //   = 1.5 * 2^50: |r| <= 0.875 q.  Lazy key-product sums add at most 2^3 values below q: far below 2^53.
+    return q < (1ULL << 30) ? kArN30 : (q < (1ULL << 31) ? kArN31 : (q < (1ULL << 46) ? kArD : kArW));
 }
 
 // Stages per pass: at most kLastR = 4 (16 coefficients in registers per thread).
