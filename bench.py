@@ -267,7 +267,9 @@ def run_reference(args, rank, world):
     line = dict(metric="genotype x ciphertext MatMult GB/s (B_alg / t)", value=v, unit="GB/s", n_gpus=args.gpus, steps=args.steps,
                 warmup=args.warmup, ms_per_step=t * 1e3, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="u64",
                 data="synthetic", impl="reference",
-                config=dict(workload=args.workload, ckks_params=w["params"], orientation=w["orientation"], s=w["s"],
+                config=dict(workload=args.workload, ckks_params=w["params"], logN=CKKS[w["params"]]["logN"], s=w["s"], orientation=w["orientation"],
+                            max_level=5, num_block_rows=full_wf["nbr"], m_ct=full_wf["m_ct"], diag_polys=full_wf["diag_polys"],
+                            b_alg_bytes=full_wf["b_alg"], mac_alg=full_wf["mac_alg"], key_switches=[full_wf["ks_baby"], full_wf["ks_giant"]],
                             note="CPU arm (rank 0 only): a complete call on a bounded sample of the workload, see cpu_baseline.sample",
                             sample_rows=cs.nrows, sample_cols=cs.ncols, sample_b_alg_bytes=cs.wf["b_alg"], preprocess_s=cs.t_prep),
                 cpu_baseline=dict(value=v, unit="GB/s", cores=cs.nthreads, kind="port", sample=desc, est_full_workload_gbs=est_full),

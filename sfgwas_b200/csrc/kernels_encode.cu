@@ -210,9 +210,13 @@ k_encode(const int8_t *__restrict__ X, size_t ld, const EncJob *__restrict__ job
             }
             if ((tid & 31) == 0) red[tid >> 5] = acc;
             __syncthreads();
-            if (tid == 0) {
-                dd tot{0.0, 0.0};
-                for (int w = 0; w < (T + 31) / 32; w++) tot = dd_add(tot, red[w]);
+            if (tid < 32) {  // warp 0 combines the warp partials with a shuffle tree (a serial sum by one thread was ~5 000 cycles of dependent FP64)
+                dd tot = tid < (T + 31) / 32 ? red[tid] : dd{0.0, 0.0};
+                for (int o = 16; o > 0; o >>= 1) {
+                    dd other{__shfl_down_sync(0xffffffffu, tot.hi, o), __shfl_down_sync(0xffffffffu, tot.lo, o)};
+                    tot = dd_add(tot, other);
+                }
+              if (tid == 0) {
                 if (k >= n) { tot.hi = -tot.hi; tot.lo = -tot.lo; }
                 dd x = dd_mul_d(tot, sc);
                 const bool neg = x.hi < 0;
@@ -225,6 +229,7 @@ k_encode(const int8_t *__restrict__ X, size_t ld, const EncJob *__restrict__ job
                 flag_val[f] = neg ? -v : v;
                 atomicAdd(&stats[0], 1ULL);
                 if (fabs(fr - 0.5) < 1e-13) atomicAdd(&stats[1], 1ULL);
+              }
             }
             __syncthreads();
         }

@@ -175,6 +175,9 @@ k_ks_inner2(const uint64_t *__restrict__ in, const long long *__restrict__ in_of
     constexpr int NREG = ACC_SMEM ? 1 : kLastE;
     T a0[NREG], a1[NREG];
     T *s0a = s + ntt_smem_elems(S), *s1a = s0a + ntt_smem_elems(S);
+    // twiddles of the passes before the last one: staged once per CTA (one target modulus), read by every digit's transform
+    typename A::TW *tw_s = reinterpret_cast<typename A::TW *>(s1a + ntt_smem_elems(S));
+    ntt_stage_twiddles<A>(tw_s, tab, logN);
     const int abase = kLastE * threadIdx.x;
 #pragma unroll
     for (int k = 0; k < kLastE; k++) {
@@ -184,6 +187,7 @@ k_ks_inner2(const uint64_t *__restrict__ in, const long long *__restrict__ in_of
             a0[k] = a1[k] = 0;
         }
     }
+    __syncthreads();  // the staged twiddles are visible to every warp before the first transform
 
     for (int i = 0; i < beta; i++) {
         const BaseConv &bc = ks[(size_t)i * nt + tt];
@@ -255,7 +259,7 @@ k_ks_inner2(const uint64_t *__restrict__ in, const long long *__restrict__ in_of
                     return sl ? y : x;
                 }
             };
-            ntt_forward<A>(s, logN, logS, sl, plan, tab, c, ld0, mac);
+            ntt_forward<A>(s, logN, logS, sl, plan, tab, c, ld0, mac, tw_s);
         }
         __syncthreads();
     }
@@ -650,7 +654,7 @@ template <class A, int CS, bool A1>
 static int inner_launch2(Ctx *c, const KsBatch &b, BaseConv *ks, const TgtSel &sel, cudaStream_t st) {
     const int logN = c->logN, logS = logN - CS, S = 1 << logS;
     const PassPlan plan = make_pass_plan(logS - kLastR);
-    const size_t smem = 3 * ntt_smem_elems(S) * sizeof(typename A::T);
+    const size_t smem = 3 * ntt_smem_elems(S) * sizeof(typename A::T) + (size_t)ntt_mid_twiddles(logN) * sizeof(typename A::TW);
     dim3 g(sel.n << CS, b.nct);
     auto go = [&](auto kern) -> int {
         SFG_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

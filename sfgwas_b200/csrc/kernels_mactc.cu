@@ -129,6 +129,9 @@ struct MacTcParams {
     int col_lo, col_hi;         // global columns written
     int accumulate;             // cv += (mod q) instead of cv =
     int SA, NGF, SBN;
+    int ni[kTcMaxL];              // coefficients per item of limb l: 4, or 8 for the 32-bit classes (their results are staged as u32, so 8
+                                  // consecutive coefficients leave as ONE 64-byte store instead of two scattered 32-byte sectors)
+    long long item_base[kTcMaxL + 1];  // first item of limb l (items are limb-major)
     int tbuf_stride;            // TMEM column stride between the two accumulator buffers (256) or 0 = single buffer
     int bslot_bytes;
     int dbg;                    // debug knobs (SFG_TC_DBG): 1 = no global stores, 2 = no epilogue math
@@ -140,21 +143,24 @@ struct MacTcParams {
 namespace {
 
 struct Item {
-    int l, n4, ct, sb, n4l;
+    int l, ct, NI, n0;   // limb, column tile, coefficients in this item, first coefficient
+    long long tg0;       // index of coefficient n0's A-stage group inside the limb's part of the P image
 };
 __device__ __forceinline__ Item decode_item(const MacTcParams &p, long long item) {
     const int ntr = p.tile_hi - p.tile_lo;
-    const int N4 = p.N >> 2;
-    const long long per_l = (long long)N4 * ntr;
     Item it;
-    it.l = (int)(item / per_l);
-    const int rem = (int)(item - (long long)it.l * per_l);
-    const int per_sb = ntr * p.SBN;
-    it.sb = rem / per_sb;
-    const int rem2 = rem - it.sb * per_sb;
-    it.ct = p.tile_lo + rem2 / p.SBN;
-    it.n4l = rem2 % p.SBN;
-    it.n4 = it.sb * p.SBN + it.n4l;
+    it.l = 0;
+    while (it.l + 1 < p.L && item >= p.item_base[it.l + 1]) it.l++;
+    it.NI = p.ni[it.l];
+    const int rem = (int)(item - p.item_base[it.l]);
+    const int SBC = p.SBN * 4;            // coefficients per superblock
+    const int GS = SBC / it.NI;           // items per (superblock, tile)
+    const int per_sb = ntr * GS;
+    const int sb = rem / per_sb, rem2 = rem - sb * per_sb;
+    it.ct = p.tile_lo + rem2 / GS;
+    const int gl = rem2 % GS;
+    it.n0 = sb * SBC + gl * it.NI;
+    it.tg0 = ((long long)sb * p.img_ntiles + (it.ct - p.img_tile0)) * SBC + gl * it.NI;
     return it;
 }
 
@@ -189,9 +195,9 @@ __device__ __forceinline__ uint64_t recombine(const uint32_t *T, const uint64_t 
 // One accumulator tile: straight-line code per chunk of 4 rows (NB and the reduction class are compile-time, the four rows
 // are independent dependency chains), results staged in shared memory as outb[row][slot][column].
 template <int NB, int FAST>
-__device__ __forceinline__ void epilogue_tile(const MacTcParams &p, int l, uint32_t taddr, int slot, uint64_t *outb, int t, int half) {
+__device__ __forceinline__ void epilogue_tile(const MacTcParams &p, int l, uint32_t taddr, int slot, uint64_t *outb, int t, int half, int ngf) {
     constexpr int NS = 2 * NB - 1;
-    const int RP = p.RP, rows = p.rows, NGF = p.NGF;
+    const int RP = p.RP, rows = p.rows;
     const LimbConst lc = p.lc[l];
     const uint32_t nqinv32 = 0u - (uint32_t)lc.qinv;  // -q^-1 mod 2^32
     uint64_t cs[NS];
@@ -220,17 +226,20 @@ __device__ __forceinline__ void epilogue_tile(const MacTcParams &p, int l, uint3
 #pragma unroll
         for (int r = 0; r < 4; r++) {
             const int row = 4 * q + r;
-            if (row < rows && (!(p.dbg & 8) || val[r] == 0xdeadbeefULL)) outb[((size_t)row * NGF + slot) * 128 + t] = val[r];
+            if (row < rows && (!(p.dbg & 8) || val[r] == 0xdeadbeefULL)) {
+                if (FAST == 2 && p.ni[l] == 8) reinterpret_cast<uint32_t *>(outb)[((size_t)row * ngf + slot) * 128 + t] = (uint32_t)val[r];  // < q < 2^31
+                else outb[((size_t)row * ngf + slot) * 128 + t] = val[r];
+            }
         }
     }
 }
 
 template <int NB>
-__device__ __forceinline__ void epilogue_nb(const MacTcParams &p, int l, uint32_t taddr, int slot, uint64_t *outb, int t, int half) {
+__device__ __forceinline__ void epilogue_nb(const MacTcParams &p, int l, uint32_t taddr, int slot, uint64_t *outb, int t, int half, int ngf) {
     const int f = p.fast[l];
-    if (f == 2) epilogue_tile<NB, 2>(p, l, taddr, slot, outb, t, half);
-    else if (f == 1) epilogue_tile<NB, 1>(p, l, taddr, slot, outb, t, half);
-    else epilogue_tile<NB, 0>(p, l, taddr, slot, outb, t, half);
+    if (f == 2) epilogue_tile<NB, 2>(p, l, taddr, slot, outb, t, half, ngf);
+    else if (f == 1) epilogue_tile<NB, 1>(p, l, taddr, slot, outb, t, half, ngf);
+    else epilogue_tile<NB, 0>(p, l, taddr, slot, outb, t, half, ngf);
 }
 
 }  // namespace
@@ -275,8 +284,7 @@ __global__ void __launch_bounds__(384, 1) k_mac_tc(const __grid_constant__ MacTc
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int ntr = p.tile_hi - p.tile_lo;
-    const long long nitems = (long long)p.L * (p.N >> 2) * ntr;
+    const long long nitems = p.item_base[p.L];
 
     if (wid == 0) {
         // ===================== producer =====================
@@ -288,9 +296,9 @@ __global__ void __launch_bounds__(384, 1) k_mac_tc(const __grid_constant__ MacTc
                 const Item it = decode_item(p, item);
                 const int nb = p.nb[it.l];
                 const uint32_t bbytes = (uint32_t)p.npad[it.l] * p.Kg;
-                const long long tg0 = (((long long)it.sb * p.img_ntiles + (it.ct - p.img_tile0)) * p.SBN + it.n4l) * 4;
-                for (int i = 0; i < 4; i++) {
-                    const int n = it.n4 * 4 + i;
+                const long long tg0 = it.tg0;
+                for (int i = 0; i < it.NI; i++) {
+                    const int n = it.n0 + i;
                     for (int g = 0; g < p.ngroups; g++) {  // every K group of this coefficient accumulates into the same TMEM tile
                         mbar_wait(&b_empty[bs], bph ^ 1u);
                         mbar_arrive_expect_tx(&b_full[bs], bbytes);
@@ -323,7 +331,7 @@ __global__ void __launch_bounds__(384, 1) k_mac_tc(const __grid_constant__ MacTc
                 const int nb = p.nb[it.l], npad = p.npad[it.l];
                 const int region = (nb - 1) * p.RP + npad;
                 const uint32_t idesc = umma_idesc_u8(npad);
-                for (int i = 0; i < 4; i++) {
+                for (int i = 0; i < it.NI; i++) {
                     mbar_wait(&t_empty[tb], tph ^ 1u);
                     tc_fence_after();
                     const uint32_t d_base = tmem_base + tb * (uint32_t)p.tbuf_stride;
@@ -375,7 +383,9 @@ __global__ void __launch_bounds__(384, 1) k_mac_tc(const __grid_constant__ MacTc
             const int l = it.l;
             const uint64_t q = p.lc[l].q;
             const int col = it.ct * 128 + t;
-            for (int i = 0; i < 4; i++) {
+            const bool narrow8 = it.NI == 8;                 // u32 staging, 8 coefficients per flush
+            const int ngf = narrow8 ? 8 : p.NGF;             // staged coefficients per flush (slots of 4 resp. 8 bytes: same bytes per row)
+            for (int i = 0; i < it.NI; i++) {
                 mbar_wait(&t_full[tb], tph);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + lane_base + tb * (uint32_t)p.tbuf_stride;
@@ -386,12 +396,12 @@ __global__ void __launch_bounds__(384, 1) k_mac_tc(const __grid_constant__ MacTc
                     outb[t] = v[0];
                 } else {
                     switch (p.nb[l]) {  // uniform across the CTA
-                        case 1: epilogue_nb<1>(p, l, taddr, i % p.NGF, outb, t, half); break;
-                        case 2: epilogue_nb<2>(p, l, taddr, i % p.NGF, outb, t, half); break;
-                        case 3: epilogue_nb<3>(p, l, taddr, i % p.NGF, outb, t, half); break;
-                        case 4: epilogue_nb<4>(p, l, taddr, i % p.NGF, outb, t, half); break;
-                        case 5: epilogue_nb<5>(p, l, taddr, i % p.NGF, outb, t, half); break;
-                        default: epilogue_nb<6>(p, l, taddr, i % p.NGF, outb, t, half); break;
+                        case 1: epilogue_nb<1>(p, l, taddr, i % ngf, outb, t, half, ngf); break;
+                        case 2: epilogue_nb<2>(p, l, taddr, i % ngf, outb, t, half, ngf); break;
+                        case 3: epilogue_nb<3>(p, l, taddr, i % ngf, outb, t, half, ngf); break;
+                        case 4: epilogue_nb<4>(p, l, taddr, i % ngf, outb, t, half, ngf); break;
+                        case 5: epilogue_nb<5>(p, l, taddr, i % ngf, outb, t, half, ngf); break;
+                        default: epilogue_nb<6>(p, l, taddr, i % ngf, outb, t, half, ngf); break;
                     }
                 }
                 tc_fence_before();
@@ -400,14 +410,28 @@ __global__ void __launch_bounds__(384, 1) k_mac_tc(const __grid_constant__ MacTc
                     tb = 0;
                     tph ^= 1u;
                 }
-                if ((i + 1) % p.NGF == 0) {
+                if ((i + 1) % ngf == 0) {
                     asm volatile("bar.sync 1, 256;\n" ::: "memory");
                     if (col >= p.col_lo && col < p.col_hi && !(p.dbg & 1)) {
-                        const int n0 = it.n4 * 4 + (i + 1 - p.NGF);
+                        const int n0 = it.n0 + (i + 1 - ngf);
                         uint64_t *dst = p.cv + ((size_t)(col - p.col_lo) * p.cv_rows + p.cv_row0 + half) * LN + (size_t)l * p.N + n0;
                         for (int row = half; row < p.rows; row += 2, dst += 2 * LN) {
-                            const uint64_t *src = outb + (size_t)row * p.NGF * 128 + t;
-                            if (p.NGF == 4) {
+                            if (narrow8) {
+                                // 8 consecutive coefficients of a 32-bit-class limb: widened to u64 and written as one 64-byte run
+                                const uint32_t *src = reinterpret_cast<const uint32_t *>(outb) + (size_t)row * 8 * 128 + t;
+                                uint64_t v[8];
+#pragma unroll
+                                for (int x = 0; x < 8; x++) v[x] = src[x * 128];
+                                if (p.accumulate) {
+#pragma unroll
+                                    for (int x = 0; x < 8; x++) v[x] = add_mod(v[x], dst[x], q);
+                                }
+                                asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};\n" ::"l"(dst), "l"(v[0]), "l"(v[1]), "l"(v[2]), "l"(v[3]) : "memory");
+                                asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};\n" ::"l"(dst + 4), "l"(v[4]), "l"(v[5]), "l"(v[6]), "l"(v[7]) : "memory");
+                                continue;
+                            }
+                            const uint64_t *src = outb + (size_t)row * ngf * 128 + t;
+                            if (ngf == 4) {
                                 uint64_t v0 = src[0], v1 = src[128], v2 = src[256], v3 = src[384];
                                 if (p.accumulate) {
                                     uint64_t o0, o1, o2, o3;
@@ -420,7 +444,7 @@ __global__ void __launch_bounds__(384, 1) k_mac_tc(const __grid_constant__ MacTc
                                 // one full 32-byte sector per store (STG.256)
                                 asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};\n" ::"l"(dst), "l"(v0), "l"(v1), "l"(v2), "l"(v3) : "memory");
                             } else {
-                                for (int x = 0; x < p.NGF; x++) {
+                                for (int x = 0; x < ngf; x++) {
                                     uint64_t v = src[x * 128];
                                     if (p.accumulate) v = add_mod(v, dst[x], q);
                                     dst[x] = v;
@@ -758,6 +782,14 @@ int launch_mac_tc(Ctx *c, const TcGeomP &gp, const TcGeomR &gr, const void *Pimg
     }
     if (SA < 3) SFG_FAIL(c, "tensor-core MAC does not fit shared memory (rows = %d, Kg = %d)", gr.rows, gp.Kg);
     p.NGF = NGF;
+    // items: 4 coefficients of one (limb, column tile); 8 for the 32-bit classes when the staging buffer holds 8 of their 4-byte results
+    // per row (NGF == 4) -- their outputs then leave as 64-byte runs (SFG_TC_NI4=1 keeps 4 everywhere for A/B runs)
+    static const bool ni4 = [] { const char *e = getenv("SFG_TC_NI4"); return e && *e == '1'; }();
+    p.item_base[0] = 0;
+    for (int l = 0; l < gp.L; l++) {
+        p.ni[l] = (!ni4 && p.fast[l] == 2 && NGF == 4 && (gp.SBN * 4) % 8 == 0) ? 8 : 4;
+        p.item_base[l + 1] = p.item_base[l] + (long long)(c->N / p.ni[l]) * (tile_hi - tile_lo);
+    }
     if (const char *e = getenv("SFG_TC_DBG")) p.dbg = atoi(e);
     if (const char *e = getenv("SFG_TC_SA")) SA = std::min(SA, atoi(e));
     p.SA = SA;
@@ -765,7 +797,7 @@ int launch_mac_tc(Ctx *c, const TcGeomP &gp, const TcGeomR &gr, const void *Pimg
     SFG_CUDA(c, cudaFuncSetAttribute(k_mac_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int nsm = 0;
     SFG_CUDA(c, cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->device));
-    const long long nitems = (long long)gp.L * (c->N / 4) * (tile_hi - tile_lo);
+    const long long nitems = p.item_base[gp.L];
     const int grid = (int)std::min<long long>(nsm, nitems);
     k_mac_tc<<<grid, 384, smem, st>>>(p);
     SFG_LAUNCHED(c, "k_mac_tc", st);

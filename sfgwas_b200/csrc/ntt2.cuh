@@ -257,7 +257,10 @@ struct TwTab {
 // passes.  A transform works on the slice `sl` (2^logS consecutive coefficients) of a 2^logN ring; local index j is global
 // index (sl << logS) + j.  ld(j) / st(j, v) move one coefficient (registers <-> wherever the caller keeps it).
 // ---------------------------------------------------------------------------------------------------------------
-template <class A, int R, bool LAST, class LD, class ST>
+// TWS: the twiddles of the passes before the last one (NttPsi[0 .. N/16), warp-uniform or nearly so) come from a SHARED-memory copy: with
+// 105-209 KB of shared memory per CTA the L1 is ~20 KB, every __ldg of a twiddle is an L2 round trip, and ncu shows the first multiply of
+// every butterfly group waiting for it (k_ks_inner2<ArD>: DMUL 6 % of the instructions, 13 % of the stall samples).
+template <class A, int R, bool LAST, class LD, class ST, bool TWS = false>
 __device__ __forceinline__ void fwd_pass(int s0, int logN, int logS, int sl, const typename A::TW *__restrict__ tw,
                                          const typename A::C &c, LD ld, ST st) {
     using T = typename A::T;
@@ -279,6 +282,7 @@ __device__ __forceinline__ void fwd_pass(int s0, int logN, int logS, int sl, con
             for (int g = 0; g < (1 << r); g++) {
                 TW w;
                 if (LAST) w = __ldg(tw + (size_t)((1 << r) - 1 + g) * (size_t)(1 << (logN - kLastR)) + hi);
+                else if (TWS) w = tw[(1 << (s0 + r)) + (hi << r) + g];
                 else w = __ldg(tw + (1 << (s0 + r)) + (hi << r) + g);
 #pragma unroll
                 for (int j = 0; j < half; j++) A::fwd(v[g * 2 * half + j], v[g * 2 * half + j + half], w, c);
@@ -322,23 +326,32 @@ __device__ __forceinline__ void inv_pass(int s0, int logN, int logS, int sl, con
 }
 
 // run-time stage count -> compile-time radix
-template <class A, bool INV, class LD, class ST>
+template <class A, bool INV, class LD, class ST, bool TWS = false>
 __device__ __forceinline__ void mid_pass(int R, int s0, int logN, int logS, int sl, const typename A::TW *tw, const typename A::C &c, LD ld,
                                          ST st) {
     switch (R) {
-        case 1: INV ? inv_pass<A, 1, false>(s0, logN, logS, sl, tw, c, ld, st) : fwd_pass<A, 1, false>(s0, logN, logS, sl, tw, c, ld, st); break;
-        case 2: INV ? inv_pass<A, 2, false>(s0, logN, logS, sl, tw, c, ld, st) : fwd_pass<A, 2, false>(s0, logN, logS, sl, tw, c, ld, st); break;
-        case 3: INV ? inv_pass<A, 3, false>(s0, logN, logS, sl, tw, c, ld, st) : fwd_pass<A, 3, false>(s0, logN, logS, sl, tw, c, ld, st); break;
-        default: INV ? inv_pass<A, 4, false>(s0, logN, logS, sl, tw, c, ld, st) : fwd_pass<A, 4, false>(s0, logN, logS, sl, tw, c, ld, st); break;
+        case 1: INV ? inv_pass<A, 1, false>(s0, logN, logS, sl, tw, c, ld, st) : fwd_pass<A, 1, false, LD, ST, TWS>(s0, logN, logS, sl, tw, c, ld, st); break;
+        case 2: INV ? inv_pass<A, 2, false>(s0, logN, logS, sl, tw, c, ld, st) : fwd_pass<A, 2, false, LD, ST, TWS>(s0, logN, logS, sl, tw, c, ld, st); break;
+        case 3: INV ? inv_pass<A, 3, false>(s0, logN, logS, sl, tw, c, ld, st) : fwd_pass<A, 3, false, LD, ST, TWS>(s0, logN, logS, sl, tw, c, ld, st); break;
+        default: INV ? inv_pass<A, 4, false>(s0, logN, logS, sl, tw, c, ld, st) : fwd_pass<A, 4, false, LD, ST, TWS>(s0, logN, logS, sl, tw, c, ld, st); break;
     }
 }
 
 // Forward transform of slice `sl`.  ld0(j, k) supplies the input of local coefficient j in the policy's input range, AFTER the
 // first (logN - logS) stages when the ring is sliced (see slice_input()).  The passes before the last one go through the padded
 // shared-memory array `s`; the results of the last pass are handed to fin(j, value, k), k = j mod 16 the register index -- 16 consecutive j per thread, lazy range.
+// number of twiddles the passes before the last one can touch: NttPsi[0 .. 2^(logN - kLastR))
+__host__ __device__ inline int ntt_mid_twiddles(int logN) { return logN > kLastR ? 1 << (logN - kLastR) : 1; }
+// cooperative copy of those twiddles into shared memory (call once per CTA and modulus, then __syncthreads())
+template <class A>
+__device__ __forceinline__ void ntt_stage_twiddles(typename A::TW *tw_s, const TwTab &tab, int logN) {
+    const typename A::TW *g = reinterpret_cast<const typename A::TW *>(tab.fwd);
+    for (int i = threadIdx.x; i < ntt_mid_twiddles(logN); i += blockDim.x) tw_s[i] = __ldg(g + i);
+}
+
 template <class A, class LD, class FIN>
 __device__ __forceinline__ void ntt_forward(typename A::T *s, int logN, int logS, int sl, const PassPlan &plan, const TwTab &tab,
-                                            const typename A::C &c, LD ld0, FIN fin) {
+                                            const typename A::C &c, LD ld0, FIN fin, const typename A::TW *tw_s = nullptr) {
     using T = typename A::T;
     using TW = typename A::TW;
     const TW *tw = reinterpret_cast<const TW *>(tab.fwd);
@@ -350,8 +363,13 @@ __device__ __forceinline__ void ntt_forward(typename A::T *s, int logN, int logS
     }
 #pragma unroll
     for (int i = 0; i < plan.n; i++) {
-        if (i == 0) mid_pass<A, false>(plan.R[i], s0, logN, logS, sl, tw, c, ld0, sts);
-        else mid_pass<A, false>(plan.R[i], s0, logN, logS, sl, tw, c, lds, sts);
+        if (tw_s) {  // twiddles staged in shared memory (ntt_stage_twiddles)
+            if (i == 0) mid_pass<A, false, LD, decltype(sts), true>(plan.R[i], s0, logN, logS, sl, tw_s, c, ld0, sts);
+            else mid_pass<A, false, decltype(lds), decltype(sts), true>(plan.R[i], s0, logN, logS, sl, tw_s, c, lds, sts);
+        } else {
+            if (i == 0) mid_pass<A, false>(plan.R[i], s0, logN, logS, sl, tw, c, ld0, sts);
+            else mid_pass<A, false>(plan.R[i], s0, logN, logS, sl, tw, c, lds, sts);
+        }
         s0 += plan.R[i];
         __syncthreads();
     }
