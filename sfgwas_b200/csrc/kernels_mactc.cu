@@ -711,7 +711,9 @@ int launch_img_extract(Ctx *c, const TcGeomP &g, const void *img_group, int l, i
 int tc_max_fused_groups(const TcGeomP &gp) {
     int nbmax = 1;
     for (int l = 0; l < gp.L; l++) nbmax = std::max(nbmax, gp.nb[l]);
-    return (int)std::max<long long>(1, 2147483647LL / ((long long)nbmax * gp.Kg * 65025LL));
+    long long g = std::max<long long>(1, 2147483647LL / ((long long)nbmax * gp.Kg * 65025LL));
+    if (const char *e = getenv("SFG_TC_MAXGROUPS")) g = std::max<long long>(1, std::min<long long>(g, atoll(e)));  // tests: force the multi-launch path
+    return (int)g;
 }
 
 int launch_mac_tc(Ctx *c, const TcGeomP &gp, const TcGeomR &gr, const void *Pimg_group, long long p_gstride, int img_ntiles, int img_tile0,

@@ -510,6 +510,30 @@ def test_seven_k_groups_transposed_shape(small13):
     assert (out == want).all()
 
 
+def test_k_groups_split_over_launches_accumulate_mod_q(small13, monkeypatch):
+    """K groups normally accumulate in TMEM inside ONE launch; beyond the s32 range of the partial sums (K > ~6 600) the K range is cut into
+    several launches that add into cv mod q in the epilogue.  SFG_TC_MAXGROUPS forces that path on a 7-group shape (2 + 2 + 2 + 1 groups):
+    same bits as the fused launch and as the oracle (covers the read-modify-write of the 64-byte output runs)."""
+    from sfgwas_b200 import GenoFileStream, MatMult4StreamCompute, MatMult4StreamPreprocess
+
+    o, cps, sk, keys = small13
+    nbr = (6 * 256) // o.d + 1
+    nr, nc, s = (nbr - 1) * o.slots + 5, o.slots + 9, 3
+    rng = np.random.default_rng(71)
+    X = rng.integers(0, 3, (nr, nc)).astype(np.int8)
+    A = enc_matrix(o, sk, rng.normal(size=(s, nr)))
+    cache = MatMult4StreamPreprocess(cps, GenoFileStream.from_matrix(cps, X), 5)
+    fused = MatMult4StreamCompute(cps, A, 5, cache)
+    monkeypatch.setenv("SFG_TC_MAXGROUPS", "2")
+    split = MatMult4StreamCompute(cps, A, 5, cache)
+    monkeypatch.delenv("SFG_TC_MAXGROUPS")
+    assert (split == fused).all()
+    dc = o.preprocess(X, 5, nproc=8)
+    want = o.compute(A, dc, keys, 5, nproc=8)
+    o.cache_free(dc)
+    assert (fused == want).all()
+
+
 @pytest.mark.parametrize("case", ["pn13_2x4_s10", "pn14_2x2_s15"])
 def test_benchmarked_geometry_golden(case):
     """Preprocess + Compute at the REAL parameter sets and the benchmarked geometry (several block rows, full 128-column tiles, giant
