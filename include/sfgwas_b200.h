@@ -189,6 +189,27 @@ int sfg_inner_sum_all(sfg_ctx *ctx, int level, const uint64_t *cts, int nvec, in
 /* EncodeNTT of an int8 slot vector v[slots] at params.Scale (the 0/1 mask of crypto.MaskTrunc), correctly rounded: out [level+1][N] */
 int sfg_encode_slots_i8(sfg_ctx *ctx, const int8_t *v, int level, int mont, uint64_t *out);
 
+/* ---- device-resident ciphertext vectors ("keeps Q on device across a power iteration") -------------------------------
+ * The host-buffer entry points above move every operand over PCIe/C2C per call.  A sfg_cts is an array of n degree-1 ciphertexts
+ * [n][2][nl][N] that STAYS in HBM between calls: the callers' algebra (CMult, CMultScalar, InnerSumAll, MaskTrunc, Sub) and the MatMult
+ * itself chain on handles; only what the Go side really needs on the host (the ciphertexts that go into the network bootstrap, final
+ * results) is downloaded.  Scale and level bookkeeping stays with the caller exactly as for the host-buffer variants. */
+typedef struct sfg_cts sfg_cts;
+int sfg_cts_upload(sfg_ctx *ctx, const uint64_t *host, int n, int nl, sfg_cts **out);
+int sfg_cts_download(sfg_ctx *ctx, const sfg_cts *cts, uint64_t *host);
+int sfg_cts_shape(const sfg_cts *cts, int *n, int *nl);
+void sfg_cts_destroy(sfg_cts *cts);
+/* copy of ciphertexts [first, first + count) (e.g. one row of a CipherMatrix stored row-major) */
+int sfg_cts_slice(sfg_ctx *ctx, const sfg_cts *cts, int first, int count, sfg_cts **out);
+/* MatMult4StreamCompute on handles: A holds s * num_block_rows ciphertexts (row-major), out s * m_ct at level max_level-1 */
+int sfg_cts_matmult4_stream_compute(sfg_ctx *ctx, const sfg_cts *A, int s, int num_block_rows, int max_level, const sfg_cache *cache,
+                                    sfg_cts **out);
+/* crypto.CMult / CMultScalar, MaskTrunc (plaintext from the host), eval.Sub / Add, crypto.InnerSumAll -- see the host-buffer variants */
+int sfg_cts_mul_relin(sfg_ctx *ctx, int level, const sfg_cts *x, const sfg_cts *y, int nrescale, sfg_cts **out);
+int sfg_cts_mul_plain(sfg_ctx *ctx, int level, const uint64_t *pt, int npt, int pt_nl, const sfg_cts *cts, int nrescale, sfg_cts **out);
+int sfg_cts_addsub(sfg_ctx *ctx, int level, const sfg_cts *a, const sfg_cts *b, int subtract, sfg_cts **out);
+int sfg_cts_inner_sum_all(sfg_ctx *ctx, int level, const sfg_cts *cts, int nvec, int cnt, sfg_cts **out);
+
 /* ---- local arithmetic of the collective bootstrap (mpc/mhe.go:262-341: CollectiveBootstrap / CollectiveBootstrapMat) ----
  * What every party computes per ciphertext around the two network aggregations (AggregateRefreshShare*, which stay in Go).  The random
  * draws stay in Go as well -- the mask (ring.RandInt, crypto/rand), the Gaussian noise, the common reference polynomial `crp` of the

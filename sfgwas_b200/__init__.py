@@ -4,6 +4,6 @@ Only what the path needs lives here: ``csrc/`` (CUDA kernels + the C ABI of incl
 host-side mirror of the reference interface (``gwas.py``).  There is no CPU fallback.
 """
 from ._lib import LIB_PATH, SYMBOLS, SfgError, load  # noqa: F401
-from .gwas import (CAdd, Ciphertext, CMult, CMultScalar, CryptoParams, CSub, DiagCache, GenoFileStream,  # noqa: F401
+from .gwas import (CAdd, Ciphertext, CMult, CMultScalar, CryptoParams, CSub, DeviceCipherVector, DiagCache, GenoFileStream,  # noqa: F401
                    InnerProd, InnerSumAll, LoadCipherMatrixFromFile, MaskTrunc, MatMult4Stream, MatMult4StreamCompute, MatMult4StreamPreprocess,
-                   QXLazyNormStream, QXtLazyNormStream, RefreshFinish, RefreshGenShares, SaveCipherMatrixToFile, SetRelinKey)
+                   QXLazyNormStream, QXtLazyNormStream, QXtLazyNormStreamDevice, RefreshFinish, RefreshGenShares, SaveCipherMatrixToFile, SetRelinKey)

@@ -27,7 +27,8 @@ SYMBOLS = [
     "sfg_matmult4_stream_preprocess_rows", "sfg_matmult4_stream_preprocess_giants", "sfg_ct_mod_reduce",
     "sfg_matmult4_finish_dev", "sfg_cipher_matrix_save", "sfg_cipher_matrix_info", "sfg_cipher_matrix_load",
     "sfg_refresh_gen_shares", "sfg_refresh_finish", "sfg_matmult4_baby_chunk_bytes", "sfg_matmult4_baby_dev",
-    "sfg_matmult4_stream_compute_r_dev",
+    "sfg_matmult4_stream_compute_r_dev", "sfg_cts_upload", "sfg_cts_download", "sfg_cts_shape", "sfg_cts_destroy", "sfg_cts_slice",
+    "sfg_cts_matmult4_stream_compute", "sfg_cts_mul_relin", "sfg_cts_mul_plain", "sfg_cts_addsub", "sfg_cts_inner_sum_all",
 ]
 
 _lib = None
@@ -113,6 +114,16 @@ def load():
     L.sfg_matmult4_baby_chunk_bytes.argtypes = [vp, vp, i32, i32]
     L.sfg_matmult4_baby_dev.argtypes = [vp, vp, i32, i32, i32, i32, vp, i32, i32, vp]
     L.sfg_matmult4_stream_compute_r_dev.argtypes = [vp, vp, i32, i32, vp, vp]
+    L.sfg_cts_upload.argtypes = [vp, vp, i32, i32, C.POINTER(vp)]
+    L.sfg_cts_download.argtypes = [vp, vp, vp]
+    L.sfg_cts_shape.argtypes = [vp, C.POINTER(i32), C.POINTER(i32)]
+    L.sfg_cts_destroy.argtypes = [vp]
+    L.sfg_cts_slice.argtypes = [vp, vp, i32, i32, C.POINTER(vp)]
+    L.sfg_cts_matmult4_stream_compute.argtypes = [vp, vp, i32, i32, i32, vp, C.POINTER(vp)]
+    L.sfg_cts_mul_relin.argtypes = [vp, i32, vp, vp, i32, C.POINTER(vp)]
+    L.sfg_cts_mul_plain.argtypes = [vp, i32, vp, i32, i32, vp, i32, C.POINTER(vp)]
+    L.sfg_cts_addsub.argtypes = [vp, i32, vp, vp, i32, C.POINTER(vp)]
+    L.sfg_cts_inner_sum_all.argtypes = [vp, i32, vp, i32, i32, C.POINTER(vp)]
     L.sfg_ctx_sync.argtypes = [vp]
     L.sfg_ctx_last_timings.argtypes = [vp, C.POINTER(C.c_float)]
     L.sfg_ctx_stream.restype = vp

@@ -16,6 +16,11 @@ struct sfg_geno {
 struct sfg_cache {
     Cache *ca;
 };
+struct sfg_cts {  // n ciphertexts [n][2][nl][N] resident in HBM
+    int device;
+    int n, nl;
+    uint64_t *d;
+};
 
 static std::string g_create_err;
 
@@ -626,6 +631,143 @@ int sfg_inner_sum_all(sfg_ctx *h, int level, const uint64_t *cts, int nvec, int 
     if (inner_sum_all_dev(c, level, io.in[0].as<uint64_t>(), nvec, cnt, io.out.as<uint64_t>())) return -1;
     return io.down(out, (size_t)nvec * ct);
 }
+// ---- device-resident ciphertext vectors: the *_dev orchestration of matmult.cu behind handles ----
+static int cts_new(Ctx *c, int n, int nl, sfg_cts **out) {
+    *out = nullptr;
+    if (n < 1 || nl < 1 || nl > c->nQ) SFG_FAIL(c, "sfg_cts: bad shape (%d ciphertexts, %d limbs)", n, nl);
+    SFG_CUDA(c, cudaSetDevice(c->device));
+    uint64_t *d = nullptr;
+    if (dev_alloc(c, (void **)&d, (size_t)n * 2 * nl * c->N * 8, "ciphertext vector")) return -1;
+    *out = new sfg_cts{c->device, n, nl, d};
+    return 0;
+}
+int sfg_cts_upload(sfg_ctx *h, const uint64_t *host, int n, int nl, sfg_cts **out) {
+    Ctx *c = &h->c;
+    if (cts_new(c, n, nl, out)) return -1;
+    if (upload(c, (*out)->d, host, (size_t)n * 2 * nl * c->N * 8)) {
+        sfg_cts_destroy(*out);
+        *out = nullptr;
+        return -1;
+    }
+    return 0;
+}
+int sfg_cts_download(sfg_ctx *h, const sfg_cts *v, uint64_t *host) {
+    Ctx *c = &h->c;
+    SFG_CUDA(c, cudaSetDevice(c->device));
+    SFG_CUDA(c, cudaMemcpyAsync(host, v->d, (size_t)v->n * 2 * v->nl * c->N * 8, cudaMemcpyDefault, c->stream));
+    SFG_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+int sfg_cts_shape(const sfg_cts *v, int *n, int *nl) {
+    if (n) *n = v->n;
+    if (nl) *nl = v->nl;
+    return 0;
+}
+void sfg_cts_destroy(sfg_cts *v) {
+    if (!v) return;
+    cudaSetDevice(v->device);
+    cudaFree(v->d);
+    delete v;
+}
+int sfg_cts_slice(sfg_ctx *h, const sfg_cts *v, int first, int count, sfg_cts **out) {
+    Ctx *c = &h->c;
+    if (first < 0 || count < 1 || first + count > v->n) SFG_FAIL(c, "sfg_cts_slice: [%d, %d) out of %d ciphertexts", first, first + count, v->n);
+    if (cts_new(c, count, v->nl, out)) return -1;
+    const size_t ct = (size_t)2 * v->nl * c->N;
+    SFG_CUDA(c, cudaMemcpyAsync((*out)->d, v->d + first * ct, count * ct * 8, cudaMemcpyDefault, c->stream));
+    SFG_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+int sfg_cts_matmult4_stream_compute(sfg_ctx *h, const sfg_cts *A, int s, int nbr, int max_level, const sfg_cache *cache, sfg_cts **out) {
+    Ctx *c = &h->c;
+    *out = nullptr;
+    if (s < 1 || nbr < 1 || s * nbr != A->n) SFG_FAIL(c, "sfg_cts_matmult4_stream_compute: A holds %d ciphertexts, not %d x %d", A->n, s, nbr);
+    sfg_cts *o = nullptr;
+    if (cts_new(c, s * cache->ca->m_ct, max_level, &o)) return -1;
+    if (mm_compute_dev(c, A->d, s, nbr, A->nl - 1, max_level, cache->ca, o->d)) {
+        sfg_cts_destroy(o);
+        return -1;
+    }
+    *out = o;
+    return 0;
+}
+int sfg_cts_mul_relin(sfg_ctx *h, int level, const sfg_cts *x, const sfg_cts *y, int nrescale, sfg_cts **out) {
+    Ctx *c = &h->c;
+    *out = nullptr;
+    if (nrescale < 0 || nrescale > level) SFG_FAIL(c, "sfg_cts_mul_relin: bad rescale count");
+    const int n = std::max(x->n, y->n);
+    sfg_cts *full = nullptr, *o = nullptr;
+    if (cts_new(c, n, level + 1, &full)) return -1;  // mul_relin_dev needs the un-rescaled product as scratch when nrescale > 0
+    int rc = mul_relin_dev(c, level, x->d, x->n, x->nl, y->d, y->n, y->nl, nrescale, full->d);
+    if (!rc && nrescale > 0) {  // results are dense [n][2][level+1-nrescale][N] at the front of the buffer: move into a right-sized handle
+        rc = cts_new(c, n, level + 1 - nrescale, &o);
+        if (!rc) {
+            cudaMemcpyAsync(o->d, full->d, (size_t)n * 2 * (level + 1 - nrescale) * c->N * 8, cudaMemcpyDefault, c->stream);
+            cudaStreamSynchronize(c->stream);
+        }
+        sfg_cts_destroy(full);
+        full = o;
+    }
+    if (rc) {
+        sfg_cts_destroy(full);
+        return -1;
+    }
+    *out = full;
+    return 0;
+}
+int sfg_cts_mul_plain(sfg_ctx *h, int level, const uint64_t *pt, int npt, int pt_nl, const sfg_cts *v, int nrescale, sfg_cts **out) {
+    Ctx *c = &h->c;
+    *out = nullptr;
+    if (npt < 1 || pt_nl < level + 1 || nrescale < 0 || nrescale > level) SFG_FAIL(c, "sfg_cts_mul_plain: bad counts");
+    SFG_CUDA(c, cudaSetDevice(c->device));
+    Buf dpt;
+    if (dpt.alloc(c, (size_t)npt * pt_nl * c->N * 8) || upload(c, dpt.p, pt, (size_t)npt * pt_nl * c->N * 8)) return -1;
+    sfg_cts *full = nullptr, *o = nullptr;
+    if (cts_new(c, v->n, level + 1, &full)) return -1;
+    int rc = mul_plain_dev(c, level, dpt.as<uint64_t>(), npt, pt_nl, v->d, v->n, v->nl, nrescale, full->d);
+    if (!rc && nrescale > 0) {
+        rc = cts_new(c, v->n, level + 1 - nrescale, &o);
+        if (!rc) {
+            cudaMemcpyAsync(o->d, full->d, (size_t)v->n * 2 * (level + 1 - nrescale) * c->N * 8, cudaMemcpyDefault, c->stream);
+            cudaStreamSynchronize(c->stream);
+        }
+        sfg_cts_destroy(full);
+        full = o;
+    }
+    if (rc) {
+        sfg_cts_destroy(full);
+        return -1;
+    }
+    *out = full;
+    return 0;
+}
+int sfg_cts_addsub(sfg_ctx *h, int level, const sfg_cts *a, const sfg_cts *b, int subtract, sfg_cts **out) {
+    Ctx *c = &h->c;
+    *out = nullptr;
+    sfg_cts *o = nullptr;
+    if (cts_new(c, std::max(a->n, b->n), level + 1, &o)) return -1;
+    if (addsub_dev(c, level, a->d, a->n, a->nl, b->d, b->n, b->nl, subtract != 0, o->d)) {
+        sfg_cts_destroy(o);
+        return -1;
+    }
+    *out = o;
+    return 0;
+}
+int sfg_cts_inner_sum_all(sfg_ctx *h, int level, const sfg_cts *v, int nvec, int cnt, sfg_cts **out) {
+    Ctx *c = &h->c;
+    *out = nullptr;
+    if (nvec < 1 || cnt < 1 || nvec * cnt != v->n || v->nl != level + 1)
+        SFG_FAIL(c, "sfg_cts_inner_sum_all: %d ciphertexts of %d limbs are not %d vectors of %d at level %d", v->n, v->nl, nvec, cnt, level);
+    sfg_cts *o = nullptr;
+    if (cts_new(c, nvec, level + 1, &o)) return -1;
+    if (inner_sum_all_dev(c, level, v->d, nvec, cnt, o->d)) {
+        sfg_cts_destroy(o);
+        return -1;
+    }
+    *out = o;
+    return 0;
+}
+
 // ---- local arithmetic of the collective bootstrap (mpc/mhe.go:262-341) ----
 int sfg_refresh_gen_shares(sfg_ctx *h, int level, int nct, const uint64_t *c1, const uint64_t *sk_mont, const uint64_t *crp, const uint64_t *mask_mag,
                            const int8_t *mask_sign, int nwords, double in_scale, double out_scale, const int64_t *e0, const int64_t *e1, uint64_t *share_decrypt,

@@ -21,6 +21,7 @@ import numpy as np
 from ._lib import SfgError, load
 
 __all__ = [
+    "DeviceCipherVector", "QXtLazyNormStreamDevice",
     "SaveCipherMatrixToFile", "LoadCipherMatrixFromFile", "RefreshGenShares", "RefreshFinish",
     "CryptoParams", "GenoFileStream", "DiagCache", "MatMult4StreamPreprocess", "MatMult4StreamCompute", "MatMult4Stream",
     "SfgError", "Ciphertext", "SetRelinKey", "CMult", "CMultScalar", "CSub", "CAdd", "InnerSumAll", "InnerProd", "MaskTrunc",
@@ -568,3 +569,99 @@ def QXtLazyNormStream(cps: CryptoParams, mpcObj, Q, XTcache: DiagCache, XMean, X
     for i in range(len(out)):
         out[i] = CMult(cps, out[i], XStdInv)
     return out
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# Device-resident ciphertext vectors ("keeps Q on device across a power iteration").  Same algebra as above, but the
+# operands live in HBM between calls (sfg_cts handles); only what has to reach the host (the network bootstrap, final results) moves.
+# ------------------------------------------------------------------------------------------------------------------------
+class DeviceCipherVector:
+    """n degree-1 ciphertexts at one level and scale, resident in HBM (a CipherVector, or a CipherMatrix stored row-major)."""
+
+    def __init__(self, cps: CryptoParams, h, scale: float):
+        self.cps, self.h, self.scale = cps, h, float(scale)
+        n, nl = C.c_int(), C.c_int()
+        cps.L.sfg_cts_shape(h, C.byref(n), C.byref(nl))
+        self.n, self.nl = n.value, nl.value
+        cps._children.add(self)
+
+    @classmethod
+    def upload(cls, cps: CryptoParams, cts) -> "DeviceCipherVector":
+        """cts: list of Ciphertext at one level and scale."""
+        lvl = min(c.Level() for c in cts)
+        a = _stack(cts, lvl)
+        h = C.c_void_p()
+        cps._check(cps.L.sfg_cts_upload(cps.h, _p(a), a.shape[0], lvl + 1, C.byref(h)), "sfg_cts_upload")
+        return cls(cps, h, cts[0].scale)
+
+    def download(self):
+        out = np.zeros((self.n, 2, self.nl, self.cps.N), dtype=np.uint64)
+        self.cps._check(self.cps.L.sfg_cts_download(self.cps.h, self.h, _p(out)), "sfg_cts_download")
+        return [Ciphertext(out[k], self.scale) for k in range(self.n)]
+
+    def Level(self) -> int:
+        return self.nl - 1
+
+    def slice(self, first: int, count: int) -> "DeviceCipherVector":
+        h = C.c_void_p()
+        self.cps._check(self.cps.L.sfg_cts_slice(self.cps.h, self.h, first, count, C.byref(h)), "sfg_cts_slice")
+        return DeviceCipherVector(self.cps, h, self.scale)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.cps.L.sfg_cts_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _dev_cmult(cps, X: DeviceCipherVector, Y: DeviceCipherVector) -> DeviceCipherVector:
+    """crypto.CMult / CMultScalar on handles (a side of length 1 broadcasts)."""
+    lvl = min(X.Level(), Y.Level())
+    k, sc = _nrescale(cps, X.scale * Y.scale, lvl)
+    h = C.c_void_p()
+    cps._check(cps.L.sfg_cts_mul_relin(cps.h, lvl, X.h, Y.h, k, C.byref(h)), "sfg_cts_mul_relin")
+    return DeviceCipherVector(cps, h, sc)
+
+
+def _dev_sub(cps, a: DeviceCipherVector, b: DeviceCipherVector) -> DeviceCipherVector:
+    r = max(a.scale, b.scale) / min(a.scale, b.scale)
+    if math.floor(r) > 1:
+        raise SfgError("ciphertext sub with scales %g and %g needs scale matching, which this path never does" % (a.scale, b.scale))
+    lvl = min(a.Level(), b.Level())
+    h = C.c_void_p()
+    cps._check(cps.L.sfg_cts_addsub(cps.h, lvl, a.h, b.h, 1, C.byref(h)), "sfg_cts_addsub")
+    return DeviceCipherVector(cps, h, max(a.scale, b.scale))
+
+
+def QXtLazyNormStreamDevice(cps: CryptoParams, mpcObj, Q: DeviceCipherVector, s: int, XTcache: DiagCache, XMean: DeviceCipherVector,
+                            XStdInv: DeviceCipherVector) -> DeviceCipherVector:
+    """gwas/matmult.go:83-116 with Q (s rows x num_block_rows ciphertexts, row-major), XMean and XStdInv resident in HBM: MatMult, the
+    row sums, the mean correction and the final scaling chain on the device; the only host round trip is the network bootstrap
+    (``mpcObj.Network.BootstrapMatAll``), which the reference performs on the host as well.  Bit-identical to QXtLazyNormStream."""
+    if mpcObj.GetPid() == 0:
+        return None
+    L = cps.L
+    nbr = Q.n // s
+    h = C.c_void_p()
+    cps._check(L.sfg_cts_matmult4_stream_compute(cps.h, Q.h, s, nbr, 5, XTcache.h, C.byref(h)), "sfg_cts_matmult4_stream_compute")
+    out = DeviceCipherVector(cps, h, Q.scale * cps.scale)
+    m_ct = out.n // s
+    # the collective bootstrap is a network protocol: download, bootstrap, upload (what the reference does with every MatMult output)
+    host = out.download()
+    boot = mpcObj.Network.BootstrapMatAll(cps, [host[i * m_ct:(i + 1) * m_ct] for i in range(s)])
+    out = DeviceCipherVector.upload(cps, [c for row in boot for c in row])
+    rows = []
+    for i in range(s):
+        qi = Q.slice(i * nbr, nbr)
+        hs = C.c_void_p()
+        cps._check(L.sfg_cts_inner_sum_all(cps.h, qi.Level(), qi.h, 1, nbr, C.byref(hs)), "sfg_cts_inner_sum_all")
+        rowSum = DeviceCipherVector(cps, hs, qi.scale)
+        Q1m = _dev_cmult(cps, XMean, rowSum)            # CMultScalar(XMean, rowSum)
+        oi = _dev_sub(cps, out.slice(i * m_ct, m_ct), Q1m)
+        rows.append(_dev_cmult(cps, oi, XStdInv))       # CMult(out[i], XStdInv)
+    return rows

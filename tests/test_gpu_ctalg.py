@@ -244,3 +244,16 @@ def test_qxt_lazy_norm_stream(env):
             dec = o.decrypt_vector(sk, got[i][j].value, got[i][j].scale).real
             seg = ref[i, j * o.slots:(j + 1) * o.slots]
             assert np.abs(dec[: len(seg)] - seg).max() < 2e-2, np.abs(dec[: len(seg)] - seg).max()
+    # the same wrapper with Q, XMean and XStdInv resident in HBM (sfg_cts handles): the MatMult, the row sums, the mean correction and the
+    # final scaling chain on the device; bit-identical to the host-buffer path
+    from sfgwas_b200 import DeviceCipherVector, QXtLazyNormStreamDevice
+
+    dQ = DeviceCipherVector.upload(cps, [Ciphertext(c, o.scale) for q in Q for c in q])
+    dMean = DeviceCipherVector.upload(cps, [Ciphertext(c, o.scale) for c in XMean])
+    dStd = DeviceCipherVector.upload(cps, [Ciphertext(c, o.scale) for c in XStdInv])
+    rows = QXtLazyNormStreamDevice(cps, _Mpc(_Net(o, sk, Ciphertext)), dQ, kp, cache, dMean, dStd)
+    for i in range(kp):
+        host = rows[i].download()
+        assert len(host) == len(got[i])
+        for j in range(len(host)):
+            assert (host[j].value == got[i][j].value).all() and abs(host[j].scale / got[i][j].scale - 1) < 1e-12, (i, j)
