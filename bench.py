@@ -52,6 +52,11 @@ WORKLOADS = {
     # the regime of configs 4 / 5: the cache cannot be HBM-resident, every call re-encodes the diagonals chunk by chunk
     "mm_10k_x_100k_k10_logN13_otf": dict(nrows=10000, ncols=100000, s=10, params="PN13QP218", orientation="A.X", otf=True),
     "mm_16k_x_64k_k15_logN14_otf": dict(nrows=16384, ncols=65536, s=15, params="PN14QP438", orientation="Q.X^T slice", otf=True),
+    # BASELINE config 4 at FULL size (one party's PCA half-iteration, Q.X^T direction: 13 x 62 blocks, 6.6 M diagonals per call): meant
+    # for --gpus 8.  colshard: every rank holds only ITS block columns of the int8 matrix (SNP-block sharding, 6.5 of the 50 GB) and
+    # produces those block columns of the output -- no all-reduce; the baby-step rotations are still shared 1/N + one all-gather
+    "pca_100k_x_500k_k15_logN14_otf": dict(nrows=100000, ncols=500000, s=15, params="PN14QP438", orientation="Q.X^T (config 4, full size)", otf=True,
+                                           colshard=True),
     "mm_32k_x_128k_k15_logN14_otf": dict(nrows=32768, ncols=131072, s=15, params="PN14QP438", orientation="Q.X^T slice (config 4, 4 x 16 of 13 x 62 blocks)", otf=True),
 }
 # complete small call the CPU arm times (same parameter set and s; one block row): (nrows, ncols)
@@ -184,7 +189,8 @@ def verify_decrypt(o, sk, Ap, xcols, out, picks):
 
     worst, scale_ref = 0.0, 1.0
     for i, bj in picks:
-        ref = Ap[i] @ xcols[bj]
+        xc = xcols[bj]  # int8 on the host; converted in row chunks (the full-size config-4 column is 100k x 8192)
+        ref = sum(Ap[i][r:r + 8192] @ xc[r:r + 8192].astype(np.float64) for r in range(0, xc.shape[0], 8192))
         got = o.decrypt_vector(sk, out[i, bj], o.scale * o.scale).real[: len(ref)]
         worst = max(worst, float(np.abs(got - ref).max()))
         scale_ref = max(scale_ref, float(np.abs(ref).max()))
@@ -306,6 +312,10 @@ def run_ours(args, rank, local_rank, world):
     ext = torch.cuda.ExternalStream(L.sfg_ctx_stream(cps.h), device=dev)
     torch.cuda.set_stream(ext)
     otf = bool(w.get("otf")) or args.cache_budget_gb is not None
+    colshard = (bool(w.get("colshard")) or args.col_sharding) and world > 1
+    bc_lo, bc_hi = partition(m_ct, world)[rank] if colshard else (0, m_ct)  # block columns this rank holds and produces
+    c_lo, c_hi = bc_lo * slots, min(bc_hi * slots, ncols)
+    m_loc = bc_hi - bc_lo
     if otf:
         cps.set_cache_budget(int((args.cache_budget_gb if args.cache_budget_gb is not None else 0.001) * 1e9))
 
@@ -338,36 +348,37 @@ def run_ours(args, rank, local_rank, world):
     # ---- genotype matrix on the device (same on every rank), pushed through the ABI in row chunks; the block columns used by the
     #      decrypt check are kept on the host ----
     g = C.c_void_p()
-    cps._check(L.sfg_geno_create(cps.h, nrows, ncols, C.byref(g)), "geno_create")
+    cps._check(L.sfg_geno_create(cps.h, nrows, c_hi - c_lo, C.byref(g)), "geno_create")
     gx = torch.Generator(device=dev)
     gx.manual_seed(1)
     maf = torch.rand(ncols, generator=gx, device=dev) * 0.45 + 0.05
     picks = sorted({(0, 0), (s // 2, m_ct // 2), (s - 1, m_ct - 1)})
-    xcols = {bj: [] for _, bj in picks}
+    keeper = (lambda bj: bc_lo <= bj < bc_hi) if colshard else (lambda bj: rank == 0)  # who checks (and so keeps) a block column
+    xcols = {bj: [] for _, bj in picks if real and keeper(bj)}
     for r0 in range(0, nrows, 512):
         r1 = min(nrows, r0 + 512)
         x = (torch.rand(r1 - r0, ncols, generator=gx, device=dev) < maf).to(torch.int8) + \
             (torch.rand(r1 - r0, ncols, generator=gx, device=dev) < maf).to(torch.int8)
-        cps._check(L.sfg_geno_push_rows(g, C.c_void_p(x.data_ptr()), r1 - r0), "geno_push_rows")
-        if real and rank == 0:
-            for bj in xcols:
-                xcols[bj].append(x[:, bj * slots:(bj + 1) * slots].cpu().numpy().astype(np.float64))
-    del x
-    xcols = {bj: np.concatenate(v) for bj, v in xcols.items()} if real and rank == 0 else {}
+        xl = x[:, c_lo:c_hi].contiguous() if colshard else x
+        cps._check(L.sfg_geno_push_rows(g, C.c_void_p(xl.data_ptr()), r1 - r0), "geno_push_rows")
+        for bj in xcols:
+            xcols[bj].append(x[:, bj * slots:(bj + 1) * slots].cpu().numpy())  # int8: converted when the check runs
+    del x, xl
+    xcols = {bj: np.concatenate(v) for bj, v in xcols.items()}
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     cache = C.c_void_p()
-    if world > 1:
+    if world > 1 and not colshard:
         cps._check(L.sfg_matmult4_stream_preprocess_giants(cps.h, g, 5, rank, world, C.byref(cache)), "preprocess_giants")
     else:
         cps._check(L.sfg_matmult4_stream_preprocess(cps.h, g, 5, C.byref(cache)), "preprocess")
     t_prep = time.perf_counter() - t0
     npoly, cbytes, mat = C.c_size_t(), C.c_size_t(), C.c_int()
     L.sfg_cache_info(cache, C.byref(npoly), C.byref(cbytes), C.byref(mat), None, None)
-    assert npoly.value == wf["diag_polys"], (npoly.value, wf["diag_polys"])
+    assert colshard or npoly.value == wf["diag_polys"], (npoly.value, wf["diag_polys"])
     assert bool(mat.value) != otf or cbytes.value == 0, "cache materialisation does not match the workload (otf=%s)" % otf
 
-    d_out = torch.zeros(s, m_ct, 2, 5, N, dtype=torch.int64, device=dev)
+    d_out = torch.zeros(s, m_loc, 2, 5, N, dtype=torch.int64, device=dev)
     h_A = torch.empty(d_A.shape, dtype=torch.int64, pin_memory=True)
     h_A.copy_(d_A)
     h_out = torch.empty(d_out.shape, dtype=torch.int64, pin_memory=True)
@@ -395,6 +406,10 @@ def run_ours(args, rank, local_rank, world):
             # baby-step sharding: 1/world of the rotation-cache entries per rank, ONE all-gather over NVLink, then MAC + giant-step sums
             chunk = int(L.sfg_matmult4_baby_chunk_bytes(cps.h, cache, s, world))
             if R_buf[0] is None:
+                if colshard:  # every rank's own cache must see the same baby steps (true when each holds a full-width block column)
+                    cmm = torch.tensor([chunk, -chunk], device=dev)
+                    dist.all_reduce(cmm, op=dist.ReduceOp.MAX)
+                    assert int(cmm[0]) == chunk == -int(cmm[1]), "ranks disagree on the rotation-cache share"
                 R_buf[0] = torch.empty(world * chunk, dtype=torch.uint8, device=dev)
             R = R_buf[0]
             cps._check(L.sfg_matmult4_baby_dev(cps.h, C.c_void_p(d_A.data_ptr()), s, nbr, 5, 5, cache, rank, world, C.c_void_p(R.data_ptr())),
@@ -406,7 +421,7 @@ def run_ours(args, rank, local_rank, world):
             cps._check(L.sfg_matmult4_stream_compute_r_dev(cps.h, C.c_void_p(R.data_ptr()), s, 5, cache, C.c_void_p(d_out.data_ptr())),
                        "compute_r_dev")
             add_timings()
-        if world > 1:  # partial sums over this rank's giant steps -> the full product on every rank (modular-add all-reduce over NVLink)
+        if world > 1 and not colshard:  # partial sums over this rank's giant steps -> the full product on every rank (modular-add all-reduce)
             ct_mod_allreduce_(d_out, cps, 5)
 
     def step_e2e():
@@ -417,7 +432,9 @@ def run_ours(args, rank, local_rank, world):
         d_A.copy_(h_A, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         step_dev()
-        if row_hi > row_lo:
+        if colshard:
+            h_out.copy_(d_out, non_blocking=True)
+        elif row_hi > row_lo:
             h_out[row_lo:row_hi].copy_(d_out[row_lo:row_hi], non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
@@ -481,9 +498,27 @@ def run_ours(args, rank, local_rank, world):
 
     # ---- correctness of what was just timed (outside the timed region) ----
     verify = None
-    if world > 1:  # the host copy is striped over the ranks: gather the stripes on rank 0 for the check
+    if colshard:  # every rank decrypt-checks the picked outputs among its own block columns; rank 0 merges
+        mine = None
+        if real:
+            out_np = h_out.numpy().view(np.uint64)
+            mp = [(i, bj) for i, bj in picks if keeper(bj)]
+            mine = verify_decrypt(o, sk, Ap, {bj - bc_lo: v for bj, v in xcols.items()}, out_np, [(i, bj - bc_lo) for i, bj in mp])
+            mine["checked"] = [list(p) for p in mp]
+            mine["dev_equals_e2e"] = bool((d_out.cpu().numpy().view(np.uint64) == out_np).all())
+        parts = [None] * world
+        dist.all_gather_object(parts, mine)
+        if real and rank == 0:
+            verify = dict(decrypt_max_abs_err=max(p["decrypt_max_abs_err"] for p in parts),
+                          tolerance=min(p["tolerance"] for p in parts if p["checked"]),  # each rank's own: 1e-3 of ITS largest reference value
+                          max_abs_reference=max(p["max_abs_reference"] for p in parts), checked=sum((p["checked"] for p in parts), []),
+                          ok=all(p["ok"] for p in parts), dev_equals_e2e=all(p["dev_equals_e2e"] for p in parts))
+            if not (verify["ok"] and verify["dev_equals_e2e"] and len(verify["checked"]) == len(picks)):
+                print(json.dumps(dict(error="verification failed", verify=verify)), flush=True)
+                sys.exit(1)
+    elif world > 1:  # the host copy is striped over the ranks: gather the stripes on rank 0 for the check
         h_full = d_out.cpu()
-    if real and rank == 0:
+    if real and rank == 0 and not colshard:
         out_np = (h_out if world == 1 else h_full).numpy().view(np.uint64)
         verify = verify_decrypt(o, sk, Ap, xcols, out_np, picks)
         verify["dev_equals_e2e"] = bool((d_out.cpu().numpy().view(np.uint64) == out_np).all())
@@ -515,18 +550,24 @@ def run_ours(args, rank, local_rank, world):
                         step="MatMult4StreamCompute over the HBM-resident diagonal cache" if not otf else
                              "MatMult4StreamCompute with the diagonals re-encoded from the int8 genotypes inside every call (cache over budget)",
                         cache_bytes=cbytes.value, cache_materialised=bool(mat.value), preprocess_s=t_prep, input_setup_s=t_inputs,
+                        hbm_in_use_gb=round((lambda fr, tot: (tot - fr) / 1e9)(*torch.cuda.mem_get_info()), 1),
                         inputs="real encryptions of a known matrix under seeded keys (decrypt-checked, see verify)" if real else
                                "uniformly random residues",
                         l2_policy="inputs (%.1f GB cache per rank) larger than L2; no flush needed" % (cbytes.value / 1e9) if not otf else
                                   "every call streams freshly encoded diagonals (GBs per chunk) through HBM; larger than L2",
-                        sharding=("giant-step sharding of ONE product over %d ranks: 1/%d of the cache, MAC and giant-step key-switches per "
+                        sharding=("SNP-block (block-column) sharding of ONE product over %d ranks: each holds %d-%d of the %d block columns of the "
+                                  "int8 matrix and produces those columns of the output (no all-reduce); baby-step rotations sharded 1/%d "
+                                  "per rank + one all-gather of the rotation cache inside the timed region"
+                                  % (world, m_ct // world, -(-m_ct // world), m_ct, world)) if colshard else
+                                 ("giant-step sharding of ONE product over %d ranks: 1/%d of the cache, MAC and giant-step key-switches per "
                                   "rank, baby-step rotations %s, modular-add all-reduce of the %d output ciphertexts (NCCL SUM + mod q) inside "
                                   "the timed region" % (world, world, "replicated" if args.no_baby_sharding else
                                                         "sharded 1/%d per rank + one all-gather of the rotation cache" % world, s * m_ct)) if world > 1 else "single GPU",
                         encoder_rechecked_coeffs=enc_stats[0], encoder_unresolved=enc_stats[1]),
             e2e=dict(value=e2e_v, unit="GB/s", ms_per_step=ms_e2e / args.steps, h2d_bytes_per_step=int(h_A.numel() * 8),
-                     d2h_bytes_per_step=int(h_out.numel() * 8) if world == 1 else int(h_out[row_lo:row_hi].numel() * 8),
+                     d2h_bytes_per_step=int(h_out.numel() * 8) if world == 1 or colshard else int(h_out[row_lo:row_hi].numel() * 8),
                      path="sfg_matmult4_stream_compute (pinned host A and out, D2H overlapped with the giant-step sums)" if world == 1 else
+                          "per rank: pinned A -> device, compute, this rank's block columns of the output -> pinned host" if colshard else
                           "per rank: pinned A -> device, compute + all-reduce, this rank's stripe of output rows -> pinned host"),
             gpu_launches=int(launches),
             roofline=dict(bound="hbm", kernel="k_mac_tc (K1+K2: tcgen05 kind::i8 byte-plane MAC + recombine + modular reduce)",
@@ -572,6 +613,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--synthetic-inputs", action="store_true", help="uniformly random residues instead of real keys / encryptions (no decrypt check)")
     ap.add_argument("--no-baby-sharding", action="store_true", help="N > 1: every rank repeats all baby-step rotations (no all-gather)")
+    ap.add_argument("--col-sharding", action="store_true", help="N > 1: SNP-block sharding (each rank holds and produces its block columns) instead of giant-step sharding")
     ap.add_argument("--cache-budget-gb", type=float, default=None, help="HBM budget of the diagonal cache; below the image size the diagonals are re-encoded on the fly")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

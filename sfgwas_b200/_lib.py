@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libsfgwas_b200.so")
+# SFG_B200_LIB: load another build of the library (A/B runs of kernel variants under profiles/); the default is the in-tree build
+LIB_PATH = os.environ.get("SFG_B200_LIB") or os.path.join(_HERE, "lib", "libsfgwas_b200.so")
 
 # every symbol declared in include/sfgwas_b200.h (checked by tests/test_abi.py)
 SYMBOLS = [

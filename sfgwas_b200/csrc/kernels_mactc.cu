@@ -492,6 +492,8 @@ __global__ void __launch_bounds__(512, 1) k_img_build(const __grid_constant__ Im
     const int n0 = blockIdx.x * NCH, r0 = blockIdx.y * 16;
     const int tid = threadIdx.x;
     const uint8_t *src = p.src + p.limb_off[li] + (size_t)n0 * sizeof(T);
+    // (one 32-byte sector per source record and thread.  Requesting 2-4 sectors per thread before the first use was measured SLOWER,
+    //  profiles/r2/ab_img_build_load_batching.txt: the phase is not bound by the bytes in flight)
     for (int idx = tid; idx < p.Kg * 16; idx += blockDim.x) {
         const int c = idx & 15, k = idx >> 4;
         const int row = r0 + c;

@@ -87,14 +87,15 @@ static int encode_jobs(Ctx *c, const Cache *ca, const std::vector<EncJob> &jobs,
     return 0;
 }
 
-// Encode the diagonals of column tiles [tile_lo, tile_hi) (columns = (active giant, block column) pairs, 128 per tile; all K
-// groups) and lay them out as a tensor-core image holding exactly those tiles.  img: ngroups * tc_group_bytes(ntiles) bytes.
+// Encode the diagonals of column tiles [tile_lo, tile_hi) (columns = (active giant, block column) pairs, 128 per tile) for the K
+// groups [grp_lo, grp_hi) and lay them out as a tensor-core image holding exactly those tiles and groups.
+// img: (grp_hi - grp_lo) * tc_group_bytes(ntiles) bytes.
 static long long tc_group_bytes(const Cache *ca, int ntiles) {
     long long b = 0;
     for (int l = 0; l < ca->tc.L; l++) b += (long long)ca->tc.N * ntiles * ca->tc.nb[l] * 128 * ca->tc.Kg;
     return b;
 }
-static int build_p_tiles(Ctx *c, const Cache *ca, int tile_lo, int tile_hi, unsigned char *img) {
+static int build_p_tiles(Ctx *c, const Cache *ca, int tile_lo, int tile_hi, int grp_lo, int grp_hi, unsigned char *img) {
     const TcGeomP &tc = ca->tc;
     const int d = ca->d, m_ct = ca->m_ct, slots = ca->slots, Kg = tc.Kg, K = tc.K;
     const int ntl = tile_hi - tile_lo;
@@ -108,7 +109,7 @@ static int build_p_tiles(Ctx *c, const Cache *ca, int tile_lo, int tile_hi, unsi
     std::vector<long long> tab((size_t)128 * Kg);
     std::vector<EncJob> jobs;
     for (int ct = tile_lo; ct < tile_hi; ct++)
-        for (int grp = 0; grp < tc.ngroups; grp++) {
+        for (int grp = grp_lo; grp < grp_hi; grp++) {
             jobs.clear();
             std::fill(tab.begin(), tab.end(), -1LL);
             for (int cc = 0; cc < 128; cc++) {
@@ -130,7 +131,8 @@ static int build_p_tiles(Ctx *c, const Cache *ca, int tile_lo, int tile_hi, unsi
             }
             SFG_CUDA(c, cudaMemcpyAsync(dtab, tab.data(), tab.size() * sizeof(long long), cudaMemcpyDefault, c->stream));
             if (!jobs.empty() && encode_jobs(c, ca, jobs, tmp)) return -1;  // (no diagonal in this block: the all -1 table writes zeros)
-            if (launch_img_p(c, tc, ca->lay, tmp, (const long long *)dtab, ntl, ct - tile_lo, img + (size_t)grp * gbytes, c->stream)) return -1;
+            if (launch_img_p(c, tc, ca->lay, tmp, (const long long *)dtab, ntl, ct - tile_lo, img + (size_t)(grp - grp_lo) * gbytes, c->stream))
+                return -1;
         }
     return 0;
 }
@@ -243,7 +245,7 @@ int cache_build(Ctx *c, Geno *g, int maxLevel, Cache **out, int bi_lo, int bi_hi
         if (e == cudaSuccess) {
             ca->img_bytes = bytes;
             poison_fill(c, ca->img, bytes);  // SFG_POISON=1: a byte the image builder failed to write would surface as a parity failure
-            if (build_p_tiles(c, ca, 0, ca->tc.ntiles, ca->img) || cudaStreamSynchronize(c->stream) != cudaSuccess) {
+            if (build_p_tiles(c, ca, 0, ca->tc.ntiles, 0, ca->tc.ngroups, ca->img) || cudaStreamSynchronize(c->stream) != cudaSuccess) {
                 if (c->err.empty()) c->err = "diagonal cache build failed";
                 cache_destroy(ca);
                 return -1;
@@ -545,28 +547,36 @@ static int run_mac(Ctx *c, const Cache *ca, const void *R, const std::vector<int
     // all K groups accumulate in TMEM inside one launch (many block rows: the transposed orientation, PCA shapes); only when their
     // products could overflow the s32 partial sums is the K range cut into several launches that add into cv mod q
     const int gf = tc_max_fused_groups(tc);
-    auto mac = [&](const unsigned char *pimg, long long p_gstride, int img_ntiles, int img_tile0, int t0, int t1) -> int {
+    // pimg holds the K groups [g_lo, g_hi) of some tiles; the first group of the whole K range overwrites cv, the others add into it
+    auto mac = [&](const unsigned char *pimg, long long p_gstride, int img_ntiles, int img_tile0, int t0, int t1, int g_lo, int g_hi) -> int {
         if (g_tm) g_tm->mark(3);  // the MAC kernel alone, on the stream it is launched on (bench.py roofline)
         for (const MacPart &pt : parts)
-            for (int grp = 0; grp < tc.ngroups; grp += gf)
-                if (launch_mac_tc(c, tc, pt.gr, pimg + (size_t)grp * p_gstride, p_gstride, img_ntiles, img_tile0,
-                                  pt.rimg + (size_t)grp * pt.gr.group_bytes, pt.gr.group_bytes, std::min(gf, tc.ngroups - grp), t0, t1, col_lo, col_hi,
+            for (int grp = g_lo; grp < g_hi; grp += gf)
+                if (launch_mac_tc(c, tc, pt.gr, pimg + (size_t)(grp - g_lo) * p_gstride, p_gstride, img_ntiles, img_tile0,
+                                  pt.rimg + (size_t)grp * pt.gr.group_bytes, pt.gr.group_bytes, std::min(gf, g_hi - grp), t0, t1, col_lo, col_hi,
                                   grp > 0, d_cv, c->stream))
                     return -1;
         if (g_tm) g_tm->mark(1);
         return 0;
     };
-    if (ca->materialised) return mac(ca->img, tc.group_bytes, tc.ntiles, 0, tile_lo, tile_hi);
-    // diagonals regenerated on the fly: tile chunks bounded by a temporary image of at most ~6 GiB; every chunk is encoded ONCE and
-    // consumed by all row parts
-    const long long per_tile = tc_group_bytes(ca, 1) * tc.ngroups;
-    const int tchunk = (int)std::max<long long>(1, std::min<long long>(tile_hi - tile_lo, ((long long)6 << 30) / per_tile));
+    if (ca->materialised) return mac(ca->img, tc.group_bytes, tc.ntiles, 0, tile_lo, tile_hi, 0, tc.ngroups);
+    // diagonals regenerated on the fly: a temporary image of at most ~6 GiB (SFG_OTF_IMG_MB overrides: tests) holds a chunk of tiles
+    // with all their K groups -- or, when one tile's groups alone exceed it (many block rows: PCA shapes), one tile and as many K
+    // groups as fit.  Every diagonal is encoded ONCE and consumed by all row parts.
+    long long img_budget = (long long)6 << 30;
+    if (const char *e = getenv("SFG_OTF_IMG_MB")) img_budget = std::max(1LL, atoll(e)) << 20;
+    const long long per_tg = tc_group_bytes(ca, 1), per_tile = per_tg * tc.ngroups;
+    const int tchunk = (int)std::max<long long>(1, std::min<long long>(tile_hi - tile_lo, img_budget / per_tile));
+    const int gchunk = per_tile <= img_budget ? tc.ngroups : (int)std::max<long long>(1, img_budget / per_tg);
     void *pimg;
-    if (ws_get(c, WS_PIMG, (size_t)per_tile * tchunk, &pimg)) return -1;
+    if (ws_get(c, WS_PIMG, (size_t)per_tg * tchunk * gchunk, &pimg)) return -1;
     for (int t0 = tile_lo; t0 < tile_hi; t0 += tchunk) {
         const int t1 = std::min(tile_hi, t0 + tchunk);
-        if (build_p_tiles(c, ca, t0, t1, (unsigned char *)pimg)) return -1;
-        if (mac((const unsigned char *)pimg, tc_group_bytes(ca, t1 - t0), t1 - t0, t0, t0, t1)) return -1;
+        for (int g0 = 0; g0 < tc.ngroups; g0 += gchunk) {
+            const int g1 = std::min(tc.ngroups, g0 + gchunk);
+            if (build_p_tiles(c, ca, t0, t1, g0, g1, (unsigned char *)pimg)) return -1;
+            if (mac((const unsigned char *)pimg, tc_group_bytes(ca, t1 - t0), t1 - t0, t0, t0, t1, g0, g1)) return -1;
+        }
     }
     return 0;
 }

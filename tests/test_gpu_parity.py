@@ -534,6 +534,33 @@ def test_k_groups_split_over_launches_accumulate_mod_q(small13, monkeypatch):
     assert (fused == want).all()
 
 
+def test_on_the_fly_image_chunked_by_k_group(small13, monkeypatch):
+    """Diagonals re-encoded inside the call, many block rows: when the K groups of ONE column tile exceed the temporary image (config 4
+    at full size: 5 groups x 14 GB), the image holds one tile and as many K groups as fit, and the MAC adds group chunk after group
+    chunk into cv.  SFG_OTF_IMG_MB shrinks the image so that a 7-group shape runs as 2 + 2 + 2 + 1: same bits as the resident cache."""
+    from sfgwas_b200 import GenoFileStream, MatMult4StreamCompute, MatMult4StreamPreprocess
+
+    o, cps, sk, keys = small13
+    nbr = (6 * 256) // o.d + 1
+    nr, nc, s = (nbr - 1) * o.slots + 5, 2 * o.slots + 9, 3
+    rng = np.random.default_rng(72)
+    X = rng.integers(0, 3, (nr, nc)).astype(np.int8)
+    A = enc_matrix(o, sk, rng.normal(size=(s, nr)))
+    gfs = GenoFileStream.from_matrix(cps, X)
+    resident = MatMult4StreamCompute(cps, A, 5, MatMult4StreamPreprocess(cps, gfs, 5))
+    cps.set_cache_budget(1)
+    c2 = MatMult4StreamPreprocess(cps, gfs, 5)
+    cps.set_cache_budget(0)
+    assert not c2.materialised
+    whole_tiles = MatMult4StreamCompute(cps, A, 5, c2)
+    per_tg_mb = o.N * sum((int(q) - 1).bit_length() + 7 >> 3 for q in o.Q[:5]) * 128 * 256 >> 20
+    monkeypatch.setenv("SFG_OTF_IMG_MB", str(2 * per_tg_mb + 1))
+    by_group = MatMult4StreamCompute(cps, A, 5, c2)
+    monkeypatch.delenv("SFG_OTF_IMG_MB")
+    assert (whole_tiles == resident).all()
+    assert (by_group == resident).all()
+
+
 @pytest.mark.parametrize("case", ["pn13_2x4_s10", "pn14_2x2_s15"])
 def test_benchmarked_geometry_golden(case):
     """Preprocess + Compute at the REAL parameter sets and the benchmarked geometry (several block rows, full 128-column tiles, giant
