@@ -78,7 +78,7 @@ struct TcGeomR {                 // geometry of the rotated-ciphertext image (pe
     int tbuf_stride;
 };
 int tc_geom_p(Ctx *c, int L, int K, int ncols, TcGeomP *g);
-int tc_geom_r(Ctx *c, const TcGeomP &gp, int rows, TcGeomR *g);
+int tc_geom_r(Ctx *c, const TcGeomP &gp, int rows, TcGeomR *g, int rp_min = 0);
 // records -> image.  src_off_dev: device [Kg][128] (P) / [Kg][rows] (R) byte offsets of the source records, -1 = zero.
 int launch_img_p(Ctx *c, const TcGeomP &g, const PolyLayout &lay, const void *records, const long long *src_off_dev, int img_ntiles,
                  int ct_in_img, void *img_group, cudaStream_t st);
@@ -90,7 +90,9 @@ int launch_img_extract(Ctx *c, const TcGeomP &g, const void *img_group, int l, i
 int tc_max_fused_groups(const TcGeomP &gp);
 int launch_mac_tc(Ctx *c, const TcGeomP &gp, const TcGeomR &gr, const void *Pimg_group, long long p_gstride, int img_ntiles, int img_tile0,
                   const void *Rimg_group, long long r_gstride, int ngroups, int tile_lo, int tile_hi, int col_lo, int col_hi, bool accumulate,
-                  uint64_t *cv, cudaStream_t st);
+                  uint64_t *cv, cudaStream_t st, const void *Rimg_group2 = nullptr, int cv_row0_2 = 0, int rows2 = 0);
+// Rimg_group2 != nullptr ("pair mode"): a second row part of the SAME image geometry (RP, npad) with rows2 rows starting at cv_row0_2 is computed by
+// the same launch -- 2-CTA clusters, each CTA fetches half of every P stage and multicasts it to both, so P leaves HBM once for both parts
 
 // ---- key-switch + automorphism (kernels_ks.cu) ----
 // A batch is a list of ciphertexts, each rotated with its own Galois key.  All arrays are DEVICE arrays of nct entries.

@@ -70,6 +70,23 @@ __device__ __forceinline__ void bulk_g2s_hint(void *smem, const void *gmem, uint
                  "l"(gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
                  : "memory");
 }
+// the same copy delivered to the same shared-memory offset (and mbarrier offset) of every CTA of the cluster named in cta_mask
+__device__ __forceinline__ void bulk_g2s_mc_hint(void *smem, const void *gmem, uint32_t bytes, uint64_t *bar, uint16_t cta_mask, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster.L2::cache_hint [%0], [%1], %2, [%3], %4, %5;\n" ::"r"(
+            smem_u32(smem)),
+        "l"(gmem), "r"(bytes), "r"(smem_u32(bar)), "h"(cta_mask), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
 __device__ __forceinline__ uint64_t policy_evict_first() {
     uint64_t p;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(p));
@@ -84,6 +101,12 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+// the same arrival on the mbarrier at this offset in every CTA of cta_mask
+__device__ __forceinline__ void tc_commit_mc(uint64_t *bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(smem_u32(bar)),
+                 "h"(cta_mask)
+                 : "memory");
 }
 // D[tmem] (+)= A[smem] * B[smem]^T, u8 x u8 -> s32, M = 128, K = 32 per instruction
 __device__ __forceinline__ void umma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -118,6 +141,9 @@ constexpr int kZeroBytes = 8192;
 struct MacTcParams {
     const uint8_t *P;     // P image of this K group
     const uint8_t *R;     // R image of this K group
+    const uint8_t *R2;    // pair mode: the R image of the second row part (CTA rank 1 of every 2-CTA cluster), same geometry
+    int pair, cv_row0_2, rows2;  // pair mode: both CTAs of a cluster walk the same items; each fetches HALF of every A stage and multicasts it
+                          // to both, so the P image is read from HBM once for two row parts; cv_row0_2 / rows2 = first cv row / rows of the second part
     uint64_t *cv;         // [col - col_lo][rows][L][N] canonical residues
     const LimbConst *lc;
     int L, N, rows, RP, Kg;
@@ -195,9 +221,10 @@ __device__ __forceinline__ uint64_t recombine(const uint32_t *T, const uint64_t 
 // One accumulator tile: straight-line code per chunk of 4 rows (NB and the reduction class are compile-time, the four rows
 // are independent dependency chains), results staged in shared memory as outb[row][slot][column].
 template <int NB, int FAST>
-__device__ __forceinline__ void epilogue_tile(const MacTcParams &p, int l, uint32_t taddr, int slot, uint64_t *outb, int t, int half, int ngf) {
+__device__ __forceinline__ void epilogue_tile(const MacTcParams &p, int rows, int l, uint32_t taddr, int slot, uint64_t *outb, int t, int half,
+                                              int ngf) {
     constexpr int NS = 2 * NB - 1;
-    const int RP = p.RP, rows = p.rows;
+    const int RP = p.RP;
     const LimbConst lc = p.lc[l];
     const uint32_t nqinv32 = 0u - (uint32_t)lc.qinv;  // -q^-1 mod 2^32
     uint64_t cs[NS];
@@ -235,11 +262,12 @@ __device__ __forceinline__ void epilogue_tile(const MacTcParams &p, int l, uint3
 }
 
 template <int NB>
-__device__ __forceinline__ void epilogue_nb(const MacTcParams &p, int l, uint32_t taddr, int slot, uint64_t *outb, int t, int half, int ngf) {
+__device__ __forceinline__ void epilogue_nb(const MacTcParams &p, int rows, int l, uint32_t taddr, int slot, uint64_t *outb, int t, int half,
+                                            int ngf) {
     const int f = p.fast[l];
-    if (f == 2) epilogue_tile<NB, 2>(p, l, taddr, slot, outb, t, half, ngf);
-    else if (f == 1) epilogue_tile<NB, 1>(p, l, taddr, slot, outb, t, half, ngf);
-    else epilogue_tile<NB, 0>(p, l, taddr, slot, outb, t, half, ngf);
+    if (f == 2) epilogue_tile<NB, 2>(p, rows, l, taddr, slot, outb, t, half, ngf);
+    else if (f == 1) epilogue_tile<NB, 1>(p, rows, l, taddr, slot, outb, t, half, ngf);
+    else epilogue_tile<NB, 0>(p, rows, l, taddr, slot, outb, t, half, ngf);
 }
 
 }  // namespace
@@ -259,11 +287,16 @@ __global__ void __launch_bounds__(384, 1) k_mac_tc(const __grid_constant__ MacTc
 
     const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
     const int ntbuf = p.tbuf_stride ? 2 : 1;
+    // pair mode: CTA `rank` of cluster `cta0` handles row part `rank`; items are strided over the clusters
+    const uint32_t rank = p.pair ? cluster_ctarank() : 0u;
+    const int cta0 = p.pair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, ncta = p.pair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const uint8_t *Rimg = rank ? p.R2 : p.R;
+    const int cv_row0 = rank ? p.cv_row0_2 : p.cv_row0, rows = rank ? p.rows2 : p.rows;
 
     if (tid == 0) {
         for (int s = 0; s < p.SA; s++) {
             mbar_init(&a_full[s], 1);
-            mbar_init(&a_empty[s], 1);
+            mbar_init(&a_empty[s], p.pair ? 2 : 1);  // pair mode: a stage is free when BOTH CTAs' MMAs have read their copy of it
         }
         for (int s = 0; s < 2; s++) {
             mbar_init(&b_full[s], 1);
@@ -282,6 +315,7 @@ __global__ void __launch_bounds__(384, 1) k_mac_tc(const __grid_constant__ MacTc
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    if (p.pair) cluster_sync_all();  // the partner's mbarriers exist before anything is multicast to them
     const uint32_t tmem_base = *tmem_slot;
 
     const long long nitems = p.item_base[p.L];
@@ -292,7 +326,7 @@ __global__ void __launch_bounds__(384, 1) k_mac_tc(const __grid_constant__ MacTc
             uint32_t as = 0, aph = 0, bs = 0, bph = 0;
             // the diagonals are read exactly once (evict first); the rotated ciphertext image is re-read by every column tile
             const uint64_t pol_p = policy_evict_first(), pol_r = policy_evict_last();
-            for (long long item = blockIdx.x; item < nitems; item += gridDim.x) {
+            for (long long item = cta0; item < nitems; item += ncta) {
                 const Item it = decode_item(p, item);
                 const int nb = p.nb[it.l];
                 const uint32_t bbytes = (uint32_t)p.npad[it.l] * p.Kg;
@@ -302,7 +336,7 @@ __global__ void __launch_bounds__(384, 1) k_mac_tc(const __grid_constant__ MacTc
                     for (int g = 0; g < p.ngroups; g++) {  // every K group of this coefficient accumulates into the same TMEM tile
                         mbar_wait(&b_empty[bs], bph ^ 1u);
                         mbar_arrive_expect_tx(&b_full[bs], bbytes);
-                        bulk_g2s_hint(b_ring + (size_t)bs * p.bslot_bytes, p.R + g * p.r_gstride + p.rbase[it.l] + (long long)n * bbytes, bbytes,
+                        bulk_g2s_hint(b_ring + (size_t)bs * p.bslot_bytes, Rimg + g * p.r_gstride + p.rbase[it.l] + (long long)n * bbytes, bbytes,
                                       &b_full[bs], pol_r);
                         bs ^= 1u;
                         if (bs == 0) bph ^= 1u;
@@ -310,7 +344,13 @@ __global__ void __launch_bounds__(384, 1) k_mac_tc(const __grid_constant__ MacTc
                         for (int j = 0; j < nb; j++) {
                             mbar_wait(&a_empty[as], aph ^ 1u);
                             mbar_arrive_expect_tx(&a_full[as], (uint32_t)stage_bytes);
-                            bulk_g2s_hint(a_ring + (size_t)as * stage_bytes, src + (long long)j * stage_bytes, (uint32_t)stage_bytes, &a_full[as], pol_p);
+                            if (p.pair) {  // my half of the stage, to both CTAs (the partner sends the other half)
+                                const uint32_t hb = (uint32_t)stage_bytes >> 1;
+                                bulk_g2s_mc_hint(a_ring + (size_t)as * stage_bytes + rank * hb, src + (long long)j * stage_bytes + rank * hb, hb,
+                                                 &a_full[as], (uint16_t)3, pol_p);
+                            } else {
+                                bulk_g2s_hint(a_ring + (size_t)as * stage_bytes, src + (long long)j * stage_bytes, (uint32_t)stage_bytes, &a_full[as], pol_p);
+                            }
                             if (++as == (uint32_t)p.SA) {
                                 as = 0;
                                 aph ^= 1u;
@@ -326,7 +366,7 @@ __global__ void __launch_bounds__(384, 1) k_mac_tc(const __grid_constant__ MacTc
             uint32_t as = 0, aph = 0, bs = 0, bph = 0, tb = 0, tph = 0;
             const uint32_t zaddr = smem_u32(zblk);
             const int ksteps = p.Kg >> 5;
-            for (long long item = blockIdx.x; item < nitems; item += gridDim.x) {
+            for (long long item = cta0; item < nitems; item += ncta) {
                 const Item it = decode_item(p, item);
                 const int nb = p.nb[it.l], npad = p.npad[it.l];
                 const int region = (nb - 1) * p.RP + npad;
@@ -354,7 +394,8 @@ __global__ void __launch_bounds__(384, 1) k_mac_tc(const __grid_constant__ MacTc
                                 umma_i8(d_base + j * p.RP, umma_desc(aaddr + ks * 4096, 2048, 128),
                                         umma_desc(baddr + ks * npad * 32, npad * 16, 128), idesc, 1u);
                             }
-                            tc_commit(&a_empty[as]);
+                            if (p.pair) tc_commit_mc(&a_empty[as], (uint16_t)3);
+                            else tc_commit(&a_empty[as]);
                             if (++as == (uint32_t)p.SA) {
                                 as = 0;
                                 aph ^= 1u;
@@ -378,7 +419,7 @@ __global__ void __launch_bounds__(384, 1) k_mac_tc(const __grid_constant__ MacTc
         const uint32_t lane_base = (uint32_t)((wid & 3) * 32) << 16;
         uint32_t tb = 0, tph = 0;
         const size_t LN = (size_t)p.L * p.N;
-        for (long long item = blockIdx.x; item < nitems; item += gridDim.x) {
+        for (long long item = cta0; item < nitems; item += ncta) {
             const Item it = decode_item(p, item);
             const int l = it.l;
             const uint64_t q = p.lc[l].q;
@@ -396,12 +437,12 @@ __global__ void __launch_bounds__(384, 1) k_mac_tc(const __grid_constant__ MacTc
                     outb[t] = v[0];
                 } else {
                     switch (p.nb[l]) {  // uniform across the CTA
-                        case 1: epilogue_nb<1>(p, l, taddr, i % ngf, outb, t, half, ngf); break;
-                        case 2: epilogue_nb<2>(p, l, taddr, i % ngf, outb, t, half, ngf); break;
-                        case 3: epilogue_nb<3>(p, l, taddr, i % ngf, outb, t, half, ngf); break;
-                        case 4: epilogue_nb<4>(p, l, taddr, i % ngf, outb, t, half, ngf); break;
-                        case 5: epilogue_nb<5>(p, l, taddr, i % ngf, outb, t, half, ngf); break;
-                        default: epilogue_nb<6>(p, l, taddr, i % ngf, outb, t, half, ngf); break;
+                        case 1: epilogue_nb<1>(p, rows, l, taddr, i % ngf, outb, t, half, ngf); break;
+                        case 2: epilogue_nb<2>(p, rows, l, taddr, i % ngf, outb, t, half, ngf); break;
+                        case 3: epilogue_nb<3>(p, rows, l, taddr, i % ngf, outb, t, half, ngf); break;
+                        case 4: epilogue_nb<4>(p, rows, l, taddr, i % ngf, outb, t, half, ngf); break;
+                        case 5: epilogue_nb<5>(p, rows, l, taddr, i % ngf, outb, t, half, ngf); break;
+                        default: epilogue_nb<6>(p, rows, l, taddr, i % ngf, outb, t, half, ngf); break;
                     }
                 }
                 tc_fence_before();
@@ -414,8 +455,8 @@ __global__ void __launch_bounds__(384, 1) k_mac_tc(const __grid_constant__ MacTc
                     asm volatile("bar.sync 1, 256;\n" ::: "memory");
                     if (col >= p.col_lo && col < p.col_hi && !(p.dbg & 1)) {
                         const int n0 = it.n0 + (i + 1 - ngf);
-                        uint64_t *dst = p.cv + ((size_t)(col - p.col_lo) * p.cv_rows + p.cv_row0 + half) * LN + (size_t)l * p.N + n0;
-                        for (int row = half; row < p.rows; row += 2, dst += 2 * LN) {
+                        uint64_t *dst = p.cv + ((size_t)(col - p.col_lo) * p.cv_rows + cv_row0 + half) * LN + (size_t)l * p.N + n0;
+                        for (int row = half; row < rows; row += 2, dst += 2 * LN) {
                             if (narrow8) {
                                 // 8 consecutive coefficients of a 32-bit-class limb: widened to u64 and written as one 64-byte run
                                 const uint32_t *src = reinterpret_cast<const uint32_t *>(outb) + (size_t)row * 8 * 128 + t;
@@ -459,6 +500,7 @@ __global__ void __launch_bounds__(384, 1) k_mac_tc(const __grid_constant__ MacTc
     }
     tc_fence_before();
     __syncthreads();
+    if (p.pair) cluster_sync_all();  // the partner's last commits arrive on this CTA's mbarriers: do not leave before it is done too
     if (wid == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512));
@@ -611,10 +653,10 @@ int tc_geom_p(Ctx *c, int L, int K, int ncols, TcGeomP *g) {
     return 0;
 }
 
-int tc_geom_r(Ctx *c, const TcGeomP &gp, int rows, TcGeomR *g) {
+int tc_geom_r(Ctx *c, const TcGeomP &gp, int rows, TcGeomR *g, int rp_min) {
     memset(g, 0, sizeof *g);
     g->rows = rows;
-    g->RP = (rows + 3) / 4 * 4;
+    g->RP = std::max((rows + 3) / 4 * 4, rp_min);  // rp_min: the row pitch of the part this one is paired with (same image geometry)
     long long off = 0;
     int maxreg = 0;
     for (int l = 0; l < gp.L; l++) {
@@ -720,13 +762,17 @@ int tc_max_fused_groups(const TcGeomP &gp) {
 
 int launch_mac_tc(Ctx *c, const TcGeomP &gp, const TcGeomR &gr, const void *Pimg_group, long long p_gstride, int img_ntiles, int img_tile0,
                   const void *Rimg_group, long long r_gstride, int ngroups, int tile_lo, int tile_hi, int col_lo, int col_hi, bool accumulate,
-                  uint64_t *cv, cudaStream_t st) {
+                  uint64_t *cv, cudaStream_t st, const void *Rimg_group2, int cv_row0_2, int rows2) {
     if (tile_hi <= tile_lo || col_hi <= col_lo || ngroups < 1) return 0;
     if (ngroups > tc_max_fused_groups(gp)) SFG_FAIL(c, "tensor-core MAC: %d K groups exceed the s32 accumulator range", ngroups);
     const int Ktot = ngroups * gp.Kg;  // products summed per accumulator by this launch
     MacTcParams p{};
     p.P = (const uint8_t *)Pimg_group;
     p.R = (const uint8_t *)Rimg_group;
+    p.R2 = (const uint8_t *)Rimg_group2;
+    p.pair = Rimg_group2 ? 1 : 0;
+    p.cv_row0_2 = cv_row0_2;
+    p.rows2 = rows2;
     p.ngroups = ngroups;
     p.p_gstride = p_gstride;
     p.r_gstride = r_gstride;
@@ -802,8 +848,30 @@ int launch_mac_tc(Ctx *c, const TcGeomP &gp, const TcGeomR &gr, const void *Pimg
     int nsm = 0;
     SFG_CUDA(c, cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->device));
     const long long nitems = p.item_base[gp.L];
-    const int grid = (int)std::min<long long>(nsm, nitems);
-    k_mac_tc<<<grid, 384, smem, st>>>(p);
+    if (p.pair) {
+        // 2-CTA clusters, one CTA per SM: as many clusters as the device can hold at once (the kernel is persistent)
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)(nsm & ~1), 1, 1);
+        cfg.blockDim = dim3(384, 1, 1);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        int nclusters = 0;
+        SFG_CUDA(c, cudaOccupancyMaxActiveClusters(&nclusters, k_mac_tc, &cfg));
+        if (nclusters < 1) SFG_FAIL(c, "tensor-core MAC: no 2-CTA cluster fits the device");
+        const int grid = 2 * (int)std::min<long long>(std::min(nclusters, nsm / 2), nitems);
+        cfg.gridDim = dim3((unsigned)grid, 1, 1);
+        SFG_CUDA(c, cudaLaunchKernelEx(&cfg, k_mac_tc, p));
+    } else {
+        const int grid = (int)std::min<long long>(nsm, nitems);
+        k_mac_tc<<<grid, 384, smem, st>>>(p);
+    }
     SFG_LAUNCHED(c, "k_mac_tc", st);
     return 0;
 }

@@ -507,7 +507,8 @@ static int run_mac(Ctx *c, const Cache *ca, const void *R, const std::vector<int
     std::vector<MacPart> parts(ranges.size());
     size_t rimg_total = 0, tab_total = 0;
     for (size_t pi = 0; pi < ranges.size(); pi++) {
-        if (tc_geom_r(c, tc, ranges[pi].second, &parts[pi].gr)) return -1;
+        // a second part takes the first one's row pitch: identical image geometry, so that the two can share the P stream (pair mode)
+        if (tc_geom_r(c, tc, ranges[pi].second, &parts[pi].gr, pi ? parts[0].gr.RP : 0)) return -1;
         parts[pi].gr.cv_rows = rows_all;
         parts[pi].gr.cv_row0 = ranges[pi].first;
         rimg_total += (size_t)parts[pi].gr.group_bytes * tc.ngroups;
@@ -550,12 +551,25 @@ static int run_mac(Ctx *c, const Cache *ca, const void *R, const std::vector<int
     // pimg holds the K groups [g_lo, g_hi) of some tiles; the first group of the whole K range overwrites cv, the others add into it
     auto mac = [&](const unsigned char *pimg, long long p_gstride, int img_ntiles, int img_tile0, int t0, int t1, int g_lo, int g_hi) -> int {
         if (g_tm) g_tm->mark(3);  // the MAC kernel alone, on the stream it is launched on (bench.py roofline)
-        for (const MacPart &pt : parts)
+        // Two row parts with the same image geometry (kp = 9 .. 16 with 5-6 byte planes: the 2 kp rows do not fit TMEM twice) can run as
+        // ONE launch of 2-CTA clusters that share the P stream by multicast (pair mode, SFG_TC_PAIR=1) instead of two launches that each
+        // read the whole image.  Bit-identical (test_pair_mode_shares_the_p_stream_bit_exact) and half the HBM traffic, but measured
+        // NEUTRAL at logN 14 / kp = 15 (26.9 vs 26.8 ms, profiles/r2/mac14_pair_mode_probe.txt): the kernel is not HBM-bound there -- the
+        // u64 epilogue of the two parts takes as long as the two passes over P, and the lock-stepped 4-stage ring of a pair tops out at
+        // 20 ms without any epilogue.  Off by default until the epilogue gets more warps.
+        const char *pe = getenv("SFG_TC_PAIR");
+        bool pair = pe && *pe == '1' && parts.size() == 2 && parts[0].gr.RP == parts[1].gr.RP && parts[0].gr.group_bytes == parts[1].gr.group_bytes &&
+                    parts[0].gr.tbuf_stride == parts[1].gr.tbuf_stride;
+        for (int l = 0; pair && l < tc.L; l++) pair = parts[0].gr.npad[l] == parts[1].gr.npad[l] && parts[0].gr.rbase[l] == parts[1].gr.rbase[l];
+        for (size_t pi = 0; pi < parts.size(); pi += pair ? 2 : 1) {
+            const MacPart &pt = parts[pi];
             for (int grp = g_lo; grp < g_hi; grp += gf)
                 if (launch_mac_tc(c, tc, pt.gr, pimg + (size_t)(grp - g_lo) * p_gstride, p_gstride, img_ntiles, img_tile0,
                                   pt.rimg + (size_t)grp * pt.gr.group_bytes, pt.gr.group_bytes, std::min(gf, g_hi - grp), t0, t1, col_lo, col_hi,
-                                  grp > 0, d_cv, c->stream))
+                                  grp > 0, d_cv, c->stream, pair ? parts[1].rimg + (size_t)grp * parts[1].gr.group_bytes : nullptr,
+                                  pair ? parts[1].gr.cv_row0 : 0, pair ? parts[1].gr.rows : 0))
                     return -1;
+        }
         if (g_tm) g_tm->mark(1);
         return 0;
     };

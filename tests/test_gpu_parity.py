@@ -365,6 +365,45 @@ def test_pn14_shape_bit_exact(small14, s):
     assert (out == want).all()
 
 
+@pytest.mark.parametrize("s", [9, 13, 15, 16])
+def test_pair_mode_shares_the_p_stream_bit_exact(small14, s, monkeypatch):
+    """kp = 13 .. 16 at the logN-14 limb widths: the 2 kp rows do not fit TMEM twice, so the MAC runs as two row parts, by default as two
+    launches.  SFG_TC_PAIR=1 runs them as ONE launch of 2-CTA clusters (each CTA fetches half of every P stage and multicasts it to
+    both: P leaves HBM once).  Same bits, several column tiles per cluster, resident cache and on-the-fly diagonals; kp = 9 (one part)
+    must not be affected by the switch."""
+    from sfgwas_b200 import GenoFileStream, MatMult4StreamCompute, MatMult4StreamPreprocess
+
+    o, cps, sk, keys = small14
+    rng = np.random.default_rng(140 + s)
+    nr, nc = 2 * o.slots + 11, 13 * o.slots + 5  # 3 block rows; 14 block columns x d giants > 128 columns: more than one column tile
+    X = rng.integers(0, 3, (nr, nc)).astype(np.int8)
+    A = enc_matrix(o, sk, rng.normal(size=(s, nr)))
+    gfs = GenoFileStream.from_matrix(cps, X)
+    cache = MatMult4StreamPreprocess(cps, gfs, 5)
+    two_launches = MatMult4StreamCompute(cps, A, 5, cache)
+    launches0 = cps.launch_count()
+    monkeypatch.setenv("SFG_TC_PAIR", "1")
+    paired = MatMult4StreamCompute(cps, A, 5, cache)
+    launches_paired = cps.launch_count() - launches0
+    cps.set_cache_budget(1)
+    otf = MatMult4StreamPreprocess(cps, gfs, 5)
+    cps.set_cache_budget(0)
+    assert not otf.materialised
+    paired_otf = MatMult4StreamCompute(cps, A, 5, otf)
+    monkeypatch.delenv("SFG_TC_PAIR")
+    launches0 = cps.launch_count()
+    MatMult4StreamCompute(cps, A, 5, cache)
+    launches_two = cps.launch_count() - launches0
+    assert (paired == two_launches).all()
+    assert (paired_otf == two_launches).all()
+    assert (launches_paired < launches_two) if s >= 13 else (launches_paired == launches_two)  # one MAC launch instead of two when the rows are split
+    if s == 15:
+        dc = o.preprocess(X, 5, nproc=1)
+        want = o.compute(A, dc, keys, 5, nproc=1)
+        o.cache_free(dc)
+        assert (paired == want).all()
+
+
 @pytest.mark.parametrize("nc", [140, 144])  # 144: the 16-byte genotype scan (ncols % 16 == 0); 140: the byte-wise one
 def test_matmult4_stream_fused(small13, nc):
     from sfgwas_b200 import GenoFileStream, MatMult4Stream
