@@ -122,6 +122,51 @@ def mod_reduce_scatter_(t, share: int, cps: CryptoParams = None, nl: int = 0, gr
     return mine
 
 
+def _compute_shared_baby_steps(cps: CryptoParams, cache: DiagCache, d_A, d_out, s: int, nbr: int, level_a: int, max_level: int, rank: int,
+                               world: int, holder: dict, group=None, check_chunks: bool = False):
+    """MatMult4StreamCompute over this rank's `cache` with the baby-step rotations shared between the ranks: every rank rotates 1/world
+    of the (block row, baby step) entries (``sfg_matmult4_baby_dev``), ONE all-gather over NVLink completes the rotation cache, then MAC +
+    giant-step sums run on it (``sfg_matmult4_stream_compute_r_dev``).  Falls back to the plain device call when there is nothing to share
+    (world == 1, s > 16).  `holder` keeps the gathered buffer between calls; returns the library's phase timings of the call."""
+    import torch
+    import torch.distributed as dist
+
+    L = cps.L
+    ph = dict(baby_ms=0.0, mac_ms=0.0, giant_ms=0.0, mac_kernel_ms=0.0)
+
+    def add_timings():
+        t = cps.last_timings()
+        for k in ph:
+            ph[k] += t[k]
+
+    # the library's stream is non-blocking: whatever torch still has in flight for d_A / d_out (fills, copies) must be done first
+    torch.cuda.current_stream().synchronize()
+    if world > 1 and s <= 16:
+        chunk = int(L.sfg_matmult4_baby_chunk_bytes(cps.h, cache.h, s, world))
+        R = holder.get("R")
+        if R is None or R.numel() != world * chunk:
+            if check_chunks:  # caches built from different columns must still see the same baby steps
+                cmm = torch.tensor([chunk, -chunk], device=d_A.device)
+                dist.all_reduce(cmm, op=dist.ReduceOp.MAX, group=group)
+                if int(cmm[0]) != chunk or -int(cmm[1]) != chunk:
+                    raise SfgError("ranks disagree on the rotation-cache share (a rank without a full-width block column?)")
+            R = holder["R"] = torch.empty(world * chunk, dtype=torch.uint8, device=d_A.device)
+        cps._check(L.sfg_matmult4_baby_dev(cps.h, C.c_void_p(d_A.data_ptr()), s, nbr, level_a, max_level, cache.h, rank, world,
+                                           C.c_void_p(R.data_ptr())), "sfg_matmult4_baby_dev")
+        add_timings()
+        mine = R[rank * chunk:(rank + 1) * chunk].clone()
+        dist.all_gather_into_tensor(R, mine, group=group)
+        torch.cuda.current_stream().synchronize()
+        cps._check(L.sfg_matmult4_stream_compute_r_dev(cps.h, C.c_void_p(R.data_ptr()), s, max_level, cache.h, C.c_void_p(d_out.data_ptr())),
+                   "sfg_matmult4_stream_compute_r_dev")
+        add_timings()
+    else:
+        cps._check(L.sfg_matmult4_stream_compute_dev(cps.h, C.c_void_p(d_A.data_ptr()), s, nbr, level_a, max_level, cache.h,
+                                                     C.c_void_p(d_out.data_ptr())), "sfg_matmult4_stream_compute_dev")
+        add_timings()
+    return ph
+
+
 class GiantSharded:
     """Strong scaling of ONE MatMult4StreamCompute over the GPUs of a box: rank `rank` of `world` holds the diagonals of its share of the
     giant steps and produces the partial sum over them; ``compute`` all-reduces the partial outputs mod q (device-resident throughout).
@@ -135,40 +180,14 @@ class GiantSharded:
         cps._check(cps.L.sfg_matmult4_stream_preprocess_giants(cps.h, gfs.h, max_level, rank, world, C.byref(h)),
                    "sfg_matmult4_stream_preprocess_giants")
         self.cache = DiagCache(cps, h)
-        self._R = None
+        self._hold = {}
         self.phases_ms = dict(baby_ms=0.0, mac_ms=0.0, giant_ms=0.0, mac_kernel_ms=0.0)  # of the last compute_dev
 
     def compute_dev(self, d_A, d_out, s: int, nbr: int, level_a: int, group=None):
         """d_A [s][nbr][2][level_a+1][N], d_out [s][m_ct][2][max_level][N]: int64 CUDA tensors; d_out = the FULL product on every rank."""
-        import torch
-        import torch.distributed as dist
-
-        cps, L = self.cps, self.cps.L
-        ph = dict(baby_ms=0.0, mac_ms=0.0, giant_ms=0.0, mac_kernel_ms=0.0)
-
-        def add_timings():
-            t = cps.last_timings()
-            for k in ph:
-                ph[k] += t[k]
-
-        if self.shard_baby and s <= 16:
-            chunk = int(L.sfg_matmult4_baby_chunk_bytes(cps.h, self.cache.h, s, self.world))
-            if self._R is None or self._R.numel() != self.world * chunk:
-                self._R = torch.empty(self.world * chunk, dtype=torch.uint8, device=d_A.device)
-            R = self._R
-            cps._check(L.sfg_matmult4_baby_dev(cps.h, C.c_void_p(d_A.data_ptr()), s, nbr, level_a, self.max_level, self.cache.h, self.rank,
-                                               self.world, C.c_void_p(R.data_ptr())), "sfg_matmult4_baby_dev")
-            add_timings()
-            mine = R[self.rank * chunk:(self.rank + 1) * chunk].clone()
-            dist.all_gather_into_tensor(R, mine, group=group)
-            torch.cuda.current_stream().synchronize()
-            cps._check(L.sfg_matmult4_stream_compute_r_dev(cps.h, C.c_void_p(R.data_ptr()), s, self.max_level, self.cache.h,
-                                                           C.c_void_p(d_out.data_ptr())), "sfg_matmult4_stream_compute_r_dev")
-            add_timings()
-        else:
-            cps._check(L.sfg_matmult4_stream_compute_dev(cps.h, C.c_void_p(d_A.data_ptr()), s, nbr, level_a, self.max_level, self.cache.h,
-                                                         C.c_void_p(d_out.data_ptr())), "sfg_matmult4_stream_compute_dev")
-            add_timings()
+        cps = self.cps
+        ph = _compute_shared_baby_steps(cps, self.cache, d_A, d_out, s, nbr, level_a, self.max_level, self.rank,
+                                        self.world if self.shard_baby else 1, self._hold, group)
         if self.world > 1:
             ct_mod_allreduce_(d_out, cps, self.max_level, group)
         self.phases_ms = ph
@@ -199,6 +218,7 @@ class ColumnSharded:
         if hi > lo and X_local_cols.shape[1] != want:
             raise SfgError("rank %d owns %d columns, got %d" % (rank, want, X_local_cols.shape[1]))
         self.empty = hi <= lo
+        self._hold = {}
         if not self.empty:
             self.gfs = GenoFileStream.from_matrix(cps, X_local_cols)
             self.cache = MatMult4StreamPreprocess(cps, self.gfs, max_level)
@@ -214,6 +234,17 @@ class ColumnSharded:
         if self.empty:
             return np.zeros((A.shape[0], 0, 2, self.max_level, self.cps.N), dtype=np.uint64)
         return MatMult4StreamCompute(self.cps, A, self.max_level, self.cache)
+
+    def compute_dev(self, d_A, d_out, s: int, nbr: int, level_a: int, group=None, share_baby: bool = True):
+        """Device-resident: d_A [s][nbr][2][level_a+1][N] (the same A on every rank), d_out [s][hi-lo][2][max_level][N] = this rank's block
+        columns of the product.  With ``share_baby`` the baby-step rotations -- identical on every rank -- are split 1/world per rank and
+        completed by ONE all-gather (the layout the full-size config-4 run uses: bench.py --col-sharding); every rank must then own at
+        least one full-width block column so that all caches see the same baby steps (checked)."""
+        if self.empty:
+            raise SfgError("rank %d owns no block column" % self.rank)
+        self.phases_ms = _compute_shared_baby_steps(self.cps, self.cache, d_A, d_out, s, nbr, level_a, self.max_level, self.rank,
+                                                    self.world if share_baby else 1, self._hold, group, check_chunks=True)
+        return d_out
 
     def gather(self, out_local: np.ndarray, group=None) -> np.ndarray:
         """All ranks get the full [s][m_ct][2][maxLevel][N] output (all-gather of equal-sized padded pieces)."""

@@ -117,6 +117,14 @@ def _gpu_worker(rank, world, port, q):
         c0, c1 = ColumnSharded.local_columns(nc, o.slots, rank, world)
         cs = ColumnSharded(cps, X[:, c0:c1], nc, rank, world)
         col_ok = bool((cs.gather(cs.compute(A)) == single).all())
+        # device-resident, baby-step rotations shared between the ranks (the layout of the full-size config-4 run)
+        dev = torch.device("cuda", rank)
+        lo, hi = cs.ranges[rank]
+        d_A = torch.from_numpy(A.view(np.int64)).to(dev)
+        for share in (True, False):
+            d_out = torch.zeros((s, hi - lo, 2, 5, o.N), dtype=torch.int64, device=dev)
+            cs.compute_dev(d_A, d_out, s, nbr, 5, share_baby=share)
+            col_ok = col_ok and bool((d_out.cpu().numpy().view(np.uint64) == single[:, lo:hi]).all())
         rs = RowSharded(cps, X, rank, world)
         row_ok = bool((rs.compute(A) == single).all())
         gs = GiantSharded(cps, GenoFileStream.from_matrix(cps, X), rank, world)
