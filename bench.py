@@ -287,6 +287,33 @@ def run_reference(args, rank, world):
 
 # ------------------------------------------------------------------------------------------------------------------
 def run_ours(args, rank, local_rank, world):
+    """Our arm.  The measurement itself is _run_ours(); this wrapper owns the teardown ORDER: torch's current stream is the library's
+    stream during the run, so every tensor has to be released (the frame of _run_ours is gone) and torch given its own stream back
+    BEFORE the library context -- and with it that stream -- is destroyed.  (Freeing a tensor that NCCL has touched queries the current
+    stream; with the stream already destroyed every rank of an N > 1 run aborted at exit with "CUDA error: context is destroyed" after
+    the JSON line was out -- a non-zero exit code under torchrun.)"""
+    import gc
+
+    import torch
+    import torch.distributed as dist
+
+    keep = {}
+    try:
+        _run_ours(args, rank, local_rank, world, keep)
+    finally:
+        try:
+            torch.cuda.synchronize()
+            torch.cuda.set_stream(torch.cuda.default_stream(torch.device("cuda", local_rank)))
+        except Exception:
+            pass
+        gc.collect()
+        if world > 1 and dist.is_initialized():
+            dist.destroy_process_group()
+        if keep.get("cps") is not None:
+            keep["cps"].close()
+
+
+def _run_ours(args, rank, local_rank, world, keep):
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -303,7 +330,7 @@ def run_ours(args, rank, local_rank, world):
     P = CKKS[pname]
     wf = work_figures(nrows, ncols, s, P["logN"])
     N, slots, d, nbr, m_ct = wf["N"], wf["slots"], wf["d"], wf["nbr"], wf["m_ct"]
-    cps = CryptoParams(P["logN"], P["Q"], P["P"], P["scale"], device=local_rank)
+    cps = keep["cps"] = CryptoParams(P["logN"], P["Q"], P["P"], P["scale"], device=local_rank)
     L = cps.L
     mods = P["Q"] + P["P"]
     # The library's stream is NON-BLOCKING: it is not ordered after torch's default stream.  Everything torch produces for the library
@@ -598,9 +625,6 @@ def run_ours(args, rank, local_rank, world):
         print(json.dumps(line), flush=True)
     L.sfg_cache_destroy(cache)
     L.sfg_geno_destroy(g)
-    cps.close()
-    if world > 1:
-        dist.destroy_process_group()
 
 
 def main():
