@@ -56,3 +56,34 @@ def test_roofline_traffic_comes_from_the_committed_capture():
     traffic, src = bench.read_traffic()
     assert traffic and 5e10 < traffic < 9e10, (traffic, src)  # dram read + write of one k_mac_tc launch of config 2: ~66.5 GB
     assert "profiles/r2" in src
+
+
+def test_run_ours_teardown_closes_the_context_last(monkeypatch):
+    """The wrapper around the measurement owns the teardown order (tensors, torch's current stream, process group, THEN the library
+    context).  Without a GPU the measurement is replaced by a stub: the context must be closed exactly once, after the stub returned or
+    raised, and an exception of the measurement must propagate."""
+    import pytest
+
+    events = []
+
+    class FakeCtx:
+        def close(self):
+            events.append("close")
+
+    def fake_run(args, rank, local_rank, world, keep):
+        keep["cps"] = FakeCtx()
+        events.append("run")
+
+    monkeypatch.setattr(bench, "_run_ours", fake_run)
+    bench.run_ours(None, 0, 0, 1)
+    assert events == ["run", "close"]
+
+    def failing_run(args, rank, local_rank, world, keep):
+        keep["cps"] = FakeCtx()
+        raise RuntimeError("measurement failed")
+
+    events.clear()
+    monkeypatch.setattr(bench, "_run_ours", failing_run)
+    with pytest.raises(RuntimeError):
+        bench.run_ours(None, 0, 0, 1)
+    assert events == ["close"]
